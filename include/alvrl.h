@@ -1,0 +1,185 @@
+/*
+ * alvrl.h -- C ABI of the B200-native Adaptive-LightSlice VRL hot path (libalvrl.so).
+ *
+ * This is the drop-in boundary a Mitsuba `integrator type="vrl"` plugin binds instead of
+ * running the reference's CPU loops.  Every entry point names the reference code it replaces
+ * (paths relative to the reference tree, neodyme06/mitsuba-ALVRL).  Plain pointers and sizes
+ * only; no C++ types, no exceptions; every function returns ALVRL_OK (0) or a negative error
+ * code and leaves a message in alvrl_last_error().  Host buffers belong to the caller and are
+ * copied during the call; device memory belongs to the library.  One handle drives one GPU and
+ * is not thread-safe.  There is no CPU fallback: without a usable CUDA device alvrl_create fails.
+ *
+ * Pixel indexing follows the reference's `m_slices[y + H*x]` (vrlIntegrator.cpp:560,
+ * Preprocessor.cpp:1140-1146): "pixel index" below always means  y + H*x  (x-major).
+ */
+#ifndef ALVRL_H
+#define ALVRL_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ALVRL_OK              0
+#define ALVRL_ERR_ARG        -1   /* invalid argument / parameter (the reference Log(EError)s) */
+#define ALVRL_ERR_STATE      -2   /* call order violated (e.g. build_R before build_slices)      */
+#define ALVRL_ERR_CUDA       -3   /* CUDA runtime failure                                         */
+#define ALVRL_ERR_IO         -4   /* file could not be read                                       */
+#define ALVRL_ERR_UNSUPPORTED -5  /* scene feature outside the hot path          */
+
+#define ALVRL_NO_SLICE 0xffffffffu      /* UINT32_T_MAX slice id, Preprocessor.cpp:1201 */
+#define ALVRL_NO_HIT   0xffffffffu
+
+/* BSDF type bits the path needs (include/mitsuba/render/bsdf.h:230-284) */
+#define ALVRL_BSDF_SMOOTH 1u            /* diffuse reflectance: ESmooth */
+
+#define ALVRL_PHASE_ISOTROPIC 0         /* src/phase/isotropic.cpp:76-78 */
+#define ALVRL_PHASE_HG        1         /* src/phase/hg.cpp:107-110      */
+
+#define ALVRL_RNG_MODE_COUNTER 0        /* include/alvrl_rng.h                                        */
+#define ALVRL_RNG_MODE_SFMT    1        /* reference stream: one SFMT-19937 sampler, workerCount = 1  */
+
+/*
+ * XML parameters of the reference plugin (vrlIntegrator.cpp:128-208, same names and defaults),
+ * the inherited ones the path reads, and a few implementation knobs that have no XML equivalent.
+ */
+typedef struct alvrl_params {
+    int32_t shortVrls;                  /* true  */
+    int32_t vrlTargetNum;               /* 500  (tracer only; kept for the plugin interface) */
+    int32_t maxParticleDepth;           /* -1   (tracer only) */
+    int32_t specularForcedRRdepth;      /* 100  (specular chains; host side) */
+    float   initialSpecularThroughput;  /* 20 */
+    int32_t volVolSamples;              /* 2, must be 0 or >= 2 */
+    int32_t volSurfSamples;             /* 2, must be 0 or >= 2 */
+    int32_t globalCluster;              /* false */
+    float   globalUndersampling;        /* -1 */
+    int32_t localRefinement;            /* true */
+    float   localUndersampling;         /* -1 */
+    float   fallBackUndersampling;      /* 5 */
+    int32_t targetNumSlices;            /* 100 */
+    float   targetPixelUndersampling;   /* 64 */
+    float   sliceCurvatureFactor;       /* 0.5 */
+    int32_t neighbourCount;             /* 0 */
+    float   neighbourWeight;            /* 0 */
+    int32_t Rsamples;                   /* 1 */
+    float   depthCorrection;            /* 1 */
+    int32_t numVrlFalseColor;           /* false */
+    int32_t slicesFalseColor;           /* false */
+    int32_t convergenceFalseColor;      /* false */
+    int32_t maxPasses;                  /* 1 (src/librender/integrator.cpp:348) */
+    /* ---- implementation knobs ---- */
+    int32_t rngMode;                    /* ALVRL_RNG_MODE_COUNTER */
+    uint64_t seed;                      /* 0 */
+    int32_t anyHitShadowRays;           /* 1: shadow rays stop at the first occluder (same T as closest hit
+                                           in scenes without ENull surfaces, scene.cpp:634-642) */
+    int32_t workerCount;                /* 1: emulated Scheduler::getWorkerCount() -- decides how the SFMT
+                                           sampler is cloned over contiguous slice ranges
+                                           (vrlIntegrator.cpp:305-321,1048-1051; Preprocessor.cpp:738-741) */
+    int32_t reserved[6];
+} alvrl_params;
+
+typedef struct alvrl_ctx *alvrl_handle;
+
+typedef struct alvrl_stats {
+    uint64_t pairsPreprocess;   /* "Number of integrated VRLs during preprocessing", vrlIntegrator.cpp:119 */
+    uint64_t pairsRender;       /* "Number of integrated VRLs during rendering",     vrlIntegrator.cpp:121 */
+    uint64_t shadowRays;
+    float msSlices, msSliceMapping, msBuildR, msClusters, msRender;   /* device/host phase timers */
+    float msTransportKernelR, msTransportKernelRender;                /* CUDA-event time of the kernels */
+    uint32_t kernelLaunches;    /* kernels launched by this handle since creation */
+    uint32_t numSlices, numRows, numVrls, bvhNodes;
+} alvrl_stats;
+
+/* ---- life cycle -------------------------------------------------------------------------- */
+void alvrl_params_default(alvrl_params *p);                   /* vrlIntegrator.cpp:128-208 defaults */
+/* CreateInstance(props) -> new vrlIntegrator(props), vrlIntegrator.cpp:128,1127 */
+int  alvrl_create(int cuda_device, const alvrl_params *p, alvrl_handle *out);
+void alvrl_destroy(alvrl_handle h);
+const char *alvrl_last_error(void);
+int  alvrl_get_params(alvrl_handle h, alvrl_params *out);
+
+/* ---- scene upload (what the plugin marshals out of `const Scene *`) -------------------- */
+/* Triangle soup + per-triangle material; replaces ShapeKDTree's TriAccel array
+ * (include/mitsuba/render/triaccel.h:61-95, src/librender/skdtree.cpp:60-104) with a device BVH. */
+int alvrl_set_mesh(alvrl_handle h, const float *verts_xyz, uint32_t nverts,
+                   const uint32_t *tris, uint32_t ntris, const uint32_t *tri_material);
+/* Diffuse reflectance + type bits per material (src/bsdfs/diffuse.cpp:110-118). */
+int alvrl_set_materials(alvrl_handle h, const float *albedo_rgb, const uint32_t *type_bits, uint32_t nmat);
+/* Extra points to union into Scene::getAABB() (sensor/emitter boxes, scene.cpp:387-413). */
+int alvrl_set_extra_bounds(alvrl_handle h, const float *points_xyz, uint32_t npoints);
+/* HomogeneousMedium (src/medium/homogeneous.cpp:156-184,354-396); samplingWeight < 0 => reference default. */
+int alvrl_set_medium_homogeneous(alvrl_handle h, const float sigmaA[3], const float sigmaS[3],
+                                 float mediumSamplingWeight, int32_t phaseType, float g);
+/* HeterogeneousMedium, method=simpson, over a float32 grid (src/medium/heterogeneous.cpp:301-376,665-691;
+ * src/volume/gridvolume.cpp:188-215,337-388).  sigmaS_base is Medium::getSigmaS() (quirk B2). */
+int alvrl_set_medium_grid(alvrl_handle h, const float *density, const int32_t res[3],
+                          const float bbox_min[3], const float bbox_max[3], float scale,
+                          const float albedo[3], const float sigmaS_base[3],
+                          int32_t phaseType, float g);
+/* PerspectiveCamera (src/sensors/perspective.cpp:126-175,247-269): row-major 4x4 matrices. */
+int alvrl_set_camera(alvrl_handle h, const float sampleToCamera[16], const float cameraToWorld[16],
+                     uint32_t width, uint32_t height, float nearClip, float farClip);
+/* vrlVector (src/integrators/vrl/VRL.h:105-194); zero-power / zero-length VRLs are dropped like put()
+ * (VRL.h:148-158).  particleCount == 0 => number of kept VRLs (VRL.h:128). */
+int alvrl_set_vrls(alvrl_handle h, const float *start_xyz, const float *end_xyz, const float *power_rgb,
+                   uint32_t n, uint64_t particleCount);
+/* ASCII VRL file, 9 floats per line (VRL.h:43-54,120-128; vrlIntegrator.cpp:243-252). */
+int alvrl_load_vrl_file(alvrl_handle h, const char *path);
+/* Parity mode for build_R: u(row, vrl, k) = tape[(row*N + vrl)*(2*Nvv+Nvs) + k]. NULL clears. */
+int alvrl_set_sample_tape(alvrl_handle h, const float *tape, uint64_t n);
+
+/* ---- the path ------------------------------------------------------------------------------- */
+/* vrlIntegrator::preprocess -> Preprocessor::buildSlices (Preprocessor.cpp:1130-1227,1349-1418). */
+int alvrl_build_slices(alvrl_handle h);
+/* Same, from caller-supplied gather points (P x 3 position, P x 3 scaled normal; NaN = miss). */
+int alvrl_build_slices_from_gather(alvrl_handle h, const float *pos_xyz, const float *dir_xyz);
+/* Preprocessor::sampleSliceMapping (Preprocessor.cpp:66-121,1502-1525). */
+int alvrl_sample_slice_mapping(alvrl_handle h);
+/* "Building R": prepass loops + Rbuilder + getLiLuminanceVrlContributions + getVRLContributions
+ * (vrlIntegrator.cpp:302-337,527-539,792-825,1038-1083). */
+int alvrl_build_R(alvrl_handle h);
+/* Preprocessor::buildClusters (Preprocessor.cpp:133-283). */
+int alvrl_build_clusters(alvrl_handle h);
+/* vrlIntegrator::prepass = the three calls above (vrlIntegrator.cpp:270-356). */
+int alvrl_prepass(alvrl_handle h);
+/* Render pass: Li -> getClusteredVrlContributions for every pixel centre (vrlIntegrator.cpp:386-393,
+ * 542-599; src/librender/integrator.cpp:232-264 with spp == 1, rfilter = box).
+ * rgb: W*H*3 floats, row-major image order [y][x][c]. */
+int alvrl_render(alvrl_handle h, float *rgb_host);
+/* Unclustered render (globalCluster = localRefinement = false): getVRLContributions over all VRLs. */
+int alvrl_render_unclustered(alvrl_handle h, float *rgb_host);
+/* Device variants for multi-GPU: only slices [sliceBegin, sliceEnd) are processed; the
+ * framebuffer (W*H*4 floats, zero-initialised by the caller) lives in caller-owned device memory. */
+int alvrl_set_slice_range(alvrl_handle h, uint32_t sliceBegin, uint32_t sliceEnd);
+int alvrl_render_device(alvrl_handle h, void *rgba_device, void *cuda_stream);
+
+/* ---- results / introspection (tests, multi-GPU exchange) -------------------------------- */
+int alvrl_get_stats(alvrl_handle h, alvrl_stats *out);
+int alvrl_get_num_vrls(alvrl_handle h, uint32_t *n);          /* vrlVector::size() after the put() filter */
+int alvrl_get_primary_hits(alvrl_handle h, uint32_t *prim /*P*/, float *t /*P*/, float *p_xyz /*3P*/, float *n_xyz /*3P*/);
+int alvrl_get_pixel_to_slice(alvrl_handle h, uint32_t *out /*P*/);
+int alvrl_get_num_slices(alvrl_handle h, uint32_t *nslices, uint32_t *nrows);
+int alvrl_get_rep_pixels(alvrl_handle h, uint32_t *sliceRowOffset /*S+1*/, uint32_t *rowPixel /*G*/);
+int alvrl_set_rep_pixels(alvrl_handle h, const uint32_t *sliceRowOffset, const uint32_t *rowPixel, uint32_t nslices);
+int alvrl_get_R(alvrl_handle h, uint32_t rowBegin, uint32_t rowEnd, float *mean_var /*(rows*N*2)*/);
+int alvrl_set_R(alvrl_handle h, const float *mean_var /*(G*N*2)*/);
+int alvrl_get_cluster_counts(alvrl_handle h, uint32_t *sliceOffset /*S+1*/, uint32_t *nGlobal, uint32_t *nFallback);
+int alvrl_get_clusters(alvrl_handle h, uint32_t *vrls, float *weights,
+                       uint32_t *globalVrls, float *globalWeights,
+                       uint32_t *fallbackVrls, float *fallbackWeights);
+int alvrl_set_clusters(alvrl_handle h, const uint32_t *sliceOffset, uint32_t nslices,
+                       const uint32_t *vrls, const float *weights,
+                       const uint32_t *fallbackVrls, const float *fallbackWeights, uint32_t nFallback);
+/* Closest-hit query through the device BVH with ShapeKDTree::rayIntersect semantics
+ * (skdtree.cpp:112-204): prim = triangle index or ALVRL_NO_HIT. */
+int alvrl_trace_rays(alvrl_handle h, const float *o_xyz, const float *d_xyz, const float *mint,
+                     const float *maxt, uint32_t n, uint32_t *prim, float *t);
+/* Scene::evalTransmittance (scene.cpp:619-679) for n point pairs. */
+int alvrl_eval_transmittance(alvrl_handle h, const float *p1_xyz, const int32_t *p1OnSurface,
+                             const float *p2_xyz, uint32_t n, float *T_rgb);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALVRL_H */

@@ -1,0 +1,647 @@
+/*
+ * oracle_capi.cpp -- TEST INFRASTRUCTURE ONLY (see oracle_core.hpp).
+ *
+ * extern "C" surface of the CPU oracle: the orc_* functions mirror the alvrl_* entry points of
+ * include/alvrl.h one to one (same arguments, same meaning) so that parity tests drive both
+ * sides with the same script.  The top-level flow restates vrlIntegrator::preprocess / prepass /
+ * Li (src/integrators/vrl/vrlIntegrator.cpp:237-356,386-599) and Preprocessor::buildSlices /
+ * sampleSliceMapping / buildClusters (Preprocessor.cpp:133-283,1130-1193,1502-1525).
+ */
+#include "oracle_prep.hpp"
+#include <thread>
+#include <memory>
+#include <chrono>
+#include <cstdio>
+
+using namespace orc;
+
+namespace {
+
+thread_local std::string g_err;
+
+struct Ctx {
+    alvrl_params P;
+    Scene scene; Medium medium; Camera cam;
+    bool haveMesh = false, haveMat = false, haveMedium = false, haveCam = false, haveVrls = false;
+    std::vector<VRL> vrls; uint64_t particleCount = 0;
+    std::vector<Ray> rays; std::vector<Intersection> hits;       // per pixel index y + H*x
+    bool havePrimary = false;
+    std::vector<uint32_t> pixelToSlice; std::vector<SliceData> slices; bool haveSlices = false;
+    std::vector<uint32_t> rowOffset, rowPixel; bool haveRows = false;
+    std::vector<Float> sliceUndersampling; Float globalPixelUndersampling = -1;
+    std::vector<VrlContribution> R; bool haveR = false;
+    std::vector<std::vector<uint32_t>> selectedVrls; std::vector<std::vector<Float>> clusterWeight;
+    std::vector<uint32_t> gcVrls, fallBackVrls; std::vector<Float> gcWeight, fallBackWeight; bool haveClusters = false;
+    std::unique_ptr<Sampler> mainSampler;
+    const float *tape = nullptr; uint64_t tapeLen = 0; std::vector<float> tapeStore;
+    int threads = 1;
+    bool noVisibility = false;
+    uint32_t sliceBegin = 0, sliceEnd = 0xffffffffu;
+    alvrl_stats stats;
+    uint32_t nearTieSplits = 0;
+    uint64_t clusterVarianceSteps = 0, clusterSplits = 0;
+
+    Ctx() { memset(&stats, 0, sizeof(stats)); }
+    uint32_t P_() const { return cam.W * cam.H; }
+    uint32_t K() const { return 2 * P.volVolSamples + P.volSurfSamples; }
+    Sampler *newStream() {
+        if (P.rngMode == ALVRL_RNG_MODE_SFMT) return new SfmtSampler(P.seed);
+        return new CounterSampler(P.seed);
+    }
+    IntegratorCore core() {
+        IntegratorCore c; c.scene = &scene; c.medium = &medium; c.volVolSamples = P.volVolSamples;
+        c.volSurfSamples = P.volSurfSamples; c.shortVrls = P.shortVrls != 0; c.noVisibility = noVisibility;
+        return c;
+    }
+};
+
+int seterr(int code, const std::string &m) { g_err = m; return code; }
+double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+#define ORC_TRY try {
+#define ORC_CATCH } catch (const std::exception &e) { return seterr(ALVRL_ERR_ARG, e.what()); } return ALVRL_OK;
+
+void tracePrimary(Ctx *c) {
+    if (c->havePrimary) return;
+    uint32_t W = c->cam.W, H = c->cam.H;
+    c->rays.resize((size_t) W * H); c->hits.resize((size_t) W * H);
+    auto work = [&](uint32_t x0, uint32_t x1) {
+        for (uint32_t i = x0; i < x1; i++)
+            for (uint32_t j = 0; j < H; j++) {
+                size_t idx = (size_t) i * H + j;
+                c->rays[idx] = c->cam.sampleRay(i + 0.5f, j + 0.5f);       // Preprocessor.cpp:1144-1146
+                c->scene.rayIntersect(c->rays[idx], c->hits[idx]);
+            }
+    };
+    int T = std::max(1, c->threads);
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; t++) th.emplace_back(work, (uint32_t) ((uint64_t) W * t / T), (uint32_t) ((uint64_t) W * (t + 1) / T));
+    for (auto &t : th) t.join();
+    c->havePrimary = true;
+}
+
+/* getVRLContributions for one row, vrlIntegrator.cpp:792-825 with vrlContributions != NULL */
+void buildRow(Ctx *c, IntegratorCore &core, Sampler *sampler, uint32_t row, VrlContribution *out) {
+    uint32_t N = c->vrls.size();
+    uint32_t pixel = c->rowPixel[row];
+    const Ray &ray = c->rays[pixel];
+    const Intersection &its = c->hits[pixel];
+    for (uint32_t v = 0; v < N; v++) out[v] = VrlContribution{0, 0};
+    if (!its.isValid()) return;                                             // vrlIntegrator.cpp:418-423
+    if (c->medium.sigmaS.isZero()) return;                                   // 795-797
+    for (int s = 0; s < c->P.Rsamples; s++) {                                // LiInternal samples loop, 427-442 (quirk B3)
+        for (uint32_t v = 0; v < N; v++) {
+            Float normalization = 1.0 / c->particleCount;
+            Float contribution, variance;
+            if (s == 0) sampler->setContext(ALVRL_RNG_R, row, v);
+            core.integrateVRL(ray, its, c->vrls[v], sampler, &contribution, &variance, Spec(1.0f));
+            out[v].mean += contribution * normalization;
+            out[v].var += variance * normalization * normalization;
+        }
+    }
+}
+
+} // namespace
+
+extern "C" {
+
+const char *orc_last_error(void) { return g_err.c_str(); }
+
+void orc_params_default(alvrl_params *p) {
+    memset(p, 0, sizeof(*p));
+    p->shortVrls = 1; p->vrlTargetNum = 500; p->maxParticleDepth = -1; p->specularForcedRRdepth = 100;
+    p->initialSpecularThroughput = 20; p->volVolSamples = 2; p->volSurfSamples = 2; p->globalCluster = 0;
+    p->globalUndersampling = -1; p->localRefinement = 1; p->localUndersampling = -1; p->fallBackUndersampling = 5;
+    p->targetNumSlices = 100; p->targetPixelUndersampling = 64; p->sliceCurvatureFactor = 0.5f;
+    p->neighbourCount = 0; p->neighbourWeight = 0; p->Rsamples = 1; p->depthCorrection = 1; p->maxPasses = 1;
+    p->rngMode = ALVRL_RNG_MODE_COUNTER; p->seed = 0; p->anyHitShadowRays = 1; p->workerCount = 1;
+}
+
+int orc_create(int, const alvrl_params *p, void **out) {
+    /* vrlIntegrator ctor checks, vrlIntegrator.cpp:149-156; Preprocessor ctor, Preprocessor.cpp:36-38 */
+    if (p->volVolSamples != 0 && p->volVolSamples < 2) return seterr(ALVRL_ERR_ARG, "Need at least 2 volVolSamples for variance estimate");
+    if (p->volSurfSamples != 0 && p->volSurfSamples < 2) return seterr(ALVRL_ERR_ARG, "Need at least 2 volSurfSamples for variance estimate");
+    if (p->targetNumSlices < 1) return seterr(ALVRL_ERR_ARG, "Invalid target number of slices!");
+    if (p->neighbourWeight > 0) return seterr(ALVRL_ERR_UNSUPPORTED, "neighbourWeight > 0 is not restated");
+    Ctx *c = new Ctx();
+    c->P = *p;
+    c->mainSampler.reset(c->newStream());
+    *out = c;
+    return ALVRL_OK;
+}
+void orc_destroy(void *h) { delete (Ctx *) h; }
+int orc_set_threads(void *h, int n) { ((Ctx *) h)->threads = std::max(1, n); return ALVRL_OK; }
+int orc_set_no_visibility(void *h, int on) { ((Ctx *) h)->noVisibility = on != 0; return ALVRL_OK; }
+
+int orc_set_mesh(void *h, const float *v, uint32_t nv, const uint32_t *tris, uint32_t nt, const uint32_t *mat) {
+    Ctx *c = (Ctx *) h;
+    c->scene.verts.resize(nv);
+    for (uint32_t i = 0; i < nv; i++) c->scene.verts[i] = V3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+    c->scene.tris.assign(tris, tris + 3 * (size_t) nt);
+    c->scene.triMat.assign(mat, mat + nt);
+    for (size_t i = 0; i < 3 * (size_t) nt; i++) if (tris[i] >= nv) return seterr(ALVRL_ERR_ARG, "triangle index out of range");
+    c->scene.finalize();
+    c->haveMesh = true; c->havePrimary = false;
+    return ALVRL_OK;
+}
+int orc_set_materials(void *h, const float *albedo, const uint32_t *bits, uint32_t nm) {
+    Ctx *c = (Ctx *) h;
+    c->scene.albedo.resize(nm); c->scene.matBits.assign(bits, bits + nm);
+    for (uint32_t i = 0; i < nm; i++) c->scene.albedo[i] = Spec(albedo[3 * i], albedo[3 * i + 1], albedo[3 * i + 2]);
+    c->haveMat = true;
+    return ALVRL_OK;
+}
+int orc_set_extra_bounds(void *h, const float *p, uint32_t n) {
+    Ctx *c = (Ctx *) h;
+    c->scene.extraBounds.clear();
+    for (uint32_t i = 0; i < n; i++) c->scene.extraBounds.push_back(V3(p[3 * i], p[3 * i + 1], p[3 * i + 2]));
+    if (c->haveMesh) c->scene.finalize();
+    return ALVRL_OK;
+}
+int orc_set_medium_homogeneous(void *h, const float a[3], const float s[3], float w, int32_t phase, float g) {
+    Ctx *c = (Ctx *) h;
+    c->medium.setHomogeneous(a, s, w); c->medium.phaseType = phase; c->medium.g = g;
+    c->haveMedium = true;
+    return ALVRL_OK;
+}
+int orc_set_medium_grid(void *h, const float *density, const int32_t res[3], const float mn[3], const float mx[3], float scale,
+                        const float albedo[3], const float sBase[3], int32_t phase, float g) {
+    Ctx *c = (Ctx *) h;
+    int r[3] = {res[0], res[1], res[2]};
+    c->medium.setGrid(density, r, V3(mn[0], mn[1], mn[2]), V3(mx[0], mx[1], mx[2]), scale, albedo, sBase);
+    c->medium.phaseType = phase; c->medium.g = g;
+    c->haveMedium = true;
+    return ALVRL_OK;
+}
+int orc_set_camera(void *h, const float s2c[16], const float c2w[16], uint32_t W, uint32_t H, float nearClip, float farClip) {
+    Ctx *c = (Ctx *) h;
+    memcpy(c->cam.s2c, s2c, 64); memcpy(c->cam.c2w, c2w, 64);
+    c->cam.W = W; c->cam.H = H; c->cam.nearClip = nearClip; c->cam.farClip = farClip;
+    c->haveCam = true; c->havePrimary = false;
+    return ALVRL_OK;
+}
+int orc_set_vrls(void *h, const float *s, const float *e, const float *p, uint32_t n, uint64_t particleCount) {
+    Ctx *c = (Ctx *) h;
+    c->vrls.clear();
+    for (uint32_t i = 0; i < n; i++) {                                     // vrlVector::put, VRL.h:148-158
+        VRL v; v.start = V3(s[3 * i], s[3 * i + 1], s[3 * i + 2]); v.end = V3(e[3 * i], e[3 * i + 1], e[3 * i + 2]);
+        v.power = Spec(p[3 * i], p[3 * i + 1], p[3 * i + 2]);
+        if (!v.power.isValid()) return seterr(ALVRL_ERR_ARG, "invalid parsed VRL power");     // VRL.h:51-53
+        if (c->haveMedium && c->medium.sigmaS.isZero()) continue;
+        if (v.power.isZero()) continue;
+        if (distance(v.start, v.end) == 0) continue;
+        c->vrls.push_back(v);
+    }
+    c->particleCount = particleCount ? particleCount : c->vrls.size();
+    c->haveVrls = true;
+    return ALVRL_OK;
+}
+int orc_get_num_vrls(void *h, uint32_t *n) { *n = ((Ctx *) h)->vrls.size(); return ALVRL_OK; }
+int orc_set_sample_tape(void *h, const float *tape, uint64_t n) {
+    Ctx *c = (Ctx *) h;
+    if (!tape) { c->tape = nullptr; c->tapeLen = 0; c->tapeStore.clear(); return ALVRL_OK; }
+    c->tapeStore.assign(tape, tape + n); c->tape = c->tapeStore.data(); c->tapeLen = n;
+    return ALVRL_OK;
+}
+
+/* Preprocessor::buildSlices, Preprocessor.cpp:1130-1193 */
+int orc_build_slices(void *h) {
+    Ctx *c = (Ctx *) h;
+    if (!(c->haveMesh && c->haveCam && c->haveMat)) return seterr(ALVRL_ERR_STATE, "scene incomplete");
+    ORC_TRY
+    double t0 = now_ms();
+    tracePrimary(c);
+    uint32_t P = c->P_();
+    std::vector<V3> gather(P), dirs(P);
+    Float directionScale = distance(c->scene.sceneAABB.min, c->scene.sceneAABB.max) / 8 * c->P.sliceCurvatureFactor;
+    const Float nan = std::numeric_limits<Float>::quiet_NaN();
+    for (uint32_t i = 0; i < P; i++) {
+        if (c->hits[i].isValid()) { gather[i] = c->hits[i].p; dirs[i] = directionScale * c->hits[i].n; }
+        else { gather[i] = V3(nan); dirs[i] = V3(nan); }
+    }
+    c->pixelToSlice = SliceBuilder::getSlices(gather, dirs, c->P.targetNumSlices, c->slices);
+    c->haveSlices = true; c->haveRows = false; c->haveR = false; c->haveClusters = false;
+    c->stats.msSlices = (float) (now_ms() - t0);
+    c->stats.numSlices = c->slices.size();
+    ORC_CATCH
+}
+int orc_build_slices_from_gather(void *h, const float *pos, const float *dir) {
+    Ctx *c = (Ctx *) h;
+    if (!c->haveCam) return seterr(ALVRL_ERR_STATE, "camera not set");
+    ORC_TRY
+    uint32_t P = c->P_();
+    std::vector<V3> gather(P), dirs(P);
+    for (uint32_t i = 0; i < P; i++) { gather[i] = V3(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]); dirs[i] = V3(dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]); }
+    c->pixelToSlice = SliceBuilder::getSlices(gather, dirs, c->P.targetNumSlices, c->slices);
+    c->haveSlices = true; c->haveRows = false; c->haveR = false; c->haveClusters = false;
+    c->stats.numSlices = c->slices.size();
+    ORC_CATCH
+}
+int orc_get_gather_points(void *h, float *pos, float *dir) {
+    Ctx *c = (Ctx *) h;
+    tracePrimary(c);
+    Float directionScale = distance(c->scene.sceneAABB.min, c->scene.sceneAABB.max) / 8 * c->P.sliceCurvatureFactor;
+    const Float nan = std::numeric_limits<Float>::quiet_NaN();
+    for (uint32_t i = 0; i < c->P_(); i++) {
+        V3 g(nan), d(nan);
+        if (c->hits[i].isValid()) { g = c->hits[i].p; d = directionScale * c->hits[i].n; }
+        pos[3 * i] = g.x; pos[3 * i + 1] = g.y; pos[3 * i + 2] = g.z; dir[3 * i] = d.x; dir[3 * i + 1] = d.y; dir[3 * i + 2] = d.z;
+    }
+    return ALVRL_OK;
+}
+
+/* Preprocessor::sampleSliceMapping, Preprocessor.cpp:1502-1525 */
+int orc_sample_slice_mapping(void *h) {
+    Ctx *c = (Ctx *) h;
+    if (!c->haveSlices) return seterr(ALVRL_ERR_STATE, "build_slices first");
+    ORC_TRY
+    double t0 = now_ms();
+    size_t S = c->slices.size();
+    c->rowOffset.assign(S + 1, 0); c->rowPixel.clear(); c->sliceUndersampling.resize(S);
+    size_t totalPix = 0, totalRep = 0;
+    for (size_t i = 0; i < S; i++) {
+        c->mainSampler->setContext(ALVRL_RNG_SLICEMAP, (uint32_t) i, 0);
+        std::vector<uint32_t> px = SliceBuilder::sampleRepresentativePixels(c->slices[i], c->P.targetPixelUndersampling, c->mainSampler.get());
+        c->rowPixel.insert(c->rowPixel.end(), px.begin(), px.end());
+        c->rowOffset[i + 1] = c->rowPixel.size();
+        c->sliceUndersampling[i] = ((Float) px.size()) / c->slices[i].gatherIdx.size();
+        totalRep += px.size(); totalPix += c->slices[i].gatherIdx.size();
+    }
+    c->globalPixelUndersampling = ((Float) totalRep) / totalPix;
+    c->haveRows = true; c->haveR = false; c->haveClusters = false;
+    c->stats.msSliceMapping = (float) (now_ms() - t0);
+    c->stats.numRows = c->rowPixel.size();
+    ORC_CATCH
+}
+
+static int buildR_impl(Ctx *c, std::vector<float> *recordTape) {
+    if (!c->haveRows || !c->haveVrls || !c->haveMedium) return seterr(ALVRL_ERR_STATE, "sample_slice_mapping / set_vrls / set_medium first");
+    ORC_TRY
+    double t0 = now_ms();
+    tracePrimary(c);
+    uint32_t N = c->vrls.size(), G = c->rowPixel.size(), S = c->slices.size();
+    c->R.assign((size_t) G * N, VrlContribution{0, 0});
+    uint32_t sb = std::min(c->sliceBegin, S), se = std::min(c->sliceEnd, S);
+    uint64_t shadow = 0;
+    if (c->tape) {
+        int T = std::max(1, c->threads);
+        std::vector<std::thread> th; std::vector<uint64_t> sh(T, 0);
+        for (int t = 0; t < T; t++) th.emplace_back([&, t]() {
+            TapeSampler smp(c->tape, c->tapeLen, c->K() * c->P.Rsamples, N);
+            IntegratorCore core = c->core();
+            uint32_t s0 = sb + (uint64_t) (se - sb) * t / T, s1 = sb + (uint64_t) (se - sb) * (t + 1) / T;
+            for (uint32_t row = c->rowOffset[s0]; row < c->rowOffset[s1]; row++) buildRow(c, core, &smp, row, &c->R[(size_t) row * N]);
+            sh[t] = core.shadowRays;
+        });
+        for (auto &t : th) t.join();
+        for (uint64_t s : sh) shadow += s;
+    } else if (c->P.rngMode == ALVRL_RNG_MODE_SFMT || recordTape) {
+        /* reference stream order: prepass loops (workerCount == 1, vrlIntegrator.cpp:322-333) or one
+         * cloned sampler per Rbuilder over contiguous slice ranges (305-321, 1048-1051) */
+        int w = std::max(1, c->P.workerCount);
+        std::vector<std::unique_ptr<Sampler>> clones;
+        if (w > 1) for (int i = 0; i < w; i++) clones.emplace_back(c->mainSampler->clone());
+        std::vector<std::thread> th; std::vector<uint64_t> sh(w, 0);
+        auto work = [&](int id) {
+            Sampler *smp = w > 1 ? clones[id].get() : c->mainSampler.get();
+            std::unique_ptr<RecordingSampler> rec;
+            if (recordTape) { rec.reset(new RecordingSampler(smp, *recordTape, c->K() * c->P.Rsamples, N)); smp = rec.get(); }
+            IntegratorCore core = c->core();
+            uint32_t s0 = ((uint64_t) id * S) / w, s1 = ((uint64_t) (id + 1) * S) / w;
+            for (uint32_t row = c->rowOffset[s0]; row < c->rowOffset[s1]; row++) buildRow(c, core, smp, row, &c->R[(size_t) row * N]);
+            sh[id] = core.shadowRays;
+        };
+        if (w > 1) { for (int i = 0; i < w; i++) th.emplace_back(work, i); for (auto &t : th) t.join(); }
+        else work(0);
+        for (uint64_t s : sh) shadow += s;
+    } else {
+        int T = std::max(1, c->threads);
+        std::vector<std::thread> th; std::vector<uint64_t> sh(T, 0);
+        for (int t = 0; t < T; t++) th.emplace_back([&, t]() {
+            CounterSampler smp(c->P.seed);
+            IntegratorCore core = c->core();
+            uint32_t s0 = sb + (uint64_t) (se - sb) * t / T, s1 = sb + (uint64_t) (se - sb) * (t + 1) / T;
+            for (uint32_t row = c->rowOffset[s0]; row < c->rowOffset[s1]; row++) buildRow(c, core, &smp, row, &c->R[(size_t) row * N]);
+            sh[t] = core.shadowRays;
+        });
+        for (auto &t : th) t.join();
+        for (uint64_t s : sh) shadow += s;
+    }
+    c->haveR = true; c->haveClusters = false;
+    c->stats.msBuildR = (float) (now_ms() - t0);
+    c->stats.pairsPreprocess += (uint64_t) (c->rowOffset[se] - c->rowOffset[sb]) * N * c->P.Rsamples;
+    c->stats.shadowRays += shadow;
+    c->stats.numVrls = N;
+    ORC_CATCH
+}
+int orc_build_R(void *h) { return buildR_impl((Ctx *) h, nullptr); }
+/* build R in this context's stream order and record every uniform into the fixed-slot tape layout */
+int orc_build_R_record_tape(void *h, float *tapeOut, uint64_t n) {
+    Ctx *c = (Ctx *) h;
+    uint64_t need = (uint64_t) c->rowPixel.size() * c->vrls.size() * c->K() * c->P.Rsamples;
+    if (n < need) return seterr(ALVRL_ERR_ARG, "tape buffer too small");
+    if (c->P.workerCount > 1) return seterr(ALVRL_ERR_ARG, "record with workerCount == 1");
+    std::vector<float> tape(need, 0.5f);
+    int rc = buildR_impl(c, &tape);
+    memcpy(tapeOut, tape.data(), need * sizeof(float));
+    return rc;
+}
+
+/* Preprocessor::buildClusters, Preprocessor.cpp:133-283,838-898 */
+int orc_build_clusters(void *h) {
+    Ctx *c = (Ctx *) h;
+    if (!c->haveR) return seterr(ALVRL_ERR_STATE, "build_R first");
+    ORC_TRY
+    double t0 = now_ms();
+    uint32_t N = c->vrls.size(), G = c->rowPixel.size(), S = c->slices.size();
+    if (c->globalPixelUndersampling < 0) fail("Invalid pixel undersampling. Did you forget to call buildSlices first?");
+    MatView flat; flat.nVrls = N;
+    for (uint32_t r = 0; r < G; r++) flat.rows.push_back(&c->R[(size_t) r * N]);
+    Sampler *smp = c->mainSampler.get();
+    smp->setContext(ALVRL_RNG_CLUSTER, ALVRL_RNG_GLOBAL_ID, 0);
+    ClusterStats cstats;
+    /* cluster(), 838-898 */
+    std::vector<std::vector<uint32_t>> globalVrlsPerCluster;
+    std::vector<uint32_t> nonZero, zero;
+    for (uint32_t i = 0; i < N; i++) {
+        Float sum = 0;                                                       // totalVrlContribution, 936-945
+        for (uint32_t r = 0; r < G; r++) sum += flat.rows[r][i].mean;
+        if (sum != 0) nonZero.push_back(i); else zero.push_back(i);
+    }
+    if (!nonZero.empty()) {
+        if (c->P.globalCluster) {                                           // clusterRefinement, 899-912
+            std::vector<std::vector<uint32_t>> init(1, nonZero);
+            std::vector<double> lw(G, 1.0 / G);
+            Clustering cl(init, flat, lw, c->globalPixelUndersampling, 1, &cstats);
+            if (!cl.refine(c->P.globalUndersampling, smp)) fail("Couldn't refine global clustering!");
+            globalVrlsPerCluster = cl.getVrlsPerCluster();
+            c->nearTieSplits += cl.nearTieSplits;
+        } else globalVrlsPerCluster.assign(1, nonZero);
+    }
+    if (!zero.empty()) globalVrlsPerCluster.push_back(zero);
+    /* global clustering + fallback, 165-181 */
+    {
+        std::vector<double> lw(G, 1.0 / G);
+        Clustering gcl(globalVrlsPerCluster, flat, lw, c->globalPixelUndersampling, 1, &cstats);
+        gcl.sampleRepresentatives(c->gcVrls, c->gcWeight, smp);
+        if (!gcl.refine(c->P.fallBackUndersampling, smp)) fail("couldn't refine global clustering! (but all VRLs should be non-zero!)");
+        gcl.sampleRepresentatives(c->fallBackVrls, c->fallBackWeight, smp);
+        c->nearTieSplits += gcl.nearTieSplits;
+    }
+    /* refinePerSlice, 199-283 */
+    c->selectedVrls.assign(S, {}); c->clusterWeight.assign(S, {});
+    bool sfmt = c->P.rngMode == ALVRL_RNG_MODE_SFMT;
+    int w = sfmt ? std::max(1, c->P.workerCount) : std::max(1, c->threads);
+    std::vector<std::unique_ptr<Sampler>> clones;
+    if (w > 1 || !sfmt) for (int i = 0; i < w; i++) clones.emplace_back(c->mainSampler->clone());   // ClusterRefiner ctor, 738
+    std::vector<uint32_t> ties(w, 0); std::vector<ClusterStats> cs(w);
+    std::vector<std::string> errs(w);
+    auto work = [&](int id) {
+        try {
+        Sampler *s = (w > 1 || !sfmt) ? clones[id].get() : smp;
+        uint32_t s0 = ((uint64_t) id * S) / w, s1 = ((uint64_t) (id + 1) * S) / w;
+        for (uint32_t i = s0; i < s1; i++) {
+            /* refineSlice, 254-283; getLocalMatrix with neighbourWeight <= 0, 779-794 */
+            MatView L; L.nVrls = N;
+            uint32_t nr = c->rowOffset[i + 1] - c->rowOffset[i];
+            for (uint32_t r = c->rowOffset[i]; r < c->rowOffset[i + 1]; r++) L.rows.push_back(&c->R[(size_t) r * N]);
+            std::vector<double> lw(nr);
+            for (uint32_t k = 0; k < nr; k++) lw[k] = 1.0 / nr;
+            s->setContext(ALVRL_RNG_CLUSTER, i, 0);
+            Clustering cl(globalVrlsPerCluster, L, lw, c->sliceUndersampling[i], c->P.depthCorrection, &cs[id]);
+            if (!c->P.localRefinement) { cl.sampleRepresentatives(c->selectedVrls[i], c->clusterWeight[i], s); continue; }
+            if (cl.refine(c->P.localUndersampling, s)) cl.sampleRepresentatives(c->selectedVrls[i], c->clusterWeight[i], s);
+            else { c->selectedVrls[i] = c->fallBackVrls; c->clusterWeight[i] = c->fallBackWeight; }
+            ties[id] += cl.nearTieSplits;
+        }
+        } catch (const std::exception &e) { errs[id] = e.what(); }
+    };
+    if (w > 1) { std::vector<std::thread> th; for (int i = 0; i < w; i++) th.emplace_back(work, i); for (auto &t : th) t.join(); }
+    else work(0);
+    for (auto &e : errs) if (!e.empty()) fail(e);
+    for (int i = 0; i < w; i++) { c->nearTieSplits += ties[i]; cstats.splits += cs[i].splits; cstats.varianceSteps += cs[i].varianceSteps; }
+    c->clusterSplits = cstats.splits; c->clusterVarianceSteps = cstats.varianceSteps;
+    c->haveClusters = true;
+    c->stats.msClusters = (float) (now_ms() - t0);
+    ORC_CATCH
+}
+int orc_prepass(void *h) {
+    int rc;
+    if ((rc = orc_sample_slice_mapping(h))) return rc;
+    if ((rc = orc_build_R(h))) return rc;
+    return orc_build_clusters(h);
+}
+
+/* Li for every pixel centre, vrlIntegrator.cpp:386-393,542-599; image layout [y][x][c].
+ * pixelSubset (optional): only these pixel indices are evaluated (bounded CPU baseline sample). */
+static int render_impl(Ctx *c, float *rgb, bool clustered, const uint32_t *pixelSubset, uint32_t nSubset) {
+    ORC_TRY
+    double t0 = now_ms();
+    tracePrimary(c);
+    uint32_t W = c->cam.W, H = c->cam.H, P = W * H, N = c->vrls.size();
+    uint32_t count = pixelSubset ? nSubset : P;
+    if (!pixelSubset) for (size_t i = 0; i < (size_t) P * 3; i++) rgb[i] = 0;
+    int T = std::max(1, c->threads);
+    std::vector<std::thread> th; std::vector<uint64_t> pairs(T, 0), sh(T, 0);
+    uint32_t S = c->slices.size();
+    uint32_t sb = std::min(c->sliceBegin, S), se = std::min(c->sliceEnd, S);
+    for (int t = 0; t < T; t++) th.emplace_back([&, t]() {
+        CounterSampler smp(c->P.seed);
+        IntegratorCore core = c->core();
+        for (uint32_t q = (uint64_t) count * t / T; q < (uint64_t) count * (t + 1) / T; q++) {
+            uint32_t pix = pixelSubset ? pixelSubset[q] : q;
+            uint32_t x = pix / H, y = pix % H;
+            const Intersection &its = c->hits[pix];
+            Spec Li(0.0f);
+            if (its.isValid() && !c->medium.sigmaS.isZero()) {
+                if (clustered) {
+                    uint32_t slice = c->pixelToSlice[pix];
+                    if (slice != ALVRL_NO_SLICE && (slice < sb || slice >= se)) continue;
+                    const std::vector<uint32_t> &vr = slice == ALVRL_NO_SLICE ? c->fallBackVrls : c->selectedVrls[slice];
+                    const std::vector<Float> &wt = slice == ALVRL_NO_SLICE ? c->fallBackWeight : c->clusterWeight[slice];
+                    for (size_t i = 0; i < vr.size(); i++) {
+                        smp.setContext(ALVRL_RNG_RENDER, pix, (uint32_t) i);
+                        Li += wt.at(i) * core.integrateVRL(c->rays[pix], its, c->vrls[vr.at(i)], &smp, nullptr, nullptr);
+                    }
+                    Li /= (Float) c->particleCount;
+                    pairs[t] += vr.size();
+                } else {
+                    for (uint32_t v = 0; v < N; v++) {                       // getVRLContributions, 803-816
+                        Float normalization = 1.0 / c->particleCount;
+                        smp.setContext(ALVRL_RNG_RENDER, pix, v);
+                        Spec vc = core.integrateVRL(c->rays[pix], its, c->vrls[v], &smp, nullptr, nullptr);
+                        vc *= normalization;
+                        Li += vc;
+                    }
+                    pairs[t] += N;
+                }
+            }
+            float *o = pixelSubset ? rgb + 3 * (size_t) q : rgb + 3 * ((size_t) y * W + x);
+            o[0] = Li[0]; o[1] = Li[1]; o[2] = Li[2];
+        }
+        sh[t] = core.shadowRays;
+    });
+    for (auto &t : th) t.join();
+    for (int t = 0; t < T; t++) { c->stats.pairsRender += pairs[t]; c->stats.shadowRays += sh[t]; }
+    c->stats.msRender = (float) (now_ms() - t0);
+    ORC_CATCH
+}
+int orc_render(void *h, float *rgb) {
+    Ctx *c = (Ctx *) h;
+    if (!c->haveClusters) return seterr(ALVRL_ERR_STATE, "build_clusters first");
+    return render_impl(c, rgb, true, nullptr, 0);
+}
+int orc_render_unclustered(void *h, float *rgb) {
+    Ctx *c = (Ctx *) h;
+    if (!c->haveVrls || !c->haveMedium) return seterr(ALVRL_ERR_STATE, "set_vrls / set_medium first");
+    return render_impl(c, rgb, false, nullptr, 0);
+}
+int orc_render_pixels(void *h, const uint32_t *pixels, uint32_t n, float *rgb, int clustered) {
+    Ctx *c = (Ctx *) h;
+    if (clustered && !c->haveClusters) return seterr(ALVRL_ERR_STATE, "build_clusters first");
+    return render_impl(c, rgb, clustered != 0, pixels, n);
+}
+int orc_set_slice_range(void *h, uint32_t b, uint32_t e) { Ctx *c = (Ctx *) h; c->sliceBegin = b; c->sliceEnd = e; return ALVRL_OK; }
+
+/* ---- getters / setters ---------------------------------------------------------------------- */
+int orc_get_stats(void *h, alvrl_stats *out) { *out = ((Ctx *) h)->stats; return ALVRL_OK; }
+int orc_get_cluster_diag(void *h, uint32_t *nearTies, uint64_t *splits, uint64_t *varianceSteps) {
+    Ctx *c = (Ctx *) h; *nearTies = c->nearTieSplits; *splits = c->clusterSplits; *varianceSteps = c->clusterVarianceSteps; return ALVRL_OK;
+}
+int orc_get_primary_hits(void *h, uint32_t *prim, float *t, float *p, float *n) {
+    Ctx *c = (Ctx *) h;
+    if (!(c->haveMesh && c->haveCam)) return seterr(ALVRL_ERR_STATE, "scene incomplete");
+    tracePrimary(c);
+    for (uint32_t i = 0; i < c->P_(); i++) {
+        const Intersection &its = c->hits[i];
+        if (prim) prim[i] = its.prim;
+        if (t) t[i] = its.t;
+        if (p) { p[3 * i] = its.p.x; p[3 * i + 1] = its.p.y; p[3 * i + 2] = its.p.z; }
+        if (n) { n[3 * i] = its.n.x; n[3 * i + 1] = its.n.y; n[3 * i + 2] = its.n.z; }
+    }
+    return ALVRL_OK;
+}
+int orc_get_primary_ties(void *h, uint8_t *tie) {
+    Ctx *c = (Ctx *) h; tracePrimary(c);
+    for (uint32_t i = 0; i < c->P_(); i++) tie[i] = c->hits[i].tie;
+    return ALVRL_OK;
+}
+int orc_get_pixel_to_slice(void *h, uint32_t *out) {
+    Ctx *c = (Ctx *) h;
+    if (!c->haveSlices) return seterr(ALVRL_ERR_STATE, "build_slices first");
+    memcpy(out, c->pixelToSlice.data(), c->pixelToSlice.size() * 4);
+    return ALVRL_OK;
+}
+int orc_get_num_slices(void *h, uint32_t *ns, uint32_t *nr) {
+    Ctx *c = (Ctx *) h; *ns = c->slices.size(); *nr = c->haveRows ? c->rowPixel.size() : 0; return ALVRL_OK;
+}
+int orc_get_rep_pixels(void *h, uint32_t *off, uint32_t *px) {
+    Ctx *c = (Ctx *) h;
+    if (!c->haveRows) return seterr(ALVRL_ERR_STATE, "sample_slice_mapping first");
+    memcpy(off, c->rowOffset.data(), c->rowOffset.size() * 4); memcpy(px, c->rowPixel.data(), c->rowPixel.size() * 4);
+    return ALVRL_OK;
+}
+int orc_set_rep_pixels(void *h, const uint32_t *off, const uint32_t *px, uint32_t ns) {
+    Ctx *c = (Ctx *) h;
+    if (!c->haveSlices || ns != c->slices.size()) return seterr(ALVRL_ERR_STATE, "slice count mismatch");
+    c->rowOffset.assign(off, off + ns + 1); c->rowPixel.assign(px, px + off[ns]);
+    c->sliceUndersampling.resize(ns);
+    size_t totalPix = 0;
+    for (uint32_t i = 0; i < ns; i++) {
+        c->sliceUndersampling[i] = ((Float) (off[i + 1] - off[i])) / c->slices[i].gatherIdx.size();
+        totalPix += c->slices[i].gatherIdx.size();
+    }
+    c->globalPixelUndersampling = ((Float) off[ns]) / totalPix;
+    c->haveRows = true; c->haveR = false; c->haveClusters = false;
+    return ALVRL_OK;
+}
+int orc_get_R(void *h, uint32_t r0, uint32_t r1, float *mv) {
+    Ctx *c = (Ctx *) h;
+    if (!c->haveR) return seterr(ALVRL_ERR_STATE, "build_R first");
+    size_t N = c->vrls.size();
+    memcpy(mv, &c->R[(size_t) r0 * N], (size_t) (r1 - r0) * N * sizeof(VrlContribution));
+    return ALVRL_OK;
+}
+int orc_set_R(void *h, const float *mv) {
+    Ctx *c = (Ctx *) h;
+    if (!c->haveRows || !c->haveVrls) return seterr(ALVRL_ERR_STATE, "rows / vrls first");
+    size_t n = (size_t) c->rowPixel.size() * c->vrls.size();
+    c->R.resize(n); memcpy(c->R.data(), mv, n * sizeof(VrlContribution));
+    c->haveR = true; c->haveClusters = false;
+    return ALVRL_OK;
+}
+int orc_get_cluster_counts(void *h, uint32_t *off, uint32_t *ng, uint32_t *nf) {
+    Ctx *c = (Ctx *) h;
+    if (!c->haveClusters) return seterr(ALVRL_ERR_STATE, "build_clusters first");
+    off[0] = 0;
+    for (size_t i = 0; i < c->selectedVrls.size(); i++) off[i + 1] = off[i] + c->selectedVrls[i].size();
+    *ng = c->gcVrls.size(); *nf = c->fallBackVrls.size();
+    return ALVRL_OK;
+}
+int orc_get_clusters(void *h, uint32_t *vrls, float *weights, uint32_t *gv, float *gw, uint32_t *fv, float *fw) {
+    Ctx *c = (Ctx *) h;
+    if (!c->haveClusters) return seterr(ALVRL_ERR_STATE, "build_clusters first");
+    size_t o = 0;
+    for (size_t i = 0; i < c->selectedVrls.size(); i++)
+        for (size_t j = 0; j < c->selectedVrls[i].size(); j++, o++) { vrls[o] = c->selectedVrls[i][j]; weights[o] = c->clusterWeight[i][j]; }
+    for (size_t j = 0; j < c->gcVrls.size(); j++) { if (gv) gv[j] = c->gcVrls[j]; if (gw) gw[j] = c->gcWeight[j]; }
+    for (size_t j = 0; j < c->fallBackVrls.size(); j++) { if (fv) fv[j] = c->fallBackVrls[j]; if (fw) fw[j] = c->fallBackWeight[j]; }
+    return ALVRL_OK;
+}
+int orc_set_clusters(void *h, const uint32_t *off, uint32_t ns, const uint32_t *vrls, const float *weights,
+                     const uint32_t *fv, const float *fw, uint32_t nf) {
+    Ctx *c = (Ctx *) h;
+    c->selectedVrls.assign(ns, {}); c->clusterWeight.assign(ns, {});
+    for (uint32_t i = 0; i < ns; i++) {
+        c->selectedVrls[i].assign(vrls + off[i], vrls + off[i + 1]);
+        c->clusterWeight[i].assign(weights + off[i], weights + off[i + 1]);
+    }
+    c->fallBackVrls.assign(fv, fv + nf); c->fallBackWeight.assign(fw, fw + nf);
+    c->haveClusters = true;
+    return ALVRL_OK;
+}
+int orc_trace_rays(void *h, const float *o, const float *d, const float *mint, const float *maxt, uint32_t n,
+                   uint32_t *prim, float *t, uint8_t *tie) {
+    Ctx *c = (Ctx *) h;
+    if (!c->haveMesh) return seterr(ALVRL_ERR_STATE, "set_mesh first");
+    for (uint32_t i = 0; i < n; i++) {
+        Ray ray(V3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), V3(d[3 * i], d[3 * i + 1], d[3 * i + 2]), mint[i], maxt[i]);
+        Float u, v, tt; uint32_t pr; bool ti;
+        c->scene.closestHit(ray, true, tt, pr, u, v, &ti);
+        prim[i] = pr; if (t) t[i] = tt; if (tie) tie[i] = ti;
+    }
+    return ALVRL_OK;
+}
+int orc_eval_transmittance(void *h, const float *p1, const int32_t *onSurf, const float *p2, uint32_t n, float *T) {
+    Ctx *c = (Ctx *) h;
+    if (!c->haveMesh || !c->haveMedium) return seterr(ALVRL_ERR_STATE, "set_mesh / set_medium first");
+    for (uint32_t i = 0; i < n; i++) {
+        Spec s = evalTransmittance(c->scene, c->medium, V3(p1[3 * i], p1[3 * i + 1], p1[3 * i + 2]), onSurf && onSurf[i],
+                                   V3(p2[3 * i], p2[3 * i + 1], p2[3 * i + 2]), false);
+        T[3 * i] = s[0]; T[3 * i + 1] = s[1]; T[3 * i + 2] = s[2];
+    }
+    return ALVRL_OK;
+}
+/* SFMT known-answer access for tests (src/tests/test_random.cpp:433-481) */
+int orc_sfmt_ulongs(uint64_t seed, uint64_t *out, uint32_t n) { Random r(seed); for (uint32_t i = 0; i < n; i++) out[i] = r.nextULong(); return ALVRL_OK; }
+int orc_sfmt_floats(uint64_t seed, float *out, uint32_t n) { Random r(seed); for (uint32_t i = 0; i < n; i++) out[i] = r.nextFloat(); return ALVRL_OK; }
+int orc_sfmt_clone_ulongs(uint64_t seed, uint32_t skipParent, uint64_t *out, uint32_t n) {
+    Random parent(seed); for (uint32_t i = 0; i < skipParent; i++) parent.nextULong();
+    Random child(&parent); for (uint32_t i = 0; i < n; i++) out[i] = child.nextULong(); return ALVRL_OK;
+}
+/* single integrateVRL call: row of (mean, var, r, g, b) */
+int orc_integrate_pair(void *h, uint32_t pixel, uint32_t vrl, const float *uniforms, uint32_t nu, float out[5]) {
+    Ctx *c = (Ctx *) h;
+    ORC_TRY
+    tracePrimary(c);
+    TapeSampler smp(uniforms, nu, nu, 1);
+    smp.setContext(0, 0, 0);
+    IntegratorCore core = c->core();
+    Float m = 0, v = 0;
+    Spec s(0.0f);
+    if (c->hits[pixel].isValid()) s = core.integrateVRL(c->rays[pixel], c->hits[pixel], c->vrls[vrl], &smp, &m, &v);
+    out[0] = m; out[1] = v; out[2] = s[0]; out[3] = s[1]; out[4] = s[2];
+    ORC_CATCH
+}
+
+} // extern "C"
