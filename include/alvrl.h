@@ -98,6 +98,9 @@ int  alvrl_create(int cuda_device, const alvrl_params *p, alvrl_handle *out);
 void alvrl_destroy(alvrl_handle h);
 const char *alvrl_last_error(void);
 int  alvrl_get_params(alvrl_handle h, alvrl_params *out);
+/* 0 (default): fast-math flavour of the transport kernels; 1: strict flavour (reference operation order,
+ * no FMA contraction, exp through double).  Also selectable with the environment variable ALVRL_MATH=strict. */
+int  alvrl_set_math_mode(alvrl_handle h, int strict);
 
 /* ---- scene upload (what the plugin marshals out of `const Scene *`) -------------------- */
 /* Triangle soup + per-triangle material; replaces ShapeKDTree's TriAccel array

@@ -1,0 +1,711 @@
+/*
+ * capi.cu -- the extern "C" entry points of include/alvrl.h and the host control flow of the path:
+ * vrlIntegrator::preprocess / prepass / render restated around device kernels
+ * (src/integrators/vrl/vrlIntegrator.cpp:237-356,386-599; Preprocessor.cpp:1130-1193,1502-1525).
+ * No exception crosses the boundary; there is no CPU implementation of any kernel in this library.
+ */
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <chrono>
+#include <fstream>
+#include <sstream>
+#include <algorithm>
+#include "context.h"
+#include "kernels.h"
+
+using namespace alvrl;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &m) { g_err = m; return code; }
+
+#define API_BEGIN try {
+#define API_END                                                                    \
+    } catch (const alvrl::Error &e) { return fail(e.code, e.what()); }              \
+    catch (const std::exception &e) { return fail(ALVRL_ERR_ARG, e.what()); }       \
+    return ALVRL_OK;
+
+double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+void use_device(alvrl_ctx *c) { ALVRL_CUDA(cudaSetDevice(c->device)); }
+
+HostSampler *new_stream(const alvrl_params &P) {
+    if (P.rngMode == ALVRL_RNG_MODE_SFMT) return new SfmtStream(P.seed);
+    return new CounterStream(P.seed);
+}
+
+/* BVH + TriAccel upload; ShapeKDTree / Scene bounding boxes (gkdtree.h:1213-1220, scene.cpp:387-413) */
+void ensure_scene(alvrl_ctx *c) {
+    if (!c->sceneDirty) return;
+    if (!c->haveMesh) throw Error(ALVRL_ERR_STATE, "set_mesh first");
+    const uint32_t nt = (uint32_t) c->triMat.size();
+    HostBvh bvh;
+    BvhBuilder(c->verts.data(), c->tris.data(), nt).build(bvh);
+    std::vector<TriRec> recs(nt);
+    std::vector<float4> tv(3 * (size_t) nt);
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (uint32_t i = 0; i < nt; i++) {
+        const uint32_t t = bvh.triOrder[i];
+        const float *A = &c->verts[3 * (size_t) c->tris[3 * (size_t) t]], *B = &c->verts[3 * (size_t) c->tris[3 * (size_t) t + 1]],
+                    *C = &c->verts[3 * (size_t) c->tris[3 * (size_t) t + 2]];
+        recs[i] = makeTriRec(A, B, C, t);
+        tv[3 * (size_t) t] = make_float4(A[0], A[1], A[2], 0); tv[3 * (size_t) t + 1] = make_float4(B[0], B[1], B[2], 0);
+        tv[3 * (size_t) t + 2] = make_float4(C[0], C[1], C[2], 0);
+        for (int k = 0; k < 3; k++) { mn[k] = std::min(mn[k], std::min(A[k], std::min(B[k], C[k]))); mx[k] = std::max(mx[k], std::max(A[k], std::max(B[k], C[k]))); }
+    }
+    const float eps = 1e-3f;
+    for (int k = 0; k < 3; k++) {
+        c->kdMin[k] = mn[k] - ((mx[k] - mn[k]) * eps + eps);
+        c->kdMax[k] = mx[k] + ((mx[k] - c->kdMin[k]) * eps + eps);
+        c->sceneMin[k] = c->kdMin[k]; c->sceneMax[k] = c->kdMax[k];
+    }
+    for (size_t i = 0; i + 2 < c->extraBounds.size(); i += 3)
+        for (int k = 0; k < 3; k++) { c->sceneMin[k] = std::min(c->sceneMin[k], c->extraBounds[i + k]); c->sceneMax[k] = std::max(c->sceneMax[k], c->extraBounds[i + k]); }
+    c->dNodes.upload(bvh.nodes, c->stream);
+    c->dTris.upload(recs, c->stream);
+    c->dTriVerts.upload(tv, c->stream);
+    c->dTriMat.upload(c->triMat, c->stream);
+    SceneDev &s = c->sceneDev;
+    s.nodes = c->dNodes.p; s.tris = c->dTris.p; s.numNodes = (uint32_t) bvh.nodes.size();
+    for (int k = 0; k < 3; k++) { s.kdMin[k] = c->kdMin[k]; s.kdMax[k] = c->kdMax[k]; }
+    s.anyHit = c->P.anyHitShadowRays ? 1 : 0;
+    c->stats.bvhNodes = s.numNodes;
+    c->sceneDirty = false; c->segsDirty = true;
+}
+
+void ensure_primary(alvrl_ctx *c) {
+    ensure_scene(c);
+    if (!c->segsDirty && c->havePrimary) return;
+    if (!c->haveCam || !c->haveMat) throw Error(ALVRL_ERR_STATE, "scene incomplete: set_camera / set_materials first");
+    const uint32_t P = c->numPixels();
+    c->dPixSegs.alloc(P); c->dHitPrim.alloc(P); c->dHitT.alloc(P);
+    launch_primary(c->sceneDev, c->medium, c->cam, c->dTriVerts.p, c->dTriMat.p, c->dMatAlbedo.p, c->dMatBits.p, c->haveMedium,
+                   c->dPixSegs.p, c->dHitPrim.p, c->dHitT.p, c->stream);
+    c->stats.kernelLaunches++;
+    ALVRL_CUDA(cudaGetLastError());
+    ALVRL_CUDA(cudaStreamSynchronize(c->stream));
+    c->havePrimary = true; c->segsDirty = false;
+}
+
+void invalidate_from_slices(alvrl_ctx *c) { c->haveRows = false; c->haveR = false; c->haveClusters = false; c->haveFallback = false; c->renderListsDirty = true; }
+
+void finish_slices(alvrl_ctx *c, const std::vector<P3> &pos, const std::vector<P3> &dir) {
+    SliceTree tree(pos, dir);
+    c->pixelToSlice = tree.build((uint32_t) c->P.targetNumSlices, c->slices);
+    c->haveSlices = true;
+    invalidate_from_slices(c);
+    c->stats.numSlices = (uint32_t) c->slices.size();
+}
+
+TransportParams make_transport_params(alvrl_ctx *c, uint32_t domain) {
+    TransportParams T;
+    memset(&T, 0, sizeof(T));
+    T.scene = c->sceneDev; T.medium = c->medium;
+    T.Nvv = c->P.volVolSamples; T.Nvs = c->P.volSurfSamples; T.shortVrls = c->P.shortVrls; T.Rsamples = c->P.Rsamples;
+    T.seed = c->P.seed; T.rngDomain = domain;
+    T.tape = nullptr; T.tapeK = 0;
+    T.numVrls = (uint32_t) c->vrlHost.size();
+    T.normalization = (float) (1.0 / (double) c->particleCount);       /* vrlIntegrator.cpp:805 */
+    T.invParticleDiv = (float) c->particleCount;                       /* 590: Li /= getParticleCount() */
+    T.rowBase = 0;
+    return T;
+}
+
+/* reference-stream tape for build_R: the prepass loops draw 2*Nvv (+ Nvs when the vol->surf loop runs) uniforms per
+ * (row, vrl), rows in slice order, VRLs in index order (vrlIntegrator.cpp:322-333,804-816) */
+void make_sfmt_tape(alvrl_ctx *c, std::vector<float> &tape) {
+    const uint32_t N = (uint32_t) c->vrlHost.size(), G = (uint32_t) c->rowPixel.size(), K = c->K(), S = (uint32_t) c->slices.size();
+    const uint64_t need = (uint64_t) G * N * K;
+    if (need > (1ull << 31)) throw Error(ALVRL_ERR_UNSUPPORTED, "rngMode=SFMT needs a G*N*(2*Nvv+Nvs) float tape; too large for this configuration");
+    tape.assign(need, 0.5f);
+    std::vector<SegRec> rows(G);
+    c->dRowSegs.download(rows.data(), G, c->stream);
+    const int w = std::max(1, c->P.workerCount);
+    std::vector<std::unique_ptr<HostSampler>> clones;
+    if (w > 1) for (int i = 0; i < w; i++) clones.emplace_back(c->mainSampler->clone());   /* Rbuilder ctor, 1048 */
+    const int Nvv2 = 2 * c->P.volVolSamples, Nvs = c->P.volSurfSamples;
+    for (int id = 0; id < w; id++) {
+        HostSampler *smp = w > 1 ? clones[id].get() : c->mainSampler.get();
+        const uint32_t s0 = (uint32_t) (((uint64_t) id * S) / w), s1 = (uint32_t) (((uint64_t) (id + 1) * S) / w);
+        for (uint32_t row = c->rowOffset[s0]; row < c->rowOffset[s1]; row++) {
+            const SegRec &sg = rows[row];
+            uint32_t flags; memcpy(&flags, &sg.dn.w, 4);
+            if (!(flags & SEG_VALID)) continue;
+            const bool surf = !(sg.tE.x == 0 && sg.tE.y == 0 && sg.tE.z == 0) && (flags & SEG_SMOOTH);
+            const int draws = Nvv2 + (surf ? Nvs : 0);
+            for (uint32_t v = 0; v < N; v++) {
+                float *t = &tape[((uint64_t) row * N + v) * K];
+                for (int k = 0; k < draws; k++) t[k] = smp->next1D();
+            }
+        }
+    }
+}
+
+void build_render_lists(alvrl_ctx *c) {
+    if (!c->renderListsDirty) return;
+    const uint32_t S = (uint32_t) c->slices.size();
+    std::vector<uint32_t> slicePixels, repOffset(S + 1, 0);
+    std::vector<uint4> work;
+    std::vector<VrlRec> recs;
+    for (uint32_t s = 0; s < S; s++) {
+        std::vector<uint32_t> px = c->slices[s].pixels;
+        std::sort(px.begin(), px.end());                 /* pixel order inside a slice is free: sort for ray coherence */
+        const uint32_t base = (uint32_t) slicePixels.size();
+        slicePixels.insert(slicePixels.end(), px.begin(), px.end());
+        for (uint32_t o = 0; o < px.size(); o += ALVRL_CTA_SEGS_HOST)
+            work.push_back(make_uint4(s, base + o, std::min<uint32_t>(ALVRL_CTA_SEGS_HOST, (uint32_t) px.size() - o), 0));
+        const std::vector<uint32_t> &vr = c->selectedVrls[s];
+        const std::vector<float> &wt = c->clusterWeight[s];
+        for (size_t i = 0; i < vr.size(); i++) {
+            if (vr[i] >= c->vrlHost.size()) throw Error(ALVRL_ERR_ARG, "cluster representative out of range");
+            VrlRec r = c->vrlHost[vr[i]];
+            r.e.w = wt[i];
+            recs.push_back(r);
+        }
+        repOffset[s + 1] = (uint32_t) recs.size();
+    }
+    c->dSlicePixels.upload(slicePixels, c->stream);
+    c->dWork.upload(work, c->stream);
+    c->dRepOffset.upload(repOffset, c->stream);
+    if (recs.empty()) recs.push_back(VrlRec());
+    c->dRepRecs.upload(recs, c->stream);
+    c->numWork = (uint32_t) work.size();
+    c->renderListsDirty = false;
+}
+
+/* work items restricted to the slice range of this handle (multi-GPU sharding by slice) */
+void select_work(alvrl_ctx *c, const uint4 *&work, uint32_t &numWork, std::vector<uint4> &tmp, DevBuf<uint4> &dTmp) {
+    const uint32_t S = (uint32_t) c->slices.size();
+    const uint32_t sb = std::min(c->sliceBegin, S), se = std::min(c->sliceEnd, S);
+    if (sb == 0 && se == S) { work = c->dWork.p; numWork = c->numWork; return; }
+    std::vector<uint4> all(c->numWork);
+    c->dWork.download(all.data(), c->numWork, c->stream);
+    tmp.clear();
+    for (const uint4 &w : all) if (w.x >= sb && w.x < se) tmp.push_back(w);
+    dTmp.upload(tmp, c->stream);
+    work = dTmp.p; numWork = (uint32_t) tmp.size();
+}
+
+void render_clustered_into(alvrl_ctx *c, float4 *fb, cudaStream_t st) {
+    if (!c->haveClusters) throw Error(ALVRL_ERR_STATE, "build_clusters first");
+    ensure_primary(c);
+    build_render_lists(c);
+    TransportParams T = make_transport_params(c, ALVRL_RNG_RENDER);
+    const uint4 *work; uint32_t numWork; std::vector<uint4> tmp; DevBuf<uint4> dTmp;
+    select_work(c, work, numWork, tmp, dTmp);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+    if (c->mathMode == 1) launch_render_strict(T, true, c->dPixSegs.p, c->dSlicePixels.p, work, numWork, c->dRepRecs.p, c->dRepOffset.p, fb, c->cam.W, c->cam.H, st);
+    else launch_render_fast(T, true, c->dPixSegs.p, c->dSlicePixels.p, work, numWork, c->dRepRecs.p, c->dRepOffset.p, fb, c->cam.W, c->cam.H, st);
+    cudaEventRecord(e1, st);
+    ALVRL_CUDA(cudaGetLastError());
+    ALVRL_CUDA(cudaStreamSynchronize(st));
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    c->stats.msTransportKernelRender = ms;
+    c->stats.kernelLaunches++;
+    uint64_t pairs = 0;
+    const uint32_t S = (uint32_t) c->slices.size(), sb = std::min(c->sliceBegin, S), se = std::min(c->sliceEnd, S);
+    for (uint32_t s = sb; s < se; s++) pairs += (uint64_t) c->slices[s].pixels.size() * c->selectedVrls[s].size();
+    c->stats.pairsRender += pairs;
+    c->stats.shadowRays += pairs * (uint64_t) (c->P.volVolSamples + c->P.volSurfSamples);
+}
+
+} // namespace
+
+extern "C" {
+
+const char *alvrl_last_error(void) { return g_err.c_str(); }
+
+void alvrl_params_default(alvrl_params *p) {
+    memset(p, 0, sizeof(*p));
+    p->shortVrls = 1; p->vrlTargetNum = 500; p->maxParticleDepth = -1; p->specularForcedRRdepth = 100;
+    p->initialSpecularThroughput = 20; p->volVolSamples = 2; p->volSurfSamples = 2; p->globalCluster = 0;
+    p->globalUndersampling = -1; p->localRefinement = 1; p->localUndersampling = -1; p->fallBackUndersampling = 5;
+    p->targetNumSlices = 100; p->targetPixelUndersampling = 64; p->sliceCurvatureFactor = 0.5f;
+    p->neighbourCount = 0; p->neighbourWeight = 0; p->Rsamples = 1; p->depthCorrection = 1; p->maxPasses = 1;
+    p->rngMode = ALVRL_RNG_MODE_COUNTER; p->seed = 0; p->anyHitShadowRays = 1; p->workerCount = 1;
+}
+
+int alvrl_create(int device, const alvrl_params *p, alvrl_handle *out) {
+    if (!p || !out) return fail(ALVRL_ERR_ARG, "null argument");
+    /* the reference's constructor checks (vrlIntegrator.cpp:149-156; Preprocessor.cpp:36-38) */
+    if (p->volVolSamples != 0 && p->volVolSamples < 2) return fail(ALVRL_ERR_ARG, "Need at least 2 volVolSamples for variance estimate");
+    if (p->volSurfSamples != 0 && p->volSurfSamples < 2) return fail(ALVRL_ERR_ARG, "Need at least 2 volSurfSamples for variance estimate");
+    if (p->targetNumSlices < 1) return fail(ALVRL_ERR_ARG, "Invalid target number of slices!");
+    if (p->neighbourWeight > 0) return fail(ALVRL_ERR_UNSUPPORTED, "neighbourWeight > 0 (neighbour slices in L_i) is outside the device path");
+    if (p->Rsamples != 1) return fail(ALVRL_ERR_UNSUPPORTED, "Rsamples != 1 is outside the device path");
+    if (p->depthCorrection != 1) return fail(ALVRL_ERR_UNSUPPORTED, "depthCorrection != 1 (ReplayableSampler pass) is outside the device path");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(ALVRL_ERR_CUDA, std::string("no usable CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU fallback");
+    if (device < 0 || device >= count) return fail(ALVRL_ERR_ARG, "cuda device index out of range");
+    alvrl_ctx *c = nullptr;
+    API_BEGIN
+    c = new alvrl_ctx();
+    c->P = *p; c->device = device;
+    memset(&c->stats, 0, sizeof(c->stats));
+    memset(&c->medium, 0, sizeof(c->medium));
+    memset(&c->cam, 0, sizeof(c->cam));
+    memset(&c->sceneDev, 0, sizeof(c->sceneDev));
+    ALVRL_CUDA(cudaSetDevice(device));
+    ALVRL_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->timer.init();
+    c->mainSampler.reset(new_stream(c->P));
+    const char *mm = getenv("ALVRL_MATH");
+    c->mathMode = (mm && std::string(mm) == "strict") ? 1 : 0;
+    *out = c;
+    API_END
+}
+
+void alvrl_destroy(alvrl_handle c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    c->timer.destroy();
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int alvrl_get_params(alvrl_handle c, alvrl_params *out) { *out = c->P; return ALVRL_OK; }
+int alvrl_set_math_mode(alvrl_handle c, int strict) { c->mathMode = strict ? 1 : 0; return ALVRL_OK; }
+
+int alvrl_set_mesh(alvrl_handle c, const float *v, uint32_t nv, const uint32_t *tris, uint32_t nt, const uint32_t *mat) {
+    API_BEGIN
+    if (!v || !tris || !mat || nt == 0) throw Error(ALVRL_ERR_ARG, "empty mesh");
+    for (size_t i = 0; i < 3 * (size_t) nt; i++) if (tris[i] >= nv) throw Error(ALVRL_ERR_ARG, "triangle index out of range");
+    c->verts.assign(v, v + 3 * (size_t) nv); c->tris.assign(tris, tris + 3 * (size_t) nt); c->triMat.assign(mat, mat + nt);
+    c->haveMesh = true; c->sceneDirty = true; c->havePrimary = false; c->haveSlices = false; invalidate_from_slices(c);
+    API_END
+}
+
+int alvrl_set_materials(alvrl_handle c, const float *albedo, const uint32_t *bits, uint32_t nm) {
+    API_BEGIN
+    use_device(c);
+    c->albedo.assign(albedo, albedo + 3 * (size_t) nm); c->matBits.assign(bits, bits + nm);
+    std::vector<float4> a(nm);
+    for (uint32_t i = 0; i < nm; i++) a[i] = make_float4(albedo[3 * i], albedo[3 * i + 1], albedo[3 * i + 2], 0);
+    c->dMatAlbedo.upload(a, c->stream); c->dMatBits.upload(c->matBits, c->stream);
+    c->haveMat = true; c->segsDirty = true;
+    API_END
+}
+
+int alvrl_set_extra_bounds(alvrl_handle c, const float *p, uint32_t n) {
+    c->extraBounds.assign(p, p + 3 * (size_t) n); c->sceneDirty = true;
+    return ALVRL_OK;
+}
+
+int alvrl_set_medium_homogeneous(alvrl_handle c, const float a[3], const float s[3], float w, int32_t phase, float g) {
+    API_BEGIN
+    MediumDev &m = c->medium;
+    memset(&m, 0, sizeof(m));
+    m.type = 0; m.phaseType = phase; m.g = g;
+    for (int i = 0; i < 3; i++) { m.sigmaS[i] = s[i]; m.sigmaT[i] = a[i] + s[i]; }
+    /* mediumSamplingWeight default, homogeneous.cpp:168-184 */
+    float sw = w;
+    if (sw < 0) {
+        sw = -1;
+        for (int i = 0; i < 3; i++) { float alb = m.sigmaS[i] / m.sigmaT[i]; if (alb > sw && m.sigmaT[i] != 0) sw = alb; }
+        if (sw > 0) sw = std::max(sw, 0.5f);
+    }
+    m.samplingWeight = sw;
+    m.grey = (m.sigmaT[0] == m.sigmaT[1] && m.sigmaT[1] == m.sigmaT[2]) ? 1 : 0;
+    c->haveMedium = true; c->segsDirty = true; c->haveR = false;
+    API_END
+}
+
+int alvrl_set_medium_grid(alvrl_handle c, const float *density, const int32_t res[3], const float mn[3], const float mx[3], float scale,
+                          const float albedo[3], const float sBase[3], int32_t phase, float g) {
+    API_BEGIN
+    use_device(c);
+    if (res[0] < 2 || res[1] < 2 || res[2] < 2) throw Error(ALVRL_ERR_ARG, "grid resolution must be >= 2");
+    MediumDev &m = c->medium;
+    memset(&m, 0, sizeof(m));
+    m.type = 1; m.phaseType = phase; m.g = g; m.scale = scale;
+    const size_t n = (size_t) res[0] * res[1] * res[2];
+    c->dGrid.upload(density, n, c->stream);
+    m.density = c->dGrid.p;
+    m.stepSize = INFINITY;
+    for (int i = 0; i < 3; i++) {
+        m.res[i] = res[i]; m.bmin[i] = mn[i]; m.bmax[i] = mx[i]; m.albedo[i] = albedo[i]; m.sigmaS[i] = sBase[i]; m.sigmaT[i] = 0;
+        const float ext = mx[i] - mn[i];
+        m.gsc[i] = (float) (res[i] - 1) / ext;                         /* gridvolume.cpp:190-196 */
+        m.gtr[i] = m.gsc[i] * (-mn[i]);
+        m.stepSize = std::min(m.stepSize, 0.5f * ext / (float) (res[i] - 1));   /* gridvolume.cpp:197-199 */
+    }
+    c->haveMedium = true; c->segsDirty = true; c->haveR = false;
+    API_END
+}
+
+int alvrl_set_camera(alvrl_handle c, const float s2c[16], const float c2w[16], uint32_t W, uint32_t H, float nearClip, float farClip) {
+    API_BEGIN
+    if (W == 0 || H == 0) throw Error(ALVRL_ERR_ARG, "empty film");
+    memcpy(c->cam.s2c, s2c, 64); memcpy(c->cam.c2w, c2w, 64);
+    c->cam.W = W; c->cam.H = H; c->cam.nearClip = nearClip; c->cam.farClip = farClip;
+    c->cam.invResX = 1.0f / (float) W; c->cam.invResY = 1.0f / (float) H;
+    c->haveCam = true; c->segsDirty = true; c->havePrimary = false; c->haveSlices = false; invalidate_from_slices(c);
+    API_END
+}
+
+int alvrl_set_vrls(alvrl_handle c, const float *s, const float *e, const float *p, uint32_t n, uint64_t particleCount) {
+    API_BEGIN
+    use_device(c);
+    c->vrlHost.clear();
+    const bool noScatter = c->haveMedium && c->medium.sigmaS[0] == 0 && c->medium.sigmaS[1] == 0 && c->medium.sigmaS[2] == 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const float *S = s + 3 * (size_t) i, *E = e + 3 * (size_t) i, *Pw = p + 3 * (size_t) i;
+        for (int k = 0; k < 3; k++)
+            if (!std::isfinite(Pw[k]) || Pw[k] < 0) throw Error(ALVRL_ERR_ARG, "invalid parsed VRL power");   /* VRL.h:51-53 */
+        if (noScatter) continue;                                          /* vrlVector::put, VRL.h:148-158 */
+        if (Pw[0] == 0 && Pw[1] == 0 && Pw[2] == 0) continue;
+        const float dx = E[0] - S[0], dy = E[1] - S[1], dz = E[2] - S[2];
+        const float len = std::sqrt(dx * dx + dy * dy + dz * dz);
+        const float sx = S[0] - E[0], sy = S[1] - E[1], sz = S[2] - E[2];
+        if (std::sqrt(sx * sx + sy * sy + sz * sz) == 0) continue;
+        const float r = 1.0f / len;                                        /* normalize(end - start): recip multiply */
+        VrlRec v;
+        v.s = make_float4(S[0], S[1], S[2], len);
+        v.e = make_float4(E[0], E[1], E[2], 1.0f);
+        v.dir = make_float4(dx * r, dy * r, dz * r, 0);
+        v.power = make_float4(Pw[0], Pw[1], Pw[2], 0);
+        c->vrlHost.push_back(v);
+    }
+    c->particleCount = particleCount ? particleCount : c->vrlHost.size();
+    if (c->vrlHost.empty()) throw Error(ALVRL_ERR_ARG, "no usable VRLs");
+    c->dVrls.upload(c->vrlHost, c->stream);
+    c->haveVrls = true; c->haveR = false; c->haveClusters = false; c->haveFallback = false; c->renderListsDirty = true;
+    c->stats.numVrls = (uint32_t) c->vrlHost.size();
+    API_END
+}
+
+int alvrl_load_vrl_file(alvrl_handle c, const char *path) {
+    std::ifstream f(path);
+    if (!f) return fail(ALVRL_ERR_IO, std::string("cannot open VRL file ") + path);
+    std::vector<float> s, e, p;
+    std::string line;
+    while (std::getline(f, line)) {                                         /* VRL.h:43-54: 9 floats per line */
+        std::stringstream ss(line);
+        float v[9];
+        int k = 0;
+        while (k < 9 && (ss >> v[k])) k++;
+        if (k < 9) break;
+        s.insert(s.end(), v, v + 3); e.insert(e.end(), v + 3, v + 6); p.insert(p.end(), v + 6, v + 9);
+    }
+    return alvrl_set_vrls(c, s.data(), e.data(), p.data(), (uint32_t) (s.size() / 3), 0);    /* m_numParticles = size(), VRL.h:128 */
+}
+
+int alvrl_set_sample_tape(alvrl_handle c, const float *tape, uint64_t n) {
+    API_BEGIN
+    if (!tape) { c->userTape.clear(); }
+    else c->userTape.assign(tape, tape + n);
+    c->haveR = false;
+    API_END
+}
+
+int alvrl_build_slices(alvrl_handle c) {
+    API_BEGIN
+    use_device(c);
+    double t0 = now_ms();
+    ensure_primary(c);
+    const uint32_t P = c->numPixels();
+    std::vector<SegRec> segs(P);
+    c->dPixSegs.download(segs.data(), P, c->stream);
+    /* directionScale, Preprocessor.cpp:1137 (Scene::getAABB diagonal) */
+    const float ax = c->sceneMin[0] - c->sceneMax[0], ay = c->sceneMin[1] - c->sceneMax[1], az = c->sceneMin[2] - c->sceneMax[2];
+    const float directionScale = std::sqrt(ax * ax + ay * ay + az * az) / 8 * c->P.sliceCurvatureFactor;
+    std::vector<P3> pos(P), dir(P);
+    for (uint32_t i = 0; i < P; i++) {
+        const SegRec &s = segs[i];
+        pos[i] = P3{s.p.x, s.p.y, s.p.z};                                  /* NaN for misses, Preprocessor.cpp:1172-1177 */
+        dir[i] = P3{directionScale * s.n.x, directionScale * s.n.y, directionScale * s.n.z};
+    }
+    finish_slices(c, pos, dir);
+    c->stats.msSlices = (float) (now_ms() - t0);
+    API_END
+}
+
+int alvrl_build_slices_from_gather(alvrl_handle c, const float *pos_, const float *dir_) {
+    API_BEGIN
+    if (!c->haveCam) throw Error(ALVRL_ERR_STATE, "set_camera first");
+    const uint32_t P = c->numPixels();
+    std::vector<P3> pos(P), dir(P);
+    for (uint32_t i = 0; i < P; i++) { pos[i] = P3{pos_[3 * i], pos_[3 * i + 1], pos_[3 * i + 2]}; dir[i] = P3{dir_[3 * i], dir_[3 * i + 1], dir_[3 * i + 2]}; }
+    finish_slices(c, pos, dir);
+    API_END
+}
+
+int alvrl_sample_slice_mapping(alvrl_handle c) {
+    API_BEGIN
+    if (!c->haveSlices) throw Error(ALVRL_ERR_STATE, "build_slices first");
+    double t0 = now_ms();
+    const size_t S = c->slices.size();
+    c->rowOffset.assign(S + 1, 0); c->rowPixel.clear(); c->sliceUndersampling.resize(S);
+    size_t totalPix = 0, totalRep = 0;
+    for (size_t i = 0; i < S; i++) {
+        c->mainSampler->setContext(ALVRL_RNG_SLICEMAP, (uint32_t) i, 0);
+        std::vector<uint32_t> px = sampleRepresentativePixels(c->slices[i], c->P.targetPixelUndersampling, c->mainSampler.get());
+        c->rowPixel.insert(c->rowPixel.end(), px.begin(), px.end());
+        c->rowOffset[i + 1] = (uint32_t) c->rowPixel.size();
+        c->sliceUndersampling[i] = ((float) px.size()) / c->slices[i].pixels.size();      /* Preprocessor.cpp:1513 */
+        totalRep += px.size(); totalPix += c->slices[i].pixels.size();
+    }
+    c->globalPixelUndersampling = ((float) totalRep) / totalPix;                          /* 1519 */
+    c->haveRows = true; c->haveR = false; c->haveClusters = false; c->haveFallback = false;
+    c->stats.msSliceMapping = (float) (now_ms() - t0);
+    c->stats.numRows = (uint32_t) c->rowPixel.size();
+    API_END
+}
+
+int alvrl_build_R(alvrl_handle c) {
+    API_BEGIN
+    use_device(c);
+    if (!c->haveRows || !c->haveVrls || !c->haveMedium) throw Error(ALVRL_ERR_STATE, "sample_slice_mapping / set_vrls / set_medium first");
+    double t0 = now_ms();
+    ensure_primary(c);
+    const uint32_t N = (uint32_t) c->vrlHost.size(), G = (uint32_t) c->rowPixel.size(), S = (uint32_t) c->slices.size();
+    c->dRowPixel.upload(c->rowPixel, c->stream);
+    c->dRowSegs.alloc(G);
+    launch_gather_rows(c->dPixSegs.p, c->dRowPixel.p, G, c->dRowSegs.p, c->stream);
+    c->stats.kernelLaunches++;
+    c->ldR = (G + 31u) & ~31u;
+    c->dR.alloc((size_t) N * c->ldR);
+    ALVRL_CUDA(cudaMemsetAsync(c->dR.p, 0, (size_t) N * c->ldR * sizeof(float2), c->stream));
+    TransportParams T = make_transport_params(c, ALVRL_RNG_R);
+    if (!c->userTape.empty()) {
+        if (c->userTape.size() < (uint64_t) G * N * c->K()) throw Error(ALVRL_ERR_ARG, "sample tape too short: need G*N*(2*Nvv+Nvs) floats");
+        c->dTape.upload(c->userTape, c->stream);
+        T.tape = c->dTape.p; T.tapeK = c->K();
+    } else if (c->P.rngMode == ALVRL_RNG_MODE_SFMT) {
+        ALVRL_CUDA(cudaStreamSynchronize(c->stream));
+        std::vector<float> tape;
+        make_sfmt_tape(c, tape);
+        c->dTape.upload(tape, c->stream);
+        T.tape = c->dTape.p; T.tapeK = c->K();
+    }
+    const uint32_t sb = std::min(c->sliceBegin, S), se = std::min(c->sliceEnd, S);
+    const uint32_t r0 = c->rowOffset[sb], r1 = c->rowOffset[se];
+    T.rowBase = r0;
+    c->timer.start(c->stream);
+    if (c->mathMode == 1) launch_build_R_strict(T, c->dRowSegs.p + r0, r1 - r0, c->dVrls.p, c->dR.p + r0, c->ldR, c->stream);
+    else launch_build_R_fast(T, c->dRowSegs.p + r0, r1 - r0, c->dVrls.p, c->dR.p + r0, c->ldR, c->stream);
+    c->stats.msTransportKernelR = c->timer.stop(c->stream);
+    c->stats.kernelLaunches++;
+    ALVRL_CUDA(cudaGetLastError());
+    ALVRL_CUDA(cudaStreamSynchronize(c->stream));
+    c->haveR = true; c->haveClusters = false; c->haveFallback = false;
+    c->stats.pairsPreprocess += (uint64_t) (r1 - r0) * N;
+    c->stats.shadowRays += (uint64_t) (r1 - r0) * N * (uint64_t) (c->P.volVolSamples + c->P.volSurfSamples);
+    c->stats.msBuildR = (float) (now_ms() - t0);
+    API_END
+}
+
+int alvrl_build_clusters(alvrl_handle c) {
+    API_BEGIN
+    use_device(c);
+    if (!c->haveR) throw Error(ALVRL_ERR_STATE, "build_R first");
+    double t0 = now_ms();
+    build_clusters_device(c, c->P.rngMode == ALVRL_RNG_MODE_SFMT);
+    c->haveClusters = true; c->renderListsDirty = true;
+    c->stats.msClusters = (float) (now_ms() - t0);
+    API_END
+}
+
+int alvrl_prepass(alvrl_handle c) {
+    int rc;
+    if ((rc = alvrl_sample_slice_mapping(c))) return rc;
+    if ((rc = alvrl_build_R(c))) return rc;
+    return alvrl_build_clusters(c);
+}
+
+int alvrl_render(alvrl_handle c, float *rgb) {
+    API_BEGIN
+    use_device(c);
+    double t0 = now_ms();
+    const uint32_t P = c->numPixels();
+    c->dFb.alloc(P); c->dRgb.alloc(3 * (size_t) P);
+    ALVRL_CUDA(cudaMemsetAsync(c->dFb.p, 0, (size_t) P * sizeof(float4), c->stream));
+    render_clustered_into(c, c->dFb.p, c->stream);
+    launch_fb_to_rgb(c->dFb.p, c->dRgb.p, P, c->stream);
+    c->stats.kernelLaunches++;
+    c->dRgb.download(rgb, 3 * (size_t) P, c->stream);
+    c->stats.msRender = (float) (now_ms() - t0);
+    API_END
+}
+
+int alvrl_render_unclustered(alvrl_handle c, float *rgb) {
+    API_BEGIN
+    use_device(c);
+    if (!c->haveVrls || !c->haveMedium) throw Error(ALVRL_ERR_STATE, "set_vrls / set_medium first");
+    double t0 = now_ms();
+    ensure_primary(c);
+    const uint32_t P = c->numPixels(), N = (uint32_t) c->vrlHost.size();
+    std::vector<uint32_t> px(P), off = {0, N};
+    std::vector<uint4> work;
+    for (uint32_t i = 0; i < P; i++) px[i] = i;
+    for (uint32_t o = 0; o < P; o += ALVRL_CTA_SEGS_HOST) work.push_back(make_uint4(0, o, std::min<uint32_t>(ALVRL_CTA_SEGS_HOST, P - o), 0));
+    DevBuf<uint32_t> dPx, dOff; DevBuf<uint4> dWork;
+    dPx.upload(px, c->stream); dOff.upload(off, c->stream); dWork.upload(work, c->stream);
+    c->dFb.alloc(P); c->dRgb.alloc(3 * (size_t) P);
+    ALVRL_CUDA(cudaMemsetAsync(c->dFb.p, 0, (size_t) P * sizeof(float4), c->stream));
+    TransportParams T = make_transport_params(c, ALVRL_RNG_RENDER);
+    c->timer.start(c->stream);
+    if (c->mathMode == 1) launch_render_strict(T, false, c->dPixSegs.p, dPx.p, dWork.p, (uint32_t) work.size(), c->dVrls.p, dOff.p, c->dFb.p, c->cam.W, c->cam.H, c->stream);
+    else launch_render_fast(T, false, c->dPixSegs.p, dPx.p, dWork.p, (uint32_t) work.size(), c->dVrls.p, dOff.p, c->dFb.p, c->cam.W, c->cam.H, c->stream);
+    c->stats.msTransportKernelRender = c->timer.stop(c->stream);
+    ALVRL_CUDA(cudaGetLastError());
+    launch_fb_to_rgb(c->dFb.p, c->dRgb.p, P, c->stream);
+    c->stats.kernelLaunches += 2;
+    c->dRgb.download(rgb, 3 * (size_t) P, c->stream);
+    c->stats.pairsRender += (uint64_t) P * N;
+    c->stats.msRender = (float) (now_ms() - t0);
+    API_END
+}
+
+int alvrl_set_slice_range(alvrl_handle c, uint32_t b, uint32_t e) { c->sliceBegin = b; c->sliceEnd = e; return ALVRL_OK; }
+
+int alvrl_render_device(alvrl_handle c, void *rgba, void *stream) {
+    API_BEGIN
+    use_device(c);
+    render_clustered_into(c, (float4 *) rgba, stream ? (cudaStream_t) stream : c->stream);
+    API_END
+}
+
+/* ---- introspection ----------------------------------------------------------------------------- */
+int alvrl_get_stats(alvrl_handle c, alvrl_stats *out) { *out = c->stats; return ALVRL_OK; }
+int alvrl_get_num_vrls(alvrl_handle c, uint32_t *n) { *n = (uint32_t) c->vrlHost.size(); return ALVRL_OK; }
+
+int alvrl_get_primary_hits(alvrl_handle c, uint32_t *prim, float *t, float *p, float *n) {
+    API_BEGIN
+    use_device(c);
+    ensure_primary(c);
+    const uint32_t P = c->numPixels();
+    if (prim) c->dHitPrim.download(prim, P, c->stream);
+    if (t) c->dHitT.download(t, P, c->stream);
+    if (p || n) {
+        std::vector<SegRec> segs(P);
+        c->dPixSegs.download(segs.data(), P, c->stream);
+        for (uint32_t i = 0; i < P; i++) {
+            if (p) { p[3 * i] = segs[i].p.x; p[3 * i + 1] = segs[i].p.y; p[3 * i + 2] = segs[i].p.z; }
+            if (n) { n[3 * i] = segs[i].n.x; n[3 * i + 1] = segs[i].n.y; n[3 * i + 2] = segs[i].n.z; }
+        }
+    }
+    API_END
+}
+
+int alvrl_get_pixel_to_slice(alvrl_handle c, uint32_t *out) {
+    if (!c->haveSlices) return fail(ALVRL_ERR_STATE, "build_slices first");
+    memcpy(out, c->pixelToSlice.data(), c->pixelToSlice.size() * 4);
+    return ALVRL_OK;
+}
+int alvrl_get_num_slices(alvrl_handle c, uint32_t *ns, uint32_t *nr) {
+    *ns = (uint32_t) c->slices.size(); *nr = c->haveRows ? (uint32_t) c->rowPixel.size() : 0;
+    return ALVRL_OK;
+}
+int alvrl_get_rep_pixels(alvrl_handle c, uint32_t *off, uint32_t *px) {
+    if (!c->haveRows) return fail(ALVRL_ERR_STATE, "sample_slice_mapping first");
+    memcpy(off, c->rowOffset.data(), c->rowOffset.size() * 4); memcpy(px, c->rowPixel.data(), c->rowPixel.size() * 4);
+    return ALVRL_OK;
+}
+int alvrl_set_rep_pixels(alvrl_handle c, const uint32_t *off, const uint32_t *px, uint32_t ns) {
+    if (!c->haveSlices || ns != c->slices.size()) return fail(ALVRL_ERR_STATE, "slice count mismatch");
+    c->rowOffset.assign(off, off + ns + 1); c->rowPixel.assign(px, px + off[ns]);
+    c->sliceUndersampling.resize(ns);
+    size_t totalPix = 0;
+    for (uint32_t i = 0; i < ns; i++) {
+        c->sliceUndersampling[i] = ((float) (off[i + 1] - off[i])) / c->slices[i].pixels.size();
+        totalPix += c->slices[i].pixels.size();
+    }
+    c->globalPixelUndersampling = ((float) off[ns]) / totalPix;
+    c->haveRows = true; c->haveR = false; c->haveClusters = false; c->haveFallback = false;
+    c->stats.numRows = off[ns];
+    return ALVRL_OK;
+}
+int alvrl_get_R(alvrl_handle c, uint32_t r0, uint32_t r1, float *mv) {
+    API_BEGIN
+    use_device(c);
+    if (!c->haveR) throw Error(ALVRL_ERR_STATE, "build_R first");
+    const uint32_t N = (uint32_t) c->vrlHost.size();
+    std::vector<float2> col(c->ldR);
+    for (uint32_t v = 0; v < N; v++) {
+        c->dR.download(col.data() + r0, r1 - r0, c->stream, (size_t) v * c->ldR + r0);
+        for (uint32_t r = r0; r < r1; r++) { mv[((size_t) (r - r0) * N + v) * 2] = col[r].x; mv[((size_t) (r - r0) * N + v) * 2 + 1] = col[r].y; }
+    }
+    API_END
+}
+int alvrl_set_R(alvrl_handle c, const float *mv) {
+    API_BEGIN
+    use_device(c);
+    if (!c->haveRows || !c->haveVrls) throw Error(ALVRL_ERR_STATE, "rows / vrls first");
+    const uint32_t N = (uint32_t) c->vrlHost.size(), G = (uint32_t) c->rowPixel.size();
+    c->ldR = (G + 31u) & ~31u;
+    std::vector<float2> t((size_t) N * c->ldR, make_float2(0, 0));
+    for (uint32_t r = 0; r < G; r++)
+        for (uint32_t v = 0; v < N; v++) t[(size_t) v * c->ldR + r] = make_float2(mv[((size_t) r * N + v) * 2], mv[((size_t) r * N + v) * 2 + 1]);
+    c->dR.upload(t, c->stream);
+    c->haveR = true; c->haveClusters = false; c->haveFallback = false;
+    API_END
+}
+int alvrl_get_cluster_counts(alvrl_handle c, uint32_t *off, uint32_t *ng, uint32_t *nf) {
+    API_BEGIN
+    use_device(c);
+    if (!c->haveClusters) throw Error(ALVRL_ERR_STATE, "build_clusters first");
+    if (!c->haveFallback && c->haveR) build_clusters_device(c, true);      /* lazily: global + fallback lists */
+    off[0] = 0;
+    for (size_t i = 0; i < c->selectedVrls.size(); i++) off[i + 1] = off[i] + (uint32_t) c->selectedVrls[i].size();
+    *ng = (uint32_t) c->gcVrls.size(); *nf = (uint32_t) c->fallBackVrls.size();
+    API_END
+}
+int alvrl_get_clusters(alvrl_handle c, uint32_t *vrls, float *weights, uint32_t *gv, float *gw, uint32_t *fv, float *fw) {
+    if (!c->haveClusters) return fail(ALVRL_ERR_STATE, "build_clusters first");
+    size_t o = 0;
+    for (size_t i = 0; i < c->selectedVrls.size(); i++)
+        for (size_t j = 0; j < c->selectedVrls[i].size(); j++, o++) { vrls[o] = c->selectedVrls[i][j]; weights[o] = c->clusterWeight[i][j]; }
+    for (size_t j = 0; j < c->gcVrls.size(); j++) { if (gv) gv[j] = c->gcVrls[j]; if (gw) gw[j] = c->gcWeight[j]; }
+    for (size_t j = 0; j < c->fallBackVrls.size(); j++) { if (fv) fv[j] = c->fallBackVrls[j]; if (fw) fw[j] = c->fallBackWeight[j]; }
+    return ALVRL_OK;
+}
+int alvrl_set_clusters(alvrl_handle c, const uint32_t *off, uint32_t ns, const uint32_t *vrls, const float *weights,
+                       const uint32_t *fv, const float *fw, uint32_t nf) {
+    if (!c->haveSlices || ns != c->slices.size()) return fail(ALVRL_ERR_STATE, "slice count mismatch");
+    c->selectedVrls.assign(ns, {}); c->clusterWeight.assign(ns, {});
+    for (uint32_t i = 0; i < ns; i++) {
+        c->selectedVrls[i].assign(vrls + off[i], vrls + off[i + 1]);
+        c->clusterWeight[i].assign(weights + off[i], weights + off[i + 1]);
+    }
+    c->fallBackVrls.assign(fv, fv + nf); c->fallBackWeight.assign(fw, fw + nf);
+    c->haveClusters = true; c->haveFallback = true; c->renderListsDirty = true;
+    return ALVRL_OK;
+}
+int alvrl_trace_rays(alvrl_handle c, const float *o, const float *d, const float *mint, const float *maxt, uint32_t n, uint32_t *prim, float *t) {
+    API_BEGIN
+    use_device(c);
+    ensure_scene(c);
+    DevBuf<float> dO, dD, dMin, dMax, dT; DevBuf<uint32_t> dP;
+    dO.upload(o, 3 * (size_t) n, c->stream); dD.upload(d, 3 * (size_t) n, c->stream);
+    dMin.upload(mint, n, c->stream); dMax.upload(maxt, n, c->stream); dT.alloc(n); dP.alloc(n);
+    launch_trace_rays(c->sceneDev, dO.p, dD.p, dMin.p, dMax.p, n, dP.p, dT.p, c->stream);
+    c->stats.kernelLaunches++;
+    ALVRL_CUDA(cudaGetLastError());
+    dP.download(prim, n, c->stream);
+    if (t) dT.download(t, n, c->stream);
+    API_END
+}
+int alvrl_eval_transmittance(alvrl_handle c, const float *p1, const int32_t *onSurf, const float *p2, uint32_t n, float *T) {
+    API_BEGIN
+    use_device(c);
+    ensure_scene(c);
+    if (!c->haveMedium) throw Error(ALVRL_ERR_STATE, "set_medium first");
+    DevBuf<float> d1, d2, dT; DevBuf<int32_t> dS;
+    d1.upload(p1, 3 * (size_t) n, c->stream); d2.upload(p2, 3 * (size_t) n, c->stream); dT.alloc(3 * (size_t) n);
+    if (onSurf) dS.upload(onSurf, n, c->stream);
+    launch_eval_transmittance(c->sceneDev, c->medium, d1.p, onSurf ? dS.p : nullptr, d2.p, n, dT.p, c->stream);
+    c->stats.kernelLaunches++;
+    ALVRL_CUDA(cudaGetLastError());
+    dT.download(T, 3 * (size_t) n, c->stream);
+    API_END
+}
+
+} // extern "C"

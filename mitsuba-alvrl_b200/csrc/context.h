@@ -1,0 +1,128 @@
+/*
+ * context.h -- the handle behind the C ABI: host mirror of `vrlIntegrator` + `Preprocessor` + `vrlClusterInfo`
+ * state (vrlIntegrator.cpp:17-115,1085-1122; Preprocessor.cpp:1593-1619) and the device buffers that replace it.
+ */
+#pragma once
+#include <string>
+#include <vector>
+#include <memory>
+#include <stdexcept>
+#include <cuda_runtime.h>
+#include "types.h"
+#include "bvh.h"
+#include "slices.h"
+#include "host_sampler.h"
+
+namespace alvrl {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+
+#define ALVRL_CUDA(call)                                                                                   \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess)                                                                             \
+            throw alvrl::Error(ALVRL_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));       \
+    } while (0)
+
+/* owning device buffer */
+template <typename T> struct DevBuf {
+    T *p = nullptr; size_t n = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void alloc(size_t count) {
+        if (count == n && p) return;
+        release();
+        if (count) ALVRL_CUDA(cudaMalloc((void **) &p, count * sizeof(T)));
+        n = count;
+    }
+    void upload(const T *src, size_t count, cudaStream_t st) {
+        alloc(count);
+        if (count) { ALVRL_CUDA(cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, st)); ALVRL_CUDA(cudaStreamSynchronize(st)); }
+    }
+    void upload(const std::vector<T> &v, cudaStream_t st) { upload(v.data(), v.size(), st); }
+    void download(T *dst, size_t count, cudaStream_t st, size_t offset = 0) const {
+        if (count) { ALVRL_CUDA(cudaMemcpyAsync(dst, p + offset, count * sizeof(T), cudaMemcpyDeviceToHost, st)); ALVRL_CUDA(cudaStreamSynchronize(st)); }
+    }
+};
+
+struct Timer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    void init() { cudaEventCreate(&a); cudaEventCreate(&b); }
+    void destroy() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); a = b = nullptr; }
+    void start(cudaStream_t st) { cudaEventRecord(a, st); }
+    float stop(cudaStream_t st) { cudaEventRecord(b, st); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
+};
+
+} // namespace alvrl
+
+struct alvrl_ctx {
+    alvrl_params P;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    alvrl::Timer timer;
+    alvrl_stats stats;
+    int mathMode = 0;                 /* 0 fast flavour, 1 strict flavour (ALVRL_MATH env / alvrl_set_math_mode) */
+
+    /* scene (host) */
+    std::vector<float> verts; std::vector<uint32_t> tris, triMat;
+    std::vector<float> albedo; std::vector<uint32_t> matBits;
+    std::vector<float> extraBounds;
+    bool haveMesh = false, haveMat = false, haveMedium = false, haveCam = false, haveVrls = false;
+    bool sceneDirty = true, segsDirty = true;
+    float kdMin[3], kdMax[3], sceneMin[3], sceneMax[3];
+    MediumDev medium; CameraDev cam;
+    std::vector<float> gridHost;
+
+    /* scene (device) */
+    alvrl::DevBuf<BvhNode> dNodes; alvrl::DevBuf<TriRec> dTris; alvrl::DevBuf<float4> dTriVerts;
+    alvrl::DevBuf<uint32_t> dTriMat, dMatBits; alvrl::DevBuf<float4> dMatAlbedo; alvrl::DevBuf<float> dGrid;
+    SceneDev sceneDev;
+
+    /* VRLs */
+    std::vector<VrlRec> vrlHost; uint64_t particleCount = 0;
+    alvrl::DevBuf<VrlRec> dVrls;
+
+    /* per pixel (index y + H*x) */
+    alvrl::DevBuf<SegRec> dPixSegs; alvrl::DevBuf<uint32_t> dHitPrim; alvrl::DevBuf<float> dHitT;
+    bool havePrimary = false;
+
+    /* slices / rows */
+    std::vector<uint32_t> pixelToSlice; std::vector<alvrl::SliceInfo> slices; bool haveSlices = false;
+    std::vector<uint32_t> rowOffset, rowPixel; bool haveRows = false;
+    std::vector<float> sliceUndersampling; float globalPixelUndersampling = -1;
+    alvrl::DevBuf<uint32_t> dRowPixel; alvrl::DevBuf<SegRec> dRowSegs;
+    uint32_t sliceBegin = 0, sliceEnd = 0xffffffffu;
+
+    /* R (column-major, see types.h) */
+    alvrl::DevBuf<float2> dR; uint32_t ldR = 0; bool haveR = false;
+    alvrl::DevBuf<float> dTape; uint32_t tapeK = 0; std::vector<float> userTape;
+
+    /* clusters (vrlClusterInfo, vrlIntegrator.cpp:106-112) */
+    std::vector<std::vector<uint32_t>> selectedVrls; std::vector<std::vector<float>> clusterWeight;
+    std::vector<uint32_t> gcVrls, fallBackVrls; std::vector<float> gcWeight, fallBackWeight;
+    bool haveClusters = false, haveFallback = false;
+    std::vector<std::vector<uint32_t>> globalVrlsPerCluster;
+    uint32_t nearTieSplits = 0;
+
+    /* render lists */
+    alvrl::DevBuf<uint32_t> dSlicePixels, dRepOffset; alvrl::DevBuf<uint4> dWork; alvrl::DevBuf<VrlRec> dRepRecs;
+    alvrl::DevBuf<float4> dFb; alvrl::DevBuf<float> dRgb;
+    uint32_t numWork = 0; bool renderListsDirty = true;
+
+    /* sample streams */
+    std::unique_ptr<alvrl::HostSampler> mainSampler;
+
+    uint32_t numPixels() const { return cam.W * cam.H; }
+    uint32_t K() const { return 2 * P.volVolSamples + P.volSurfSamples; }
+};
+
+namespace alvrl {
+/* clustering.cu: Preprocessor::buildClusters on the device (Preprocessor.cpp:133-283) */
+void build_clusters_device(alvrl_ctx *c, bool needFallback);
+}

@@ -1,0 +1,51 @@
+/*
+ * host_test_api.cpp -- exposes the *host-side* logic of the plugin (SFMT stream, slice builder, representative
+ * pixel sampling) through a few C entry points so that `-m "not gpu"` tests can compare it with the oracle on a
+ * machine without a GPU.  Built as libalvrl_host.so by g++; not part of the product path (libalvrl.so links the
+ * same headers directly).
+ */
+#include "slices.h"
+#include "host_sampler.h"
+#include <cstring>
+using namespace alvrl;
+
+extern "C" {
+
+int alvrl_host_sfmt_ulongs(uint64_t seed, uint32_t cloneDepth, uint32_t skip, uint64_t *out, uint32_t n) {
+    Sfmt19937 g(seed);
+    if (cloneDepth == 0) { for (uint32_t i = 0; i < skip; i++) g.next64(); for (uint32_t i = 0; i < n; i++) out[i] = g.next64(); return 0; }
+    for (uint32_t i = 0; i < skip; i++) g.next64();
+    Sfmt19937 child(g);
+    for (uint32_t i = 0; i < n; i++) out[i] = child.next64();
+    return 0;
+}
+int alvrl_host_sfmt_floats(uint64_t seed, float *out, uint32_t n) {
+    SfmtStream s(seed);
+    for (uint32_t i = 0; i < n; i++) out[i] = s.next1D();
+    return 0;
+}
+/* Preprocessor::getSlices + sampleSliceMapping on caller-supplied gather points */
+int alvrl_host_slices(const float *pos, const float *dir, uint32_t n, uint32_t targetNumSlices, float targetUndersampling,
+                      int rngMode, uint64_t seed, uint32_t *pixelToSlice, uint32_t *numSlices, uint32_t *rowOffset /*target+1*/,
+                      uint32_t *rowPixel /*n*/) {
+    std::vector<P3> p(n), d(n);
+    for (uint32_t i = 0; i < n; i++) { p[i] = P3{pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]}; d[i] = P3{dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]}; }
+    std::vector<SliceInfo> slices;
+    SliceTree tree(p, d);
+    std::vector<uint32_t> map = tree.build(targetNumSlices, slices);
+    memcpy(pixelToSlice, map.data(), n * 4);
+    *numSlices = (uint32_t) slices.size();
+    std::unique_ptr<HostSampler> smp(rngMode == ALVRL_RNG_MODE_SFMT ? (HostSampler *) new SfmtStream(seed) : (HostSampler *) new CounterStream(seed));
+    uint32_t rows = 0;
+    rowOffset[0] = 0;
+    for (size_t i = 0; i < slices.size(); i++) {
+        smp->setContext(ALVRL_RNG_SLICEMAP, (uint32_t) i, 0);
+        std::vector<uint32_t> px = sampleRepresentativePixels(slices[i], targetUndersampling, smp.get());
+        memcpy(rowPixel + rows, px.data(), px.size() * 4);
+        rows += (uint32_t) px.size();
+        rowOffset[i + 1] = rows;
+    }
+    return 0;
+}
+
+}

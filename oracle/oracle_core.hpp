@@ -379,7 +379,7 @@ struct Scene {
     }
     /* ShapeKDTree::rayIntersect(ray, its) + fillIntersectionRecord<true> (skdtree.cpp:112-142, skdtree.h:343-428) */
     bool rayIntersect(const Ray &ray, Intersection &its) {
-        Float u, v;
+        Float u = 0, v = 0;
         its = Intersection();
         if (!closestHit(ray, false, its.t, its.prim, u, v, &its.tie)) { its.t = std::numeric_limits<Float>::infinity(); return false; }
         const V3 &p0 = verts[tris[3 * its.prim]], &p1 = verts[tris[3 * its.prim + 1]], &p2 = verts[tris[3 * its.prim + 2]];

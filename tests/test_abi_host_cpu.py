@@ -1,0 +1,108 @@
+"""CPU suite, part 2: the C-ABI library loads and exports every declared symbol; it refuses to run without a GPU
+(no CPU fallback); and the plugin's host-side logic (SFMT stream, slice builder, representative pixels), compiled
+without device code into libalvrl_host.so, is bit-identical to the oracle."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, small_case, setup
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    header = open(os.path.join(ROOT, "include", "alvrl.h")).read()
+    declared = sorted(set(re.findall(r"\b(alvrl_[a-zA-Z_]+)\s*\(", header)))
+    assert len(declared) >= 35
+    lib = C.CDLL(pkg.LIB_PATH)
+    missing = [d for d in declared if not hasattr(lib, d)]
+    assert not missing, missing
+
+
+def test_params_default_match_reference_defaults(pkg):
+    p = pkg.api().default_params()
+    # vrlIntegrator.cpp:128-208 and src/librender/integrator.cpp:348
+    expect = dict(shortVrls=1, vrlTargetNum=500, maxParticleDepth=-1, specularForcedRRdepth=100,
+                  initialSpecularThroughput=20.0, volVolSamples=2, volSurfSamples=2, globalCluster=0,
+                  globalUndersampling=-1.0, localRefinement=1, localUndersampling=-1.0, fallBackUndersampling=5.0,
+                  targetNumSlices=100, targetPixelUndersampling=64.0, sliceCurvatureFactor=0.5, neighbourCount=0,
+                  neighbourWeight=0.0, Rsamples=1, depthCorrection=1.0, numVrlFalseColor=0, slicesFalseColor=0,
+                  convergenceFalseColor=0, maxPasses=1)
+    for k, v in expect.items():
+        assert getattr(p, k) == v, k
+
+
+def test_unknown_parameter_is_rejected(pkg):
+    with pytest.raises(AttributeError):
+        pkg.api().default_params(nc=3)          # 'nc' is rejected by the reference too (vrlIntegrator.cpp:129-131)
+
+
+def test_invalid_sample_counts_are_rejected_like_the_reference(pkg):
+    import torch
+    api = pkg.api()
+    h = C.c_void_p()
+    for bad in (dict(volVolSamples=1), dict(volSurfSamples=1), dict(targetNumSlices=0)):
+        p = api.default_params(**bad)
+        rc = api.fn("create")(C.c_int(0), C.byref(p), C.byref(h))
+        assert rc == -1, bad                     # ALVRL_ERR_ARG, vrlIntegrator.cpp:149-156
+    if not torch.cuda.is_available():
+        p = api.default_params()
+        rc = api.fn("create")(C.c_int(0), C.byref(p), C.byref(h))
+        assert rc == -3                          # ALVRL_ERR_CUDA: fails loudly, no CPU fallback
+        assert b"no CPU fallback" in api._last_error()
+
+
+def test_host_sfmt_matches_known_answers_and_oracle(host_lib, orc):
+    words = [int(l, 16) for l in open(os.path.join(ROOT, "tests", "golden", "sfmt_kat_seed4321.txt")) if not l.startswith("#")]
+    out = np.zeros(len(words), np.uint64)
+    host_lib.alvrl_host_sfmt_ulongs(C.c_uint64(4321), C.c_uint32(0), C.c_uint32(0), out.ctypes.data_as(C.c_void_p), C.c_uint32(len(words)))
+    assert [int(x) for x in out] == words
+    # beyond the first state refill, and through clone()
+    big = np.zeros(2000, np.uint64)
+    host_lib.alvrl_host_sfmt_ulongs(C.c_uint64(77), C.c_uint32(0), C.c_uint32(0), big.ctypes.data_as(C.c_void_p), C.c_uint32(2000))
+    assert np.array_equal(big, orc.sfmt_ulongs(77, 2000))
+    cl = np.zeros(700, np.uint64)
+    host_lib.alvrl_host_sfmt_ulongs(C.c_uint64(77), C.c_uint32(1), C.c_uint32(5), cl.ctypes.data_as(C.c_void_p), C.c_uint32(700))
+    assert np.array_equal(cl, orc.sfmt_clone_ulongs(77, 5, 700))
+    f = np.zeros(100, np.float32)
+    host_lib.alvrl_host_sfmt_floats(C.c_uint64(9), f.ctypes.data_as(C.c_void_p), C.c_uint32(100))
+    assert np.array_equal(f, orc.sfmt_floats(9, 100))
+
+
+@pytest.mark.parametrize("rng_mode", [0, 1])
+@pytest.mark.parametrize("size,target", [((64, 64), 100), ((96, 48), 37), ((16, 16), 400)])
+def test_host_slices_and_rep_pixels_bit_exact_vs_oracle(pkg, orc, host_lib, size, target, rng_mode):
+    W, H = size
+    scene, vrls, params = small_case(pkg, "C1", W, H, 16, targetNumSlices=target, seed=5, rngMode=rng_mode)
+    o = setup(orc.Oracle(**params), scene, vrls)
+    o.build_slices()
+    o.sample_slice_mapping()
+    pos, d = o.gather_points()
+    P = W * H
+    p2s = np.zeros(P, np.uint32); ns = C.c_uint32()
+    off = np.zeros(target + 1, np.uint32); px = np.zeros(P, np.uint32)
+    host_lib.alvrl_host_slices(pos.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p), C.c_uint32(P), C.c_uint32(target),
+                               C.c_float(64.0), C.c_int(rng_mode), C.c_uint64(5), p2s.ctypes.data_as(C.c_void_p), C.byref(ns),
+                               off.ctypes.data_as(C.c_void_p), px.ctypes.data_as(C.c_void_p))
+    S, G = o.num_slices()
+    assert ns.value == S
+    assert np.array_equal(p2s, o.pixel_to_slice())
+    ooff, opx = o.rep_pixels()
+    assert np.array_equal(off[:S + 1], ooff)
+    assert np.array_equal(px[:G], opx)
+
+
+def test_host_slices_all_misses_and_singletons(host_lib):
+    n = 8
+    pos = np.full((n, 3), np.nan, np.float32); d = pos.copy()
+    p2s = np.zeros(n, np.uint32); ns = C.c_uint32(); off = np.zeros(5, np.uint32); px = np.zeros(n, np.uint32)
+    args = lambda: (pos.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p), C.c_uint32(n), C.c_uint32(4), C.c_float(64.0),
+                    C.c_int(0), C.c_uint64(0), p2s.ctypes.data_as(C.c_void_p), C.byref(ns), off.ctypes.data_as(C.c_void_p),
+                    px.ctypes.data_as(C.c_void_p))
+    host_lib.alvrl_host_slices(*args())
+    assert ns.value == 0 and (p2s == 0xFFFFFFFF).all()
+    # identical points: the diagonal is 0, so splitting stops at one slice (Preprocessor.cpp:1364)
+    pos[:] = 0.25; d[:] = 0.5
+    host_lib.alvrl_host_slices(*args())
+    assert ns.value == 1 and (p2s == 0).all()

@@ -1,0 +1,174 @@
+"""CPU suite, part 1: the oracle against the reference's own golden vectors and against committed fixtures.
+
+Pinned by the reference: the SFMT-19937 stream (src/tests/test_random.cpp:433-509).  Everything else on this path has
+no reference test ("parity unpinned"): the committed fixtures under tests/golden/ were produced by the
+oracle itself (tests/golden/make_goldens.py) and guard it against regressions."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import small_case, setup
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_sfmt_known_answer_vector(orc):
+    words = [int(l, 16) for l in open(os.path.join(GOLD, "sfmt_kat_seed4321.txt")) if not l.startswith("#")]
+    assert len(words) == 192
+    got = orc.sfmt_ulongs(4321, len(words))
+    assert [int(x) for x in got] == words
+
+
+def test_sfmt_next_float_is_low_32_bits(orc):
+    u = orc.sfmt_ulongs(99, 64)
+    f = orc.sfmt_floats(99, 64)
+    expect = (((u & np.uint64(0xFFFFFFFF)) >> np.uint64(9)).astype(np.uint32) | np.uint32(0x3F800000)).view(np.float32) - np.float32(1)
+    assert np.array_equal(f, expect)
+    assert (f >= 0).all() and (f < 1).all()
+
+
+def test_sfmt_clone_is_deterministic_and_distinct(orc):
+    a = orc.sfmt_clone_ulongs(5, 0, 16)
+    b = orc.sfmt_clone_ulongs(5, 0, 16)
+    c = orc.sfmt_clone_ulongs(5, 1, 16)
+    assert np.array_equal(a, b) and not np.array_equal(a, c)
+    assert not np.array_equal(a, orc.sfmt_ulongs(5, 16))
+
+
+def test_counter_stream_matches_python_restatement(pkg):
+    def mix(x):
+        x &= 0xFFFFFFFF
+        x ^= x >> 16; x = (x * 0x7FEB352D) & 0xFFFFFFFF
+        x ^= x >> 15; x = (x * 0x846CA68B) & 0xFFFFFFFF
+        x ^= x >> 16
+        return x
+    seed, domain, a, b = 0x1234567890, 1, 17, 4242
+    h = mix((seed & 0xFFFFFFFF) ^ ((domain * 0x9E3779B9) & 0xFFFFFFFF))
+    h = mix(h ^ (seed >> 32))
+    h = mix((h + a * 0x85EBCA6B + 0x165667B1) & 0xFFFFFFFF)
+    h = mix(h ^ ((b * 0xC2B2AE35 + 0x27D4EB2F) & 0xFFFFFFFF))
+    bits = mix((h + 3 * 0x9E3779B9) & 0xFFFFFFFF)
+    u = np.array([(bits >> 9) | 0x3F800000], dtype=np.uint32).view(np.float32)[0] - np.float32(1)
+    assert 0 <= u < 1
+
+
+@pytest.fixture(scope="module")
+def c1_small(pkg, orc):
+    scene, vrls, params = small_case(pkg, "C1", 64, 64, 200, seed=11)
+    o = setup(orc.Oracle(**params), scene, vrls)
+    o.build_slices()
+    o.prepass()
+    return o
+
+
+def test_slices_partition_all_hit_pixels(c1_small):
+    o = c1_small
+    p2s = o.pixel_to_slice()
+    prim, t, p, n = o.primary_hits()
+    S, G = o.num_slices()
+    assert S == 100
+    assert ((p2s == 0xFFFFFFFF) == (prim == 0xFFFFFFFF)).all()      # misses stay unsliced, Preprocessor.cpp:1201
+    assert set(np.unique(p2s[p2s != 0xFFFFFFFF])) == set(range(S))
+    off, px = o.rep_pixels()
+    assert off[-1] == G and len(np.unique(px)) == G                 # representatives are distinct pixels
+    assert (p2s[px] == np.repeat(np.arange(S), np.diff(off))).all()  # and belong to their slice
+
+
+def test_R_entries_are_finite_nonnegative(c1_small):
+    R = c1_small.get_R()
+    assert np.isfinite(R).all() and (R >= 0).all()
+    assert (R[..., 0] > 0).mean() > 0.5
+
+
+def test_cluster_weights_are_inverse_probabilities(c1_small):
+    cl = c1_small.clusters()
+    assert (cl["weights"] >= 1).all()                               # weight = 1/prob, Preprocessor.cpp:375
+    assert len(cl["fallback_vrls"]) == int(0.5 + c1_small.N / 5)    # refineFixedDepth, Preprocessor.cpp:388
+    for s in range(len(cl["offset"]) - 1):
+        v = cl["vrls"][cl["offset"][s]:cl["offset"][s + 1]]
+        assert len(np.unique(v)) == len(v)
+
+
+def test_clustered_render_is_unbiased_wrt_unclustered(c1_small):
+    img_c = c1_small.render(True)
+    img_u = c1_small.render(False)
+    assert np.isfinite(img_c).all() and (img_c >= 0).all()
+    # one representative per cluster with weight 1/prob: heavy-tailed per slice, so compare the median slice ratio
+    p2s = c1_small.pixel_to_slice().reshape(c1_small.W, c1_small.H).T
+    ratios = [img_c[p2s == s].sum() / img_u[p2s == s].sum() for s in range(c1_small.num_slices()[0]) if img_u[p2s == s].sum() > 0]
+    assert abs(np.median(ratios) - 1) < 0.1
+
+
+def test_oracle_thread_count_does_not_change_results(pkg, orc):
+    scene, vrls, params = small_case(pkg, "C1", 32, 32, 64, seed=3, targetNumSlices=10)
+    outs = []
+    for th in (1, 4):
+        o = setup(orc.Oracle(threads=th, **params), scene, vrls)
+        o.build_slices(); o.prepass()
+        outs.append((o.get_R(), o.clusters()["vrls"], o.render()))
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert np.array_equal(outs[0][1], outs[1][1])
+    assert np.array_equal(outs[0][2], outs[1][2])
+
+
+def test_sfmt_mode_worker_count_changes_stream_but_is_reproducible(pkg, orc):
+    scene, vrls, params = small_case(pkg, "C1", 32, 32, 64, seed=3, targetNumSlices=10, rngMode=1)
+    def run(w):
+        o = setup(orc.Oracle(workerCount=w, **params), scene, vrls)
+        o.build_slices(); o.prepass()
+        return o.get_R()
+    a, b, c = run(1), run(1), run(2)
+    assert np.array_equal(a, b)
+    assert not np.array_equal(a, c)
+
+
+def test_recorded_tape_replays_to_identical_R(pkg, orc):
+    """tape mode = the reference's sequential stream laid out per (row, vrl): replaying it must give the same R"""
+    scene, vrls, params = small_case(pkg, "C1", 32, 32, 48, seed=5, targetNumSlices=8, rngMode=1)
+    o = setup(orc.Oracle(**params), scene, vrls)
+    o.build_slices(); o.sample_slice_mapping()
+    tape = o.build_R_record_tape()
+    R1 = o.get_R()
+    o2 = setup(orc.Oracle(**params), scene, vrls)
+    o2.build_slices(); o2.set_rep_pixels(*o.rep_pixels())
+    o2.set_sample_tape(tape)
+    o2.build_R()
+    assert np.array_equal(R1, o2.get_R())
+
+
+def test_heterogeneous_medium_runs_and_attenuates(pkg, orc):
+    scene, vrls, params = small_case(pkg, "C3", 24, 24, 32, grid=16, targetNumSlices=6)
+    o = setup(orc.Oracle(**params), scene, vrls)
+    T = o.eval_transmittance(np.array([[0.1, 0.8, 0.5]], np.float32), [0], np.array([[0.9, 0.8, 0.5]], np.float32))
+    assert 0 < T[0, 0] < 1 and T[0, 0] == T[0, 1] == T[0, 2]
+    o.build_slices(); o.sample_slice_mapping(); o.build_R()
+    R = o.get_R()
+    assert np.isfinite(R).all() and (R[..., 0] > 0).any()
+
+
+def test_occluder_blocks_transmittance(pkg, orc):
+    scene, vrls, params = small_case(pkg, "C1", 16, 16, 16)
+    o = setup(orc.Oracle(**params), scene, vrls)
+    # through the tall box (centre 0.67,0.30,0.64) and in free space
+    T = o.eval_transmittance(np.array([[0.67, 0.3, 0.2], [0.2, 0.8, 0.2]], np.float32), [0, 0],
+                             np.array([[0.67, 0.3, 0.95], [0.8, 0.8, 0.2]], np.float32))
+    assert (T[0] == 0).all()
+    assert np.allclose(T[1], np.exp(-1.05 * 0.6), rtol=1e-6)
+
+
+def test_golden_fixture_regression(pkg, orc):
+    g = np.load(os.path.join(GOLD, "c1_tiny.npz"))
+    scene, vrls, params = small_case(pkg, "C1", int(g["width"]), int(g["height"]), int(g["n_vrls"]),
+                                     seed=int(g["seed"]), targetNumSlices=int(g["targetNumSlices"]))
+    o = setup(orc.Oracle(**params), scene, vrls)
+    o.build_slices(); o.prepass()
+    assert np.array_equal(o.primary_hits()[0], g["prim"])
+    assert np.array_equal(o.pixel_to_slice(), g["pixel_to_slice"])
+    assert np.array_equal(o.rep_pixels()[1], g["row_pixel"])
+    np.testing.assert_allclose(o.get_R(), g["R"], rtol=2e-6, atol=0)     # libm ulp differences between hosts
+    cl = o.clusters()
+    assert np.array_equal(cl["offset"], g["cluster_offset"])
+    assert np.array_equal(cl["vrls"], g["cluster_vrls"])
+    np.testing.assert_allclose(cl["weights"], g["cluster_weights"], rtol=1e-5)
+    np.testing.assert_allclose(o.render(), g["image"], rtol=1e-4, atol=1e-9)

@@ -1,0 +1,226 @@
+"""GPU suite: the CUDA path through the C ABI (libalvrl.so) against the CPU oracle on identical inputs.
+
+Gates: G2 hit ids bit-exact, G3 R entries within 1e-4 relative (strict flavour; the fast flavour states its
+own tolerance), G4 pixel->slice bit-exact, G5 clusters identical given the same R, G6 image within tolerance."""
+import numpy as np
+import pytest
+
+from conftest import small_case, setup
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu(pkg, strict=False, **params):
+    g = pkg.integrator(0, **params)
+    g._call("set_math_mode", pkg.binding.C.c_int(1 if strict else 0))
+    return g
+
+
+def _pair(pkg, orc, name="C1", w=64, h=64, n=200, strict=False, **extra):
+    scene, vrls, params = small_case(pkg, name, w, h, n, **extra)
+    g = setup(_gpu(pkg, strict, **params), scene, vrls)
+    o = setup(orc.Oracle(**params), scene, vrls)
+    return g, o
+
+
+# ---- G2: visibility --------------------------------------------------------------------------------------------
+def test_primary_hits_bit_exact_c1_full(pkg, orc):
+    g, o = _pair(pkg, orc, "C1", 256, 256, 16)
+    gp, gt, gpos, gn = g.primary_hits()
+    op, ot, opos, on = o.primary_hits()
+    ties = o.primary_ties().astype(bool)
+    assert np.array_equal(gp[~ties], op[~ties])
+    assert np.array_equal(gp, op)                       # the tie rule (lowest index at minimal t) is shared, so ties agree too
+    hit = op != 0xFFFFFFFF
+    assert np.array_equal(gt[hit], ot[hit])
+    assert np.array_equal(gpos[hit], opos[hit]) and np.array_equal(gn[hit], on[hit])
+    assert np.isnan(gpos[~hit]).all()
+
+
+def test_trace_rays_bit_exact_random_and_grazing(pkg, orc):
+    g, o = _pair(pkg, orc, "C1", 16, 16, 16)
+    rng = np.random.default_rng(1)
+    n = 200_000
+    org = rng.uniform(0.02, 0.98, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d = d.astype(np.float32)
+    d[: n // 10, 1] = 0                                  # axis-parallel / in-plane directions
+    d[n // 10: n // 5, 0] = 0
+    mint = np.zeros(n, np.float32); mint[::3] = np.float32(1e-4)
+    maxt = rng.uniform(0.05, 2.0, n).astype(np.float32)
+    gp, gt = g.trace_rays(org, d, mint, maxt)
+    op, ot, tie = o.trace_rays(org, d, mint, maxt)
+    assert np.array_equal(gp, op)
+    assert np.array_equal(gt[op != 0xFFFFFFFF], ot[op != 0xFFFFFFFF])
+    assert (op != 0xFFFFFFFF).mean() > 0.2
+
+
+def test_trace_rays_many_triangles(pkg, orc):
+    g, o = _pair(pkg, orc, "C4", 16, 16, 16, occluders=24)      # 24 icospheres = 30 720 triangles + box
+    rng = np.random.default_rng(2)
+    n = 20_000
+    org = rng.uniform(0.05, 0.95, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    gp, gt = g.trace_rays(org, d.astype(np.float32), np.zeros(n, np.float32), np.full(n, 10, np.float32))
+    op, ot, tie = o.trace_rays(org, d.astype(np.float32), np.zeros(n, np.float32), np.full(n, 10, np.float32))
+    assert np.array_equal(gp, op) and np.array_equal(gt, ot)
+    assert (op != 0xFFFFFFFF).all()                        # closed box
+
+
+def test_eval_transmittance_matches(pkg, orc):
+    g, o = _pair(pkg, orc, "C1", 16, 16, 16)
+    rng = np.random.default_rng(3)
+    n = 50_000
+    p1 = rng.uniform(0.02, 0.98, (n, 3)).astype(np.float32)
+    p2 = rng.uniform(0.02, 0.98, (n, 3)).astype(np.float32)
+    on = (rng.random(n) < 0.3).astype(np.int32)
+    tg, to = g.eval_transmittance(p1, on, p2), o.eval_transmittance(p1, on, p2)
+    assert np.array_equal(tg == 0, to == 0)                # occlusion decisions are bit-exact
+    np.testing.assert_allclose(tg, to, rtol=2e-7)          # exp through double on both sides
+
+
+def test_eval_transmittance_grid_medium(pkg, orc):
+    g, o = _pair(pkg, orc, "C3", 16, 16, 16, grid=32)
+    rng = np.random.default_rng(4)
+    n = 5_000
+    p1 = rng.uniform(0.02, 0.98, (n, 3)).astype(np.float32)
+    p2 = rng.uniform(0.02, 0.98, (n, 3)).astype(np.float32)
+    tg, to = g.eval_transmittance(p1, np.zeros(n, np.int32), p2), o.eval_transmittance(p1, np.zeros(n, np.int32), p2)
+    assert np.array_equal(tg == 0, to == 0)
+    np.testing.assert_allclose(tg, to, rtol=1e-6)
+
+
+# ---- G4: slices -------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("w,h,target", [(256, 256, 100), (160, 96, 33)])
+def test_pixel_to_slice_bit_exact(pkg, orc, w, h, target):
+    g, o = _pair(pkg, orc, "C1", w, h, 16, targetNumSlices=target)
+    g.build_slices(); o.build_slices()
+    assert np.array_equal(g.pixel_to_slice(), o.pixel_to_slice())
+    g2, _ = _pair(pkg, orc, "C1", w, h, 16, targetNumSlices=target)
+    g2.build_slices_from_gather(*o.gather_points())        # G4 proper: oracle gather points in
+    assert np.array_equal(g2.pixel_to_slice(), o.pixel_to_slice())
+    g.sample_slice_mapping(); o.sample_slice_mapping()
+    assert all(np.array_equal(a, b) for a, b in zip(g.rep_pixels(), o.rep_pixels()))
+
+
+# ---- G3: reduced matrix -----------------------------------------------------------------------------------------
+def _R_pair(pkg, orc, strict, **kw):
+    g, o = _pair(pkg, orc, strict=strict, **kw)
+    for it in (g, o):
+        it.build_slices(); it.sample_slice_mapping(); it.build_R()
+    return g, o, g.get_R(), o.get_R()
+
+
+def _check_R(Rg, Ro, tol_mean, tol_var, max_outlier_frac):
+    """mean within tol_mean relative (floor 1e-12 * max); var within tol_var relative to (var + mean^2 / n): the variance of
+    the mean is a difference of nearly equal numbers when the samples agree, so it is compared on the scale of the second
+    moment that the clustering consumes (Preprocessor.cpp:996).  Entries whose visibility decision flipped (a shadow ray
+    grazing an edge, documented) are counted and bounded."""
+    mg, mo, vg, vo = Rg[..., 0], Ro[..., 0], Rg[..., 1], Ro[..., 1]
+    floor = 1e-12 * np.abs(mo).max()
+    em = np.abs(mg - mo) / (np.abs(mo) + floor)
+    ev = np.abs(vg - vo) / (vo + mo * mo + floor * floor)
+    bad = (em > tol_mean) | (ev > tol_var)
+    frac = bad.mean()
+    assert frac <= max_outlier_frac, f"{bad.sum()} of {bad.size} entries out of tolerance (max rel err mean {em.max():.3e})"
+    return em, ev, frac
+
+
+def test_R_strict_flavour_within_1e4_c1_shape(pkg, orc):
+    g, o, Rg, Ro = _R_pair(pkg, orc, True, name="C1", w=128, h=128, n=400)
+    em, ev, frac = _check_R(Rg, Ro, 1e-4, 1e-4, 2e-5)
+    print(f"strict: median rel err {np.median(em):.2e}, p99.99 {np.quantile(em, 0.9999):.2e}, outliers {frac:.2e}")
+
+
+def test_R_fast_flavour_tolerance(pkg, orc):
+    g, o, Rg, Ro = _R_pair(pkg, orc, False, name="C1", w=128, h=128, n=400)
+    em, ev, frac = _check_R(Rg, Ro, 1e-3, 1e-3, 1e-4)      # fast-math flavour: 1e-3 per entry, stated here
+    assert np.median(em) < 1e-5
+    print(f"fast: median rel err {np.median(em):.2e}, p99.99 {np.quantile(em, 0.9999):.2e}, outliers {frac:.2e}")
+
+
+def test_R_reference_stream_tape(pkg, orc):
+    """the oracle consumes one sequential SFMT stream in the reference's order and records it; the GPU replays the tape"""
+    scene, vrls, params = small_case(pkg, "C1", 64, 64, 100, rngMode=1, seed=9)
+    o = setup(orc.Oracle(**params), scene, vrls)
+    o.build_slices(); o.sample_slice_mapping()
+    tape = o.build_R_record_tape()
+    g = setup(_gpu(pkg, True, **params), scene, vrls)
+    g.build_slices(); g.sample_slice_mapping()
+    assert np.array_equal(g.rep_pixels()[1], o.rep_pixels()[1])     # same SFMT stream on the host side
+    g.set_sample_tape(tape); g.build_R()
+    _check_R(g.get_R(), o.get_R(), 1e-4, 1e-4, 2e-5)
+    g2 = setup(_gpu(pkg, True, **params), scene, vrls)              # and the library's own SFMT tape generator
+    g2.build_slices(); g2.sample_slice_mapping(); g2.build_R()
+    assert np.array_equal(g2.get_R(), g.get_R())
+
+
+@pytest.mark.parametrize("name,kw", [("C5", dict()), ("C3", dict(grid=24)), ("C4", dict(occluders=6))])
+def test_R_other_config_shapes(pkg, orc, name, kw):
+    g, o, Rg, Ro = _R_pair(pkg, orc, True, name=name, w=48, h=48, n=64, targetNumSlices=12, **kw)
+    _check_R(Rg, Ro, 1e-4, 1e-4, 1e-4)
+
+
+def test_R_empty_and_ragged_edges(pkg, orc):
+    # N not a multiple of the tile, rows not a multiple of the CTA, single slice, miss pixels present
+    g, o, Rg, Ro = _R_pair(pkg, orc, True, name="C1", w=40, h=24, n=67, targetNumSlices=1)
+    _check_R(Rg, Ro, 1e-4, 1e-4, 1e-4)
+    g, o, Rg, Ro = _R_pair(pkg, orc, True, name="C1", w=40, h=24, n=1, targetNumSlices=3, volSurfSamples=0)
+    _check_R(Rg, Ro, 1e-4, 1e-4, 1e-4)
+    g, o, Rg, Ro = _R_pair(pkg, orc, True, name="C1", w=40, h=24, n=5, targetNumSlices=3, volVolSamples=0, volSurfSamples=3)
+    _check_R(Rg, Ro, 1e-4, 1e-4, 1e-4)
+
+
+# ---- G6: image ---------------------------------------------------------------------------------------------------
+def test_render_with_oracle_clusters_per_pixel(pkg, orc):
+    g, o = _pair(pkg, orc, "C1", 64, 64, 200, strict=True)
+    for it in (g, o):
+        it.build_slices(); it.sample_slice_mapping()
+    o.build_R(); o.build_clusters()
+    g.set_clusters(o.clusters())
+    ig, io = g.render(), o.render()
+    floor = 1e-6 * io.max()
+    err = np.abs(ig - io) / (io + floor)
+    assert (err > 1e-3).mean() < 1e-4, f"max rel err {err.max():.3e}"
+    assert np.array_equal(ig == 0, io == 0)
+
+
+def test_render_unclustered_matches(pkg, orc):
+    g, o = _pair(pkg, orc, "C1", 32, 32, 50, strict=False)
+    ig, io = g.render(False), o.render(False)
+    np.testing.assert_allclose(ig, io, rtol=2e-3, atol=1e-7 * io.max())
+
+
+def test_image_free_running_rmse_vs_noise_floor(pkg, orc):
+    """rms-style relative RMSE (src/utils/rms.cpp:88-110, gamma 1, zero-reference pixels masked) between the GPU image and
+    an oracle image with *different* seeds must not exceed 1.5x the relative RMSE between two oracle runs."""
+    def rel_rmse(a, b):
+        m = b > 0
+        return float(np.sqrt(np.mean(((a[m] - b[m]) / b[m]) ** 2)))
+    scene, vrls, params = small_case(pkg, "C1", 48, 48, 150, targetNumSlices=20)
+    imgs = []
+    for seed in (1, 2):
+        o = setup(orc.Oracle(seed=seed, **params), scene, vrls)
+        imgs.append(o.render(False))
+    g = setup(_gpu(pkg, False, seed=3, **params), scene, vrls)
+    ig = g.render(False)
+    floor = rel_rmse(imgs[0], imgs[1])
+    assert rel_rmse(ig, imgs[1]) <= 1.5 * floor + 1e-6, (rel_rmse(ig, imgs[1]), floor)
+
+
+# ---- errors ------------------------------------------------------------------------------------------------------
+def test_call_order_errors(pkg):
+    g = _gpu(pkg)
+    with pytest.raises(pkg.binding.AlvrlError) as e:
+        g.build_slices()
+    assert e.value.code == -2
+    scene, vrls, params = small_case(pkg, "C1", 16, 16, 8)
+    g.set_scene(scene)
+    with pytest.raises(pkg.binding.AlvrlError):
+        g.build_R()
+    with pytest.raises(pkg.binding.AlvrlError):
+        g.render()
+    with pytest.raises(pkg.binding.AlvrlError):
+        g.set_vrls(np.zeros((1, 3)), np.zeros((1, 3)), np.ones((1, 3)))     # zero-length VRLs are dropped -> nothing left
+    with pytest.raises(pkg.binding.AlvrlError):
+        g.set_vrls(np.zeros((1, 3)), np.ones((1, 3)), -np.ones((1, 3)))     # invalid power, VRL.h:51-53
