@@ -35,8 +35,8 @@ template <typename T> struct DevBuf {
     DevBuf &operator=(const DevBuf &) = delete;
     ~DevBuf() { release(); }
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
-    void alloc(size_t count) {
-        if (count == n && p) return;
+    void alloc(size_t count) {                     /* n is a capacity: buffers only grow */
+        if (count <= n && p) return;
         release();
         if (count) ALVRL_CUDA(cudaMalloc((void **) &p, count * sizeof(T)));
         n = count;
@@ -117,6 +117,7 @@ struct alvrl_ctx {
 
     /* sample streams */
     std::unique_ptr<alvrl::HostSampler> mainSampler;
+    std::unique_ptr<alvrl::HostSampler> globalStream;   /* counter mode: the (CLUSTER, GLOBAL_ID) stream, kept for the lazy fallback */
 
     uint32_t numPixels() const { return cam.W * cam.H; }
     uint32_t K() const { return 2 * P.volVolSamples + P.volSurfSamples; }

@@ -44,10 +44,11 @@ __device__ __forceinline__ float m_exp(float x) { return exp_ref(x); }
 __device__ __forceinline__ float m_rcp(float x) { return 1.0f / x; }
 __device__ __forceinline__ float m_div(float a, float b) { return a / b; }
 __device__ __forceinline__ float m_sqrt(float x) { return sqrtf(x); }
-__device__ __forceinline__ float m_atan(float x) { return atanf(x); }
-__device__ __forceinline__ float m_tan(float x) { return tanf(x); }
-__device__ __forceinline__ float m_sinh(float x) { return sinhf(x); }
-__device__ __forceinline__ float m_asinh(float x) { return asinhf(x); }
+/* correctly rounded through double, like the oracle pins them (libm version of the reference is unpinned) */
+__device__ __forceinline__ float m_atan(float x) { return (float) atan((double) x); }
+__device__ __forceinline__ float m_tan(float x) { return (float) tan((double) x); }
+__device__ __forceinline__ float m_sinh(float x) { return (float) sinh((double) x); }
+__device__ __forceinline__ float m_asinh(float x) { return (float) asinh((double) x); }
 #endif
 
 __device__ __forceinline__ float m_len(const F3 &a) { return m_sqrt(len2(a)); }

@@ -62,6 +62,12 @@ inline Float distanceSquared(const V3 &a, const V3 &b) { return (a - b).lengthSq
 inline Float safe_sqrt(Float v) { return std::sqrt(std::max((Float) 0, v)); }          // math.h:260-267
 inline double safe_sqrt(double v) { return std::sqrt(std::max(0.0, v)); }
 inline Float fastexp(Float v) { return (Float) ::exp((double) v); }                        // math.h:185-187
+/* asinh / sinh / atan / tan: the reference calls the libm overloads of whatever glibc the build host has (version
+ * unpinned, results differ by an ulp between versions).  The oracle pins them to the correctly rounded value. */
+inline Float o_asinh(Float v) { return (Float) ::asinh((double) v); }
+inline Float o_sinh(Float v) { return (Float) ::sinh((double) v); }
+inline Float o_atan(Float v) { return (Float) ::atan((double) v); }
+inline Float o_tan(Float v) { return (Float) ::tan((double) v); }
 
 /* ---- include/mitsuba/core/spectrum.h (RGB, SPECTRUM_SAMPLES = 3) ------------------------ */
 struct Spec {
@@ -618,7 +624,7 @@ struct IntegratorCore {
         S2h = S2P0 + tc * (S2P1 - S2P0);
         return dP.length();
     }
-    static Float A(Float x, Float h, Float sinTheta) { return asinhf((x / h) * sinTheta); }   // 955-957
+    static Float A(Float x, Float h, Float sinTheta) { return o_asinh((x / h) * sinTheta); }   // 955-957
     /* vrlIntegrator.cpp:916-953 */
     static Float sampleVtoDistance(const Ray &eyeRay, const V3 &itsP, const VRL &vrl, V3 &V, Float uniform) {
         if (distance(vrl.start, vrl.end) == 0) { V = vrl.start; return 1; }
@@ -632,7 +638,7 @@ struct IntegratorCore {
         Float h = getClosestPoints(eyeRay.o, itsP, vrl.start, vrl.end, Uh, Vh);
         Float V0c = -1 * distance(Vh, vrl.start);
         Float V1c = distance(Vh, vrl.end);
-        Float newV = h * sinhf(A(V0c, h, sinTheta) + (uniform * (A(V1c, h, sinTheta) - A(V0c, h, sinTheta))));
+        Float newV = h * o_sinh(A(V0c, h, sinTheta) + (uniform * (A(V1c, h, sinTheta) - A(V0c, h, sinTheta))));
         newV = newV / sinTheta;
         Float result = 1.0f / std::sqrt(h * h + newV * newV * sinTheta * sinTheta);
         Float denom = (A(V1c, h, sinTheta) - A(V0c, h, sinTheta)) / sinTheta;
@@ -646,14 +652,14 @@ struct IntegratorCore {
         Float dotPr = dot(dir, D - Apt);
         V3 I = Apt + (dotPr * dir);
         Float Dis = distance(D, I);
-        Float angle_a = atanf(distance(Apt, I) / Dis);
-        Float angle_b = atanf(distance(I, B) / Dis);
+        Float angle_a = o_atan(distance(Apt, I) / Dis);
+        Float angle_b = o_atan(distance(I, B) / Dis);
         if (dotPr > 0) {
             angle_a *= -1;
             if (distance(Apt, I) > distance(Apt, B)) angle_b *= -1;
         }
         Float uniform = sampler->next1D();
-        Float t = Dis * tanf(((1.0f - uniform) * angle_a) + (uniform * angle_b));
+        Float t = Dis * o_tan(((1.0f - uniform) * angle_a) + (uniform * angle_b));
         Float pdf = Dis / ((angle_b - angle_a) * (Dis * Dis + t * t));
         result = I + (t * dir);
         return pdf;
