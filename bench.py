@@ -1,0 +1,298 @@
+"""bench.py -- headline benchmark of the VRL hot path (BASELINE.json: VRL-segment contributions/s + 1024^2 frame time).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port) on the host cores
+
+One "step" = one frame of the hot path on synthetic input (config C2 of BASELINE.json: Cornell box, homogeneous
+isotropic medium, 1024x1024, 100k VRLs, volVolSamples = volSurfSamples = 4):
+    Preprocessor::buildSlices -> sampleSliceMapping -> "Building R" -> buildClusters -> clustered render of every pixel
+`value`  : integrateVRL evaluations (R entries + clustered render terms, the reference's own StatsCounter unit) per second,
+           whole job, VRL set / BVH / medium resident in HBM when the timed region starts, framebuffer left on the device.
+`e2e`    : the same metric through the C ABI with HOST buffers: every step uploads the VRL set (alvrl_set_vrls from host
+           arrays) and reads the W x H x 3 float image back (alvrl_render into a host buffer).
+Multi-GPU: slices are sharded over the ranks (VRLs, BVH, medium replicated); the only exchanges are an N-byte all-reduce
+of the zero / non-zero column flags and the framebuffer reduce over NCCL.  Total work is fixed -> "scaling": "strong".
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def flops_per_pair(nvv, nvs, hg):
+    """algorithmic flops of one integrateVRL call, traversal excluded."""
+    return 160 + (158 if hg else 136) * nvv + (102 if hg else 91) * nvs
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(self.rows)}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C2")
+    ap.add_argument("--width", type=int, default=None)
+    ap.add_argument("--height", type=int, default=None)
+    ap.add_argument("--vrls", type=int, default=None)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the bounded cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload(pkg, a):
+    scene, vrls, params = pkg.scenes.make_config(a.config, width=a.width, height=a.height, n_vrls=a.vrls)
+    cfg = pkg.scenes.CONFIGS[a.config]
+    W, H = scene["camera"]["width"], scene["camera"]["height"]
+    desc = {"workload": f"{a.config}: Cornell box, homogeneous isotropic medium, {W}x{H}, {len(vrls[0])} VRLs, "
+                        f"volVolSamples={params['volVolSamples']}, volSurfSamples={params['volSurfSamples']}",
+            "slices": params.get("targetNumSlices", 100), "pixel_undersampling": 64,
+            "l2_note": "inputs larger than L2: R alone is rows x VRLs x 8 B (13.1 GB at C2) and is rewritten every step"}
+    hg = cfg.get("hg") is not None
+    return scene, vrls, params, desc, hg
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_baseline(pkg, scene, vrls, params, hg, seconds, full_desc):
+    """The reference's CPU algorithm (oracle port, -O3 + the reference's -funsafe-math-optimizations) on a bounded sample
+    of the same workload with all host threads: R rows of a few slices x all VRLs."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import orc  # the CPU oracle: allowed here (cpu_baseline / --impl reference legs only)
+    cores = os.cpu_count() or 1
+    o = orc.Oracle(fast=True, threads=cores, **params)
+    o.set_scene(scene)
+    o.set_vrls(*vrls)
+    o.build_slices()
+    o.sample_slice_mapping()
+    S, G = o.num_slices()
+    # calibrate: time one slice, then take as many slices as fit the budget
+    off, _ = o.rep_pixels()
+    o.set_slice_range(0, 1)
+    t0 = time.perf_counter()
+    o.build_R()
+    t1 = time.perf_counter() - t0
+    pairs1 = int(off[1] - off[0]) * o.N
+    rate = pairs1 / t1
+    n_slices = int(max(1, min(S, seconds * rate / max(1, (G / S) * o.N))))
+    o.set_slice_range(0, n_slices)
+    t0 = time.perf_counter()
+    o.build_R()
+    dt = time.perf_counter() - t0
+    pairs = int(off[n_slices] - off[0]) * o.N
+    return {"value": pairs / dt, "unit": "VRL-segment contributions/s", "cores": cores, "kind": "port",
+            "sample": f"R rows of slices [0,{n_slices}) = {int(off[n_slices])} rows x {o.N} VRLs ({pairs:.3e} integrateVRL calls) "
+                      f"of {full_desc}; oracle port built -O3 -march=x86-64-v3 -funsafe-math-optimizations, {cores} threads, {dt:.1f} s"}, dt
+
+
+def run_reference(a):
+    """--impl reference: the reference's own CPU implementation of the path.  The reference cannot be built in this image
+    (Boost/Xerces-C/OpenEXR/SCons missing), so this is the oracle port, with all host threads, on bounded
+    samples of the same workload.  Under torchrun only rank 0 works."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import alvrl_loader
+    pkg = alvrl_loader.load()
+    scene, vrls, params, desc, hg = workload(pkg, a)
+    vals, times = [], []
+    base = None
+    budget = max(2.0, min(a.cpu_seconds, 150.0 / max(1, a.steps + a.warmup)))
+    for i in range(a.warmup + a.steps):
+        base, dt = cpu_baseline(pkg, scene, vrls, params, hg, budget, desc["workload"])
+        if i >= a.warmup:
+            vals.append(base["value"]); times.append(dt)
+    v = float(np.mean(vals))
+    base["value"] = v
+    line = {"impl": "reference", "metric": "vrl_segment_contributions_per_s", "value": v, "unit": "VRL-segment contributions/s",
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": float(np.mean(times)) * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": desc, "cpu_baseline": base,
+            "e2e": {"value": v, "unit": "VRL-segment contributions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    import alvrl_loader
+    pkg = alvrl_loader.load()
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    multi = world > 1
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if multi:
+        dist.init_process_group("nccl", device_id=dev)
+
+    scene, vrls, params, desc, hg = workload(pkg, a)
+    g = pkg.integrator(local, **params)
+    g.set_scene(scene)
+    g.set_vrls(*vrls)
+    W, H, N = g.W, g.H, g.N
+    fb = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
+    host_img = None
+
+    def barrier():
+        torch.cuda.synchronize()
+        if multi:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def frame(e2e):
+        """one step; returns (#integrateVRL evaluations of this rank, transport-kernel ms of this rank)"""
+        nonlocal host_img
+        s0 = g.stats()
+        if e2e:
+            g.set_vrls(*vrls)                                    # host -> device: the step's input (VRL set)
+        g.build_slices()
+        S, _ = g.num_slices()
+        if multi:
+            g.set_slice_range(S * rank // world, S * (rank + 1) // world)
+        g.sample_slice_mapping()
+        g.build_R()
+        if multi:                                                # zero / non-zero columns over ALL rows: OR across ranks
+            fl = torch.from_numpy(g.column_nonzero()).to(dev)
+            dist.all_reduce(fl, op=dist.ReduceOp.MAX)
+            g.set_column_nonzero(fl.cpu().numpy())
+        g.build_clusters()
+        if e2e and not multi:
+            host_img = g.render()                                # device -> host: the step's result (image)
+        else:
+            fb.zero_()
+            torch.cuda.synchronize()
+            g.render_device(fb.data_ptr())
+            if multi:
+                dist.reduce(fb, dst=0, op=dist.ReduceOp.SUM)     # framebuffer gather over NCCL / NVLink
+            if e2e and rank == 0:
+                host_img = fb[..., :3].contiguous().cpu().numpy()
+        s1 = g.stats()
+        pairs = (s1.pairsPreprocess - s0.pairsPreprocess) + (s1.pairsRender - s0.pairsRender)
+        return pairs, s1.msTransportKernelR, s1.msTransportKernelRender, s1.pairsPreprocess - s0.pairsPreprocess, \
+            s1.kernelLaunches - s0.kernelLaunches, s1
+
+    def timed(e2e, steps):
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        tot_pairs = tot_launch = 0
+        kr, kp, kpairs = [], [], []
+        last = None
+        for _ in range(steps):
+            p, msr, msp, rp, nl, last = frame(e2e)
+            tot_pairs += p; tot_launch += nl
+            kr.append(msr); kp.append(msp); kpairs.append(rp)
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        t = torch.tensor([ms, float(tot_pairs), float(tot_launch)], dtype=torch.float64, device=dev)
+        if multi:
+            tm = t.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            ts = t.clone(); dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+            ms, tot_pairs, tot_launch = float(tm[0]), float(ts[1]), float(ts[2])
+        return ms, tot_pairs, tot_launch, kr, kp, kpairs, last
+
+    for _ in range(max(3, a.warmup)):
+        frame(False)
+    clocks = ClockSampler(local)
+    clocks.start()
+    ms, pairs, launches, kr, kp, kpairs, st = timed(False, a.steps)
+    clk = clocks.finish()
+    ms_e, pairs_e, _, _, _, _, _ = timed(True, a.steps)
+
+    # roofline of the dominant kernel (k_build_R_fast): algorithmic flops per launch / CUDA-event duration of that launch,
+    # measured inside the library on the launching stream (alvrl_stats.msTransportKernelR)
+    F = flops_per_pair(params["volVolSamples"], params["volSurfSamples"], hg)
+    k_ms = float(np.mean(kr))
+    k_pairs = float(np.mean(kpairs))
+    peak = pkg.binding.C.c_float()
+    pkg.api().lib.alvrl_measure_fp32_peak(pkg.binding.C.c_int(local), pkg.binding.C.byref(peak))
+    achieved = k_pairs * F / (k_ms * 1e-3) / 1e12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    roof = {"bound": "fp32", "kernel": "k_build_R_fast<homogeneous>", "achieved": achieved, "peak": float(peak.value), "unit": "TFLOP/s",
+            "frac": achieved / float(peak.value) if peak.value else None, "traffic": None,
+            "peak_source": "FP32 FFMA microbenchmark measured live on this device (alvrl_measure_fp32_peak); north_star names the "
+                           "non-tensor FP32 roofline for this kernel (no dense contraction, tensor cores unused); nominal 148 SM x 128 x 2 x 1.965 GHz = 74.5",
+            "flops_per_contribution": F, "contributions_per_launch": k_pairs, "launch_ms": k_ms,
+            "contributions_per_s_kernel": k_pairs / (k_ms * 1e-3),
+            "hbm": {"algorithmic_bytes_per_launch": k_pairs * 8, "achieved_gbs": k_pairs * 8 / (k_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                    "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
+
+    if rank == 0:
+        line = {"metric": "vrl_segment_contributions_per_s", "value": pairs / (ms * 1e-3), "unit": "VRL-segment contributions/s",
+                "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup), "ms_per_step": ms / a.steps, "frame_time_ms": ms / a.steps,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": dict(desc, parallelism=f"slice-sharded x{world}"),
+                "e2e": {"value": pairs_e / (ms_e * 1e-3), "unit": "VRL-segment contributions/s", "ms_per_step": ms_e / a.steps,
+                        "h2d_bytes_per_step": int(N * 9 * 4), "d2h_bytes_per_step": int(W * H * 3 * 4)},
+                "gpu_launches": int(launches), "clocks": clk, "roofline": roof,
+                "phases_ms": {"slices": st.msSlices, "slice_mapping": st.msSliceMapping, "build_R": st.msBuildR, "clusters": st.msClusters,
+                              "render_kernel": st.msTransportKernelRender},
+                "contributions_per_step": pairs / a.steps, "rows": st.numRows, "vrls": st.numVrls, "slices": st.numSlices}
+        if not a.no_cpu_baseline and world == 1:
+            line["cpu_baseline"], _ = cpu_baseline(pkg, scene, vrls, params, hg, a.cpu_seconds, desc["workload"])
+        print(json.dumps(line))
+    if multi:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

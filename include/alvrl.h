@@ -142,6 +142,12 @@ int alvrl_sample_slice_mapping(alvrl_handle h);
 /* "Building R": prepass loops + Rbuilder + getLiLuminanceVrlContributions + getVRLContributions
  * (vrlIntegrator.cpp:302-337,527-539,792-825,1038-1083). */
 int alvrl_build_R(alvrl_handle h);
+/* Multi-GPU exchange step of buildClusters: Preprocessor::cluster() splits the VRLs into zero / non-zero columns over
+ * ALL rows of R (Preprocessor.cpp:846-855,936-945).  With rows sharded by slice each rank computes its local flags
+ * (get), the ranks combine them with a logical OR (e.g. ncclAllReduce MAX on N bytes) and hand the result back (set)
+ * before build_clusters.  Without a set call the local flags are used (single GPU). */
+int alvrl_get_column_nonzero(alvrl_handle h, uint8_t *flags /*N*/);
+int alvrl_set_column_nonzero(alvrl_handle h, const uint8_t *flags /*N, NULL clears*/);
 /* Preprocessor::buildClusters (Preprocessor.cpp:133-283). */
 int alvrl_build_clusters(alvrl_handle h);
 /* vrlIntegrator::prepass = the three calls above (vrlIntegrator.cpp:270-356). */
@@ -159,6 +165,8 @@ int alvrl_render_device(alvrl_handle h, void *rgba_device, void *cuda_stream);
 
 /* ---- results / introspection (tests, multi-GPU exchange) -------------------------------- */
 int alvrl_get_stats(alvrl_handle h, alvrl_stats *out);
+/* sustained FP32 FFMA rate of the device measured by a register-resident microbenchmark (roofline denominator) */
+int alvrl_measure_fp32_peak(int cuda_device, float *tflops);
 int alvrl_get_num_vrls(alvrl_handle h, uint32_t *n);          /* vrlVector::size() after the put() filter */
 int alvrl_get_primary_hits(alvrl_handle h, uint32_t *prim /*P*/, float *t /*P*/, float *p_xyz /*3P*/, float *n_xyz /*3P*/);
 int alvrl_get_pixel_to_slice(alvrl_handle h, uint32_t *out /*P*/);

@@ -203,6 +203,22 @@ class Integrator:
     def build_R(self):
         self._call("build_R")
 
+    def column_nonzero(self):
+        out = np.zeros(self.N, np.uint8)
+        self._call("get_column_nonzero", _p(out))
+        return out
+
+    def set_column_nonzero(self, flags):
+        if flags is None:
+            self._call("set_column_nonzero", None)
+        else:
+            f = np.ascontiguousarray(flags, dtype=np.uint8)
+            self._call("set_column_nonzero", _p(f))
+
+    def render_device(self, fb_ptr, stream_ptr=0):
+        """fb_ptr: device pointer of a zero-initialised W*H*4 float32 framebuffer owned by the caller"""
+        self._call("render_device", C.c_void_p(fb_ptr), C.c_void_p(stream_ptr))
+
     def build_clusters(self):
         self._call("build_clusters")
 

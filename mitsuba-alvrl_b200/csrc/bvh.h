@@ -143,4 +143,23 @@ inline TriRec makeTriRec(const float *A, const float *B, const float *C, uint32_
     return r;
 }
 
+/* plane + barycentric functionals of a triangle (double precision set-up, stored as float) */
+inline TriFast makeTriFast(const float *A, const float *B, const float *C) {
+    const double e1[3] = {(double) B[0] - A[0], (double) B[1] - A[1], (double) B[2] - A[2]};
+    const double e2[3] = {(double) C[0] - A[0], (double) C[1] - A[1], (double) C[2] - A[2]};
+    const double N[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+    const double n2 = N[0] * N[0] + N[1] * N[1] + N[2] * N[2];
+    TriFast t;
+    if (!(n2 > 0)) { t.p = make_float4(0, 0, 0, 1); t.q = make_float4(0, 0, 0, -1); t.r = make_float4(0, 0, 0, -1); return t; }
+    const double inv = 1.0 / std::sqrt(n2);
+    const double n[3] = {N[0] * inv, N[1] * inv, N[2] * inv};
+    /* u (weight of B) = dot(P - A, e2 x N) / |N|^2, v (weight of C) = dot(P - A, N x e1) / |N|^2 */
+    const double eu[3] = {(e2[1] * N[2] - e2[2] * N[1]) / n2, (e2[2] * N[0] - e2[0] * N[2]) / n2, (e2[0] * N[1] - e2[1] * N[0]) / n2};
+    const double ev[3] = {(N[1] * e1[2] - N[2] * e1[1]) / n2, (N[2] * e1[0] - N[0] * e1[2]) / n2, (N[0] * e1[1] - N[1] * e1[0]) / n2};
+    t.p = make_float4((float) n[0], (float) n[1], (float) n[2], (float) (n[0] * A[0] + n[1] * A[1] + n[2] * A[2]));
+    t.q = make_float4((float) eu[0], (float) eu[1], (float) eu[2], (float) -(eu[0] * A[0] + eu[1] * A[1] + eu[2] * A[2]));
+    t.r = make_float4((float) ev[0], (float) ev[1], (float) ev[2], (float) -(ev[0] * A[0] + ev[1] * A[1] + ev[2] * A[2]));
+    return t;
+}
+
 } // namespace alvrl

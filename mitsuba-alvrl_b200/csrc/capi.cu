@@ -46,6 +46,7 @@ void ensure_scene(alvrl_ctx *c) {
     HostBvh bvh;
     BvhBuilder(c->verts.data(), c->tris.data(), nt).build(bvh);
     std::vector<TriRec> recs(nt);
+    std::vector<TriFast> fast(nt);
     std::vector<float4> tv(3 * (size_t) nt);
     float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (uint32_t i = 0; i < nt; i++) {
@@ -53,6 +54,7 @@ void ensure_scene(alvrl_ctx *c) {
         const float *A = &c->verts[3 * (size_t) c->tris[3 * (size_t) t]], *B = &c->verts[3 * (size_t) c->tris[3 * (size_t) t + 1]],
                     *C = &c->verts[3 * (size_t) c->tris[3 * (size_t) t + 2]];
         recs[i] = makeTriRec(A, B, C, t);
+        fast[i] = makeTriFast(A, B, C);
         tv[3 * (size_t) t] = make_float4(A[0], A[1], A[2], 0); tv[3 * (size_t) t + 1] = make_float4(B[0], B[1], B[2], 0);
         tv[3 * (size_t) t + 2] = make_float4(C[0], C[1], C[2], 0);
         for (int k = 0; k < 3; k++) { mn[k] = std::min(mn[k], std::min(A[k], std::min(B[k], C[k]))); mx[k] = std::max(mx[k], std::max(A[k], std::max(B[k], C[k]))); }
@@ -67,10 +69,11 @@ void ensure_scene(alvrl_ctx *c) {
         for (int k = 0; k < 3; k++) { c->sceneMin[k] = std::min(c->sceneMin[k], c->extraBounds[i + k]); c->sceneMax[k] = std::max(c->sceneMax[k], c->extraBounds[i + k]); }
     c->dNodes.upload(bvh.nodes, c->stream);
     c->dTris.upload(recs, c->stream);
+    c->dTrisFast.upload(fast, c->stream);
     c->dTriVerts.upload(tv, c->stream);
     c->dTriMat.upload(c->triMat, c->stream);
     SceneDev &s = c->sceneDev;
-    s.nodes = c->dNodes.p; s.tris = c->dTris.p; s.numNodes = (uint32_t) bvh.nodes.size();
+    s.nodes = c->dNodes.p; s.tris = c->dTris.p; s.trisFast = c->dTrisFast.p; s.numNodes = (uint32_t) bvh.nodes.size();
     for (int k = 0; k < 3; k++) { s.kdMin[k] = c->kdMin[k]; s.kdMax[k] = c->kdMax[k]; }
     s.anyHit = c->P.anyHitShadowRays ? 1 : 0;
     c->stats.bvhNodes = s.numNodes;
@@ -499,6 +502,28 @@ int alvrl_build_R(alvrl_handle c) {
     c->stats.pairsPreprocess += (uint64_t) (r1 - r0) * N;
     c->stats.shadowRays += (uint64_t) (r1 - r0) * N * (uint64_t) (c->P.volVolSamples + c->P.volSurfSamples);
     c->stats.msBuildR = (float) (now_ms() - t0);
+    API_END
+}
+
+int alvrl_get_column_nonzero(alvrl_handle c, uint8_t *flags) {
+    API_BEGIN
+    use_device(c);
+    if (!c->haveR) throw Error(ALVRL_ERR_STATE, "build_R first");
+    std::vector<uint8_t> f;
+    column_nonzero_device(c, f);
+    memcpy(flags, f.data(), f.size());
+    API_END
+}
+int alvrl_set_column_nonzero(alvrl_handle c, const uint8_t *flags) {
+    if (!flags) { c->columnFlagsOverride.clear(); return ALVRL_OK; }
+    c->columnFlagsOverride.assign(flags, flags + c->vrlHost.size());
+    return ALVRL_OK;
+}
+int alvrl_measure_fp32_peak(int device, float *tflops) {
+    API_BEGIN
+    ALVRL_CUDA(cudaSetDevice(device));
+    *tflops = measure_fp32_peak_tflops();
+    ALVRL_CUDA(cudaGetLastError());
     API_END
 }
 

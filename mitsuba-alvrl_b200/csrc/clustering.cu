@@ -611,6 +611,51 @@ struct Workspace {
 
 } // namespace
 
+void column_nonzero_device(alvrl_ctx *c, std::vector<uint8_t> &flags) {
+    const uint32_t N = (uint32_t) c->vrlHost.size(), G = (uint32_t) c->rowPixel.size();
+    DevBuf<uint8_t> dNz; dNz.alloc(N);
+    k_total_contribution<<<(N + 127) / 128, 128, 0, c->stream>>>(c->dR.p, c->ldR, G, N, dNz.p);
+    c->stats.kernelLaunches++;
+    ALVRL_CUDA(cudaGetLastError());
+    flags.resize(N);
+    dNz.download(flags.data(), N, c->stream);
+}
+
+/* register-resident FFMA chains: 8 independent accumulators per thread, all SMs full */
+__global__ void k_ffma_peak(float *out, int iters) {
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const float m = 0.999f, b = 1e-3f;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            a0 = fmaf(a0, m, b); a1 = fmaf(a1, m, b); a2 = fmaf(a2, m, b); a3 = fmaf(a3, m, b);
+            a4 = fmaf(a4, m, b); a5 = fmaf(a5, m, b); a6 = fmaf(a6, m, b); a7 = fmaf(a7, m, b);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+float measure_fp32_peak_tflops() {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int blocks = sms * 8, threads = 256, iters = 4096;
+    float *d = nullptr;
+    if (cudaMalloc(&d, (size_t) blocks * threads * sizeof(float)) != cudaSuccess) return 0;
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    k_ffma_peak<<<blocks, threads>>>(d, 64);
+    float best = 0;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(a);
+        k_ffma_peak<<<blocks, threads>>>(d, iters);
+        cudaEventRecord(b); cudaEventSynchronize(b);
+        float ms = 0; cudaEventElapsedTime(&ms, a, b);
+        const double flops = 2.0 * 64.0 * iters * (double) blocks * threads;
+        best = std::max(best, (float) (flops / (ms * 1e-3) / 1e12));
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d);
+    return best;
+}
+
 void build_clusters_device(alvrl_ctx *c, bool needFallback) {
     const uint32_t N = (uint32_t) c->vrlHost.size(), G = (uint32_t) c->rowPixel.size(), S = (uint32_t) c->slices.size();
     if (c->globalPixelUndersampling < 0) throw Error(ALVRL_ERR_STATE, "Invalid pixel undersampling. Did you forget to call buildSlices first?");
@@ -634,12 +679,9 @@ void build_clusters_device(alvrl_ctx *c, bool needFallback) {
 
     if (!lazyFallbackCall) {
         /* cluster(), 838-898: zero / non-zero columns over all rows */
-        DevBuf<uint8_t> dNz; dNz.alloc(N);
-        k_total_contribution<<<(N + 127) / 128, 128, 0, st>>>(c->dR.p, c->ldR, G, N, dNz.p);
-        c->stats.kernelLaunches++;
-        ALVRL_CUDA(cudaGetLastError());
-        std::vector<uint8_t> nz(N);
-        dNz.download(nz.data(), N, st);
+        std::vector<uint8_t> nz;
+        if (c->columnFlagsOverride.size() == N) nz = c->columnFlagsOverride;
+        else column_nonzero_device(c, nz);
         std::vector<uint32_t> nonZero, zero;
         for (uint32_t i = 0; i < N; i++) (nz[i] ? nonZero : zero).push_back(i);
         c->globalVrlsPerCluster.clear();

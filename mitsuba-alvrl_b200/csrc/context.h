@@ -80,7 +80,7 @@ struct alvrl_ctx {
     std::vector<float> gridHost;
 
     /* scene (device) */
-    alvrl::DevBuf<BvhNode> dNodes; alvrl::DevBuf<TriRec> dTris; alvrl::DevBuf<float4> dTriVerts;
+    alvrl::DevBuf<BvhNode> dNodes; alvrl::DevBuf<TriRec> dTris; alvrl::DevBuf<TriFast> dTrisFast; alvrl::DevBuf<float4> dTriVerts;
     alvrl::DevBuf<uint32_t> dTriMat, dMatBits; alvrl::DevBuf<float4> dMatAlbedo; alvrl::DevBuf<float> dGrid;
     SceneDev sceneDev;
 
@@ -109,6 +109,7 @@ struct alvrl_ctx {
     bool haveClusters = false, haveFallback = false;
     std::vector<std::vector<uint32_t>> globalVrlsPerCluster;
     uint32_t nearTieSplits = 0;
+    std::vector<uint8_t> columnFlagsOverride;     /* all-reduced zero / non-zero column flags (multi-GPU) */
 
     /* render lists */
     alvrl::DevBuf<uint32_t> dSlicePixels, dRepOffset; alvrl::DevBuf<uint4> dWork; alvrl::DevBuf<VrlRec> dRepRecs;
@@ -126,4 +127,6 @@ struct alvrl_ctx {
 namespace alvrl {
 /* clustering.cu: Preprocessor::buildClusters on the device (Preprocessor.cpp:133-283) */
 void build_clusters_device(alvrl_ctx *c, bool needFallback);
+void column_nonzero_device(alvrl_ctx *c, std::vector<uint8_t> &flags);
+float measure_fp32_peak_tflops();
 }

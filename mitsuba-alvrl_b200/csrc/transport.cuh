@@ -96,8 +96,22 @@ __device__ __forceinline__ void medium_eval(const MediumDev &m, const F3 &o, con
 template <int MED>
 __device__ __forceinline__ bool eval_transmittance(const TransportParams &P, const F3 &p1, bool onSurf, const F3 &p2, float T[3]) {
     F3 dir; float remaining;
+#ifdef ALVRL_FAST
+    {
+        const F3 dd = p2 - p1;
+        const float l2 = len2(dd);
+        const float il = rsqrtf(l2);
+        remaining = l2 * il;
+        dir = dd * il;
+        if (!(remaining > 0)) { T[0] = T[1] = T[2] = 1; return true; }
+        /* adaptive epsilon of the shadow-ray overload, skdtree.cpp:154-157 */
+        const float mint = onSurf ? ALVRL_EPSILON * fmaxf(fmaxf(fabsf(p1.x), fabsf(p1.y)), fabsf(p1.z)) : 0.0f;
+        if (remaining > mint && bvh_occluded_fast(P.scene, p1, dir, mint, remaining)) { T[0] = T[1] = T[2] = 0; return false; }
+    }
+#else
     if (segment_occluded(P.scene, p1, onSurf, p2, dir, remaining)) { T[0] = T[1] = T[2] = 0; return false; }
     if (!(remaining > 0)) { T[0] = T[1] = T[2] = 1; return true; }
+#endif
     if (MED == 0) {
         const float negLength = 0.0f - remaining;                          /* homogeneous.cpp:266-273 */
 #pragma unroll

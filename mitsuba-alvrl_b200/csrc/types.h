@@ -58,6 +58,10 @@ struct TriRec {
     float4 c;      /* c_nu, c_nv, __int_as_float(original triangle index), 0 */
 };
 
+/* fast-flavour triangle: plane + barycentric functionals, no axis switch.
+ *   t = (p.w - dot(p.xyz, o)) / dot(p.xyz, d);  u = dot(q.xyz, P) + q.w;  v = dot(r.xyz, P) + r.w;  P = o + t d */
+struct TriFast { float4 p, q, r; };
+
 struct MediumDev {
     int type;               /* 0 homogeneous, 1 grid (simpson) */
     int phaseType; float g;
@@ -75,7 +79,7 @@ struct CameraDev {
 };
 
 struct SceneDev {
-    const BvhNode *nodes; const TriRec *tris; uint32_t numNodes;
+    const BvhNode *nodes; const TriRec *tris; const TriFast *trisFast; uint32_t numNodes;
     float kdMin[3], kdMax[3];     /* ShapeKDTree AABB incl. the 1e-3 enlargement (gkdtree.h:1213-1220) */
     int anyHit;
 };

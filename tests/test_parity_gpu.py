@@ -254,7 +254,11 @@ def test_clusters_identical_sfmt_stream(pkg, orc):
         g, o = _pair(pkg, orc, "C1", 48, 48, 120, seed=6, rngMode=1, workerCount=w, targetNumSlices=24)
         for it in (g, o):
             it.build_slices(); it.sample_slice_mapping()
-        o.build_R()
+        # R from a tape, so that neither side's SFMT stream advances during build_R and both enter buildClusters in the
+        # same stream state (the stream order *through* build_R is covered by test_R_reference_stream_tape)
+        S, G = o.num_slices()
+        tape = np.random.default_rng(w).random((G, o.N, 6), dtype=np.float32)
+        o.set_sample_tape(tape); o.build_R()
         g.set_R(o.get_R())
         o.build_clusters(); g.build_clusters()
         _clusters_equal(g.clusters(), o.clusters(), f"workerCount={w}")
