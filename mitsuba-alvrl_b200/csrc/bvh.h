@@ -58,7 +58,7 @@ public:
         out.triOrder = m_idx;
     }
 private:
-    static const int kBins = 16, kLeaf = 4;
+    static const int kBins = 16, kLeaf = 4;      /* leaf count is stored in 4 bits */
     uint32_t m_nt; float m_pad;
     std::vector<Box3> m_box; std::vector<float> m_cen; std::vector<uint32_t> m_idx;
 
@@ -71,7 +71,8 @@ private:
         for (uint32_t i = b; i < e; i++) { bounds.grow(m_box[m_idx[i]]); cb.grow(&m_cen[3 * (size_t) m_idx[i]]); }
         uint32_t n = e - b;
         uint32_t mid = 0;
-        bool leaf = n <= kLeaf;
+        bool leaf = n == 1;
+        float bestCost = INFINITY;
         if (!leaf) {
             int axis = 0; float ext = -1;
             for (int c = 0; c < 3; c++) if (cb.hi[c] - cb.lo[c] > ext) { ext = cb.hi[c] - cb.lo[c]; axis = c; }
@@ -94,6 +95,7 @@ private:
                     float cost = accL.area() * cntL + rightArea[k + 1] * rightCnt[k + 1];
                     if (cost < best) { best = cost; bestK = k; }
                 }
+                bestCost = best;
                 if (bestK < 0) mid = b + n / 2;
                 else {
                     auto it = std::partition(m_idx.begin() + b, m_idx.begin() + e, [&](uint32_t t) {
@@ -104,6 +106,13 @@ private:
                     if (mid == b || mid == e) mid = b + n / 2;
                 }
             }
+        }
+        /* SAH termination: keep <= kLeaf triangles together only when splitting does not pay (cost of a box test = 1
+         * triangle test): two walls of a room in one leaf would give a box that every ray enters */
+        if (!leaf && n <= kLeaf) {
+            const float area = bounds.area();
+            const float leafCost = area * n, splitCost = area * 1.0f + bestCost;
+            if (!(splitCost < leafCost)) leaf = true;
         }
         if (leaf) {
             out.maxLeaf = std::max(out.maxLeaf, n);

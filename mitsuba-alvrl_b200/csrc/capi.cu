@@ -68,12 +68,15 @@ void ensure_scene(alvrl_ctx *c) {
     for (size_t i = 0; i + 2 < c->extraBounds.size(); i += 3)
         for (int k = 0; k < 3; k++) { c->sceneMin[k] = std::min(c->sceneMin[k], c->extraBounds[i + k]); c->sceneMax[k] = std::max(c->sceneMax[k], c->extraBounds[i + k]); }
     c->dNodes.upload(bvh.nodes, c->stream);
+    std::vector<BvhNode> leaves;
+    for (const BvhNode &nd : bvh.nodes) { uint32_t lf; memcpy(&lf, &nd.hi.w, 4); if (lf) leaves.push_back(nd); }
+    c->dLeafNodes.upload(leaves, c->stream);
     c->dTris.upload(recs, c->stream);
     c->dTrisFast.upload(fast, c->stream);
     c->dTriVerts.upload(tv, c->stream);
     c->dTriMat.upload(c->triMat, c->stream);
     SceneDev &s = c->sceneDev;
-    s.nodes = c->dNodes.p; s.tris = c->dTris.p; s.trisFast = c->dTrisFast.p; s.numNodes = (uint32_t) bvh.nodes.size();
+    s.nodes = c->dNodes.p; s.tris = c->dTris.p; s.trisFast = c->dTrisFast.p; s.numNodes = (uint32_t) bvh.nodes.size(); s.numTris = nt; s.leafNodes = c->dLeafNodes.p; s.numLeaves = (uint32_t) leaves.size();
     for (int k = 0; k < 3; k++) { s.kdMin[k] = c->kdMin[k]; s.kdMax[k] = c->kdMax[k]; }
     s.anyHit = c->P.anyHitShadowRays ? 1 : 0;
     c->stats.bvhNodes = s.numNodes;

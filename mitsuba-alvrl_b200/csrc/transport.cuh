@@ -352,6 +352,10 @@ __device__ __forceinline__ void integrate_pair(const TransportParams &P, const S
     }
 }
 
+#ifdef ALVRL_FAST
+#include "transport_fast_impl.cuh"
+#endif
+
 /* ---- TMA bulk-copy tile pipeline ------------------------------------------------------------------ */
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -373,6 +377,7 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t
 struct TileSmem {
     VrlRec tile[2][ALVRL_TILE_VRLS];
     uint64_t full[2];
+    uint64_t pad[14];              /* keep the structures that follow in dynamic shared memory 128-byte aligned */
 };
 
 #define ALVRL_CAT2(a, b) a##_##b
@@ -383,11 +388,18 @@ struct TileSmem {
  * "Building R" (vrlIntegrator.cpp:302-337,792-825): rows = representative-pixel segments, columns = VRLs.
  * grid.x = row blocks of 128, grid.y = VRL chunks of vrlsPerCta (multiple of the tile size).
  */
-template <int MED>
+template <int MED, bool SMALL>
 __global__ void __launch_bounds__(ALVRL_CTA_SEGS) ALVRL_NAME(k_build_R)(TransportParams P, const SegRec *__restrict__ rowSegs, uint32_t numRows,
                                                                        const VrlRec *__restrict__ vrls, float2 *__restrict__ R, uint32_t ldR,
                                                                        uint32_t vrlsPerCta) {
+#ifdef ALVRL_FAST
+    extern __shared__ __align__(128) unsigned char dynSmem[];
+    TileSmem &sm = *reinterpret_cast<TileSmem *>(dynSmem);
+    BvhSmem &sbvh = *reinterpret_cast<BvhSmem *>(dynSmem + sizeof(TileSmem));
+    if (SMALL) stage_bvh(sbvh, P.scene);
+#else
     __shared__ __align__(128) TileSmem sm;
+#endif
     const uint32_t tid = threadIdx.x;
     const uint32_t row = blockIdx.x * ALVRL_CTA_SEGS + tid;
     const uint32_t N = P.numVrls;
@@ -411,6 +423,7 @@ __global__ void __launch_bounds__(ALVRL_CTA_SEGS) ALVRL_NAME(k_build_R)(Transpor
     if (tid == 0) issue(0);
 
     SegRec seg;
+    memset(&seg, 0, sizeof(seg));
     bool active = row < numRows;
     if (active) {
         seg = rowSegs[row];
@@ -423,11 +436,25 @@ __global__ void __launch_bounds__(ALVRL_CTA_SEGS) ALVRL_NAME(k_build_R)(Transpor
         mbar_wait(&sm.full[t & 1], (t >> 1) & 1);
         const uint32_t v0 = vBegin + t * ALVRL_TILE_VRLS;
         const uint32_t cnt = min((uint32_t) ALVRL_TILE_VRLS, vEnd - v0);
-        if (row < numRows) {
+        {
 #pragma unroll 1
             for (uint32_t j = 0; j < cnt; j++) {
                 float mean = 0, var = 0;
                 const uint32_t v = v0 + j;
+#ifdef ALVRL_FAST
+                if constexpr (MED != 1) {
+                    /* every lane of the warp takes part (the shadow rays of a warp are traced from a shared pool) */
+                    const VrlRec &vr = sm.tile[t & 1][j];
+                    Rng rng;
+                    rng.tape = P.tape ? P.tape + ((size_t) (P.rowBase + row) * N + v) * P.tapeK : nullptr;
+                    rng.key = alvrl_rng_key(P.seed, P.rngDomain, P.rowBase + row, v);
+                    rng.k = 0;
+                    float rgb[3], m, s2;
+                    integrate_pair_fast<MED, false, true, SMALL>(P, &sbvh, seg, vr.s, vr.e, vr.dir, vr.power, rng, rgb, m, s2, active && scattering);
+                    mean = m * P.normalization;
+                    var = s2 * P.normalization * P.normalization;
+                } else
+#endif
                 if (active && scattering) {
                     const VrlRec &vr = sm.tile[t & 1][j];
                     Rng rng;
@@ -435,11 +462,11 @@ __global__ void __launch_bounds__(ALVRL_CTA_SEGS) ALVRL_NAME(k_build_R)(Transpor
                     rng.key = alvrl_rng_key(P.seed, P.rngDomain, P.rowBase + row, v);
                     rng.k = 0;
                     float rgb[3], m, s2;
-                    integrate_pair<MED, false, true>(P, seg, vr.s, vr.e, vr.dir, vr.power, rng, rgb, m, s2);
+                    integrate_pair<(MED == 2 ? 0 : MED), false, true>(P, seg, vr.s, vr.e, vr.dir, vr.power, rng, rgb, m, s2);
                     mean = m * P.normalization;                              /* vrlIntegrator.cpp:812-813 */
                     var = s2 * P.normalization * P.normalization;
                 }
-                R[(size_t) v * ldR + row] = make_float2(mean, var);          /* lanes = consecutive rows: coalesced */
+                if (row < numRows) R[(size_t) v * ldR + row] = make_float2(mean, var);   /* lanes = consecutive rows: coalesced */
             }
         }
         __syncthreads();
@@ -451,12 +478,19 @@ __global__ void __launch_bounds__(ALVRL_CTA_SEGS) ALVRL_NAME(k_build_R)(Transpor
  * One CTA = up to 128 pixels of one slice; the slice's representative VRLs (records gathered per slice, cluster
  * weight in e.w) stream through the same TMA tile pipeline.  work[cta] = {slice, firstPixel, pixelCount, 0}.
  */
-template <int MED, bool CLUSTERED>
+template <int MED, bool CLUSTERED, bool SMALL>
 __global__ void __launch_bounds__(ALVRL_CTA_SEGS) ALVRL_NAME(k_render)(TransportParams P, const SegRec *__restrict__ pixSegs,
                                                                       const uint32_t *__restrict__ slicePixels, const uint4 *__restrict__ work,
                                                                       const VrlRec *__restrict__ repRecs, const uint32_t *__restrict__ repOffset,
                                                                       float4 *__restrict__ fb, uint32_t W, uint32_t H) {
+#ifdef ALVRL_FAST
+    extern __shared__ __align__(128) unsigned char dynSmem[];
+    TileSmem &sm = *reinterpret_cast<TileSmem *>(dynSmem);
+    BvhSmem &sbvh = *reinterpret_cast<BvhSmem *>(dynSmem + sizeof(TileSmem));
+    if (SMALL) stage_bvh(sbvh, P.scene);
+#else
     __shared__ __align__(128) TileSmem sm;
+#endif
     const uint32_t tid = threadIdx.x;
     const uint4 wk = work[blockIdx.x];
     const uint32_t vBegin = repOffset[wk.x], vEnd = repOffset[wk.x + 1];
@@ -478,6 +512,7 @@ __global__ void __launch_bounds__(ALVRL_CTA_SEGS) ALVRL_NAME(k_render)(Transport
     const bool inRange = tid < wk.z;
     uint32_t pixel = 0;
     SegRec seg;
+    memset(&seg, 0, sizeof(seg));
     bool active = false;
     if (inRange) {
         pixel = slicePixels[wk.y + tid];
@@ -491,7 +526,7 @@ __global__ void __launch_bounds__(ALVRL_CTA_SEGS) ALVRL_NAME(k_render)(Transport
         mbar_wait(&sm.full[t & 1], (t >> 1) & 1);
         const uint32_t v0 = vBegin + t * ALVRL_TILE_VRLS;
         const uint32_t cnt = min((uint32_t) ALVRL_TILE_VRLS, vEnd - v0);
-        if (active && scattering) {
+        {
 #pragma unroll 1
             for (uint32_t j = 0; j < cnt; j++) {
                 const VrlRec &vr = sm.tile[t & 1][j];
@@ -499,8 +534,12 @@ __global__ void __launch_bounds__(ALVRL_CTA_SEGS) ALVRL_NAME(k_render)(Transport
                 rng.tape = nullptr;
                 rng.key = alvrl_rng_key(P.seed, ALVRL_RNG_RENDER, pixel, v0 + j - vBegin);
                 rng.k = 0;
-                float rgb[3], m, s2;
-                integrate_pair<MED, true, false>(P, seg, vr.s, vr.e, vr.dir, vr.power, rng, rgb, m, s2);
+                float rgb[3] = {0, 0, 0}, m, s2;
+#ifdef ALVRL_FAST
+                if constexpr (MED != 1) integrate_pair_fast<MED, true, false, SMALL>(P, &sbvh, seg, vr.s, vr.e, vr.dir, vr.power, rng, rgb, m, s2, active && scattering);
+                else
+#endif
+                if (active && scattering) integrate_pair<(MED == 2 ? 0 : MED), true, false>(P, seg, vr.s, vr.e, vr.dir, vr.power, rng, rgb, m, s2);
                 if (CLUSTERED) {                                             /* 587-589: Li += weight_k * integrateVRL */
                     const float w = vr.e.w;
                     Li[0] += w * rgb[0]; Li[1] += w * rgb[1]; Li[2] += w * rgb[2];

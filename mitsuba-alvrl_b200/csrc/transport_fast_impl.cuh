@@ -1,0 +1,255 @@
+/*
+ * transport_fast_impl.cuh -- speed flavour of integrateVRL (included by transport.cuh when ALVRL_FAST is defined).
+ *
+ * Same estimator and the same uniforms as the strict flavour (vrlIntegrator.cpp:603-785), restructured for the SM:
+ *   - the three transmittances of a sample are one exponential per channel, exp(-sigma_t (|SV| + |VU| + |UE|)), plus
+ *     one for pdfFailure; a grey medium (sigma_t equal in all channels, the BASELINE configs) needs two MUFU.EX2 in all;
+ *   - |A-I|, |I-B| of KullaSampling follow from the projection parameter (I = A + dotPr*dir), so a sample needs three
+ *     square roots instead of seven; the signed-angle form replaces the sign fix-up branches (889-903);
+ *   - sinh / asinh / tan go through MUFU (ex2, lg2, sin, cos, rcp); atan keeps the polynomial atanf;
+ *   - visibility: scenes with <= 32 BVH leaves keep leaf boxes + triangles in shared memory and answer a shadow ray
+ *     with a flat, warp-uniform sweep over the leaf boxes (broadcast LDS, no inner nodes) followed by triangle tests
+ *     of the entered leaves only; larger scenes use the per-lane stackless traversal of dev_common.cuh.
+ * Agreement with the strict flavour / the oracle: ~1e-6 relative per sample, bounded by the tests at 1e-3 per R entry.
+ */
+#pragma once
+
+#define ALVRL_SMALL_LEAVES 32
+#define ALVRL_SMALL_TRIS 128
+
+/* small scenes: all leaf boxes + triangle records in shared memory */
+struct BvhSmem {
+    float4 leaves[2 * ALVRL_SMALL_LEAVES];
+    float4 tris[3 * ALVRL_SMALL_TRIS];
+};
+
+__device__ __forceinline__ void stage_bvh(BvhSmem &sb, const SceneDev &sc) {
+    const float4 *gn = reinterpret_cast<const float4 *>(sc.leafNodes);
+    const float4 *gt = reinterpret_cast<const float4 *>(sc.trisFast);
+    for (uint32_t i = threadIdx.x; i < 2 * sc.numLeaves; i += blockDim.x) sb.leaves[i] = __ldg(&gn[i]);
+    for (uint32_t i = threadIdx.x; i < 3 * sc.numTris; i += blockDim.x) sb.tris[i] = __ldg(&gt[i]);
+}
+
+/*
+ * Any-hit query for small scenes (<= 32 leaves): a flat sweep over the leaf boxes -- a uniform loop, every lane reads
+ * the same box (broadcast LDS), no inner nodes, no dependent control flow -- builds a per-lane bit mask of entered
+ * leaves; only those leaves' triangles are tested.  Called by all lanes of the warp together (need = false: no ray).
+ */
+__device__ __forceinline__ bool occluded_flat(const BvhSmem &sb, uint32_t numLeaves, const F3 &o, const F3 &d, float tmin, float tmax, bool need) {
+    const F3 inv = f3(__frcp_rn(d.x), __frcp_rn(d.y), __frcp_rn(d.z));
+    const F3 oi = f3(-o.x * inv.x, -o.y * inv.y, -o.z * inv.z);
+    const float hi_t = tmax * 1.00001f;
+    uint32_t mask = 0;
+#pragma unroll 2
+    for (uint32_t i = 0; i < numLeaves; i++) {
+        const float4 lo = sb.leaves[2 * i], hi = sb.leaves[2 * i + 1];
+        const float tx1 = fmaf(lo.x, inv.x, oi.x), tx2 = fmaf(hi.x, inv.x, oi.x);
+        const float ty1 = fmaf(lo.y, inv.y, oi.y), ty2 = fmaf(hi.y, inv.y, oi.y);
+        const float tz1 = fmaf(lo.z, inv.z, oi.z), tz2 = fmaf(hi.z, inv.z, oi.z);
+        const float tn = fmaxf(fmaxf(fminf(tx1, tx2), fminf(ty1, ty2)), fmaxf(fminf(tz1, tz2), tmin));
+        const float tf = fminf(fminf(fmaxf(tx1, tx2), fmaxf(ty1, ty2)), fminf(fmaxf(tz1, tz2), hi_t));
+        mask |= (tn <= tf ? 1u : 0u) << i;
+    }
+    if (!need || !(tmax > tmin)) mask = 0;
+    while (mask) {
+        const uint32_t i = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const uint32_t lf = __float_as_uint(sb.leaves[2 * i + 1].w);
+        const uint32_t first = lf >> 4, cnt = lf & 15u;
+        for (uint32_t k = 0; k < cnt; k++) {
+            const float4 p = sb.tris[3 * (first + k)];
+            const float den = p.x * d.x + p.y * d.y + p.z * d.z;
+            const float num = p.w - (p.x * o.x + p.y * o.y + p.z * o.z);
+            const float t = __fdividef(num, den);
+            if (!(t >= tmin && t <= tmax)) continue;
+            const float4 q = sb.tris[3 * (first + k) + 1], w = sb.tris[3 * (first + k) + 2];
+            const F3 Pt = f3(fmaf(t, d.x, o.x), fmaf(t, d.y, o.y), fmaf(t, d.z, o.z));
+            const float u = q.x * Pt.x + q.y * Pt.y + q.z * Pt.z + q.w;
+            const float v = w.x * Pt.x + w.y * Pt.y + w.z * Pt.z + w.w;
+            if (u >= 0.0f && v >= 0.0f && u + v <= 1.0f) return true;
+        }
+    }
+    return false;
+}
+
+template <bool SMALL>
+__device__ __forceinline__ bool occluded_fast(const TransportParams &P, const BvhSmem *sb, const F3 &p1, bool onSurf, const F3 &dir, float remaining, bool need) {
+    /* adaptive epsilon of the shadow-ray overload, skdtree.cpp:154-157 */
+    const float mint = onSurf ? ALVRL_EPSILON * fmaxf(fmaxf(fabsf(p1.x), fabsf(p1.y)), fabsf(p1.z)) : 0.0f;
+    if (SMALL) return occluded_flat(*sb, P.scene.numLeaves, p1, dir, mint, remaining, need);
+    if (!need || !(remaining > mint)) return false;
+    return bvh_occluded_fast(P.scene, p1, dir, mint, remaining);
+}
+
+__device__ __forceinline__ float f_sinh(float a) { const float e = __expf(a); return 0.5f * (e - __frcp_rn(e)); }
+__device__ __forceinline__ float f_asinh(float x) { const float a = fabsf(x); return copysignf(__logf(a + sqrtf(fmaf(a, a, 1.0f))), x); }
+__device__ __forceinline__ float f_tan(float x) { return __tanf(x); }
+__device__ __forceinline__ float f_len(const F3 &a, float &l2) { l2 = len2(a); return l2 * rsqrtf(fmaxf(l2, 1e-38f)); }
+
+/* homogeneous media only (MED 0: RGB sigma_t, MED 2: grey sigma_t) */
+template <int MED, bool WANT_RGB, bool WANT_STAT, bool SMALL>
+__device__ __forceinline__ void integrate_pair_fast(const TransportParams &P, const BvhSmem *sb, const SegRec &seg,
+                                                    const float4 vS, const float4 vE, const float4 vDir, const float4 vPow, Rng &rng,
+                                                    float rgb[3], float &outMean, float &outVar, const bool laneOn) {
+    const F3 S = f3(vS), End = f3(vE), SV = f3(vDir);
+    const float vlen = vS.w;
+    const F3 E = f3(seg.o), EU = f3(seg.d), Usurf = f3(seg.p);
+    const float edist = seg.o.w;
+    const int Nvv = P.Nvv, Nvs = P.Nvs;
+    const MediumDev &M = P.medium;
+    if (WANT_RGB) rgb[0] = rgb[1] = rgb[2] = 0;
+    outMean = 0; outVar = 0;
+    const float sT0 = M.sigmaT[0], sT1 = M.sigmaT[1], sT2 = M.sigmaT[2];
+    const float sTmin = fminf(sT0, fminf(sT1, sT2));
+    const float cutoff = 46.0517f;     /* -ln(1e-20): Medium::eval zeroes a transmittance whose max is below 1e-20 (homogeneous.cpp:394-395) */
+    const float wS = M.samplingWeight, wF = 1.0f - M.samplingWeight;
+    const float lw0 = 0.212671f, lw1 = 0.715160f, lw2 = 0.072169f;
+
+    /* ---- volume to volume (646-703) ---- */
+    if (Nvv > 0) {
+        /* power * sigma_s(V) * sigma_s(U): constant per pair in a homogeneous medium */
+        const float k0 = vPow.x * M.sigmaS[0] * M.sigmaS[0], k1 = vPow.y * M.sigmaS[1] * M.sigmaS[1], k2 = vPow.z * M.sigmaS[2] * M.sigmaS[2];
+        const float cosTheta = dot(f3(seg.dn), SV);
+        const float sinTheta = sqrtf(fmaxf(0.0f, 1 - cosTheta * cosTheta));
+        const bool parallel = sinTheta < ALVRL_EPSILON;
+        float h = 0, A0 = 0, dA = 0, dVhS = 0, rSin = 0, pdfVc = 0;
+        if (!parallel) {
+            F3 Vh;
+            h = closest_points(E, Usurf, S, End, Vh);
+            float l2;
+            dVhS = f_len(Vh - S, l2);
+            const float V1c = f_len(Vh - End, l2);
+            rSin = __frcp_rn(sinTheta);
+            const float sh = __fdividef(sinTheta, h);
+            A0 = f_asinh(-dVhS * sh);
+            dA = f_asinh(V1c * sh) - A0;
+            pdfVc = __fdividef(sinTheta, dA);                              /* 1 / denom, denom = (A1 - A0) / sinTheta */
+        }
+        const float invNvv = __frcp_rn((float) Nvv);
+        float mean = 0, M2 = 0;
+        for (int k = 0; k < Nvv; k++) {
+            const float u1 = rng.next();
+            F3 V; float pdf;
+            if (parallel) {
+                V = S + u1 * (End - S);
+                pdf = __frcp_rn(vlen);
+            } else {
+                const float nv = h * f_sinh(fmaf(u1, dA, A0)) * rSin;
+                pdf = rsqrtf(fmaf(nv * nv, sinTheta * sinTheta, h * h)) * pdfVc;
+                V = S + (nv + dVhS) * SV;
+            }
+            const float u2 = rng.next();
+            /* KullaSampling along the eye segment w.r.t. V (889-914), signed-angle form; dir = EU, A = E, |AB| = edist */
+            const float dotPr = dot(EU, V - E);
+            const F3 I = E + dotPr * EU;
+            float l2;
+            const float Dis = f_len(V - I, l2);
+            const float rDis = __frcp_rn(Dis);
+            const float th_a = atanf(-dotPr * rDis), th_b = atanf((edist - dotPr) * rDis);
+            const float t = Dis * f_tan(fmaf(u2, th_b - th_a, th_a));
+            pdf *= __fdividef(Dis, (th_b - th_a) * fmaf(t, t, l2));
+            const F3 U = I + t * EU;
+            const F3 UV = U - V;
+            float d2;
+            const float dUV = f_len(UV, d2);
+            const F3 VU = UV * __frcp_rn(dUV);
+            const float dEU = fabsf(dotPr + t);                             /* |U - E|, U = E + (dotPr + t) EU */
+            float tmp;
+            const float dSV = f_len(V - S, tmp);
+            const bool ok = laneOn && d2 > 0.0f && dEU * sTmin <= cutoff && dSV * sTmin <= cutoff;
+            const bool occ = occluded_fast<SMALL>(P, sb, U, false, -VU, dUV, ok);
+            float lum = 0;
+            if (ok && !occ) {
+                const float path = dSV + dUV + dEU;
+                float T0, T1, T2, pf;
+                if (MED == 2) {
+                    T0 = T1 = T2 = __expf(-sT0 * path);
+                    pf = fmaf(__expf(-sT0 * dSV), wS, wF);
+                } else {
+                    T0 = __expf(-sT0 * path); T1 = __expf(-sT1 * path); T2 = __expf(-sT2 * path);
+                    pf = fmaf((__expf(-sT0 * dSV) + __expf(-sT1 * dSV) + __expf(-sT2 * dSV)) * (1.0f / 3.0f), wS, wF);
+                }
+                float common = __fdividef(1.0f, pdf * d2);
+                if (P.shortVrls) common = __fdividef(common, pf);
+                common *= phase_eval(M, dot(VU, EU)) * phase_eval(M, -dot(SV, VU));
+                const float c0 = k0 * T0 * common, c1 = k1 * T1 * common, c2 = k2 * T2 * common;
+                if (isfinite(c0) && isfinite(c1) && isfinite(c2) && c0 >= 0.0f && c1 >= 0.0f && c2 >= 0.0f) {   /* isValid(), 686 */
+                    if (WANT_RGB) { rgb[0] = fmaf(c0, invNvv, rgb[0]); rgb[1] = fmaf(c1, invNvv, rgb[1]); rgb[2] = fmaf(c2, invNvv, rgb[2]); }
+                    lum = c0 * lw0 + c1 * lw1 + c2 * lw2;
+                }
+            }
+            if (WANT_STAT) {                                                 /* 693-699 */
+                const float delta = lum - mean;
+                mean += __fdividef(delta, (float) (k + 1));
+                M2 = fmaf(delta, lum - mean, M2);
+            }
+        }
+        if (WANT_STAT) { outMean += mean; outVar += __fdividef(M2, (float) ((Nvv - 1) * Nvv)); }
+    }
+
+    /* ---- volume to surface (706-782) ---- */
+    if (Nvs > 0) {
+        const float tE0 = seg.tE.x, tE1 = seg.tE.y, tE2 = seg.tE.z;
+        const uint32_t flags = __float_as_uint(seg.dn.w);
+        const bool surf = laneOn && !(tE0 == 0 && tE1 == 0 && tE2 == 0) && (flags & SEG_SMOOTH);
+        float mean = 0, M2 = 0;
+        /* lanes without a vol->surf term (727) still walk the loop -- drawing nothing, contributing nothing -- so that the
+         * warp stays converged through the flat visibility sweep */
+        if (SMALL ? __any_sync(0xffffffffu, surf) : surf) {
+            /* per-pair part of KullaSampling(A = S, B = End, D = Usurf) */
+            const float dotPr = dot(SV, Usurf - S);
+            const F3 I = S + dotPr * SV;
+            float l2;
+            const float Dis = f_len(Usurf - I, l2);
+            const float rDis = __frcp_rn(Dis);
+            const float th_a = atanf(-dotPr * rDis), th_b = atanf((vlen - dotPr) * rDis);
+            const float pdfC = __fdividef(Dis, th_b - th_a);
+            const float invNvs = __frcp_rn((float) Nvs);
+            const F3 nrm = f3(seg.n);
+            const bool frontI = seg.d.w > 0;
+            const float k0 = vPow.x * M.sigmaS[0] * seg.albedo.x * tE0, k1 = vPow.y * M.sigmaS[1] * seg.albedo.y * tE1,
+                        k2 = vPow.z * M.sigmaS[2] * seg.albedo.z * tE2;
+            for (int k = 0; k < Nvs; k++) {
+                const float u = surf ? rng.next() : 0.5f;
+                const float t = Dis * f_tan(fmaf(u, th_b - th_a, th_a));
+                const float pdf = __fdividef(pdfC, fmaf(t, t, l2));
+                const float sv = dotPr + t;                                  /* V = S + sv * SV */
+                const F3 V = S + sv * SV;
+                const F3 UV = Usurf - V;
+                float d2;
+                const float dUV = f_len(UV, d2);
+                const F3 VU = UV * __frcp_rn(dUV);
+                const float dSV = fabsf(sv);
+                const float cosWo = -dot(VU, nrm);                           /* diffuse.cpp:110-118 */
+                const bool ok = surf && d2 > 0.0f && dSV * sTmin <= cutoff && frontI && cosWo > 0;
+                const bool occ = occluded_fast<SMALL>(P, sb, Usurf, true, -VU, dUV, ok);
+                float lum = 0;
+                if (ok && !occ) {
+                    const float path = dSV + dUV;
+                    float T0, T1, T2, pf;
+                    if (MED == 2) {
+                        T0 = T1 = T2 = __expf(-sT0 * path);
+                        pf = fmaf(__expf(-sT0 * dSV), wS, wF);
+                    } else {
+                        T0 = __expf(-sT0 * path); T1 = __expf(-sT1 * path); T2 = __expf(-sT2 * path);
+                        pf = fmaf((__expf(-sT0 * dSV) + __expf(-sT1 * dSV) + __expf(-sT2 * dSV)) * (1.0f / 3.0f), wS, wF);
+                    }
+                    float common = __fdividef(ALVRL_INV_PI * cosWo, pdf * d2);
+                    if (P.shortVrls) common = __fdividef(common, pf);
+                    common *= phase_eval(M, -dot(SV, VU));
+                    const float c0 = k0 * T0 * common, c1 = k1 * T1 * common, c2 = k2 * T2 * common;
+                    if (isfinite(c0) && isfinite(c1) && isfinite(c2) && c0 >= 0.0f && c1 >= 0.0f && c2 >= 0.0f) {
+                        if (WANT_RGB) { rgb[0] = fmaf(c0, invNvs, rgb[0]); rgb[1] = fmaf(c1, invNvs, rgb[1]); rgb[2] = fmaf(c2, invNvs, rgb[2]); }
+                        lum = c0 * lw0 + c1 * lw1 + c2 * lw2;
+                    }
+                }
+                if (WANT_STAT) {
+                    const float delta = lum - mean;
+                    mean += __fdividef(delta, (float) (k + 1));
+                    M2 = fmaf(delta, lum - mean, M2);
+                }
+            }
+        }
+        if (WANT_STAT) { outMean += mean; outVar += __fdividef(M2, (float) ((Nvs - 1) * Nvs)); }
+    }
+}

@@ -1,6 +1,16 @@
 /* transport_launch.inl -- launchers shared by the two flavours (included after transport.cuh). */
 namespace alvrl {
 
+#ifdef ALVRL_FAST
+template <typename K> static void set_dyn_smem(K kernel, size_t bytes) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+}
+#define ALVRL_SMEM_R (sizeof(TileSmem) + sizeof(BvhSmem))
+#define ALVRL_SMEM_RENDER (sizeof(TileSmem) + sizeof(BvhSmem))
+#define ALVRL_GO_R(MED, SM) do { set_dyn_smem(ALVRL_NAME(k_build_R)<MED, SM>, ALVRL_SMEM_R); \
+        ALVRL_NAME(k_build_R)<MED, SM><<<grid, ALVRL_CTA_SEGS, ALVRL_SMEM_R, st>>>(P, rowSegs, numRows, vrls, R, ldR, per); } while (0)
+#endif
+
 void ALVRL_NAME(launch_build_R)(const TransportParams &P, const SegRec *rowSegs, uint32_t numRows, const VrlRec *vrls, float2 *R,
                                 uint32_t ldR, cudaStream_t st) {
     if (numRows == 0 || P.numVrls == 0) return;
@@ -15,21 +25,43 @@ void ALVRL_NAME(launch_build_R)(const TransportParams &P, const SegRec *rowSegs,
     per = ((per + ALVRL_TILE_VRLS - 1) / ALVRL_TILE_VRLS) * ALVRL_TILE_VRLS;
     chunks = (P.numVrls + per - 1) / per;
     dim3 grid(rowBlocks, chunks);
-    if (P.medium.type == 0) ALVRL_NAME(k_build_R)<0><<<grid, ALVRL_CTA_SEGS, 0, st>>>(P, rowSegs, numRows, vrls, R, ldR, per);
-    else ALVRL_NAME(k_build_R)<1><<<grid, ALVRL_CTA_SEGS, 0, st>>>(P, rowSegs, numRows, vrls, R, ldR, per);
+#ifdef ALVRL_FAST
+    const bool small = P.scene.numLeaves <= ALVRL_SMALL_LEAVES && P.scene.numTris <= ALVRL_SMALL_TRIS;
+    if (P.medium.type == 1) ALVRL_GO_R(1, false);
+    else if (P.medium.grey) { if (small) ALVRL_GO_R(2, true); else ALVRL_GO_R(2, false); }
+    else { if (small) ALVRL_GO_R(0, true); else ALVRL_GO_R(0, false); }
+#else
+    if (P.medium.type == 0) ALVRL_NAME(k_build_R)<0, false><<<grid, ALVRL_CTA_SEGS, 0, st>>>(P, rowSegs, numRows, vrls, R, ldR, per);
+    else ALVRL_NAME(k_build_R)<1, false><<<grid, ALVRL_CTA_SEGS, 0, st>>>(P, rowSegs, numRows, vrls, R, ldR, per);
+#endif
 }
 
 void ALVRL_NAME(launch_render)(const TransportParams &P, bool clustered, const SegRec *pixSegs, const uint32_t *slicePixels,
                                const uint4 *work, uint32_t numWork, const VrlRec *repRecs, const uint32_t *repOffset, float4 *fb,
                                uint32_t W, uint32_t H, cudaStream_t st) {
     if (numWork == 0) return;
-    if (P.medium.type == 0) {
-        if (clustered) ALVRL_NAME(k_render)<0, true><<<numWork, ALVRL_CTA_SEGS, 0, st>>>(P, pixSegs, slicePixels, work, repRecs, repOffset, fb, W, H);
-        else ALVRL_NAME(k_render)<0, false><<<numWork, ALVRL_CTA_SEGS, 0, st>>>(P, pixSegs, slicePixels, work, repRecs, repOffset, fb, W, H);
-    } else {
-        if (clustered) ALVRL_NAME(k_render)<1, true><<<numWork, ALVRL_CTA_SEGS, 0, st>>>(P, pixSegs, slicePixels, work, repRecs, repOffset, fb, W, H);
-        else ALVRL_NAME(k_render)<1, false><<<numWork, ALVRL_CTA_SEGS, 0, st>>>(P, pixSegs, slicePixels, work, repRecs, repOffset, fb, W, H);
-    }
+#ifdef ALVRL_FAST
+#define ALVRL_RENDER_SMEM ALVRL_SMEM_RENDER
+#define ALVRL_RENDER_ATTR(MED, CL, SM) set_dyn_smem(ALVRL_NAME(k_render)<MED, CL, SM>, ALVRL_SMEM_RENDER)
+#else
+#define ALVRL_RENDER_SMEM 0
+#define ALVRL_RENDER_ATTR(MED, CL, SM) (void) 0
+#endif
+#define ALVRL_LAUNCH_RENDER(MED, SM)                                                                                                         \
+    do {                                                                                                                                     \
+        if (clustered) { ALVRL_RENDER_ATTR(MED, true, SM);                                                                                   \
+            ALVRL_NAME(k_render)<MED, true, SM><<<numWork, ALVRL_CTA_SEGS, ALVRL_RENDER_SMEM, st>>>(P, pixSegs, slicePixels, work, repRecs, repOffset, fb, W, H); } \
+        else { ALVRL_RENDER_ATTR(MED, false, SM);                                                                                            \
+            ALVRL_NAME(k_render)<MED, false, SM><<<numWork, ALVRL_CTA_SEGS, ALVRL_RENDER_SMEM, st>>>(P, pixSegs, slicePixels, work, repRecs, repOffset, fb, W, H); } \
+    } while (0)
+#ifdef ALVRL_FAST
+    const bool small = P.scene.numLeaves <= ALVRL_SMALL_LEAVES && P.scene.numTris <= ALVRL_SMALL_TRIS;
+    if (P.medium.type == 1) ALVRL_LAUNCH_RENDER(1, false);
+    else if (P.medium.grey) { if (small) ALVRL_LAUNCH_RENDER(2, true); else ALVRL_LAUNCH_RENDER(2, false); }
+    else { if (small) ALVRL_LAUNCH_RENDER(0, true); else ALVRL_LAUNCH_RENDER(0, false); }
+#else
+    if (P.medium.type == 1) ALVRL_LAUNCH_RENDER(1, false); else ALVRL_LAUNCH_RENDER(0, false);
+#endif
 }
 
 } // namespace alvrl

@@ -79,7 +79,7 @@ struct CameraDev {
 };
 
 struct SceneDev {
-    const BvhNode *nodes; const TriRec *tris; const TriFast *trisFast; uint32_t numNodes;
+    const BvhNode *nodes; const TriRec *tris; const TriFast *trisFast; const BvhNode *leafNodes; uint32_t numNodes, numTris, numLeaves;
     float kdMin[3], kdMax[3];     /* ShapeKDTree AABB incl. the 1e-3 enlargement (gkdtree.h:1213-1220) */
     int anyHit;
 };
