@@ -7,8 +7,8 @@
  *     k_column_weights       calculateColumnWeigths (985-1008)         sqrt(sum_r w_r (mean^2 + var))
  *     k_unclustered          calculateUnclusteredVariance (1022-1048)  Welford across VRLs, per row
  *     k_direction/k_project  Clustering::split (604-640)               split direction + column projections
- *     k_cluster_variance     calculateClusterVariance (1058-1120)      forward / reverse prefix variances
- *     k_combine              reduction of the per-row-block partials into the (float, float) prefix pairs
+ *     k_weights/k_seg_sums/k_carry/k_seg_main/k_final
+ *                            calculateClusterVariance (1058-1120)      forward / reverse prefix variances (segmented)
  * The decision logic whose *order* defines the result -- the binary max-heap of multi-clusters (boost::heap::
  * priority_queue = std::vector + push_heap/pop_heap), the front-inserted singleton list, the sequential fp32 prefix
  * sums of weightedSample (1534-1580), std::sort of (projection, vrl) pairs and the first-minimum argmin (664-675) --
@@ -26,6 +26,9 @@
 #include <algorithm>
 #include <numeric>
 #include <cmath>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include "context.h"
 
 namespace alvrl {
@@ -41,7 +44,10 @@ struct ClTask {                 /* one Clustering object's piece of work in a ba
     uint64_t listOff;           /* instance's vrl list in dLists */
     uint64_t cwOff;             /* instance's column weights in dCw */
     uint64_t outOff;            /* first step / projection slot of this task in the round scratch */
-    uint64_t partOff;           /* first partial slot (steps x rowBlocks) */
+    uint64_t stepOff;           /* first step slot of this task in the w / W / partial arrays of the launch */
+    uint64_t partOff;           /* first partial slot (steps x rowBlocks double2) */
+    uint64_t carryOff;          /* first carry slot (nseg x rowBlocks x CL_THREADS doubles) */
+    uint32_t nseg, segOff;      /* number of CL_SEG-step segments, first global segment index */
     uint64_t dirOff;            /* direction vector slot */
     double lw;                  /* uniform locality weight 1 / nr */
 };
@@ -150,107 +156,182 @@ __global__ void k_scatter_lists(const ClTask *__restrict__ tasks, const uint32_t
 }
 
 /*
- * calculateClusterVariance (1058-1120).  thread = row, sequential over the VRLs of the range (reverse: from the end),
- * CL_CHUNK steps at a time: the loads of a chunk are issued together, the weight-only factors of the recurrence are
- * computed once per step by one thread, and the per-step sums over rows are reduced from shared memory by one warp
- * per step instead of a block-wide reduction per step.
+ * calculateClusterVariance (1058-1120) as a segmented, fully parallel pipeline.
+ *
+ * Reference recurrence per row r over the ordered VRLs k (x = mean, w = column weight, W = prefix weight):
+ *     M_r(k) = (W_k / W_{k-1})^2 M_r(k-1) + (1/w_k + 1/W_{k-1}) (w_k S_r(k-1) - W_{k-1} x_r(k))^2,   S_r = prefix sum of x_r
+ *     first(k)  = sum_r lw M_r(k) / W_k          second(k) = sum_r lw W_k sumVars_r(k),  sumVars_r = prefix sum of var_r / w
+ * The factors (W_k / W_{k-1})^2 telescope: M_r(k) = W_k^2 sum_{j<=k} b_r(j) / W_j^2, and the sum over rows commutes with the
+ * prefix over k.  So a range is cut into segments of CL_SEG steps that run concurrently:
+ *     k_weights    w_k (gather) and W_k (block scan)                                  per task
+ *     k_seg_sums   column sums of x over each segment                                  per segment x row block
+ *     k_carry      exclusive prefix of those sums over the segments -> S carry-in      per task x row block
+ *     k_seg_main   thread = row walks its segment: B(k) = sum_r tmp_r(k)^2, V(k) = sum_r var_r(k) / w_k   (row-reduced per step)
+ *     k_final      Q = scan(c2_k B_k / W_k^2), SV = scan(V_k); first = lw W_k Q_k, second = lw W_k SV_k -> (float, float)
+ * All sums are double; they differ from the reference's sequential order in the last double bits only.
  */
-__global__ void __launch_bounds__(CL_THREADS) k_cluster_variance(const float2 *__restrict__ R, uint32_t ldR, const ClTask *__restrict__ tasks,
-                                                                 const uint32_t *__restrict__ lists, const float *__restrict__ cw,
-                                                                 double2 *__restrict__ partial, double *__restrict__ Wk) {
-    __shared__ double sM[CL_CHUNK][CL_THREADS];
-    __shared__ double sV[CL_CHUNK][CL_THREADS];
-    __shared__ double sC1[CL_CHUNK], sC2[CL_CHUNK], sRw[CL_CHUNK], sWgt[CL_CHUNK], sW[CL_CHUNK + 1];
-    __shared__ uint32_t sVid[CL_CHUNK];
-    const ClTask t = tasks[blockIdx.y];
-    if (blockIdx.x >= t.rowBlocks) return;
-    const uint32_t tid = threadIdx.x;
-    const uint32_t lr = blockIdx.x * CL_THREADS + tid;
-    const bool active = lr < t.nr;
-    const uint32_t row = t.r0 + (active ? lr : 0);
+#define CL_SEG 256
+
+struct SegDesc { uint32_t task, seg; };
+
+/* inclusive block scan of one value per thread with a running carry (all threads get the same carry back) */
+__device__ __forceinline__ double block_scan_incl(double v, double &carry, double *sh) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) { const double n = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += n; }
+    if (lane == 31) sh[warp] = v;
+    __syncthreads();
+    double off = 0, total = 0;
+    for (int i = 0; i < CL_THREADS / 32; i++) { const double t = sh[i]; if (i < warp) off += t; total += t; }
+    const double r = carry + off + v;
+    __syncthreads();
+    carry += total;
+    return r;
+}
+
+__global__ void __launch_bounds__(CL_THREADS) k_weights(const ClTask *__restrict__ tasks, const uint32_t *__restrict__ lists, const float *__restrict__ cw,
+                                                        double *__restrict__ wArr, double *__restrict__ WArr) {
+    __shared__ double sh[CL_THREADS / 32];
+    const ClTask t = tasks[blockIdx.x];
     const uint32_t n = t.end - t.begin;
-    const uint32_t *list = lists + t.listOff;
-    const float *w = cw + t.cwOff;
-    double sum = 0, M = 0, sumVars = 0;
-    if (tid == 0) sW[0] = 0;
-    for (uint32_t k0 = 0; k0 < n; k0 += CL_CHUNK) {
-        const uint32_t cnt = min((uint32_t) CL_CHUNK, n - k0);
-        /* weight-only part: prefix weight sums (sequential, double) and the factors of the M recurrence */
-        if (tid == 0) {
-            double W = sW[0];
-            for (uint32_t j = 0; j < cnt; j++) {
-                const uint32_t idx = t.reverse ? (t.end - 1 - (k0 + j)) : (t.begin + k0 + j);
-                const uint32_t vid = list[idx];
-                const double weight = w[vid];
-                const double newW = W + weight;
-                sVid[j] = vid;
-                sWgt[j] = weight;
-                sRw[j] = 1.0 / weight;
-                if (k0 + j > 0) { sC1[j] = (newW * newW) / (W * W); sC2[j] = 1.0 / weight + 1.0 / W; }
-                else { sC1[j] = 0; sC2[j] = 0; }
-                W = newW;
-                sW[j + 1] = W;
-            }
+    double carry = 0;
+    for (uint32_t k0 = 0; k0 < n; k0 += CL_THREADS) {
+        const uint32_t k = k0 + threadIdx.x;
+        double w = 0;
+        if (k < n) {
+            const uint32_t idx = t.reverse ? (t.end - 1 - k) : (t.begin + k);
+            w = (double) cw[t.cwOff + lists[t.listOff + idx]];
         }
-        __syncthreads();
-        float2 x[CL_CHUNK];
-#pragma unroll
-        for (uint32_t j = 0; j < CL_CHUNK; j++) x[j] = (j < cnt) ? R[(size_t) sVid[j] * ldR + row] : make_float2(0, 0);
-#pragma unroll
-        for (uint32_t j = 0; j < CL_CHUNK; j++) {
-            if (j < cnt) {
-                const double xm = x[j].x;
-                if (k0 + j > 0) {
-                    const double tmp = sWgt[j] * sum - sW[j] * xm;
-                    M = sC1[j] * M + sC2[j] * (tmp * tmp);
-                }
-                sumVars += (double) x[j].y * sRw[j];
-                sum = sum + xm;
-                sM[j][tid] = active ? M : 0.0;
-                sV[j][tid] = active ? sumVars : 0.0;
-            }
-        }
-        __syncthreads();
-        /* one warp per step: sum over the rows of this block */
-        const uint32_t warp = tid >> 5, lane = tid & 31;
-        for (uint32_t j = warp; j < cnt; j += CL_THREADS / 32) {
-            double a = 0, b = 0;
-            for (uint32_t i = lane; i < CL_THREADS; i += 32) { a += sM[j][i]; b += sV[j][i]; }
-            for (int o = 16; o > 0; o >>= 1) { a += __shfl_down_sync(0xffffffffu, a, o); b += __shfl_down_sync(0xffffffffu, b, o); }
-            if (lane == 0) {
-                const uint32_t step = k0 + j;
-                if (!t.finalOnly || step == n - 1) {
-                    const uint64_t slot = t.finalOnly ? 0 : step;
-                    partial[t.partOff + slot * t.rowBlocks + blockIdx.x] = make_double2(a, b);
-                    if (blockIdx.x == 0) Wk[t.outOff + slot] = sW[j + 1];
-                }
-            }
-        }
-        __syncthreads();
-        if (tid == 0) sW[0] = sW[cnt];
+        const double W = block_scan_incl(w, carry, sh);
+        if (k < n) { wArr[t.stepOff + k] = w; WArr[t.stepOff + k] = W; }
     }
 }
 
-/* (undersampling variance, integration variance) prefix pairs: inner_prod(localityWeights, M / weightSum),
- * inner_prod(localityWeights, sumVars * weightSum) (1098-1106), uniform locality weights */
-__global__ void k_combine(const ClTask *__restrict__ tasks, const double2 *__restrict__ partial, const double *__restrict__ Wk, float2 *__restrict__ out) {
-    const ClTask t = tasks[blockIdx.y];
-    const uint32_t n = t.finalOnly ? 1 : (t.end - t.begin);
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    double a = 0, b = 0;
-    for (uint32_t rb = 0; rb < t.rowBlocks; rb++) { const double2 p = partial[t.partOff + (uint64_t) s * t.rowBlocks + rb]; a += p.x; b += p.y; }
-    const double W = Wk[t.outOff + s];
-    const bool first = !t.finalOnly && s == 0;
-    const bool single = t.finalOnly && (t.end - t.begin) == 1;
-    float2 r;
-    r.x = (first || single) ? 0.0f : (float) (t.lw * (a / W));
-    r.y = (float) (t.lw * (b * W));
-    out[t.outOff + s] = r;
+__global__ void __launch_bounds__(CL_THREADS) k_seg_sums(const float2 *__restrict__ R, uint32_t ldR, const ClTask *__restrict__ tasks,
+                                                         const SegDesc *__restrict__ segs, const uint32_t *__restrict__ lists, double *__restrict__ carry) {
+    const SegDesc sd = segs[blockIdx.x];
+    const ClTask t = tasks[sd.task];
+    if (blockIdx.y >= t.rowBlocks || t.nseg <= 1) return;
+    const uint32_t lr = blockIdx.y * CL_THREADS + threadIdx.x;
+    const uint32_t row = t.r0 + (lr < t.nr ? lr : 0);
+    const uint32_t n = t.end - t.begin, k0 = sd.seg * CL_SEG, k1 = min(n, k0 + CL_SEG);
+    const uint32_t *list = lists + t.listOff;
+    double s = 0;
+    for (uint32_t k = k0; k < k1; k++) {
+        const uint32_t idx = t.reverse ? (t.end - 1 - k) : (t.begin + k);
+        s += (double) R[(size_t) list[idx] * ldR + row].x;
+    }
+    carry[t.carryOff + (uint64_t) sd.seg * (t.rowBlocks * CL_THREADS) + lr] = s;
+}
+
+__global__ void __launch_bounds__(CL_THREADS) k_carry(const ClTask *__restrict__ tasks, double *__restrict__ carry) {
+    const ClTask t = tasks[blockIdx.x];
+    if (blockIdx.y >= t.rowBlocks || t.nseg <= 1) return;
+    const uint32_t lr = blockIdx.y * CL_THREADS + threadIdx.x;
+    const uint64_t stride = (uint64_t) t.rowBlocks * CL_THREADS;
+    double run = 0;
+    for (uint32_t sgi = 0; sgi < t.nseg; sgi++) {
+        double *p = &carry[t.carryOff + sgi * stride + lr];
+        const double v = *p;
+        *p = run;
+        run += v;
+    }
+}
+
+__global__ void __launch_bounds__(CL_THREADS) k_seg_main(const float2 *__restrict__ R, uint32_t ldR, const ClTask *__restrict__ tasks,
+                                                         const SegDesc *__restrict__ segs, const uint32_t *__restrict__ lists,
+                                                         const double *__restrict__ wArr, const double *__restrict__ WArr,
+                                                         const double *__restrict__ carry, double2 *__restrict__ partial) {
+    __shared__ double sB[CL_CHUNK][CL_THREADS];
+    __shared__ double sV[CL_CHUNK][CL_THREADS];
+    const SegDesc sd = segs[blockIdx.x];
+    const ClTask t = tasks[sd.task];
+    if (blockIdx.y >= t.rowBlocks) return;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t lr = blockIdx.y * CL_THREADS + tid;
+    const bool active = lr < t.nr;
+    const uint32_t row = t.r0 + (active ? lr : 0);
+    const uint32_t n = t.end - t.begin, kBeg = sd.seg * CL_SEG, kEnd = min(n, kBeg + CL_SEG);
+    const uint32_t *list = lists + t.listOff;
+    const double *w = wArr + t.stepOff, *W = WArr + t.stepOff;
+    double S = (t.nseg > 1) ? carry[t.carryOff + (uint64_t) sd.seg * (t.rowBlocks * CL_THREADS) + lr] : 0.0;
+    for (uint32_t k0 = kBeg; k0 < kEnd; k0 += CL_CHUNK) {
+        const uint32_t cnt = min((uint32_t) CL_CHUNK, kEnd - k0);
+        float2 x[CL_CHUNK];
+#pragma unroll
+        for (uint32_t j = 0; j < CL_CHUNK; j++) {
+            if (j < cnt) {
+                const uint32_t k = k0 + j;
+                const uint32_t idx = t.reverse ? (t.end - 1 - k) : (t.begin + k);
+                x[j] = R[(size_t) list[idx] * ldR + row];
+            } else x[j] = make_float2(0, 0);
+        }
+#pragma unroll
+        for (uint32_t j = 0; j < CL_CHUNK; j++) {
+            if (j < cnt) {
+                const uint32_t k = k0 + j;
+                const double wk = w[k], Wprev = k ? W[k - 1] : 0.0;
+                const double xm = x[j].x;
+                const double tmp = wk * S - Wprev * xm;
+                S += xm;
+                sB[j][tid] = active ? tmp * tmp : 0.0;
+                sV[j][tid] = active ? (double) x[j].y / wk : 0.0;
+            }
+        }
+        __syncthreads();
+        const uint32_t warp = tid >> 5, lane = tid & 31;
+        for (uint32_t j = warp; j < cnt; j += CL_THREADS / 32) {
+            double a = 0, b = 0;
+            for (uint32_t i = lane; i < CL_THREADS; i += 32) { a += sB[j][i]; b += sV[j][i]; }
+            for (int o = 16; o > 0; o >>= 1) { a += __shfl_down_sync(0xffffffffu, a, o); b += __shfl_down_sync(0xffffffffu, b, o); }
+            if (lane == 0) partial[t.partOff + (uint64_t) (k0 + j) * t.rowBlocks + blockIdx.y] = make_double2(a, b);
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(CL_THREADS) k_final(const ClTask *__restrict__ tasks, const double *__restrict__ wArr, const double *__restrict__ WArr,
+                                                      const double2 *__restrict__ partial, float2 *__restrict__ out) {
+    __shared__ double sh[CL_THREADS / 32];
+    const ClTask t = tasks[blockIdx.x];
+    const uint32_t n = t.end - t.begin;
+    const double *w = wArr + t.stepOff, *W = WArr + t.stepOff;
+    double carryQ = 0, carryV = 0;
+    for (uint32_t k0 = 0; k0 < n; k0 += CL_THREADS) {
+        const uint32_t k = k0 + threadIdx.x;
+        double tq = 0, tv = 0, Wk = 1;
+        if (k < n) {
+            double B = 0, V = 0;
+            for (uint32_t rb = 0; rb < t.rowBlocks; rb++) { const double2 p = partial[t.partOff + (uint64_t) k * t.rowBlocks + rb]; B += p.x; V += p.y; }
+            Wk = W[k];
+            if (k > 0) tq = (1.0 / w[k] + 1.0 / W[k - 1]) * B / (Wk * Wk);
+            tv = V;
+        }
+        const double Q = block_scan_incl(tq, carryQ, sh);
+        const double SV = block_scan_incl(tv, carryV, sh);
+        if (k < n) {
+            float2 r;
+            r.x = (k == 0) ? 0.0f : (float) (t.lw * (Wk * Q));
+            r.y = (float) (t.lw * (SV * Wk));
+            if (!t.finalOnly) out[t.outOff + k] = r;
+            else if (k == n - 1) out[t.outOff] = r;
+        }
+    }
 }
 
 /* ---- host side ------------------------------------------------------------------------------------ */
 namespace {
+
+/* optional phase timers of the clustering rounds (ALVRL_PROFILE=1) */
+struct Prof {
+    double t[8] = {0, 0, 0, 0, 0, 0, 0, 0}; uint64_t rounds = 0, tasks = 0, steps = 0;
+    bool on = getenv("ALVRL_PROFILE") != nullptr;
+    static double now() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+    ~Prof() {
+        if (on && rounds) fprintf(stderr, "[alvrl clustering] rounds %llu tasks %llu steps %llu | ms: sample+tasks %.1f dir+proj %.1f d2h-proj %.1f sort %.1f "
+                                  "h2d+variance %.1f d2h-pairs %.1f argmin %.1f\n", (unsigned long long) rounds, (unsigned long long) tasks,
+                                  (unsigned long long) steps, t[0], t[1], t[2], t[3], t[4], t[5], t[6]);
+    }
+};
 
 struct ClusterNode {                                                           /* Preprocessor.cpp:289-298 */
     float undersamplingVar, integrationVar; uint32_t begin, end;
@@ -347,14 +428,16 @@ struct Inst {                                                                  /
 
 /* device-side workspace shared by all Clustering objects of one buildClusters call */
 struct Workspace {
-    alvrl_ctx *c; cudaStream_t st; uint32_t N, ldR; const float2 *R;
+    alvrl_ctx *c = nullptr; cudaStream_t st = nullptr; uint32_t N = 0, ldR = 0; const float2 *R = nullptr;
     DevBuf<uint32_t> dLists; DevBuf<float> dCw;
     DevBuf<ClTask> dTasks; DevBuf<float> dDir, dProj; DevBuf<uint32_t> dFlags, dStaged;
-    DevBuf<double2> dPartial, dUncl; DevBuf<double> dWk; DevBuf<float2> dPairs;
+    DevBuf<double2> dPartial, dUncl; DevBuf<double> dW1, dW2, dCarry; DevBuf<float2> dPairs; DevBuf<SegDesc> dSegs;
     std::vector<Inst *> insts;
+    Prof prof;
 
     template <typename T> static void ensure(DevBuf<T> &b, size_t n) { if (b.n < n) b.alloc(n + n / 4 + 16); }
-    void launches(uint32_t k) { c->stats.kernelLaunches += k; }
+    uint32_t launchCount = 0; bool serialSort = false;
+    void launches(uint32_t k) { launchCount += k; }
 
     void allocInstances() {
         ensure(dLists, insts.size() * (size_t) N); ensure(dCw, insts.size() * (size_t) N);
@@ -394,16 +477,42 @@ struct Workspace {
         ALVRL_CUDA(cudaMemcpyAsync(dLists.p, all.data(), all.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         ALVRL_CUDA(cudaStreamSynchronize(st));
     }
+    /* calculateClusterVariance for a batch of ranges; results in dPairs at task.outOff (n pairs, or 1 when finalOnly).
+     * Returns the number of result slots. */
+    uint64_t runVariance(std::vector<ClTask> &tasks, DevBuf<ClTask> &dT) {
+        uint64_t out = 0, steps = 0, carry = 0, part = 0; uint32_t segTotal = 0, maxRb = 1;
+        std::vector<SegDesc> segs;
+        for (size_t i = 0; i < tasks.size(); i++) {
+            ClTask &t = tasks[i];
+            const uint32_t n = t.end - t.begin;
+            t.outOff = out; t.stepOff = steps; t.carryOff = carry; t.partOff = part;
+            part += (uint64_t) n * t.rowBlocks;
+            t.nseg = (n + CL_SEG - 1) / CL_SEG; t.segOff = segTotal;
+            out += t.finalOnly ? 1 : n; steps += n;
+            if (t.nseg > 1) carry += (uint64_t) t.nseg * t.rowBlocks * CL_THREADS;
+            for (uint32_t sgi = 0; sgi < t.nseg; sgi++) segs.push_back(SegDesc{(uint32_t) i, sgi});
+            segTotal += t.nseg; maxRb = std::max(maxRb, t.rowBlocks);
+        }
+        ensure(dW1, steps); ensure(dW2, steps); ensure(dCarry, std::max<uint64_t>(carry, 1)); ensure(dPartial, part); ensure(dPairs, out);
+        dT.upload(tasks, st);
+        dSegs.upload(segs, st);
+        const uint32_t T = (uint32_t) tasks.size();
+        k_weights<<<T, CL_THREADS, 0, st>>>(dT.p, dLists.p, dCw.p, dW1.p, dW2.p);
+        if (carry) {
+            k_seg_sums<<<dim3(segTotal, maxRb), CL_THREADS, 0, st>>>(R, ldR, dT.p, dSegs.p, dLists.p, dCarry.p);
+            k_carry<<<dim3(T, maxRb), CL_THREADS, 0, st>>>(dT.p, dCarry.p);
+            launches(2);
+        }
+        k_seg_main<<<dim3(segTotal, maxRb), CL_THREADS, 0, st>>>(R, ldR, dT.p, dSegs.p, dLists.p, dW1.p, dW2.p, dCarry.p, dPartial.p);
+        k_final<<<T, CL_THREADS, 0, st>>>(dT.p, dW1.p, dW2.p, dPartial.p, dPairs.p);
+        launches(3);
+        ALVRL_CUDA(cudaGetLastError());
+        return out;
+    }
     /* variance of whole ranges (addCluster(begin, end), 576-579): one (uvar, ivar) pair per task */
     std::vector<float2> rangeVariances(std::vector<ClTask> &tasks) {
-        uint64_t out = 0, part = 0; uint32_t maxRb = 1;
-        for (ClTask &t : tasks) { t.finalOnly = 1; t.reverse = 0; t.outOff = out; t.partOff = part; out += 1; part += t.rowBlocks; maxRb = std::max(maxRb, t.rowBlocks); }
-        ensure(dPartial, part); ensure(dWk, out); ensure(dPairs, out);
-        dTasks.upload(tasks, st);
-        k_cluster_variance<<<dim3(maxRb, (uint32_t) tasks.size()), CL_THREADS, 0, st>>>(R, ldR, dTasks.p, dLists.p, dCw.p, dPartial.p, dWk.p);
-        k_combine<<<dim3(1, (uint32_t) tasks.size()), 32, 0, st>>>(dTasks.p, dPartial.p, dWk.p, dPairs.p);
-        launches(2);
-        ALVRL_CUDA(cudaGetLastError());
+        for (ClTask &t : tasks) { t.finalOnly = 1; t.reverse = 0; }
+        const uint64_t out = runVariance(tasks, dTasks);
         std::vector<float2> res(out);
         dPairs.download(res.data(), out, st);
         return res;
@@ -496,6 +605,8 @@ struct Workspace {
         const size_t T = round.size();
         std::vector<ClTask> tasks(T);
         uint64_t out = 0, dirOff = 0;
+        double p0 = Prof::now(), p1;
+        prof.rounds++; prof.tasks += T;
         for (size_t i = 0; i < T; i++) {
             Inst &in = *round[i];
             in.cur = in.popMulti();
@@ -512,7 +623,9 @@ struct Workspace {
             tasks[i] = t;
         }
         ensure(dDir, dirOff); ensure(dProj, out); ensure(dFlags, T); ensure(dStaged, out);
+        prof.steps += out;
         dTasks.upload(tasks, st);
+        p1 = Prof::now(); prof.t[0] += p1 - p0; p0 = p1;
         uint32_t maxN = 0; for (const ClTask &t : tasks) maxN = std::max(maxN, t.end - t.begin);
         k_direction<<<(uint32_t) T, 128, 0, st>>>(R, ldR, dTasks.p, dDir.p, dFlags.p);
         k_project<<<dim3((maxN + 127) / 128, (uint32_t) T), 128, 0, st>>>(R, ldR, dTasks.p, dLists.p, dDir.p, dProj.p);
@@ -520,6 +633,7 @@ struct Workspace {
         ALVRL_CUDA(cudaGetLastError());
         std::vector<uint32_t> flags(T);
         dFlags.download(flags.data(), T, st);
+        p1 = Prof::now(); prof.t[1] += p1 - p0; p0 = p1;
         bool redo = false;
         for (size_t i = 0; i < T; i++) if (flags[i]) {
             /* degenerate centres: direction uniform on the n-sphere, squareToStdNormal(next2D()).x per row (616-622) */
@@ -547,6 +661,7 @@ struct Workspace {
         }
         std::vector<float> proj(out);
         dProj.download(proj.data(), out, st);
+        p1 = Prof::now(); prof.t[2] += p1 - p0; p0 = p1;
         /* std::sort of (projection, vrl) pairs (641-646), instances in parallel on host threads */
         std::vector<uint32_t> staged(out);
         auto sortOne = [&](size_t i) {
@@ -560,34 +675,26 @@ struct Workspace {
         };
         {
             const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-            if (T == 1 || hw == 1) for (size_t i = 0; i < T; i++) sortOne(i);
+            if (T == 1 || hw == 1 || serialSort || out < 4096) for (size_t i = 0; i < T; i++) sortOne(i);
             else {
                 std::vector<std::thread> th;
                 for (unsigned w = 0; w < hw; w++) th.emplace_back([&, w]() { for (size_t i = w; i < T; i += hw) sortOne(i); });
                 for (auto &x : th) x.join();
             }
         }
+        p1 = Prof::now(); prof.t[3] += p1 - p0; p0 = p1;
         ALVRL_CUDA(cudaMemcpyAsync(dStaged.p, staged.data(), out * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         k_scatter_lists<<<dim3((maxN + 127) / 128, (uint32_t) T), 128, 0, st>>>(dTasks.p, dStaged.p, dLists.p);
         /* forward and reverse prefix variances (648-657) */
         std::vector<ClTask> vt(2 * T);
-        uint64_t part = 0, steps = 0; uint32_t maxRb = 1;
         for (size_t i = 0; i < T; i++)
-            for (int rev = 0; rev < 2; rev++) {
-                ClTask t = tasks[i];
-                t.reverse = rev; t.finalOnly = 0; t.outOff = steps; t.partOff = part;
-                steps += t.end - t.begin; part += (uint64_t) (t.end - t.begin) * t.rowBlocks; maxRb = std::max(maxRb, t.rowBlocks);
-                vt[2 * i + rev] = t;
-            }
-        ensure(dPartial, part); ensure(dWk, steps); ensure(dPairs, steps);
-        DevBuf<ClTask> &dT2 = dTasks2;
-        dT2.upload(vt, st);
-        k_cluster_variance<<<dim3(maxRb, (uint32_t) vt.size()), CL_THREADS, 0, st>>>(R, ldR, dT2.p, dLists.p, dCw.p, dPartial.p, dWk.p);
-        k_combine<<<dim3((maxN + 127) / 128, (uint32_t) vt.size()), 128, 0, st>>>(dT2.p, dPartial.p, dWk.p, dPairs.p);
-        launches(3);
-        ALVRL_CUDA(cudaGetLastError());
+            for (int rev = 0; rev < 2; rev++) { ClTask t = tasks[i]; t.reverse = rev; t.finalOnly = 0; vt[2 * i + rev] = t; }
+        const uint64_t steps = runVariance(vt, dTasks2);
+        ALVRL_CUDA(cudaStreamSynchronize(st));
+        p1 = Prof::now(); prof.t[4] += p1 - p0; p0 = p1;
         std::vector<float2> pairs(steps);
         dPairs.download(pairs.data(), steps, st);
+        p1 = Prof::now(); prof.t[5] += p1 - p0; p0 = p1;
         for (size_t i = 0; i < T; i++) {
             Inst &in = *round[i];
             const uint32_t begin = tasks[i].begin, end = tasks[i].end, n = end - begin;
@@ -605,6 +712,7 @@ struct Workspace {
             in.addCluster(begin, splitIndex, fromStart[bestIndex - 1].x, fromStart[bestIndex - 1].y);
             in.addCluster(splitIndex, end, fromEnd[n - 1 - bestIndex].x, fromEnd[n - 1 - bestIndex].y);
         }
+        p1 = Prof::now(); prof.t[6] += p1 - p0;
     }
     DevBuf<ClTask> dTasks2;
 };
@@ -694,6 +802,7 @@ void build_clusters_device(alvrl_ctx *c, bool needFallback) {
                 if (g.failed) throw Error(ALVRL_ERR_ARG, "Couldn't refine global clustering!");
                 c->globalVrlsPerCluster = g.vrlsPerCluster();
                 c->nearTieSplits += g.nearTies;
+                c->stats.kernelLaunches += ws.launchCount; ws.launchCount = 0;
             } else c->globalVrlsPerCluster.assign(1, nonZero);
         }
         if (!zero.empty()) c->globalVrlsPerCluster.push_back(zero);
@@ -709,6 +818,7 @@ void build_clusters_device(alvrl_ctx *c, bool needFallback) {
         if (g.failed) throw Error(ALVRL_ERR_ARG, "couldn't refine global clustering! (but all VRLs should be non-zero!)");
         g.sampleRepresentatives(c->fallBackVrls, c->fallBackWeight);             /* 179 */
         c->nearTieSplits += g.nearTies;
+        c->stats.kernelLaunches += w2.launchCount;
         c->haveFallback = true;
     };
     if (lazyFallbackCall) { computeFallback(); return; }
@@ -741,18 +851,50 @@ void build_clusters_device(alvrl_ctx *c, bool needFallback) {
     ws.insts.clear();
     for (auto &p : store) ws.insts.push_back(p.get());
     if (!ws.insts.empty()) {
-        ws.allocInstances();
-        ws.columnWeights();
-        ws.construct(c->globalVrlsPerCluster);
         if (sfmt) {
             /* a shared sequential stream: refine and sample slice after slice, in slice order (230-233, 746-752) */
+            ws.allocInstances();
+            ws.columnWeights();
+            ws.construct(c->globalVrlsPerCluster);
             for (Inst *in : ws.insts) {
                 if (c->P.localRefinement) ws.refine({in}, c->P.localUndersampling);
                 if (!in->failed) in->sampleRepresentatives(c->selectedVrls[in->id], c->clusterWeight[in->id]);
             }
+            c->stats.kernelLaunches += ws.launchCount;
         } else {
-            if (c->P.localRefinement) ws.refine(ws.insts, c->P.localUndersampling);
-            for (Inst *in : ws.insts) if (!in->failed) in->sampleRepresentatives(c->selectedVrls[in->id], c->clusterWeight[in->id]);
+            /* independent per-slice streams: the Clustering objects are dealt to a few host threads, each driving its own CUDA
+             * stream, so that one group's host work (sorting, heap updates) overlaps the other groups' kernels and copies */
+            const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+            const size_t nGroups = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(8, hw / 2), ws.insts.size() / 4 + 1));
+            std::vector<std::unique_ptr<Workspace>> groups(nGroups);
+            std::vector<std::string> errors(nGroups);
+            std::vector<std::thread> threads;
+            for (size_t gI = 0; gI < nGroups; gI++) {
+                groups[gI].reset(new Workspace());
+                Workspace &w2 = *groups[gI];
+                w2.c = c; w2.N = N; w2.ldR = c->ldR; w2.R = c->dR.p; w2.serialSort = nGroups > 1;
+                for (size_t i = gI; i < ws.insts.size(); i += nGroups) w2.insts.push_back(ws.insts[i]);
+            }
+            for (size_t gI = 0; gI < nGroups; gI++) threads.emplace_back([&, gI]() {
+                Workspace &w2 = *groups[gI];
+                try {
+                    ALVRL_CUDA(cudaSetDevice(c->device));
+                    ALVRL_CUDA(cudaStreamCreateWithFlags(&w2.st, cudaStreamNonBlocking));
+                    w2.allocInstances();
+                    w2.columnWeights();
+                    w2.construct(c->globalVrlsPerCluster);
+                    if (c->P.localRefinement) w2.refine(w2.insts, c->P.localUndersampling);
+                    for (Inst *in : w2.insts) if (!in->failed) in->sampleRepresentatives(c->selectedVrls[in->id], c->clusterWeight[in->id]);
+                    cudaStreamSynchronize(w2.st);
+                } catch (const std::exception &e) { errors[gI] = e.what(); }
+                if (w2.st) { cudaStreamDestroy(w2.st); w2.st = nullptr; }
+            });
+            for (auto &t : threads) t.join();
+            for (size_t gI = 0; gI < nGroups; gI++) {
+                c->stats.kernelLaunches += groups[gI]->launchCount;
+                if (!errors[gI].empty()) throw Error(ALVRL_ERR_ARG, errors[gI]);
+            }
+            groups.clear();          /* frees the group workspaces before the fallback, if any */
         }
         bool anyFailed = false;
         for (Inst *in : ws.insts) { anyFailed |= in->failed; c->nearTieSplits += in->nearTies; }
