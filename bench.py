@@ -246,7 +246,7 @@ def run_ours(a):
     clocks.start()
     ms, pairs, launches, kr, kp, kpairs, st = timed(False, a.steps)
     clk = clocks.finish()
-    ms_e, pairs_e, _, _, _, _, _ = timed(True, a.steps)
+    ms_e, pairs_e, _, _, _, _, st_e = timed(True, a.steps)
 
     # roofline of the dominant kernel (k_build_R_fast): algorithmic flops per launch / CUDA-event duration of that launch,
     # measured inside the library on the launching stream (alvrl_stats.msTransportKernelR)
@@ -281,6 +281,7 @@ def run_ours(a):
                 "gpu_launches": int(launches), "clocks": clk, "roofline": roof,
                 "phases_ms": {"slices": st.msSlices, "slice_mapping": st.msSliceMapping, "build_R": st.msBuildR, "clusters": st.msClusters,
                               "render_kernel": st.msTransportKernelRender},
+                "e2e_phases_ms": {"slices": st_e.msSlices, "build_R": st_e.msBuildR, "clusters": st_e.msClusters, "render_total": st_e.msRender},
                 "contributions_per_step": pairs / a.steps, "rows": st.numRows, "vrls": st.numVrls, "slices": st.numSlices}
         if not a.no_cpu_baseline and world == 1:
             line["cpu_baseline"], _ = cpu_baseline(pkg, scene, vrls, params, hg, a.cpu_seconds, desc["workload"])

@@ -29,6 +29,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cub/device/device_segmented_sort.cuh>
 #include "context.h"
 
 namespace alvrl {
@@ -40,14 +41,16 @@ struct ClTask {                 /* one Clustering object's piece of work in a ba
     uint32_t r0, nr, rowBlocks; /* rows of the local matrix L_i (getLocalMatrix with neighbourWeight <= 0, 779-794) */
     uint32_t begin, end;        /* range in the instance's vrl list */
     uint32_t reverse, finalOnly;
-    uint32_t vrl1, vrl2;        /* split centres */
+    uint32_t vrl1, vrl2;        /* split centres (host rounds) */
+    float u1, u2;               /* uniforms of the two weightedSample calls (device rounds) */
     uint64_t listOff;           /* instance's vrl list in dLists */
     uint64_t cwOff;             /* instance's column weights in dCw */
     uint64_t outOff;            /* first step / projection slot of this task in the round scratch */
     uint64_t stepOff;           /* first step slot of this task in the w / W / partial arrays of the launch */
     uint64_t partOff;           /* first partial slot (steps x rowBlocks double2) */
     uint64_t carryOff;          /* first carry slot (nseg x rowBlocks x CL_THREADS doubles) */
-    uint32_t nseg, segOff;      /* number of CL_SEG-step segments, first global segment index */
+    uint32_t nseg, segOff;      /* number of segLen-step segments, first global segment index */
+    uint32_t segLen;            /* steps per segment: short for small ranges (latency), CL_SEG for large ones */
     uint64_t dirOff;            /* direction vector slot */
     double lw;                  /* uniform locality weight 1 / nr */
 };
@@ -132,21 +135,69 @@ __global__ void k_direction(const float2 *__restrict__ R, uint32_t ldR, const Cl
     for (uint32_t r = threadIdx.x; r < t.nr; r += blockDim.x) dir[t.dirOff + r] = (c2[r].x - c1[r].x) / sDiffLen;
 }
 
-/* projections of the normalised columns on the direction (625-640), sequential fp32 in row order */
-__global__ void k_project(const float2 *__restrict__ R, uint32_t ldR, const ClTask *__restrict__ tasks, const uint32_t *__restrict__ lists,
-                          const float *__restrict__ dir, float *__restrict__ proj) {
+/* projections of the normalised columns on the direction (625-640), sequential fp32 in row order.
+ * warp = VRL: the lanes fetch 32 consecutive rows of the column at a time (coalesced, all chunks in flight), and the strictly
+ * ordered sums are carried by a shuffle-broadcast chain, so a column costs a few microseconds instead of 2 x nr dependent
+ * DRAM round trips.  keys != NULL: also emit the 64-bit sort key that orders like std::sort on pair<float, uint32_t> (641). */
+#define CL_PROJ_WARPS 4
+#define CL_PROJ_MAXCH 8          /* columns of up to 256 rows stay in registers; longer ones are re-read per pass */
+__global__ void __launch_bounds__(CL_PROJ_WARPS * 32) k_project(const float2 *__restrict__ R, uint32_t ldR, const ClTask *__restrict__ tasks,
+                                                               const uint32_t *__restrict__ lists, const float *__restrict__ dir,
+                                                               float *__restrict__ proj, uint64_t *__restrict__ keys) {
     const ClTask t = tasks[blockIdx.y];
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t j = blockIdx.x * CL_PROJ_WARPS + (threadIdx.x >> 5);
     if (j >= t.end - t.begin) return;
     const uint32_t vid = lists[t.listOff + t.begin + j];
     const float2 *col = R + (size_t) vid * ldR + t.r0;
     const float *d = dir + t.dirOff;
+    const uint32_t nch = (t.nr + 31) / 32;
+    float x[CL_PROJ_MAXCH], dv[CL_PROJ_MAXCH];
+    const bool inReg = nch <= CL_PROJ_MAXCH;
+    if (inReg) {
+#pragma unroll
+        for (uint32_t c = 0; c < CL_PROJ_MAXCH; c++) {
+            const uint32_t r = c * 32 + lane;
+            x[c] = (c < nch && r < t.nr) ? col[r].x : 0.0f;
+            dv[c] = (c < nch && r < t.nr) ? d[r] : 0.0f;
+        }
+    }
     float s = 0;
-    for (uint32_t r = 0; r < t.nr; r++) { const float u = fabsf(col[r].x); s += u * u; }
+    for (uint32_t c = 0; c < nch; c++) {
+        float xv;
+        if (inReg) {
+            xv = 0;
+#pragma unroll
+            for (uint32_t k = 0; k < CL_PROJ_MAXCH; k++) if (k == c) xv = x[k];
+        } else { const uint32_t r = c * 32 + lane; xv = r < t.nr ? col[r].x : 0.0f; }
+        const float u = fabsf(xv), sq = u * u;
+        const uint32_t cnt = min(32u, t.nr - c * 32);
+        for (uint32_t i = 0; i < cnt; i++) s += __shfl_sync(0xffffffffu, sq, i);
+    }
     const float len = sqrtf(s);
     float p = 0;
-    if (len != 0) for (uint32_t r = 0; r < t.nr; r++) p += d[r] * (col[r].x / len);
-    proj[t.outOff + j] = p;
+    if (len != 0) {
+        for (uint32_t c = 0; c < nch; c++) {
+            float xv, dd;
+            if (inReg) {
+                xv = 0; dd = 0;
+#pragma unroll
+                for (uint32_t k = 0; k < CL_PROJ_MAXCH; k++) if (k == c) { xv = x[k]; dd = dv[k]; }
+            } else { const uint32_t r = c * 32 + lane; xv = r < t.nr ? col[r].x : 0.0f; dd = r < t.nr ? d[r] : 0.0f; }
+            const float term = dd * (xv / len);
+            const uint32_t cnt = min(32u, t.nr - c * 32);
+            for (uint32_t i = 0; i < cnt; i++) p += __shfl_sync(0xffffffffu, term, i);
+        }
+    }
+    if (lane == 0) {
+        if (proj) proj[t.outOff + j] = p;
+        if (keys) {
+            const float q = p + 0.0f;                                   /* -0.0 and +0.0 compare equal in the pair order */
+            uint32_t b = __float_as_uint(q);
+            b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+            keys[t.outOff + j] = ((uint64_t) b << 32) | vid;
+        }
+    }
 }
 
 __global__ void k_scatter_lists(const ClTask *__restrict__ tasks, const uint32_t *__restrict__ staged, uint32_t *__restrict__ lists) {
@@ -213,7 +264,7 @@ __global__ void __launch_bounds__(CL_THREADS) k_seg_sums(const float2 *__restric
     if (blockIdx.y >= t.rowBlocks || t.nseg <= 1) return;
     const uint32_t lr = blockIdx.y * CL_THREADS + threadIdx.x;
     const uint32_t row = t.r0 + (lr < t.nr ? lr : 0);
-    const uint32_t n = t.end - t.begin, k0 = sd.seg * CL_SEG, k1 = min(n, k0 + CL_SEG);
+    const uint32_t n = t.end - t.begin, k0 = sd.seg * t.segLen, k1 = min(n, k0 + t.segLen);
     const uint32_t *list = lists + t.listOff;
     double s = 0;
     for (uint32_t k = k0; k < k1; k++) {
@@ -250,7 +301,7 @@ __global__ void __launch_bounds__(CL_THREADS) k_seg_main(const float2 *__restric
     const uint32_t lr = blockIdx.y * CL_THREADS + tid;
     const bool active = lr < t.nr;
     const uint32_t row = t.r0 + (active ? lr : 0);
-    const uint32_t n = t.end - t.begin, kBeg = sd.seg * CL_SEG, kEnd = min(n, kBeg + CL_SEG);
+    const uint32_t n = t.end - t.begin, kBeg = sd.seg * t.segLen, kEnd = min(n, kBeg + t.segLen);
     const uint32_t *list = lists + t.listOff;
     const double *w = wArr + t.stepOff, *W = WArr + t.stepOff;
     double S = (t.nseg > 1) ? carry[t.carryOff + (uint64_t) sd.seg * (t.rowBlocks * CL_THREADS) + lr] : 0.0;
@@ -318,6 +369,132 @@ __global__ void __launch_bounds__(CL_THREADS) k_final(const ClTask *__restrict__
     }
 }
 
+/* ---- device rounds (counter stream): centre picking, sort and argmin without a host round trip ----------------- */
+struct RoundResult {            /* what the host needs back from one split */
+    uint32_t bestIndex, vrl1, vrl2, flags;      /* flags: 1 = degenerate centres (host path), 2 = non-positive weight sum */
+    float2 head, tail;                          /* variance pairs of the two halves */
+    float best, second;
+    uint32_t firstVrl, lastVrl;                 /* VRL ids at the ends of the sorted range (singleton halves) */
+};
+
+/*
+ * One block per split: weightedSample x 2 (Preprocessor.cpp:597-602,1534-1580) -- sequential fp32 sums in list order by
+ * one thread over shared-memory chunks that the block stages (the second draw sees the first centre's weight as 0) --
+ * followed by the split direction (604-623): three threads accumulate |col1|, |col2|, |col2 - col1| in row order.
+ */
+#define CL_PICK_CHUNK 2048
+__global__ void __launch_bounds__(128) k_pick_direction(const float2 *__restrict__ R, uint32_t ldR, const ClTask *__restrict__ tasks,
+                                                        const uint32_t *__restrict__ lists, const float *__restrict__ cw,
+                                                        RoundResult *__restrict__ res, float *__restrict__ dir) {
+    __shared__ float sw[CL_PICK_CHUNK];
+    __shared__ float sAcc; __shared__ uint32_t sIdx, sFound;
+    __shared__ float sNorm[3];
+    const ClTask t = tasks[blockIdx.x];
+    const uint32_t n = t.end - t.begin;
+    const uint32_t *list = lists + t.listOff + t.begin;
+    const float *w = cw + t.cwOff;
+    uint32_t idx1 = 0xffffffffu, picks[2] = {0, 0}, flags = 0;
+    for (int draw = 0; draw < 2; draw++) {
+        if (threadIdx.x == 0) sAcc = 0.0f;
+        for (uint32_t c0 = 0; c0 < n; c0 += CL_PICK_CHUNK) {
+            const uint32_t cnt = min((uint32_t) CL_PICK_CHUNK, n - c0);
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) sw[i] = (c0 + i == idx1) ? 0.0f : w[list[c0 + i]];
+            __syncthreads();
+            if (threadIdx.x == 0) { float a = sAcc; for (uint32_t i = 0; i < cnt; i++) a += sw[i]; sAcc = a; }
+        }
+        __syncthreads();
+        const float weightSum = sAcc;
+        if (!(weightSum > 0)) flags |= 2u;
+        const float alpha = (draw == 0 ? t.u1 : t.u2) * weightSum;
+        __syncthreads();
+        if (threadIdx.x == 0) { sAcc = 0.0f; sIdx = 0; sFound = 0; }
+        for (uint32_t c0 = 0; c0 < n; c0 += CL_PICK_CHUNK) {
+            const uint32_t cnt = min((uint32_t) CL_PICK_CHUNK, n - c0);
+            __syncthreads();
+            if (sFound) break;
+            for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) sw[i] = (c0 + i == idx1) ? 0.0f : w[list[c0 + i]];
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                float a = sAcc;
+                for (uint32_t i = 0; i < cnt; i++) { a += sw[i]; if (a >= alpha) { sIdx = c0 + i; sFound = 1; break; } }
+                sAcc = a;
+            }
+        }
+        __syncthreads();
+        picks[draw] = sIdx;
+        if (draw == 0) idx1 = sIdx;
+        __syncthreads();
+    }
+    const uint32_t vrl1 = list[picks[0]], vrl2 = list[picks[1]];
+    /* direction: norms in row order, one accumulator per thread (three independent sequential chains) */
+    const float2 *c1 = R + (size_t) vrl1 * ldR + t.r0, *c2 = R + (size_t) vrl2 * ldR + t.r0;
+    float *cA = sw, *cB = sw + CL_PICK_CHUNK / 2;
+    float acc = 0;
+    for (uint32_t r0 = 0; r0 < t.nr; r0 += CL_PICK_CHUNK / 2) {
+        const uint32_t cnt = min((uint32_t) CL_PICK_CHUNK / 2, t.nr - r0);
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) { cA[i] = c1[r0 + i].x; cB[i] = c2[r0 + i].x; }
+        __syncthreads();
+        if (threadIdx.x == 0) for (uint32_t i = 0; i < cnt; i++) acc += fabsf(cA[i]) * fabsf(cA[i]);
+        else if (threadIdx.x == 32) for (uint32_t i = 0; i < cnt; i++) acc += fabsf(cB[i]) * fabsf(cB[i]);
+        else if (threadIdx.x == 64) for (uint32_t i = 0; i < cnt; i++) { const float d = cB[i] - cA[i]; acc += fabsf(d) * fabsf(d); }
+    }
+    if (threadIdx.x == 0) sNorm[0] = sqrtf(acc);
+    if (threadIdx.x == 32) sNorm[1] = sqrtf(acc);
+    if (threadIdx.x == 64) sNorm[2] = sqrtf(acc);
+    __syncthreads();
+    const bool degenerate = !(sNorm[0] != 0 && sNorm[1] != 0 && sNorm[2] != 0);
+    if (degenerate) flags |= 1u;
+    const float diffLen = sNorm[2];
+    for (uint32_t r = threadIdx.x; r < t.nr; r += blockDim.x) dir[t.dirOff + r] = degenerate ? 0.0f : (c2[r].x - c1[r].x) / diffLen;
+    if (threadIdx.x == 0) {
+        RoundResult r;
+        r.bestIndex = 0xffffffffu; r.flags = flags; r.vrl1 = vrl1; r.vrl2 = vrl2;
+        r.head = make_float2(0, 0); r.tail = make_float2(0, 0); r.best = 0; r.second = 0; r.firstVrl = 0; r.lastVrl = 0;
+        res[blockIdx.x] = r;
+    }
+}
+
+__global__ void k_scatter_sorted(const ClTask *__restrict__ tasks, const uint64_t *__restrict__ keys, uint32_t *__restrict__ lists) {
+    const ClTask t = tasks[blockIdx.y];
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < t.end - t.begin) lists[t.listOff + t.begin + j] = (uint32_t) (keys[t.outOff + j] & 0xffffffffull);
+}
+
+/* first minimum of head + tail variance over the split index (664-675), plus the runner-up for the near-tie flag */
+__global__ void __launch_bounds__(CL_THREADS) k_argmin(const ClTask *__restrict__ vt, const float2 *__restrict__ pairs, const uint32_t *__restrict__ lists,
+                                                       RoundResult *__restrict__ res) {
+    __shared__ float sb[CL_THREADS], ss[CL_THREADS]; __shared__ uint32_t si[CL_THREADS];
+    const ClTask f = vt[2 * blockIdx.x], r = vt[2 * blockIdx.x + 1];
+    const uint32_t n = f.end - f.begin;
+    const float2 *fromStart = pairs + f.outOff, *fromEnd = pairs + r.outOff;
+    float best = INFINITY, second = INFINITY; uint32_t bi = 0xffffffffu;
+    for (uint32_t k = 1 + threadIdx.x; k < n; k += CL_THREADS) {
+        const float2 h = fromStart[k - 1], tl = fromEnd[n - 1 - k];
+        const float v = h.x + h.y + tl.x + tl.y;
+        if (v < best) { second = best; best = v; bi = k; }
+        else if (v < second) second = v;
+    }
+    sb[threadIdx.x] = best; ss[threadIdx.x] = second; si[threadIdx.x] = bi;
+    __syncthreads();
+    for (int o = CL_THREADS / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            const float b1 = sb[threadIdx.x], b2 = sb[threadIdx.x + o], s1 = ss[threadIdx.x], s2 = ss[threadIdx.x + o];
+            const uint32_t i1 = si[threadIdx.x], i2 = si[threadIdx.x + o];
+            if (b2 < b1 || (b2 == b1 && i2 < i1)) { sb[threadIdx.x] = b2; si[threadIdx.x] = i2; ss[threadIdx.x] = fminf(s2, b1); }
+            else ss[threadIdx.x] = fminf(s1, b2);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        RoundResult &o = res[blockIdx.x];
+        o.bestIndex = si[0]; o.best = sb[0]; o.second = ss[0];
+        if (si[0] != 0xffffffffu) { o.head = fromStart[si[0] - 1]; o.tail = fromEnd[n - 1 - si[0]]; }
+        o.firstVrl = lists[f.listOff + f.begin]; o.lastVrl = lists[f.listOff + f.end - 1];
+    }
+}
+
 /* ---- host side ------------------------------------------------------------------------------------ */
 namespace {
 
@@ -326,7 +503,9 @@ struct Prof {
     double t[8] = {0, 0, 0, 0, 0, 0, 0, 0}; uint64_t rounds = 0, tasks = 0, steps = 0;
     bool on = getenv("ALVRL_PROFILE") != nullptr;
     static double now() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+    double *evMs = nullptr;
     ~Prof() {
+        if (on && rounds && evMs) fprintf(stderr, "[alvrl clustering] device ms: pick+dir %.1f project %.1f sort %.1f scatter %.1f variance(incl. uploads) %.1f argmin %.1f\n", evMs[0], evMs[1], evMs[2], evMs[3], evMs[4], evMs[5]);
         if (on && rounds) fprintf(stderr, "[alvrl clustering] rounds %llu tasks %llu steps %llu | ms: sample+tasks %.1f dir+proj %.1f d2h-proj %.1f sort %.1f "
                                   "h2d+variance %.1f d2h-pairs %.1f argmin %.1f\n", (unsigned long long) rounds, (unsigned long long) tasks,
                                   (unsigned long long) steps, t[0], t[1], t[2], t[3], t[4], t[5], t[6]);
@@ -374,6 +553,7 @@ struct Inst {                                                                  /
     uint32_t targetClusters = 0; float bestConstant = 0;
     ClusterNode cur{0, 0, 0, 0}; uint32_t vrl1 = 0, vrl2 = 0;
     uint32_t nearTies = 0;
+    bool listsStale = false;      /* the device holds a newer permutation than `vrls` */
 
     uint32_t numMulti() const { return (uint32_t) pq.size(); }
     uint32_t numClusters() const { return (uint32_t) (pq.size() + singletons.size()); }
@@ -437,9 +617,11 @@ struct Workspace {
 
     template <typename T> static void ensure(DevBuf<T> &b, size_t n) { if (b.n < n) b.alloc(n + n / 4 + 16); }
     uint32_t launchCount = 0; bool serialSort = false;
+    bool deviceRounds = false;        /* counter stream: centres / sort / argmin on the device (no host round trip per phase) */
     void launches(uint32_t k) { launchCount += k; }
 
     void allocInstances() {
+        prof.evMs = evMs;
         ensure(dLists, insts.size() * (size_t) N); ensure(dCw, insts.size() * (size_t) N);
         for (size_t i = 0; i < insts.size(); i++) { insts[i]->listOff = i * (uint64_t) N; insts[i]->cwOff = i * (uint64_t) N; }
     }
@@ -478,36 +660,47 @@ struct Workspace {
         ALVRL_CUDA(cudaStreamSynchronize(st));
     }
     /* calculateClusterVariance for a batch of ranges; results in dPairs at task.outOff (n pairs, or 1 when finalOnly).
-     * Returns the number of result slots. */
-    uint64_t runVariance(std::vector<ClTask> &tasks, DevBuf<ClTask> &dT) {
-        uint64_t out = 0, steps = 0, carry = 0, part = 0; uint32_t segTotal = 0, maxRb = 1;
+     * prepareVariance assigns offsets and uploads the task / segment tables (host-known: can run before the kernels that
+     * produce the sorted lists are even launched); launchVariance enqueues the pipeline. */
+    struct VarPlan { uint64_t out = 0, carry = 0; uint32_t segTotal = 0, maxRb = 1, T = 0; };
+    VarPlan prepareVariance(std::vector<ClTask> &tasks, DevBuf<ClTask> &dT) {
+        VarPlan pl;
+        uint64_t steps = 0, part = 0;
         std::vector<SegDesc> segs;
         for (size_t i = 0; i < tasks.size(); i++) {
             ClTask &t = tasks[i];
             const uint32_t n = t.end - t.begin;
-            t.outOff = out; t.stepOff = steps; t.carryOff = carry; t.partOff = part;
+            t.outOff = pl.out; t.stepOff = steps; t.carryOff = pl.carry; t.partOff = part;
             part += (uint64_t) n * t.rowBlocks;
-            t.nseg = (n + CL_SEG - 1) / CL_SEG; t.segOff = segTotal;
-            out += t.finalOnly ? 1 : n; steps += n;
-            if (t.nseg > 1) carry += (uint64_t) t.nseg * t.rowBlocks * CL_THREADS;
+            t.segLen = n <= 8192 ? 32 : CL_SEG;
+            t.nseg = (n + t.segLen - 1) / t.segLen; t.segOff = pl.segTotal;
+            pl.out += t.finalOnly ? 1 : n; steps += n;
+            if (t.nseg > 1) pl.carry += (uint64_t) t.nseg * t.rowBlocks * CL_THREADS;
             for (uint32_t sgi = 0; sgi < t.nseg; sgi++) segs.push_back(SegDesc{(uint32_t) i, sgi});
-            segTotal += t.nseg; maxRb = std::max(maxRb, t.rowBlocks);
+            pl.segTotal += t.nseg; pl.maxRb = std::max(pl.maxRb, t.rowBlocks);
         }
-        ensure(dW1, steps); ensure(dW2, steps); ensure(dCarry, std::max<uint64_t>(carry, 1)); ensure(dPartial, part); ensure(dPairs, out);
+        pl.T = (uint32_t) tasks.size();
+        ensure(dW1, steps); ensure(dW2, steps); ensure(dCarry, std::max<uint64_t>(pl.carry, 1)); ensure(dPartial, part); ensure(dPairs, pl.out);
         dT.upload(tasks, st);
         dSegs.upload(segs, st);
-        const uint32_t T = (uint32_t) tasks.size();
-        k_weights<<<T, CL_THREADS, 0, st>>>(dT.p, dLists.p, dCw.p, dW1.p, dW2.p);
-        if (carry) {
-            k_seg_sums<<<dim3(segTotal, maxRb), CL_THREADS, 0, st>>>(R, ldR, dT.p, dSegs.p, dLists.p, dCarry.p);
-            k_carry<<<dim3(T, maxRb), CL_THREADS, 0, st>>>(dT.p, dCarry.p);
+        return pl;
+    }
+    void launchVariance(const VarPlan &pl, DevBuf<ClTask> &dT) {
+        k_weights<<<pl.T, CL_THREADS, 0, st>>>(dT.p, dLists.p, dCw.p, dW1.p, dW2.p);
+        if (pl.carry) {
+            k_seg_sums<<<dim3(pl.segTotal, pl.maxRb), CL_THREADS, 0, st>>>(R, ldR, dT.p, dSegs.p, dLists.p, dCarry.p);
+            k_carry<<<dim3(pl.T, pl.maxRb), CL_THREADS, 0, st>>>(dT.p, dCarry.p);
             launches(2);
         }
-        k_seg_main<<<dim3(segTotal, maxRb), CL_THREADS, 0, st>>>(R, ldR, dT.p, dSegs.p, dLists.p, dW1.p, dW2.p, dCarry.p, dPartial.p);
-        k_final<<<T, CL_THREADS, 0, st>>>(dT.p, dW1.p, dW2.p, dPartial.p, dPairs.p);
+        k_seg_main<<<dim3(pl.segTotal, pl.maxRb), CL_THREADS, 0, st>>>(R, ldR, dT.p, dSegs.p, dLists.p, dW1.p, dW2.p, dCarry.p, dPartial.p);
+        k_final<<<pl.T, CL_THREADS, 0, st>>>(dT.p, dW1.p, dW2.p, dPartial.p, dPairs.p);
         launches(3);
         ALVRL_CUDA(cudaGetLastError());
-        return out;
+    }
+    uint64_t runVariance(std::vector<ClTask> &tasks, DevBuf<ClTask> &dT) {
+        const VarPlan pl = prepareVariance(tasks, dT);
+        launchVariance(pl, dT);
+        return pl.out;
     }
     /* variance of whole ranges (addCluster(begin, end), 576-579): one (uvar, ivar) pair per task */
     std::vector<float2> rangeVariances(std::vector<ClTask> &tasks) {
@@ -589,7 +782,7 @@ struct Workspace {
                 round.push_back(in);
             }
             if (round.empty()) break;
-            splitRound(round);
+            if (deviceRounds) splitRoundDevice(round); else splitRound(round);
             for (Inst *in : round) {
                 if (in->adaptive) {
                     const float curr = in->convergenceConstant();               /* 436-452 */
@@ -598,10 +791,11 @@ struct Workspace {
                 } else if (!(in->numClusters() < in->targetClusters && in->numMulti() > 0)) in->done = true;
             }
         }
+        syncLists(which);
         for (Inst *in : which) in->refining = false;
     }
     /* Clustering::split (590-684) for one cluster of every instance in `round` */
-    void splitRound(const std::vector<Inst *> &round) {
+    void splitRound(const std::vector<Inst *> &round, const std::vector<std::pair<uint32_t, uint32_t>> *centres = nullptr) {
         const size_t T = round.size();
         std::vector<ClTask> tasks(T);
         uint64_t out = 0, dirOff = 0;
@@ -609,14 +803,17 @@ struct Workspace {
         prof.rounds++; prof.tasks += T;
         for (size_t i = 0; i < T; i++) {
             Inst &in = *round[i];
-            in.cur = in.popMulti();
+            if (!centres) in.cur = in.popMulti();
             const uint32_t begin = in.cur.begin, end = in.cur.end;
             if (end - begin < 2) throw Error(ALVRL_ERR_ARG, "couldn't split cluster!");
-            in.vrl1 = in.vrls[weighted_sample(in.cw, in.smp, nullptr, begin, end, in.vrls)];   /* 597-602 */
-            const float weight1 = in.cw[in.vrl1];
-            in.cw[in.vrl1] = 0.0f;
-            in.vrl2 = in.vrls[weighted_sample(in.cw, in.smp, nullptr, begin, end, in.vrls)];
-            in.cw[in.vrl1] = weight1;
+            if (centres) { in.vrl1 = (*centres)[i].first; in.vrl2 = (*centres)[i].second; }
+            else {
+                in.vrl1 = in.vrls[weighted_sample(in.cw, in.smp, nullptr, begin, end, in.vrls)];   /* 597-602 */
+                const float weight1 = in.cw[in.vrl1];
+                in.cw[in.vrl1] = 0.0f;
+                in.vrl2 = in.vrls[weighted_sample(in.cw, in.smp, nullptr, begin, end, in.vrls)];
+                in.cw[in.vrl1] = weight1;
+            }
             ClTask t = baseTask(in);
             t.begin = begin; t.end = end; t.vrl1 = in.vrl1; t.vrl2 = in.vrl2; t.outOff = out; t.dirOff = dirOff;
             out += end - begin; dirOff += in.nr;
@@ -628,7 +825,7 @@ struct Workspace {
         p1 = Prof::now(); prof.t[0] += p1 - p0; p0 = p1;
         uint32_t maxN = 0; for (const ClTask &t : tasks) maxN = std::max(maxN, t.end - t.begin);
         k_direction<<<(uint32_t) T, 128, 0, st>>>(R, ldR, dTasks.p, dDir.p, dFlags.p);
-        k_project<<<dim3((maxN + 127) / 128, (uint32_t) T), 128, 0, st>>>(R, ldR, dTasks.p, dLists.p, dDir.p, dProj.p);
+        k_project<<<dim3((maxN + CL_PROJ_WARPS - 1) / CL_PROJ_WARPS, (uint32_t) T), CL_PROJ_WARPS * 32, 0, st>>>(R, ldR, dTasks.p, dLists.p, dDir.p, dProj.p, nullptr);
         launches(2);
         ALVRL_CUDA(cudaGetLastError());
         std::vector<uint32_t> flags(T);
@@ -655,7 +852,7 @@ struct Workspace {
             redo = true;
         }
         if (redo) {
-            k_project<<<dim3((maxN + 127) / 128, (uint32_t) T), 128, 0, st>>>(R, ldR, dTasks.p, dLists.p, dDir.p, dProj.p);
+            k_project<<<dim3((maxN + CL_PROJ_WARPS - 1) / CL_PROJ_WARPS, (uint32_t) T), CL_PROJ_WARPS * 32, 0, st>>>(R, ldR, dTasks.p, dLists.p, dDir.p, dProj.p, nullptr);
             launches(1);
             ALVRL_CUDA(cudaGetLastError());
         }
@@ -715,6 +912,100 @@ struct Workspace {
         p1 = Prof::now(); prof.t[6] += p1 - p0;
     }
     DevBuf<ClTask> dTasks2;
+    cudaEvent_t ev[8] = {nullptr}; double evMs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    void evRec(int i) { if (prof.on) { if (!ev[i]) cudaEventCreate(&ev[i]); cudaEventRecord(ev[i], st); } }
+    DevBuf<float> dWtmp; DevBuf<uint64_t> dKeys, dKeysOut; DevBuf<RoundResult> dRes; DevBuf<int> dSegOff; DevBuf<unsigned char> dSortTemp;
+
+    /* Clustering::split for one cluster of every instance in `round`, device rounds: the host only pops the heap nodes, draws
+     * the two uniforms per split and pushes the two halves; centres, sort and argmin never leave the device. */
+    void splitRoundDevice(const std::vector<Inst *> &round) {
+        const size_t T = round.size();
+        std::vector<ClTask> tasks(T);
+        std::vector<int> segOff(2 * T);
+        uint64_t out = 0, dirOff = 0;
+        double p0 = Prof::now(), p1;
+        prof.rounds++; prof.tasks += T;
+        uint32_t maxN = 0;
+        for (size_t i = 0; i < T; i++) {
+            Inst &in = *round[i];
+            in.cur = in.popMulti();
+            const uint32_t begin = in.cur.begin, end = in.cur.end;
+            if (end - begin < 2) throw Error(ALVRL_ERR_ARG, "couldn't split cluster!");
+            ClTask t = baseTask(in);
+            t.begin = begin; t.end = end; t.outOff = out; t.dirOff = dirOff;
+            t.u1 = in.smp->next1D(); t.u2 = in.smp->next1D();                   /* the two weightedSample draws, 597-602 */
+            segOff[i] = (int) out; segOff[T + i] = (int) (out + (end - begin));
+            out += end - begin; dirOff += in.nr;
+            maxN = std::max(maxN, end - begin);
+            tasks[i] = t;
+        }
+        if (out > 0x7fffffffull) throw Error(ALVRL_ERR_UNSUPPORTED, "clustering round larger than 2^31 entries");
+        ensure(dDir, dirOff); ensure(dKeys, out); ensure(dKeysOut, out); ensure(dRes, T);
+        prof.steps += out;
+        dTasks.upload(tasks, st);
+        dSegOff.upload(segOff, st);
+        std::vector<ClTask> vt(2 * T);
+        for (size_t i = 0; i < T; i++)
+            for (int rev = 0; rev < 2; rev++) { ClTask t = tasks[i]; t.reverse = rev; t.finalOnly = 0; vt[2 * i + rev] = t; }
+        const VarPlan plan = prepareVariance(vt, dTasks2);                  /* everything the host knows goes up before the first launch */
+        size_t tempBytes = 0;
+        cub::DeviceSegmentedSort::SortKeys(nullptr, tempBytes, dKeys.p, dKeysOut.p, (int) out, (int) T, dSegOff.p, dSegOff.p + T, st);
+        ensure(dSortTemp, tempBytes + 16);
+        p1 = Prof::now(); prof.t[0] += p1 - p0; p0 = p1;
+        const dim3 gN((maxN + 127) / 128, (uint32_t) T);
+        evRec(0);
+        k_pick_direction<<<(uint32_t) T, 128, 0, st>>>(R, ldR, dTasks.p, dLists.p, dCw.p, dRes.p, dDir.p);
+        evRec(1);
+        k_project<<<dim3((maxN + CL_PROJ_WARPS - 1) / CL_PROJ_WARPS, (uint32_t) T), CL_PROJ_WARPS * 32, 0, st>>>(R, ldR, dTasks.p, dLists.p, dDir.p, nullptr, dKeys.p);
+        evRec(2);
+        cub::DeviceSegmentedSort::SortKeys(dSortTemp.p, tempBytes, dKeys.p, dKeysOut.p, (int) out, (int) T, dSegOff.p, dSegOff.p + T, st);
+        evRec(3);
+        k_scatter_sorted<<<gN, 128, 0, st>>>(dTasks.p, dKeysOut.p, dLists.p);
+        launches(6);
+        ALVRL_CUDA(cudaGetLastError());
+        p1 = Prof::now(); prof.t[1] += p1 - p0; p0 = p1;
+        evRec(4);
+        launchVariance(plan, dTasks2);
+        evRec(5);
+        k_argmin<<<(uint32_t) T, CL_THREADS, 0, st>>>(dTasks2.p, dPairs.p, dLists.p, dRes.p);
+        evRec(6);
+        launches(1);
+        ALVRL_CUDA(cudaGetLastError());
+        std::vector<RoundResult> res(T);
+        dRes.download(res.data(), T, st);
+        if (prof.on) for (int i = 0; i < 6; i++) { float ms = 0; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); evMs[i] += ms; }
+        p1 = Prof::now(); prof.t[4] += p1 - p0; p0 = p1;
+        std::vector<Inst *> hostRound; std::vector<std::pair<uint32_t, uint32_t>> hostCentres;
+        for (size_t i = 0; i < T; i++) {
+            Inst &in = *round[i];
+            const RoundResult &r = res[i];
+            const uint32_t begin = tasks[i].begin, end = tasks[i].end;
+            if (r.flags) {                                                      /* degenerate centres: random direction on the host (616-622) */
+                std::vector<uint32_t> seg(end - begin);
+                dLists.download(seg.data(), end - begin, st, in.listOff + begin);
+                std::copy(seg.begin(), seg.end(), in.vrls.begin() + begin);
+                hostRound.push_back(&in); hostCentres.push_back(std::make_pair(r.vrl1, r.vrl2));
+                continue;
+            }
+            if (r.bestIndex == 0xffffffffu) throw Error(ALVRL_ERR_ARG, "Couldn't find best splitting index!");
+            if (std::isfinite(r.second) && std::fabs(r.second - r.best) <= 1e-6f * std::fabs(r.best)) in.nearTies++;
+            const uint32_t splitIndex = begin + r.bestIndex;
+            in.listsStale = true;
+            in.vrls[begin] = r.firstVrl; in.vrls[end - 1] = r.lastVrl;          /* singleton halves record their VRL id (561) */
+            in.addCluster(begin, splitIndex, r.head.x, r.head.y);
+            in.addCluster(splitIndex, end, r.tail.x, r.tail.y);
+        }
+        p1 = Prof::now(); prof.t[6] += p1 - p0;
+        if (!hostRound.empty()) splitRound(hostRound, &hostCentres);
+    }
+    /* bring the host mirrors of the VRL permutations up to date (device rounds reorder them on the device only) */
+    void syncLists(const std::vector<Inst *> &which) {
+        for (Inst *in : which) {
+            if (!in->listsStale) continue;
+            dLists.download(in->vrls.data(), in->vrls.size(), st, in->listOff);
+            in->listsStale = false;
+        }
+    }
 };
 
 } // namespace
@@ -771,7 +1062,7 @@ void build_clusters_device(alvrl_ctx *c, bool needFallback) {
     const bool sfmt = c->P.rngMode == ALVRL_RNG_MODE_SFMT;
     const bool lazyFallbackCall = c->haveClusters && !c->haveFallback;       /* called again only for the global / fallback lists */
 
-    Workspace ws; ws.c = c; ws.st = st; ws.N = N; ws.ldR = c->ldR; ws.R = c->dR.p;
+    Workspace ws; ws.c = c; ws.st = st; ws.N = N; ws.ldR = c->ldR; ws.R = c->dR.p; ws.deviceRounds = !sfmt;
 
     /* the global stream: cluster() -> global representatives -> fallback refinement, in this order (159-179) */
     HostSampler *globalSmp = c->mainSampler.get();
@@ -810,7 +1101,7 @@ void build_clusters_device(alvrl_ctx *c, bool needFallback) {
 
     auto computeFallback = [&]() {
         Inst g; makeGlobalInst(g);
-        Workspace w2; w2.c = c; w2.st = st; w2.N = N; w2.ldR = c->ldR; w2.R = c->dR.p;
+        Workspace w2; w2.c = c; w2.st = st; w2.N = N; w2.ldR = c->ldR; w2.R = c->dR.p; w2.deviceRounds = !sfmt;
         w2.insts = {&g}; w2.allocInstances(); w2.columnWeights();
         w2.construct(c->globalVrlsPerCluster);
         g.sampleRepresentatives(c->gcVrls, c->gcWeight);                         /* 169 */
@@ -865,14 +1156,18 @@ void build_clusters_device(alvrl_ctx *c, bool needFallback) {
             /* independent per-slice streams: the Clustering objects are dealt to a few host threads, each driving its own CUDA
              * stream, so that one group's host work (sorting, heap updates) overlaps the other groups' kernels and copies */
             const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-            const size_t nGroups = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(8, hw / 2), ws.insts.size() / 4 + 1));
+            /* device rounds leave little host work per round, and every round costs ~20 launches whatever its size: few groups
+             * (more Clustering objects per launch) beat many */
+            size_t wantGroups = 3;
+            if (const char *e = getenv("ALVRL_CLUSTER_GROUPS")) wantGroups = (size_t) std::max(1, atoi(e));
+            const size_t nGroups = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(wantGroups, hw), ws.insts.size() / 4 + 1));
             std::vector<std::unique_ptr<Workspace>> groups(nGroups);
             std::vector<std::string> errors(nGroups);
             std::vector<std::thread> threads;
             for (size_t gI = 0; gI < nGroups; gI++) {
                 groups[gI].reset(new Workspace());
                 Workspace &w2 = *groups[gI];
-                w2.c = c; w2.N = N; w2.ldR = c->ldR; w2.R = c->dR.p; w2.serialSort = nGroups > 1;
+                w2.c = c; w2.N = N; w2.ldR = c->ldR; w2.R = c->dR.p; w2.serialSort = nGroups > 1; w2.deviceRounds = true;
                 for (size_t i = gI; i < ws.insts.size(); i += nGroups) w2.insts.push_back(ws.insts[i]);
             }
             for (size_t gI = 0; gI < nGroups; gI++) threads.emplace_back([&, gI]() {

@@ -1,0 +1,80 @@
+/*
+ * mts_mock.h -- the slice of Mitsuba 0.6's plugin interface that the `vrl` integrator touches, mocked so that the plugin
+ * shim (vrl_plugin.cpp) compiles and is testable in an image without Mitsuba (Boost, Xerces-C, OpenEXR and SCons are not
+ * installed here, so the real headers do not compile).  A maintainer building inside a Mitsuba tree defines
+ * ALVRL_WITH_MITSUBA and these declarations are replaced by <mitsuba/render/scene.h>.
+ *
+ * Mirrors: Properties (include/mitsuba/core/properties.h), the CreateInstance/GetDescription plugin ABI
+ * (include/mitsuba/core/cobject.h:99-107), Integrator::preprocess/render hooks (include/mitsuba/render/integrator.h:49-130,
+ * 483-511) and the few Scene/Sensor/Film/Medium/TriMesh accessors preprocess() marshals from.
+ */
+#pragma once
+#include <cstdint>
+#include <map>
+#include <set>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace mts {
+
+/* Log(EError, ...) throws std::runtime_error (src/libcore/logger.cpp:100,147) */
+[[noreturn]] inline void LogError(const std::string &msg) { throw std::runtime_error(msg); }
+
+class Properties {
+public:
+    void setBoolean(const std::string &k, bool v) { m_b[k] = v; }
+    void setInteger(const std::string &k, int v) { m_i[k] = v; }
+    void setFloat(const std::string &k, float v) { m_f[k] = v; }
+    void setString(const std::string &k, const std::string &v) { m_s[k] = v; }
+    bool hasProperty(const std::string &k) const { return m_b.count(k) || m_i.count(k) || m_f.count(k) || m_s.count(k); }
+    bool getBoolean(const std::string &k, bool d) const { m_q.insert(k); auto it = m_b.find(k); return it == m_b.end() ? d : it->second; }
+    int getInteger(const std::string &k, int d) const { m_q.insert(k); auto it = m_i.find(k); return it == m_i.end() ? d : it->second; }
+    float getFloat(const std::string &k, float d) const {
+        m_q.insert(k);
+        auto it = m_f.find(k); if (it != m_f.end()) return it->second;
+        auto ii = m_i.find(k); return ii == m_i.end() ? d : (float) ii->second;
+    }
+    std::string getString(const std::string &k, const std::string &d) const { m_q.insert(k); auto it = m_s.find(k); return it == m_s.end() ? d : it->second; }
+    /* the loader warns about attributes that were never queried (src/librender/scenehandler.cpp:792-795) */
+    std::vector<std::string> getUnqueried() const {
+        std::vector<std::string> out;
+        for (auto &kv : m_b) if (!m_q.count(kv.first)) out.push_back(kv.first);
+        for (auto &kv : m_i) if (!m_q.count(kv.first)) out.push_back(kv.first);
+        for (auto &kv : m_f) if (!m_q.count(kv.first)) out.push_back(kv.first);
+        for (auto &kv : m_s) if (!m_q.count(kv.first)) out.push_back(kv.first);
+        return out;
+    }
+private:
+    std::map<std::string, bool> m_b; std::map<std::string, int> m_i; std::map<std::string, float> m_f; std::map<std::string, std::string> m_s;
+    mutable std::set<std::string> m_q;
+};
+
+/* what preprocess() reads from `const Scene *` (triangle meshes with diffuse BSDFs, one medium, a perspective sensor) */
+struct TriMeshView { const float *positions; uint32_t vertexCount; const uint32_t *indices; uint32_t triangleCount; float reflectance[3]; bool smooth; };
+struct MediumView {
+    bool homogeneous; float sigmaA[3], sigmaS[3]; float mediumSamplingWeight; int phaseType; float g;
+    const float *grid; int res[3]; float bboxMin[3], bboxMax[3]; float scale; float albedo[3];
+};
+struct SensorView { float sampleToCamera[16], cameraToWorld[16]; uint32_t width, height; float nearClip, farClip; float position[3]; };
+class Film { public: virtual ~Film() {} virtual void setImage(const float *rgb, uint32_t width, uint32_t height) = 0; };
+class Scene {
+public:
+    std::vector<TriMeshView> meshes; std::vector<MediumView> media; SensorView sensor; Film *film = nullptr;
+};
+
+class Integrator {
+public:
+    virtual ~Integrator() {}
+    virtual bool preprocess(const Scene *scene) = 0;
+    virtual bool prepass(const Scene *scene) = 0;
+    virtual bool render(Scene *scene) = 0;
+    virtual void cancel() {}
+};
+
+} // namespace mts
+
+extern "C" {
+void *CreateInstance(const mts::Properties &props);     /* include/mitsuba/core/cobject.h:99-107 */
+const char *GetDescription();
+}

@@ -1,0 +1,140 @@
+/*
+ * vrl_plugin.cpp -- host side of the drop-in: `integrator type="vrl"` as a Mitsuba plugin whose hot path runs in
+ * libalvrl.so (include/alvrl.h) instead of the reference's CPU loops.
+ *
+ * Mirrors src/integrators/vrl/vrlIntegrator.cpp: same XML parameter names, defaults and constructor errors (128-208),
+ * `preprocess` loads the ASCII `vrlFile` and builds the slices (237-267), `prepass` runs sampleSliceMapping -> "Building
+ * R" -> buildClusters (270-356).  Where the reference answers Li() per camera sample on worker threads (386-393), a GPU
+ * replacement renders the whole frame at once: render() hands the framebuffer to the film ("Threading").
+ * Exported plugin ABI: CreateInstance / GetDescription (include/mitsuba/core/cobject.h:99-107, vrlIntegrator.cpp:1127).
+ */
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../../include/alvrl.h"
+#ifdef ALVRL_WITH_MITSUBA
+#error "inside a Mitsuba tree: replace mts_mock.h by the Mitsuba headers as described in INTEGRATION.md"
+#else
+#include "mts_mock.h"
+#endif
+
+namespace {
+
+class vrlIntegrator : public mts::Integrator {
+public:
+    explicit vrlIntegrator(const mts::Properties &props) {
+        if (props.hasProperty("nc"))
+            mts::LogError("Neighbourcount is now called 'neighbourCount' instead of 'nc'!");            /* 129-131 */
+        alvrl_params_default(&m_p);
+        m_p.shortVrls = props.getBoolean("shortVrls", true);
+        m_p.vrlTargetNum = props.getInteger("vrlTargetNum", 500);
+        m_p.maxParticleDepth = props.getInteger("maxParticleDepth", -1);
+        m_p.specularForcedRRdepth = props.getInteger("specularForcedRRdepth", 100);
+        m_p.initialSpecularThroughput = props.getFloat("initialSpecularThroughput", 20);
+        m_p.volVolSamples = props.getInteger("volVolSamples", 2);
+        if (m_p.volVolSamples != 0 && m_p.volVolSamples < 2)
+            mts::LogError("Need at least 2 volVolSamples for variance estimate, but received: " + std::to_string(m_p.volVolSamples));
+        m_p.volSurfSamples = props.getInteger("volSurfSamples", 2);
+        if (m_p.volSurfSamples != 0 && m_p.volSurfSamples < 2)
+            mts::LogError("Need at least 2 volSurfSamples for variance estimate, but received: " + std::to_string(m_p.volSurfSamples));
+        m_p.globalCluster = props.getBoolean("globalCluster", false);
+        m_p.globalUndersampling = props.getFloat("globalUndersampling", -1);
+        m_p.localRefinement = props.getBoolean("localRefinement", true);
+        m_p.localUndersampling = props.getFloat("localUndersampling", -1);
+        m_p.fallBackUndersampling = props.getFloat("fallBackUndersampling", 5);
+        m_p.targetNumSlices = props.getInteger("targetNumSlices", 100);
+        m_p.targetPixelUndersampling = props.getFloat("targetPixelUndersampling", 64);
+        m_p.sliceCurvatureFactor = props.getFloat("sliceCurvatureFactor", 0.5f);
+        m_p.neighbourCount = props.getInteger("neighbourCount", 0);
+        m_p.neighbourWeight = props.getFloat("neighbourWeight", 0.0f);
+        m_p.Rsamples = props.getInteger("Rsamples", 1);
+        m_p.depthCorrection = props.getFloat("depthCorrection", 1);
+        m_p.numVrlFalseColor = props.getBoolean("numVrlFalseColor", false);
+        m_p.slicesFalseColor = props.getBoolean("slicesFalseColor", false);
+        m_p.convergenceFalseColor = props.getBoolean("convergenceFalseColor", false);
+        m_vrlFile = props.getString("vrlFile", "");
+        /* inherited (src/librender/integrator.cpp:53,272-298,348-349): queried so that the loader does not warn */
+        m_p.maxPasses = props.getInteger("maxPasses", 1);
+        props.getBoolean("dumpPasses", false); props.getInteger("rrDepth", 5); props.getInteger("maxDepth", -1);
+        props.getBoolean("strictNormals", false); props.getBoolean("hideEmitters", false); props.getInteger("numPasses", 1);
+        /* device selection has no XML equivalent in the reference */
+        m_device = props.getInteger("cudaDevice", 0);
+        m_p.seed = (uint64_t) props.getInteger("seed", 0);
+    }
+    ~vrlIntegrator() override { if (m_h) alvrl_destroy(m_h); }
+
+    const alvrl_params &params() const { return m_p; }
+
+    /* vrlIntegrator::preprocess, 237-267 */
+    bool preprocess(const mts::Scene *scene) override {
+        if (m_vrlFile.empty())
+            mts::LogError("the B200 path integrates preloaded VRLs: set 'vrlFile' (the VRL tracer, vrlTracer.h, is upstream of it)");
+        if (scene->media.size() != 1)                                                                    /* 244-248 */
+            mts::LogError("When loading VRLs from a file, the scene should (currently) contain exactly one medium, which will be the "
+                          "medium where all VRLs will 'live'");
+        chk(alvrl_create(m_device, &m_p, &m_h));
+        /* triangle soup + one diffuse material per mesh */
+        std::vector<float> verts, albedo; std::vector<uint32_t> tris, mat, bits;
+        for (size_t m = 0; m < scene->meshes.size(); m++) {
+            const mts::TriMeshView &tm = scene->meshes[m];
+            const uint32_t base = (uint32_t) (verts.size() / 3);
+            verts.insert(verts.end(), tm.positions, tm.positions + 3 * (size_t) tm.vertexCount);
+            for (uint32_t i = 0; i < 3 * tm.triangleCount; i++) tris.push_back(base + tm.indices[i]);
+            mat.insert(mat.end(), tm.triangleCount, (uint32_t) m);
+            albedo.insert(albedo.end(), tm.reflectance, tm.reflectance + 3);
+            bits.push_back(tm.smooth ? ALVRL_BSDF_SMOOTH : 0u);
+        }
+        chk(alvrl_set_mesh(m_h, verts.data(), (uint32_t) (verts.size() / 3), tris.data(), (uint32_t) (tris.size() / 3), mat.data()));
+        chk(alvrl_set_materials(m_h, albedo.data(), bits.data(), (uint32_t) bits.size()));
+        chk(alvrl_set_extra_bounds(m_h, scene->sensor.position, 1));                                    /* scene.cpp:387-413 */
+        const mts::MediumView &md = scene->media[0];
+        if (md.homogeneous) chk(alvrl_set_medium_homogeneous(m_h, md.sigmaA, md.sigmaS, md.mediumSamplingWeight, md.phaseType, md.g));
+        else chk(alvrl_set_medium_grid(m_h, md.grid, md.res, md.bboxMin, md.bboxMax, md.scale, md.albedo, md.sigmaS, md.phaseType, md.g));
+        const mts::SensorView &s = scene->sensor;
+        chk(alvrl_set_camera(m_h, s.sampleToCamera, s.cameraToWorld, s.width, s.height, s.nearClip, s.farClip));
+        chk(alvrl_load_vrl_file(m_h, m_vrlFile.c_str()));                                               /* 249-251 */
+        if (m_p.globalCluster || m_p.localRefinement) chk(alvrl_build_slices(m_h));                     /* 254-265 */
+        return true;
+    }
+    /* vrlIntegrator::prepass, 270-356 */
+    bool prepass(const mts::Scene *) override {
+        if (!m_h) mts::LogError("VRL filename given, but vrls were not loaded!");                       /* 285-286 */
+        if (m_p.globalCluster || m_p.localRefinement) chk(alvrl_prepass(m_h));
+        return true;
+    }
+    /* the render pass: every pixel centre through Li (386-393) */
+    bool render(mts::Scene *scene) override {
+        std::vector<float> rgb((size_t) scene->sensor.width * scene->sensor.height * 3);
+        if (m_p.globalCluster || m_p.localRefinement) chk(alvrl_render(m_h, rgb.data()));
+        else chk(alvrl_render_unclustered(m_h, rgb.data()));
+        if (scene->film) scene->film->setImage(rgb.data(), scene->sensor.width, scene->sensor.height);
+        return true;
+    }
+    alvrl_handle handle() const { return m_h; }
+private:
+    static void chk(int rc) { if (rc != ALVRL_OK) mts::LogError(alvrl_last_error()); }
+    alvrl_params m_p; std::string m_vrlFile; int m_device = 0; alvrl_handle m_h = nullptr;
+};
+
+} // namespace
+
+extern "C" {
+void *CreateInstance(const mts::Properties &props) { return new vrlIntegrator(props); }
+const char *GetDescription() { return "An implementation of Adaptive Lightslice for Virtual Ray Lights (B200 device path)"; }
+/* test hook: the parsed parameter block of an instance */
+void alvrl_plugin_get_params(void *inst, alvrl_params *out) { *out = static_cast<vrlIntegrator *>(inst)->params(); }
+void alvrl_plugin_destroy(void *inst) { delete static_cast<vrlIntegrator *>(inst); }
+/* test hooks for building a Properties object from C */
+void *alvrl_plugin_props_new() { return new mts::Properties(); }
+void alvrl_plugin_props_free(void *p) { delete static_cast<mts::Properties *>(p); }
+void alvrl_plugin_props_set_int(void *p, const char *k, int v) { static_cast<mts::Properties *>(p)->setInteger(k, v); }
+void alvrl_plugin_props_set_float(void *p, const char *k, float v) { static_cast<mts::Properties *>(p)->setFloat(k, v); }
+void alvrl_plugin_props_set_bool(void *p, const char *k, int v) { static_cast<mts::Properties *>(p)->setBoolean(k, v != 0); }
+void alvrl_plugin_props_set_string(void *p, const char *k, const char *v) { static_cast<mts::Properties *>(p)->setString(k, v); }
+/* CreateInstance with the reference's error behaviour (Log(EError) throws) turned into a status + message */
+int alvrl_plugin_create(void *props, void **inst, char *err, int errLen) {
+    try { *inst = CreateInstance(*static_cast<mts::Properties *>(props)); return 0; }
+    catch (const std::exception &e) { strncpy(err, e.what(), errLen - 1); err[errLen - 1] = 0; return -1; }
+}
+int alvrl_plugin_unqueried(void *props) { return (int) static_cast<mts::Properties *>(props)->getUnqueried().size(); }
+}

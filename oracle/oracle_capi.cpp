@@ -38,6 +38,7 @@ struct Ctx {
     bool noVisibility = false;
     uint32_t sliceBegin = 0, sliceEnd = 0xffffffffu;
     alvrl_stats stats;
+    std::vector<uint8_t> columnFlagsOverride;      // all-reduced zero / non-zero column flags (multi-rank runs)
     uint32_t nearTieSplits = 0;
     uint64_t clusterVarianceSteps = 0, clusterSplits = 0;
 
@@ -366,7 +367,9 @@ int orc_build_clusters(void *h) {
     for (uint32_t i = 0; i < N; i++) {
         Float sum = 0;                                                       // totalVrlContribution, 936-945
         for (uint32_t r = 0; r < G; r++) sum += flat.rows[r][i].mean;
-        if (sum != 0) nonZero.push_back(i); else zero.push_back(i);
+        bool nz = sum != 0;
+        if (c->columnFlagsOverride.size() == N) nz = c->columnFlagsOverride[i] != 0;
+        if (nz) nonZero.push_back(i); else zero.push_back(i);
     }
     if (!nonZero.empty()) {
         if (c->P.globalCluster) {                                           // clusterRefinement, 899-912
@@ -424,6 +427,18 @@ int orc_build_clusters(void *h) {
     c->haveClusters = true;
     c->stats.msClusters = (float) (now_ms() - t0);
     ORC_CATCH
+}
+int orc_get_column_nonzero(void *h, uint8_t *flags) {
+    Ctx *c = (Ctx *) h;
+    if (!c->haveR) return seterr(ALVRL_ERR_STATE, "build_R first");
+    uint32_t N = c->vrls.size(), G = c->rowPixel.size();
+    for (uint32_t i = 0; i < N; i++) { Float sum = 0; for (uint32_t r = 0; r < G; r++) sum += c->R[(size_t) r * N + i].mean; flags[i] = sum != 0; }
+    return ALVRL_OK;
+}
+int orc_set_column_nonzero(void *h, const uint8_t *flags) {
+    Ctx *c = (Ctx *) h;
+    if (!flags) c->columnFlagsOverride.clear(); else c->columnFlagsOverride.assign(flags, flags + c->vrls.size());
+    return ALVRL_OK;
 }
 int orc_prepass(void *h) {
     int rc;

@@ -302,10 +302,16 @@ def test_multi_handle_slice_ranges_compose(pkg, orc):
     full = setup(_gpu(pkg, False, **params), scene, vrls)
     full.build_slices(); full.prepass()
     img = full.render()
-    parts = []
+    hs = []
     for rng_ in ((0, 4), (4, 10)):
         h = setup(_gpu(pkg, False, **params), scene, vrls)
-        h.build_slices(); h.set_slice_range(*rng_); h.prepass()
+        h.build_slices(); h.set_slice_range(*rng_); h.sample_slice_mapping(); h.build_R()
+        hs.append(h)
+    flags = np.maximum(hs[0].column_nonzero(), hs[1].column_nonzero())      # the all-reduce (MAX) of the multi-GPU path
+    assert np.array_equal(flags, full.column_nonzero())
+    parts = []
+    for h in hs:
+        h.set_column_nonzero(flags); h.build_clusters()
         parts.append(h.render())
     assert np.array_equal(parts[0] + parts[1], img)
     assert not np.array_equal(parts[0], img)
