@@ -99,32 +99,36 @@ def workload(pkg, a):
 # ---------------------------------------------------------------------------------------------------------------------
 def cpu_baseline(pkg, scene, vrls, params, hg, seconds, full_desc):
     """The reference's CPU algorithm (oracle port, -O3 + the reference's -funsafe-math-optimizations) on a bounded sample
-    of the same workload with all host threads: R rows of a few slices x all VRLs."""
+    of the same workload with all host threads: the R rows of the first slices x a prefix of the VRL set, sized from a
+    short calibration so that the timed part takes about `seconds`."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import orc  # the CPU oracle: allowed here (cpu_baseline / --impl reference legs only)
     cores = os.cpu_count() or 1
-    o = orc.Oracle(fast=True, threads=cores, **params)
-    o.set_scene(scene)
-    o.set_vrls(*vrls)
-    o.build_slices()
-    o.sample_slice_mapping()
-    S, G = o.num_slices()
-    # calibrate: time one slice, then take as many slices as fit the budget
-    off, _ = o.rep_pixels()
-    o.set_slice_range(0, 1)
-    t0 = time.perf_counter()
-    o.build_R()
-    t1 = time.perf_counter() - t0
-    pairs1 = int(off[1] - off[0]) * o.N
-    rate = pairs1 / t1
-    n_slices = int(max(1, min(S, seconds * rate / max(1, (G / S) * o.N))))
-    o.set_slice_range(0, n_slices)
-    t0 = time.perf_counter()
-    o.build_R()
-    dt = time.perf_counter() - t0
-    pairs = int(off[n_slices] - off[0]) * o.N
+    start, end, power, pc = vrls
+
+    def run(n_vrls, n_slices):
+        o = orc.Oracle(fast=True, threads=cores, **params)
+        o.set_scene(scene)
+        o.set_vrls(start[:n_vrls], end[:n_vrls], power[:n_vrls], pc)
+        o.build_slices()
+        o.sample_slice_mapping()
+        off, _ = o.rep_pixels()
+        n_slices = min(n_slices, len(off) - 1)
+        o.set_slice_range(0, n_slices)
+        t0 = time.perf_counter()
+        o.build_R()
+        dt = time.perf_counter() - t0
+        return int(off[n_slices]) * o.N, dt, int(off[n_slices]), o.N
+
+    pairs, dt, _, _ = run(min(len(start), 2000), 1)                    # calibration (a second or so)
+    rate = pairs / max(dt, 1e-3)
+    rows_per_slice = max(1, pairs // min(len(start), 2000))
+    want = seconds * rate
+    n_vrls = int(min(len(start), max(2000, want / rows_per_slice)))
+    n_slices = int(max(1, want / (rows_per_slice * n_vrls)))
+    pairs, dt, rows, n_used = run(n_vrls, n_slices)
     return {"value": pairs / dt, "unit": "VRL-segment contributions/s", "cores": cores, "kind": "port",
-            "sample": f"R rows of slices [0,{n_slices}) = {int(off[n_slices])} rows x {o.N} VRLs ({pairs:.3e} integrateVRL calls) "
+            "sample": f"R rows of the first {n_slices} slice(s) = {rows} rows x the first {n_used} VRLs ({pairs:.3e} integrateVRL calls) "
                       f"of {full_desc}; oracle port built -O3 -march=x86-64-v3 -funsafe-math-optimizations, {cores} threads, {dt:.1f} s"}, dt
 
 
@@ -171,6 +175,7 @@ def run_ours(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if multi:
+        os.environ["NCCL_DEBUG"] = os.environ.get("ALVRL_NCCL_DEBUG", "WARN")     # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     scene, vrls, params, desc, hg = workload(pkg, a)

@@ -26,7 +26,7 @@
 #error "define ALVRL_FLAVOR (strict|fast) before including transport.cuh"
 #endif
 
-#define ALVRL_TILE_VRLS 64
+#define ALVRL_TILE_VRLS 256
 #define ALVRL_CTA_SEGS 128
 
 /* ---- flavoured math ---------------------------------------------------------------------------- */

@@ -290,8 +290,10 @@ static int buildR_impl(Ctx *c, std::vector<float> *recordTape) {
         for (int t = 0; t < T; t++) th.emplace_back([&, t]() {
             TapeSampler smp(c->tape, c->tapeLen, c->K() * c->P.Rsamples, N);
             IntegratorCore core = c->core();
-            uint32_t s0 = sb + (uint64_t) (se - sb) * t / T, s1 = sb + (uint64_t) (se - sb) * (t + 1) / T;
-            for (uint32_t row = c->rowOffset[s0]; row < c->rowOffset[s1]; row++) buildRow(c, core, &smp, row, &c->R[(size_t) row * N]);
+            /* rows are independent in the addressed streams: split the row range evenly over the threads */
+            const uint32_t rb = c->rowOffset[sb], re = c->rowOffset[se];
+            const uint32_t r0 = rb + (uint64_t) (re - rb) * t / T, r1 = rb + (uint64_t) (re - rb) * (t + 1) / T;
+            for (uint32_t row = r0; row < r1; row++) buildRow(c, core, &smp, row, &c->R[(size_t) row * N]);
             sh[t] = core.shadowRays;
         });
         for (auto &t : th) t.join();
@@ -321,8 +323,10 @@ static int buildR_impl(Ctx *c, std::vector<float> *recordTape) {
         for (int t = 0; t < T; t++) th.emplace_back([&, t]() {
             CounterSampler smp(c->P.seed);
             IntegratorCore core = c->core();
-            uint32_t s0 = sb + (uint64_t) (se - sb) * t / T, s1 = sb + (uint64_t) (se - sb) * (t + 1) / T;
-            for (uint32_t row = c->rowOffset[s0]; row < c->rowOffset[s1]; row++) buildRow(c, core, &smp, row, &c->R[(size_t) row * N]);
+            /* rows are independent in the addressed streams: split the row range evenly over the threads */
+            const uint32_t rb = c->rowOffset[sb], re = c->rowOffset[se];
+            const uint32_t r0 = rb + (uint64_t) (re - rb) * t / T, r1 = rb + (uint64_t) (re - rb) * (t + 1) / T;
+            for (uint32_t row = r0; row < r1; row++) buildRow(c, core, &smp, row, &c->R[(size_t) row * N]);
             sh[t] = core.shadowRays;
         });
         for (auto &t : th) t.join();
