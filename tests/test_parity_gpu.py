@@ -315,3 +315,40 @@ def test_multi_handle_slice_ranges_compose(pkg, orc):
         parts.append(h.render())
     assert np.array_equal(parts[0] + parts[1], img)
     assert not np.array_equal(parts[0], img)
+
+
+# ---- full BASELINE size (C2), size-independent properties -------------------------------------------------------
+def test_c2_full_size_properties(pkg):
+    """1024x1024, 100k VRLs, 4/4: too large for the oracle, so the path is checked through properties it must have at any
+    size: slices partition the hit pixels; build_R is idempotent; R is linear in the VRL power (x2 is exact in fp32: mean
+    doubles, variance quadruples, bit for bit); the frame is finite and non-negative; slice ranges compose."""
+    scene, vrls, params = pkg.scenes.make_config("C2")
+    start, end, power, pc = vrls
+    g = _gpu(pkg, False, **params)
+    g.set_scene(scene); g.set_vrls(start, end, power, pc)
+    g.build_slices()
+    p2s = g.pixel_to_slice()
+    prim = g.primary_hits()[0]
+    S, _ = g.num_slices()
+    assert S == 100 and ((p2s == 0xFFFFFFFF) == (prim == 0xFFFFFFFF)).all()
+    assert np.array_equal(np.unique(p2s[p2s != 0xFFFFFFFF]), np.arange(S))
+    g.set_slice_range(0, 3)
+    g.sample_slice_mapping()
+    off, px = g.rep_pixels()
+    assert abs(off[-1] / (p2s != 0xFFFFFFFF).sum() - 1 / 64) < 2e-3            # targetPixelUndersampling = 64
+    rows = int(off[3])
+    g.build_R(); R1 = g.get_R(0, rows)
+    g.build_R(); R2 = g.get_R(0, rows)
+    assert np.array_equal(R1, R2)                                               # idempotent
+    assert np.isfinite(R1).all() and (R1 >= 0).all() and (R1[..., 0] > 0).mean() > 0.5
+    g.set_vrls(start, end, 2 * power, pc)
+    g.build_R(); R3 = g.get_R(0, rows)
+    assert np.array_equal(R3[..., 0], 2 * R1[..., 0]) and np.array_equal(R3[..., 1], 4 * R1[..., 1])   # linear in the power
+    # whole frame, and the same frame from two handles that own disjoint slice ranges
+    g.set_vrls(start, end, power, pc)
+    g.set_slice_range(0, S); g.prepass()
+    img = g.render()
+    assert np.isfinite(img).all() and (img >= 0).all() and img.mean() > 0
+    assert (img.reshape(-1, 3)[(p2s == 0xFFFFFFFF).reshape(1024, 1024).T.reshape(-1)] == 0).all()     # misses stay black
+    st = g.stats()
+    assert st.numRows == off[-1] and st.numVrls == len(start)
