@@ -4,7 +4,7 @@
 set -e
 cd "$(dirname "$0")"
 OUT=../libalvrl.so
-NV="nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-ffp-contract=off,-fno-fast-math,-Wall,-Wno-unused-function"
+NV="nvcc $ALVRL_EXTRA_NVCC -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-ffp-contract=off,-fno-fast-math,-Wall,-Wno-unused-function"
 mkdir -p obj
 build_one() { # src flags...
   local src=$1; shift

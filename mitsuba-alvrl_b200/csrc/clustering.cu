@@ -517,6 +517,12 @@ struct ClusterNode {                                                           /
     bool operator<(const ClusterNode &o) const { return undersamplingVar + integrationVar < o.undersamplingVar + o.integrationVar; }
 };
 
+} // namespace (anonymous)
+} // namespace alvrl
+#include "refine.cuh"
+namespace alvrl {
+namespace {
+
 /* weightedSample, Preprocessor.cpp:1534-1580 (sequential fp32 prefix sums, reference order) */
 size_t weighted_sample(const std::vector<float> &weights, HostSampler *smp, float *prob, size_t begin, size_t end, const std::vector<uint32_t> &ind) {
     if (begin >= end) throw Error(ALVRL_ERR_ARG, "Trying to take weighted sample of empty set!");
@@ -772,6 +778,7 @@ struct Workspace {
                 if (in->numClusters() >= in->targetClusters || in->numMulti() <= 0) in->done = true;
             }
         }
+        if (deviceRounds && !getenv("ALVRL_HOST_ROUNDS")) refineDevice(which);
         for (;;) {
             /* one runnable instance per sampler group: a shared sequential stream (SFMT) serialises its instances */
             std::vector<Inst *> round; std::vector<int> groupsBusy;
@@ -793,6 +800,119 @@ struct Workspace {
         }
         syncLists(which);
         for (Inst *in : which) in->refining = false;
+    }
+    /* Device-resident refinement (refine.cuh): every object of `which` that is not done and that the kernel supports runs to
+     * completion in one launch; objects it hands back (RF_RESUME_HOST: queue larger than the shared-memory heap) and the ones
+     * it does not take (more than RF_MAXROWS rows, sequential sample streams) continue in the host-driven rounds below. */
+    void refineDevice(const std::vector<Inst *> &which) {
+        std::vector<Inst *> dev;
+        std::vector<RfInst> hi;
+        std::vector<ClusterNode> initNodes; std::vector<uint32_t> initSingles;
+        uint64_t xFloats = 0;
+        size_t freeB = 0, totalB = 0;
+        ALVRL_CUDA(cudaMemGetInfo(&freeB, &totalB));
+        for (Inst *in : which) {
+            uint32_t key = 0, pos = 0;
+            if (in->done || in->nr > RF_MAXROWS || in->nr == 0 || !in->smp->counterState(key, pos)) continue;
+            if (in->pq.size() + 2 > RF_HEAP_CAP || in->singletons.size() + 2 > RF_NODE_CAP) continue;
+            if (2 * (xFloats + (uint64_t) N * (in->nr + 4)) * sizeof(float) + (dev.size() + 1) * (uint64_t) N * 64 > freeB / 2) continue;   /* the two compacted copies would not fit */
+            RfInst r; memset(&r, 0, sizeof(r));
+            r.r0 = in->r0; r.nr = in->nr; r.lw = in->lw; r.listOff = in->listOff; r.cwOff = in->cwOff;
+            r.nrP = (in->nr + 3u) & ~3u; r.xOff = xFloats; r.vOff = (uint64_t) dev.size() * N;
+            xFloats += (uint64_t) N * r.nrP;
+            r.numVrlsTotal = in->numVrlsTotal; r.pixelUndersampling = in->pixelUndersampling; r.tracingVar = in->tracingVar; r.unclIntVar = in->unclIntVar;
+            r.adaptive = in->adaptive ? 1u : 0u; r.targetClusters = in->targetClusters; r.rngKey = key; r.rngPos = pos;
+            r.underVar = in->underVar; r.intVar = in->intVar; r.bestConstant = in->bestConstant;
+            r.heapCount = r.nodeCount = (uint32_t) in->pq.size(); r.singleCount = (uint32_t) in->singletons.size();
+            r.initNodeOff = (uint32_t) initNodes.size(); r.initSingleOff = (uint32_t) initSingles.size();
+            initNodes.insert(initNodes.end(), in->pq.begin(), in->pq.end());
+            for (auto it = in->singletons.rbegin(); it != in->singletons.rend(); ++it) initSingles.push_back(*it);   /* insertion order */
+            dev.push_back(in); hi.push_back(r);
+        }
+        if (dev.empty()) return;
+        double p0 = Prof::now();
+        int devId = 0, sms = 0;
+        ALVRL_CUDA(cudaGetDevice(&devId));
+        ALVRL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, devId));
+        const uint32_t grid = (uint32_t) std::min<size_t>(dev.size(), (size_t) std::max(1, sms));
+        uint64_t keyStride = 2; while (keyStride < N) keyStride <<= 1;
+        DevBuf<RfInst> dInst; DevBuf<ClusterNode> dInitNodes, dOutNodes, dNodes; DevBuf<uint32_t> dInitSingles, dOutSingles, dSingles, dCursors;
+        DevBuf<HeapEntry> dSnap; DevBuf<unsigned long long> dKeysG; DevBuf<double> dWG, dVcol; DevBuf<float2> dPairsG; DevBuf<float> dX, dX2; DevBuf<uint32_t> dSrcPos;
+        initNodes.push_back(ClusterNode{0, 0, 0, 0}); initSingles.push_back(0);                  /* never empty */
+        dInst.upload(hi, st); dInitNodes.upload(initNodes, st); dInitSingles.upload(initSingles, st);
+        dOutNodes.alloc(dev.size() * (size_t) (2 * RF_HEAP_CAP)); dOutSingles.alloc(dev.size() * (size_t) RF_NODE_CAP);
+        dNodes.alloc((size_t) grid * RF_NODE_CAP); dSingles.alloc((size_t) grid * RF_NODE_CAP); dSnap.alloc((size_t) grid * RF_HEAP_CAP);
+        dKeysG.alloc((size_t) grid * keyStride); dWG.alloc((size_t) grid * 3 * N); dPairsG.alloc((size_t) grid * 2 * N);
+        dCursors.alloc(4);
+        dX.alloc(xFloats); dX2.alloc(xFloats); dVcol.alloc(dev.size() * (size_t) N); dSrcPos.alloc((size_t) grid * 2 * N);
+        k_rf_compact<<<dim3((N + 7) / 8, (uint32_t) dev.size()), 256, 0, st>>>(R, ldR, N, dInst.p, dLists.p, dCw.p, dX.p, dVcol.p);
+        ALVRL_CUDA(cudaMemsetAsync(dCursors.p, 0, 4 * sizeof(uint32_t), st));
+        RfScratch scr;
+        scr.keys = dKeysG.p; scr.w = dWG.p; scr.Wf = dWG.p + (size_t) grid * N; scr.Wr = dWG.p + (size_t) grid * 2 * N; scr.pairs = dPairsG.p;
+        scr.keyStride = keyStride; scr.stepStride = N;
+        scr.snapHeap = dSnap.p; scr.nodes = dNodes.p; scr.singles = dSingles.p;
+        scr.srcPos = dSrcPos.p; scr.posTmp = dSrcPos.p + (size_t) grid * N;
+        scr.initNodes = dInitNodes.p; scr.initSingles = dInitSingles.p; scr.outNodes = dOutNodes.p; scr.outSingles = dOutSingles.p; scr.cursors = dCursors.p;
+        ALVRL_CUDA(cudaFuncSetAttribute(k_refine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(RfShared)));
+        k_refine<<<grid, RF_THREADS, sizeof(RfShared), st>>>(dX.p, dX2.p, dVcol.p, dInst.p, (uint32_t) dev.size(), dLists.p, dCw.p, scr);
+        launches(2);
+        ALVRL_CUDA(cudaGetLastError());
+        dInst.download(hi.data(), hi.size(), st);
+        uint32_t cursors[4];
+        dCursors.download(cursors, 4, st);
+        std::vector<ClusterNode> outNodes(std::max<uint32_t>(cursors[1], 1)); std::vector<uint32_t> outSingles(std::max<uint32_t>(cursors[2], 1));
+        if (cursors[1]) dOutNodes.download(outNodes.data(), cursors[1], st);
+        if (cursors[2]) dOutSingles.download(outSingles.data(), cursors[2], st);
+        uint64_t splits = 0, degenerate = 0, resumed = 0;
+        unsigned long long clk[2][12] = {{0}};
+        std::vector<std::pair<unsigned long long, size_t>> perObj;
+        for (size_t i = 0; i < dev.size(); i++) {
+            Inst &in = *dev[i];
+            const RfInst &r = hi[i];
+            switch (r.status) {
+                case RF_DONE: case RF_RESUME_HOST: break;
+                case RF_ERR_CONSTANT: throw Error(ALVRL_ERR_ARG, "invalid convergence constant");
+                case RF_ERR_LOWER: throw Error(ALVRL_ERR_ARG, "invalid lower bound on convergence constant");
+                case RF_ERR_SPLIT: throw Error(ALVRL_ERR_ARG, "couldn't split cluster!");
+                case RF_ERR_NOBEST: throw Error(ALVRL_ERR_ARG, "Couldn't find best splitting index!");
+                case RF_ERR_SINGLETON_VAR: throw Error(ALVRL_ERR_ARG, "Trying to add singleton cluster with non-zero undersampling variance");
+                default: throw Error(ALVRL_ERR_ARG, "non-positive column weight sum in a cluster split");
+            }
+            const ClusterNode *cur = outNodes.data() + r.outNodeOff, *snap = cur + r.heapCount;
+            const uint32_t *sg = outSingles.data() + r.outSingleOff;
+            in.pq.assign(cur, cur + r.heapCount); in.s_pq.assign(snap, snap + r.sHeapCount);
+            in.singletons.clear(); in.s_single.clear();
+            for (uint32_t k = 0; k < r.singleCount; k++) in.singletons.push_front(sg[k]);
+            for (uint32_t k = 0; k < r.sSingleCount; k++) in.s_single.push_front(sg[k]);
+            in.underVar = r.underVar; in.intVar = r.intVar; in.s_under = r.sUnder; in.s_int = r.sInt; in.bestConstant = r.bestConstant;
+            in.smp->setCounterPos(r.rngPos);
+            in.nearTies += r.nearTies; in.listsStale = true;
+            splits += r.splits; degenerate += r.degenerate;
+            { unsigned long long tot = 0; for (int a = 0; a < 24; a++) { clk[a / 12][a % 12] += r.clk[a / 12][a % 12]; if (a % 12 != 9) tot += r.clk[a / 12][a % 12]; } perObj.push_back(std::make_pair(tot, i)); }
+            if (r.status == RF_DONE) { if (in.adaptive) in.restore(); in.done = true; }
+            else resumed++;
+        }
+        prof.tasks += splits;
+        if (prof.on) fprintf(stderr, "[alvrl clustering] device refinement: %zu objects on %u CTAs, %llu splits (%llu random directions, %llu handed back) in %.1f ms\n",
+                             dev.size(), grid, (unsigned long long) splits, (unsigned long long) degenerate, (unsigned long long) resumed, Prof::now() - p0);
+        if (prof.on) {
+            uint32_t nrMax = 0; size_t skippedRows = 0;
+            for (Inst *in : which) { nrMax = std::max(nrMax, in->nr); if (in->nr > RF_MAXROWS) skippedRows++; }
+            fprintf(stderr, "[alvrl clustering]   objects %zu, %zu with more than %d rows (max %u)\n", which.size(), skippedRows, RF_MAXROWS, nrMax);
+            for (int k = 0; k < 2; k++)
+                fprintf(stderr, "[alvrl clustering]   %s splits %llu, Mcycles summed over CTAs: pick %.1f direction %.1f stage %.1f project %.1f sort %.1f weights %.1f sweep %.1f pairs %.1f argmin+queue %.1f\n",
+                        k ? "large" : "small", clk[k][9], clk[k][0] * 1e-6, clk[k][1] * 1e-6, clk[k][2] * 1e-6, clk[k][3] * 1e-6, clk[k][4] * 1e-6, clk[k][5] * 1e-6, clk[k][6] * 1e-6,
+                        clk[k][7] * 1e-6, clk[k][8] * 1e-6);
+            fprintf(stderr, "[alvrl clustering]   staging detail (thread 0): small issue %.1f wait %.1f | large issue %.1f wait %.1f\n", clk[0][10] * 1e-6, clk[0][11] * 1e-6, clk[1][10] * 1e-6, clk[1][11] * 1e-6);
+            std::sort(perObj.rbegin(), perObj.rend());
+            for (size_t k = 0; k < std::min<size_t>(4, perObj.size()); k++) {
+                const RfInst &r = hi[perObj[k].second];
+                fprintf(stderr, "[alvrl clustering]   slowest #%zu: %.1f Mcycles, nr %u, splits %u (large %llu): stage %.1f project %.1f sort %.1f sweep %.1f | large: stage %.1f project %.1f sort %.1f sweep %.1f pick %.1f\n",
+                        k, perObj[k].first * 1e-6, r.nr, r.splits, r.clk[1][9], r.clk[0][2] * 1e-6, r.clk[0][3] * 1e-6, r.clk[0][4] * 1e-6, r.clk[0][6] * 1e-6,
+                        r.clk[1][2] * 1e-6, r.clk[1][3] * 1e-6, r.clk[1][4] * 1e-6, r.clk[1][6] * 1e-6, r.clk[1][0] * 1e-6);
+            }
+            fprintf(stderr, "[alvrl clustering]   mean per object %.1f Mcycles\n", (double) std::accumulate(perObj.begin(), perObj.end(), 0ull, [](unsigned long long a, const std::pair<unsigned long long, size_t> &b) { return a + b.first; }) * 1e-6 / perObj.size());
+        }
     }
     /* Clustering::split (590-684) for one cluster of every instance in `round` */
     void splitRound(const std::vector<Inst *> &round, const std::vector<std::pair<uint32_t, uint32_t>> *centres = nullptr) {
@@ -841,7 +961,7 @@ struct Workspace {
                 for (uint32_t r = 0; r < in.nr; r++) {
                     const float s1 = in.smp->next1D(), s2 = in.smp->next1D();
                     const float rr = std::sqrt(-2 * (float) std::log((double) (1 - s1))), phi = (float) (2 * M_PI * s2);
-                    d[r] = cosf(phi) * rr;
+                    d[r] = (float) std::cos((double) phi) * rr;          /* pinned transcendental: double, then rounded (as refine.cuh and the oracle) */
                 }
                 float t = 0; for (float u : d) t += std::fabs(u) * std::fabs(u);
                 nrm = std::sqrt(t);
@@ -1158,7 +1278,7 @@ void build_clusters_device(alvrl_ctx *c, bool needFallback) {
             const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
             /* device rounds leave little host work per round, and every round costs ~20 launches whatever its size: few groups
              * (more Clustering objects per launch) beat many */
-            size_t wantGroups = 3;
+            size_t wantGroups = getenv("ALVRL_HOST_ROUNDS") ? 3 : 1;      /* the device-resident refinement needs no host overlap */
             if (const char *e = getenv("ALVRL_CLUSTER_GROUPS")) wantGroups = (size_t) std::max(1, atoi(e));
             const size_t nGroups = std::max<size_t>(1, std::min<size_t>(std::min<size_t>(wantGroups, hw), ws.insts.size() / 4 + 1));
             std::vector<std::unique_ptr<Workspace>> groups(nGroups);

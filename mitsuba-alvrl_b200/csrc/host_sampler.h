@@ -22,6 +22,9 @@ public:
     virtual float next1D() = 0;
     virtual HostSampler *clone() = 0;
     virtual void setContext(uint32_t /*domain*/, uint32_t /*a*/, uint32_t /*b*/) {}
+    /* addressed streams expose (key, position) so that device code can continue them (refine.cuh) */
+    virtual bool counterState(uint32_t & /*key*/, uint32_t & /*pos*/) const { return false; }
+    virtual void setCounterPos(uint32_t /*pos*/) {}
 };
 
 class Sfmt19937 {
@@ -127,6 +130,8 @@ public:
     void setContext(uint32_t domain, uint32_t a, uint32_t b) override { key = alvrl_rng_key(seed, domain, a, b); k = 0; }
     float next1D() override { return alvrl_rng_uniform(key, k++); }
     HostSampler *clone() override { return new CounterStream(seed); }
+    bool counterState(uint32_t &key_, uint32_t &pos) const override { key_ = key; pos = k; return true; }
+    void setCounterPos(uint32_t pos) override { k = pos; }
 };
 
 } // namespace alvrl

@@ -6,6 +6,8 @@
  */
 #include "slices.h"
 #include "host_sampler.h"
+#include "heap_order.h"
+#include <algorithm>
 #include <cstring>
 using namespace alvrl;
 
@@ -46,6 +48,27 @@ int alvrl_host_slices(const float *pos, const float *dir, uint32_t n, uint32_t t
         rowOffset[i + 1] = rows;
     }
     return 0;
+}
+
+/* heap_order.h against std::push_heap / std::pop_heap (the boost::heap::priority_queue of Clustering): replays a sequence
+ * of operations (op[i] != 0: push keys[i]; op[i] == 0: pop) on both and compares the whole array after every step.
+ * Returns -1 when identical throughout, else the index of the first differing operation. */
+int alvrl_host_heap_check(const float *keys, const uint8_t *op, uint32_t n) {
+    struct Node { float key; uint32_t id; bool operator<(const Node &o) const { return key < o.key; } };
+    std::vector<Node> ref; std::vector<HeapEntry> mine(n + 1); uint32_t count = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        if (op[i] || ref.empty()) {
+            ref.push_back(Node{keys[i], i}); std::push_heap(ref.begin(), ref.end());
+            HeapEntry e; e.key = keys[i]; e.id = i; heap_push(mine.data(), count, e);
+        } else {
+            std::pop_heap(ref.begin(), ref.end()); const Node top = ref.back(); ref.pop_back();
+            const HeapEntry t = heap_pop(mine.data(), count);
+            if (t.id != top.id) return (int) i;
+        }
+        if (count != ref.size()) return (int) i;
+        for (uint32_t k = 0; k < count; k++) if (mine[k].id != ref[k].id) return (int) i;
+    }
+    return -1;
 }
 
 }

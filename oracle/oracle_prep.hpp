@@ -299,7 +299,7 @@ private:
                     /* warp::squareToStdNormal(sampler->next2D()).x, src/libcore/warp.cpp:131-137 */
                     Float s1 = sampler->next1D(), s2 = sampler->next1D();
                     Float r = std::sqrt(-2 * (Float) ::log((double) (1 - s1))), phi = (Float) (2 * M_PI * s2);
-                    direction[i] = cosf(phi) * r;
+                    direction[i] = (Float) ::cos((double) phi) * r;     /* sincosf pinned: evaluated in double, then rounded (libm-independent; the product does the same) */
                 }
             } while (norm2f(direction) == 0);
             Float n = norm2f(direction);

@@ -70,6 +70,18 @@ def test_host_sfmt_matches_known_answers_and_oracle(host_lib, orc):
     assert np.array_equal(f, orc.sfmt_floats(9, 100))
 
 
+def test_device_heap_order_matches_std_heap(host_lib):
+    """heap_order.h (the multi-cluster queue of refine.cuh) replays libstdc++'s push_heap / pop_heap array order, ties included."""
+    rng = np.random.default_rng(5)
+    for n, levels in [(2000, 7), (5000, 100000), (300, 2), (64, 1)]:
+        keys = (rng.integers(0, levels, n) / np.float32(levels)).astype(np.float32)      # many duplicate keys
+        op = (rng.random(n) < 0.6).astype(np.uint8)
+        assert host_lib.alvrl_host_heap_check(keys.ctypes.data_as(C.c_void_p), op.ctypes.data_as(C.c_void_p), C.c_uint32(n)) == -1
+    # grow, then drain completely
+    keys = rng.random(1000).astype(np.float32); op = np.r_[np.ones(500, np.uint8), np.zeros(500, np.uint8)]
+    assert host_lib.alvrl_host_heap_check(keys.ctypes.data_as(C.c_void_p), op.ctypes.data_as(C.c_void_p), C.c_uint32(1000)) == -1
+
+
 @pytest.mark.parametrize("rng_mode", [0, 1])
 @pytest.mark.parametrize("size,target", [((64, 64), 100), ((96, 48), 37), ((16, 16), 400)])
 def test_host_slices_and_rep_pixels_bit_exact_vs_oracle(pkg, orc, host_lib, size, target, rng_mode):
