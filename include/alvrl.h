@@ -89,6 +89,7 @@ typedef struct alvrl_stats {
     float msTransportKernelR, msTransportKernelRender;                /* CUDA-event time of the kernels */
     uint32_t kernelLaunches;    /* kernels launched by this handle since creation */
     uint32_t numSlices, numRows, numVrls, bvhNodes;
+    uint32_t visMode;           /* shadow-ray strategy of the fast flavour: 0 BVH traversal, 1 flat leaf sweep, 2 compiled occluder set */
 } alvrl_stats;
 
 /* ---- life cycle -------------------------------------------------------------------------- */

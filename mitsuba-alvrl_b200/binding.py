@@ -40,7 +40,7 @@ class Stats(C.Structure):
         ("msClusters", C.c_float), ("msRender", C.c_float),
         ("msTransportKernelR", C.c_float), ("msTransportKernelRender", C.c_float),
         ("kernelLaunches", C.c_uint32), ("numSlices", C.c_uint32), ("numRows", C.c_uint32),
-        ("numVrls", C.c_uint32), ("bvhNodes", C.c_uint32),
+        ("numVrls", C.c_uint32), ("bvhNodes", C.c_uint32), ("visMode", C.c_uint32),
     ]
 
 

@@ -13,6 +13,7 @@
 #include <sstream>
 #include <algorithm>
 #include "context.h"
+#include "occluders.h"
 #include "kernels.h"
 
 using namespace alvrl;
@@ -79,7 +80,19 @@ void ensure_scene(alvrl_ctx *c) {
     s.nodes = c->dNodes.p; s.tris = c->dTris.p; s.trisFast = c->dTrisFast.p; s.numNodes = (uint32_t) bvh.nodes.size(); s.numTris = nt; s.leafNodes = c->dLeafNodes.p; s.numLeaves = (uint32_t) leaves.size();
     for (int k = 0; k < 3; k++) { s.kdMin[k] = c->kdMin[k]; s.kdMax[k] = c->kdMax[k]; }
     s.anyHit = c->P.anyHitShadowRays ? 1 : 0;
-    c->stats.bvhNodes = s.numNodes;
+    /* visibility strategy of the fast flavour for small scenes (ALVRL_VIS=tree|flat|occ overrides the choice) */
+    s.occ = nullptr; s.numSlabs = s.numPlanes = s.numOccTris = 0;
+    s.visMode = (s.numLeaves <= 32 && nt <= 128) ? 1 : 0;
+    const char *visEnv = getenv("ALVRL_VIS");
+    if (s.visMode == 1 && !(visEnv && !strcmp(visEnv, "flat"))) {
+        const OccluderSet os = compile_occluders(c->verts.data(), c->tris.data(), nt, s.numLeaves);
+        if (os.use) {
+            c->dOcc.upload(os.stream, c->stream);
+            s.occ = c->dOcc.p; s.numSlabs = os.numSlabs; s.numPlanes = os.numPlanes; s.numOccTris = os.numTris; s.visMode = 2;
+        }
+    }
+    if (visEnv && !strcmp(visEnv, "tree")) s.visMode = 0;
+    c->stats.bvhNodes = s.numNodes; c->stats.visMode = (uint32_t) s.visMode;
     c->sceneDirty = false; c->segsDirty = true;
 }
 

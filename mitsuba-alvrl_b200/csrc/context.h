@@ -80,7 +80,7 @@ struct alvrl_ctx {
     std::vector<float> gridHost;
 
     /* scene (device) */
-    alvrl::DevBuf<BvhNode> dNodes, dLeafNodes; alvrl::DevBuf<TriRec> dTris; alvrl::DevBuf<TriFast> dTrisFast; alvrl::DevBuf<float4> dTriVerts;
+    alvrl::DevBuf<BvhNode> dNodes, dLeafNodes; alvrl::DevBuf<TriRec> dTris; alvrl::DevBuf<TriFast> dTrisFast; alvrl::DevBuf<float4> dTriVerts, dOcc;
     alvrl::DevBuf<uint32_t> dTriMat, dMatBits; alvrl::DevBuf<float4> dMatAlbedo; alvrl::DevBuf<float> dGrid;
     SceneDev sceneDev;
 

@@ -7,6 +7,8 @@
 #include "slices.h"
 #include "host_sampler.h"
 #include "heap_order.h"
+#include "occluders.h"
+#include "occ_query.h"
 #include <algorithm>
 #include <cstring>
 using namespace alvrl;
@@ -69,6 +71,30 @@ int alvrl_host_heap_check(const float *keys, const uint8_t *op, uint32_t n) {
         for (uint32_t k = 0; k < count; k++) if (mine[k].id != ref[k].id) return (int) i;
     }
     return -1;
+}
+
+
+/* occluders.h: compile a small mesh; counts = {use, numSlabs, numPlanes, numTris, numPolytopes}; returns the stream length in float4 */
+int alvrl_host_compile_occluders(const float *verts, const uint32_t *tris, uint32_t nt, uint32_t numLeaves, uint32_t *counts, float *stream,
+                                 uint32_t maxFloat4) {
+    const OccluderSet os = compile_occluders(verts, tris, nt, numLeaves);
+    counts[0] = os.use; counts[1] = os.numSlabs; counts[2] = os.numPlanes; counts[3] = os.numTris; counts[4] = os.numPolytopes;
+    if (os.stream.size() > maxFloat4) return -1;
+    memcpy(stream, os.stream.data(), os.stream.size() * sizeof(float4));
+    return (int) os.stream.size();
+}
+/* occ_query.h on the host: n segments (origin o, unit direction d, [tmin, tmax]) against a compiled stream */
+int alvrl_host_occ_query(const float *stream, const uint32_t *counts, const float *o, const float *d, const float *tmin, const float *tmax,
+                         uint32_t n, uint8_t *out) {
+    const uint32_t ns = counts[1], np = counts[2];
+    const float4 *g = reinterpret_cast<const float4 *>(stream);
+    std::vector<float2> slabB(ns); std::vector<uint32_t> info(np);
+    for (uint32_t i = 0; i < ns; i++) slabB[i] = make_float2(g[ns + i].x, g[ns + i].y);
+    for (uint32_t i = 0; i < np; i++) memcpy(&info[i], &g[2 * ns + np + i].x, 4);
+    for (uint32_t i = 0; i < n; i++)
+        out[i] = occ_query(g, slabB.data(), ns, g + 2 * ns, info.data(), np, g + 2 * ns + 2 * np, o[3 * i], o[3 * i + 1], o[3 * i + 2],
+                           d[3 * i], d[3 * i + 1], d[3 * i + 2], tmin[i], tmax[i], true) ? 1 : 0;
+    return 0;
 }
 
 }

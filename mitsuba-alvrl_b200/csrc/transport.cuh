@@ -388,7 +388,7 @@ struct TileSmem {
  * "Building R" (vrlIntegrator.cpp:302-337,792-825): rows = representative-pixel segments, columns = VRLs.
  * grid.x = row blocks of 128, grid.y = VRL chunks of vrlsPerCta (multiple of the tile size).
  */
-template <int MED, bool SMALL>
+template <int MED, int SMALL>
 __global__ void __launch_bounds__(ALVRL_CTA_SEGS) ALVRL_NAME(k_build_R)(TransportParams P, const SegRec *__restrict__ rowSegs, uint32_t numRows,
                                                                        const VrlRec *__restrict__ vrls, float2 *__restrict__ R, uint32_t ldR,
                                                                        uint32_t vrlsPerCta) {
@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(ALVRL_CTA_SEGS) ALVRL_NAME(k_build_R)(Transpor
     extern __shared__ __align__(128) unsigned char dynSmem[];
     TileSmem &sm = *reinterpret_cast<TileSmem *>(dynSmem);
     BvhSmem &sbvh = *reinterpret_cast<BvhSmem *>(dynSmem + sizeof(TileSmem));
-    if (SMALL) stage_bvh(sbvh, P.scene);
+    if (SMALL) stage_bvh<SMALL>(sbvh, P.scene);
 #else
     __shared__ __align__(128) TileSmem sm;
 #endif
@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(ALVRL_CTA_SEGS) ALVRL_NAME(k_build_R)(Transpor
  * One CTA = up to 128 pixels of one slice; the slice's representative VRLs (records gathered per slice, cluster
  * weight in e.w) stream through the same TMA tile pipeline.  work[cta] = {slice, firstPixel, pixelCount, 0}.
  */
-template <int MED, bool CLUSTERED, bool SMALL>
+template <int MED, bool CLUSTERED, int SMALL>
 __global__ void __launch_bounds__(ALVRL_CTA_SEGS) ALVRL_NAME(k_render)(TransportParams P, const SegRec *__restrict__ pixSegs,
                                                                       const uint32_t *__restrict__ slicePixels, const uint4 *__restrict__ work,
                                                                       const VrlRec *__restrict__ repRecs, const uint32_t *__restrict__ repOffset,
@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(ALVRL_CTA_SEGS) ALVRL_NAME(k_render)(Transport
     extern __shared__ __align__(128) unsigned char dynSmem[];
     TileSmem &sm = *reinterpret_cast<TileSmem *>(dynSmem);
     BvhSmem &sbvh = *reinterpret_cast<BvhSmem *>(dynSmem + sizeof(TileSmem));
-    if (SMALL) stage_bvh(sbvh, P.scene);
+    if (SMALL) stage_bvh<SMALL>(sbvh, P.scene);
 #else
     __shared__ __align__(128) TileSmem sm;
 #endif

@@ -26,13 +26,13 @@ void ALVRL_NAME(launch_build_R)(const TransportParams &P, const SegRec *rowSegs,
     chunks = (P.numVrls + per - 1) / per;
     dim3 grid(rowBlocks, chunks);
 #ifdef ALVRL_FAST
-    const bool small = P.scene.numLeaves <= ALVRL_SMALL_LEAVES && P.scene.numTris <= ALVRL_SMALL_TRIS;
-    if (P.medium.type == 1) ALVRL_GO_R(1, false);
-    else if (P.medium.grey) { if (small) ALVRL_GO_R(2, true); else ALVRL_GO_R(2, false); }
-    else { if (small) ALVRL_GO_R(0, true); else ALVRL_GO_R(0, false); }
+    const int vis = P.scene.visMode;
+    if (P.medium.type == 1) ALVRL_GO_R(1, 0);
+    else if (P.medium.grey) { if (vis == 2) ALVRL_GO_R(2, 2); else if (vis == 1) ALVRL_GO_R(2, 1); else ALVRL_GO_R(2, 0); }
+    else { if (vis == 2) ALVRL_GO_R(0, 2); else if (vis == 1) ALVRL_GO_R(0, 1); else ALVRL_GO_R(0, 0); }
 #else
-    if (P.medium.type == 0) ALVRL_NAME(k_build_R)<0, false><<<grid, ALVRL_CTA_SEGS, 0, st>>>(P, rowSegs, numRows, vrls, R, ldR, per);
-    else ALVRL_NAME(k_build_R)<1, false><<<grid, ALVRL_CTA_SEGS, 0, st>>>(P, rowSegs, numRows, vrls, R, ldR, per);
+    if (P.medium.type == 0) ALVRL_NAME(k_build_R)<0, 0><<<grid, ALVRL_CTA_SEGS, 0, st>>>(P, rowSegs, numRows, vrls, R, ldR, per);
+    else ALVRL_NAME(k_build_R)<1, 0><<<grid, ALVRL_CTA_SEGS, 0, st>>>(P, rowSegs, numRows, vrls, R, ldR, per);
 #endif
 }
 
@@ -55,12 +55,12 @@ void ALVRL_NAME(launch_render)(const TransportParams &P, bool clustered, const S
             ALVRL_NAME(k_render)<MED, false, SM><<<numWork, ALVRL_CTA_SEGS, ALVRL_RENDER_SMEM, st>>>(P, pixSegs, slicePixels, work, repRecs, repOffset, fb, W, H); } \
     } while (0)
 #ifdef ALVRL_FAST
-    const bool small = P.scene.numLeaves <= ALVRL_SMALL_LEAVES && P.scene.numTris <= ALVRL_SMALL_TRIS;
-    if (P.medium.type == 1) ALVRL_LAUNCH_RENDER(1, false);
-    else if (P.medium.grey) { if (small) ALVRL_LAUNCH_RENDER(2, true); else ALVRL_LAUNCH_RENDER(2, false); }
-    else { if (small) ALVRL_LAUNCH_RENDER(0, true); else ALVRL_LAUNCH_RENDER(0, false); }
+    const int vis = P.scene.visMode;
+    if (P.medium.type == 1) ALVRL_LAUNCH_RENDER(1, 0);
+    else if (P.medium.grey) { if (vis == 2) ALVRL_LAUNCH_RENDER(2, 2); else if (vis == 1) ALVRL_LAUNCH_RENDER(2, 1); else ALVRL_LAUNCH_RENDER(2, 0); }
+    else { if (vis == 2) ALVRL_LAUNCH_RENDER(0, 2); else if (vis == 1) ALVRL_LAUNCH_RENDER(0, 1); else ALVRL_LAUNCH_RENDER(0, 0); }
 #else
-    if (P.medium.type == 1) ALVRL_LAUNCH_RENDER(1, false); else ALVRL_LAUNCH_RENDER(0, false);
+    if (P.medium.type == 1) ALVRL_LAUNCH_RENDER(1, 0); else ALVRL_LAUNCH_RENDER(0, 0);
 #endif
 }
 

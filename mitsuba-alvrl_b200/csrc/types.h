@@ -82,6 +82,8 @@ struct SceneDev {
     const BvhNode *nodes; const TriRec *tris; const TriFast *trisFast; const BvhNode *leafNodes; uint32_t numNodes, numTris, numLeaves;
     float kdMin[3], kdMax[3];     /* ShapeKDTree AABB incl. the 1e-3 enlargement (gkdtree.h:1213-1220) */
     int anyHit;
+    /* small scenes, fast flavour (occluders.h): visMode 0 = tree traversal, 1 = flat leaf sweep, 2 = compiled occluder set */
+    const float4 *occ; uint32_t numSlabs, numPlanes, numOccTris; int visMode;
 };
 
 struct TransportParams {

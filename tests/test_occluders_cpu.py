@@ -1,0 +1,172 @@
+"""CPU suite: the occluder compiler (csrc/occluders.h) and its query (csrc/occ_query.h, the function the transport
+kernels inline) decide what brute-force triangle tests decide.  The reference's definition of a shadow query is "any
+triangle hit inside [mint, maxt]" (Scene::evalTransmittance, src/librender/scene.cpp:619-679, through
+ShapeKDTree::rayIntersect, skdtree.cpp:144-204); here it is restated with Moeller-Trumbore in float64."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+
+def compile_occ(host_lib, verts, tris, num_leaves=18):
+    verts = np.ascontiguousarray(verts, dtype=np.float32)
+    tris = np.ascontiguousarray(tris, dtype=np.uint32)
+    counts = np.zeros(5, dtype=np.uint32)
+    stream = np.zeros((4096, 4), dtype=np.float32)
+    n = host_lib.alvrl_host_compile_occluders(verts.ctypes.data_as(C.c_void_p), tris.ctypes.data_as(C.c_void_p), C.c_uint32(len(tris)),
+                                              C.c_uint32(num_leaves), counts.ctypes.data_as(C.c_void_p), stream.ctypes.data_as(C.c_void_p),
+                                              C.c_uint32(len(stream)))
+    assert n >= 0
+    return counts, stream[:n].copy()
+
+
+def query(host_lib, counts, stream, o, d, tmin, tmax):
+    o, d = (np.ascontiguousarray(a, dtype=np.float32) for a in (o, d))
+    tmin, tmax = (np.ascontiguousarray(a, dtype=np.float32) for a in (tmin, tmax))
+    out = np.zeros(len(o), dtype=np.uint8)
+    host_lib.alvrl_host_occ_query(stream.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p),
+                                  d.ctypes.data_as(C.c_void_p), tmin.ctypes.data_as(C.c_void_p), tmax.ctypes.data_as(C.c_void_p),
+                                  C.c_uint32(len(o)), out.ctypes.data_as(C.c_void_p))
+    return out.astype(bool)
+
+
+def brute(verts, tris, o, d, tmin, tmax, margin=0.0):
+    """(hit, graze): any-hit by Moeller-Trumbore in float64; graze marks segments within `margin` of an edge / range end"""
+    v = verts.astype(np.float64)
+    o, d = o.astype(np.float64), d.astype(np.float64)
+    hit = np.zeros(len(o), dtype=bool)
+    graze = np.zeros(len(o), dtype=bool)
+    for a, b, c in tris:
+        A, e1, e2 = v[a], v[b] - v[a], v[c] - v[a]
+        p = np.cross(d, e2)
+        det = p @ e1
+        with np.errstate(divide="ignore", invalid="ignore"):
+            inv = 1.0 / det
+            s = o - A
+            u = (s * p).sum(1) * inv
+            q = np.cross(s, e1)
+            w = (d * q).sum(1) * inv
+            t = (q @ e2) * inv
+        m = margin
+        inside = (u >= 0) & (w >= 0) & (u + w <= 1) & (t >= tmin) & (t <= tmax) & (np.abs(det) > 1e-12)
+        near = (u >= -m) & (w >= -m) & (u + w <= 1 + m) & (t >= tmin - m) & (t <= tmax + m)
+        far = (u >= m) & (w >= m) & (u + w <= 1 - m) & (t >= tmin + m) & (t <= tmax - m) & (np.abs(det) > 1e-6)
+        hit |= inside
+        graze |= near & ~far
+    return hit, graze
+
+
+def random_segments(rng, n, lo=-0.2, hi=1.2):
+    a = rng.uniform(lo, hi, (n, 3))
+    b = rng.uniform(lo, hi, (n, 3))
+    d = b - a
+    L = np.linalg.norm(d, axis=1)
+    return a.astype(np.float32), (d / L[:, None]).astype(np.float32), L.astype(np.float32)
+
+
+def test_cornell_compiles_to_two_boxes_and_five_walls(pkg, host_lib):
+    scene, _, _ = pkg.scenes.make_config("C1", width=8, height=8, n_vrls=4)
+    counts, stream = compile_occ(host_lib, scene["verts"], scene["tris"])
+    use, slabs, planes, ntris, polys = (int(x) for x in counts)
+    assert (use, slabs, planes, ntris, polys) == (1, 6, 5, 10, 2)
+    assert len(stream) == 2 * slabs + 2 * planes + 3 * ntris
+    # each box: three slabs with finite lower bounds, unit normals, the last one flagged
+    assert np.isfinite(stream[:slabs, 3]).all()
+    assert np.allclose(np.linalg.norm(stream[:slabs, :3], axis=1), 1, atol=1e-6)
+    assert list(stream[slabs:2 * slabs, 1].view(np.uint32)) == [0, 0, 1, 0, 0, 1]
+
+
+@pytest.mark.parametrize("closed", [False, True])
+def test_cornell_queries_match_brute_force(pkg, host_lib, closed):
+    scene = pkg.scenes.cornell_scene(8, 8, closed=closed)
+    verts, tris = scene["verts"], scene["tris"]
+    counts, stream = compile_occ(host_lib, verts, tris)
+    assert counts[0] == 1
+    rng = np.random.default_rng(5)
+    o, d, L = random_segments(rng, 40000)
+    tmin = np.zeros_like(L)
+    got = query(host_lib, counts, stream, o, d, tmin, L)
+    want, graze = brute(verts, tris, o, d, tmin, L, margin=1e-4)
+    assert 0.2 < want.mean() < 0.95
+    bad = (got != want) & ~graze
+    assert not bad.any(), (int(bad.sum()), o[bad][:3], d[bad][:3], L[bad][:3])
+    assert graze.mean() < 0.01
+    # segments that start ON a surface with the adaptive epsilon of the shadow-ray overload (skdtree.cpp:154-157)
+    v = verts.astype(np.float64)
+    t = tris[rng.integers(0, len(tris), 20000)]
+    bary = rng.dirichlet((1, 1, 1), len(t))
+    p = (v[t[:, 0]] * bary[:, :1] + v[t[:, 1]] * bary[:, 1:2] + v[t[:, 2]] * bary[:, 2:]).astype(np.float32)
+    q = rng.uniform(0.02, 0.98, (len(t), 3)).astype(np.float32)
+    dd = q - p
+    L = np.linalg.norm(dd, axis=1).astype(np.float32)
+    dd = (dd / L[:, None]).astype(np.float32)
+    tmin = (1e-4 * np.abs(p).max(axis=1)).astype(np.float32)
+    got = query(host_lib, counts, stream, p, dd, tmin, L)
+    want, graze = brute(verts, tris, p, dd, tmin, L, margin=2e-4)
+    bad = (got != want) & ~graze
+    assert not bad.any(), int(bad.sum())
+
+
+def _tetra(offset, s=0.3):
+    v = np.array([[0, 0, 0], [s, 0, 0], [0, s, 0], [0, 0, s]], dtype=np.float32) + np.asarray(offset, dtype=np.float32)
+    t = np.array([[0, 2, 1], [0, 1, 3], [0, 3, 2], [1, 2, 3]], dtype=np.uint32)
+    return v, t
+
+
+def test_general_polytopes_open_and_nonconvex_parts(pkg, host_lib):
+    """a tetrahedron (4 lone half-spaces), an L-shaped non-convex closed prism (falls back to planar groups), a lone quad"""
+    vt, tt = _tetra((0.1, 0.1, 0.1))
+    # L-shaped prism: closed but not convex
+    poly = [(0, 0), (0.4, 0), (0.4, 0.15), (0.15, 0.15), (0.15, 0.4), (0, 0.4)]
+    base, top = 0.55, 0.8
+    vl = np.array([(x + 0.5, base, y + 0.5) for x, y in poly] + [(x + 0.5, top, y + 0.5) for x, y in poly], dtype=np.float32)
+    n = len(poly)
+    tl = []
+    for i in range(n):
+        j = (i + 1) % n
+        tl += [(i, j, n + j), (i, n + j, n + i)]
+    fan = [(0, 1, 2), (0, 2, 3), (0, 3, 4), (0, 4, 5)]
+    tl += [(a, c, b) for a, b, c in fan] + [(n + a, n + b, n + c) for a, b, c in fan]
+    tl = np.array(tl, dtype=np.uint32)
+    vq = np.array([[0.2, 0.9, 0.2], [0.8, 0.9, 0.2], [0.8, 0.9, 0.8], [0.2, 0.9, 0.8]], dtype=np.float32)
+    tq = np.array([[0, 1, 2], [0, 2, 3]], dtype=np.uint32)
+    verts = np.concatenate([vt, vl, vq])
+    tris = np.concatenate([tt, tl + len(vt), tq + len(vt) + len(vl)])
+    counts, stream = compile_occ(host_lib, verts, tris, num_leaves=32)
+    use, slabs, planes, ntris, polys = (int(x) for x in counts)
+    assert use == 1 and polys == 1 and slabs == 4                      # only the tetrahedron is a convex solid
+    assert np.isinf(stream[:slabs, 3]).all()                           # lone half-spaces: c_lo = -inf
+    assert ntris == len(tl) + len(tq) and planes == 6 + 2 + 1          # 6 side planes + 2 caps + the quad
+    rng = np.random.default_rng(11)
+    o, d, L = random_segments(rng, 60000, 0.0, 1.0)
+    tmin = np.zeros_like(L)
+    got = query(host_lib, counts, stream, o, d, tmin, L)
+    want, graze = brute(verts, tris, o, d, tmin, L, margin=1e-4)
+    assert 0.05 < want.mean() < 0.9
+    bad = (got != want) & ~graze
+    assert not bad.any(), int(bad.sum())
+
+
+def test_compiler_declines_what_it_cannot_hold(pkg, host_lib):
+    # more triangles than the shared-memory budget
+    v, t = _tetra((0, 0, 0))
+    verts = np.concatenate([v + i for i in range(40)])
+    tris = np.concatenate([t + 4 * i for i in range(40)])
+    counts, stream = compile_occ(host_lib, verts, tris)
+    assert counts[0] == 0 and len(stream) == 0
+    # cheaper as a flat sweep: 30 separate triangles in 2 leaves
+    rng = np.random.default_rng(3)
+    verts = rng.uniform(0, 1, (90, 3)).astype(np.float32)
+    tris = np.arange(90, dtype=np.uint32).reshape(30, 3)
+    counts, _ = compile_occ(host_lib, verts, tris, num_leaves=2)
+    assert counts[0] == 0
+    # degenerate triangles are dropped, a segment inside a solid does not touch its boundary
+    v, t = _tetra((0, 0, 0), s=1.0)
+    t = np.concatenate([t, [[0, 0, 1]]]).astype(np.uint32)
+    counts, stream = compile_occ(host_lib, v, t, num_leaves=8)
+    assert counts[0] == 1 and counts[4] == 1 and counts[3] == 0
+    o = np.array([[0.1, 0.1, 0.1], [0.1, 0.1, 0.1], [-1, 0.2, 0.2]], dtype=np.float32)
+    d = np.array([[1, 0, 0], [1, 0, 0], [1, 0, 0]], dtype=np.float32)
+    got = query(host_lib, counts, stream, o, d, np.zeros(3, np.float32), np.array([0.3, 5.0, 0.5], np.float32))
+    assert list(got) == [False, True, False]

@@ -139,6 +139,23 @@ def test_R_fast_flavour_tolerance(pkg, orc):
     print(f"fast: median rel err {np.median(em):.2e}, p99.99 {np.quantile(em, 0.9999):.2e}, outliers {frac:.2e}")
 
 
+def test_R_fast_visibility_strategies_agree(pkg, orc, monkeypatch):
+    """the three shadow-ray strategies of the fast flavour (BVH traversal, flat leaf sweep, compiled occluder set of
+    csrc/occluders.h) give the same R within the fast tolerance against the oracle, and agree with each other except on
+    grazing shadow rays"""
+    Rs = {}
+    for vis, mode in (("tree", 0), ("flat", 1), ("auto", 2)):
+        monkeypatch.setenv("ALVRL_VIS", vis)
+        g, o, Rg, Ro = _R_pair(pkg, orc, False, name="C1", w=96, h=96, n=300)
+        assert g.stats().visMode == mode
+        _check_R(Rg, Ro, 1e-3, 1e-3, 1e-4)
+        Rs[vis] = Rg
+    for a, b in (("flat", "auto"), ("tree", "auto")):
+        ma, mb = Rs[a][..., 0], Rs[b][..., 0]
+        diff = np.abs(ma - mb) > 1e-4 * (np.abs(mb) + 1e-9 * np.abs(mb).max())
+        assert diff.mean() < 1e-4, (a, b, diff.mean())
+
+
 def test_R_reference_stream_tape(pkg, orc):
     """the oracle consumes one sequential SFMT stream in the reference's order and records it; the GPU replays the tape"""
     scene, vrls, params = small_case(pkg, "C1", 64, 64, 100, rngMode=1, seed=9)
