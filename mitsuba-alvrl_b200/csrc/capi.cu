@@ -81,14 +81,14 @@ void ensure_scene(alvrl_ctx *c) {
     for (int k = 0; k < 3; k++) { s.kdMin[k] = c->kdMin[k]; s.kdMax[k] = c->kdMax[k]; }
     s.anyHit = c->P.anyHitShadowRays ? 1 : 0;
     /* visibility strategy of the fast flavour for small scenes (ALVRL_VIS=tree|flat|occ overrides the choice) */
-    s.occ = nullptr; s.numSlabs = s.numPlanes = s.numOccTris = 0;
+    s.occTris = nullptr; s.numOccTris = 0; memset(&c->occHost, 0, sizeof(c->occHost));
     s.visMode = (s.numLeaves <= 32 && nt <= 128) ? 1 : 0;
     const char *visEnv = getenv("ALVRL_VIS");
     if (s.visMode == 1 && !(visEnv && !strcmp(visEnv, "flat"))) {
         const OccluderSet os = compile_occluders(c->verts.data(), c->tris.data(), nt, s.numLeaves);
         if (os.use) {
-            c->dOcc.upload(os.stream, c->stream);
-            s.occ = c->dOcc.p; s.numSlabs = os.numSlabs; s.numPlanes = os.numPlanes; s.numOccTris = os.numTris; s.visMode = 2;
+            c->dOcc.upload(os.tris, c->stream);
+            s.occTris = c->dOcc.p; s.numOccTris = os.numTris; s.visMode = 2; c->occHost = os.dev;
         }
     }
     if (visEnv && !strcmp(visEnv, "tree")) s.visMode = 0;
@@ -123,7 +123,7 @@ void finish_slices(alvrl_ctx *c, const std::vector<P3> &pos, const std::vector<P
 TransportParams make_transport_params(alvrl_ctx *c, uint32_t domain) {
     TransportParams T;
     memset(&T, 0, sizeof(T));
-    T.scene = c->sceneDev; T.medium = c->medium;
+    T.scene = c->sceneDev; T.medium = c->medium; T.occ = c->occHost;
     T.Nvv = c->P.volVolSamples; T.Nvs = c->P.volSurfSamples; T.shortVrls = c->P.shortVrls; T.Rsamples = c->P.Rsamples;
     T.seed = c->P.seed; T.rngDomain = domain;
     T.tape = nullptr; T.tapeK = 0;

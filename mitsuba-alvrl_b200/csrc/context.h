@@ -82,7 +82,7 @@ struct alvrl_ctx {
     /* scene (device) */
     alvrl::DevBuf<BvhNode> dNodes, dLeafNodes; alvrl::DevBuf<TriRec> dTris; alvrl::DevBuf<TriFast> dTrisFast; alvrl::DevBuf<float4> dTriVerts, dOcc;
     alvrl::DevBuf<uint32_t> dTriMat, dMatBits; alvrl::DevBuf<float4> dMatAlbedo; alvrl::DevBuf<float> dGrid;
-    SceneDev sceneDev;
+    SceneDev sceneDev; OccDev occHost;
 
     /* VRLs */
     std::vector<VrlRec> vrlHost; uint64_t particleCount = 0;

@@ -74,26 +74,23 @@ int alvrl_host_heap_check(const float *keys, const uint8_t *op, uint32_t n) {
 }
 
 
-/* occluders.h: compile a small mesh; counts = {use, numSlabs, numPlanes, numTris, numPolytopes}; returns the stream length in float4 */
-int alvrl_host_compile_occluders(const float *verts, const uint32_t *tris, uint32_t nt, uint32_t numLeaves, uint32_t *counts, float *stream,
-                                 uint32_t maxFloat4) {
+/* occluders.h: compile a small mesh; counts = {use, numSlabs, numPlanes, numTris, numPolytopes, numBoxes}; the OccDev block
+ * (occ_query.h) is copied to `dev`, the planar groups' triangle records to `tris` (float4, up to maxFloat4) */
+int alvrl_host_compile_occluders(const float *verts, const uint32_t *tris, uint32_t nt, uint32_t numLeaves, uint32_t *counts, void *dev,
+                                 float *triRecs, uint32_t maxFloat4) {
     const OccluderSet os = compile_occluders(verts, tris, nt, numLeaves);
-    counts[0] = os.use; counts[1] = os.numSlabs; counts[2] = os.numPlanes; counts[3] = os.numTris; counts[4] = os.numPolytopes;
-    if (os.stream.size() > maxFloat4) return -1;
-    memcpy(stream, os.stream.data(), os.stream.size() * sizeof(float4));
-    return (int) os.stream.size();
+    counts[0] = os.use; counts[1] = os.numSlabs; counts[2] = os.numPlanes; counts[3] = os.numTris; counts[4] = os.numPolytopes; counts[5] = os.numBoxes;
+    if (os.tris.size() > maxFloat4) return -1;
+    if (os.use) { memcpy(dev, &os.dev, sizeof(OccDev)); memcpy(triRecs, os.tris.data(), os.tris.size() * sizeof(float4)); }
+    return (int) sizeof(OccDev);
 }
-/* occ_query.h on the host: n segments (origin o, unit direction d, [tmin, tmax]) against a compiled stream */
-int alvrl_host_occ_query(const float *stream, const uint32_t *counts, const float *o, const float *d, const float *tmin, const float *tmax,
+/* occ_query.h on the host: n segments (origin o, unit direction d, [tmin, tmax]) against a compiled set */
+int alvrl_host_occ_query(const void *dev, const float *triRecs, const float *o, const float *d, const float *tmin, const float *tmax,
                          uint32_t n, uint8_t *out) {
-    const uint32_t ns = counts[1], np = counts[2];
-    const float4 *g = reinterpret_cast<const float4 *>(stream);
-    std::vector<float2> slabB(ns); std::vector<uint32_t> info(np);
-    for (uint32_t i = 0; i < ns; i++) slabB[i] = make_float2(g[ns + i].x, g[ns + i].y);
-    for (uint32_t i = 0; i < np; i++) memcpy(&info[i], &g[2 * ns + np + i].x, 4);
+    OccDev oc; memcpy(&oc, dev, sizeof(oc));
+    const float4 *tr = reinterpret_cast<const float4 *>(triRecs);
     for (uint32_t i = 0; i < n; i++)
-        out[i] = occ_query(g, slabB.data(), ns, g + 2 * ns, info.data(), np, g + 2 * ns + 2 * np, o[3 * i], o[3 * i + 1], o[3 * i + 2],
-                           d[3 * i], d[3 * i + 1], d[3 * i + 2], tmin[i], tmax[i], true) ? 1 : 0;
+        out[i] = occ_query(oc, tr, o[3 * i], o[3 * i + 1], o[3 * i + 2], d[3 * i], d[3 * i + 1], d[3 * i + 2], tmin[i], tmax[i], true) ? 1 : 0;
     return 0;
 }
 

@@ -1,15 +1,30 @@
 /*
  * occ_query.h -- any-hit query against the compiled occluder set of occluders.h; one source for the transport kernels
- * (shared-memory arrays, MUFU reciprocal) and for the host-side unit test (libalvrl_host.so, IEEE division).
+ * and for the host-side unit test (libalvrl_host.so, IEEE division instead of MUFU.RCP).
  *
- * Uniform loops: every slab clips the parametric interval of its solid, every plane contributes one bit "crossed
- * inside [tmin, tmax]"; triangle records are only touched for crossed planes.  On the device all lanes of a warp call
- * it together (need = false: the lane has no ray) so that the loops stay converged and the loads are broadcasts.
+ * The set travels in the kernel parameters (constant bank): the loops below are warp-uniform, so slab and plane records
+ * arrive through the uniform datapath (LDCU) instead of the LSU.  Boxes -- solids of exactly three finite slabs -- come
+ * first and are clipped by an unrolled body without flag tests; other convex solids follow as flagged slab runs; every
+ * plane of a planar group contributes one bit "crossed inside [tmin, tmax]", and triangle records (shared memory) are
+ * only touched for crossed planes.  On the device all lanes of a warp call it together (need = false: the lane has no
+ * ray) so that the loops stay converged.
  */
 #pragma once
 #include <stdint.h>
 #include <math.h>
 #include <cuda_runtime.h>
+
+#define ALVRL_OCC_MAX_SLABS 24
+#define ALVRL_OCC_MAX_PLANES 24
+#define ALVRL_OCC_MAX_TRIS 128
+
+struct OccDev {
+    float4 slabA[ALVRL_OCC_MAX_SLABS];       /* n.xyz, c_lo  (c_lo <= n.x <= c_hi; a lone half-space has c_lo = -inf) */
+    float2 slabB[ALVRL_OCC_MAX_SLABS];       /* c_hi, bits != 0: last slab of its solid */
+    float4 planes[ALVRL_OCC_MAX_PLANES];     /* n.xyz, c */
+    uint32_t planeInfo[ALVRL_OCC_MAX_PLANES];/* first << 8 | count into the triangle records */
+    uint32_t numBoxes, numSlabs, numPlanes, numTris;   /* slabs [0, 3 numBoxes) are the boxes */
+};
 
 #ifdef __CUDA_ARCH__
 #define ALVRL_OCC_HD __device__ __forceinline__
@@ -25,37 +40,44 @@ static inline uint32_t alvrl_occ_bits(float f) { uint32_t u; __builtin_memcpy(&u
 #define ALVRL_OCC_BITS(f) alvrl_occ_bits(f)
 #endif
 
-ALVRL_OCC_HD bool occ_query(const float4 *slabA, const float2 *slabB, uint32_t numSlabs, const float4 *planes, const uint32_t *planeInfo,
-                            uint32_t numPlanes, const float4 *tris, float ox, float oy, float oz, float dx, float dy, float dz, float tmin,
+/* clip the parametric interval [tn, tf] of the line o + t d by the slab c_lo <= n.x <= c_hi */
+#define ALVRL_OCC_CLIP(a, chi)                                                     \
+    do {                                                                           \
+        const float den_ = fmaf((a).x, dx, fmaf((a).y, dy, (a).z * dz));           \
+        const float no_ = fmaf((a).x, ox, fmaf((a).y, oy, (a).z * oz));            \
+        const float r_ = ALVRL_OCC_RCP(den_);                                      \
+        const float t1_ = ((a).w - no_) * r_, t2_ = ((chi) - no_) * r_;            \
+        tn = fmaxf(tn, fminf(t1_, t2_));                                           \
+        tf = fminf(tf, fmaxf(t1_, t2_));                                           \
+    } while (0)
+/* the segment touches the solid's boundary iff the clipped line is non-empty and enters or leaves it inside [tmin, tmax] */
+#define ALVRL_OCC_TOUCH() (tn <= tf && ((tn >= tmin && tn <= tmax) || (tf >= tmin && tf <= tmax)))
+
+ALVRL_OCC_HD bool occ_query(const OccDev &oc, const float4 *tris, float ox, float oy, float oz, float dx, float dy, float dz, float tmin,
                             float tmax, bool need) {
     const float INF = INFINITY;
     bool hit = false;
-    float tn = -INF, tf = INF;
-#ifdef __CUDA_ARCH__
-#pragma unroll 3
-#endif
-    for (uint32_t i = 0; i < numSlabs; i++) {
-        const float4 a = slabA[i];
-        const float2 b = slabB[i];
-        const float den = fmaf(a.x, dx, fmaf(a.y, dy, a.z * dz));
-        const float no = fmaf(a.x, ox, fmaf(a.y, oy, a.z * oz));
-        const float r = ALVRL_OCC_RCP(den);
-        const float t1 = (a.w - no) * r, t2 = (b.x - no) * r;
-        tn = fmaxf(tn, fminf(t1, t2));
-        tf = fminf(tf, fmaxf(t1, t2));
-        if (ALVRL_OCC_BITS(b.y)) {
-            /* last slab of a solid: the segment touches its boundary iff the clipped line is non-empty and enters or
-             * leaves the solid inside [tmin, tmax] */
-            hit |= tn <= tf && ((tn >= tmin && tn <= tmax) || (tf >= tmin && tf <= tmax));
-            tn = -INF; tf = INF;
+    const uint32_t nb = oc.numBoxes;
+    for (uint32_t b = 0; b < nb; b++) {
+        float tn = -INF, tf = INF;
+        ALVRL_OCC_CLIP(oc.slabA[3 * b], oc.slabB[3 * b].x);
+        ALVRL_OCC_CLIP(oc.slabA[3 * b + 1], oc.slabB[3 * b + 1].x);
+        ALVRL_OCC_CLIP(oc.slabA[3 * b + 2], oc.slabB[3 * b + 2].x);
+        hit |= ALVRL_OCC_TOUCH();
+    }
+    {
+        float tn = -INF, tf = INF;
+        for (uint32_t i = 3 * nb; i < oc.numSlabs; i++) {
+            ALVRL_OCC_CLIP(oc.slabA[i], oc.slabB[i].x);
+            if (ALVRL_OCC_BITS(oc.slabB[i].y)) {
+                hit |= ALVRL_OCC_TOUCH();
+                tn = -INF; tf = INF;
+            }
         }
     }
     uint32_t mask = 0;
-#ifdef __CUDA_ARCH__
-#pragma unroll 5
-#endif
-    for (uint32_t i = 0; i < numPlanes; i++) {
-        const float4 p = planes[i];
+    for (uint32_t i = 0; i < oc.numPlanes; i++) {
+        const float4 p = oc.planes[i];
         const float den = fmaf(p.x, dx, fmaf(p.y, dy, p.z * dz));
         const float no = fmaf(p.x, ox, fmaf(p.y, oy, p.z * oz));
         const float t = (p.w - no) * ALVRL_OCC_RCP(den);
@@ -66,12 +88,12 @@ ALVRL_OCC_HD bool occ_query(const float4 *slabA, const float2 *slabB, uint32_t n
     while (mask) {
         const uint32_t i = ALVRL_OCC_FFS(mask);
         mask &= mask - 1;
-        const float4 p = planes[i];
+        const float4 p = oc.planes[i];
         const float den = fmaf(p.x, dx, fmaf(p.y, dy, p.z * dz));
         const float no = fmaf(p.x, ox, fmaf(p.y, oy, p.z * oz));
         const float t = (p.w - no) * ALVRL_OCC_RCP(den);
         const float Px = fmaf(t, dx, ox), Py = fmaf(t, dy, oy), Pz = fmaf(t, dz, oz);
-        const uint32_t info = planeInfo[i], first = info >> 8, cnt = info & 255u;
+        const uint32_t info = oc.planeInfo[i], first = info >> 8, cnt = info & 255u;
         for (uint32_t k = 0; k < cnt; k++) {
             const float4 q = tris[3 * (first + k) + 1], w = tris[3 * (first + k) + 2];
             const float u = fmaf(q.x, Px, fmaf(q.y, Py, fmaf(q.z, Pz, q.w)));

@@ -13,8 +13,8 @@
  *     evaluation decides whether the segment crosses the plane inside [mint, maxt]; only then are the group's
  *     triangles tested (plane + barycentric functionals, TriFast).  For two points inside a room no wall is crossed.
  *
- * The result is a flat float4 stream the transport kernels keep in shared memory (transport_fast_impl.cuh,
- * occluded_occ).  It decides exactly what the triangle tests decide, up to grazing rays (the documented tie class).
+ * The result (OccDev, occ_query.h) travels in the kernel parameters of the transport kernels; only the planar groups'
+ * triangle records live in shared memory.  It decides exactly what the triangle tests decide, up to grazing rays (the documented tie class).
  * The compiler declines (use = false) when the scene does not fit the budgets or a flat leaf sweep would be cheaper.
  */
 #pragma once
@@ -27,19 +27,15 @@
 #include <numeric>
 #include "types.h"
 #include "bvh.h"
+#include "occ_query.h"
 
 namespace alvrl {
 
-#define ALVRL_OCC_MAX_SLABS 32
-#define ALVRL_OCC_MAX_PLANES 32
-#define ALVRL_OCC_MAX_TRIS 128
-
 struct OccluderSet {
     bool use = false;
-    uint32_t numSlabs = 0, numPlanes = 0, numTris = 0, numPolytopes = 0;
-    /* stream: slabA[numSlabs] (n.xyz, c_lo) | slabB[numSlabs] (c_hi, last-of-polytope bits, 0, 0) | planes[numPlanes] (n.xyz, c)
-     *         | planeInfo[numPlanes] ((first << 8 | count) bits, 0, 0, 0) | tris[3 * numTris] (TriFast p, q, r)        */
-    std::vector<float4> stream;
+    uint32_t numSlabs = 0, numPlanes = 0, numTris = 0, numPolytopes = 0, numBoxes = 0;
+    OccDev dev;                       /* slabs (boxes first) and planes: travels in the kernel parameters */
+    std::vector<float4> tris;         /* TriFast p, q, r of the planar groups' triangles: shared memory */
 };
 
 namespace occ_detail {
@@ -113,7 +109,10 @@ inline OccluderSet compile_occluders(const float *verts, const uint32_t *tris, u
     std::vector<uint8_t> closed(nt, 1);                           /* per component root */
     for (auto &e : edges) if (e.second.size() != 2) closed[dsu.find(e.second[0])] = 0;
 
-    std::vector<float4> slabA, slabB, planes, planeInfo, triStream;
+    struct Solid { std::vector<float4> a; std::vector<float> chi; bool box; };
+    std::vector<Solid> solids;
+    std::vector<float4> planes, triStream;
+    std::vector<uint32_t> planeInfo;
     std::vector<uint8_t> inPolytope(nt, 0);
     for (uint32_t root = 0; root < nt; root++) {
         if (!ok[root] || dsu.find(root) != root || !closed[root]) continue;
@@ -145,22 +144,23 @@ inline OccluderSet compile_occluders(const float *verts, const uint32_t *tris, u
         if (!solid) continue;
         /* pair antiparallel faces into slabs */
         std::vector<uint8_t> used(faces.size(), 0);
-        const size_t firstSlab = slabA.size();
+        Solid sol; sol.box = true;
         for (size_t i = 0; i < faces.size(); i++) {
             if (used[i]) continue;
             used[i] = 1;
             double clo = -INFINITY;
             for (size_t j = i + 1; j < faces.size(); j++)
                 if (!used[j] && ndist(faces[i].n, faces[j].n, -1.0) < dirTol) { used[j] = 1; clo = -faces[j].c; break; }
-            slabA.push_back(make_float4((float) faces[i].n[0], (float) faces[i].n[1], (float) faces[i].n[2], (float) clo));
-            slabB.push_back(make_float4((float) faces[i].c, 0.0f, 0.0f, 0.0f));
+            sol.a.push_back(make_float4((float) faces[i].n[0], (float) faces[i].n[1], (float) faces[i].n[2], (float) clo));
+            sol.chi.push_back((float) faces[i].c);
+            if (!std::isfinite(clo)) sol.box = false;
         }
-        if (slabA.size() > firstSlab) {
-            const uint32_t one = 1u; memcpy(&slabB.back().y, &one, 4);
-            out.numPolytopes++;
-            for (uint32_t t : comp) inPolytope[t] = 1;
-        }
+        sol.box = sol.box && sol.a.size() == 3;
+        solids.push_back(sol);
+        out.numPolytopes++;
+        for (uint32_t t : comp) inPolytope[t] = 1;
     }
+    std::stable_sort(solids.begin(), solids.end(), [](const Solid &x, const Solid &y) { return x.box > y.box; });
 
     /* planar groups of the remaining triangles */
     struct Group { Plane p; std::vector<uint32_t> tris; };
@@ -179,25 +179,30 @@ inline OccluderSet compile_occluders(const float *verts, const uint32_t *tris, u
     for (const Group &g : groups) {
         const uint32_t first = (uint32_t) (triStream.size() / 3), info = (first << 8) | (uint32_t) g.tris.size();
         planes.push_back(make_float4((float) g.p.n[0], (float) g.p.n[1], (float) g.p.n[2], (float) g.p.c));
-        float4 pi = make_float4(0, 0, 0, 0); memcpy(&pi.x, &info, 4);
-        planeInfo.push_back(pi);
+        planeInfo.push_back(info);
         for (uint32_t t : g.tris) {
             const TriFast f = makeTriFast(verts + 3 * (size_t) tris[3 * t], verts + 3 * (size_t) tris[3 * t + 1], verts + 3 * (size_t) tris[3 * t + 2]);
             triStream.push_back(f.p); triStream.push_back(f.q); triStream.push_back(f.r);
         }
     }
 
-    out.numSlabs = (uint32_t) slabA.size(); out.numPlanes = (uint32_t) planes.size(); out.numTris = (uint32_t) (triStream.size() / 3);
+    for (const Solid &so : solids) { out.numSlabs += (uint32_t) so.a.size(); out.numBoxes += so.box ? 1 : 0; }
+    out.numPlanes = (uint32_t) planes.size(); out.numTris = (uint32_t) (triStream.size() / 3);
     if (out.numSlabs > ALVRL_OCC_MAX_SLABS || out.numPlanes > ALVRL_OCC_MAX_PLANES || out.numTris > ALVRL_OCC_MAX_TRIS) return out;
     /* instruction estimates per shadow ray: 15 per slab, 13 per plane; flat sweep: 22 per leaf box + ~100 of triangle tests */
     const uint32_t costOcc = 15 * out.numSlabs + 13 * out.numPlanes, costFlat = 22 * numLeaves + 100;
     if (costOcc > costFlat) return out;
-    out.stream.reserve(2 * slabA.size() + 2 * planes.size() + triStream.size());
-    out.stream.insert(out.stream.end(), slabA.begin(), slabA.end());
-    out.stream.insert(out.stream.end(), slabB.begin(), slabB.end());
-    out.stream.insert(out.stream.end(), planes.begin(), planes.end());
-    out.stream.insert(out.stream.end(), planeInfo.begin(), planeInfo.end());
-    out.stream.insert(out.stream.end(), triStream.begin(), triStream.end());
+    memset(&out.dev, 0, sizeof(out.dev));
+    uint32_t k = 0;
+    for (const Solid &so : solids)
+        for (size_t i = 0; i < so.a.size(); i++, k++) {
+            out.dev.slabA[k] = so.a[i];
+            out.dev.slabB[k] = make_float2(so.chi[i], 0.0f);
+            if (i + 1 == so.a.size()) { const uint32_t one = 1u; memcpy(&out.dev.slabB[k].y, &one, 4); }
+        }
+    for (size_t i = 0; i < planes.size(); i++) { out.dev.planes[i] = planes[i]; out.dev.planeInfo[i] = planeInfo[i]; }
+    out.dev.numBoxes = out.numBoxes; out.dev.numSlabs = out.numSlabs; out.dev.numPlanes = out.numPlanes; out.dev.numTris = out.numTris;
+    out.tris = triStream;
     out.use = true;
     return out;
 }

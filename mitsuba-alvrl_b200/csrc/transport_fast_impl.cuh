@@ -18,16 +18,11 @@
 #define ALVRL_SMALL_LEAVES 32
 #define ALVRL_SMALL_TRIS 128
 
-#define ALVRL_OCC_SLABS 32
-#define ALVRL_OCC_PLANES 32
-
-/* small scenes: VIS 1 = all leaf boxes + triangle records in shared memory, VIS 2 = the compiled occluder set
- * (occluders.h): slabs of the convex solids, planes of the planar groups, the groups' triangle records */
+/* small scenes: VIS 1 = all leaf boxes + triangle records in shared memory; VIS 2 = the compiled occluder set
+ * (occluders.h): slabs and planes come from the kernel parameters, shared memory only holds the planar groups' triangles */
 struct BvhSmem {
-    float4 leaves[2 * ALVRL_SMALL_LEAVES];     /* VIS 2: slabA[32] (n, c_lo) | planes[32] (n, c) */
+    float4 leaves[2 * ALVRL_SMALL_LEAVES];
     float4 tris[3 * ALVRL_SMALL_TRIS];
-    float2 slabB[ALVRL_OCC_SLABS];             /* c_hi, last-slab-of-its-solid flag */
-    uint32_t planeInfo[ALVRL_OCC_PLANES];      /* first << 8 | count into tris */
 };
 
 template <int VIS>
@@ -38,23 +33,8 @@ __device__ __forceinline__ void stage_bvh(BvhSmem &sb, const SceneDev &sc) {
         for (uint32_t i = threadIdx.x; i < 2 * sc.numLeaves; i += blockDim.x) sb.leaves[i] = __ldg(&gn[i]);
         for (uint32_t i = threadIdx.x; i < 3 * sc.numTris; i += blockDim.x) sb.tris[i] = __ldg(&gt[i]);
     } else if (VIS == 2) {
-        const float4 *g = sc.occ;
-        const uint32_t ns = sc.numSlabs, np = sc.numPlanes;
-        for (uint32_t i = threadIdx.x; i < ns; i += blockDim.x) {
-            sb.leaves[i] = __ldg(&g[i]);
-            const float4 b = __ldg(&g[ns + i]);
-            sb.slabB[i] = make_float2(b.x, b.y);
-        }
-        for (uint32_t i = threadIdx.x; i < np; i += blockDim.x) {
-            sb.leaves[ALVRL_OCC_SLABS + i] = __ldg(&g[2 * ns + i]);
-            sb.planeInfo[i] = __float_as_uint(__ldg(&g[2 * ns + np + i]).x);
-        }
-        for (uint32_t i = threadIdx.x; i < 3 * sc.numOccTris; i += blockDim.x) sb.tris[i] = __ldg(&g[2 * ns + 2 * np + i]);
+        for (uint32_t i = threadIdx.x; i < 3 * sc.numOccTris; i += blockDim.x) sb.tris[i] = __ldg(&sc.occTris[i]);
     }
-}
-
-__device__ __forceinline__ bool occluded_occ(const BvhSmem &sb, uint32_t numSlabs, uint32_t numPlanes, const F3 &o, const F3 &d, float tmin, float tmax, bool need) {
-    return occ_query(sb.leaves, sb.slabB, numSlabs, sb.leaves + ALVRL_OCC_SLABS, sb.planeInfo, numPlanes, sb.tris, o.x, o.y, o.z, d.x, d.y, d.z, tmin, tmax, need);
 }
 
 /*
@@ -103,7 +83,7 @@ template <int SMALL>
 __device__ __forceinline__ bool occluded_fast(const TransportParams &P, const BvhSmem *sb, const F3 &p1, bool onSurf, const F3 &dir, float remaining, bool need) {
     /* adaptive epsilon of the shadow-ray overload, skdtree.cpp:154-157 */
     const float mint = onSurf ? ALVRL_EPSILON * fmaxf(fmaxf(fabsf(p1.x), fabsf(p1.y)), fabsf(p1.z)) : 0.0f;
-    if (SMALL == 2) return occluded_occ(*sb, P.scene.numSlabs, P.scene.numPlanes, p1, dir, mint, remaining, need);
+    if (SMALL == 2) return occ_query(P.occ, sb->tris, p1.x, p1.y, p1.z, dir.x, dir.y, dir.z, mint, remaining, need);
     if (SMALL == 1) return occluded_flat(*sb, P.scene.numLeaves, p1, dir, mint, remaining, need);
     if (!need || !(remaining > mint)) return false;
     return bvh_occluded_fast(P.scene, p1, dir, mint, remaining);

@@ -19,6 +19,7 @@
 #include <stdint.h>
 #include <cuda_runtime.h>
 #include "../../include/alvrl.h"
+#include "occ_query.h"
 
 #define ALVRL_EPSILON 1e-4f          /* include/mitsuba/core/constants.h:32 */
 #define ALVRL_SHADOW_EPSILON 1e-3f   /* constants.h:33 */
@@ -83,7 +84,7 @@ struct SceneDev {
     float kdMin[3], kdMax[3];     /* ShapeKDTree AABB incl. the 1e-3 enlargement (gkdtree.h:1213-1220) */
     int anyHit;
     /* small scenes, fast flavour (occluders.h): visMode 0 = tree traversal, 1 = flat leaf sweep, 2 = compiled occluder set */
-    const float4 *occ; uint32_t numSlabs, numPlanes, numOccTris; int visMode;
+    const float4 *occTris; uint32_t numOccTris; int visMode;
 };
 
 struct TransportParams {
@@ -95,4 +96,5 @@ struct TransportParams {
     float normalization;                   /* (float)(1.0 / particleCount), vrlIntegrator.cpp:805 */
     float invParticleDiv;                  /* particleCount as float (Li /= particleCount, 590) */
     uint32_t rowBase;                      /* global index of the first row handed to k_build_R (slice sharding) */
+    OccDev occ;                            /* compiled occluder set (scene.visMode == 2), read through the constant bank */
 };

@@ -9,23 +9,34 @@ import numpy as np
 import pytest
 
 
+MAX_SLABS, MAX_PLANES = 24, 24        # csrc/occ_query.h
+
+
+class OccDev(C.Structure):            # mirrors struct OccDev (csrc/occ_query.h)
+    _fields_ = [("slabA", C.c_float * (4 * MAX_SLABS)), ("slabB", C.c_float * (2 * MAX_SLABS)),
+                ("planes", C.c_float * (4 * MAX_PLANES)), ("planeInfo", C.c_uint32 * MAX_PLANES),
+                ("numBoxes", C.c_uint32), ("numSlabs", C.c_uint32), ("numPlanes", C.c_uint32), ("numTris", C.c_uint32)]
+
+
 def compile_occ(host_lib, verts, tris, num_leaves=18):
     verts = np.ascontiguousarray(verts, dtype=np.float32)
     tris = np.ascontiguousarray(tris, dtype=np.uint32)
-    counts = np.zeros(5, dtype=np.uint32)
-    stream = np.zeros((4096, 4), dtype=np.float32)
+    counts = np.zeros(6, dtype=np.uint32)
+    dev = OccDev()
+    recs = np.zeros((3 * 128, 4), dtype=np.float32)
     n = host_lib.alvrl_host_compile_occluders(verts.ctypes.data_as(C.c_void_p), tris.ctypes.data_as(C.c_void_p), C.c_uint32(len(tris)),
-                                              C.c_uint32(num_leaves), counts.ctypes.data_as(C.c_void_p), stream.ctypes.data_as(C.c_void_p),
-                                              C.c_uint32(len(stream)))
-    assert n >= 0
-    return counts, stream[:n].copy()
+                                              C.c_uint32(num_leaves), counts.ctypes.data_as(C.c_void_p), C.byref(dev),
+                                              recs.ctypes.data_as(C.c_void_p), C.c_uint32(len(recs)))
+    assert n == C.sizeof(OccDev)
+    return counts, (dev, recs)
 
 
-def query(host_lib, counts, stream, o, d, tmin, tmax):
+def query(host_lib, counts, occ, o, d, tmin, tmax):
+    dev, recs = occ
     o, d = (np.ascontiguousarray(a, dtype=np.float32) for a in (o, d))
     tmin, tmax = (np.ascontiguousarray(a, dtype=np.float32) for a in (tmin, tmax))
     out = np.zeros(len(o), dtype=np.uint8)
-    host_lib.alvrl_host_occ_query(stream.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p),
+    host_lib.alvrl_host_occ_query(C.byref(dev), recs.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p),
                                   d.ctypes.data_as(C.c_void_p), tmin.ctypes.data_as(C.c_void_p), tmax.ctypes.data_as(C.c_void_p),
                                   C.c_uint32(len(o)), out.ctypes.data_as(C.c_void_p))
     return out.astype(bool)
@@ -67,14 +78,16 @@ def random_segments(rng, n, lo=-0.2, hi=1.2):
 
 def test_cornell_compiles_to_two_boxes_and_five_walls(pkg, host_lib):
     scene, _, _ = pkg.scenes.make_config("C1", width=8, height=8, n_vrls=4)
-    counts, stream = compile_occ(host_lib, scene["verts"], scene["tris"])
-    use, slabs, planes, ntris, polys = (int(x) for x in counts)
-    assert (use, slabs, planes, ntris, polys) == (1, 6, 5, 10, 2)
-    assert len(stream) == 2 * slabs + 2 * planes + 3 * ntris
+    counts, (dev, _) = compile_occ(host_lib, scene["verts"], scene["tris"])
+    use, slabs, planes, ntris, polys, boxes = (int(x) for x in counts)
+    assert (use, slabs, planes, ntris, polys, boxes) == (1, 6, 5, 10, 2, 2)
+    assert (dev.numBoxes, dev.numSlabs, dev.numPlanes, dev.numTris) == (2, 6, 5, 10)
     # each box: three slabs with finite lower bounds, unit normals, the last one flagged
-    assert np.isfinite(stream[:slabs, 3]).all()
-    assert np.allclose(np.linalg.norm(stream[:slabs, :3], axis=1), 1, atol=1e-6)
-    assert list(stream[slabs:2 * slabs, 1].view(np.uint32)) == [0, 0, 1, 0, 0, 1]
+    A = np.array(dev.slabA[:4 * slabs]).reshape(slabs, 4)
+    B = np.array(dev.slabB[:2 * slabs], dtype=np.float32).reshape(slabs, 2)
+    assert np.isfinite(A[:, 3]).all() and (A[:, 3] < B[:, 0]).all()
+    assert np.allclose(np.linalg.norm(A[:, :3], axis=1), 1, atol=1e-6)
+    assert list(B[:, 1].view(np.uint32)) == [0, 0, 1, 0, 0, 1]
 
 
 @pytest.mark.parametrize("closed", [False, True])
@@ -134,9 +147,9 @@ def test_general_polytopes_open_and_nonconvex_parts(pkg, host_lib):
     verts = np.concatenate([vt, vl, vq])
     tris = np.concatenate([tt, tl + len(vt), tq + len(vt) + len(vl)])
     counts, stream = compile_occ(host_lib, verts, tris, num_leaves=32)
-    use, slabs, planes, ntris, polys = (int(x) for x in counts)
-    assert use == 1 and polys == 1 and slabs == 4                      # only the tetrahedron is a convex solid
-    assert np.isinf(stream[:slabs, 3]).all()                           # lone half-spaces: c_lo = -inf
+    use, slabs, planes, ntris, polys, boxes = (int(x) for x in counts)
+    assert use == 1 and polys == 1 and slabs == 4 and boxes == 0       # only the tetrahedron is a convex solid
+    assert np.isinf(np.array(stream[0].slabA[:16]).reshape(4, 4)[:, 3]).all()   # lone half-spaces: c_lo = -inf
     assert ntris == len(tl) + len(tq) and planes == 6 + 2 + 1          # 6 side planes + 2 caps + the quad
     rng = np.random.default_rng(11)
     o, d, L = random_segments(rng, 60000, 0.0, 1.0)
@@ -154,7 +167,7 @@ def test_compiler_declines_what_it_cannot_hold(pkg, host_lib):
     verts = np.concatenate([v + i for i in range(40)])
     tris = np.concatenate([t + 4 * i for i in range(40)])
     counts, stream = compile_occ(host_lib, verts, tris)
-    assert counts[0] == 0 and len(stream) == 0
+    assert counts[0] == 0
     # cheaper as a flat sweep: 30 separate triangles in 2 leaves
     rng = np.random.default_rng(3)
     verts = rng.uniform(0, 1, (90, 3)).astype(np.float32)
