@@ -275,6 +275,7 @@ int alvrl_create(int device, const alvrl_params *p, alvrl_handle *out) {
     ALVRL_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->timer.init();
     c->mainSampler.reset(new_stream(c->P));
+    DevPool::get().addHandle(device);
     const char *mm = getenv("ALVRL_MATH");
     c->mathMode = (mm && std::string(mm) == "strict") ? 1 : 0;
     *out = c;
@@ -286,7 +287,9 @@ void alvrl_destroy(alvrl_handle c) {
     cudaSetDevice(c->device);
     c->timer.destroy();
     if (c->stream) cudaStreamDestroy(c->stream);
+    const int dev = c->device;
     delete c;
+    DevPool::get().dropHandle(dev);
 }
 
 int alvrl_get_params(alvrl_handle c, alvrl_params *out) { *out = c->P; return ALVRL_OK; }

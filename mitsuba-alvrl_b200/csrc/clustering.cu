@@ -814,7 +814,6 @@ struct Workspace {
         for (Inst *in : which) {
             uint32_t key = 0, pos = 0;
             if (in->done || in->nr > RF_MAXROWS || in->nr == 0 || !in->smp->counterState(key, pos)) continue;
-            if (in->pq.size() + 2 > RF_HEAP_CAP || in->singletons.size() + 2 > RF_NODE_CAP) continue;
             if (2 * (xFloats + (uint64_t) N * (in->nr + 4)) * sizeof(float) + (dev.size() + 1) * (uint64_t) N * 64 > freeB / 2) continue;   /* the two compacted copies would not fit */
             RfInst r; memset(&r, 0, sizeof(r));
             r.r0 = in->r0; r.nr = in->nr; r.lw = in->lw; r.listOff = in->listOff; r.cwOff = in->cwOff;
@@ -830,33 +829,42 @@ struct Workspace {
             dev.push_back(in); hi.push_back(r);
         }
         if (dev.empty()) return;
-        double p0 = Prof::now();
+        double p0 = Prof::now(), pr0 = p0;
+        auto rlap = [&](const char *what) { if (prof.on) { cudaStreamSynchronize(st); const double n_ = Prof::now(); fprintf(stderr, "[alvrl clustering]   refineDevice %s %.1f ms\n", what, n_ - pr0); pr0 = n_; } };
         int devId = 0, sms = 0;
         ALVRL_CUDA(cudaGetDevice(&devId));
         ALVRL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, devId));
         const uint32_t grid = (uint32_t) std::min<size_t>(dev.size(), (size_t) std::max(1, sms));
         uint64_t keyStride = 2; while (keyStride < N) keyStride <<= 1;
+        /* a queue holds at most N / 2 multi-clusters, a split tree at most N - 1 nodes on top of the initial ones, N singletons */
+        size_t initMax = 0; for (Inst *in : dev) initMax = std::max(initMax, in->pq.size());
+        const uint32_t heapCap = std::max<uint32_t>(RF_HEAP_CAP + 8, N / 2 + (uint32_t) initMax + 8), nodeCap = N + (uint32_t) initMax + 8;
+        DevBuf<HeapEntry> dHeapOv;
         DevBuf<RfInst> dInst; DevBuf<ClusterNode> dInitNodes, dOutNodes, dNodes; DevBuf<uint32_t> dInitSingles, dOutSingles, dSingles, dCursors;
         DevBuf<HeapEntry> dSnap; DevBuf<unsigned long long> dKeysG; DevBuf<double> dWG, dVcol; DevBuf<float2> dPairsG; DevBuf<float> dX, dX2; DevBuf<uint32_t> dSrcPos;
         initNodes.push_back(ClusterNode{0, 0, 0, 0}); initSingles.push_back(0);                  /* never empty */
         dInst.upload(hi, st); dInitNodes.upload(initNodes, st); dInitSingles.upload(initSingles, st);
-        dOutNodes.alloc(dev.size() * (size_t) (2 * RF_HEAP_CAP)); dOutSingles.alloc(dev.size() * (size_t) RF_NODE_CAP);
-        dNodes.alloc((size_t) grid * RF_NODE_CAP); dSingles.alloc((size_t) grid * RF_NODE_CAP); dSnap.alloc((size_t) grid * RF_HEAP_CAP);
+        dOutNodes.alloc(dev.size() * (size_t) (2 * heapCap)); dOutSingles.alloc(dev.size() * (size_t) nodeCap);
+        dNodes.alloc((size_t) grid * nodeCap); dSingles.alloc((size_t) grid * nodeCap); dSnap.alloc((size_t) grid * heapCap);
+        dHeapOv.alloc((size_t) grid * (heapCap - RF_HEAP_CAP));
         dKeysG.alloc((size_t) grid * keyStride); dWG.alloc((size_t) grid * 3 * N); dPairsG.alloc((size_t) grid * 2 * N);
         dCursors.alloc(4);
         dX.alloc(xFloats); dX2.alloc(xFloats); dVcol.alloc(dev.size() * (size_t) N); dSrcPos.alloc((size_t) grid * 2 * N);
+        rlap("alloc+upload");
         k_rf_compact<<<dim3((N + 7) / 8, (uint32_t) dev.size()), 256, 0, st>>>(R, ldR, N, dInst.p, dLists.p, dCw.p, dX.p, dVcol.p);
+        rlap("compact");
         ALVRL_CUDA(cudaMemsetAsync(dCursors.p, 0, 4 * sizeof(uint32_t), st));
         RfScratch scr;
         scr.keys = dKeysG.p; scr.w = dWG.p; scr.Wf = dWG.p + (size_t) grid * N; scr.Wr = dWG.p + (size_t) grid * 2 * N; scr.pairs = dPairsG.p;
         scr.keyStride = keyStride; scr.stepStride = N;
-        scr.snapHeap = dSnap.p; scr.nodes = dNodes.p; scr.singles = dSingles.p;
+        scr.snapHeap = dSnap.p; scr.nodes = dNodes.p; scr.singles = dSingles.p; scr.heapOv = dHeapOv.p; scr.heapCap = heapCap; scr.nodeCap = nodeCap;
         scr.srcPos = dSrcPos.p; scr.posTmp = dSrcPos.p + (size_t) grid * N;
         scr.initNodes = dInitNodes.p; scr.initSingles = dInitSingles.p; scr.outNodes = dOutNodes.p; scr.outSingles = dOutSingles.p; scr.cursors = dCursors.p;
         ALVRL_CUDA(cudaFuncSetAttribute(k_refine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(RfShared)));
         k_refine<<<grid, RF_THREADS, sizeof(RfShared), st>>>(dX.p, dX2.p, dVcol.p, dInst.p, (uint32_t) dev.size(), dLists.p, dCw.p, scr);
         launches(2);
         ALVRL_CUDA(cudaGetLastError());
+        rlap("k_refine");
         dInst.download(hi.data(), hi.size(), st);
         uint32_t cursors[4];
         dCursors.download(cursors, 4, st);
@@ -892,6 +900,7 @@ struct Workspace {
             if (r.status == RF_DONE) { if (in.adaptive) in.restore(); in.done = true; }
             else resumed++;
         }
+        rlap("readback");
         prof.tasks += splits;
         if (prof.on) fprintf(stderr, "[alvrl clustering] device refinement: %zu objects on %u CTAs, %llu splits (%llu random directions, %llu handed back) in %.1f ms\n",
                              dev.size(), grid, (unsigned long long) splits, (unsigned long long) degenerate, (unsigned long long) resumed, Prof::now() - p0);
@@ -1196,11 +1205,13 @@ void build_clusters_device(alvrl_ctx *c, bool needFallback) {
         g.pixelUndersampling = c->globalPixelUndersampling; g.smp = globalSmp; g.group = -1;
     };
 
+    const double tb0 = Prof::now();
     if (!lazyFallbackCall) {
         /* cluster(), 838-898: zero / non-zero columns over all rows */
         std::vector<uint8_t> nz;
         if (c->columnFlagsOverride.size() == N) nz = c->columnFlagsOverride;
         else column_nonzero_device(c, nz);
+        if (ws.prof.on) fprintf(stderr, "[alvrl clustering] column_nonzero %.1f ms\n", Prof::now() - tb0);
         std::vector<uint32_t> nonZero, zero;
         for (uint32_t i = 0; i < N; i++) (nz[i] ? nonZero : zero).push_back(i);
         c->globalVrlsPerCluster.clear();
@@ -1295,12 +1306,15 @@ void build_clusters_device(alvrl_ctx *c, bool needFallback) {
                 try {
                     ALVRL_CUDA(cudaSetDevice(c->device));
                     ALVRL_CUDA(cudaStreamCreateWithFlags(&w2.st, cudaStreamNonBlocking));
-                    w2.allocInstances();
-                    w2.columnWeights();
-                    w2.construct(c->globalVrlsPerCluster);
+                    double q0 = Prof::now(), q1;
+                    auto lap = [&](const char *what) { if (w2.prof.on) { cudaStreamSynchronize(w2.st); q1 = Prof::now(); fprintf(stderr, "[alvrl clustering] group %zu %s %.1f ms\n", gI, what, q1 - q0); q0 = q1; } };
+                    w2.allocInstances(); lap("allocInstances");
+                    w2.columnWeights(); lap("columnWeights");
+                    w2.construct(c->globalVrlsPerCluster); lap("construct");
                     if (c->P.localRefinement) w2.refine(w2.insts, c->P.localUndersampling);
+                    lap("refine");
                     for (Inst *in : w2.insts) if (!in->failed) in->sampleRepresentatives(c->selectedVrls[in->id], c->clusterWeight[in->id]);
-                    cudaStreamSynchronize(w2.st);
+                    cudaStreamSynchronize(w2.st); lap("sampleRepresentatives");
                 } catch (const std::exception &e) { errors[gI] = e.what(); }
                 if (w2.st) { cudaStreamDestroy(w2.st); w2.st = nullptr; }
             });
@@ -1309,7 +1323,9 @@ void build_clusters_device(alvrl_ctx *c, bool needFallback) {
                 c->stats.kernelLaunches += groups[gI]->launchCount;
                 if (!errors[gI].empty()) throw Error(ALVRL_ERR_ARG, errors[gI]);
             }
+            const double tf0 = Prof::now();
             groups.clear();          /* frees the group workspaces before the fallback, if any */
+            if (ws.prof.on) fprintf(stderr, "[alvrl clustering] free workspaces %.1f ms, build_clusters so far %.1f ms\n", Prof::now() - tf0, Prof::now() - tb0);
         }
         bool anyFailed = false;
         for (Inst *in : ws.insts) { anyFailed |= in->failed; c->nearTieSplits += in->nearTies; }

@@ -7,6 +7,8 @@
 #include <vector>
 #include <memory>
 #include <stdexcept>
+#include <map>
+#include <mutex>
 #include <cuda_runtime.h>
 #include "types.h"
 #include "bvh.h"
@@ -27,18 +29,68 @@ struct Error : std::runtime_error {
             throw alvrl::Error(ALVRL_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));       \
     } while (0)
 
+/* Device-memory pool behind DevBuf.  A frame allocates and frees the same multi-gigabyte workspaces (the compacted slice
+ * matrices of the cluster refinement, per-round scratch) every time, and cudaMalloc / cudaFree of such blocks cost tens to
+ * hundreds of milliseconds each: released blocks are kept and handed out again (best fit, at most twice the request).
+ * put() synchronises the device like cudaFree does, so a recycled block is never still in use.  trim() returns everything
+ * to the driver (called when the last handle of a device is destroyed, or when an allocation fails). */
+class DevPool {
+public:
+    static DevPool &get() { static DevPool pool; return pool; }
+    void *take(size_t bytes, size_t &cap) {
+        int dev = 0; cudaGetDevice(&dev);
+        bytes = (bytes + 511) & ~(size_t) 511;
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            auto &fl = free_[dev];
+            auto it = fl.lower_bound(bytes);
+            if (it != fl.end() && it->first <= 2 * bytes + (1u << 20)) { void *p = it->second; cap = it->first; fl.erase(it); return p; }
+        }
+        void *p = nullptr;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            trim(dev);
+            cudaError_t e = cudaMalloc(&p, bytes);
+            if (e != cudaSuccess) throw Error(ALVRL_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+        }
+        cap = bytes;
+        return p;
+    }
+    void put(void *p, size_t cap) {
+        int dev = 0; cudaGetDevice(&dev);
+        cudaDeviceSynchronize();
+        std::lock_guard<std::mutex> lk(m_);
+        free_[dev].emplace(cap, p);
+    }
+    void trim(int dev) {
+        std::lock_guard<std::mutex> lk(m_);
+        for (auto &kv : free_[dev]) cudaFree(kv.second);
+        free_[dev].clear();
+    }
+    void addHandle(int dev) { std::lock_guard<std::mutex> lk(m_); handles_[dev]++; }
+    void dropHandle(int dev) {
+        bool last;
+        { std::lock_guard<std::mutex> lk(m_); last = --handles_[dev] <= 0; }
+        if (last) trim(dev);
+    }
+private:
+    std::mutex m_;
+    std::map<int, std::multimap<size_t, void *>> free_;
+    std::map<int, int> handles_;
+};
+
 /* owning device buffer */
 template <typename T> struct DevBuf {
-    T *p = nullptr; size_t n = 0;
+    T *p = nullptr; size_t n = 0; size_t capBytes = 0;
     DevBuf() {}
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
     ~DevBuf() { release(); }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release() { if (p) DevPool::get().put(p, capBytes); p = nullptr; n = 0; capBytes = 0; }
     void alloc(size_t count) {                     /* n is a capacity: buffers only grow */
         if (count <= n && p) return;
         release();
-        if (count) ALVRL_CUDA(cudaMalloc((void **) &p, count * sizeof(T)));
+        if (count) p = static_cast<T *>(DevPool::get().take(count * sizeof(T), capBytes));
         n = count;
     }
     void upload(const T *src, size_t count, cudaStream_t st) {

@@ -19,8 +19,9 @@ namespace alvrl {
 
 struct HeapEntry { float key; uint32_t id; };      /* key = undersamplingVar + integrationVar (ClusterNode::operator<, 289-298) */
 
-/* std::push_heap(first, first + count + 1) with the new element `v` at the back */
-ALVRL_HEAP_HD void heap_push(HeapEntry *h, uint32_t &count, HeapEntry v) {
+/* std::push_heap(first, first + count + 1) with the new element `v` at the back; H: HeapEntry * or any indexable view */
+template <typename H>
+ALVRL_HEAP_HD void heap_push(H h, uint32_t &count, HeapEntry v) {
     uint32_t hole = count++;
     while (hole > 0) {
         const uint32_t parent = (hole - 1) >> 1;
@@ -31,7 +32,8 @@ ALVRL_HEAP_HD void heap_push(HeapEntry *h, uint32_t &count, HeapEntry v) {
 }
 
 /* std::pop_heap(first, first + count); back(); pop_back() */
-ALVRL_HEAP_HD HeapEntry heap_pop(HeapEntry *h, uint32_t &count) {
+template <typename H>
+ALVRL_HEAP_HD HeapEntry heap_pop(H h, uint32_t &count) {
     const HeapEntry top = h[0];
     if (count > 1) {
         const uint32_t len = count - 1;
@@ -56,5 +58,11 @@ ALVRL_HEAP_HD HeapEntry heap_pop(HeapEntry *h, uint32_t &count) {
     count--;
     return top;
 }
+
+/* a queue whose first `cap` entries live in one array (shared memory) and the rest in another (global memory) */
+struct SplitHeap {
+    HeapEntry *lo, *hi; uint32_t cap;
+    ALVRL_HEAP_HD HeapEntry &operator[](uint32_t i) const { return i < cap ? lo[i] : hi[i - cap]; }
+};
 
 } // namespace alvrl

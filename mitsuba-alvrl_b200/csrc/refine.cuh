@@ -33,8 +33,7 @@ namespace alvrl {
 #define RF_WARPS (RF_THREADS / 32)
 #define RF_MAXROWS 512
 #define RF_TILE_FLOATS 24576
-#define RF_HEAP_CAP 4096
-#define RF_NODE_CAP (4 * RF_HEAP_CAP)
+#define RF_HEAP_CAP 4096           /* queue entries kept in shared memory; deeper levels spill to global memory (SplitHeap) */
 #define RF_SMALL 1024
 #define RF_CHUNK 1024
 #define RF_MAXCHUNKS 1024
@@ -64,9 +63,11 @@ struct RfInst {
 struct RfScratch {                      /* per CTA */
     unsigned long long *keys; double *w, *Wf, *Wr; float2 *pairs; uint64_t keyStride, stepStride;   /* clusters too large for shared memory */
     uint32_t *srcPos, *posTmp;          /* [stepStride] source position of every sorted step / position of every VRL id (large clusters) */
-    HeapEntry *snapHeap;                /* [RF_HEAP_CAP] best-so-far snapshot of the queue */
-    ClusterNode *nodes;                 /* [RF_NODE_CAP] append-only node table the queue entries index */
-    uint32_t *singles;                  /* [RF_NODE_CAP] singleton VRL ids in insertion order */
+    uint32_t heapCap, nodeCap;          /* capacities per CTA: queue entries (>= RF_HEAP_CAP), nodes / singletons */
+    HeapEntry *heapOv;                  /* [heapCap - RF_HEAP_CAP] queue entries beyond the shared-memory part */
+    HeapEntry *snapHeap;                /* [heapCap] best-so-far snapshot of the queue */
+    ClusterNode *nodes;                 /* [nodeCap] append-only node table the queue entries index */
+    uint32_t *singles;                  /* [nodeCap] singleton VRL ids in insertion order */
     const ClusterNode *initNodes; const uint32_t *initSingles; ClusterNode *outNodes; uint32_t *outSingles;
     uint32_t *cursors;                  /* [0] next object, [1] output node cursor, [2] output singleton cursor */
 };
@@ -217,9 +218,10 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_refine(float *XA, float *XB, 
     double *wG = scr.w + (uint64_t) blockIdx.x * scr.stepStride, *WfG = scr.Wf + (uint64_t) blockIdx.x * scr.stepStride,
            *WrG = scr.Wr + (uint64_t) blockIdx.x * scr.stepStride;
     float2 *pairsG = scr.pairs + (uint64_t) blockIdx.x * 2 * scr.stepStride;
-    HeapEntry *snapHeap = scr.snapHeap + (uint64_t) blockIdx.x * RF_HEAP_CAP;
-    ClusterNode *nodes = scr.nodes + (uint64_t) blockIdx.x * RF_NODE_CAP;
-    uint32_t *singles = scr.singles + (uint64_t) blockIdx.x * RF_NODE_CAP;
+    HeapEntry *snapHeap = scr.snapHeap + (uint64_t) blockIdx.x * scr.heapCap;
+    ClusterNode *nodes = scr.nodes + (uint64_t) blockIdx.x * scr.nodeCap;
+    uint32_t *singles = scr.singles + (uint64_t) blockIdx.x * scr.nodeCap;
+    SplitHeap heap; heap.lo = sm.heap; heap.hi = scr.heapOv + (uint64_t) blockIdx.x * (scr.heapCap - RF_HEAP_CAP); heap.cap = RF_HEAP_CAP;
     uint32_t *srcG = scr.srcPos + (uint64_t) blockIdx.x * scr.stepStride, *posTmp = scr.posTmp + (uint64_t) blockIdx.x * scr.stepStride;
     uint32_t scanIt = 0;
     uint32_t ringPhase = 0;                             /* parity of the two ring barriers of this thread's half */
@@ -249,7 +251,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_refine(float *XA, float *XB, 
         for (uint32_t i = tid; i < I->heapCount; i += RF_THREADS) {
             const ClusterNode cn = scr.initNodes[I->initNodeOff + i];
             HeapEntry e; e.key = cn.undersamplingVar + cn.integrationVar; e.id = i;
-            nodes[i] = cn; sm.heap[i] = e; snapHeap[i] = e;
+            nodes[i] = cn; heap[i] = e; snapHeap[i] = e;
         }
         for (uint32_t i = tid; i < I->singleCount; i += RF_THREADS) singles[i] = scr.initSingles[I->initSingleOff + i];
         if (tid == 0) {
@@ -264,9 +266,9 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_refine(float *XA, float *XB, 
         for (;;) {                                                  /* one Clustering::split per iteration */
             if (tid == 0) {
                 sm.done = 0; sm.snap = 0;
-                if (sm.heapCount + 2 > RF_HEAP_CAP || sm.nodeCount + 2 > RF_NODE_CAP || sm.singleCount + 2 > RF_NODE_CAP) { sm.err = RF_RESUME_HOST; sm.done = 1; }
+                if (sm.heapCount + 2 > scr.heapCap || sm.nodeCount + 2 > scr.nodeCap || sm.singleCount + 2 > scr.nodeCap) { sm.err = RF_RESUME_HOST; sm.done = 1; }
                 else {
-                    const HeapEntry top = heap_pop(sm.heap, sm.heapCount);                  /* popMulti, 581-587 */
+                    const HeapEntry top = heap_pop(heap, sm.heapCount);                  /* popMulti, 581-587 */
                     const ClusterNode cn = nodes[top.id];
                     sm.underVar -= cn.undersamplingVar; sm.intVar -= cn.integrationVar;
                     sm.begin = cn.begin & 0x7fffffffu; sm.end = cn.end; sm.srcBuf = cn.begin >> 31;   /* bit 31: which copy holds the columns */
@@ -707,7 +709,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_refine(float *XA, float *XB, 
                             ClusterNode cn; cn.undersamplingVar = pv.x; cn.integrationVar = pv.y; cn.begin = b | ((srcBuf ^ 1u) << 31); cn.end = e;
                             nodes[sm.nodeCount] = cn;
                             HeapEntry he; he.key = pv.x + pv.y; he.id = sm.nodeCount++;
-                            heap_push(sm.heap, sm.heapCount, he);
+                            heap_push(heap, sm.heapCount, he);
                             sm.underVar += pv.x; sm.intVar += pv.y;
                         }
                     }
@@ -729,7 +731,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_refine(float *XA, float *XB, 
             RF_TICK(8);
             const bool doSnap = sm.snap != 0, isDone = sm.done != 0;
             if (doSnap) {
-                for (uint32_t i = tid; i < sm.heapCount; i += RF_THREADS) snapHeap[i] = sm.heap[i];
+                for (uint32_t i = tid; i < sm.heapCount; i += RF_THREADS) snapHeap[i] = heap[i];
                 if (tid == 0) { sm.sHeapCount = sm.heapCount; sm.sSingleCount = sm.singleCount; sm.sUnder = sm.underVar; sm.sInt = sm.intVar; }
             }
             __syncthreads();
@@ -741,7 +743,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_refine(float *XA, float *XB, 
             sm.end = atomicAdd(scr.cursors + 2, sm.singleCount);
         }
         __syncthreads();
-        for (uint32_t i = tid; i < sm.heapCount; i += RF_THREADS) { ClusterNode cn = nodes[sm.heap[i].id]; cn.begin &= 0x7fffffffu; scr.outNodes[sm.begin + i] = cn; }
+        for (uint32_t i = tid; i < sm.heapCount; i += RF_THREADS) { ClusterNode cn = nodes[heap[i].id]; cn.begin &= 0x7fffffffu; scr.outNodes[sm.begin + i] = cn; }
         for (uint32_t i = tid; i < sm.sHeapCount; i += RF_THREADS) { ClusterNode cn = nodes[snapHeap[i].id]; cn.begin &= 0x7fffffffu; scr.outNodes[sm.begin + sm.heapCount + i] = cn; }
         for (uint32_t i = tid; i < sm.singleCount; i += RF_THREADS) scr.outSingles[sm.end + i] = singles[i];
         if (tid == 0) {
