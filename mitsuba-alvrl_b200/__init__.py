@@ -9,7 +9,7 @@ import os
 from . import binding, scenes  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libalvrl.so")
+LIB_PATH = os.environ.get("ALVRL_LIB", os.path.join(_HERE, "libalvrl.so"))   # ALVRL_LIB: kernel-variant experiments (tools/build_variant.sh)
 _api = None
 
 

@@ -26,7 +26,23 @@
 #error "define ALVRL_FLAVOR (strict|fast) before including transport.cuh"
 #endif
 
+/* VRL records per TMA tile and resident CTAs per SM the kernels are compiled for.  Fast flavour: 8 CTAs (32 warps) per
+ * SM at 64 registers, 23 KB of shared memory each -- measured best of {5, 6, 7, 8, 10, 12} x {64, 128, 256} on the C2
+ * R build (profiles/README.md); the strict flavour keeps its registers. */
+#ifndef ALVRL_TILE_VRLS
+#ifdef ALVRL_FAST
+#define ALVRL_TILE_VRLS 128
+#else
 #define ALVRL_TILE_VRLS 256
+#endif
+#endif
+#ifndef ALVRL_MIN_CTAS
+#ifdef ALVRL_FAST
+#define ALVRL_MIN_CTAS 8
+#else
+#define ALVRL_MIN_CTAS 1
+#endif
+#endif
 #define ALVRL_CTA_SEGS 128
 
 /* ---- flavoured math ---------------------------------------------------------------------------- */
@@ -389,7 +405,7 @@ struct TileSmem {
  * grid.x = row blocks of 128, grid.y = VRL chunks of vrlsPerCta (multiple of the tile size).
  */
 template <int MED, int SMALL>
-__global__ void __launch_bounds__(ALVRL_CTA_SEGS) ALVRL_NAME(k_build_R)(TransportParams P, const SegRec *__restrict__ rowSegs, uint32_t numRows,
+__global__ void __launch_bounds__(ALVRL_CTA_SEGS, ALVRL_MIN_CTAS) ALVRL_NAME(k_build_R)(TransportParams P, const SegRec *__restrict__ rowSegs, uint32_t numRows,
                                                                        const VrlRec *__restrict__ vrls, float2 *__restrict__ R, uint32_t ldR,
                                                                        uint32_t vrlsPerCta) {
 #ifdef ALVRL_FAST
@@ -479,7 +495,7 @@ __global__ void __launch_bounds__(ALVRL_CTA_SEGS) ALVRL_NAME(k_build_R)(Transpor
  * weight in e.w) stream through the same TMA tile pipeline.  work[cta] = {slice, firstPixel, pixelCount, 0}.
  */
 template <int MED, bool CLUSTERED, int SMALL>
-__global__ void __launch_bounds__(ALVRL_CTA_SEGS) ALVRL_NAME(k_render)(TransportParams P, const SegRec *__restrict__ pixSegs,
+__global__ void __launch_bounds__(ALVRL_CTA_SEGS, ALVRL_MIN_CTAS) ALVRL_NAME(k_render)(TransportParams P, const SegRec *__restrict__ pixSegs,
                                                                       const uint32_t *__restrict__ slicePixels, const uint4 *__restrict__ work,
                                                                       const VrlRec *__restrict__ repRecs, const uint32_t *__restrict__ repOffset,
                                                                       float4 *__restrict__ fb, uint32_t W, uint32_t H) {

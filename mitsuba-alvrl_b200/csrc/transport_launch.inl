@@ -1,4 +1,6 @@
 /* transport_launch.inl -- launchers shared by the two flavours (included after transport.cuh). */
+#include <cstdlib>
+#include <algorithm>
 namespace alvrl {
 
 #ifdef ALVRL_FAST
@@ -15,8 +17,12 @@ void ALVRL_NAME(launch_build_R)(const TransportParams &P, const SegRec *rowSegs,
                                 uint32_t ldR, cudaStream_t st) {
     if (numRows == 0 || P.numVrls == 0) return;
     const uint32_t rowBlocks = (numRows + ALVRL_CTA_SEGS - 1) / ALVRL_CTA_SEGS;
-    /* aim at >= 16 CTAs per SM (148 SMs) so that the tail is short, VRL chunks being multiples of the tile */
-    const uint32_t target = 148u * 16u;
+    /* CTAs run for milliseconds and ~5 fit on an SM: with a few thousand of them the last, partly filled wave costs up to
+     * a fifth of the kernel (2 480 CTAs = 3.35 waves at C2).  Aim at ~128 CTAs per SM (148 SMs), i.e. >= 20 waves, VRL chunks
+     * being multiples of the tile (ALVRL_R_CTAS_PER_SM overrides, for experiments) */
+    uint32_t perSm = 128u;
+    if (const char *e = getenv("ALVRL_R_CTAS_PER_SM")) perSm = (uint32_t) std::max(1, atoi(e));
+    const uint32_t target = 148u * perSm;
     uint32_t chunks = (target + rowBlocks - 1) / rowBlocks;
     const uint32_t maxChunks = (P.numVrls + ALVRL_TILE_VRLS - 1) / ALVRL_TILE_VRLS;
     if (chunks > maxChunks) chunks = maxChunks;
