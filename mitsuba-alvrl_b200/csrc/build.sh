@@ -11,14 +11,19 @@ build_one() { # src flags...
   local obj=obj/${src%.cu}.o
   if [ ! -f "$obj" ] || [ -n "$(find . -maxdepth 1 \( -name '*.cu' -o -name '*.cuh' -o -name '*.h' -o -name '*.inl' \) -newer "$obj" -print -quit)" ] \
      || [ ../../include/alvrl.h -nt "$obj" ] || [ ../../include/alvrl_rng.h -nt "$obj" ]; then
+    rm -f "$obj"            # a failed compile must never leave a stale object for the link step
     $NV "$@" -c "$src" -o "$obj" &
+    pids+=($!)
   fi
 }
+pids=()
 build_one primary.cu -fmad=false
 build_one transport_strict.cu -fmad=false
 build_one transport_fast.cu
 build_one clustering.cu -fmad=false
 build_one capi.cu -fmad=false
-wait
+fail=0
+for p in "${pids[@]}"; do wait "$p" || fail=1; done
+if [ $fail -ne 0 ]; then echo "build.sh: compilation failed" >&2; exit 1; fi
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $OUT obj/primary.o obj/transport_strict.o obj/transport_fast.o obj/clustering.o obj/capi.o
 echo "built $OUT"

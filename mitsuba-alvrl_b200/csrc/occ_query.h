@@ -26,10 +26,12 @@ struct OccDev {
     uint32_t numBoxes, numSlabs, numPlanes, numTris;   /* slabs [0, 3 numBoxes) are the boxes */
 };
 
+#ifdef __CUDACC__
+__device__ __forceinline__ float alvrl_occ_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+#endif
 #ifdef __CUDA_ARCH__
 #define ALVRL_OCC_HD __device__ __forceinline__
 #define ALVRL_OCC_RCP(x) alvrl_occ_rcp(x)
-__device__ __forceinline__ float alvrl_occ_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 #define ALVRL_OCC_FFS(m) (__ffs(m) - 1)
 #define ALVRL_OCC_BITS(f) __float_as_uint(f)
 #else

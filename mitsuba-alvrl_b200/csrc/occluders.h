@@ -25,6 +25,7 @@
 #include <cstring>
 #include <algorithm>
 #include <numeric>
+#include <cstdlib>
 #include "types.h"
 #include "bvh.h"
 #include "occ_query.h"

@@ -60,6 +60,7 @@ def brute(verts, tris, o, d, tmin, tmax, margin=0.0):
             w = (d * q).sum(1) * inv
             t = (q @ e2) * inv
         m = margin
+        u, w, t = (np.nan_to_num(a, nan=np.inf, posinf=np.inf, neginf=-np.inf) for a in (u, w, t))
         inside = (u >= 0) & (w >= 0) & (u + w <= 1) & (t >= tmin) & (t <= tmax) & (np.abs(det) > 1e-12)
         near = (u >= -m) & (w >= -m) & (u + w <= 1 + m) & (t >= tmin - m) & (t <= tmax + m)
         far = (u >= m) & (w >= m) & (u + w <= 1 - m) & (t >= tmin + m) & (t <= tmax - m) & (np.abs(det) > 1e-6)
@@ -183,3 +184,39 @@ def test_compiler_declines_what_it_cannot_hold(pkg, host_lib):
     d = np.array([[1, 0, 0], [1, 0, 0], [1, 0, 0]], dtype=np.float32)
     got = query(host_lib, counts, stream, o, d, np.zeros(3, np.float32), np.array([0.3, 5.0, 0.5], np.float32))
     assert list(got) == [False, True, False]
+
+
+def test_mixed_solids_boxes_first_and_axis_parallel_segments(pkg, host_lib):
+    """a tetrahedron, a rotated box and an axis-aligned box (boxes are ordered first), a slanted and an axis-aligned quad"""
+    m = pkg.scenes._Mesh()
+    m.box((0.3, 0.3, 0.7), (0.1, 0.15, 0.1), 30.0, 0)
+    m.box((0.7, 0.2, 0.3), (0.1, 0.2, 0.1), 0.0, 0)
+    m.quad((0.1, 0.8, 0.1), (0.9, 0.9, 0.1), (0.9, 0.9, 0.9), (0.1, 0.8, 0.9), 0)     # slanted
+    m.quad((0.0, 0.0, 1.0), (0.0, 1.0, 1.0), (1.0, 1.0, 1.0), (1.0, 0.0, 1.0), 0)     # z = 1
+    vb, tb, _ = m.arrays()
+    vt, tt = _tetra((0.1, 0.4, 0.1), s=0.25)
+    verts = np.concatenate([vt, vb])
+    tris = np.concatenate([tt, tb + len(vt)])
+    counts, occ = compile_occ(host_lib, verts, tris, num_leaves=32)
+    use, slabs, planes, ntris, polys, boxes = (int(x) for x in counts)
+    assert (use, slabs, planes, ntris, polys, boxes) == (1, 10, 2, 4, 3, 2)
+    dev = occ[0]
+    assert np.isfinite(np.array(dev.slabA[:4 * 6]).reshape(6, 4)[:, 3]).all()          # the two boxes come first
+    assert np.isinf(np.array(dev.slabA[4 * 6:4 * 10]).reshape(4, 4)[:, 3]).all()       # then the tetrahedron's half-spaces
+    rng = np.random.default_rng(21)
+    o, d, L = random_segments(rng, 60000, 0.0, 1.0)
+    tmin = np.zeros_like(L)
+    got = query(host_lib, counts, occ, o, d, tmin, L)
+    want, graze = brute(verts, tris, o, d, tmin, L, margin=1e-4)
+    assert 0.05 < want.mean() < 0.9
+    bad = (got != want) & ~graze
+    assert not bad.any(), int(bad.sum())
+    # axis-parallel segments (a zero direction component: reciprocal = inf) behave
+    o = rng.uniform(0, 1, (20000, 3)).astype(np.float32)
+    d = np.zeros((20000, 3), dtype=np.float32)
+    d[np.arange(20000), rng.integers(0, 3, 20000)] = rng.choice([-1.0, 1.0], 20000)
+    L = rng.uniform(0.05, 1.0, 20000).astype(np.float32)
+    got = query(host_lib, counts, occ, o, d, np.zeros_like(L), L)
+    want, graze = brute(verts, tris, o, d, np.zeros_like(L), L, margin=1e-4)
+    bad = (got != want) & ~graze
+    assert not bad.any(), int(bad.sum())
