@@ -23,6 +23,7 @@
  */
 #include <list>
 #include <thread>
+#include <atomic>
 #include <algorithm>
 #include <numeric>
 #include <cmath>
@@ -101,13 +102,21 @@ __global__ void __launch_bounds__(CL_THREADS) k_unclustered(const float2 *__rest
     const uint32_t *list = lists + t.listOff;
     double mean = 0, M2 = 0, summedVars = 0;
     size_t n = 0;
-    for (uint32_t k = t.begin; k < t.end; k++) {
-        n++;
-        const float2 e = R[(size_t) list[k] * ldR + row];
-        summedVars += (double) e.y;
-        const double x = e.x, delta = x - mean;
-        mean += delta / (double) n;
-        M2 += delta * (x - mean);
+    /* the Welford chain is sequential (reference order); the loads are not: eight columns in flight per thread */
+    for (uint32_t k0 = t.begin; k0 < t.end; k0 += 8) {
+        float2 e[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) e[u] = (k0 + u < t.end) ? R[(size_t) list[k0 + u] * ldR + row] : make_float2(0.0f, 0.0f);
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            if (k0 + u < t.end) {
+                n++;
+                summedVars += (double) e[u].y;
+                const double x = e[u].x, delta = x - mean;
+                mean += delta / (double) n;
+                M2 += delta * (x - mean);
+            }
+        }
     }
     double a = active ? summedVars : 0.0, b = active ? M2 : 0.0;
     block_reduce2(a, b, sh);
@@ -659,7 +668,17 @@ struct Workspace {
         ALVRL_CUDA(cudaMemcpyAsync(dCw.p, all.data(), all.size() * sizeof(float), cudaMemcpyHostToDevice, st));
         ALVRL_CUDA(cudaStreamSynchronize(st));
     }
-    void uploadLists() {
+    /* sameLists: every instance starts from the same list (construct): one upload, replicated on the device */
+    void uploadLists(bool sameLists = false) {
+        if (sameLists && !insts.empty()) {
+            const size_t n = insts[0]->vrls.size();
+            ALVRL_CUDA(cudaMemsetAsync(dLists.p, 0, insts.size() * (size_t) N * sizeof(uint32_t), st));
+            ALVRL_CUDA(cudaMemcpyAsync(dLists.p, insts[0]->vrls.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+            for (size_t i = 1; i < insts.size(); i++)
+                ALVRL_CUDA(cudaMemcpyAsync(dLists.p + i * (size_t) N, dLists.p, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+            ALVRL_CUDA(cudaStreamSynchronize(st));
+            return;
+        }
         std::vector<uint32_t> all(insts.size() * (size_t) N, 0);
         for (size_t i = 0; i < insts.size(); i++) std::copy(insts[i]->vrls.begin(), insts[i]->vrls.end(), all.begin() + i * (size_t) N);
         ALVRL_CUDA(cudaMemcpyAsync(dLists.p, all.data(), all.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
@@ -718,6 +737,8 @@ struct Workspace {
     }
     /* Clustering constructor (301-341) for all instances: initial clusters + unclustered variance */
     void construct(const std::vector<std::vector<uint32_t>> &vrlsPerCluster) {
+        double c0_ = Prof::now();
+        auto clap = [&](const char *what) { if (prof.on) { cudaStreamSynchronize(st); const double n_ = Prof::now(); fprintf(stderr, "[alvrl clustering]   construct %s %.1f ms\n", what, n_ - c0_); c0_ = n_; } };
         uint32_t total = 0;
         for (auto &cl : vrlsPerCluster) total += (uint32_t) cl.size();
         for (Inst *in : insts) {
@@ -727,13 +748,16 @@ struct Workspace {
             if (std::fabs((float) (in->lw * in->nr) - 1) > 1e-3) throw Error(ALVRL_ERR_ARG, "Incorrect normalization in localityWeights");
             if (in->pixelUndersampling <= 0 || in->pixelUndersampling > 1) throw Error(ALVRL_ERR_ARG, "Invalid pixel undersampling");
         }
-        uploadLists();
+        clap("host lists");
+        uploadLists(true);
+        clap("uploadLists");
         std::vector<ClTask> tasks;
         for (Inst *in : insts) {
             uint32_t begin = 0;
             for (auto &cl : vrlsPerCluster) { ClTask t = baseTask(*in); t.begin = begin; t.end = begin + (uint32_t) cl.size(); tasks.push_back(t); begin = t.end; }
         }
         std::vector<float2> res = rangeVariances(tasks);
+        clap("rangeVariances");
         size_t k = 0;
         for (Inst *in : insts) {
             uint32_t begin = 0;
@@ -756,6 +780,7 @@ struct Workspace {
         ALVRL_CUDA(cudaGetLastError());
         std::vector<double2> u(ut.size() * (size_t) maxRb);
         dUncl.download(u.data(), u.size(), st);
+        clap("unclustered");
         for (size_t i = 0; i < insts.size(); i++) {
             double a = 0, b = 0;
             for (uint32_t rb = 0; rb < insts[i]->rowBlocks; rb++) { a += u[i * maxRb + rb].x; b += u[i * maxRb + rb].y; }
@@ -912,7 +937,7 @@ struct Workspace {
                 fprintf(stderr, "[alvrl clustering]   %s splits %llu, Mcycles summed over CTAs: pick %.1f direction %.1f stage %.1f project %.1f sort %.1f weights %.1f sweep %.1f pairs %.1f argmin+queue %.1f\n",
                         k ? "large" : "small", clk[k][9], clk[k][0] * 1e-6, clk[k][1] * 1e-6, clk[k][2] * 1e-6, clk[k][3] * 1e-6, clk[k][4] * 1e-6, clk[k][5] * 1e-6, clk[k][6] * 1e-6,
                         clk[k][7] * 1e-6, clk[k][8] * 1e-6);
-            fprintf(stderr, "[alvrl clustering]   staging detail (thread 0): small issue %.1f wait %.1f | large issue %.1f wait %.1f\n", clk[0][10] * 1e-6, clk[0][11] * 1e-6, clk[1][10] * 1e-6, clk[1][11] * 1e-6);
+            fprintf(stderr, "[alvrl clustering]   columns visited (sum of n over splits, all objects): small %.3e (%.3e not tile-resident) | large %.3e\n", (double) clk[0][10], (double) clk[0][11], (double) clk[1][10]);
             std::sort(perObj.rbegin(), perObj.rend());
             for (size_t k = 0; k < std::min<size_t>(4, perObj.size()); k++) {
                 const RfInst &r = hi[perObj[k].second];
@@ -1313,7 +1338,18 @@ void build_clusters_device(alvrl_ctx *c, bool needFallback) {
                     w2.construct(c->globalVrlsPerCluster); lap("construct");
                     if (c->P.localRefinement) w2.refine(w2.insts, c->P.localUndersampling);
                     lap("refine");
-                    for (Inst *in : w2.insts) if (!in->failed) in->sampleRepresentatives(c->selectedVrls[in->id], c->clusterWeight[in->id]);
+                    {   /* every object draws from its own counter stream: the objects are sampled concurrently */
+                        const unsigned nt = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), 16u));
+                        std::atomic<size_t> next(0);
+                        std::vector<std::thread> pool;
+                        for (unsigned ti = 0; ti < nt; ti++) pool.emplace_back([&]() {
+                            for (size_t k = next++; k < w2.insts.size(); k = next++) {
+                                Inst *in = w2.insts[k];
+                                if (!in->failed) in->sampleRepresentatives(c->selectedVrls[in->id], c->clusterWeight[in->id]);
+                            }
+                        });
+                        for (auto &t : pool) t.join();
+                    }
                     cudaStreamSynchronize(w2.st); lap("sampleRepresentatives");
                 } catch (const std::exception &e) { errors[gI] = e.what(); }
                 if (w2.st) { cudaStreamDestroy(w2.st); w2.st = nullptr; }

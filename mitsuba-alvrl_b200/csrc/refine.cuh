@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_refine(float *XA, float *XB, 
             unsigned long long *keys = small ? sm.keys : keysG;
             double *wA = small ? sm.w : wG, *WfA = small ? sm.Wf : WfG, *WrA = small ? sm.Wr : WrG;
             float2 *pairsF = small ? sm.pairs[0] : pairsG, *pairsR = small ? sm.pairs[1] : pairsG + scr.stepStride;
-            if (tid == 0) { tPhase = clock64(); sm.clk[small ? 0 : 1][9]++; }
+            if (tid == 0) { tPhase = clock64(); sm.clk[small ? 0 : 1][9]++; sm.clk[small ? 0 : 1][10] += n; sm.clk[small ? 0 : 1][11] += (n <= TV) ? 0u : n; }
 
             /* ---- weightedSample x 2 (597-602, 1534-1580) ---- */
             const uint32_t numChunks = (n + RF_CHUNK - 1) / RF_CHUNK;
@@ -563,7 +563,10 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_refine(float *XA, float *XB, 
                 double *Bh = reinterpret_cast<double *>(half ? pairsR : pairsF);       /* B_k lives where pairs[k] goes afterwards */
                 const double *WA = half ? WrA : WfA;
                 double (*part)[32][8] = reinterpret_cast<double (*)[32][8]>(&sm.sw[0][0]) + half * 2;   /* [buffer][step][warp] */
-                const uint32_t KC = min(32u, (uint32_t) (RF_TILE_FLOATS / 4) / nrP);     /* steps per stage (>= 12 for nr <= 512) */
+                /* steps per stage (>= 12 for nr <= 512); the step loop runs in groups of 16, so 17..31 steps would pay a
+                 * second, mostly empty group per stage */
+                uint32_t KC = min(32u, (uint32_t) (RF_TILE_FLOATS / 4) / nrP);
+                if (KC > 16u && KC < 32u) KC = 16u;
                 float *ring = sm.tile + half * (RF_TILE_FLOATS / 2);
                 const uint32_t nch = (n + KC - 1) / KC;
                 auto issue = [&](uint32_t c) {                                          /* the columns of chunk c -> ring stage c & 1 */
@@ -581,10 +584,13 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_refine(float *XA, float *XB, 
                     }
                     rf_cp_commit();
                 };
-                /* thread = rows hr and hr + 256 (nr <= 512) */
-                const uint32_t rA = hr, rB = hr + 256u;
-                const bool actA = rA < nr, actB = rB < nr;
-                const uint32_t nw = (min(256u, nr) + 31) / 32;
+                /* thread = rows hr and hr + RS (nr <= 512): the rows are folded onto the fewest warps, RS = roundup(nr / 2, 32),
+                 * so that both row slots of a thread carry a row -- the sweep is issue-bound, and a warp whose second slot is
+                 * empty costs as many issue slots as a full one */
+                const uint32_t RS = min(256u, (((nr + 1u) >> 1) + 31u) & ~31u);
+                const uint32_t rA = hr, rB = hr + RS;
+                const bool actA = hr < RS && rA < nr, actB = hr < RS && rB < nr;
+                const uint32_t nw = RS >> 5;
                 double SA = 0, SB = 0;
                 uint32_t buf = 0;
                 if (!fits) issue(0);
