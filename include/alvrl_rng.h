@@ -16,7 +16,13 @@
  *                        b = position in the slice's representative list, k as above
  *     ALVRL_RNG_SLICEMAP a = slice, b = 0, k = draw number in sampleRepresentativePixels
  *     ALVRL_RNG_CLUSTER  a = clustering id (slice, or ALVRL_RNG_GLOBAL_ID), b = 0,
- *                        k = draw number inside that Clustering object
+ *                        k = draw number inside that Clustering object (sampleRepresentatives);
+ *                        the draws of Clustering::split (Preprocessor.cpp:590-684) are addressed by the
+ *                        cluster they split: key' = alvrl_rng_node_key(key, begin, end), k = 0, 1 for the
+ *                        two weightedSample draws, k = 2.. for the random direction of degenerate centres.
+ *                        A split is thus a pure function of the cluster's list range and columns, whatever
+ *                        the order in which the refinement visits the clusters -- which is what lets the
+ *                        device split many clusters of one Clustering object concurrently.
  *
  * The float conversion is the reference's own ((x >> 9) | 0x3f800000) - 1.0f
  * (random.cpp:630-639), so u is in [0, 1).  Integer-only => bit-identical on host and device.
@@ -56,6 +62,12 @@ ALVRL_HD uint32_t alvrl_rng_key(uint64_t seed, uint32_t domain, uint32_t a, uint
     h = alvrl_mix32(h + a * 0x85ebca6bu + 0x165667b1u);
     h = alvrl_mix32(h ^ (b * 0xc2b2ae35u + 0x27d4eb2fu));
     return h;
+}
+
+/* sub-stream of one cluster [begin, end) of a Clustering object's VRL list */
+ALVRL_HD uint32_t alvrl_rng_node_key(uint32_t key, uint32_t begin, uint32_t end) {
+    uint32_t h = alvrl_mix32(key ^ (begin * 0x85ebca6bu + 0x2545f491u));
+    return alvrl_mix32(h + end * 0xc2b2ae35u + 0x68e31da4u);
 }
 
 ALVRL_HD uint32_t alvrl_rng_bits(uint32_t key, uint32_t k) {

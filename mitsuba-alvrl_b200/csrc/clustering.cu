@@ -839,7 +839,7 @@ struct Workspace {
         for (Inst *in : which) {
             uint32_t key = 0, pos = 0;
             if (in->done || in->nr > RF_MAXROWS || in->nr == 0 || !in->smp->counterState(key, pos)) continue;
-            if (2 * (xFloats + (uint64_t) N * (in->nr + 4)) * sizeof(float) + (dev.size() + 1) * (uint64_t) N * 64 > freeB / 2) continue;   /* the two compacted copies would not fit */
+            if (2 * (xFloats + (uint64_t) N * (in->nr + 4)) * sizeof(float) + (dev.size() + 1) * (uint64_t) N * 160 > freeB / 2) continue;   /* the two compacted copies would not fit */
             RfInst r; memset(&r, 0, sizeof(r));
             r.r0 = in->r0; r.nr = in->nr; r.lw = in->lw; r.listOff = in->listOff; r.cwOff = in->cwOff;
             r.nrP = (in->nr + 3u) & ~3u; r.xOff = xFloats; r.vOff = (uint64_t) dev.size() * N;
@@ -859,19 +859,24 @@ struct Workspace {
         int devId = 0, sms = 0;
         ALVRL_CUDA(cudaGetDevice(&devId));
         ALVRL_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, devId));
-        const uint32_t grid = (uint32_t) std::min<size_t>(dev.size(), (size_t) std::max(1, sms));
         uint64_t keyStride = 2; while (keyStride < N) keyStride <<= 1;
         /* a queue holds at most N / 2 multi-clusters, a split tree at most N - 1 nodes on top of the initial ones, N singletons */
         size_t initMax = 0; for (Inst *in : dev) initMax = std::max(initMax, in->pq.size());
         const uint32_t heapCap = std::max<uint32_t>(RF_HEAP_CAP + 8, N / 2 + (uint32_t) initMax + 8), nodeCap = N + (uint32_t) initMax + 8;
+        /* many CTAs per object (k_refine_mt) unless asked for the one-CTA-per-object kernel or the task encoding does not fit */
+        const bool mt = !getenv("ALVRL_REFINE_ST") && dev.size() < 0x8000u && nodeCap < 0x1000000u;
+        const uint32_t grid = mt ? (uint32_t) std::max(1, sms) : (uint32_t) std::min<size_t>(dev.size(), (size_t) std::max(1, sms));
+        const size_t pool = mt ? dev.size() : (size_t) grid;                   /* node tables and queues: per object / per CTA */
         DevBuf<HeapEntry> dHeapOv;
         DevBuf<RfInst> dInst; DevBuf<ClusterNode> dInitNodes, dOutNodes, dNodes; DevBuf<uint32_t> dInitSingles, dOutSingles, dSingles, dCursors;
         DevBuf<HeapEntry> dSnap; DevBuf<unsigned long long> dKeysG; DevBuf<double> dWG, dVcol; DevBuf<float2> dPairsG; DevBuf<float> dX, dX2; DevBuf<uint32_t> dSrcPos;
         initNodes.push_back(ClusterNode{0, 0, 0, 0}); initSingles.push_back(0);                  /* never empty */
         dInst.upload(hi, st); dInitNodes.upload(initNodes, st); dInitSingles.upload(initSingles, st);
         dOutNodes.alloc(dev.size() * (size_t) (2 * heapCap)); dOutSingles.alloc(dev.size() * (size_t) nodeCap);
-        dNodes.alloc((size_t) grid * nodeCap); dSingles.alloc((size_t) grid * nodeCap); dSnap.alloc((size_t) grid * heapCap);
-        dHeapOv.alloc((size_t) grid * (heapCap - RF_HEAP_CAP));
+        DevBuf<MtNode> dMtNodes; DevBuf<HeapEntry> dMtHeap; DevBuf<uint32_t> dOutstanding, dLists1, dCtr; DevBuf<unsigned long long> dSlots, dMtClk;
+        if (mt) { dMtNodes.alloc(pool * nodeCap); dMtHeap.alloc(pool * heapCap); dOutstanding.alloc(pool); dLists1.alloc(dLists.n); dCtr.alloc(4); }
+        else { dNodes.alloc((size_t) grid * nodeCap); dHeapOv.alloc((size_t) grid * (heapCap - RF_HEAP_CAP)); }
+        dSingles.alloc(pool * nodeCap); dSnap.alloc(pool * heapCap);
         dKeysG.alloc((size_t) grid * keyStride); dWG.alloc((size_t) grid * 3 * N); dPairsG.alloc((size_t) grid * 2 * N);
         dCursors.alloc(4);
         dX.alloc(xFloats); dX2.alloc(xFloats); dVcol.alloc(dev.size() * (size_t) N); dSrcPos.alloc((size_t) grid * 2 * N);
@@ -885,8 +890,40 @@ struct Workspace {
         scr.snapHeap = dSnap.p; scr.nodes = dNodes.p; scr.singles = dSingles.p; scr.heapOv = dHeapOv.p; scr.heapCap = heapCap; scr.nodeCap = nodeCap;
         scr.srcPos = dSrcPos.p; scr.posTmp = dSrcPos.p + (size_t) grid * N;
         scr.initNodes = dInitNodes.p; scr.initSingles = dInitSingles.p; scr.outNodes = dOutNodes.p; scr.outSingles = dOutSingles.p; scr.cursors = dCursors.p;
-        ALVRL_CUDA(cudaFuncSetAttribute(k_refine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(RfShared)));
-        k_refine<<<grid, RF_THREADS, sizeof(RfShared), st>>>(dX.p, dX2.p, dVcol.p, dInst.p, (uint32_t) dev.size(), dLists.p, dCw.p, scr);
+        if (mt) {
+            /* the ticket ring: at most MT_K split tasks or one control task per object are in flight */
+            uint32_t qcap = 65536; while (qcap < 4 * (MT_K + 1) * dev.size()) qcap <<= 1;
+            dSlots.alloc(qcap); dMtClk.alloc((size_t) grid * 32);
+            ALVRL_CUDA(cudaMemsetAsync(dSlots.p, 0, qcap * sizeof(unsigned long long), st));
+            ALVRL_CUDA(cudaMemsetAsync(dOutstanding.p, 0, pool * sizeof(uint32_t), st));
+            ALVRL_CUDA(cudaMemsetAsync(dMtClk.p, 0, (size_t) grid * 32 * sizeof(unsigned long long), st));
+            std::vector<unsigned long long> first(dev.size());                  /* one control task per object to start with */
+            for (size_t i = 0; i < dev.size(); i++) first[i] = (1ull << 40) | (1ull << 39) | ((unsigned long long) i << 24);
+            dSlots.upload(first, st);
+            const std::vector<uint32_t> ctr = {0u, (uint32_t) dev.size(), (uint32_t) dev.size(), 0u};
+            dCtr.upload(ctr, st);
+            MtPools mp;
+            mp.nodes = dMtNodes.p; mp.heap = dMtHeap.p; mp.snap = dSnap.p; mp.singles = dSingles.p; mp.outstanding = dOutstanding.p;
+            mp.slots = dSlots.p; mp.qmask = qcap - 1; mp.ctr = dCtr.p; mp.nodeCap = nodeCap; mp.heapCap = heapCap; mp.clk = dMtClk.p;
+            ALVRL_CUDA(cudaFuncSetAttribute(k_refine_mt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(RfShared)));
+            k_refine_mt<<<grid, RF_THREADS, sizeof(RfShared), st>>>(dX.p, dX2.p, dVcol.p, dInst.p, (uint32_t) dev.size(), dLists.p, dLists1.p, dCw.p, scr, mp);
+            ALVRL_CUDA(cudaGetLastError());
+            if (prof.on) {
+                std::vector<unsigned long long> ck((size_t) grid * 32);
+                dMtClk.download(ck.data(), ck.size(), st);
+                unsigned long long t[32] = {0};
+                for (size_t i = 0; i < ck.size(); i++) t[i % 32] += ck[i];
+                fprintf(stderr, "[alvrl clustering]   k_refine_mt on %u CTAs: control passes %llu (%.1f Mcycles), split tasks %llu, waiting for tickets %.1f Mcycles\n",
+                        grid, t[26], t[24] * 1e-6, t[27], t[25] * 1e-6);
+                for (int k = 0; k < 2; k++)
+                    fprintf(stderr, "[alvrl clustering]   %s split tasks %llu, Mcycles summed over CTAs: pick %.1f direction %.1f stage %.1f project %.1f sort %.1f weights %.1f sweep %.1f pairs %.1f result %.1f\n",
+                            k ? "large" : "small", t[12 * k + 9], t[12 * k + 0] * 1e-6, t[12 * k + 1] * 1e-6, t[12 * k + 2] * 1e-6, t[12 * k + 3] * 1e-6, t[12 * k + 4] * 1e-6,
+                            t[12 * k + 5] * 1e-6, t[12 * k + 6] * 1e-6, t[12 * k + 7] * 1e-6, t[12 * k + 8] * 1e-6);
+            }
+        } else {
+            ALVRL_CUDA(cudaFuncSetAttribute(k_refine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(RfShared)));
+            k_refine<<<grid, RF_THREADS, sizeof(RfShared), st>>>(dX.p, dX2.p, dVcol.p, dInst.p, (uint32_t) dev.size(), dLists.p, dCw.p, scr);
+        }
         launches(2);
         ALVRL_CUDA(cudaGetLastError());
         rlap("k_refine");
@@ -962,6 +999,7 @@ struct Workspace {
             if (end - begin < 2) throw Error(ALVRL_ERR_ARG, "couldn't split cluster!");
             if (centres) { in.vrl1 = (*centres)[i].first; in.vrl2 = (*centres)[i].second; }
             else {
+                in.smp->enterNode(begin, end);                                      /* counter stream: the cluster's own draws (alvrl_rng.h) */
                 in.vrl1 = in.vrls[weighted_sample(in.cw, in.smp, nullptr, begin, end, in.vrls)];   /* 597-602 */
                 const float weight1 = in.cw[in.vrl1];
                 in.cw[in.vrl1] = 0.0f;
@@ -1063,6 +1101,7 @@ struct Workspace {
             in.addCluster(begin, splitIndex, fromStart[bestIndex - 1].x, fromStart[bestIndex - 1].y);
             in.addCluster(splitIndex, end, fromEnd[n - 1 - bestIndex].x, fromEnd[n - 1 - bestIndex].y);
         }
+        for (Inst *in : round) in->smp->leaveNode();
         p1 = Prof::now(); prof.t[6] += p1 - p0;
     }
     DevBuf<ClTask> dTasks2;
@@ -1087,6 +1126,7 @@ struct Workspace {
             if (end - begin < 2) throw Error(ALVRL_ERR_ARG, "couldn't split cluster!");
             ClTask t = baseTask(in);
             t.begin = begin; t.end = end; t.outOff = out; t.dirOff = dirOff;
+            in.smp->enterNode(begin, end);                                      /* counter stream: the cluster's own draws (alvrl_rng.h) */
             t.u1 = in.smp->next1D(); t.u2 = in.smp->next1D();                   /* the two weightedSample draws, 597-602 */
             segOff[i] = (int) out; segOff[T + i] = (int) (out + (end - begin));
             out += end - begin; dirOff += in.nr;
@@ -1151,6 +1191,7 @@ struct Workspace {
         }
         p1 = Prof::now(); prof.t[6] += p1 - p0;
         if (!hostRound.empty()) splitRound(hostRound, &hostCentres);
+        for (Inst *in : round) in->smp->leaveNode();
     }
     /* bring the host mirrors of the VRL permutations up to date (device rounds reorder them on the device only) */
     void syncLists(const std::vector<Inst *> &which) {

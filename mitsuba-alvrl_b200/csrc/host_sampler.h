@@ -25,6 +25,9 @@ public:
     /* addressed streams expose (key, position) so that device code can continue them (refine.cuh) */
     virtual bool counterState(uint32_t & /*key*/, uint32_t & /*pos*/) const { return false; }
     virtual void setCounterPos(uint32_t /*pos*/) {}
+    /* counter stream: the draws of Clustering::split come from the sub-stream of the cluster [begin, end) (alvrl_rng.h) */
+    virtual void enterNode(uint32_t /*begin*/, uint32_t /*end*/) {}
+    virtual void leaveNode() {}
 };
 
 class Sfmt19937 {
@@ -124,14 +127,16 @@ public:
 };
 
 class CounterStream : public HostSampler {
-    uint64_t seed; uint32_t key = 0, k = 0;
+    uint64_t seed; uint32_t key = 0, k = 0, outerKey = 0, outerK = 0; bool inNode = false;
 public:
     explicit CounterStream(uint64_t s) : seed(s) {}
-    void setContext(uint32_t domain, uint32_t a, uint32_t b) override { key = alvrl_rng_key(seed, domain, a, b); k = 0; }
+    void setContext(uint32_t domain, uint32_t a, uint32_t b) override { key = alvrl_rng_key(seed, domain, a, b); k = 0; inNode = false; }
+    void enterNode(uint32_t begin, uint32_t end) override { leaveNode(); outerKey = key; outerK = k; key = alvrl_rng_node_key(key, begin, end); k = 0; inNode = true; }
+    void leaveNode() override { if (inNode) { key = outerKey; k = outerK; inNode = false; } }
     float next1D() override { return alvrl_rng_uniform(key, k++); }
     HostSampler *clone() override { return new CounterStream(seed); }
-    bool counterState(uint32_t &key_, uint32_t &pos) const override { key_ = key; pos = k; return true; }
-    void setCounterPos(uint32_t pos) override { k = pos; }
+    bool counterState(uint32_t &key_, uint32_t &pos) const override { key_ = inNode ? outerKey : key; pos = inNode ? outerK : k; return true; }
+    void setCounterPos(uint32_t pos) override { if (inNode) outerK = pos; else k = pos; }
 };
 
 } // namespace alvrl

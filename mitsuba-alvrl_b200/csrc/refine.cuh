@@ -58,6 +58,7 @@ struct RfInst {
      * out: the final queue followed by the best-so-far snapshot (nodes in array order) and the singletons, compacted */
     uint32_t initNodeOff, initSingleOff, outNodeOff, outSingleOff;
     unsigned long long clk[2][12];      /* cycles per phase, [small | large cluster]: pick, direction, stage, project, sort, weights, sweep, pairs, argmin+queue, count */
+    uint32_t mtInit, mtWaves;           /* k_refine_mt: the object's queue has been set up / control passes so far */
 };
 
 struct RfScratch {                      /* per CTA */
@@ -86,7 +87,9 @@ struct RfShared {
     uint64_t mbar[2][2];                                /* [half][stage]: completion of the bulk copies of the variance ring */           /* [half][stage][step]: w_k and W_{k-1} of the staged steps (large clusters) */
     float rb[RF_WARPS], rs[RF_WARPS]; uint32_t ri[RF_WARPS];
     /* control block (written by thread 0 between barriers) */
-    uint32_t inst, begin, end, srcBuf, found, pick[2], flags, done, snap, err;
+    uint32_t inst, begin, end, srcBuf, found, pick[2], flags, done, snap, err, nodeKey, nodePos;
+    uint32_t task[2], stop, selCount, sel[32];             /* k_refine_mt: the task in hand, the control pass */
+    unsigned long long mtClk[4];
     float u1, u2, norm[3];
     /* refinement state (thread 0) */
     uint32_t rngPos, heapCount, nodeCount, singleCount, sHeapCount, sSingleCount, nearTies, splits, degenerate;
@@ -273,7 +276,8 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_refine(float *XA, float *XB, 
                     sm.underVar -= cn.undersamplingVar; sm.intVar -= cn.integrationVar;
                     sm.begin = cn.begin & 0x7fffffffu; sm.end = cn.end; sm.srcBuf = cn.begin >> 31;   /* bit 31: which copy holds the columns */
                     if (sm.end - sm.begin < 2) { sm.err = RF_ERR_SPLIT; sm.done = 1; }
-                    sm.u1 = alvrl_rng_uniform(key, sm.rngPos++); sm.u2 = alvrl_rng_uniform(key, sm.rngPos++);   /* 597-602 */
+                    sm.nodeKey = alvrl_rng_node_key(key, sm.begin, sm.end);              /* the cluster's own sub-stream (alvrl_rng.h) */
+                    sm.u1 = alvrl_rng_uniform(sm.nodeKey, 0); sm.u2 = alvrl_rng_uniform(sm.nodeKey, 1); sm.nodePos = 2;   /* 597-602 */
                     sm.flags = 0; sm.found = 0xffffffffu;
                 }
             }
@@ -292,405 +296,8 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_refine(float *XA, float *XB, 
             float2 *pairsF = small ? sm.pairs[0] : pairsG, *pairsR = small ? sm.pairs[1] : pairsG + scr.stepStride;
             if (tid == 0) { tPhase = clock64(); sm.clk[small ? 0 : 1][9]++; sm.clk[small ? 0 : 1][10] += n; sm.clk[small ? 0 : 1][11] += (n <= TV) ? 0u : n; }
 
-            /* ---- weightedSample x 2 (597-602, 1534-1580) ---- */
-            const uint32_t numChunks = (n + RF_CHUNK - 1) / RF_CHUNK;
-            uint32_t idx[2] = {0, 0};
-            {
-                uint32_t cT = 0;                                    /* chunk whose running sums acc[] holds */
-                for (int draw = 0; draw < 2; draw++) {
-                    /* running sums: chunkEnd[c] = sum after chunk c.  Draw 1 resumes in the chunk of the first centre. */
-                    uint32_t cFrom = 0;
-                    if (draw == 1) {
-                        const uint32_t l1 = idx[0] - cT * RF_CHUNK, cnt = min((uint32_t) RF_CHUNK, n - cT * RF_CHUNK);
-                        if (tid == 0) {
-                            float a = l1 ? sm.acc[l1 - 1] : (cT ? sm.chunkEnd[cT - 1] : 0.0f);
-                            a += 0.0f; sm.acc[l1] = a;
-                            for (uint32_t i = l1 + 1; i < cnt; i++) { a += sm.sw[0][i]; sm.acc[i] = a; }
-                            sm.chunkEnd[cT] = a;
-                        }
-                        cFrom = cT + 1;
-                    }
-                    if (draw == 0 && numChunks == 1) {
-                        if (tid < n) sm.sw[0][tid] = icw[list[tid]];
-                        if (tid + RF_THREADS < n) sm.sw[0][tid + RF_THREADS] = icw[list[tid + RF_THREADS]];
-                        __syncthreads();
-                        if (tid == 0) { float a = 0.0f; for (uint32_t i = 0; i < n; i++) { a += sm.sw[0][i]; sm.acc[i] = a; } sm.chunkEnd[0] = a; }
-                    } else if (cFrom < numChunks) {                 /* double-buffered gather / chain over the remaining chunks */
-                        __syncthreads();
-                        for (uint32_t i = tid; i < min((uint32_t) RF_CHUNK, n - cFrom * RF_CHUNK); i += RF_THREADS) sm.sw[1][i] = icw[list[cFrom * RF_CHUNK + i]];
-                        for (uint32_t c = cFrom; c < numChunks; c++) {
-                            const uint32_t b = (c - cFrom + 1) & 1;
-                            __syncthreads();
-                            if (c + 1 < numChunks)
-                                for (uint32_t i = tid; i < min((uint32_t) RF_CHUNK, n - (c + 1) * RF_CHUNK); i += RF_THREADS) sm.sw[b ^ 1][i] = icw[list[(c + 1) * RF_CHUNK + i]];
-                            if (tid == 0) {
-                                float a = c ? sm.chunkEnd[c - 1] : 0.0f;
-                                const uint32_t cnt = min((uint32_t) RF_CHUNK, n - c * RF_CHUNK);
-                                for (uint32_t i = 0; i < cnt; i++) a += sm.sw[b][i];
-                                sm.chunkEnd[c] = a;
-                            }
-                        }
-                    }
-                    __syncthreads();
-                    const float weightSum = sm.chunkEnd[numChunks - 1];
-                    const float alpha = (draw == 0 ? sm.u1 : sm.u2) * weightSum;
-                    if (tid == 0 && !(weightSum > 0)) sm.flags |= 2u;
-                    uint32_t cNew = 0;
-                    if (numChunks > 1) {                            /* first chunk whose end sum reaches alpha */
-                        for (uint32_t c = tid; c < numChunks; c += RF_THREADS) if (sm.chunkEnd[c] >= alpha) atomicMin(&sm.found, c);
-                        __syncthreads();
-                        cNew = sm.found == 0xffffffffu ? 0u : sm.found;
-                        __syncthreads();
-                        if (tid == 0) sm.found = 0xffffffffu;
-                        if (!(draw == 1 && cNew == cT)) {           /* re-chain that chunk, keeping its running sums */
-                            const uint32_t cnt = min((uint32_t) RF_CHUNK, n - cNew * RF_CHUNK);
-                            for (uint32_t i = tid; i < cnt; i += RF_THREADS) sm.sw[0][i] = icw[list[cNew * RF_CHUNK + i]];
-                            __syncthreads();
-                            if (tid == 0) { float a = cNew ? sm.chunkEnd[cNew - 1] : 0.0f; for (uint32_t i = 0; i < cnt; i++) { a += sm.sw[0][i]; sm.acc[i] = a; } }
-                        }
-                        __syncthreads();
-                    }
-                    cT = cNew;
-                    {
-                        const uint32_t cnt = min((uint32_t) RF_CHUNK, n - cT * RF_CHUNK);
-                        for (uint32_t i = tid; i < cnt; i += RF_THREADS) if (sm.acc[i] >= alpha) atomicMin(&sm.found, i);
-                    }
-                    __syncthreads();
-                    if (sm.found == 0xffffffffu) { idx[draw] = 0; if (tid == 0) sm.flags |= 2u; }
-                    else idx[draw] = cT * RF_CHUNK + sm.found;
-                    __syncthreads();
-                    if (tid == 0) sm.found = 0xffffffffu;
-                }
-            }
-            __syncthreads();
-            if (sm.flags & 2u) { if (tid == 0) sm.err = RF_ERR_WEIGHTS; break; }
-            RF_TICK(0);
-
-            /* ---- direction (604-623) ---- */
-            for (uint32_t r = tid; r < nr; r += RF_THREADS) { sm.c1[r] = Xs[(size_t) idx[0] * nrP + r]; sm.c2[r] = Xs[(size_t) idx[1] * nrP + r]; }
-            __syncthreads();
-            if (tid == 0) { float a = 0; for (uint32_t r = 0; r < nr; r++) a += fabsf(sm.c1[r]) * fabsf(sm.c1[r]); sm.norm[0] = sqrtf(a); }
-            else if (tid == 32) { float a = 0; for (uint32_t r = 0; r < nr; r++) a += fabsf(sm.c2[r]) * fabsf(sm.c2[r]); sm.norm[1] = sqrtf(a); }
-            else if (tid == 64) { float a = 0; for (uint32_t r = 0; r < nr; r++) { const float d = sm.c2[r] - sm.c1[r]; a += fabsf(d) * fabsf(d); } sm.norm[2] = sqrtf(a); }
-            __syncthreads();
-            if (sm.norm[0] != 0 && sm.norm[1] != 0 && sm.norm[2] != 0) {
-                const float dl = sm.norm[2];
-                for (uint32_t r = tid; r < nrP; r += RF_THREADS) sm.sdir[r] = r < nr ? (sm.c2[r] - sm.c1[r]) / dl : 0.0f;
-            } else {
-                /* degenerate centres: direction uniform on the n-sphere, warp::squareToStdNormal(next2D()).x per row (616-622);
-                 * log and cos evaluated in double and rounded (pinned transcendental, same on the host path and in the oracle) */
-                for (;;) {
-                    const uint32_t base = sm.rngPos;
-                    for (uint32_t r = tid; r < nr; r += RF_THREADS) {
-                        const float s1 = alvrl_rng_uniform(key, base + 2 * r), s2 = alvrl_rng_uniform(key, base + 2 * r + 1);
-                        const float rr = sqrtf(-2 * (float) log((double) (1 - s1))), phi = (float) (2 * M_PI * s2);
-                        sm.c1[r] = (float) cos((double) phi) * rr;
-                    }
-                    __syncthreads();
-                    if (tid == 0) {
-                        sm.rngPos = base + 2 * nr; sm.degenerate++;
-                        float a = 0; for (uint32_t r = 0; r < nr; r++) a += fabsf(sm.c1[r]) * fabsf(sm.c1[r]);
-                        sm.norm[2] = sqrtf(a);
-                    }
-                    __syncthreads();
-                    if (sm.norm[2] != 0) break;
-                }
-                const float dl = sm.norm[2];
-                for (uint32_t r = tid; r < nrP; r += RF_THREADS) sm.sdir[r] = r < nr ? sm.c1[r] / dl : 0.0f;
-            }
-            __syncthreads();
-
-            RF_TICK(1);
-            /* ---- projections (625-640).  The columns are staged through the tile in chunks with asynchronous 16-byte copies (the
-             *      whole chunk is in flight at once), then thread = column sums sequentially in fp32 in row order out of shared
-             *      memory (the zero padding of columns and direction adds exact zeros).  A local matrix that fits the tile in one
-             *      chunk stays there for the variance sweep. ---- */
-            const bool fits = n <= TV;
-            if (fits) {
-                for (uint32_t i = tid; i < n * nq; i += RF_THREADS) {
-                    const uint32_t c = i / nq, q = i - c * nq;
-                    rf_cp_async16(sm.tile + c * tS + 4 * (q ^ (c & 7u)), Xs + (size_t) c * nrP + 4 * q);
-                }
-                rf_cp_commit(); rf_cp_wait<0>();
-                __syncthreads();
-            }
-            RF_TICK(2);
-            for (uint32_t c = tid; c < n; c += RF_THREADS) {
-                float s = 0, pj = 0;
-                if (fits) {
-                    const float *x = sm.tile + c * tS;
-                    const uint32_t sw = c & 7u;
-#pragma unroll 2
-                    for (uint32_t q = 0; q < nq; q++) {
-                        const float4 e = *reinterpret_cast<const float4 *>(x + 4 * (q ^ sw));
-                        float a;
-                        a = fabsf(e.x); s += a * a; a = fabsf(e.y); s += a * a; a = fabsf(e.z); s += a * a; a = fabsf(e.w); s += a * a;
-                    }
-                    const float len = sqrtf(s);
-                    if (len != 0) {
-#pragma unroll 2
-                        for (uint32_t q = 0; q < nq; q++) {
-                            const float4 e = *reinterpret_cast<const float4 *>(x + 4 * (q ^ sw));
-                            const float4 d = *reinterpret_cast<const float4 *>(sm.sdir + 4 * q);
-                            pj += d.x * (e.x / len); pj += d.y * (e.y / len); pj += d.z * (e.z / len); pj += d.w * (e.w / len);
-                        }
-                    }
-                } else {
-                    /* too large for the tile: every thread streams its own (contiguous) column from L2, eight loads in flight */
-                    const float4 *col4 = reinterpret_cast<const float4 *>(Xs + (size_t) c * nrP);
-                    for (uint32_t q0 = 0; q0 < nq; q0 += 8) {
-                        float4 e[8];
-#pragma unroll
-                        for (int u = 0; u < 8; u++) e[u] = (q0 + u < nq) ? col4[q0 + u] : make_float4(0, 0, 0, 0);
-#pragma unroll
-                        for (int u = 0; u < 8; u++) {
-                            float a;
-                            a = fabsf(e[u].x); s += a * a; a = fabsf(e[u].y); s += a * a; a = fabsf(e[u].z); s += a * a; a = fabsf(e[u].w); s += a * a;
-                        }
-                    }
-                    const float len = sqrtf(s);
-                    if (len != 0) {
-                        for (uint32_t q0 = 0; q0 < nq; q0 += 8) {
-                            float4 e[8];
-#pragma unroll
-                            for (int u = 0; u < 8; u++) e[u] = (q0 + u < nq) ? col4[q0 + u] : make_float4(0, 0, 0, 0);
-#pragma unroll
-                            for (int u = 0; u < 8; u++) {
-                                if (q0 + u < nq) {
-                                    const float4 d = *reinterpret_cast<const float4 *>(sm.sdir + 4 * (q0 + u));
-                                    pj += d.x * (e[u].x / len); pj += d.y * (e[u].y / len); pj += d.z * (e[u].z / len); pj += d.w * (e[u].w / len);
-                                }
-                            }
-                        }
-                    }
-                }
-                const float q = pj + 0.0f;                                      /* -0.0 and +0.0 compare equal in the pair order */
-                uint32_t b = __float_as_uint(q);
-                b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-                const uint32_t vid = list[c];
-                keys[c] = ((unsigned long long) b << 32) | vid;
-                if (small) sm.pos[c] = (uint16_t) c; else posTmp[vid] = c;
-            }
-            /* ---- std::sort of (projection, vrl) pairs (641): bitonic network on the unique keys, always out of shared memory:
-             *      up to RF_SORT_BLOCK keys in one piece (the tile is free when the keys live in global memory), more as
-             *      block-local passes plus global steps for the strides that span blocks ---- */
-            uint32_t m = 2; while (m < n) m <<= 1;
-            for (uint32_t i = n + tid; i < m; i += RF_THREADS) { keys[i] = ~0ull; if (small) sm.pos[i] = 0; }
-            __syncthreads();
-            RF_TICK(3);
-            if (small) {
-                for (uint32_t k = 2; k <= m; k <<= 1) rf_sort_steps(sm.keys, m, 0, k, k >> 1, sm.pos);
-            } else {
-                unsigned long long *sk = reinterpret_cast<unsigned long long *>(sm.tile);
-                const uint32_t blkLen = min(m, (uint32_t) RF_SORT_BLOCK);
-                for (uint32_t blk = 0; blk < m; blk += blkLen) {                /* every block sorted (direction by global index) */
-                    for (uint32_t i = tid; i < blkLen; i += RF_THREADS) sk[i] = keys[blk + i];
-                    __syncthreads();
-                    for (uint32_t k = 2; k <= blkLen; k <<= 1) rf_sort_steps(sk, blkLen, blk, k, k >> 1, nullptr);
-                    for (uint32_t i = tid; i < blkLen; i += RF_THREADS) keys[blk + i] = sk[i];
-                    __syncthreads();
-                }
-                for (uint32_t k = 2 * blkLen; k <= m; k <<= 1) {                /* merges across blocks */
-                    for (uint32_t j = k >> 1; j >= blkLen; j >>= 1) {
-                        for (uint32_t t = tid; t < (m >> 1); t += RF_THREADS) {
-                            const uint32_t lo = ((t & ~(j - 1)) << 1) | (t & (j - 1)), hi = lo | j;
-                            const unsigned long long a = keys[lo], b = keys[hi];
-                            if ((a > b) == ((lo & k) == 0)) { keys[lo] = b; keys[hi] = a; }
-                        }
-                        __syncthreads();
-                    }
-                    for (uint32_t blk = 0; blk < m; blk += blkLen) {
-                        for (uint32_t i = tid; i < blkLen; i += RF_THREADS) sk[i] = keys[blk + i];
-                        __syncthreads();
-                        rf_sort_steps(sk, blkLen, blk, k, blkLen >> 1, nullptr);
-                        for (uint32_t i = tid; i < blkLen; i += RF_THREADS) keys[blk + i] = sk[i];
-                        __syncthreads();
-                    }
-                }
-            }
-            RF_TICK(4);
-            /* ---- sorted list, weights and prefix weights (forward and reverse order) ---- */
-            {
-                double cW[2] = {0, 0};
-                for (uint32_t k0 = 0; k0 < n; k0 += RF_THREADS) {
-                    const uint32_t k = k0 + tid, cnt = min((uint32_t) RF_THREADS, n - k0);
-                    double v[2] = {0, 0}, tot[2];
-                    if (k < n) {
-                        const uint32_t vf = (uint32_t) (keys[k] & 0xffffffffull), vr = (uint32_t) (keys[n - 1 - k] & 0xffffffffull);
-                        list[k] = vf;
-                        if (!small) srcG[k] = posTmp[vf];
-                        v[0] = (double) icw[vf]; v[1] = (double) icw[vr];
-                        wA[k] = v[0];
-                    }
-                    rf_scan<2, false>(v, sm.scan[(scanIt++) & 1], (cnt + 31) / 32, n > RF_THREADS, tot);
-                    if (k < n) { WfA[k] = cW[0] + v[0]; WrA[k] = cW[1] + v[1]; }
-                    cW[0] += tot[0]; cW[1] += tot[1];
-                }
-            }
-            /* the sorted copy: from the tile when the local matrix is resident, else gathered column by column (the variance
-             * sweeps then stream it with bulk copies) */
-            if (fits) {
-                for (uint32_t i = tid; i < n * nq; i += RF_THREADS) {
-                    const uint32_t k = i / nq, q = i - k * nq, pc = sm.pos[k];
-                    *reinterpret_cast<float4 *>(Xd + (size_t) k * nrP + 4 * q) = *reinterpret_cast<const float4 *>(sm.tile + pc * tS + 4 * (q ^ (pc & 7u)));
-                }
-            } else {
-                for (uint32_t k4 = warp * 4; k4 < n; k4 += RF_WARPS * 4) {     /* warp = column, four columns in flight */
-                    const float4 *src[4];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) { const uint32_t k = min(k4 + u, n - 1); src[u] = reinterpret_cast<const float4 *>(Xs + (size_t) (small ? (uint32_t) sm.pos[k] : srcG[k]) * nrP); }
-                    for (uint32_t q = lane; q < nq; q += 32) {
-                        float4 e[4];
-#pragma unroll
-                        for (int u = 0; u < 4; u++) e[u] = src[u][q];
-#pragma unroll
-                        for (int u = 0; u < 4; u++) if (k4 + u < n) reinterpret_cast<float4 *>(Xd + (size_t) (k4 + u) * nrP)[q] = e[u];
-                    }
-                }
-                __threadfence_block();
-                asm volatile("fence.proxy.async;" ::: "memory");
-            }
-            __syncthreads();
-            RF_TICK(5);
-            /* ---- calculateClusterVariance (1058-1120): the forward sweep on threads 0..255 and the reverse sweep on threads
-             *      256..511, thread = row, sequential over the sorted steps (S_r is a running sum, accesses are contiguous across
-             *      rows).  A local matrix that is not resident streams from the sorted copy through a two-stage ring in the tile,
-             *      one bulk copy (TMA) per KC steps, the next chunk in flight while the current one is computed.  The per-step sums
-             *      over rows B_k = sum_r (w_k S_r(k-1) - W_{k-1} x_r(k))^2 are reduced 16 steps at a time by a transposing
-             *      shuffle reduction and across warps through a double-buffered stage ---- */
-            {
-                const uint32_t half = tid >> 8, hr = tid & 255u, hw = hr >> 5;
-                double *Bh = reinterpret_cast<double *>(half ? pairsR : pairsF);       /* B_k lives where pairs[k] goes afterwards */
-                const double *WA = half ? WrA : WfA;
-                double (*part)[32][8] = reinterpret_cast<double (*)[32][8]>(&sm.sw[0][0]) + half * 2;   /* [buffer][step][warp] */
-                /* steps per stage (>= 12 for nr <= 512); the step loop runs in groups of 16, so 17..31 steps would pay a
-                 * second, mostly empty group per stage */
-                uint32_t KC = min(32u, (uint32_t) (RF_TILE_FLOATS / 4) / nrP);
-                if (KC > 16u && KC < 32u) KC = 16u;
-                float *ring = sm.tile + half * (RF_TILE_FLOATS / 2);
-                const uint32_t nch = (n + KC - 1) / KC;
-                auto issue = [&](uint32_t c) {                                          /* the columns of chunk c -> ring stage c & 1 */
-                    const uint32_t k0 = c * KC, cnt = min(KC, n - k0);
-                    if (hr == 0) {
-                        asm volatile("fence.proxy.async;" ::: "memory");
-                        const uint32_t bytes = cnt * nrP * (uint32_t) sizeof(float);
-                        rf_mbar_expect_tx(&sm.mbar[half][c & 1u], bytes);
-                        rf_bulk_load(ring + (c & 1u) * KC * nrP, Xd + (size_t) (half ? n - k0 - cnt : k0) * nrP, bytes, &sm.mbar[half][c & 1u]);
-                    }
-                    if (!small && hr < cnt) {                                           /* w_k, W_{k-1} live in global memory */
-                        const uint32_t k = k0 + hr, sp = half ? n - 1 - k : k;
-                        rf_cp_async8(&sm.stepW[half][c & 1u][hr], wA + sp);
-                        if (k) rf_cp_async8(&sm.stepWp[half][c & 1u][hr], WA + k - 1); else sm.stepWp[half][c & 1u][hr] = 0.0;
-                    }
-                    rf_cp_commit();
-                };
-                /* thread = rows hr and hr + RS (nr <= 512): the rows are folded onto the fewest warps, RS = roundup(nr / 2, 32),
-                 * so that both row slots of a thread carry a row -- the sweep is issue-bound, and a warp whose second slot is
-                 * empty costs as many issue slots as a full one */
-                const uint32_t RS = min(256u, (((nr + 1u) >> 1) + 31u) & ~31u);
-                const uint32_t rA = hr, rB = hr + RS;
-                const bool actA = hr < RS && rA < nr, actB = hr < RS && rB < nr;
-                const uint32_t nw = RS >> 5;
-                double SA = 0, SB = 0;
-                uint32_t buf = 0;
-                if (!fits) issue(0);
-                for (uint32_t c = 0; c < nch; c++) {
-                    const uint32_t k0 = c * KC, cnt = min(KC, n - k0);
-                    if (!fits) {
-                        if (c + 1 < nch) { issue(c + 1); rf_cp_wait<1>(); } else rf_cp_wait<0>();
-                        rf_mbar_wait(&sm.mbar[half][c & 1u], (ringPhase >> (c & 1u)) & 1u);
-                        ringPhase ^= 1u << (c & 1u);
-                        if (!small) asm volatile("bar.sync %0, 256;" ::"r"(1 + half) : "memory");
-                    }
-                    if (hw < nw) {
-                        const float *stage = ring + (c & 1u) * KC * nrP;
-                        for (uint32_t g = 0; g < cnt; g += 16) {
-                            float xa[16], xb[16]; double b[16];
-#pragma unroll
-                            for (int u = 0; u < 16; u++) {
-                                xa[u] = 0; xb[u] = 0;
-                                if (g + u < cnt) {
-                                    if (fits) {
-                                        const uint32_t k = k0 + g + u, pc = sm.pos[half ? n - 1 - k : k];
-                                        const float *colp = sm.tile + pc * tS;
-                                        if (actA) xa[u] = colp[4 * ((rA >> 2) ^ (pc & 7u)) + (rA & 3u)];
-                                        if (actB) xb[u] = colp[4 * ((rB >> 2) ^ (pc & 7u)) + (rB & 3u)];
-                                    } else {
-                                        const float *colp = stage + (half ? cnt - 1 - (g + u) : g + u) * nrP;
-                                        if (actA) xa[u] = colp[rA];
-                                        if (actB) xb[u] = colp[rB];
-                                    }
-                                }
-                            }
-#pragma unroll
-                            for (int u = 0; u < 16; u++) {
-                                b[u] = 0;
-                                if (g + u < cnt) {
-                                    const uint32_t k = k0 + g + u, sp = half ? n - 1 - k : k;
-                                    const double wk = small ? wA[sp] : sm.stepW[half][c & 1u][g + u];
-                                    const double Wp = small ? (k ? WA[k - 1] : 0.0) : sm.stepWp[half][c & 1u][g + u];
-                                    const double xad = (double) xa[u], xbd = (double) xb[u];
-                                    const double ta = wk * SA - Wp * xad, tb = wk * SB - Wp * xbd;
-                                    SA += xad; SB += xbd;
-                                    b[u] = ta * ta + tb * tb;
-                                }
-                            }
-                            rf_reduce16(b, lane);
-                            if (lane < 16 && g + lane < cnt) part[buf][g + lane][hw] = b[0];
-                        }
-                    }
-                    asm volatile("bar.sync %0, 256;" ::"r"(1 + half) : "memory");
-                    if (hr < cnt) {
-                        double sum = 0;
-                        for (uint32_t w8 = 0; w8 < nw; w8++) sum += part[buf][hr][w8];
-                        Bh[k0 + hr] = sum;
-                    }
-                    buf ^= 1;
-                }
-            }
-            __syncthreads();
-            RF_TICK(6);
-            /* prefix pairs (1098-1106), thread = step: first = lw W_k Q_k, second = lw W_k SV_k */
-            for (uint32_t dir = 0; dir < 2; dir++) {
-                const double *WA = dir ? WrA : WfA;
-                float2 *pairs = dir ? pairsR : pairsF;
-                const double *Bh = reinterpret_cast<const double *>(pairs);
-                double cQ = 0, cV = 0;
-                for (uint32_t k0 = 0; k0 < n; k0 += RF_THREADS) {
-                    const uint32_t cnt = min((uint32_t) RF_THREADS, n - k0), k = k0 + tid;
-                    const bool on = tid < cnt;
-                    double v2[2] = {0, 0}, tot2[2], Wk = 1.0;
-                    if (on) {
-                        const uint32_t sp = dir ? n - 1 - k : k;
-                        const double wk = wA[sp];
-                        Wk = WA[k];
-                        if (k) { const double Wp = WA[k - 1]; v2[0] = (1.0 / wk + 1.0 / Wp) * Bh[k] / (Wk * Wk); }
-                        v2[1] = Vi[(uint32_t) (keys[sp] & 0xffffffffull)];
-                    }
-                    rf_scan<2, false>(v2, sm.scan[(scanIt++) & 1], (cnt + 31) / 32, n > RF_THREADS, tot2);
-                    if (on) pairs[k] = make_float2(k == 0 ? 0.0f : (float) (lw * (Wk * (cQ + v2[0]))), (float) (lw * ((cV + v2[1]) * Wk)));
-                    cQ += tot2[0]; cV += tot2[1];
-                }
-            }
-            __syncthreads();
-            RF_TICK(7);
-            /* ---- first minimum of head + tail variance (664-675) ---- */
-            float best = INFINITY, second = INFINITY; uint32_t bi = 0xffffffffu;
-            for (uint32_t k = 1 + tid; k < n; k += RF_THREADS) {
-                const float2 h = pairsF[k - 1], tl = pairsR[n - 1 - k];
-                const float v = h.x + h.y + tl.x + tl.y;
-                if (v < best) { second = best; best = v; bi = k; }
-                else if (v < second) second = v;
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float b2 = __shfl_down_sync(0xffffffffu, best, o), s2 = __shfl_down_sync(0xffffffffu, second, o);
-                const uint32_t i2 = __shfl_down_sync(0xffffffffu, bi, o);
-                if (b2 < best || (b2 == best && i2 < bi)) { second = fminf(s2, best); best = b2; bi = i2; }
-                else second = fminf(second, b2);
-            }
-            if (lane == 0) { sm.rb[warp] = best; sm.rs[warp] = second; sm.ri[warp] = bi; }
-            __syncthreads();
+            uint32_t *listDst = list;                                  /* this kernel sorts the list in place */
+#include "refine_split.inl"
             if (tid == 0) {
                 best = sm.rb[0]; second = sm.rs[0]; bi = sm.ri[0];
                 for (uint32_t i = 1; i < RF_WARPS; i++) {
@@ -760,6 +367,358 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_refine(float *XA, float *XB, 
             I->sHeapCount = sm.sHeapCount; I->sSingleCount = sm.sSingleCount; I->sUnder = sm.sUnder; I->sInt = sm.sInt;
             I->nearTies = sm.nearTies; I->status = sm.err; I->splits = sm.splits; I->degenerate = sm.degenerate;
         }
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------------------------------
+ * k_refine_mt: the same refinement with MANY CTAs per Clustering object.
+ *
+ * A split is a pure function of the cluster it splits: its columns, its list range and -- in the counter sample stream --
+ * its own sub-stream of uniforms (alvrl_rng_node_key).  What is sequential is only the ORDER in which the refinement consumes
+ * the results: the queue pops, the running variance sums, the convergence test, the snapshots.  So the work is cut in two
+ * kinds of tasks that persistent CTAs pull from one global ticket queue:
+ *   split(o, node)  -- refine_split.inl on one cluster of object o; the result (split index, the variance pairs of the two
+ *                      halves, the VRLs of singleton halves) goes into the node record.  The cluster's list range and columns
+ *                      are read from copy `src` (bit 31 of node.begin) and written, sorted, to the other copy, so a split
+ *                      that the refinement never gets to consume leaves the cluster's own data untouched.
+ *   control(o)      -- one CTA replays the refinement of object o as far as the results reach: pop the top of the queue, apply
+ *                      its split exactly like k_refine's thread 0 (same heap operations, same fp32 sums, same convergence
+ *                      test, snapshots), until the top is a cluster without a result.  It then hands out the MT_K unsplit
+ *                      clusters with the largest keys (the ones the queue will pop next, unless their own children overtake
+ *                      them) as split tasks.  When the last of them completes, its CTA enqueues the next control(o).
+ * Only clusters that are IN the queue are split ahead of time (never the children of a cluster whose split has not been
+ * consumed), which is what makes two copies of lists and columns enough: the destination range of such a split holds the dead
+ * source of the cluster's parent.  At the end the leaves whose list sits in copy 1 are copied into copy 0, which reproduces
+ * the in-place list of the sequential algorithm (the list inside a cluster is what the consumed splits left, 641-642).
+ * No co-residency is assumed: a CTA only waits for a ticket it has drawn, and tickets are filled by running CTAs.
+ * ------------------------------------------------------------------------------------------------------------------- */
+#define MT_K 16
+
+struct MtNode {                         /* 64 bytes */
+    float under, integ; uint32_t begin, end;            /* ClusterNode; bit 31 of begin: which copy holds list range and columns */
+    uint32_t state, bi;                                 /* 0 no result, 1 handed out, 2 split; split index relative to begin */
+    float2 pvH, pvT;                                    /* (undersampling, integration) variance of the head / tail half */
+    uint32_t svH, svT;                                  /* first / last VRL of the sorted order (a singleton half) */
+    uint32_t flags;                                     /* bit 0 near tie, bits 8..27 random-direction draws, bits 28..31 RF_ERR_* */
+    uint32_t pad[3];
+};
+
+struct MtPools {
+    MtNode *nodes; HeapEntry *heap, *snap; uint32_t *singles;   /* per object: [nodeCap], [heapCap], [heapCap], [nodeCap] */
+    uint32_t *outstanding;                                      /* per object: split tasks in flight */
+    unsigned long long *slots; uint32_t qmask;                  /* ticket ring: (generation << 40) | (type << 39) | (object << 24) | node */
+    uint32_t *ctr;                                              /* [0] next ticket to draw, [1] next ticket to fill, [2] objects not done */
+    uint32_t nodeCap, heapCap;
+    unsigned long long *clk;                                    /* [grid][32] profile counters */
+};
+
+__device__ __forceinline__ unsigned long long mt_word(uint32_t ticket, uint32_t qmask, uint32_t type, uint32_t obj, uint32_t node) {
+    const unsigned long long gen = (unsigned long long) (ticket / (qmask + 1u)) + 1ull;
+    return (gen << 40) | ((unsigned long long) type << 39) | ((unsigned long long) obj << 24) | (unsigned long long) node;
+}
+/* thread 0, after a __syncthreads(): publishes `cnt` tasks (everything this CTA wrote before becomes visible first) */
+__device__ __forceinline__ void mt_push(const MtPools &mp, uint32_t type, uint32_t obj, const uint32_t *nodeIds, uint32_t cnt) {
+    __threadfence();
+    const uint32_t t0 = atomicAdd(mp.ctr + 1, cnt);
+    for (uint32_t j = 0; j < cnt; j++)
+        atomicExch(mp.slots + ((t0 + j) & mp.qmask), mt_word(t0 + j, mp.qmask, type, obj, nodeIds ? nodeIds[j] : 0u));
+}
+
+__global__ void __launch_bounds__(RF_THREADS, 1) k_refine_mt(float *XA, float *XB, const double *__restrict__ Vcol, RfInst *insts, uint32_t numInst,
+                                                             uint32_t *L0, uint32_t *L1, const float *__restrict__ cw, RfScratch scr, MtPools mp) {
+    extern __shared__ __align__(16) unsigned char rfRaw[];
+    RfShared &sm = *reinterpret_cast<RfShared *>(rfRaw);
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned long long *keysG = scr.keys + (uint64_t) blockIdx.x * scr.keyStride;
+    double *wG = scr.w + (uint64_t) blockIdx.x * scr.stepStride, *WfG = scr.Wf + (uint64_t) blockIdx.x * scr.stepStride,
+           *WrG = scr.Wr + (uint64_t) blockIdx.x * scr.stepStride;
+    float2 *pairsG = scr.pairs + (uint64_t) blockIdx.x * 2 * scr.stepStride;
+    uint32_t *srcG = scr.srcPos + (uint64_t) blockIdx.x * scr.stepStride, *posTmp = scr.posTmp + (uint64_t) blockIdx.x * scr.stepStride;
+    uint32_t scanIt = 0;
+    uint32_t ringPhase = 0;
+    if (tid == 0) {
+        for (int a = 0; a < 4; a++) rf_mbar_init(&sm.mbar[a >> 1][a & 1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int a = 0; a < 24; a++) sm.clk[a / 12][a % 12] = 0;
+        for (int a = 0; a < 4; a++) sm.mtClk[a] = 0;
+    }
+    long long tPhase = 0;
+
+    for (;;) {
+        /* ---- draw a ticket and wait for its task ---- */
+        __syncthreads();
+        if (tid == 0) {
+            const long long w0 = clock64();
+            const uint32_t ticket = atomicAdd(mp.ctr, 1u);
+            const unsigned long long want = (unsigned long long) (ticket / (mp.qmask + 1u)) + 1ull;
+            volatile unsigned long long *slot = mp.slots + (ticket & mp.qmask);
+            unsigned long long w;
+            for (;;) {
+                w = *slot;
+                if ((w >> 40) == want) break;
+                if (*(volatile uint32_t *) (mp.ctr + 2) == 0u) { w = 0; break; }
+                __nanosleep(100);
+            }
+            __threadfence();
+            sm.task[0] = (uint32_t) (w & 0xffffffffull); sm.task[1] = (uint32_t) (w >> 32);
+            sm.mtClk[1] += (unsigned long long) (clock64() - w0);
+        }
+        __syncthreads();
+        const unsigned long long word = ((unsigned long long) sm.task[1] << 32) | sm.task[0];
+        if (word == 0ull) break;
+        const uint32_t o = (uint32_t) (word >> 24) & 0x7fffu, taskNode = (uint32_t) word & 0xffffffu;
+        const bool isControl = ((word >> 39) & 1ull) != 0;
+        RfInst *I = insts + o;
+        MtNode *nodes = mp.nodes + (uint64_t) o * mp.nodeCap;
+        const uint32_t nr = I->nr;
+        const double lw = I->lw;
+        const float *icw = cw + I->cwOff;
+        const uint32_t nrP = I->nrP, nq = nrP >> 2, tS = (nrP + 31u) & ~31u;
+        const double *Vi = Vcol + I->vOff;
+        const uint32_t TV = min((uint32_t) RF_SMALL, (uint32_t) RF_TILE_FLOATS / tS);
+
+        if (!isControl) {
+            /* ================= split(o, taskNode) ================= */
+            MtNode *nd = nodes + taskNode;
+            if (tid == 0) {
+                const uint32_t b = *(volatile uint32_t *) &nd->begin, e = *(volatile uint32_t *) &nd->end;
+                sm.begin = b & 0x7fffffffu; sm.end = e; sm.srcBuf = b >> 31;
+                sm.nodeKey = alvrl_rng_node_key(I->rngKey, sm.begin, sm.end);
+                sm.u1 = alvrl_rng_uniform(sm.nodeKey, 0); sm.u2 = alvrl_rng_uniform(sm.nodeKey, 1); sm.nodePos = 2;   /* 597-602 */
+                sm.flags = 0; sm.found = 0xffffffffu; sm.err = RF_DONE; sm.degenerate = 0;
+                sm.mtClk[3]++;
+            }
+            __syncthreads();
+            const uint32_t begin = sm.begin, n = sm.end - sm.begin;
+            const uint32_t srcBuf = sm.srcBuf;
+            const uint32_t *list = (srcBuf ? L1 : L0) + I->listOff + begin;
+            uint32_t *listDst = (srcBuf ? L0 : L1) + I->listOff + begin;
+            const float *Xs = (srcBuf ? XB : XA) + I->xOff + (size_t) begin * nrP;
+            float *Xd = (srcBuf ? XA : XB) + I->xOff + (size_t) begin * nrP;
+            const bool small = n <= RF_SMALL;
+            unsigned long long *keys = small ? sm.keys : keysG;
+            double *wA = small ? sm.w : wG, *WfA = small ? sm.Wf : WfG, *WrA = small ? sm.Wr : WrG;
+            float2 *pairsF = small ? sm.pairs[0] : pairsG, *pairsR = small ? sm.pairs[1] : pairsG + scr.stepStride;
+            if (tid == 0) { tPhase = clock64(); sm.clk[small ? 0 : 1][9]++; sm.clk[small ? 0 : 1][10] += n; sm.clk[small ? 0 : 1][11] += (n <= TV) ? 0u : n; }
+            if (n >= 2) {
+                do {
+#include "refine_split.inl"
+                } while (0);
+            } else if (tid == 0) sm.err = RF_ERR_SPLIT;
+            __syncthreads();
+            if (tid == 0) {
+                uint32_t flags = 0;
+                if (sm.err != RF_DONE) flags = sm.err << 28;
+                else {
+                    float best = sm.rb[0], second = sm.rs[0]; uint32_t bi = sm.ri[0];
+                    for (uint32_t i = 1; i < RF_WARPS; i++) {
+                        const float b2 = sm.rb[i], s2 = sm.rs[i]; const uint32_t i2 = sm.ri[i];
+                        if (b2 < best || (b2 == best && i2 < bi)) { second = fminf(s2, best); best = b2; bi = i2; }
+                        else second = fminf(second, b2);
+                    }
+                    if (bi == 0xffffffffu) flags = (uint32_t) RF_ERR_NOBEST << 28;
+                    else {
+                        if (isfinite(second) && fabsf(second - best) <= 1e-6f * fabsf(best)) flags |= 1u;
+                        nd->bi = bi; nd->pvH = pairsF[bi - 1]; nd->pvT = pairsR[n - 1 - bi];
+                        nd->svH = (uint32_t) (keys[0] & 0xffffffffull); nd->svT = (uint32_t) (keys[n - 1] & 0xffffffffull);
+                    }
+                }
+                flags |= min(sm.degenerate, 0xfffffu) << 8;
+                nd->flags = flags;
+                __threadfence();
+                *(volatile uint32_t *) &nd->state = 2u;
+                __threadfence();
+                const uint32_t before = atomicSub(mp.outstanding + o, 1u);
+                if (before == 1u) mt_push(mp, 1u, o, nullptr, 1u);             /* the last result of the pass: back to control */
+            }
+            RF_TICK(8);
+            continue;
+        }
+
+        /* ================= control(o) ================= */
+        const long long c0 = clock64();
+        HeapEntry *heapG = mp.heap + (uint64_t) o * mp.heapCap, *snapG = mp.snap + (uint64_t) o * mp.heapCap;
+        uint32_t *singles = mp.singles + (uint64_t) o * mp.nodeCap;
+        SplitHeap heap; heap.lo = sm.heap; heap.hi = heapG + RF_HEAP_CAP; heap.cap = RF_HEAP_CAP;
+        uint32_t *ilist0 = L0 + I->listOff;
+        const uint32_t *ilist1 = L1 + I->listOff;
+        if (!I->mtInit) {                                           /* first pass: the initial queue and singletons */
+            for (uint32_t i = tid; i < I->heapCount; i += RF_THREADS) {
+                const ClusterNode cn = scr.initNodes[I->initNodeOff + i];
+                HeapEntry e; e.key = cn.undersamplingVar + cn.integrationVar; e.id = i;
+                MtNode m; m.under = cn.undersamplingVar; m.integ = cn.integrationVar; m.begin = cn.begin; m.end = cn.end; m.state = 0; m.bi = 0;
+                m.pvH = make_float2(0, 0); m.pvT = make_float2(0, 0); m.svH = m.svT = m.flags = 0; m.pad[0] = m.pad[1] = m.pad[2] = 0;
+                nodes[i] = m; heap[i] = e; snapG[i] = e;
+            }
+            for (uint32_t i = tid; i < I->singleCount; i += RF_THREADS) singles[i] = scr.initSingles[I->initSingleOff + i];
+        } else {
+            for (uint32_t i = tid; i < min(I->heapCount, (uint32_t) RF_HEAP_CAP); i += RF_THREADS) sm.heap[i] = heapG[i];
+        }
+        __syncthreads();
+        if (tid == 0) {
+            sm.heapCount = I->heapCount; sm.nodeCount = I->nodeCount; sm.singleCount = I->singleCount;
+            sm.underVar = I->underVar; sm.intVar = I->intVar; sm.bestConstant = I->bestConstant;
+            if (!I->mtInit) {
+                sm.sHeapCount = I->heapCount; sm.sSingleCount = I->singleCount; sm.sUnder = I->underVar; sm.sInt = I->intVar;
+                sm.nearTies = 0; sm.splits = 0; sm.degenerate = 0;
+            } else {
+                sm.sHeapCount = I->sHeapCount; sm.sSingleCount = I->sSingleCount; sm.sUnder = I->sUnder; sm.sInt = I->sInt;
+                sm.nearTies = I->nearTies; sm.splits = I->splits; sm.degenerate = I->degenerate;
+            }
+            sm.err = RF_DONE; sm.done = 0; sm.stop = 0;
+            sm.mtClk[2]++;
+        }
+        __syncthreads();
+        for (;;) {                                                  /* consume one split per iteration */
+            if (tid == 0) {
+                sm.snap = 0;
+                if (sm.heapCount == 0) sm.done = 1;
+                else if (sm.heapCount + 2 > mp.heapCap || sm.nodeCount + 2 > mp.nodeCap || sm.singleCount + 2 > mp.nodeCap) { sm.err = RF_RESUME_HOST; sm.done = 1; }
+                else {
+                    const uint32_t topId = heap[0].id;
+                    MtNode *nd = nodes + topId;
+                    if (*(volatile uint32_t *) &nd->state != 2u) sm.stop = 1;
+                    else {
+                        heap_pop(heap, sm.heapCount);                                   /* popMulti, 581-587 */
+                        const MtNode cn = *nd;
+                        sm.underVar -= cn.under; sm.intVar -= cn.integ;
+                        const uint32_t begin = cn.begin & 0x7fffffffu, end = cn.end, srcBuf = cn.begin >> 31;
+                        const uint32_t err = cn.flags >> 28;
+                        sm.degenerate += (cn.flags >> 8) & 0xfffffu;
+                        if (err) { sm.err = err; sm.done = 1; }
+                        else {
+                            sm.splits++;
+                            if (cn.flags & 1u) sm.nearTies++;
+                            /* addCluster(begin, split) then addCluster(split, end), 549-572 */
+                            const uint32_t split = begin + cn.bi;
+                            for (int half = 0; half < 2; half++) {
+                                const uint32_t b = half ? split : begin, e = half ? end : split;
+                                const float2 pv = half ? cn.pvT : cn.pvH;
+                                if (e == b + 1) {
+                                    const uint32_t v = half ? cn.svT : cn.svH;
+                                    singles[sm.singleCount++] = v;
+                                    ilist0[b] = v;
+                                    if (pv.x != 0) { sm.err = RF_ERR_SINGLETON_VAR; sm.done = 1; }
+                                    sm.intVar += pv.y;
+                                } else {
+                                    MtNode m; m.under = pv.x; m.integ = pv.y; m.begin = b | ((srcBuf ^ 1u) << 31); m.end = e; m.state = 0; m.bi = 0;
+                                    m.pvH = make_float2(0, 0); m.pvT = make_float2(0, 0); m.svH = m.svT = m.flags = 0; m.pad[0] = m.pad[1] = m.pad[2] = 0;
+                                    nodes[sm.nodeCount] = m;
+                                    HeapEntry he; he.key = pv.x + pv.y; he.id = sm.nodeCount++;
+                                    heap_push(heap, sm.heapCount, he);
+                                    sm.underVar += pv.x; sm.intVar += pv.y;
+                                }
+                            }
+                            const uint32_t numClusters = sm.heapCount + sm.singleCount;
+                            if (I->adaptive) {                                              /* refineAdaptively, 436-452 */
+                                const float scale = I->numVrlsTotal * I->pixelUndersampling + numClusters;
+                                const float curr = scale * (I->tracingVar + sm.underVar + sm.intVar);
+                                const float lower = scale * (I->tracingVar + I->unclIntVar);
+                                if (!isfinite(curr) || curr <= 0) { sm.err = RF_ERR_CONSTANT; sm.done = 1; }
+                                else if (!isfinite(lower) || lower <= 0) { sm.err = RF_ERR_LOWER; sm.done = 1; }
+                                else {
+                                    if (curr < sm.bestConstant) { sm.snap = 1; sm.bestConstant = curr; }
+                                    if (lower >= sm.bestConstant || sm.heapCount == 0) sm.done = 1;
+                                }
+                            } else if (!(numClusters < I->targetClusters && sm.heapCount > 0)) sm.done = 1;     /* refineFixedDepth, 387-399 */
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            const bool doSnap = sm.snap != 0, isDone = sm.done != 0, isStop = sm.stop != 0;
+            if (doSnap) {
+                for (uint32_t i = tid; i < sm.heapCount; i += RF_THREADS) snapG[i] = heap[i];
+                if (tid == 0) { sm.sHeapCount = sm.heapCount; sm.sSingleCount = sm.singleCount; sm.sUnder = sm.underVar; sm.sInt = sm.intVar; }
+            }
+            __syncthreads();
+            if (isDone || isStop) break;
+        }
+        if (!sm.done) {
+            /* ---- hand out the unsplit clusters with the largest keys ---- */
+            float *cand = sm.tile;
+            const uint32_t m = min(sm.heapCount, (uint32_t) RF_TILE_FLOATS);
+            for (uint32_t i = tid; i < m; i += RF_THREADS) {
+                const HeapEntry e = heap[i];
+                cand[i] = (*(volatile uint32_t *) &nodes[e.id].state == 0u) ? e.key : -INFINITY;
+            }
+            if (tid == 0) sm.selCount = 0;
+            __syncthreads();
+            for (uint32_t round = 0; round < MT_K; round++) {
+                float bk = -INFINITY; uint32_t bidx = 0xffffffffu;
+                for (uint32_t i = tid; i < m; i += RF_THREADS) { const float k = cand[i]; if (k > bk) { bk = k; bidx = i; } }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    const float k2 = __shfl_down_sync(0xffffffffu, bk, off); const uint32_t i2 = __shfl_down_sync(0xffffffffu, bidx, off);
+                    if (k2 > bk || (k2 == bk && i2 < bidx)) { bk = k2; bidx = i2; }
+                }
+                if (lane == 0) { sm.rb[warp] = bk; sm.ri[warp] = bidx; }
+                __syncthreads();
+                if (tid == 0) {
+                    bk = sm.rb[0]; bidx = sm.ri[0];
+                    for (uint32_t i = 1; i < RF_WARPS; i++) { const float k2 = sm.rb[i]; const uint32_t i2 = sm.ri[i]; if (k2 > bk || (k2 == bk && i2 < bidx)) { bk = k2; bidx = i2; } }
+                    if (bidx == 0xffffffffu) sm.found = 0xffffffffu;
+                    else { sm.found = bidx; cand[bidx] = -INFINITY; sm.sel[sm.selCount++] = heap[bidx].id; }
+                }
+                __syncthreads();
+                if (sm.found == 0xffffffffu) break;
+            }
+            __syncthreads();
+            if (tid < sm.selCount) *(volatile uint32_t *) &nodes[sm.sel[tid]].state = 1u;
+            if (tid == 0 && sm.selCount == 0) { sm.err = RF_ERR_SPLIT; sm.done = 1; }      /* cannot happen: the top has no result */
+            __syncthreads();
+        }
+        /* ---- write the state back ---- */
+        for (uint32_t i = tid; i < min(sm.heapCount, (uint32_t) RF_HEAP_CAP); i += RF_THREADS) heapG[i] = sm.heap[i];
+        const bool finished = sm.done != 0;
+        if (finished) {
+            /* the list of the sequential algorithm: every leaf's range in the order its parent's sort left (copy 1 -> copy 0) */
+            for (uint32_t i = warp; i < sm.heapCount; i += RF_WARPS) {
+                const HeapEntry e = heap[i];
+                const uint32_t b = nodes[e.id].begin, en = nodes[e.id].end;
+                if (b >> 31) for (uint32_t p = (b & 0x7fffffffu) + lane; p < en; p += 32) ilist0[p] = ilist1[p];
+            }
+            if (tid == 0) {
+                sm.begin = atomicAdd(scr.cursors + 1, sm.heapCount + sm.sHeapCount);
+                sm.end = atomicAdd(scr.cursors + 2, sm.singleCount);
+            }
+            __syncthreads();
+            for (uint32_t i = tid; i < sm.heapCount; i += RF_THREADS) {
+                const MtNode &m = nodes[heap[i].id];
+                ClusterNode cn; cn.undersamplingVar = m.under; cn.integrationVar = m.integ; cn.begin = m.begin & 0x7fffffffu; cn.end = m.end;
+                scr.outNodes[sm.begin + i] = cn;
+            }
+            for (uint32_t i = tid; i < sm.sHeapCount; i += RF_THREADS) {
+                const MtNode &m = nodes[snapG[i].id];
+                ClusterNode cn; cn.undersamplingVar = m.under; cn.integrationVar = m.integ; cn.begin = m.begin & 0x7fffffffu; cn.end = m.end;
+                scr.outNodes[sm.begin + sm.heapCount + i] = cn;
+            }
+            for (uint32_t i = tid; i < sm.singleCount; i += RF_THREADS) scr.outSingles[sm.end + i] = singles[i];
+        }
+        if (tid == 0) {
+            if (finished) { I->outNodeOff = sm.begin; I->outSingleOff = sm.end; I->status = sm.err; }
+            I->underVar = sm.underVar; I->intVar = sm.intVar; I->bestConstant = sm.bestConstant;
+            I->heapCount = sm.heapCount; I->nodeCount = sm.nodeCount; I->singleCount = sm.singleCount;
+            I->sHeapCount = sm.sHeapCount; I->sSingleCount = sm.sSingleCount; I->sUnder = sm.sUnder; I->sInt = sm.sInt;
+            I->nearTies = sm.nearTies; I->splits = sm.splits; I->degenerate = sm.degenerate;
+            I->mtInit = 1; I->mtWaves++;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            if (finished) { __threadfence(); atomicSub(mp.ctr + 2, 1u); }
+            else {
+                __threadfence();
+                atomicExch(mp.outstanding + o, sm.selCount);
+                mt_push(mp, 0u, o, sm.sel, sm.selCount);
+            }
+            sm.mtClk[0] += (unsigned long long) (clock64() - c0);
+        }
+    }
+    __syncthreads();
+    if (tid == 0 && mp.clk) {
+        unsigned long long *out = mp.clk + (uint64_t) blockIdx.x * 32;
+        for (int a = 0; a < 24; a++) out[a] = sm.clk[a / 12][a % 12];
+        for (int a = 0; a < 4; a++) out[24 + a] = sm.mtClk[a];
     }
 }
 

@@ -1,0 +1,411 @@
+/*
+ * refine_split.inl -- the body of one Clustering::split (Preprocessor.cpp:590-684) as executed by one CTA: the two
+ * weightedSample draws, the direction, the projections, the sort, both prefix-variance sweeps and the first-minimum argmin.
+ * Textually included by the refinement kernels of refine.cuh (k_refine: one CTA owns a Clustering object; k_refine_mt: CTAs
+ * pull clusters of any object from a queue), which provide the names used here:
+ *   sm (RfShared), tid / lane / warp, I (RfInst *), nr / nrP / nq / tS / TV, lw, Vi, icw,
+ *   begin, n, small, list (the cluster's VRLs, read) and listDst (where the sorted order goes; may alias list),
+ *   Xs / Xd (the cluster's columns in list order, read / in sorted order, written), keys, wA / WfA / WrA, pairsF / pairsR,
+ *   srcG / posTmp, scanIt, ringPhase, tPhase, and sm.u1 / sm.u2 / sm.nodeKey / sm.nodePos (the cluster's sample sub-stream).
+ * A `break` leaves the enclosing loop with sm.err set.  On exit, warp w's candidate is in sm.rb / sm.rs / sm.ri [w], the
+ * sorted (projection, vrl) keys are in keys[], and pairsF / pairsR hold the head / tail variance pairs.
+ */
+            /* ---- weightedSample x 2 (597-602, 1534-1580) ---- */
+            const uint32_t numChunks = (n + RF_CHUNK - 1) / RF_CHUNK;
+            uint32_t idx[2] = {0, 0};
+            {
+                uint32_t cT = 0;                                    /* chunk whose running sums acc[] holds */
+                for (int draw = 0; draw < 2; draw++) {
+                    /* running sums: chunkEnd[c] = sum after chunk c.  Draw 1 resumes in the chunk of the first centre. */
+                    uint32_t cFrom = 0;
+                    if (draw == 1) {
+                        const uint32_t l1 = idx[0] - cT * RF_CHUNK, cnt = min((uint32_t) RF_CHUNK, n - cT * RF_CHUNK);
+                        if (tid == 0) {
+                            float a = l1 ? sm.acc[l1 - 1] : (cT ? sm.chunkEnd[cT - 1] : 0.0f);
+                            a += 0.0f; sm.acc[l1] = a;
+                            for (uint32_t i = l1 + 1; i < cnt; i++) { a += sm.sw[0][i]; sm.acc[i] = a; }
+                            sm.chunkEnd[cT] = a;
+                        }
+                        cFrom = cT + 1;
+                    }
+                    if (draw == 0 && numChunks == 1) {
+                        if (tid < n) sm.sw[0][tid] = icw[list[tid]];
+                        if (tid + RF_THREADS < n) sm.sw[0][tid + RF_THREADS] = icw[list[tid + RF_THREADS]];
+                        __syncthreads();
+                        if (tid == 0) { float a = 0.0f; for (uint32_t i = 0; i < n; i++) { a += sm.sw[0][i]; sm.acc[i] = a; } sm.chunkEnd[0] = a; }
+                    } else if (cFrom < numChunks) {                 /* double-buffered gather / chain over the remaining chunks */
+                        __syncthreads();
+                        for (uint32_t i = tid; i < min((uint32_t) RF_CHUNK, n - cFrom * RF_CHUNK); i += RF_THREADS) sm.sw[1][i] = icw[list[cFrom * RF_CHUNK + i]];
+                        for (uint32_t c = cFrom; c < numChunks; c++) {
+                            const uint32_t b = (c - cFrom + 1) & 1;
+                            __syncthreads();
+                            if (c + 1 < numChunks)
+                                for (uint32_t i = tid; i < min((uint32_t) RF_CHUNK, n - (c + 1) * RF_CHUNK); i += RF_THREADS) sm.sw[b ^ 1][i] = icw[list[(c + 1) * RF_CHUNK + i]];
+                            if (tid == 0) {
+                                float a = c ? sm.chunkEnd[c - 1] : 0.0f;
+                                const uint32_t cnt = min((uint32_t) RF_CHUNK, n - c * RF_CHUNK);
+                                for (uint32_t i = 0; i < cnt; i++) a += sm.sw[b][i];
+                                sm.chunkEnd[c] = a;
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    const float weightSum = sm.chunkEnd[numChunks - 1];
+                    const float alpha = (draw == 0 ? sm.u1 : sm.u2) * weightSum;
+                    if (tid == 0 && !(weightSum > 0)) sm.flags |= 2u;
+                    uint32_t cNew = 0;
+                    if (numChunks > 1) {                            /* first chunk whose end sum reaches alpha */
+                        for (uint32_t c = tid; c < numChunks; c += RF_THREADS) if (sm.chunkEnd[c] >= alpha) atomicMin(&sm.found, c);
+                        __syncthreads();
+                        cNew = sm.found == 0xffffffffu ? 0u : sm.found;
+                        __syncthreads();
+                        if (tid == 0) sm.found = 0xffffffffu;
+                        if (!(draw == 1 && cNew == cT)) {           /* re-chain that chunk, keeping its running sums */
+                            const uint32_t cnt = min((uint32_t) RF_CHUNK, n - cNew * RF_CHUNK);
+                            for (uint32_t i = tid; i < cnt; i += RF_THREADS) sm.sw[0][i] = icw[list[cNew * RF_CHUNK + i]];
+                            __syncthreads();
+                            if (tid == 0) { float a = cNew ? sm.chunkEnd[cNew - 1] : 0.0f; for (uint32_t i = 0; i < cnt; i++) { a += sm.sw[0][i]; sm.acc[i] = a; } }
+                        }
+                        __syncthreads();
+                    }
+                    cT = cNew;
+                    {
+                        const uint32_t cnt = min((uint32_t) RF_CHUNK, n - cT * RF_CHUNK);
+                        for (uint32_t i = tid; i < cnt; i += RF_THREADS) if (sm.acc[i] >= alpha) atomicMin(&sm.found, i);
+                    }
+                    __syncthreads();
+                    if (sm.found == 0xffffffffu) { idx[draw] = 0; if (tid == 0) sm.flags |= 2u; }
+                    else idx[draw] = cT * RF_CHUNK + sm.found;
+                    __syncthreads();
+                    if (tid == 0) sm.found = 0xffffffffu;
+                }
+            }
+            __syncthreads();
+            if (sm.flags & 2u) { if (tid == 0) sm.err = RF_ERR_WEIGHTS; break; }
+            RF_TICK(0);
+
+            /* ---- direction (604-623) ---- */
+            for (uint32_t r = tid; r < nr; r += RF_THREADS) { sm.c1[r] = Xs[(size_t) idx[0] * nrP + r]; sm.c2[r] = Xs[(size_t) idx[1] * nrP + r]; }
+            __syncthreads();
+            if (tid == 0) { float a = 0; for (uint32_t r = 0; r < nr; r++) a += fabsf(sm.c1[r]) * fabsf(sm.c1[r]); sm.norm[0] = sqrtf(a); }
+            else if (tid == 32) { float a = 0; for (uint32_t r = 0; r < nr; r++) a += fabsf(sm.c2[r]) * fabsf(sm.c2[r]); sm.norm[1] = sqrtf(a); }
+            else if (tid == 64) { float a = 0; for (uint32_t r = 0; r < nr; r++) { const float d = sm.c2[r] - sm.c1[r]; a += fabsf(d) * fabsf(d); } sm.norm[2] = sqrtf(a); }
+            __syncthreads();
+            if (sm.norm[0] != 0 && sm.norm[1] != 0 && sm.norm[2] != 0) {
+                const float dl = sm.norm[2];
+                for (uint32_t r = tid; r < nrP; r += RF_THREADS) sm.sdir[r] = r < nr ? (sm.c2[r] - sm.c1[r]) / dl : 0.0f;
+            } else {
+                /* degenerate centres: direction uniform on the n-sphere, warp::squareToStdNormal(next2D()).x per row (616-622);
+                 * log and cos evaluated in double and rounded (pinned transcendental, same on the host path and in the oracle) */
+                for (;;) {
+                    const uint32_t base = sm.nodePos, nkey = sm.nodeKey;
+                    for (uint32_t r = tid; r < nr; r += RF_THREADS) {
+                        const float s1 = alvrl_rng_uniform(nkey, base + 2 * r), s2 = alvrl_rng_uniform(nkey, base + 2 * r + 1);
+                        const float rr = sqrtf(-2 * (float) log((double) (1 - s1))), phi = (float) (2 * M_PI * s2);
+                        sm.c1[r] = (float) cos((double) phi) * rr;
+                    }
+                    __syncthreads();
+                    if (tid == 0) {
+                        sm.nodePos = base + 2 * nr; sm.degenerate++;
+                        float a = 0; for (uint32_t r = 0; r < nr; r++) a += fabsf(sm.c1[r]) * fabsf(sm.c1[r]);
+                        sm.norm[2] = sqrtf(a);
+                    }
+                    __syncthreads();
+                    if (sm.norm[2] != 0) break;
+                }
+                const float dl = sm.norm[2];
+                for (uint32_t r = tid; r < nrP; r += RF_THREADS) sm.sdir[r] = r < nr ? sm.c1[r] / dl : 0.0f;
+            }
+            __syncthreads();
+
+            RF_TICK(1);
+            /* ---- projections (625-640).  The columns are staged through the tile in chunks with asynchronous 16-byte copies (the
+             *      whole chunk is in flight at once), then thread = column sums sequentially in fp32 in row order out of shared
+             *      memory (the zero padding of columns and direction adds exact zeros).  A local matrix that fits the tile in one
+             *      chunk stays there for the variance sweep. ---- */
+            const bool fits = n <= TV;
+            if (fits) {
+                for (uint32_t i = tid; i < n * nq; i += RF_THREADS) {
+                    const uint32_t c = i / nq, q = i - c * nq;
+                    rf_cp_async16(sm.tile + c * tS + 4 * (q ^ (c & 7u)), Xs + (size_t) c * nrP + 4 * q);
+                }
+                rf_cp_commit(); rf_cp_wait<0>();
+                __syncthreads();
+            }
+            RF_TICK(2);
+            for (uint32_t c = tid; c < n; c += RF_THREADS) {
+                float s = 0, pj = 0;
+                if (fits) {
+                    const float *x = sm.tile + c * tS;
+                    const uint32_t sw = c & 7u;
+#pragma unroll 2
+                    for (uint32_t q = 0; q < nq; q++) {
+                        const float4 e = *reinterpret_cast<const float4 *>(x + 4 * (q ^ sw));
+                        float a;
+                        a = fabsf(e.x); s += a * a; a = fabsf(e.y); s += a * a; a = fabsf(e.z); s += a * a; a = fabsf(e.w); s += a * a;
+                    }
+                    const float len = sqrtf(s);
+                    if (len != 0) {
+#pragma unroll 2
+                        for (uint32_t q = 0; q < nq; q++) {
+                            const float4 e = *reinterpret_cast<const float4 *>(x + 4 * (q ^ sw));
+                            const float4 d = *reinterpret_cast<const float4 *>(sm.sdir + 4 * q);
+                            pj += d.x * (e.x / len); pj += d.y * (e.y / len); pj += d.z * (e.z / len); pj += d.w * (e.w / len);
+                        }
+                    }
+                } else {
+                    /* too large for the tile: every thread streams its own (contiguous) column from L2, eight loads in flight */
+                    const float4 *col4 = reinterpret_cast<const float4 *>(Xs + (size_t) c * nrP);
+                    for (uint32_t q0 = 0; q0 < nq; q0 += 8) {
+                        float4 e[8];
+#pragma unroll
+                        for (int u = 0; u < 8; u++) e[u] = (q0 + u < nq) ? col4[q0 + u] : make_float4(0, 0, 0, 0);
+#pragma unroll
+                        for (int u = 0; u < 8; u++) {
+                            float a;
+                            a = fabsf(e[u].x); s += a * a; a = fabsf(e[u].y); s += a * a; a = fabsf(e[u].z); s += a * a; a = fabsf(e[u].w); s += a * a;
+                        }
+                    }
+                    const float len = sqrtf(s);
+                    if (len != 0) {
+                        for (uint32_t q0 = 0; q0 < nq; q0 += 8) {
+                            float4 e[8];
+#pragma unroll
+                            for (int u = 0; u < 8; u++) e[u] = (q0 + u < nq) ? col4[q0 + u] : make_float4(0, 0, 0, 0);
+#pragma unroll
+                            for (int u = 0; u < 8; u++) {
+                                if (q0 + u < nq) {
+                                    const float4 d = *reinterpret_cast<const float4 *>(sm.sdir + 4 * (q0 + u));
+                                    pj += d.x * (e[u].x / len); pj += d.y * (e[u].y / len); pj += d.z * (e[u].z / len); pj += d.w * (e[u].w / len);
+                                }
+                            }
+                        }
+                    }
+                }
+                const float q = pj + 0.0f;                                      /* -0.0 and +0.0 compare equal in the pair order */
+                uint32_t b = __float_as_uint(q);
+                b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+                const uint32_t vid = list[c];
+                keys[c] = ((unsigned long long) b << 32) | vid;
+                if (small) sm.pos[c] = (uint16_t) c; else posTmp[vid] = c;
+            }
+            /* ---- std::sort of (projection, vrl) pairs (641): bitonic network on the unique keys, always out of shared memory:
+             *      up to RF_SORT_BLOCK keys in one piece (the tile is free when the keys live in global memory), more as
+             *      block-local passes plus global steps for the strides that span blocks ---- */
+            uint32_t m = 2; while (m < n) m <<= 1;
+            for (uint32_t i = n + tid; i < m; i += RF_THREADS) { keys[i] = ~0ull; if (small) sm.pos[i] = 0; }
+            __syncthreads();
+            RF_TICK(3);
+            if (small) {
+                for (uint32_t k = 2; k <= m; k <<= 1) rf_sort_steps(sm.keys, m, 0, k, k >> 1, sm.pos);
+            } else {
+                unsigned long long *sk = reinterpret_cast<unsigned long long *>(sm.tile);
+                const uint32_t blkLen = min(m, (uint32_t) RF_SORT_BLOCK);
+                for (uint32_t blk = 0; blk < m; blk += blkLen) {                /* every block sorted (direction by global index) */
+                    for (uint32_t i = tid; i < blkLen; i += RF_THREADS) sk[i] = keys[blk + i];
+                    __syncthreads();
+                    for (uint32_t k = 2; k <= blkLen; k <<= 1) rf_sort_steps(sk, blkLen, blk, k, k >> 1, nullptr);
+                    for (uint32_t i = tid; i < blkLen; i += RF_THREADS) keys[blk + i] = sk[i];
+                    __syncthreads();
+                }
+                for (uint32_t k = 2 * blkLen; k <= m; k <<= 1) {                /* merges across blocks */
+                    for (uint32_t j = k >> 1; j >= blkLen; j >>= 1) {
+                        for (uint32_t t = tid; t < (m >> 1); t += RF_THREADS) {
+                            const uint32_t lo = ((t & ~(j - 1)) << 1) | (t & (j - 1)), hi = lo | j;
+                            const unsigned long long a = keys[lo], b = keys[hi];
+                            if ((a > b) == ((lo & k) == 0)) { keys[lo] = b; keys[hi] = a; }
+                        }
+                        __syncthreads();
+                    }
+                    for (uint32_t blk = 0; blk < m; blk += blkLen) {
+                        for (uint32_t i = tid; i < blkLen; i += RF_THREADS) sk[i] = keys[blk + i];
+                        __syncthreads();
+                        rf_sort_steps(sk, blkLen, blk, k, blkLen >> 1, nullptr);
+                        for (uint32_t i = tid; i < blkLen; i += RF_THREADS) keys[blk + i] = sk[i];
+                        __syncthreads();
+                    }
+                }
+            }
+            RF_TICK(4);
+            /* ---- sorted list, weights and prefix weights (forward and reverse order) ---- */
+            {
+                double cW[2] = {0, 0};
+                for (uint32_t k0 = 0; k0 < n; k0 += RF_THREADS) {
+                    const uint32_t k = k0 + tid, cnt = min((uint32_t) RF_THREADS, n - k0);
+                    double v[2] = {0, 0}, tot[2];
+                    if (k < n) {
+                        const uint32_t vf = (uint32_t) (keys[k] & 0xffffffffull), vr = (uint32_t) (keys[n - 1 - k] & 0xffffffffull);
+                        listDst[k] = vf;
+                        if (!small) srcG[k] = posTmp[vf];
+                        v[0] = (double) icw[vf]; v[1] = (double) icw[vr];
+                        wA[k] = v[0];
+                    }
+                    rf_scan<2, false>(v, sm.scan[(scanIt++) & 1], (cnt + 31) / 32, n > RF_THREADS, tot);
+                    if (k < n) { WfA[k] = cW[0] + v[0]; WrA[k] = cW[1] + v[1]; }
+                    cW[0] += tot[0]; cW[1] += tot[1];
+                }
+            }
+            /* the sorted copy: from the tile when the local matrix is resident, else gathered column by column (the variance
+             * sweeps then stream it with bulk copies) */
+            if (fits) {
+                for (uint32_t i = tid; i < n * nq; i += RF_THREADS) {
+                    const uint32_t k = i / nq, q = i - k * nq, pc = sm.pos[k];
+                    *reinterpret_cast<float4 *>(Xd + (size_t) k * nrP + 4 * q) = *reinterpret_cast<const float4 *>(sm.tile + pc * tS + 4 * (q ^ (pc & 7u)));
+                }
+            } else {
+                for (uint32_t k4 = warp * 4; k4 < n; k4 += RF_WARPS * 4) {     /* warp = column, four columns in flight */
+                    const float4 *src[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) { const uint32_t k = min(k4 + u, n - 1); src[u] = reinterpret_cast<const float4 *>(Xs + (size_t) (small ? (uint32_t) sm.pos[k] : srcG[k]) * nrP); }
+                    for (uint32_t q = lane; q < nq; q += 32) {
+                        float4 e[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) e[u] = src[u][q];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) if (k4 + u < n) reinterpret_cast<float4 *>(Xd + (size_t) (k4 + u) * nrP)[q] = e[u];
+                    }
+                }
+                __threadfence_block();
+                asm volatile("fence.proxy.async;" ::: "memory");
+            }
+            __syncthreads();
+            RF_TICK(5);
+            /* ---- calculateClusterVariance (1058-1120): the forward sweep on threads 0..255 and the reverse sweep on threads
+             *      256..511, thread = row, sequential over the sorted steps (S_r is a running sum, accesses are contiguous across
+             *      rows).  A local matrix that is not resident streams from the sorted copy through a two-stage ring in the tile,
+             *      one bulk copy (TMA) per KC steps, the next chunk in flight while the current one is computed.  The per-step sums
+             *      over rows B_k = sum_r (w_k S_r(k-1) - W_{k-1} x_r(k))^2 are reduced 16 steps at a time by a transposing
+             *      shuffle reduction and across warps through a double-buffered stage ---- */
+            {
+                const uint32_t half = tid >> 8, hr = tid & 255u, hw = hr >> 5;
+                double *Bh = reinterpret_cast<double *>(half ? pairsR : pairsF);       /* B_k lives where pairs[k] goes afterwards */
+                const double *WA = half ? WrA : WfA;
+                double (*part)[32][8] = reinterpret_cast<double (*)[32][8]>(&sm.sw[0][0]) + half * 2;   /* [buffer][step][warp] */
+                /* steps per stage (>= 12 for nr <= 512); the step loop runs in groups of 16, so 17..31 steps would pay a
+                 * second, mostly empty group per stage */
+                uint32_t KC = min(32u, (uint32_t) (RF_TILE_FLOATS / 4) / nrP);
+                if (KC > 16u && KC < 32u) KC = 16u;
+                float *ring = sm.tile + half * (RF_TILE_FLOATS / 2);
+                const uint32_t nch = (n + KC - 1) / KC;
+                auto issue = [&](uint32_t c) {                                          /* the columns of chunk c -> ring stage c & 1 */
+                    const uint32_t k0 = c * KC, cnt = min(KC, n - k0);
+                    if (hr == 0) {
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                        const uint32_t bytes = cnt * nrP * (uint32_t) sizeof(float);
+                        rf_mbar_expect_tx(&sm.mbar[half][c & 1u], bytes);
+                        rf_bulk_load(ring + (c & 1u) * KC * nrP, Xd + (size_t) (half ? n - k0 - cnt : k0) * nrP, bytes, &sm.mbar[half][c & 1u]);
+                    }
+                    if (!small && hr < cnt) {                                           /* w_k, W_{k-1} live in global memory */
+                        const uint32_t k = k0 + hr, sp = half ? n - 1 - k : k;
+                        rf_cp_async8(&sm.stepW[half][c & 1u][hr], wA + sp);
+                        if (k) rf_cp_async8(&sm.stepWp[half][c & 1u][hr], WA + k - 1); else sm.stepWp[half][c & 1u][hr] = 0.0;
+                    }
+                    rf_cp_commit();
+                };
+                /* thread = rows hr and hr + RS (nr <= 512): the rows are folded onto the fewest warps, RS = roundup(nr / 2, 32),
+                 * so that both row slots of a thread carry a row -- the sweep is issue-bound, and a warp whose second slot is
+                 * empty costs as many issue slots as a full one */
+                const uint32_t RS = min(256u, (((nr + 1u) >> 1) + 31u) & ~31u);
+                const uint32_t rA = hr, rB = hr + RS;
+                const bool actA = hr < RS && rA < nr, actB = hr < RS && rB < nr;
+                const uint32_t nw = RS >> 5;
+                double SA = 0, SB = 0;
+                uint32_t buf = 0;
+                if (!fits) issue(0);
+                for (uint32_t c = 0; c < nch; c++) {
+                    const uint32_t k0 = c * KC, cnt = min(KC, n - k0);
+                    if (!fits) {
+                        if (c + 1 < nch) { issue(c + 1); rf_cp_wait<1>(); } else rf_cp_wait<0>();
+                        rf_mbar_wait(&sm.mbar[half][c & 1u], (ringPhase >> (c & 1u)) & 1u);
+                        ringPhase ^= 1u << (c & 1u);
+                        if (!small) asm volatile("bar.sync %0, 256;" ::"r"(1 + half) : "memory");
+                    }
+                    if (hw < nw) {
+                        const float *stage = ring + (c & 1u) * KC * nrP;
+                        for (uint32_t g = 0; g < cnt; g += 16) {
+                            float xa[16], xb[16]; double b[16];
+#pragma unroll
+                            for (int u = 0; u < 16; u++) {
+                                xa[u] = 0; xb[u] = 0;
+                                if (g + u < cnt) {
+                                    if (fits) {
+                                        const uint32_t k = k0 + g + u, pc = sm.pos[half ? n - 1 - k : k];
+                                        const float *colp = sm.tile + pc * tS;
+                                        if (actA) xa[u] = colp[4 * ((rA >> 2) ^ (pc & 7u)) + (rA & 3u)];
+                                        if (actB) xb[u] = colp[4 * ((rB >> 2) ^ (pc & 7u)) + (rB & 3u)];
+                                    } else {
+                                        const float *colp = stage + (half ? cnt - 1 - (g + u) : g + u) * nrP;
+                                        if (actA) xa[u] = colp[rA];
+                                        if (actB) xb[u] = colp[rB];
+                                    }
+                                }
+                            }
+#pragma unroll
+                            for (int u = 0; u < 16; u++) {
+                                b[u] = 0;
+                                if (g + u < cnt) {
+                                    const uint32_t k = k0 + g + u, sp = half ? n - 1 - k : k;
+                                    const double wk = small ? wA[sp] : sm.stepW[half][c & 1u][g + u];
+                                    const double Wp = small ? (k ? WA[k - 1] : 0.0) : sm.stepWp[half][c & 1u][g + u];
+                                    const double xad = (double) xa[u], xbd = (double) xb[u];
+                                    const double ta = wk * SA - Wp * xad, tb = wk * SB - Wp * xbd;
+                                    SA += xad; SB += xbd;
+                                    b[u] = ta * ta + tb * tb;
+                                }
+                            }
+                            rf_reduce16(b, lane);
+                            if (lane < 16 && g + lane < cnt) part[buf][g + lane][hw] = b[0];
+                        }
+                    }
+                    asm volatile("bar.sync %0, 256;" ::"r"(1 + half) : "memory");
+                    if (hr < cnt) {
+                        double sum = 0;
+                        for (uint32_t w8 = 0; w8 < nw; w8++) sum += part[buf][hr][w8];
+                        Bh[k0 + hr] = sum;
+                    }
+                    buf ^= 1;
+                }
+            }
+            __syncthreads();
+            RF_TICK(6);
+            /* prefix pairs (1098-1106), thread = step: first = lw W_k Q_k, second = lw W_k SV_k */
+            for (uint32_t dir = 0; dir < 2; dir++) {
+                const double *WA = dir ? WrA : WfA;
+                float2 *pairs = dir ? pairsR : pairsF;
+                const double *Bh = reinterpret_cast<const double *>(pairs);
+                double cQ = 0, cV = 0;
+                for (uint32_t k0 = 0; k0 < n; k0 += RF_THREADS) {
+                    const uint32_t cnt = min((uint32_t) RF_THREADS, n - k0), k = k0 + tid;
+                    const bool on = tid < cnt;
+                    double v2[2] = {0, 0}, tot2[2], Wk = 1.0;
+                    if (on) {
+                        const uint32_t sp = dir ? n - 1 - k : k;
+                        const double wk = wA[sp];
+                        Wk = WA[k];
+                        if (k) { const double Wp = WA[k - 1]; v2[0] = (1.0 / wk + 1.0 / Wp) * Bh[k] / (Wk * Wk); }
+                        v2[1] = Vi[(uint32_t) (keys[sp] & 0xffffffffull)];
+                    }
+                    rf_scan<2, false>(v2, sm.scan[(scanIt++) & 1], (cnt + 31) / 32, n > RF_THREADS, tot2);
+                    if (on) pairs[k] = make_float2(k == 0 ? 0.0f : (float) (lw * (Wk * (cQ + v2[0]))), (float) (lw * ((cV + v2[1]) * Wk)));
+                    cQ += tot2[0]; cV += tot2[1];
+                }
+            }
+            __syncthreads();
+            RF_TICK(7);
+            /* ---- first minimum of head + tail variance (664-675) ---- */
+            float best = INFINITY, second = INFINITY; uint32_t bi = 0xffffffffu;
+            for (uint32_t k = 1 + tid; k < n; k += RF_THREADS) {
+                const float2 h = pairsF[k - 1], tl = pairsR[n - 1 - k];
+                const float v = h.x + h.y + tl.x + tl.y;
+                if (v < best) { second = best; best = v; bi = k; }
+                else if (v < second) second = v;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float b2 = __shfl_down_sync(0xffffffffu, best, o), s2 = __shfl_down_sync(0xffffffffu, second, o);
+                const uint32_t i2 = __shfl_down_sync(0xffffffffu, bi, o);
+                if (b2 < best || (b2 == best && i2 < bi)) { second = fminf(s2, best); best = b2; bi = i2; }
+                else second = fminf(second, b2);
+            }
+            if (lane == 0) { sm.rb[warp] = best; sm.rs[warp] = second; sm.ri[warp] = bi; }
+            __syncthreads();

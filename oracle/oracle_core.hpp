@@ -216,6 +216,10 @@ struct Sampler {
     virtual Sampler *clone() = 0;
     /* (domain, a, b) addressing for the counter stream; no-op for SFMT */
     virtual void setContext(uint32_t, uint32_t, uint32_t) {}
+    /* counter stream: the draws of Clustering::split come from the sub-stream of the cluster [begin, end) (alvrl_rng.h);
+     * a sequential stream (SFMT, tapes) just keeps drawing */
+    virtual void enterNode(uint32_t, uint32_t) {}
+    virtual void leaveNode() {}
     uint64_t draws = 0;
 };
 struct SfmtSampler : Sampler {
@@ -226,9 +230,11 @@ struct SfmtSampler : Sampler {
     Sampler *clone() override { return new SfmtSampler(&rnd); }          // independent.cpp:71-80
 };
 struct CounterSampler : Sampler {
-    uint64_t seed; uint32_t key = 0, k = 0;
+    uint64_t seed; uint32_t key = 0, k = 0, outerKey = 0, outerK = 0; bool inNode = false;
     explicit CounterSampler(uint64_t s) : seed(s) {}
-    void setContext(uint32_t domain, uint32_t a, uint32_t b) override { key = alvrl_rng_key(seed, domain, a, b); k = 0; }
+    void setContext(uint32_t domain, uint32_t a, uint32_t b) override { key = alvrl_rng_key(seed, domain, a, b); k = 0; inNode = false; }
+    void enterNode(uint32_t begin, uint32_t end) override { if (inNode) fail("CounterSampler::enterNode nested"); outerKey = key; outerK = k; key = alvrl_rng_node_key(key, begin, end); k = 0; inNode = true; }
+    void leaveNode() override { if (inNode) { key = outerKey; k = outerK; inNode = false; } }
     Float next1D() override { draws++; return alvrl_rng_uniform(key, k++); }
     Sampler *clone() override { return new CounterSampler(seed); }
 };
@@ -246,6 +252,8 @@ struct RecordingSampler : Sampler {
     RecordingSampler(Sampler *in, std::vector<float> &t, uint32_t K_, uint32_t N_) : inner(in), tape(t), K(K_), N(N_) {}
     void setContext(uint32_t d, uint32_t a, uint32_t b) override { inner->setContext(d, a, b); base = ((uint64_t) a * N + b) * K; k = 0; }
     Float next1D() override { draws++; Float u = inner->next1D(); if (k < K) tape[base + k] = u; k++; return u; }
+    void enterNode(uint32_t b, uint32_t e) override { inner->enterNode(b, e); }
+    void leaveNode() override { inner->leaveNode(); }
     Sampler *clone() override { fail("RecordingSampler::clone"); }
 };
 

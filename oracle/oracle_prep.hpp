@@ -279,6 +279,8 @@ private:
         uint32_t clusterSize = end - begin;
         if (clusterSize < 2) return false;
         if (m_stats) m_stats->splits++;
+        sampler->enterNode(begin, end);                                     /* counter stream: this cluster's own draws */
+        struct Leave { Sampler *s; ~Leave() { s->leaveNode(); } } leave{sampler};
         uint32_t vrl1 = m_vrls[weightedSample(m_columnWeights, sampler, nullptr, begin, end, &m_vrls)];
         Float weight1 = m_columnWeights[vrl1];
         m_columnWeights[vrl1] = 0.0f;

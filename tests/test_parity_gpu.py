@@ -266,6 +266,30 @@ def test_clusters_identical_given_oracle_R(pkg, orc, kw):
     _clusters_equal(g.clusters(), o.clusters(), str(kw))
 
 
+_LARGE = {}
+
+
+@pytest.mark.parametrize("path", ["many_ctas_per_object", "one_cta_per_object", "host_rounds"])
+def test_clusters_large_splits_all_device_paths(pkg, orc, monkeypatch, path):
+    """9 000 VRLs: the top of every split tree has clusters beyond the shared-memory limits of the refinement kernels (1 024
+    columns, 8 192 sort keys), and a slice is refined through hundreds of splits.  The three ways the product can drive the
+    refinement in the counter stream -- CTAs pulling clusters of any object from a queue (default), one CTA per object, and
+    host-driven rounds of batched kernels -- must all reproduce the oracle's clusters."""
+    if path == "one_cta_per_object":
+        monkeypatch.setenv("ALVRL_REFINE_ST", "1")
+    elif path == "host_rounds":
+        monkeypatch.setenv("ALVRL_HOST_ROUNDS", "1")
+    g, o = _pair(pkg, orc, "C1", 64, 64, 9000, seed=21, targetNumSlices=6, targetPixelUndersampling=16)
+    if "R" not in _LARGE:
+        o.build_slices(); o.sample_slice_mapping(); o.build_R(); o.build_clusters()
+        _LARGE["R"] = o.get_R(); _LARGE["clusters"] = o.clusters(); _LARGE["diag"] = o.cluster_diag()
+    g.build_slices(); g.sample_slice_mapping()
+    g.set_R(_LARGE["R"])
+    g.build_clusters()
+    print("oracle splits", _LARGE["diag"], "clusters per slice", np.diff(_LARGE["clusters"]["offset"]))
+    _clusters_equal(g.clusters(), _LARGE["clusters"], path)
+
+
 def test_clusters_identical_sfmt_stream(pkg, orc):
     for w in (1, 3):
         g, o = _pair(pkg, orc, "C1", 48, 48, 120, seed=6, rngMode=1, workerCount=w, targetNumSlices=24)
