@@ -433,17 +433,18 @@ int alvrl_build_slices(alvrl_handle c) {
     double t0 = now_ms();
     ensure_primary(c);
     const uint32_t P = c->numPixels();
-    std::vector<SegRec> segs(P);
-    c->dPixSegs.download(segs.data(), P, c->stream);
     /* directionScale, Preprocessor.cpp:1137 (Scene::getAABB diagonal) */
     const float ax = c->sceneMin[0] - c->sceneMax[0], ay = c->sceneMin[1] - c->sceneMax[1], az = c->sceneMin[2] - c->sceneMax[2];
     const float directionScale = std::sqrt(ax * ax + ay * ay + az * az) / 8 * c->P.sliceCurvatureFactor;
+    /* gather point (NaN for misses, Preprocessor.cpp:1172-1177) and scaled normal of every pixel: 24 bytes each come back */
+    DevBuf<float> dPos, dDir; dPos.alloc(3 * (size_t) P); dDir.alloc(3 * (size_t) P);
+    launch_gather_points(c->dPixSegs.p, P, directionScale, dPos.p, dDir.p, c->stream);
+    c->stats.kernelLaunches++;
+    ALVRL_CUDA(cudaGetLastError());
     std::vector<P3> pos(P), dir(P);
-    for (uint32_t i = 0; i < P; i++) {
-        const SegRec &s = segs[i];
-        pos[i] = P3{s.p.x, s.p.y, s.p.z};                                  /* NaN for misses, Preprocessor.cpp:1172-1177 */
-        dir[i] = P3{directionScale * s.n.x, directionScale * s.n.y, directionScale * s.n.z};
-    }
+    static_assert(sizeof(P3) == 12, "P3 is three packed floats");
+    dPos.download(reinterpret_cast<float *>(pos.data()), 3 * (size_t) P, c->stream);
+    dDir.download(reinterpret_cast<float *>(dir.data()), 3 * (size_t) P, c->stream);
     finish_slices(c, pos, dir);
     c->stats.msSlices = (float) (now_ms() - t0);
     API_END

@@ -78,6 +78,44 @@ __global__ void k_column_weights(const float2 *__restrict__ R, uint32_t ldR, uin
     cw[t.cwOff + v] = (float) sqrt(fmax(0.0, acc));
 }
 
+/* The tail of calculateColumnWeigths (1000-1008) for one Clustering object per block: the fp32 average of the weights, summed
+ * sequentially in index order like std::accumulate (one thread walks chunks the block stages in shared memory), then
+ * w += average * safetyFraction for every column.  flags[object] = 1 when a weight is not finite. */
+__global__ void __launch_bounds__(CL_THREADS) k_cw_finish(uint32_t N, const ClTask *__restrict__ tasks, float *__restrict__ cw, uint32_t *__restrict__ flags) {
+    __shared__ __align__(16) float stage[2][2048];
+    __shared__ float shAdd;
+    __shared__ uint32_t shBad;
+    float *w = cw + tasks[blockIdx.x].cwOff;
+    if (threadIdx.x == 0) shBad = 0;
+    uint32_t bad = 0;
+    float acc = 0.0f;
+    const uint32_t nChunks = (N + 2047u) / 2048u;
+    for (uint32_t i = threadIdx.x; i < min(N, 2048u); i += CL_THREADS) { const float x = w[i]; stage[0][i] = x; bad |= !isfinite(x); }
+    for (uint32_t c = 0; c < nChunks; c++) {
+        __syncthreads();
+        if (c + 1 < nChunks)
+            for (uint32_t i = threadIdx.x; i < min(N - (c + 1) * 2048u, 2048u); i += CL_THREADS) { const float x = w[(c + 1) * 2048u + i]; stage[(c + 1) & 1][i] = x; bad |= !isfinite(x); }
+        if (threadIdx.x == 0) {
+            const float *sp = stage[c & 1];
+            const uint32_t cnt = min(N - c * 2048u, 2048u);
+            uint32_t i = 0;
+            for (; i + 4 <= cnt; i += 4) { const float4 v = *reinterpret_cast<const float4 *>(sp + i); acc += v.x; acc += v.y; acc += v.z; acc += v.w; }
+            for (; i < cnt; i++) acc += sp[i];
+        }
+    }
+    if (bad) atomicOr(&shBad, 1u);
+    if (threadIdx.x == 0) {
+        float averageWeight = acc / N;
+        if (averageWeight == 0) averageWeight = 1.0f;
+        const float safetyFraction = 1e-2;
+        shAdd = averageWeight * safetyFraction;
+    }
+    __syncthreads();
+    const float add = shAdd;
+    for (uint32_t i = threadIdx.x; i < N; i += CL_THREADS) w[i] += add;
+    if (threadIdx.x == 0) flags[blockIdx.x] = shBad;
+}
+
 /* block reduction of two doubles; result valid in thread 0 */
 __device__ __forceinline__ void block_reduce2(double &a, double &b, double *sh) {
     for (int o = 16; o > 0; o >>= 1) { a += __shfl_down_sync(0xffffffffu, a, o); b += __shfl_down_sync(0xffffffffu, b, o); }
@@ -101,20 +139,32 @@ __global__ void __launch_bounds__(CL_THREADS) k_unclustered(const float2 *__rest
     const uint32_t row = t.r0 + (active ? lr : 0);
     const uint32_t *list = lists + t.listOff;
     double mean = 0, M2 = 0, summedVars = 0;
-    size_t n = 0;
-    /* the Welford chain is sequential (reference order); the loads are not: eight columns in flight per thread */
-    for (uint32_t k0 = t.begin; k0 < t.end; k0 += 8) {
-        float2 e[8];
+    /* The Welford chain is sequential (reference order); the loads are not: eight columns in flight per thread.  The chain's
+     * division delta / n is the long pole (an IEEE double division is a ~40-instruction routine), and n is the same for every
+     * row: the block computes the correctly rounded reciprocals y = 1 / n of a chunk of steps once, and the chain uses
+     * q0 = delta * y, q = fma(fma(-q0, n, delta), y, q0), which IS the correctly rounded quotient (Markstein: one fma
+     * correction of a faithful quotient with the correctly rounded reciprocal; n is a small integer, far from the theorem's
+     * exceptional all-ones significands) -- bit-identical to delta / n, three dependent operations instead of forty. */
+    __shared__ double rcpN[CL_THREADS];
+    for (uint32_t c0 = t.begin; c0 < t.end; c0 += CL_THREADS) {
+        __syncthreads();
+        rcpN[threadIdx.x] = 1.0 / (double) (c0 - t.begin + threadIdx.x + 1u);
+        __syncthreads();
+        const uint32_t cEnd = min(t.end, c0 + CL_THREADS);
+        for (uint32_t k0 = c0; k0 < cEnd; k0 += 8) {
+            float2 e[8];
 #pragma unroll
-        for (int u = 0; u < 8; u++) e[u] = (k0 + u < t.end) ? R[(size_t) list[k0 + u] * ldR + row] : make_float2(0.0f, 0.0f);
+            for (int u = 0; u < 8; u++) e[u] = (k0 + u < cEnd) ? R[(size_t) list[k0 + u] * ldR + row] : make_float2(0.0f, 0.0f);
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
-            if (k0 + u < t.end) {
-                n++;
-                summedVars += (double) e[u].y;
-                const double x = e[u].x, delta = x - mean;
-                mean += delta / (double) n;
-                M2 += delta * (x - mean);
+            for (int u = 0; u < 8; u++) {
+                if (k0 + u < cEnd) {
+                    const double nD = (double) (k0 + u - t.begin + 1u), y = rcpN[k0 + u - c0];
+                    summedVars += (double) e[u].y;
+                    const double x = e[u].x, delta = x - mean;
+                    const double q0 = delta * y;
+                    mean += fma(fma(-q0, nD, delta), y, q0);          /* == delta / n */
+                    M2 += delta * (x - mean);
+                }
             }
         }
     }
@@ -653,20 +703,19 @@ struct Workspace {
         k_column_weights<<<dim3((N + 127) / 128, (uint32_t) tasks.size()), 128, 0, st>>>(R, ldR, N, dTasks.p, dCw.p);
         launches(1);
         ALVRL_CUDA(cudaGetLastError());
-        std::vector<float> all(insts.size() * (size_t) N);
-        dCw.download(all.data(), all.size(), st);
-        for (size_t i = 0; i < insts.size(); i++) {
-            Inst &in = *insts[i];
-            in.cw.assign(all.begin() + i * (size_t) N, all.begin() + (i + 1) * (size_t) N);
-            for (float w : in.cw) if (!std::isfinite(w)) throw Error(ALVRL_ERR_ARG, "Invalid calculated average column weight");
-            float averageWeight = std::accumulate(in.cw.begin(), in.cw.end(), 0.0f) / N;
-            if (averageWeight == 0) averageWeight = 1.0;
-            const float safetyFraction = 1e-2;
-            for (float &w : in.cw) w += averageWeight * safetyFraction;
-            std::copy(in.cw.begin(), in.cw.end(), all.begin() + i * (size_t) N);
+        ensure(dFlags, tasks.size());
+        k_cw_finish<<<(uint32_t) tasks.size(), CL_THREADS, 0, st>>>(N, dTasks.p, dCw.p, dFlags.p);
+        launches(1);
+        ALVRL_CUDA(cudaGetLastError());
+        /* host mirrors (weightedSample of the representatives, host-driven rounds): straight into the instances' vectors */
+        for (Inst *in : insts) {
+            in->cw.resize(N);
+            ALVRL_CUDA(cudaMemcpyAsync(in->cw.data(), dCw.p + in->cwOff, (size_t) N * sizeof(float), cudaMemcpyDeviceToHost, st));
         }
-        ALVRL_CUDA(cudaMemcpyAsync(dCw.p, all.data(), all.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+        std::vector<uint32_t> bad(tasks.size());
+        dFlags.download(bad.data(), bad.size(), st);
         ALVRL_CUDA(cudaStreamSynchronize(st));
+        for (uint32_t b : bad) if (b) throw Error(ALVRL_ERR_ARG, "Invalid calculated average column weight");
     }
     /* sameLists: every instance starts from the same list (construct): one upload, replicated on the device */
     void uploadLists(bool sameLists = false) {
@@ -741,9 +790,18 @@ struct Workspace {
         auto clap = [&](const char *what) { if (prof.on) { cudaStreamSynchronize(st); const double n_ = Prof::now(); fprintf(stderr, "[alvrl clustering]   construct %s %.1f ms\n", what, n_ - c0_); c0_ = n_; } };
         uint32_t total = 0;
         for (auto &cl : vrlsPerCluster) total += (uint32_t) cl.size();
+        {   /* every object starts from the same list: the host mirrors are filled by a few threads */
+            std::vector<uint32_t> flat; flat.reserve(total);
+            for (auto &cl : vrlsPerCluster) flat.insert(flat.end(), cl.begin(), cl.end());
+            const unsigned nt = insts.size() >= 8 ? std::max(1u, std::min(8u, std::thread::hardware_concurrency())) : 1u;
+            std::atomic<size_t> next(0);
+            auto fill = [&]() { for (size_t k = next++; k < insts.size(); k = next++) insts[k]->vrls = flat; };
+            std::vector<std::thread> pool;
+            for (unsigned ti = 1; ti < nt; ti++) pool.emplace_back(fill);
+            fill();
+            for (auto &t : pool) t.join();
+        }
         for (Inst *in : insts) {
-            in->vrls.clear();
-            for (auto &cl : vrlsPerCluster) in->vrls.insert(in->vrls.end(), cl.begin(), cl.end());
             in->numVrlsTotal = N; in->underVar = 0; in->intVar = 0; in->pq.clear(); in->singletons.clear();
             if (std::fabs((float) (in->lw * in->nr) - 1) > 1e-3) throw Error(ALVRL_ERR_ARG, "Incorrect normalization in localityWeights");
             if (in->pixelUndersampling <= 0 || in->pixelUndersampling > 1) throw Error(ALVRL_ERR_ARG, "Invalid pixel undersampling");

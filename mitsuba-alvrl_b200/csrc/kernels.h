@@ -9,6 +9,7 @@ void launch_primary(const SceneDev &sc, const MediumDev &med, const CameraDev &c
                     const uint32_t *triMat, const float4 *matAlbedo, const uint32_t *matBits, bool haveMedium,
                     SegRec *pixSegs, uint32_t *hitPrim, float *hitT, cudaStream_t st);
 void launch_gather_rows(const SegRec *pixSegs, const uint32_t *rowPixel, uint32_t numRows, SegRec *rowSegs, cudaStream_t st);
+void launch_gather_points(const SegRec *pixSegs, uint32_t P, float directionScale, float *pos, float *dir, cudaStream_t st);
 void launch_trace_rays(const SceneDev &sc, const float *o, const float *d, const float *mint, const float *maxt, uint32_t n,
                        uint32_t *prim, float *t, cudaStream_t st);
 void launch_eval_transmittance(const SceneDev &sc, const MediumDev &med, const float *p1, const int32_t *onSurf, const float *p2,

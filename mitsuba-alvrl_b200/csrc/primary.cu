@@ -92,6 +92,16 @@ __global__ void k_gather_rows(const SegRec *__restrict__ pixSegs, const uint32_t
     if (r < numRows) rowSegs[r] = pixSegs[rowPixel[r]];
 }
 
+/* the slice builder's view of a camera segment: gather point and scaled normal (Preprocessor.cpp:1137-1177), 24 bytes per
+ * pixel instead of the whole segment record */
+__global__ void k_gather_points(const SegRec *__restrict__ pixSegs, uint32_t P, float directionScale, float *__restrict__ pos, float *__restrict__ dir) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const float4 p = pixSegs[i].p, n = pixSegs[i].n;
+    pos[3 * i] = p.x; pos[3 * i + 1] = p.y; pos[3 * i + 2] = p.z;
+    dir[3 * i] = __fmul_rn(directionScale, n.x); dir[3 * i + 1] = __fmul_rn(directionScale, n.y); dir[3 * i + 2] = __fmul_rn(directionScale, n.z);
+}
+
 __global__ void k_trace_rays(SceneDev sc, const float *__restrict__ o, const float *__restrict__ d, const float *__restrict__ mint,
                              const float *__restrict__ maxt, uint32_t n, uint32_t *__restrict__ prim, float *__restrict__ tOut) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -132,6 +142,9 @@ void launch_primary(const SceneDev &sc, const MediumDev &med, const CameraDev &c
 }
 void launch_gather_rows(const SegRec *pixSegs, const uint32_t *rowPixel, uint32_t numRows, SegRec *rowSegs, cudaStream_t st) {
     if (numRows) k_gather_rows<<<(numRows + 127) / 128, 128, 0, st>>>(pixSegs, rowPixel, numRows, rowSegs);
+}
+void launch_gather_points(const SegRec *pixSegs, uint32_t P, float directionScale, float *pos, float *dir, cudaStream_t st) {
+    if (P) k_gather_points<<<(P + 255) / 256, 256, 0, st>>>(pixSegs, P, directionScale, pos, dir);
 }
 void launch_trace_rays(const SceneDev &sc, const float *o, const float *d, const float *mint, const float *maxt, uint32_t n,
                        uint32_t *prim, float *t, cudaStream_t st) {

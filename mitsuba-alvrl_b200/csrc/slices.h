@@ -29,9 +29,11 @@ class SliceTree {
         uint32_t lo, hi; float diag; unsigned char dim; float split;
         bool operator<(const Node &o) const { return diag < o.diag; }
     };
+    /* a gather point travels with its pixel index: the partition permutes these records themselves (the reference permutes
+     * an index array and gathers through it), so that every pass over a node streams contiguous memory */
+    struct Rec { float v[6]; uint32_t idx; };
     const std::vector<P3> &pos, &dir;
-    std::vector<uint32_t> order;
-    static float comp(const P3 &p, int c) { return c == 0 ? p.x : (c == 1 ? p.y : p.z); }
+    std::vector<Rec> rec;
     static bool finite3(const P3 &p) { return std::isfinite(p.x) && std::isfinite(p.y) && std::isfinite(p.z); }
 
     /* findSplitPoint, 1451-1487: midpoint of the largest extent; x wins only if strictly larger than y and z */
@@ -49,17 +51,15 @@ class SliceTree {
         Node n; n.lo = lo; n.hi = hi;
         if (lo + 1 == hi) { n.diag = 0; n.dim = 0; n.split = std::numeric_limits<float>::quiet_NaN(); return n; }
         const float inf = std::numeric_limits<float>::infinity();
-        float pmin[3] = {inf, inf, inf}, pmax[3] = {-inf, -inf, -inf}, dmin[3] = {inf, inf, inf}, dmax[3] = {-inf, -inf, -inf};
-        for (uint32_t i = lo; i < hi; i++) {
-            const P3 &p = pos[order[i]], &d = dir[order[i]];
-            for (int c = 0; c < 3; c++) {
-                const float pc = comp(p, c), dc = comp(d, c);
-                if (pc < pmin[c]) pmin[c] = pc;
-                if (pc > pmax[c]) pmax[c] = pc;
-                if (dc < dmin[c]) dmin[c] = dc;
-                if (dc > dmax[c]) dmax[c] = dc;
+        float mn[6] = {inf, inf, inf, inf, inf, inf}, mx[6] = {-inf, -inf, -inf, -inf, -inf, -inf};
+        const Rec *r = rec.data();
+        for (uint32_t i = lo; i < hi; i++)
+            for (int c = 0; c < 6; c++) {
+                const float x = r[i].v[c];
+                mn[c] = x < mn[c] ? x : mn[c];                     /* the reference's `if (x < min) min = x` */
+                mx[c] = x > mx[c] ? x : mx[c];
             }
-        }
+        const float *pmin = mn, *pmax = mx, *dmin = mn + 3, *dmax = mx + 3;
         /* sliceDistance(minPos, minDir, maxPos, maxDir), 1230-1234 */
         float dp = 0, dd = 0;
         { const float a = pmin[0] - pmax[0], b = pmin[1] - pmax[1], c = pmin[2] - pmax[2]; dp = a * a + b * b + c * c; }
@@ -71,9 +71,6 @@ class SliceTree {
         if (extP > extD) { n.dim = dimP; n.split = splitP; } else { n.dim = 3 + dimD; n.split = splitD; }   /* 1442-1448 */
         return n;
     }
-    bool larger(uint32_t g, int dim, float split) const {          /* isLarger, 1420-1430 */
-        return dim < 3 ? comp(pos[g], dim) > split : comp(dir[g], dim - 3) > split;
-    }
 public:
     SliceTree(const std::vector<P3> &p, const std::vector<P3> &d) : pos(p), dir(d) {}
 
@@ -81,13 +78,13 @@ public:
     std::vector<uint32_t> build(uint32_t targetNumSlices, std::vector<SliceInfo> &slices) {
         const uint32_t n = (uint32_t) pos.size();
         std::vector<uint32_t> toSlice(n, ALVRL_NO_SLICE);
-        order.resize(n);
-        for (uint32_t i = 0; i < n; i++) order[i] = i;
+        rec.resize(n);
+        for (uint32_t i = 0; i < n; i++) { Rec &r = rec[i]; r.v[0] = pos[i].x; r.v[1] = pos[i].y; r.v[2] = pos[i].z; r.v[3] = dir[i].x; r.v[4] = dir[i].y; r.v[5] = dir[i].z; r.idx = i; }
         /* move the misses (non-finite gather points) to the front, 1206-1221 */
         uint32_t firstGood = 0;
         while (firstGood < n && !finite3(pos[firstGood])) firstGood++;
         for (uint32_t i = firstGood + 1; i < n; i++)
-            if (!finite3(pos[i])) { order[i] = order[firstGood]; order[firstGood] = i; firstGood++; }
+            if (!finite3(pos[i])) { std::swap(rec[i], rec[firstGood]); firstGood++; }
         slices.clear();
         if (firstGood >= n) return toSlice;
         std::vector<Node> heap;
@@ -96,23 +93,26 @@ public:
             std::pop_heap(heap.begin(), heap.end());
             const Node top = heap.back();
             heap.pop_back();
-            /* Hoare partition, 1368-1393 */
+            /* Hoare partition, 1368-1393; isLarger, 1420-1430: component `dim` of (position, scaled normal) against the split */
+            const int dim = top.dim; const float split = top.split;
+            Rec *r = rec.data();
             size_t lo = top.lo, hi = top.hi - 1, i = lo - 1, j = hi + 1;
             for (;;) {
-                do { i++; } while (!(larger(order[i], top.dim, top.split) || i == hi));
-                do { j--; } while (!(!larger(order[j], top.dim, top.split) || j == lo));
+                do { i++; } while (!(r[i].v[dim] > split || i == hi));
+                do { j--; } while (!(!(r[j].v[dim] > split) || j == lo));
                 if (i >= j) break;
-                std::swap(order[i], order[j]);
+                std::swap(r[i], r[j]);
             }
             heap.push_back(makeNode(top.lo, (uint32_t) j + 1)); std::push_heap(heap.begin(), heap.end());
             heap.push_back(makeNode((uint32_t) j + 1, top.hi)); std::push_heap(heap.begin(), heap.end());
         }
         for (const Node &nd : heap) {                                         /* slice id = heap array position, 1400-1417 */
             SliceInfo si;
-            si.pixels.assign(order.begin() + nd.lo, order.begin() + nd.hi);
-            for (uint32_t g : si.pixels) toSlice[g] = (uint32_t) slices.size();
+            si.pixels.resize(nd.hi - nd.lo);
+            for (uint32_t k = nd.lo; k < nd.hi; k++) { const uint32_t g = rec[k].idx; si.pixels[k - nd.lo] = g; toSlice[g] = (uint32_t) slices.size(); }
             slices.push_back(std::move(si));
         }
+        std::vector<Rec>().swap(rec);
         return toSlice;
     }
 };
