@@ -200,8 +200,8 @@ def run_ours(a):
             g.set_vrls(*vrls)                                    # host -> device: the step's input (VRL set)
         g.build_slices()
         S, _ = g.num_slices()
-        if multi:
-            g.set_slice_range(S * rank // world, S * (rank + 1) // world)
+        if multi:                                                # contiguous slice ranges of about equal pixel counts
+            g.set_slice_range(*pkg.sharding.balanced_ranges(pkg.sharding.slice_sizes(g.pixel_to_slice(), S), world)[rank])
         g.sample_slice_mapping()
         g.build_R()
         if multi:                                                # zero / non-zero columns over ALL rows: OR across ranks

@@ -116,6 +116,47 @@ __global__ void __launch_bounds__(CL_THREADS) k_cw_finish(uint32_t N, const ClTa
     if (threadIdx.x == 0) flags[blockIdx.x] = shBad;
 }
 
+/* Clustering::sampleRepresentatives (354-378) for the multi-clusters of many objects, thread = cluster: weightedSample
+ * (1534-1580) with its sequential fp32 sums in list order; the uniform of the i-th multi-cluster of an object is draw
+ * rngPos + i of the object's counter stream (one draw per cluster, as on the host).  flags[object] = 1 when a cluster has a
+ * non-positive weight sum (the uniform-pick branch draws a data-dependent number of uniforms: the host handles that object). */
+struct RepObj { uint64_t listOff, cwOff; uint32_t firstCluster, numClusters, rngKey, rngPos; };
+__global__ void __launch_bounds__(128) k_sample_representatives(const RepObj *__restrict__ objs, const uint2 *__restrict__ clusters,
+                                                                const uint32_t *__restrict__ lists, const float *__restrict__ cw,
+                                                                uint32_t *__restrict__ reprOut, float *__restrict__ weightOut, uint32_t *__restrict__ flags) {
+    const RepObj o = objs[blockIdx.y];
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= o.numClusters) return;
+    const uint2 cl = clusters[o.firstCluster + i];
+    const uint32_t *list = lists + o.listOff;
+    const float *w = cw + o.cwOff;
+    float weightSum = 0.0f;
+    for (uint32_t k0 = cl.x; k0 < cl.y; k0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) v[u] = (k0 + u < cl.y) ? w[list[k0 + u]] : 0.0f;
+#pragma unroll
+        for (int u = 0; u < 8; u++) if (k0 + u < cl.y) weightSum += v[u];
+    }
+    if (weightSum <= 0) { atomicOr(flags + blockIdx.y, 1u); return; }
+    const float alpha = alvrl_rng_uniform(o.rngKey, o.rngPos + i) * weightSum;
+    float accum = 0.0f;
+    uint32_t idx = cl.x;
+    bool found = false;
+    for (uint32_t k0 = cl.x; k0 < cl.y && !found; k0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) v[u] = (k0 + u < cl.y) ? w[list[k0 + u]] : 0.0f;
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+            if (!found && k0 + u < cl.y) { accum += v[u]; if (accum >= alpha) { idx = k0 + u; found = true; } }
+    }
+    const uint32_t vrl = list[idx];
+    const float probability = w[vrl] / weightSum;
+    reprOut[o.firstCluster + i] = vrl;
+    weightOut[o.firstCluster + i] = 1.0f / probability;
+}
+
 /* block reduction of two doubles; result valid in thread 0 */
 __device__ __forceinline__ void block_reduce2(double &a, double &b, double *sh) {
     for (int o = 16; o > 0; o >>= 1) { a += __shfl_down_sync(0xffffffffu, a, o); b += __shfl_down_sync(0xffffffffu, b, o); }
@@ -707,15 +748,24 @@ struct Workspace {
         k_cw_finish<<<(uint32_t) tasks.size(), CL_THREADS, 0, st>>>(N, dTasks.p, dCw.p, dFlags.p);
         launches(1);
         ALVRL_CUDA(cudaGetLastError());
-        /* host mirrors (weightedSample of the representatives, host-driven rounds): straight into the instances' vectors */
+        std::vector<uint32_t> bad(tasks.size());
+        dFlags.download(bad.data(), bad.size(), st);
+        for (uint32_t b : bad) if (b) throw Error(ALVRL_ERR_ARG, "Invalid calculated average column weight");
+        cwOnHost = false;
+        if (!lazyMirrors) ensureHostCw();
+    }
+    /* Host mirrors of the column weights and of the VRL permutations are only needed by the host-side paths (weightedSample of
+     * the representatives on the host, host-driven rounds, getVrlsPerCluster): with lazyMirrors they are fetched on demand
+     * (2 x 40 MB of pageable copies per frame at C2 otherwise). */
+    bool lazyMirrors = false, cwOnHost = false;
+    void ensureHostCw() {
+        if (cwOnHost) return;
         for (Inst *in : insts) {
             in->cw.resize(N);
             ALVRL_CUDA(cudaMemcpyAsync(in->cw.data(), dCw.p + in->cwOff, (size_t) N * sizeof(float), cudaMemcpyDeviceToHost, st));
         }
-        std::vector<uint32_t> bad(tasks.size());
-        dFlags.download(bad.data(), bad.size(), st);
         ALVRL_CUDA(cudaStreamSynchronize(st));
-        for (uint32_t b : bad) if (b) throw Error(ALVRL_ERR_ARG, "Invalid calculated average column weight");
+        cwOnHost = true;
     }
     /* sameLists: every instance starts from the same list (construct): one upload, replicated on the device */
     void uploadLists(bool sameLists = false) {
@@ -881,8 +931,50 @@ struct Workspace {
                 } else if (!(in->numClusters() < in->targetClusters && in->numMulti() > 0)) in->done = true;
             }
         }
-        syncLists(which);
+        if (!lazyMirrors) syncLists(which);
         for (Inst *in : which) in->refining = false;
+    }
+    /* sampleRepresentatives for every object of this workspace on the device (counter stream); an object whose weights the
+     * kernel declines is sampled on the host from the mirrors */
+    void sampleRepresentativesDevice(std::vector<std::vector<uint32_t>> &selected, std::vector<std::vector<float>> &weights) {
+        std::vector<RepObj> objs; std::vector<uint2> clusters; std::vector<Inst *> who;
+        for (Inst *in : insts) {
+            if (in->failed) continue;
+            RepObj o; memset(&o, 0, sizeof(o));
+            if (!in->smp->counterState(o.rngKey, o.rngPos)) { hostSample(in, selected, weights); continue; }
+            o.listOff = in->listOff; o.cwOff = in->cwOff; o.firstCluster = (uint32_t) clusters.size(); o.numClusters = (uint32_t) in->pq.size();
+            for (const ClusterNode &cn : in->pq) clusters.push_back(make_uint2(cn.begin, cn.end));
+            objs.push_back(o); who.push_back(in);
+        }
+        if (objs.empty()) return;
+        uint32_t maxC = 1; for (const RepObj &o : objs) maxC = std::max(maxC, o.numClusters);
+        clusters.push_back(make_uint2(0, 0));                                   /* never empty */
+        DevBuf<RepObj> dObjs; DevBuf<uint2> dCl; DevBuf<uint32_t> dRepr, dBad; DevBuf<float> dWt;
+        dObjs.upload(objs, st); dCl.upload(clusters, st);
+        dRepr.alloc(clusters.size()); dWt.alloc(clusters.size()); dBad.alloc(objs.size());
+        ALVRL_CUDA(cudaMemsetAsync(dBad.p, 0, objs.size() * sizeof(uint32_t), st));
+        k_sample_representatives<<<dim3((maxC + 127) / 128, (uint32_t) objs.size()), 128, 0, st>>>(dObjs.p, dCl.p, dLists.p, dCw.p, dRepr.p, dWt.p, dBad.p);
+        launches(1);
+        ALVRL_CUDA(cudaGetLastError());
+        std::vector<uint32_t> repr(clusters.size()), bad(objs.size()); std::vector<float> wt(clusters.size());
+        dRepr.download(repr.data(), repr.size(), st); dWt.download(wt.data(), wt.size(), st); dBad.download(bad.data(), bad.size(), st);
+        for (size_t k = 0; k < who.size(); k++) {
+            Inst *in = who[k];
+            if (bad[k]) { hostSample(in, selected, weights); continue; }
+            std::vector<uint32_t> &r = selected[in->id]; std::vector<float> &w = weights[in->id];
+            r.resize(in->numClusters()); w.resize(in->numClusters());
+            size_t i = 0;
+            for (uint32_t v : in->singletons) { r[i] = v; w[i] = 1; i++; }
+            std::copy(repr.begin() + objs[k].firstCluster, repr.begin() + objs[k].firstCluster + objs[k].numClusters, r.begin() + i);
+            std::copy(wt.begin() + objs[k].firstCluster, wt.begin() + objs[k].firstCluster + objs[k].numClusters, w.begin() + i);
+            in->smp->setCounterPos(objs[k].rngPos + objs[k].numClusters);
+        }
+    }
+    void hostSample(Inst *in, std::vector<std::vector<uint32_t>> &selected, std::vector<std::vector<float>> &weights) {
+        ensureHostCw();
+        in->listsStale = true;
+        syncLists({in});
+        in->sampleRepresentatives(selected[in->id], weights[in->id]);
     }
     /* Device-resident refinement (refine.cuh): every object of `which` that is not done and that the kernel supports runs to
      * completion in one launch; objects it hands back (RF_RESUME_HOST: queue larger than the shared-memory heap) and the ones
@@ -1045,6 +1137,7 @@ struct Workspace {
     }
     /* Clustering::split (590-684) for one cluster of every instance in `round` */
     void splitRound(const std::vector<Inst *> &round, const std::vector<std::pair<uint32_t, uint32_t>> *centres = nullptr) {
+        ensureHostCw();
         const size_t T = round.size();
         std::vector<ClTask> tasks(T);
         uint64_t out = 0, dirOff = 0;
@@ -1433,22 +1526,12 @@ void build_clusters_device(alvrl_ctx *c, bool needFallback) {
                     double q0 = Prof::now(), q1;
                     auto lap = [&](const char *what) { if (w2.prof.on) { cudaStreamSynchronize(w2.st); q1 = Prof::now(); fprintf(stderr, "[alvrl clustering] group %zu %s %.1f ms\n", gI, what, q1 - q0); q0 = q1; } };
                     w2.allocInstances(); lap("allocInstances");
+                    w2.lazyMirrors = true;
                     w2.columnWeights(); lap("columnWeights");
                     w2.construct(c->globalVrlsPerCluster); lap("construct");
                     if (c->P.localRefinement) w2.refine(w2.insts, c->P.localUndersampling);
                     lap("refine");
-                    {   /* every object draws from its own counter stream: the objects are sampled concurrently */
-                        const unsigned nt = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), 16u));
-                        std::atomic<size_t> next(0);
-                        std::vector<std::thread> pool;
-                        for (unsigned ti = 0; ti < nt; ti++) pool.emplace_back([&]() {
-                            for (size_t k = next++; k < w2.insts.size(); k = next++) {
-                                Inst *in = w2.insts[k];
-                                if (!in->failed) in->sampleRepresentatives(c->selectedVrls[in->id], c->clusterWeight[in->id]);
-                            }
-                        });
-                        for (auto &t : pool) t.join();
-                    }
+                    w2.sampleRepresentativesDevice(c->selectedVrls, c->clusterWeight);
                     cudaStreamSynchronize(w2.st); lap("sampleRepresentatives");
                 } catch (const std::exception &e) { errors[gI] = e.what(); }
                 if (w2.st) { cudaStreamDestroy(w2.st); w2.st = nullptr; }

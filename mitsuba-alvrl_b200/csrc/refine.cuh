@@ -157,6 +157,25 @@ __device__ __forceinline__ void rf_bulk_load(void *dst, const void *src, uint32_
                  ::"r"((uint32_t) __cvta_generic_to_shared(dst)), "l"(src), "r"(bytes), "r"((uint32_t) __cvta_generic_to_shared(bar)) : "memory");
 }
 
+/* The four quotients e / len of the projection loop (Preprocessor.cpp:632), correctly rounded without four IEEE division
+ * routines: with y = RN(1 / len), q0 = RN(e y) and one fma correction, q = RN(q0 + RN(e - len q0) y) IS RN(e / len) (Markstein)
+ * as long as nothing on the way leaves the normal range and len's significand is not all ones.  lenOk states the conditions on
+ * len (1e-30 <= len < 1e6, significand != 0x7fffff; then |e| <= len keeps q0 and y normal), a non-zero |e| below 1e-30 (whose
+ * residual could underflow) takes the division.  Checked against the division on 5e9 random pairs (tools/micro/div_exact.cpp). */
+__device__ __forceinline__ float4 rf_div4(const float4 e, const float len, const float y, const bool lenOk) {
+    float4 q = make_float4(e.x * y, e.y * y, e.z * y, e.w * y);
+    q.x = fmaf(fmaf(-q.x, len, e.x), y, q.x); q.y = fmaf(fmaf(-q.y, len, e.y), y, q.y);
+    q.z = fmaf(fmaf(-q.z, len, e.z), y, q.z); q.w = fmaf(fmaf(-q.w, len, e.w), y, q.w);
+    const float tiny = 1e-30f;
+    const bool slow = !lenOk || (fabsf(e.x) < tiny && e.x != 0.0f) || (fabsf(e.y) < tiny && e.y != 0.0f) ||
+                      (fabsf(e.z) < tiny && e.z != 0.0f) || (fabsf(e.w) < tiny && e.w != 0.0f);
+    if (slow) q = make_float4(e.x / len, e.y / len, e.z / len, e.w / len);
+    return q;
+}
+__device__ __forceinline__ bool rf_div_len_ok(float len) {
+    return len >= 1e-30f && len < 1e6f && (__float_as_uint(len) & 0x7fffffu) != 0x7fffffu;
+}
+
 /* sums over the 32 lanes of 16 values per lane with 16 shuffles: afterwards b[0] of lane l holds the total of value (l & 15) */
 __device__ __forceinline__ void rf_reduce16(double (&b)[16], uint32_t lane) {
 #pragma unroll
@@ -392,7 +411,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_refine(float *XA, float *XB, 
  * the in-place list of the sequential algorithm (the list inside a cluster is what the consumed splits left, 641-642).
  * No co-residency is assumed: a CTA only waits for a ticket it has drawn, and tickets are filled by running CTAs.
  * ------------------------------------------------------------------------------------------------------------------- */
-#define MT_K 16
+#define MT_K 32
 
 struct MtNode {                         /* 64 bytes */
     float under, integ; uint32_t begin, end;            /* ClusterNode; bit 31 of begin: which copy holds list range and columns */

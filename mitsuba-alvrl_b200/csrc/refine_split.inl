@@ -133,9 +133,17 @@
                 __syncthreads();
             }
             RF_TICK(2);
-            for (uint32_t c = tid; c < n; c += RF_THREADS) {
-                float s = 0, pj = 0;
-                if (fits) {
+            auto emitKey = [&](uint32_t c, float pj) {
+                const float q = pj + 0.0f;                                      /* -0.0 and +0.0 compare equal in the pair order */
+                uint32_t b = __float_as_uint(q);
+                b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+                const uint32_t vid = list[c];
+                keys[c] = ((unsigned long long) b << 32) | vid;
+                if (small) sm.pos[c] = (uint16_t) c; else posTmp[vid] = c;
+            };
+            if (fits) {
+                for (uint32_t c = tid; c < n; c += RF_THREADS) {
+                    float s = 0, pj = 0;
                     const float *x = sm.tile + c * tS;
                     const uint32_t sw = c & 7u;
 #pragma unroll 2
@@ -146,48 +154,72 @@
                     }
                     const float len = sqrtf(s);
                     if (len != 0) {
+                        const float y = 1.0f / len;
+                        const bool lenOk = rf_div_len_ok(len);
 #pragma unroll 2
                         for (uint32_t q = 0; q < nq; q++) {
-                            const float4 e = *reinterpret_cast<const float4 *>(x + 4 * (q ^ sw));
+                            const float4 e = rf_div4(*reinterpret_cast<const float4 *>(x + 4 * (q ^ sw)), len, y, lenOk);   /* e / len */
                             const float4 d = *reinterpret_cast<const float4 *>(sm.sdir + 4 * q);
-                            pj += d.x * (e.x / len); pj += d.y * (e.y / len); pj += d.z * (e.z / len); pj += d.w * (e.w / len);
+                            pj += d.x * e.x; pj += d.y * e.y; pj += d.z * e.z; pj += d.w * e.w;
                         }
                     }
-                } else {
-                    /* too large for the tile: every thread streams its own (contiguous) column from L2, eight loads in flight */
-                    const float4 *col4 = reinterpret_cast<const float4 *>(Xs + (size_t) c * nrP);
-                    for (uint32_t q0 = 0; q0 < nq; q0 += 8) {
-                        float4 e[8];
-#pragma unroll
-                        for (int u = 0; u < 8; u++) e[u] = (q0 + u < nq) ? col4[q0 + u] : make_float4(0, 0, 0, 0);
-#pragma unroll
-                        for (int u = 0; u < 8; u++) {
-                            float a;
-                            a = fabsf(e[u].x); s += a * a; a = fabsf(e[u].y); s += a * a; a = fabsf(e[u].z); s += a * a; a = fabsf(e[u].w); s += a * a;
+                    emitKey(c, pj);
+                }
+            } else {
+                /* Too large for the tile: RF_THREADS columns at a time, thread = column, and the columns' rows pass through the tile
+                 * in blocks of 16 rows (two buffers of RF_THREADS x 16 floats, asynchronous 16-byte copies: one warp instruction
+                 * copies 64 contiguous bytes of each of 8 columns), so that global memory is read in whole sectors while the
+                 * sequential fp32 sums -- same operations in the same order -- run out of shared memory.  Granule g of column c sits
+                 * at slot g ^ ((c >> 1) & 3) of the column's 64 bytes: the LDS.128 of 8 consecutive threads cover 8 distinct slots. */
+                float *const pbuf0 = sm.tile, *const pbuf1 = sm.tile + RF_THREADS * 16;
+                const uint32_t nrb = (nq + 3u) >> 2;
+                for (uint32_t c0 = 0; c0 < n; c0 += RF_THREADS) {
+                    const uint32_t cc = min((uint32_t) RF_THREADS, n - c0);
+                    auto stageRows = [&](uint32_t rb) {
+                        float *dst = (rb & 1u) ? pbuf1 : pbuf0;
+                        const uint32_t g0 = rb << 2, gcnt = min(4u, nq - g0);
+                        for (uint32_t i = tid; i < cc * 4u; i += RF_THREADS) {
+                            const uint32_t col = i >> 2, g = i & 3u;
+                            if (g < gcnt) rf_cp_async16(dst + col * 16u + 4u * (g ^ ((col >> 1) & 3u)), Xs + (size_t) (c0 + col) * nrP + 4u * (g0 + g));
                         }
-                    }
-                    const float len = sqrtf(s);
-                    if (len != 0) {
-                        for (uint32_t q0 = 0; q0 < nq; q0 += 8) {
-                            float4 e[8];
-#pragma unroll
-                            for (int u = 0; u < 8; u++) e[u] = (q0 + u < nq) ? col4[q0 + u] : make_float4(0, 0, 0, 0);
-#pragma unroll
-                            for (int u = 0; u < 8; u++) {
-                                if (q0 + u < nq) {
-                                    const float4 d = *reinterpret_cast<const float4 *>(sm.sdir + 4 * (q0 + u));
-                                    pj += d.x * (e[u].x / len); pj += d.y * (e[u].y / len); pj += d.z * (e[u].z / len); pj += d.w * (e[u].w / len);
-                                }
+                        rf_cp_commit();
+                    };
+                    const uint32_t swz = (tid >> 1) & 3u;
+                    float s = 0, pj = 0;
+                    stageRows(0);
+                    for (uint32_t rb = 0; rb < nrb; rb++) {                         /* pass 1: |column|^2, rows in order */
+                        if (rb + 1 < nrb) { stageRows(rb + 1); rf_cp_wait<1>(); } else rf_cp_wait<0>();
+                        __syncthreads();
+                        if (tid < cc) {
+                            const float *x = ((rb & 1u) ? pbuf1 : pbuf0) + tid * 16u;
+                            const uint32_t gcnt = min(4u, nq - (rb << 2));
+                            for (uint32_t g = 0; g < gcnt; g++) {
+                                const float4 e = *reinterpret_cast<const float4 *>(x + 4u * (g ^ swz));
+                                float a;
+                                a = fabsf(e.x); s += a * a; a = fabsf(e.y); s += a * a; a = fabsf(e.z); s += a * a; a = fabsf(e.w); s += a * a;
                             }
                         }
+                        __syncthreads();
                     }
+                    const float len = sqrtf(s), y = 1.0f / len;
+                    const bool lenOk = rf_div_len_ok(len);
+                    stageRows(0);
+                    for (uint32_t rb = 0; rb < nrb; rb++) {                         /* pass 2: the projection, rows in order */
+                        if (rb + 1 < nrb) { stageRows(rb + 1); rf_cp_wait<1>(); } else rf_cp_wait<0>();
+                        __syncthreads();
+                        if (tid < cc && len != 0) {
+                            const float *x = ((rb & 1u) ? pbuf1 : pbuf0) + tid * 16u;
+                            const uint32_t g0 = rb << 2, gcnt = min(4u, nq - g0);
+                            for (uint32_t g = 0; g < gcnt; g++) {
+                                const float4 e = rf_div4(*reinterpret_cast<const float4 *>(x + 4u * (g ^ swz)), len, y, lenOk);   /* e / len */
+                                const float4 d = *reinterpret_cast<const float4 *>(sm.sdir + 4u * (g0 + g));
+                                pj += d.x * e.x; pj += d.y * e.y; pj += d.z * e.z; pj += d.w * e.w;
+                            }
+                        }
+                        __syncthreads();
+                    }
+                    if (tid < cc) emitKey(c0 + tid, pj);
                 }
-                const float q = pj + 0.0f;                                      /* -0.0 and +0.0 compare equal in the pair order */
-                uint32_t b = __float_as_uint(q);
-                b = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-                const uint32_t vid = list[c];
-                keys[c] = ((unsigned long long) b << 32) | vid;
-                if (small) sm.pos[c] = (uint16_t) c; else posTmp[vid] = c;
             }
             /* ---- std::sort of (projection, vrl) pairs (641): bitonic network on the unique keys, always out of shared memory:
              *      up to RF_SORT_BLOCK keys in one piece (the tile is free when the keys live in global memory), more as

@@ -36,7 +36,7 @@ def _worker(rank, world, port, out_dir):
     o = setup(orc.Oracle(threads=2, **params), scene, vrls)
     o.build_slices()
     S, _ = o.num_slices()
-    b, e = S * rank // world, S * (rank + 1) // world
+    b, e = pkg.sharding.balanced_ranges(pkg.sharding.slice_sizes(o.pixel_to_slice(), S), world)[rank]
     o.set_slice_range(b, e)
     o.sample_slice_mapping()
     o.build_R()
@@ -66,3 +66,18 @@ def test_slice_sharding_world_size_2(tmp_path, pkg, orc):
     o.build_slices(); o.prepass()
     np.testing.assert_array_equal(got["image"], o.render())          # slices are independent: bit-identical composition
     np.testing.assert_array_equal(got["flags"], o.column_nonzero())
+
+
+def test_balanced_ranges_cover_and_balance(pkg):
+    rng = np.random.default_rng(5)
+    for world in (1, 2, 4, 8):
+        for S in (1, 3, 8, 100):
+            sizes = rng.integers(1, 4000, S)
+            r = pkg.sharding.balanced_ranges(sizes, world)
+            assert len(r) == world and r[0][0] == 0 and r[-1][1] == S
+            assert all(r[i][1] == r[i + 1][0] for i in range(world - 1)) and all(b <= e for b, e in r)
+            if S >= 4 * world:                                   # every rank within one largest slice of its fair share
+                loads = np.array([sizes[b:e].sum() for b, e in r])
+                assert np.abs(loads - sizes.sum() / world).max() <= sizes.max()
+    p2s = np.array([0, 0, 1, 0xFFFFFFFF, 2, 2, 2], dtype=np.uint32)
+    assert list(pkg.sharding.slice_sizes(p2s, 3)) == [2, 1, 3]
