@@ -1036,7 +1036,7 @@ struct Workspace {
         ALVRL_CUDA(cudaMemsetAsync(dCursors.p, 0, 4 * sizeof(uint32_t), st));
         RfScratch scr;
         scr.keys = dKeysG.p; scr.w = dWG.p; scr.Wf = dWG.p + (size_t) grid * N; scr.Wr = dWG.p + (size_t) grid * 2 * N; scr.pairs = dPairsG.p;
-        scr.keyStride = keyStride; scr.stepStride = N;
+        scr.keyStride = keyStride; scr.stepStride = N; scr.unfoldRows = getenv("ALVRL_RF_UNFOLD") ? 1u : 0u;
         scr.snapHeap = dSnap.p; scr.nodes = dNodes.p; scr.singles = dSingles.p; scr.heapOv = dHeapOv.p; scr.heapCap = heapCap; scr.nodeCap = nodeCap;
         scr.srcPos = dSrcPos.p; scr.posTmp = dSrcPos.p + (size_t) grid * N;
         scr.initNodes = dInitNodes.p; scr.initSingles = dInitSingles.p; scr.outNodes = dOutNodes.p; scr.outSingles = dOutSingles.p; scr.cursors = dCursors.p;

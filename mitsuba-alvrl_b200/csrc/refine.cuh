@@ -25,6 +25,7 @@
  * tile (n * nr <= 24576, i.e. almost all of them) read R exactly once per split; larger ones stream columns from L2.
  */
 #pragma once
+#include <type_traits>
 #include "heap_order.h"
 
 namespace alvrl {
@@ -71,6 +72,7 @@ struct RfScratch {                      /* per CTA */
     uint32_t *singles;                  /* [nodeCap] singleton VRL ids in insertion order */
     const ClusterNode *initNodes; const uint32_t *initSingles; ClusterNode *outNodes; uint32_t *outSingles;
     uint32_t *cursors;                  /* [0] next object, [1] output node cursor, [2] output singleton cursor */
+    uint32_t unfoldRows;                /* experiment (ALVRL_RF_UNFOLD): one row per thread in the variance sweeps when nr <= 256 */
 };
 
 struct RfShared {

@@ -337,7 +337,7 @@
                 /* thread = rows hr and hr + RS (nr <= 512): the rows are folded onto the fewest warps, RS = roundup(nr / 2, 32),
                  * so that both row slots of a thread carry a row -- the sweep is issue-bound, and a warp whose second slot is
                  * empty costs as many issue slots as a full one */
-                const uint32_t RS = min(256u, (((nr + 1u) >> 1) + 31u) & ~31u);
+                const uint32_t RS = (scr.unfoldRows && nr <= 256u) ? ((nr + 31u) & ~31u) : min(256u, (((nr + 1u) >> 1) + 31u) & ~31u);
                 const uint32_t rA = hr, rB = hr + RS;
                 const bool actA = hr < RS && rA < nr, actB = hr < RS && rB < nr;
                 const uint32_t nw = RS >> 5;
@@ -354,17 +354,22 @@
                     }
                     if (hw < nw) {
                         const float *stage = ring + (c & 1u) * KC * nrP;
-                        for (uint32_t g = 0; g < cnt; g += 16) {
+                        /* one group of 16 steps; the variants are compile-time so that the common case -- a full group -- carries no
+                         * per-step predicates and each residency mode only its own addressing.  A resident column pc keeps element r
+                         * at colp[r ^ ((pc & 7) << 2)]: the granule swizzle (r / 4) ^ (pc & 7) touches bits 2..4 of r only. */
+                        auto group = [&](auto kFits, auto kSmall, auto kFull, const uint32_t g) {
+                            constexpr bool FITS = decltype(kFits)::value, SMALLC = decltype(kSmall)::value, FULL = decltype(kFull)::value;
                             float xa[16], xb[16]; double b[16];
 #pragma unroll
                             for (int u = 0; u < 16; u++) {
                                 xa[u] = 0; xb[u] = 0;
-                                if (g + u < cnt) {
-                                    if (fits) {
+                                if (FULL || g + u < cnt) {
+                                    if (FITS) {
                                         const uint32_t k = k0 + g + u, pc = sm.pos[half ? n - 1 - k : k];
                                         const float *colp = sm.tile + pc * tS;
-                                        if (actA) xa[u] = colp[4 * ((rA >> 2) ^ (pc & 7u)) + (rA & 3u)];
-                                        if (actB) xb[u] = colp[4 * ((rB >> 2) ^ (pc & 7u)) + (rB & 3u)];
+                                        const uint32_t swz = (pc & 7u) << 2;
+                                        if (actA) xa[u] = colp[rA ^ swz];
+                                        if (actB) xb[u] = colp[rB ^ swz];
                                     } else {
                                         const float *colp = stage + (half ? cnt - 1 - (g + u) : g + u) * nrP;
                                         if (actA) xa[u] = colp[rA];
@@ -375,10 +380,10 @@
 #pragma unroll
                             for (int u = 0; u < 16; u++) {
                                 b[u] = 0;
-                                if (g + u < cnt) {
+                                if (FULL || g + u < cnt) {
                                     const uint32_t k = k0 + g + u, sp = half ? n - 1 - k : k;
-                                    const double wk = small ? wA[sp] : sm.stepW[half][c & 1u][g + u];
-                                    const double Wp = small ? (k ? WA[k - 1] : 0.0) : sm.stepWp[half][c & 1u][g + u];
+                                    const double wk = SMALLC ? wA[sp] : sm.stepW[half][c & 1u][g + u];
+                                    const double Wp = SMALLC ? (k ? WA[k - 1] : 0.0) : sm.stepWp[half][c & 1u][g + u];
                                     const double xad = (double) xa[u], xbd = (double) xb[u];
                                     const double ta = wk * SA - Wp * xad, tb = wk * SB - Wp * xbd;
                                     SA += xad; SB += xbd;
@@ -386,7 +391,14 @@
                                 }
                             }
                             rf_reduce16(b, lane);
-                            if (lane < 16 && g + lane < cnt) part[buf][g + lane][hw] = b[0];
+                            if (lane < 16 && (FULL || g + lane < cnt)) part[buf][g + lane][hw] = b[0];
+                        };
+                        using T_ = std::true_type; using F_ = std::false_type;
+                        for (uint32_t g = 0; g < cnt; g += 16) {
+                            const bool full = g + 16 <= cnt;
+                            if (fits) { if (full) group(T_(), T_(), T_(), g); else group(T_(), T_(), F_(), g); }
+                            else if (small) { if (full) group(F_(), T_(), T_(), g); else group(F_(), T_(), F_(), g); }
+                            else { if (full) group(F_(), F_(), T_(), g); else group(F_(), F_(), F_(), g); }
                         }
                     }
                     asm volatile("bar.sync %0, 256;" ::"r"(1 + half) : "memory");
