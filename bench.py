@@ -175,7 +175,8 @@ def run_ours(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if multi:
-        os.environ["NCCL_DEBUG"] = os.environ.get("ALVRL_NCCL_DEBUG", "WARN")     # keep stdout to the one JSON line
+        os.environ["NCCL_DEBUG"] = os.environ.get("ALVRL_NCCL_DEBUG", "WARN")     # keep stdout to the one JSON line:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")                   # NCCL's version banner goes to stderr
         dist.init_process_group("nccl", device_id=dev)
 
     scene, vrls, params, desc, hg = workload(pkg, a)
@@ -270,8 +271,8 @@ def run_ours(a):
     roof = {"bound": "fp32", "kernel": "k_build_R_fast<homogeneous>", "achieved": achieved, "peak": float(peak.value), "unit": "TFLOP/s",
             "frac": achieved / float(peak.value) if peak.value else None,
             # dram__bytes_read.sum + dram__bytes_write.sum of this very launch (C2: 15 759 rows x 100 000 VRLs) from one
-            # `ncu --set full` capture, profiles/r1_buildR_c2_final.ncu-rep: 0.124 GB read + 12.567 GB written
-            "traffic": 12690647872 if (N == 100000 and W == 1024 and H == 1024 and world == 1) else None,
+            # `ncu --set full` capture, profiles/r1_buildR_c2_v9.ncu-rep: 0.254 GB read + 12.614 GB written
+            "traffic": 12867996160 if (N == 100000 and W == 1024 and H == 1024 and world == 1) else None,
             "peak_source": "FP32 FFMA microbenchmark measured live on this device (alvrl_measure_fp32_peak); north_star names the "
                            "non-tensor FP32 roofline for this kernel (no dense contraction, tensor cores unused); nominal 148 SM x 128 x 2 x 1.965 GHz = 74.5",
             "flops_per_contribution": F, "contributions_per_launch": k_pairs, "launch_ms": k_ms,
