@@ -1024,7 +1024,9 @@ struct Workspace {
         dInst.upload(hi, st); dInitNodes.upload(initNodes, st); dInitSingles.upload(initSingles, st);
         dOutNodes.alloc(dev.size() * (size_t) (2 * heapCap)); dOutSingles.alloc(dev.size() * (size_t) nodeCap);
         DevBuf<MtNode> dMtNodes; DevBuf<HeapEntry> dMtHeap; DevBuf<uint32_t> dOutstanding, dLists1, dCtr; DevBuf<unsigned long long> dSlots, dMtClk;
-        if (mt) { dMtNodes.alloc(pool * nodeCap); dMtHeap.alloc(pool * heapCap); dOutstanding.alloc(pool); dLists1.alloc(dLists.n); dCtr.alloc(4); }
+        DevBuf<uint32_t> dCtl, dWaitNode;
+        if (mt) { dMtNodes.alloc(pool * nodeCap); dMtHeap.alloc(pool * heapCap); dOutstanding.alloc(pool); dLists1.alloc(dLists.n); dCtr.alloc(4);
+                  dCtl.alloc(pool); dWaitNode.alloc(pool); }
         else { dNodes.alloc((size_t) grid * nodeCap); dHeapOv.alloc((size_t) grid * (heapCap - RF_HEAP_CAP)); }
         dSingles.alloc(pool * nodeCap); dSnap.alloc(pool * heapCap);
         dKeysG.alloc((size_t) grid * keyStride); dWG.alloc((size_t) grid * 3 * N); dPairsG.alloc((size_t) grid * 2 * N);
@@ -1046,6 +1048,8 @@ struct Workspace {
             dSlots.alloc(qcap); dMtClk.alloc((size_t) grid * 32);
             ALVRL_CUDA(cudaMemsetAsync(dSlots.p, 0, qcap * sizeof(unsigned long long), st));
             ALVRL_CUDA(cudaMemsetAsync(dOutstanding.p, 0, pool * sizeof(uint32_t), st));
+            ALVRL_CUDA(cudaMemsetAsync(dWaitNode.p, 0xff, pool * sizeof(uint32_t), st));            /* MT_NONE */
+            dCtl.upload(std::vector<uint32_t>(pool, 1u), st);                                        /* the first control passes are in the ring */
             ALVRL_CUDA(cudaMemsetAsync(dMtClk.p, 0, (size_t) grid * 32 * sizeof(unsigned long long), st));
             std::vector<unsigned long long> first(dev.size());                  /* one control task per object to start with */
             for (size_t i = 0; i < dev.size(); i++) first[i] = (1ull << 40) | (1ull << 39) | ((unsigned long long) i << 24);
@@ -1054,6 +1058,7 @@ struct Workspace {
             dCtr.upload(ctr, st);
             MtPools mp;
             mp.nodes = dMtNodes.p; mp.heap = dMtHeap.p; mp.snap = dSnap.p; mp.singles = dSingles.p; mp.outstanding = dOutstanding.p;
+            mp.ctl = dCtl.p; mp.waitNode = dWaitNode.p;
             mp.slots = dSlots.p; mp.qmask = qcap - 1; mp.ctr = dCtr.p; mp.nodeCap = nodeCap; mp.heapCap = heapCap; mp.clk = dMtClk.p;
             ALVRL_CUDA(cudaFuncSetAttribute(k_refine_mt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(RfShared)));
             k_refine_mt<<<grid, RF_THREADS, sizeof(RfShared), st>>>(dX.p, dX2.p, dVcol.p, dInst.p, (uint32_t) dev.size(), dLists.p, dLists1.p, dCw.p, scr, mp);

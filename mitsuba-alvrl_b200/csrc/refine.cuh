@@ -59,7 +59,7 @@ struct RfInst {
      * out: the final queue followed by the best-so-far snapshot (nodes in array order) and the singletons, compacted */
     uint32_t initNodeOff, initSingleOff, outNodeOff, outSingleOff;
     unsigned long long clk[2][12];      /* cycles per phase, [small | large cluster]: pick, direction, stage, project, sort, weights, sweep, pairs, argmin+queue, count */
-    uint32_t mtInit, mtWaves;           /* k_refine_mt: the object's queue has been set up / control passes so far */
+    uint32_t mtInit, mtWaves, mtFinishing;   /* k_refine_mt: the object's queue has been set up / control passes so far / converged, waiting for splits in flight */
 };
 
 struct RfScratch {                      /* per CTA */
@@ -427,12 +427,16 @@ struct MtNode {                         /* 64 bytes */
 struct MtPools {
     MtNode *nodes; HeapEntry *heap, *snap; uint32_t *singles;   /* per object: [nodeCap], [heapCap], [heapCap], [nodeCap] */
     uint32_t *outstanding;                                      /* per object: split tasks in flight */
+    uint32_t *ctl;                                              /* per object: 0 no control pass scheduled, 1 scheduled or running, 2 ... and asked to run again */
+    uint32_t *waitNode;                                         /* per object: the cluster whose result the last control pass stopped at (MT_NONE / MT_ANY) */
     unsigned long long *slots; uint32_t qmask;                  /* ticket ring: (generation << 40) | (type << 39) | (object << 24) | node */
     uint32_t *ctr;                                              /* [0] next ticket to draw, [1] next ticket to fill, [2] objects not done */
     uint32_t nodeCap, heapCap;
     unsigned long long *clk;                                    /* [grid][32] profile counters */
 };
 
+#define MT_NONE 0xffffffffu
+#define MT_ANY 0xfffffffeu
 __device__ __forceinline__ unsigned long long mt_word(uint32_t ticket, uint32_t qmask, uint32_t type, uint32_t obj, uint32_t node) {
     const unsigned long long gen = (unsigned long long) (ticket / (qmask + 1u)) + 1ull;
     return (gen << 40) | ((unsigned long long) type << 39) | ((unsigned long long) obj << 24) | (unsigned long long) node;
@@ -443,6 +447,16 @@ __device__ __forceinline__ void mt_push(const MtPools &mp, uint32_t type, uint32
     const uint32_t t0 = atomicAdd(mp.ctr + 1, cnt);
     for (uint32_t j = 0; j < cnt; j++)
         atomicExch(mp.slots + ((t0 + j) & mp.qmask), mt_word(t0 + j, mp.qmask, type, obj, nodeIds ? nodeIds[j] : 0u));
+}
+
+/* thread 0: make sure a control pass of object o runs after this point (at most one is scheduled or running at any time) */
+__device__ __forceinline__ void mt_request_control(const MtPools &mp, uint32_t o) {
+    for (;;) {
+        const uint32_t old = atomicCAS(mp.ctl + o, 0u, 1u);
+        if (old == 0u) { mt_push(mp, 1u, o, nullptr, 1u); return; }
+        if (old == 2u) return;
+        if (atomicCAS(mp.ctl + o, 1u, 2u) == 1u) return;
+    }
 }
 
 __global__ void __launch_bounds__(RF_THREADS, 1) k_refine_mt(float *XA, float *XB, const double *__restrict__ Vcol, RfInst *insts, uint32_t numInst,
@@ -549,8 +563,10 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_refine_mt(float *XA, float *X
                 __threadfence();
                 *(volatile uint32_t *) &nd->state = 2u;
                 __threadfence();
-                const uint32_t before = atomicSub(mp.outstanding + o, 1u);
-                if (before == 1u) mt_push(mp, 1u, o, nullptr, 1u);             /* the last result of the pass: back to control */
+                atomicSub(mp.outstanding + o, 1u);
+                __threadfence();                                                /* result and counter first, then look at the wait node */
+                const uint32_t wn = *(volatile uint32_t *) (mp.waitNode + o);
+                if (wn == taskNode || wn == MT_ANY) mt_request_control(mp, o);  /* the refinement is waiting for exactly this result */
             }
             RF_TICK(8);
             continue;
@@ -586,11 +602,13 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_refine_mt(float *XA, float *X
                 sm.sHeapCount = I->sHeapCount; sm.sSingleCount = I->sSingleCount; sm.sUnder = I->sUnder; sm.sInt = I->sInt;
                 sm.nearTies = I->nearTies; sm.splits = I->splits; sm.degenerate = I->degenerate;
             }
-            sm.err = RF_DONE; sm.done = 0; sm.stop = 0;
+            sm.err = RF_DONE; sm.done = 0; sm.stop = 0; sm.selCount = 0;
+            if (I->mtInit && I->mtFinishing) { sm.err = I->status; sm.done = 1; }    /* converged earlier: only the splits in flight were awaited */
+            *(volatile uint32_t *) (mp.waitNode + o) = MT_NONE;
             sm.mtClk[2]++;
         }
         __syncthreads();
-        for (;;) {                                                  /* consume one split per iteration */
+        for (; !sm.done;) {                                         /* consume one split per iteration */
             if (tid == 0) {
                 sm.snap = 0;
                 if (sm.heapCount == 0) sm.done = 1;
@@ -598,10 +616,21 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_refine_mt(float *XA, float *X
                 else {
                     const uint32_t topId = heap[0].id;
                     MtNode *nd = nodes + topId;
-                    if (*(volatile uint32_t *) &nd->state != 2u) sm.stop = 1;
+                    bool ready = *(volatile uint32_t *) &nd->state == 2u;
+                    if (!ready) {
+                        /* no result yet: name the cluster this object waits for, then look once more -- its split either sees the
+                         * name (and schedules the next control pass) or finished before, in which case the replay goes on */
+                        *(volatile uint32_t *) (mp.waitNode + o) = topId;
+                        __threadfence();
+                        ready = *(volatile uint32_t *) &nd->state == 2u;
+                        if (ready) *(volatile uint32_t *) (mp.waitNode + o) = MT_NONE;
+                    }
+                    if (!ready) sm.stop = 1;
                     else {
                         heap_pop(heap, sm.heapCount);                                   /* popMulti, 581-587 */
-                        const MtNode cn = *nd;
+                        MtNode cn;                                                      /* the result may have landed during this pass: read it from L2 */
+                        { const uint4 *src4 = reinterpret_cast<const uint4 *>(nd); uint4 *dst4 = reinterpret_cast<uint4 *>(&cn);
+                          for (int q4 = 0; q4 < 4; q4++) dst4[q4] = __ldcg(src4 + q4); }
                         sm.underVar -= cn.under; sm.intVar -= cn.integ;
                         const uint32_t begin = cn.begin & 0x7fffffffu, end = cn.end, srcBuf = cn.begin >> 31;
                         const uint32_t err = cn.flags >> 28;
@@ -663,9 +692,16 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_refine_mt(float *XA, float *X
                 const HeapEntry e = heap[i];
                 cand[i] = (*(volatile uint32_t *) &nodes[e.id].state == 0u) ? e.key : -INFINITY;
             }
-            if (tid == 0) sm.selCount = 0;
+            if (tid == 0) {
+                /* keep MT_K splits in flight; the top of the queue is handed out in any case (it is what the object waits for) */
+                const uint32_t inflight = *(volatile uint32_t *) (mp.outstanding + o);
+                sm.selCount = 0;
+                sm.pick[0] = inflight < MT_K ? MT_K - inflight : 0u;
+                if (sm.pick[0] == 0u && *(volatile uint32_t *) &nodes[heap[0].id].state == 0u) sm.pick[0] = 1u;
+            }
             __syncthreads();
-            for (uint32_t round = 0; round < MT_K; round++) {
+            const uint32_t budget = sm.pick[0];
+            for (uint32_t round = 0; round < budget; round++) {
                 float bk = -INFINITY; uint32_t bidx = 0xffffffffu;
                 for (uint32_t i = tid; i < m; i += RF_THREADS) { const float k = cand[i]; if (k > bk) { bk = k; bidx = i; } }
 #pragma unroll
@@ -686,12 +722,25 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_refine_mt(float *XA, float *X
             }
             __syncthreads();
             if (tid < sm.selCount) *(volatile uint32_t *) &nodes[sm.sel[tid]].state = 1u;
-            if (tid == 0 && sm.selCount == 0) { sm.err = RF_ERR_SPLIT; sm.done = 1; }      /* cannot happen: the top has no result */
+            __syncthreads();
+        }
+        if (sm.done) {
+            /* converged (or failed): splits handed out ahead of time may still be running and write into this object's lists; the
+             * final list is assembled by the pass that finds none in flight */
+            if (tid == 0) {
+                sm.stop = 0;
+                if (*(volatile uint32_t *) (mp.outstanding + o) != 0u) {
+                    *(volatile uint32_t *) (mp.waitNode + o) = MT_ANY;
+                    __threadfence();
+                    if (*(volatile uint32_t *) (mp.outstanding + o) != 0u) sm.stop = 1;
+                    else *(volatile uint32_t *) (mp.waitNode + o) = MT_NONE;
+                }
+            }
             __syncthreads();
         }
         /* ---- write the state back ---- */
         for (uint32_t i = tid; i < min(sm.heapCount, (uint32_t) RF_HEAP_CAP); i += RF_THREADS) heapG[i] = sm.heap[i];
-        const bool finished = sm.done != 0;
+        const bool finished = sm.done != 0 && sm.stop == 0;
         if (finished) {
             /* the list of the sequential algorithm: every leaf's range in the order its parent's sort left (copy 1 -> copy 0) */
             for (uint32_t i = warp; i < sm.heapCount; i += RF_WARPS) {
@@ -717,7 +766,8 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_refine_mt(float *XA, float *X
             for (uint32_t i = tid; i < sm.singleCount; i += RF_THREADS) scr.outSingles[sm.end + i] = singles[i];
         }
         if (tid == 0) {
-            if (finished) { I->outNodeOff = sm.begin; I->outSingleOff = sm.end; I->status = sm.err; }
+            if (finished) { I->outNodeOff = sm.begin; I->outSingleOff = sm.end; }
+            if (sm.done) { I->status = sm.err; I->mtFinishing = 1; }
             I->underVar = sm.underVar; I->intVar = sm.intVar; I->bestConstant = sm.bestConstant;
             I->heapCount = sm.heapCount; I->nodeCount = sm.nodeCount; I->singleCount = sm.singleCount;
             I->sHeapCount = sm.sHeapCount; I->sSingleCount = sm.sSingleCount; I->sUnder = sm.sUnder; I->sInt = sm.sInt;
@@ -726,11 +776,18 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_refine_mt(float *XA, float *X
         }
         __syncthreads();
         if (tid == 0) {
-            if (finished) { __threadfence(); atomicSub(mp.ctr + 2, 1u); }
+            if (finished) { __threadfence(); atomicSub(mp.ctr + 2, 1u); }        /* the control role is never released: no further pass */
             else {
+                if (sm.selCount) {
+                    __threadfence();
+                    atomicAdd(mp.outstanding + o, sm.selCount);                 /* before the tasks can complete */
+                    mt_push(mp, 0u, o, sm.sel, sm.selCount);
+                }
                 __threadfence();
-                atomicExch(mp.outstanding + o, sm.selCount);
-                mt_push(mp, 0u, o, sm.sel, sm.selCount);
+                if (atomicCAS(mp.ctl + o, 1u, 0u) != 1u) {                      /* a result the object waits for arrived meanwhile: run again */
+                    atomicExch(mp.ctl + o, 1u);
+                    mt_push(mp, 1u, o, nullptr, 1u);
+                }
             }
             sm.mtClk[0] += (unsigned long long) (clock64() - c0);
         }
