@@ -404,13 +404,17 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_refine(float *XA, float *XB, 
  *                      that the refinement never gets to consume leaves the cluster's own data untouched.
  *   control(o)      -- one CTA replays the refinement of object o as far as the results reach: pop the top of the queue, apply
  *                      its split exactly like k_refine's thread 0 (same heap operations, same fp32 sums, same convergence
- *                      test, snapshots), until the top is a cluster without a result.  It then hands out the MT_K unsplit
- *                      clusters with the largest keys (the ones the queue will pop next, unless their own children overtake
- *                      them) as split tasks.  When the last of them completes, its CTA enqueues the next control(o).
+ *                      test, snapshots), until the top is a cluster without a result.  It names that cluster in waitNode[o]
+ *                      and tops the splits in flight up to MT_K with the unsplit clusters of the largest keys (the ones the
+ *                      queue will pop next, unless their own children overtake them).  The split that delivers the awaited
+ *                      result schedules the next control(o); ctl[o] keeps at most one pass scheduled or running (a request
+ *                      that arrives during a pass makes it run again).  Publication and re-check are ordered by fences on both
+ *                      sides (store, fence, load), so a result cannot slip between "not ready" and "waiting for it".
  * Only clusters that are IN the queue are split ahead of time (never the children of a cluster whose split has not been
  * consumed), which is what makes two copies of lists and columns enough: the destination range of such a split holds the dead
- * source of the cluster's parent.  At the end the leaves whose list sits in copy 1 are copied into copy 0, which reproduces
- * the in-place list of the sequential algorithm (the list inside a cluster is what the consumed splits left, 641-642).
+ * source of the cluster's parent.  At the end -- once no split of the object is in flight any more -- the leaves whose list
+ * sits in copy 1 are copied into copy 0, which reproduces the in-place list of the sequential algorithm (the list inside a
+ * cluster is what the consumed splits left, 641-642).
  * No co-residency is assumed: a CTA only waits for a ticket it has drawn, and tickets are filled by running CTAs.
  * ------------------------------------------------------------------------------------------------------------------- */
 #define MT_K 32
