@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import small_case, setup
+from conftest import ROOT, small_case, setup
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -172,3 +172,48 @@ def test_golden_fixture_regression(pkg, orc):
     assert np.array_equal(cl["vrls"], g["cluster_vrls"])
     np.testing.assert_allclose(cl["weights"], g["cluster_weights"], rtol=1e-5)
     np.testing.assert_allclose(o.render(), g["image"], rtol=1e-4, atol=1e-9)
+
+
+def test_counter_stream_known_answers(tmp_path):
+    """include/alvrl_rng.h is shared by the oracle and the product, so a change of the stream would go unnoticed by the parity
+    tests: its keys (object stream, per-cluster sub-stream of Clustering::split), bits and uniforms are pinned by the vectors
+    of tests/golden/rng_kat.txt, recomputed here by an independent restatement and by the header itself (compiled with gcc)."""
+    import subprocess
+    M = 0xFFFFFFFF
+
+    def mix32(x):
+        x &= M
+        x ^= x >> 16; x = (x * 0x7feb352d) & M
+        x ^= x >> 15; x = (x * 0x846ca68b) & M
+        x ^= x >> 16
+        return x
+
+    def key(seed, domain, a, b):
+        h = mix32((seed & M) ^ ((domain * 0x9e3779b9) & M))
+        h = mix32(h ^ (seed >> 32))
+        h = mix32((h + a * 0x85ebca6b + 0x165667b1) & M)
+        return mix32(h ^ ((b * 0xc2b2ae35 + 0x27d4eb2f) & M))
+
+    def node_key(k, begin, end):
+        h = mix32(k ^ ((begin * 0x85ebca6b + 0x2545f491) & M))
+        return mix32((h + end * 0xc2b2ae35 + 0x68e31da4) & M)
+
+    def bits(k, i):
+        return mix32((k + i * 0x9e3779b9) & M)
+
+    def uniform(k, i):
+        return float(np.array([(bits(k, i) >> 9) | 0x3f800000], dtype=np.uint32).view(np.float32)[0] - np.float32(1.0))
+
+    golden = open(os.path.join(ROOT, "tests", "golden", "rng_kat.txt")).read().split("\n")
+    rows = [l.split() for l in golden if l.strip()]
+    assert len(rows) == 9
+    for seed, a, k, nk, b1, u5, un0 in rows:
+        seed, a = int(seed), int(a)
+        kk = key(seed, 4, a * 37, 0)                              # ALVRL_RNG_CLUSTER = 4
+        nn = node_key(kk, a * 1000, a * 1000 + 17 + a)
+        assert (kk, nn, bits(nn, 1)) == (int(k, 16), int(nk, 16), int(b1, 16))
+        assert abs(uniform(kk, 5) - float(u5)) < 1e-9 and abs(uniform(nn, 0) - float(un0)) < 1e-9
+        assert 0.0 <= uniform(nn, 0) < 1.0
+    exe = str(tmp_path / "rng_kat")
+    subprocess.check_call(["gcc", "-O1", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "golden", "make_rng_kat.c"), "-o", exe])
+    assert subprocess.check_output([exe]).decode().split() == open(os.path.join(ROOT, "tests", "golden", "rng_kat.txt")).read().split()
