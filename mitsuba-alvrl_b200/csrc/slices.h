@@ -13,6 +13,8 @@
 #include <cmath>
 #include <cstdint>
 #include <limits>
+#include <future>
+#include <memory>
 #include "host_sampler.h"
 #include "../../include/alvrl.h"
 
@@ -33,7 +35,7 @@ class SliceTree {
      * an index array and gathers through it), so that every pass over a node streams contiguous memory */
     struct Rec { float v[6]; uint32_t idx; };
     const std::vector<P3> &pos, &dir;
-    std::vector<Rec> rec;
+    std::unique_ptr<Rec[]> rec;                                    /* not value-initialised: every record is written before it is read */
     static bool finite3(const P3 &p) { return std::isfinite(p.x) && std::isfinite(p.y) && std::isfinite(p.z); }
 
     /* findSplitPoint, 1451-1487: midpoint of the largest extent; x wins only if strictly larger than y and z */
@@ -52,7 +54,7 @@ class SliceTree {
         if (lo + 1 == hi) { n.diag = 0; n.dim = 0; n.split = std::numeric_limits<float>::quiet_NaN(); return n; }
         const float inf = std::numeric_limits<float>::infinity();
         float mn[6] = {inf, inf, inf, inf, inf, inf}, mx[6] = {-inf, -inf, -inf, -inf, -inf, -inf};
-        const Rec *r = rec.data();
+        const Rec *r = rec.get();
         for (uint32_t i = lo; i < hi; i++)
             for (int c = 0; c < 6; c++) {
                 const float x = r[i].v[c];
@@ -78,7 +80,7 @@ public:
     std::vector<uint32_t> build(uint32_t targetNumSlices, std::vector<SliceInfo> &slices) {
         const uint32_t n = (uint32_t) pos.size();
         std::vector<uint32_t> toSlice(n, ALVRL_NO_SLICE);
-        rec.resize(n);
+        rec.reset(new Rec[n]);
         for (uint32_t i = 0; i < n; i++) { Rec &r = rec[i]; r.v[0] = pos[i].x; r.v[1] = pos[i].y; r.v[2] = pos[i].z; r.v[3] = dir[i].x; r.v[4] = dir[i].y; r.v[5] = dir[i].z; r.idx = i; }
         /* move the misses (non-finite gather points) to the front, 1206-1221 */
         uint32_t firstGood = 0;
@@ -95,7 +97,7 @@ public:
             heap.pop_back();
             /* Hoare partition, 1368-1393; isLarger, 1420-1430: component `dim` of (position, scaled normal) against the split */
             const int dim = top.dim; const float split = top.split;
-            Rec *r = rec.data();
+            Rec *r = rec.get();
             size_t lo = top.lo, hi = top.hi - 1, i = lo - 1, j = hi + 1;
             for (;;) {
                 do { i++; } while (!(r[i].v[dim] > split || i == hi));
@@ -103,8 +105,17 @@ public:
                 if (i >= j) break;
                 std::swap(r[i], r[j]);
             }
-            heap.push_back(makeNode(top.lo, (uint32_t) j + 1)); std::push_heap(heap.begin(), heap.end());
-            heap.push_back(makeNode((uint32_t) j + 1, top.hi)); std::push_heap(heap.begin(), heap.end());
+            /* the two children's extrema are independent scans: a large node's second child is scanned by another thread */
+            const uint32_t mid = (uint32_t) j + 1;
+            if (top.hi - top.lo >= (1u << 16)) {
+                std::future<Node> right = std::async(std::launch::async, [this, mid, &top]() { return makeNode(mid, top.hi); });
+                const Node left = makeNode(top.lo, mid);
+                heap.push_back(left); std::push_heap(heap.begin(), heap.end());
+                heap.push_back(right.get()); std::push_heap(heap.begin(), heap.end());
+            } else {
+                heap.push_back(makeNode(top.lo, mid)); std::push_heap(heap.begin(), heap.end());
+                heap.push_back(makeNode(mid, top.hi)); std::push_heap(heap.begin(), heap.end());
+            }
         }
         for (const Node &nd : heap) {                                         /* slice id = heap array position, 1400-1417 */
             SliceInfo si;
@@ -112,7 +123,7 @@ public:
             for (uint32_t k = nd.lo; k < nd.hi; k++) { const uint32_t g = rec[k].idx; si.pixels[k - nd.lo] = g; toSlice[g] = (uint32_t) slices.size(); }
             slices.push_back(std::move(si));
         }
-        std::vector<Rec>().swap(rec);
+        rec.reset();
         return toSlice;
     }
 };
