@@ -9,6 +9,7 @@
  */
 #include "oracle_prep.hpp"
 #include <thread>
+#include <set>
 #include <memory>
 #include <chrono>
 #include <cstdio>
@@ -29,6 +30,7 @@ struct Ctx {
     std::vector<uint32_t> pixelToSlice; std::vector<SliceData> slices; bool haveSlices = false;
     std::vector<uint32_t> rowOffset, rowPixel; bool haveRows = false;
     std::vector<Float> sliceUndersampling; Float globalPixelUndersampling = -1;
+    std::vector<std::set<std::pair<uint32_t, Float>>> localities;      // m_localities: neighbour slices (index, 6-D distance), Preprocessor.h
     std::vector<VrlContribution> R; bool haveR = false;
     std::vector<std::vector<uint32_t>> selectedVrls; std::vector<std::vector<Float>> clusterWeight;
     std::vector<uint32_t> gcVrls, fallBackVrls; std::vector<Float> gcWeight, fallBackWeight; bool haveClusters = false;
@@ -123,7 +125,6 @@ int orc_create(int, const alvrl_params *p, void **out) {
     if (p->volVolSamples != 0 && p->volVolSamples < 2) return seterr(ALVRL_ERR_ARG, "Need at least 2 volVolSamples for variance estimate");
     if (p->volSurfSamples != 0 && p->volSurfSamples < 2) return seterr(ALVRL_ERR_ARG, "Need at least 2 volSurfSamples for variance estimate");
     if (p->targetNumSlices < 1) return seterr(ALVRL_ERR_ARG, "Invalid target number of slices!");
-    if (p->neighbourWeight > 0) return seterr(ALVRL_ERR_UNSUPPORTED, "neighbourWeight > 0 is not restated");
     Ctx *c = new Ctx();
     c->P = *p;
     c->mainSampler.reset(c->newStream());
@@ -252,6 +253,39 @@ int orc_get_gather_points(void *h, float *pos, float *dir) {
 }
 
 /* Preprocessor::sampleSliceMapping, Preprocessor.cpp:1502-1525 */
+/* Preprocessor::buildLocalities, Preprocessor.cpp:1241-1293: the neighbourCount slices closest in the 6-D (position centroid,
+ * scaled direction centroid) distance, found by a replace-the-current-maximum scan.  Kept as written: `maxInd` is NOT reset
+ * between slices (1263), and a slot that no distance ever beat (NaN centroids of one-pixel slices, SURVEY B-list) keeps the
+ * entry of the previous slice.  The reference's two scratch arrays are uninitialised VLAs; they start zeroed / infinite here.
+ * With neighbourCount = 0 the reference reads distances[0] of an empty array (undefined, result unused): nothing to restate. */
+static void buildLocalities(Ctx *c) {
+    const uint32_t S = (uint32_t) c->slices.size(), nc = (uint32_t) std::max(0, c->P.neighbourCount);
+    c->localities.assign(S, {});
+    auto dist = [&](uint32_t i, uint32_t j) {
+        return SliceBuilder::sliceDistance(c->slices[i].positionCentroid, c->slices[i].directionCentroid,
+                                           c->slices[j].positionCentroid, c->slices[j].directionCentroid);
+    };
+    if (S <= nc) {                                                          // 1245-1258: everybody is everybody's neighbour
+        for (uint32_t i = 0; i < S; i++) for (uint32_t j = 0; j < S; j++) if (i != j) c->localities[i].insert(std::make_pair(j, dist(i, j)));
+        return;
+    }
+    if (nc == 0) return;
+    std::vector<Float> distances(nc, std::numeric_limits<Float>::infinity()); std::vector<uint32_t> indices(nc, 0);
+    uint32_t maxInd = 0;
+    for (uint32_t i = 0; i < S; i++) {
+        for (uint32_t j = 0; j < nc; j++) distances[j] = std::numeric_limits<Float>::infinity();
+        for (uint32_t j = 0; j < S; j++) {
+            if (i == j) continue;
+            const Float d = dist(i, j);
+            if (d < distances[maxInd]) {
+                distances[maxInd] = d; indices[maxInd] = j;
+                for (uint32_t k = 0; k < nc; k++) if (distances[k] > distances[maxInd]) maxInd = k;
+            }
+        }
+        for (uint32_t x = 0; x < nc; x++) c->localities[i].insert(std::make_pair(indices[x], distances[x]));
+    }
+}
+
 int orc_sample_slice_mapping(void *h) {
     Ctx *c = (Ctx *) h;
     if (!c->haveSlices) return seterr(ALVRL_ERR_STATE, "build_slices first");
@@ -268,6 +302,7 @@ int orc_sample_slice_mapping(void *h) {
         c->sliceUndersampling[i] = ((Float) px.size()) / c->slices[i].gatherIdx.size();
         totalRep += px.size(); totalPix += c->slices[i].gatherIdx.size();
     }
+    buildLocalities(c);                                                     // 1517
     c->globalPixelUndersampling = ((Float) totalRep) / totalPix;
     c->haveRows = true; c->haveR = false; c->haveClusters = false;
     c->stats.msSliceMapping = (float) (now_ms() - t0);
@@ -396,6 +431,8 @@ int orc_build_clusters(void *h) {
         c->nearTieSplits += gcl.nearTieSplits;
     }
     /* refinePerSlice, 199-283 */
+    if (c->P.neighbourWeight > 0 && (std::min(c->sliceBegin, S) != 0 || std::min(c->sliceEnd, S) != S))
+        fail("neighbourWeight > 0: the local matrices take rows of neighbour slices, R must hold all slices (no slice range)");
     c->selectedVrls.assign(S, {}); c->clusterWeight.assign(S, {});
     bool sfmt = c->P.rngMode == ALVRL_RNG_MODE_SFMT;
     int w = sfmt ? std::max(1, c->P.workerCount) : std::max(1, c->threads);
@@ -408,12 +445,36 @@ int orc_build_clusters(void *h) {
         Sampler *s = (w > 1 || !sfmt) ? clones[id].get() : smp;
         uint32_t s0 = ((uint64_t) id * S) / w, s1 = ((uint64_t) (id + 1) * S) / w;
         for (uint32_t i = s0; i < s1; i++) {
-            /* refineSlice, 254-283; getLocalMatrix with neighbourWeight <= 0, 779-794 */
+            /* refineSlice, 254-283; getLocalMatrix, 779-827 */
             MatView L; L.nVrls = N;
             uint32_t nr = c->rowOffset[i + 1] - c->rowOffset[i];
             for (uint32_t r = c->rowOffset[i]; r < c->rowOffset[i + 1]; r++) L.rows.push_back(&c->R[(size_t) r * N]);
-            std::vector<double> lw(nr);
-            for (uint32_t k = 0; k < nr; k++) lw[k] = 1.0 / nr;
+            std::vector<double> lw;
+            if (c->P.neighbourWeight <= 0) {
+                lw.assign(nr, 0.0);
+                for (uint32_t k = 0; k < nr; k++) lw[k] = 1.0 / nr;
+            } else {
+                /* the rows of the neighbour slices follow (set order: by slice index), weighted by inverse distance; the slice's
+                 * own rows share (1 - neighbourWeight) of the total.  Float arithmetic as written (796-820): 1.0 / dist is a
+                 * double quotient stored to Float, everything else is Float, the final weights are widened to double. */
+                const auto &loc = c->localities[i];
+                std::vector<Float> neighbourWeights(loc.size());
+                Float summedNeighbourWeight = 0;
+                size_t j = 0;
+                for (auto it = loc.begin(); it != loc.end(); ++it, ++j) {
+                    for (uint32_t r = c->rowOffset[it->first]; r < c->rowOffset[it->first + 1]; r++) L.rows.push_back(&c->R[(size_t) r * N]);
+                    neighbourWeights[j] = (Float) (1.0 / it->second);
+                    summedNeighbourWeight += neighbourWeights[j];
+                }
+                const Float sliceWeight = summedNeighbourWeight * (1 - c->P.neighbourWeight) / c->P.neighbourWeight;
+                const Float normalization = 1 / (sliceWeight + summedNeighbourWeight);
+                for (uint32_t k = 0; k < nr; k++) lw.push_back(sliceWeight * normalization / nr);
+                j = 0;
+                for (auto it = loc.begin(); it != loc.end(); ++it, ++j) {
+                    const uint32_t nrj = c->rowOffset[it->first + 1] - c->rowOffset[it->first];
+                    for (uint32_t k = 0; k < nrj; k++) lw.push_back(neighbourWeights[j] * normalization / nrj);
+                }
+            }
             s->setContext(ALVRL_RNG_CLUSTER, i, 0);
             Clustering cl(globalVrlsPerCluster, L, lw, c->sliceUndersampling[i], c->P.depthCorrection, &cs[id]);
             if (!c->P.localRefinement) { cl.sampleRepresentatives(c->selectedVrls[i], c->clusterWeight[i], s); continue; }

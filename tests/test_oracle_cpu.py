@@ -217,3 +217,36 @@ def test_counter_stream_known_answers(tmp_path):
     exe = str(tmp_path / "rng_kat")
     subprocess.check_call(["gcc", "-O1", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "golden", "make_rng_kat.c"), "-o", exe])
     assert subprocess.check_output([exe]).decode().split() == open(os.path.join(ROOT, "tests", "golden", "rng_kat.txt")).read().split()
+
+
+def test_neighbour_slices_in_local_matrices(pkg, orc):
+    """buildLocalities / getLocalMatrix with neighbourWeight > 0 (Preprocessor.cpp:1241-1293, 796-820) are restated in the
+    oracle (the CUDA path still refuses them): rows of the neighbour slices join a slice's local matrix with inverse-distance
+    weights.  No reference output pins this (parity unpinned), so the test states what must hold: valid clusters,
+    reproducible, unused when neighbourWeight = 0, different from the default when used, and the reference's failure mode
+    (no neighbours to weigh: the locality weights are not normalised)."""
+    scene, vrls, params = small_case(pkg, "C1", 32, 32, 64, seed=3, targetNumSlices=10)
+
+    def run(**kw):
+        o = setup(orc.Oracle(**dict(params, **kw)), scene, vrls)
+        o.build_slices(); o.prepass()
+        return o, o.clusters()
+
+    _, base = run()
+    _, unused = run(neighbourCount=3, neighbourWeight=0.0)
+    for k in ("offset", "vrls", "weights"):
+        assert np.array_equal(base[k], unused[k])
+    o1, nb1 = run(neighbourCount=3, neighbourWeight=0.3)
+    _, nb2 = run(neighbourCount=3, neighbourWeight=0.3)
+    for k in ("offset", "vrls", "weights"):
+        assert np.array_equal(nb1[k], nb2[k])
+    S, _ = o1.num_slices()
+    assert len(nb1["offset"]) == S + 1 and (np.diff(nb1["offset"]) >= 1).all()
+    assert (nb1["vrls"] < o1.N).all() and (nb1["weights"] >= 1 - 1e-5).all() and np.isfinite(nb1["weights"]).all()
+    assert not (np.array_equal(nb1["offset"], base["offset"]) and np.array_equal(nb1["vrls"], base["vrls"]))
+    img = o1.render()
+    assert np.isfinite(img).all() and (img >= 0).all() and img.mean() > 0
+    _, everybody = run(neighbourCount=64, neighbourWeight=0.5)                  # more neighbours asked for than slices exist
+    assert len(everybody["offset"]) == S + 1 and np.isfinite(everybody["weights"]).all()
+    with pytest.raises(Exception):
+        run(neighbourCount=0, neighbourWeight=0.5)
