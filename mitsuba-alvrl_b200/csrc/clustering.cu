@@ -911,7 +911,30 @@ struct Workspace {
                 if (in->numClusters() >= in->targetClusters || in->numMulti() <= 0) in->done = true;
             }
         }
-        if (deviceRounds && !getenv("ALVRL_HOST_ROUNDS")) refineDevice(which);
+        auto afterSplit = [](Inst *in) {
+            if (in->adaptive) {
+                const float curr = in->convergenceConstant();                   /* 436-452 */
+                if (curr < in->bestConstant) { in->snapshot(); in->bestConstant = curr; }
+                if (in->lowerBound() >= in->bestConstant || in->numMulti() == 0) { in->restore(); in->done = true; }
+            } else if (!(in->numClusters() < in->targetClusters && in->numMulti() > 0)) in->done = true;
+        };
+        if (deviceRounds && !getenv("ALVRL_HOST_ROUNDS")) {
+            /* EXPERIMENT, off unless ALVRL_HYBRID_ROUNDS=<columns> is set (not yet measured on the GPU): while the cluster at the
+             * top of an object's queue is larger than that, it is split by the batched grid-wide kernels of the rounds -- every
+             * SM works on it -- instead of by one CTA of k_refine_mt, whose chain of large splits bounds the kernel when a GPU
+             * holds few objects.  Both paths compute the same split, so the result does not depend on it. */
+            const char *hy = getenv("ALVRL_HYBRID_ROUNDS");
+            const uint32_t hybrid = hy ? (uint32_t) std::max(0, atoi(hy)) : 0u;
+            for (; hybrid;) {
+                std::vector<Inst *> round;
+                for (Inst *in : which)
+                    if (!in->done && !in->pq.empty() && in->pq.front().end - in->pq.front().begin > hybrid) round.push_back(in);
+                if (round.empty()) break;
+                splitRoundDevice(round);
+                for (Inst *in : round) afterSplit(in);
+            }
+            refineDevice(which);
+        }
         for (;;) {
             /* one runnable instance per sampler group: a shared sequential stream (SFMT) serialises its instances */
             std::vector<Inst *> round; std::vector<int> groupsBusy;
@@ -923,13 +946,7 @@ struct Workspace {
             }
             if (round.empty()) break;
             if (deviceRounds) splitRoundDevice(round); else splitRound(round);
-            for (Inst *in : round) {
-                if (in->adaptive) {
-                    const float curr = in->convergenceConstant();               /* 436-452 */
-                    if (curr < in->bestConstant) { in->snapshot(); in->bestConstant = curr; }
-                    if (in->lowerBound() >= in->bestConstant || in->numMulti() == 0) { in->restore(); in->done = true; }
-                } else if (!(in->numClusters() < in->targetClusters && in->numMulti() > 0)) in->done = true;
-            }
+            for (Inst *in : round) afterSplit(in);
         }
         if (!lazyMirrors) syncLists(which);
         for (Inst *in : which) in->refining = false;
