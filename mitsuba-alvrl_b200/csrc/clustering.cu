@@ -660,6 +660,7 @@ struct Inst {                                                                  /
     ClusterNode cur{0, 0, 0, 0}; uint32_t vrl1 = 0, vrl2 = 0;
     uint32_t nearTies = 0;
     bool listsStale = false;      /* the device holds a newer permutation than `vrls` */
+    bool currentIsBest = true;    /* adaptive refinement: the current state is the best-so-far snapshot */
 
     uint32_t numMulti() const { return (uint32_t) pq.size(); }
     uint32_t numClusters() const { return (uint32_t) (pq.size() + singletons.size()); }
@@ -905,7 +906,7 @@ struct Workspace {
                 if (in->numMulti() <= 0) { in->done = true; continue; }
                 if (in->unclusteredVariance() == 0) { in->done = true; in->failed = true; continue; }
                 in->bestConstant = in->convergenceConstant();
-                in->snapshot();
+                in->snapshot(); in->currentIsBest = true;
             } else {                                                            /* refineFixedDepth, 387-399 */
                 in->targetClusters = (uint32_t) (0.5 + in->numVrlsTotal / undersampling);
                 if (in->numClusters() >= in->targetClusters || in->numMulti() <= 0) in->done = true;
@@ -914,7 +915,8 @@ struct Workspace {
         auto afterSplit = [](Inst *in) {
             if (in->adaptive) {
                 const float curr = in->convergenceConstant();                   /* 436-452 */
-                if (curr < in->bestConstant) { in->snapshot(); in->bestConstant = curr; }
+                in->currentIsBest = curr < in->bestConstant;
+                if (in->currentIsBest) { in->snapshot(); in->bestConstant = curr; }
                 if (in->lowerBound() >= in->bestConstant || in->numMulti() == 0) { in->restore(); in->done = true; }
             } else if (!(in->numClusters() < in->targetClusters && in->numMulti() > 0)) in->done = true;
         };
@@ -928,7 +930,9 @@ struct Workspace {
             for (; hybrid;) {
                 std::vector<Inst *> round;
                 for (Inst *in : which)
-                    if (!in->done && !in->pq.empty() && in->pq.front().end - in->pq.front().begin > hybrid) round.push_back(in);
+                    if (!in->done && !in->pq.empty() &&
+                        (in->pq.front().end - in->pq.front().begin > hybrid || (in->adaptive && !in->currentIsBest)))
+                        round.push_back(in);                /* the device kernel starts from a state that is its own best-so-far snapshot */
                 if (round.empty()) break;
                 splitRoundDevice(round);
                 for (Inst *in : round) afterSplit(in);
