@@ -10,8 +10,11 @@ isotropic medium, 1024x1024, 100k VRLs, volVolSamples = volSurfSamples = 4):
            whole job, VRL set / BVH / medium resident in HBM when the timed region starts, framebuffer left on the device.
 `e2e`    : the same metric through the C ABI with HOST buffers: every step uploads the VRL set (alvrl_set_vrls from host
            arrays) and reads the W x H x 3 float image back (alvrl_render into a host buffer).
-Multi-GPU: slices are sharded over the ranks (VRLs, BVH, medium replicated); the only exchanges are an N-byte all-reduce
-of the zero / non-zero column flags and the framebuffer reduce over NCCL.  Total work is fixed -> "scaling": "strong".
+Multi-GPU: slices are sharded over the ranks (VRLs, BVH, medium replicated) by the library's own group entry point
+(alvrl_group_frame, csrc/group.cu); the only exchanges are an N-byte all-reduce of the zero / non-zero column flags and the
+framebuffer reduce over NCCL.  Total work is fixed -> "scaling": "strong".  torch.distributed carries the NCCL unique id and
+the max-over-ranks timing only.
+`parity` : the benchmarked (fast) and the strict flavour against the strict CPU oracle on a bounded sample of this workload.
 """
 import argparse
 import json
@@ -81,6 +84,9 @@ def parse():
     ap.add_argument("--vrls", type=int, default=None)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the bounded cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity sample (rank 0, N=1 only)")
+    ap.add_argument("--no-strict", action="store_true", help="skip the extra frame in the strict math flavour")
+    ap.add_argument("--parity-seconds", type=float, default=8.0, help="target CPU time of the parity sample")
     return ap.parse_args()
 
 
@@ -88,11 +94,18 @@ def workload(pkg, a):
     scene, vrls, params = pkg.scenes.make_config(a.config, width=a.width, height=a.height, n_vrls=a.vrls)
     cfg = pkg.scenes.CONFIGS[a.config]
     W, H = scene["camera"]["width"], scene["camera"]["height"]
-    desc = {"workload": f"{a.config}: Cornell box, homogeneous isotropic medium, {W}x{H}, {len(vrls[0])} VRLs, "
+    hg = cfg.get("hg") is not None
+    med = scene["medium"]
+    if med["type"] == "grid":
+        what = f"Cornell box, heterogeneous grid-volume medium ({'x'.join(str(d) for d in med['density'].shape)} procedural density, method=simpson)"
+    elif a.config == "C4":
+        what = f"{len(scene['tris'])}-triangle icosphere occluder scene in homogeneous fog inside closed Cornell walls (BVH traversal path)"
+    else:
+        what = "Cornell box, homogeneous medium, " + (f"HG phase g={cfg['hg']}" if hg else "isotropic phase")
+    desc = {"workload": f"{a.config}: {what}, {W}x{H}, {len(vrls[0])} VRLs, "
                         f"volVolSamples={params['volVolSamples']}, volSurfSamples={params['volSurfSamples']}",
             "slices": params.get("targetNumSlices", 100), "pixel_undersampling": 64,
-            "l2_note": "inputs larger than L2: R alone is rows x VRLs x 8 B (13.1 GB at C2) and is rewritten every step"}
-    hg = cfg.get("hg") is not None
+            "l2_note": f"inputs larger than L2: R alone is rows x VRLs x 8 B ({W * H / 64 * len(vrls[0]) * 8 / 1e9:.1f} GB) and is rewritten every step"}
     return scene, vrls, params, desc, hg
 
 
@@ -130,6 +143,47 @@ def cpu_baseline(pkg, scene, vrls, params, hg, seconds, full_desc):
     return {"value": pairs / dt, "unit": "VRL-segment contributions/s", "cores": cores, "kind": "port",
             "sample": f"R rows of the first {n_slices} slice(s) = {rows} rows x the first {n_used} VRLs ({pairs:.3e} integrateVRL calls) "
                       f"of {full_desc}; oracle port built -O3 -march=x86-64-v3 -funsafe-math-optimizations, {cores} threads, {dt:.1f} s"}, dt
+
+
+def parity_sample(pkg, g, scene, vrls, params, seconds):
+    """The benchmarked kernels against the STRICT oracle (liborc.so: IEEE fp32, the parity definition -- not the
+    -funsafe-math speed build cpu_baseline times) on a bounded sample of this very workload: the R rows of slice 0 x a
+    prefix of the VRL set, same counter stream (an entry depends on (seed, row, vrl) only, so a VRL prefix reproduces the
+    corresponding columns of the full R).  Entries whose shadow rays are oracle-flagged grazing ties (occlusion decision
+    within 1e-5 of flipping) are counted separately; tests/test_c2_parity_gpu.py asserts the same quantities."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import orc  # the checker; runs after the timed region
+    cores = os.cpu_count() or 1
+    start, end, power, pc = vrls
+    n = int(min(len(start), max(2000, seconds * 0.6e6 * min(cores, 32) / 8 / 160)))       # ~0.6 M pairs/s per 8 threads, ~160 rows
+    o = orc.Oracle(fast=False, threads=cores, **params)
+    o.set_scene(scene); o.set_vrls(start[:n], end[:n], power[:n], pc)
+    o.set_graze_tolerance(1e-5)
+    o.build_slices(); o.set_slice_range(0, 1); o.sample_slice_mapping()
+    off, px = o.rep_pixels()
+    rows = int(off[1])
+    goff, gpx = g.rep_pixels()
+    if not np.array_equal(gpx[:rows], px[:rows]):
+        return {"error": "representative pixels of slice 0 differ from the oracle's"}
+    t0 = time.perf_counter(); o.build_R(); dt = time.perf_counter() - t0
+    Ro, graze = o.get_R(0, rows), o.R_graze(0, rows).astype(bool)
+    out = {"rows": rows, "vrls": n, "oracle": "liborc.so (IEEE fp32, -ffp-contract=off)", "oracle_seconds": round(dt, 1), "graze_tol": 1e-5,
+           "frac_graze_flagged": float(graze.mean())}
+    for name, strict in (("fast", 0), ("strict", 1)):
+        g._call("set_math_mode", pkg.binding.C.c_int(strict))
+        g.set_slice_range(0, 1); g.sample_slice_mapping(); g.build_R()
+        Rg = g.get_R(0, rows)[:, :n]
+        mo, mg = Ro[..., 0], Rg[..., 0]
+        floor = 1e-12 * np.abs(mo).max()
+        em = np.abs(mg - mo) / (np.abs(mo) + floor)
+        ev = np.abs(Rg[..., 1] - Ro[..., 1]) / (Ro[..., 1] + mo * mo + floor * floor)
+        bad = (em > 1e-4) | (ev > 1e-4)
+        out[name] = {"max_rel": float(em.max()), "max_rel_unflagged": float(em[~graze].max()), "p9999": float(np.quantile(em, 0.9999)),
+                     "median": float(np.median(em)), "frac_gt_1e-4": float(bad.mean()),
+                     "frac_gt_1e-4_unflagged": float((bad & ~graze).sum() / max(1, (~graze).sum()))}
+    g._call("set_math_mode", pkg.binding.C.c_int(0))
+    g.set_slice_range(0, 0xFFFFFFFF)
+    return out
 
 
 def run_reference(a):
@@ -175,8 +229,9 @@ def run_ours(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if multi:
-        os.environ["NCCL_DEBUG"] = os.environ.get("ALVRL_NCCL_DEBUG", "WARN")     # keep stdout to the one JSON line:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")                   # NCCL's version banner goes to stderr
+        # the caller's NCCL_DEBUG stays as it is (the driver reads the rank count from NCCL's INFO lines); NCCL's own output
+        # goes to stderr so that stdout carries the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     scene, vrls, params, desc, hg = workload(pkg, a)
@@ -184,8 +239,14 @@ def run_ours(a):
     g.set_scene(scene)
     g.set_vrls(*vrls)
     W, H, N = g.W, g.H, g.N
-    fb = torch.zeros((H, W, 4), dtype=torch.float32, device=dev)
     host_img = None
+    # the library's multi-GPU entry point (alvrl_group_*, csrc/group.cu): this rank's handle + an NCCL communicator built
+    # from a unique id that rank 0 creates and torch.distributed carries to the other ranks (plumbing only)
+    uid = [pkg.binding.Group.unique_id(pkg.api()) if (multi and rank == 0) else None]
+    if multi:
+        dist.broadcast_object_list(uid, src=0)
+    group = pkg.binding.Group.rank(g, rank, world, uid[0])
+    comm_ranks = group.comm_size()
 
     def barrier():
         torch.cuda.synchronize()
@@ -194,32 +255,15 @@ def run_ours(a):
         torch.cuda.synchronize()
 
     def frame(e2e):
-        """one step; returns (#integrateVRL evaluations of this rank, transport-kernel ms of this rank)"""
+        """one step = alvrl_group_frame: slices -> slice range of this rank -> slice mapping -> R -> column-flag all-reduce ->
+        clusters -> render -> framebuffer reduce; returns (#integrateVRL evaluations of this rank, kernel times, ...)"""
         nonlocal host_img
         s0 = g.stats()
         if e2e:
             g.set_vrls(*vrls)                                    # host -> device: the step's input (VRL set)
-        g.build_slices()
-        S, _ = g.num_slices()
-        if multi:                                                # contiguous slice ranges of about equal pixel counts
-            g.set_slice_range(*pkg.sharding.balanced_ranges(pkg.sharding.slice_sizes(g.pixel_to_slice(), S), world)[rank])
-        g.sample_slice_mapping()
-        g.build_R()
-        if multi:                                                # zero / non-zero columns over ALL rows: OR across ranks
-            fl = torch.from_numpy(g.column_nonzero()).to(dev)
-            dist.all_reduce(fl, op=dist.ReduceOp.MAX)
-            g.set_column_nonzero(fl.cpu().numpy())
-        g.build_clusters()
-        if e2e and not multi:
-            host_img = g.render()                                # device -> host: the step's result (image)
-        else:
-            fb.zero_()
-            torch.cuda.synchronize()
-            g.render_device(fb.data_ptr())
-            if multi:
-                dist.reduce(fb, dst=0, op=dist.ReduceOp.SUM)     # framebuffer gather over NCCL / NVLink
-            if e2e and rank == 0:
-                host_img = fb[..., :3].contiguous().cpu().numpy()
+        img = group.frame(want_image=e2e and rank == 0)          # e2e: device -> host read of the step's result on rank 0
+        if img is not None:
+            host_img = img
         s1 = g.stats()
         pairs = (s1.pairsPreprocess - s0.pairsPreprocess) + (s1.pairsRender - s0.pairsRender)
         return pairs, s1.msTransportKernelR, s1.msTransportKernelRender, s1.pairsPreprocess - s0.pairsPreprocess, \
@@ -291,10 +335,30 @@ def run_ours(a):
                 "phases_ms": {"slices": st.msSlices, "slice_mapping": st.msSliceMapping, "build_R": st.msBuildR, "clusters": st.msClusters,
                               "render_kernel": st.msTransportKernelRender},
                 "e2e_phases_ms": {"slices": st_e.msSlices, "build_R": st_e.msBuildR, "clusters": st_e.msClusters, "render_total": st_e.msRender},
-                "contributions_per_step": pairs / a.steps, "rows": st.numRows, "vrls": st.numVrls, "slices": st.numSlices}
+                "contributions_per_step": pairs / a.steps, "rows": st.numRows, "vrls": st.numVrls, "slices": st.numSlices,
+                "comm": {"library": "NCCL via alvrl_group_* (csrc/group.cu)" if multi else None, "nranks": comm_ranks},
+                "frame_definition": "buildSlices + sampleSliceMapping + Building R + buildClusters (per-slice refinement; the global/"
+                                    "fallback lists are only computed when a slice cannot be refined, as no slice of this workload "
+                                    "does) + clustered render of every pixel; k_primary (camera segments) is cached across steps "
+                                    "because camera and mesh do not change (65 us)"}
+        if world == 1 and not a.no_strict:
+            # the parity flavour of the same kernels (reference operation order, no FMA contraction, exp through double): one frame
+            g._call("set_math_mode", pkg.binding.C.c_int(1))
+            frame(False)
+            ms_s, pairs_s, _, kr_s, _, kpairs_s, st_s = timed(False, 1)
+            g._call("set_math_mode", pkg.binding.C.c_int(0))
+            line["strict_flavour"] = {"value": pairs_s / (ms_s * 1e-3), "frame_time_ms": ms_s, "build_R_kernel_ms": float(kr_s[0]),
+                                      "contributions_per_s_kernel": float(kpairs_s[0]) / (float(kr_s[0]) * 1e-3),
+                                      "render_kernel_ms": st_s.msTransportKernelRender}
+        if world == 1 and not a.no_parity:
+            try:
+                line["parity"] = parity_sample(pkg, g, scene, vrls, params, a.parity_seconds)
+            except Exception as e:                                  # the checker must never take the bench line down
+                line["parity"] = {"error": repr(e)}
         if not a.no_cpu_baseline and world == 1:
             line["cpu_baseline"], _ = cpu_baseline(pkg, scene, vrls, params, hg, a.cpu_seconds, desc["workload"])
         print(json.dumps(line))
+    group.close()
     if multi:
         dist.barrier()
         dist.destroy_process_group()

@@ -191,6 +191,31 @@ int alvrl_trace_rays(alvrl_handle h, const float *o_xyz, const float *d_xyz, con
 int alvrl_eval_transmittance(alvrl_handle h, const float *p1_xyz, const int32_t *p1OnSurface,
                              const float *p2_xyz, uint32_t n, float *T_rgb);
 
+/* ---- multi-GPU: slices sharded over the GPUs of one box (group.cu) ---------------------------------------------
+ * Replaces the reference's own parallel split of the path: contiguous slice ranges over Rbuilder / ClusterRefiner threads
+ * (vrlIntegrator.cpp:305-321,1048-1051; Preprocessor.cpp:212-228,738-741) and image blocks over render workers
+ * (src/librender/integrator.cpp:181-198).  VRLs, mesh, medium and camera are replicated (upload them to every member with
+ * the alvrl_set_* calls); a frame exchanges N bytes of column flags (all-reduce, MAX) and the framebuffer (reduce to rank 0)
+ * over NCCL.  Slice ranges are cut by pixel count.  globalCluster and the fallback clustering need all rows of R on one
+ * handle and are refused (ALVRL_ERR_UNSUPPORTED) while a handle owns a proper slice range. */
+typedef struct alvrl_group *alvrl_group_handle;
+#define ALVRL_GROUP_ID_BYTES 128
+const char *alvrl_group_last_error(void);
+/* one process, several GPUs: creates ndev handles (devices[i]) and their communicator */
+int  alvrl_group_create_local(int ndev, const int *devices, const alvrl_params *p, alvrl_group_handle *out);
+/* one process per GPU: rank 0 obtains an id, the host hands it to every rank, each rank wraps its own handle */
+int  alvrl_group_unique_id(uint8_t id[ALVRL_GROUP_ID_BYTES]);
+int  alvrl_group_create_rank(alvrl_handle h, int rank, int nranks, const uint8_t id[ALVRL_GROUP_ID_BYTES], alvrl_group_handle *out);
+int  alvrl_group_size(alvrl_group_handle g, int *world, int *local);
+int  alvrl_group_member(alvrl_group_handle g, int i, alvrl_handle *h, int *rank);
+int  alvrl_group_comm_size(alvrl_group_handle g, int *nranks);            /* ncclCommCount of the communicator */
+/* buildSlices -> range of each rank -> sampleSliceMapping -> "Building R" -> flag all-reduce -> buildClusters -> render ->
+ * framebuffer reduce.  rgb_host: W*H*3 floats [y][x][c], filled where rank 0 lives (NULL: leave it on the device). */
+int  alvrl_group_frame(alvrl_group_handle g, float *rgb_host);
+int  alvrl_group_get_range(alvrl_group_handle g, int i, uint32_t *sliceBegin, uint32_t *sliceEnd);
+int  alvrl_group_framebuffer(alvrl_group_handle g, int i, void **rgba_device);
+void alvrl_group_destroy(alvrl_group_handle g);
+
 #ifdef __cplusplus
 }
 #endif

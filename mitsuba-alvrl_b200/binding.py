@@ -317,3 +317,82 @@ class Integrator:
         out = np.zeros((len(p1), 3), np.float32)
         self._call("eval_transmittance", _p(p1), _p(s), _p(p2), C.c_uint32(len(p1)), _p(out))
         return out
+
+
+class Group:
+    """alvrl_group_*: the ranks' handles + their NCCL communicator; one call renders a frame with the slices sharded over
+    the ranks (include/alvrl.h, csrc/group.cu).  `Group.local(api, devices, **params)` drives several GPUs from this process;
+    `Group.rank(integrator, rank, world, unique_id)` is the one-process-per-GPU form."""
+    ID_BYTES = 128
+
+    def __init__(self, api, handle, members):
+        self.api, self.g, self.members = api, handle, members
+
+    @staticmethod
+    def _err(api, rc):
+        f = api.lib.alvrl_group_last_error
+        f.restype = C.c_char_p
+        raise AlvrlError(rc, f().decode())
+
+    @staticmethod
+    def unique_id(api):
+        buf = (C.c_uint8 * Group.ID_BYTES)()
+        rc = api.lib.alvrl_group_unique_id(buf)
+        if rc != 0:
+            Group._err(api, rc)
+        return bytes(buf)
+
+    @classmethod
+    def rank(cls, integrator, rank, world, unique_id=None):
+        api = integrator.api
+        g = C.c_void_p()
+        idbuf = (C.c_uint8 * cls.ID_BYTES).from_buffer_copy(unique_id) if unique_id is not None else None
+        rc = api.lib.alvrl_group_create_rank(integrator.h, C.c_int(rank), C.c_int(world), idbuf, C.byref(g))
+        if rc != 0:
+            cls._err(api, rc)
+        return cls(api, g, [integrator])
+
+    @classmethod
+    def local(cls, api, devices, **params):
+        p = api.default_params(**params)
+        g = C.c_void_p()
+        dev = (C.c_int * len(devices))(*devices)
+        rc = api.lib.alvrl_group_create_local(C.c_int(len(devices)), dev, C.byref(p), C.byref(g))
+        if rc != 0:
+            cls._err(api, rc)
+        members = []
+        for i in range(len(devices)):
+            it = Integrator.__new__(Integrator)
+            it.api, it.params, it.h, it.W, it.H, it.N = api, p, C.c_void_p(), 0, 0, 0
+            api.lib.alvrl_group_member(g, C.c_int(i), C.byref(it.h), None)
+            it.close = lambda: None                       # the group owns these handles
+            members.append(it)
+        return cls(api, g, members)
+
+    def comm_size(self):
+        n = C.c_int()
+        rc = self.api.lib.alvrl_group_comm_size(self.g, C.byref(n))
+        if rc != 0:
+            self._err(self.api, rc)
+        return n.value
+
+    def frame(self, want_image=True):
+        """one frame over all ranks; returns the H x W x 3 image where rank 0 lives (None elsewhere / when not wanted)"""
+        m = self.members[0]
+        out = np.zeros((m.H, m.W, 3), dtype=np.float32) if want_image else None
+        rc = self.api.lib.alvrl_group_frame(self.g, _p(out))
+        if rc != 0:
+            self._err(self.api, rc)
+        return out
+
+    def slice_range(self, i=0):
+        b, e = C.c_uint32(), C.c_uint32()
+        self.api.lib.alvrl_group_get_range(self.g, C.c_int(i), C.byref(b), C.byref(e))
+        return b.value, e.value
+
+    def close(self):
+        if self.g:
+            d = self.api.lib.alvrl_group_destroy
+            d.restype = None
+            d(self.g)
+            self.g = C.c_void_p()

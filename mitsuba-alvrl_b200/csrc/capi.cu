@@ -100,6 +100,7 @@ void ensure_primary(alvrl_ctx *c) {
     ensure_scene(c);
     if (!c->segsDirty && c->havePrimary) return;
     if (!c->haveCam || !c->haveMat) throw Error(ALVRL_ERR_STATE, "scene incomplete: set_camera / set_materials first");
+    for (uint32_t m : c->triMat) if (m >= c->matBits.size()) throw Error(ALVRL_ERR_ARG, "triangle material index out of range of set_materials");
     const uint32_t P = c->numPixels();
     c->dPixSegs.alloc(P); c->dHitPrim.alloc(P); c->dHitT.alloc(P);
     launch_primary(c->sceneDev, c->medium, c->cam, c->dTriVerts.p, c->dTriMat.p, c->dMatAlbedo.p, c->dMatBits.p, c->haveMedium,
@@ -258,6 +259,9 @@ int alvrl_create(int device, const alvrl_params *p, alvrl_handle *out) {
     if (p->neighbourWeight > 0) return fail(ALVRL_ERR_UNSUPPORTED, "neighbourWeight > 0 (neighbour slices in L_i) is outside the device path");
     if (p->Rsamples != 1) return fail(ALVRL_ERR_UNSUPPORTED, "Rsamples != 1 is outside the device path");
     if (p->depthCorrection != 1) return fail(ALVRL_ERR_UNSUPPORTED, "depthCorrection != 1 (ReplayableSampler pass) is outside the device path");
+    if (p->numVrlFalseColor || p->slicesFalseColor || p->convergenceFalseColor)
+        return fail(ALVRL_ERR_UNSUPPORTED, "false-colour debug outputs (vrlIntegrator.cpp:199-201) are not implemented on the device path");
+    if (p->maxPasses > 1) return fail(ALVRL_ERR_UNSUPPORTED, "maxPasses > 1: the device path renders one pass per VRL set (the caller accumulates passes)");
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0)
@@ -609,7 +613,14 @@ int alvrl_render_unclustered(alvrl_handle c, float *rgb) {
     API_END
 }
 
-int alvrl_set_slice_range(alvrl_handle c, uint32_t b, uint32_t e) { c->sliceBegin = b; c->sliceEnd = e; return ALVRL_OK; }
+int alvrl_set_slice_range(alvrl_handle c, uint32_t b, uint32_t e) {
+    if (b > e) return fail(ALVRL_ERR_ARG, "slice range: begin > end");
+    if (b != c->sliceBegin || e != c->sliceEnd) {      /* R rows and clusters outside the old range do not exist on this handle */
+        c->haveR = false; c->haveClusters = false; c->haveFallback = false; c->renderListsDirty = true;
+    }
+    c->sliceBegin = b; c->sliceEnd = e;
+    return ALVRL_OK;
+}
 
 int alvrl_render_device(alvrl_handle c, void *rgba, void *stream) {
     API_BEGIN
@@ -656,6 +667,9 @@ int alvrl_get_rep_pixels(alvrl_handle c, uint32_t *off, uint32_t *px) {
 }
 int alvrl_set_rep_pixels(alvrl_handle c, const uint32_t *off, const uint32_t *px, uint32_t ns) {
     if (!c->haveSlices || ns != c->slices.size()) return fail(ALVRL_ERR_STATE, "slice count mismatch");
+    if (off[0] != 0) return fail(ALVRL_ERR_ARG, "set_rep_pixels: sliceRowOffset[0] must be 0");
+    for (uint32_t i = 0; i < ns; i++) if (off[i + 1] < off[i]) return fail(ALVRL_ERR_ARG, "set_rep_pixels: sliceRowOffset must be non-decreasing");
+    for (uint32_t i = 0; i < off[ns]; i++) if (px[i] >= c->numPixels()) return fail(ALVRL_ERR_ARG, "set_rep_pixels: pixel index out of range");
     c->rowOffset.assign(off, off + ns + 1); c->rowPixel.assign(px, px + off[ns]);
     c->sliceUndersampling.resize(ns);
     size_t totalPix = 0;
@@ -672,6 +686,7 @@ int alvrl_get_R(alvrl_handle c, uint32_t r0, uint32_t r1, float *mv) {
     API_BEGIN
     use_device(c);
     if (!c->haveR) throw Error(ALVRL_ERR_STATE, "build_R first");
+    if (r0 > r1 || r1 > c->rowPixel.size()) throw Error(ALVRL_ERR_ARG, "get_R: row range out of bounds");
     const uint32_t N = (uint32_t) c->vrlHost.size();
     std::vector<float2> col(c->ldR);
     for (uint32_t v = 0; v < N; v++) {
@@ -697,7 +712,10 @@ int alvrl_get_cluster_counts(alvrl_handle c, uint32_t *off, uint32_t *ng, uint32
     API_BEGIN
     use_device(c);
     if (!c->haveClusters) throw Error(ALVRL_ERR_STATE, "build_clusters first");
-    if (!c->haveFallback && c->haveR) build_clusters_device(c, true);      /* lazily: global + fallback lists */
+    const uint32_t S_ = (uint32_t) c->slices.size();
+    const bool ranged = !(std::min(c->sliceBegin, S_) == 0 && std::min(c->sliceEnd, S_) == S_);
+    /* lazily: global + fallback lists (they span all rows of R: a handle that owns a slice range reports them empty) */
+    if (!c->haveFallback && c->haveR && !ranged) build_clusters_device(c, true);
     off[0] = 0;
     for (size_t i = 0; i < c->selectedVrls.size(); i++) off[i + 1] = off[i] + (uint32_t) c->selectedVrls[i].size();
     *ng = (uint32_t) c->gcVrls.size(); *nf = (uint32_t) c->fallBackVrls.size();
@@ -715,6 +733,10 @@ int alvrl_get_clusters(alvrl_handle c, uint32_t *vrls, float *weights, uint32_t 
 int alvrl_set_clusters(alvrl_handle c, const uint32_t *off, uint32_t ns, const uint32_t *vrls, const float *weights,
                        const uint32_t *fv, const float *fw, uint32_t nf) {
     if (!c->haveSlices || ns != c->slices.size()) return fail(ALVRL_ERR_STATE, "slice count mismatch");
+    if (off[0] != 0) return fail(ALVRL_ERR_ARG, "set_clusters: sliceOffset[0] must be 0");
+    for (uint32_t i = 0; i < ns; i++) if (off[i + 1] < off[i]) return fail(ALVRL_ERR_ARG, "set_clusters: sliceOffset must be non-decreasing");
+    for (uint32_t i = 0; i < off[ns]; i++) if (vrls[i] >= c->vrlHost.size()) return fail(ALVRL_ERR_ARG, "set_clusters: representative out of range");
+    for (uint32_t i = 0; i < nf; i++) if (fv[i] >= c->vrlHost.size()) return fail(ALVRL_ERR_ARG, "set_clusters: fallback representative out of range");
     c->selectedVrls.assign(ns, {}); c->clusterWeight.assign(ns, {});
     for (uint32_t i = 0; i < ns; i++) {
         c->selectedVrls[i].assign(vrls + off[i], vrls + off[i + 1]);

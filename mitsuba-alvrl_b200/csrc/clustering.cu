@@ -1382,6 +1382,13 @@ struct Workspace {
 
 } // namespace
 
+/* the same flags left in a caller-owned device buffer (N bytes), for the all-reduce of the multi-GPU path */
+void column_nonzero_into(alvrl_ctx *c, uint8_t *dFlags) {
+    const uint32_t N = (uint32_t) c->vrlHost.size(), G = (uint32_t) c->rowPixel.size();
+    k_total_contribution<<<(N + 127) / 128, 128, 0, c->stream>>>(c->dR.p, c->ldR, G, N, dFlags);
+    c->stats.kernelLaunches++;
+    ALVRL_CUDA(cudaGetLastError());
+}
 void column_nonzero_device(alvrl_ctx *c, std::vector<uint8_t> &flags) {
     const uint32_t N = (uint32_t) c->vrlHost.size(), G = (uint32_t) c->rowPixel.size();
     DevBuf<uint8_t> dNz; dNz.alloc(N);
@@ -1443,7 +1450,12 @@ void build_clusters_device(alvrl_ctx *c, bool needFallback) {
         globalSmp = c->globalStream.get();
     }
 
+    /* the global Clustering object spans ALL rows of R (1/G weights, Preprocessor.cpp:159-165): a handle that owns a slice
+     * range holds zeros in the other ranks' rows, so it must not build it (the group entry points gather what they need) */
+    const bool ranged = !(std::min(c->sliceBegin, S) == 0 && std::min(c->sliceEnd, S) == S);
     auto makeGlobalInst = [&](Inst &g) {
+        if (ranged) throw Error(ALVRL_ERR_UNSUPPORTED, "global / fallback clustering needs all rows of R, but this handle owns only a slice range "
+                                                        "(globalCluster, a slice with zero unclustered variance, or alvrl_get_clusters on a sharded handle)");
         g.id = ALVRL_RNG_GLOBAL_ID; g.r0 = 0; g.nr = G; g.rowBlocks = (G + CL_THREADS - 1) / CL_THREADS; g.lw = 1.0 / G;
         g.pixelUndersampling = c->globalPixelUndersampling; g.smp = globalSmp; g.group = -1;
     };

@@ -9,11 +9,18 @@
 #include "heap_order.h"
 #include "occluders.h"
 #include "occ_query.h"
+#include "sharding.h"
 #include <algorithm>
 #include <cstring>
 using namespace alvrl;
 
 extern "C" {
+
+/* slice range of one rank (group.cu uses the same function) */
+int alvrl_host_balanced_range(const uint32_t *sizes, uint32_t S, int world, int rank, uint32_t *b, uint32_t *e) {
+    balanced_slice_range(sizes, S, world, rank, *b, *e);
+    return 0;
+}
 
 int alvrl_host_sfmt_ulongs(uint64_t seed, uint32_t cloneDepth, uint32_t skip, uint64_t *out, uint32_t n) {
     Sfmt19937 g(seed);

@@ -136,5 +136,42 @@ int alvrl_plugin_create(void *props, void **inst, char *err, int errLen) {
     try { *inst = CreateInstance(*static_cast<mts::Properties *>(props)); return 0; }
     catch (const std::exception &e) { strncpy(err, e.what(), errLen - 1); err[errLen - 1] = 0; return -1; }
 }
+/* test hooks: a mock Scene assembled from flat arrays (the arrays stay owned by the caller), and one whole frame through
+ * the integrator's virtuals in the order the host calls them -- preprocess, prepass, render (scene.cpp:416-449,
+ * integrator.cpp:380-440) -- with a Film that hands the image back */
+void *alvrl_plugin_scene_new() { return new mts::Scene(); }
+void alvrl_plugin_scene_free(void *s) { delete static_cast<mts::Scene *>(s); }
+void alvrl_plugin_scene_add_mesh(void *s, const float *positions, uint32_t nv, const uint32_t *indices, uint32_t nt, const float *reflectance, int smooth) {
+    mts::TriMeshView m; m.positions = positions; m.vertexCount = nv; m.indices = indices; m.triangleCount = nt;
+    m.reflectance[0] = reflectance[0]; m.reflectance[1] = reflectance[1]; m.reflectance[2] = reflectance[2]; m.smooth = smooth != 0;
+    static_cast<mts::Scene *>(s)->meshes.push_back(m);
+}
+void alvrl_plugin_scene_add_medium_homogeneous(void *s, const float *sigmaA, const float *sigmaS, float weight, int phaseType, float g) {
+    mts::MediumView m; memset(&m, 0, sizeof(m));
+    m.homogeneous = true; m.mediumSamplingWeight = weight; m.phaseType = phaseType; m.g = g;
+    for (int k = 0; k < 3; k++) { m.sigmaA[k] = sigmaA[k]; m.sigmaS[k] = sigmaS[k]; }
+    static_cast<mts::Scene *>(s)->media.push_back(m);
+}
+void alvrl_plugin_scene_set_sensor(void *s, const float *sampleToCamera, const float *cameraToWorld, uint32_t w, uint32_t h, float nearClip,
+                                   float farClip, const float *position) {
+    mts::SensorView &v = static_cast<mts::Scene *>(s)->sensor;
+    memcpy(v.sampleToCamera, sampleToCamera, 16 * sizeof(float)); memcpy(v.cameraToWorld, cameraToWorld, 16 * sizeof(float));
+    v.width = w; v.height = h; v.nearClip = nearClip; v.farClip = farClip;
+    memcpy(v.position, position, 3 * sizeof(float));
+}
+int alvrl_plugin_render_frame(void *inst, void *scene, float *rgbOut, char *err, int errLen) {
+    struct CopyFilm : mts::Film {
+        float *dst; explicit CopyFilm(float *d) : dst(d) {}
+        void setImage(const float *rgb, uint32_t w, uint32_t h) override { memcpy(dst, rgb, (size_t) w * h * 3 * sizeof(float)); }
+    } film(rgbOut);
+    mts::Scene *sc = static_cast<mts::Scene *>(scene);
+    mts::Integrator *it = static_cast<vrlIntegrator *>(inst);
+    try {
+        sc->film = &film;
+        it->preprocess(sc); it->prepass(sc); it->render(sc);
+        sc->film = nullptr;
+        return 0;
+    } catch (const std::exception &e) { sc->film = nullptr; strncpy(err, e.what(), errLen - 1); err[errLen - 1] = 0; return -1; }
+}
 int alvrl_plugin_unqueried(void *props) { return (int) static_cast<mts::Properties *>(props)->getUnqueried().size(); }
 }

@@ -38,6 +38,7 @@ struct Ctx {
     const float *tape = nullptr; uint64_t tapeLen = 0; std::vector<float> tapeStore;
     int threads = 1;
     bool noVisibility = false;
+    Float grazeTol = 0; std::vector<uint8_t> Rgraze;                   // test instrumentation: fragile visibility decisions per R entry
     uint32_t sliceBegin = 0, sliceEnd = 0xffffffffu;
     alvrl_stats stats;
     std::vector<uint8_t> columnFlagsOverride;      // all-reduced zero / non-zero column flags (multi-rank runs)
@@ -54,6 +55,7 @@ struct Ctx {
     IntegratorCore core() {
         IntegratorCore c; c.scene = &scene; c.medium = &medium; c.volVolSamples = P.volVolSamples;
         c.volSurfSamples = P.volSurfSamples; c.shortVrls = P.shortVrls != 0; c.noVisibility = noVisibility;
+        c.grazeTol = grazeTol;
         return c;
     }
 };
@@ -97,7 +99,9 @@ void buildRow(Ctx *c, IntegratorCore &core, Sampler *sampler, uint32_t row, VrlC
             Float normalization = 1.0 / c->particleCount;
             Float contribution, variance;
             if (s == 0) sampler->setContext(ALVRL_RNG_R, row, v);
+            core.grazed = false;
             core.integrateVRL(ray, its, c->vrls[v], sampler, &contribution, &variance, Spec(1.0f));
+            if (core.grazed && !c->Rgraze.empty()) c->Rgraze[(size_t) row * N + v] = 1;
             out[v].mean += contribution * normalization;
             out[v].var += variance * normalization * normalization;
         }
@@ -134,6 +138,15 @@ int orc_create(int, const alvrl_params *p, void **out) {
 void orc_destroy(void *h) { delete (Ctx *) h; }
 int orc_set_threads(void *h, int n) { ((Ctx *) h)->threads = std::max(1, n); return ALVRL_OK; }
 int orc_set_no_visibility(void *h, int on) { ((Ctx *) h)->noVisibility = on != 0; return ALVRL_OK; }
+/* test instrumentation: build_R also records which entries had a shadow ray whose occlusion decision is within tol of flipping */
+int orc_set_graze_tolerance(void *h, float tol) { ((Ctx *) h)->grazeTol = tol; return ALVRL_OK; }
+int orc_get_R_graze(void *h, uint32_t r0, uint32_t r1, uint8_t *out) {
+    Ctx *c = (Ctx *) h;
+    if (!c->haveR || c->Rgraze.empty()) return seterr(ALVRL_ERR_STATE, "set_graze_tolerance and build_R first");
+    size_t N = c->vrls.size();
+    memcpy(out, &c->Rgraze[(size_t) r0 * N], (size_t) (r1 - r0) * N);
+    return ALVRL_OK;
+}
 
 int orc_set_mesh(void *h, const float *v, uint32_t nv, const uint32_t *tris, uint32_t nt, const uint32_t *mat) {
     Ctx *c = (Ctx *) h;
@@ -317,6 +330,7 @@ static int buildR_impl(Ctx *c, std::vector<float> *recordTape) {
     tracePrimary(c);
     uint32_t N = c->vrls.size(), G = c->rowPixel.size(), S = c->slices.size();
     c->R.assign((size_t) G * N, VrlContribution{0, 0});
+    if (c->grazeTol > 0) c->Rgraze.assign((size_t) G * N, 0); else c->Rgraze.clear();
     uint32_t sb = std::min(c->sliceBegin, S), se = std::min(c->sliceEnd, S);
     uint64_t shadow = 0;
     if (c->tape) {

@@ -310,6 +310,22 @@ struct TriAccel {                                                          // tr
         c_nu = c[v] / denom; c_nv = -c[u] / denom;
         return 0;
     }
+    /* test instrumentation, not part of the reference: plane parameter and barycentrics without the accept tests */
+    bool planeHit(const Ray &ray, Float &u, Float &v, Float &t) const {
+        Float o_u, o_v, o_k, d_u, d_v, d_k;
+        switch (k) {
+            case 0: o_u = ray.o[1]; o_v = ray.o[2]; o_k = ray.o[0]; d_u = ray.d[1]; d_v = ray.d[2]; d_k = ray.d[0]; break;
+            case 1: o_u = ray.o[2]; o_v = ray.o[0]; o_k = ray.o[1]; d_u = ray.d[2]; d_v = ray.d[0]; d_k = ray.d[1]; break;
+            case 2: o_u = ray.o[0]; o_v = ray.o[1]; o_k = ray.o[2]; d_u = ray.d[0]; d_v = ray.d[1]; d_k = ray.d[2]; break;
+            default: return false;
+        }
+        t = (n_d - o_u * n_u - o_v * n_v - o_k) / (d_u * n_u + d_v * n_v + d_k);
+        if (!std::isfinite(t)) return false;
+        const Float hu = o_u + t * d_u - a_u, hv = o_v + t * d_v - a_v;
+        u = hv * b_nu + hu * b_nv;
+        v = hu * c_nu + hv * c_nv;
+        return true;
+    }
     bool rayIntersect(const Ray &ray, Float mint, Float maxt, Float &u, Float &v, Float &t) const { // triaccel.h:97-158
         Float o_u, o_v, o_k, d_u, d_v, d_k;
         switch (k) {
@@ -390,6 +406,24 @@ struct Scene {
             }
         }
         return found;
+    }
+    /* Test instrumentation, not part of the reference: is the occlusion decision of this shadow ray within `tol` of
+     * flipping (the "documented grazing-hit ties" of north_star)?  A triangle is hit LOOSELY when the accept tests pass
+     * with every bound relaxed by tol (barycentric units; tol x segment length on t) and ROBUSTLY when they pass with
+     * every bound tightened; the decision is fragile when some triangle is hit loosely and none robustly. */
+    bool shadowDecisionFragile(const Ray &ray, Float tol) const {
+        Float mint = ray.mint, maxt = ray.maxt;
+        if (mint == Epsilon) mint *= std::max(std::max(std::abs(ray.o.x), std::abs(ray.o.y)), std::abs(ray.o.z));
+        const Float dt = tol * std::max(maxt, (Float) 1e-3f);
+        const Float dlo = mint > 0 ? std::min(dt, 0.25f * mint) : dt;        /* a surface origin sits at t = 0 << mint by design */
+        bool loose = false, robust = false;
+        for (size_t i = 0; i < accel.size(); i++) {
+            Float u, v, t;
+            if (!accel[i].planeHit(ray, u, v, t)) continue;
+            if (t >= mint - dlo && t <= maxt + dt && u >= -tol && v >= -tol && u + v <= 1 + tol) loose = true;
+            if (t >= mint + dlo && t <= maxt - dt && u >= tol && v >= tol && u + v <= 1 - tol) robust = true;
+        }
+        return loose && !robust;
     }
     /* ShapeKDTree::rayIntersect(ray, its) + fillIntersectionRecord<true> (skdtree.cpp:112-142, skdtree.h:343-428) */
     bool rayIntersect(const Ray &ray, Intersection &its) {
@@ -590,12 +624,18 @@ struct IntegratorCore {
     Scene *scene; Medium *medium; int volVolSamples, volSurfSamples; bool shortVrls;
     uint64_t shadowRays = 0;
     bool noVisibility = false;   // test hook: skip the occlusion query (T = medium only)
+    Float grazeTol = 0;          // test hook: > 0 -> `grazed` collects "a shadow ray's decision was within grazeTol of flipping"
+    bool grazed = false;
 
     Spec transUV(const V3 &a, bool aSurf, const V3 &b) {
         shadowRays++;
         if (noVisibility) {
             V3 d = b - a; Float remaining = d.length(); d = d / remaining;
             return medium->evalTransmittance(Ray(a, d, 0, remaining));
+        }
+        if (grazeTol > 0 && !grazed) {
+            V3 d = b - a; Float remaining = d.length();
+            if (remaining > 0) { d = d / remaining; grazed = scene->shadowDecisionFragile(Ray(a, d, aSurf ? Epsilon : 0, remaining), grazeTol); }
         }
         return evalTransmittance(*scene, *medium, a, aSurf, b, false);
     }

@@ -48,6 +48,17 @@ class Oracle(binding.Integrator):
     def set_no_visibility(self, on):
         self._call("set_no_visibility", C.c_int(int(on)))
 
+    def set_graze_tolerance(self, tol):
+        self._call("set_graze_tolerance", C.c_float(tol))
+
+    def R_graze(self, r0=0, r1=None):
+        """uint8 [rows, N]: 1 where some shadow ray of the entry had an occlusion decision within the tolerance of flipping"""
+        S, G = self.num_slices()
+        r1 = G if r1 is None else r1
+        out = np.zeros((r1 - r0, self.N), np.uint8)
+        self._call("get_R_graze", C.c_uint32(r0), C.c_uint32(r1), binding._p(out))
+        return out
+
     def gather_points(self):
         P = self.W * self.H
         pos, d = np.zeros((P, 3), np.float32), np.zeros((P, 3), np.float32)

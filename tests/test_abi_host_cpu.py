@@ -118,3 +118,20 @@ def test_host_slices_all_misses_and_singletons(host_lib):
     pos[:] = 0.25; d[:] = 0.5
     host_lib.alvrl_host_slices(*args())
     assert ns.value == 1 and (p2s == 0).all()
+
+
+def test_balanced_slice_ranges_match_the_python_sharding_helper(host_lib, pkg):
+    """csrc/sharding.h (used by alvrl_group_frame) cuts the same contiguous, covering ranges as sharding.balanced_ranges"""
+    rng = np.random.default_rng(0)
+    for S, world in ((100, 1), (100, 2), (100, 8), (7, 8), (512, 8), (3, 2), (1, 4)):
+        sizes = rng.integers(1, 20000, S).astype(np.uint32)
+        if S > 5:
+            sizes[rng.integers(0, S, 3)] = 0
+        want = pkg.sharding.balanced_ranges(sizes, world)
+        got = []
+        for r in range(world):
+            b, e = C.c_uint32(), C.c_uint32()
+            host_lib.alvrl_host_balanced_range(sizes.ctypes.data_as(C.c_void_p), C.c_uint32(S), C.c_int(world), C.c_int(r), C.byref(b), C.byref(e))
+            got.append((b.value, e.value))
+        assert got == want, (S, world)
+        assert got[0][0] == 0 and got[-1][1] == S and all(got[i][1] == got[i + 1][0] for i in range(world - 1))

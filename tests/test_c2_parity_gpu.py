@@ -1,0 +1,142 @@
+"""GPU suite, part 2: the BENCHMARKED kernels (fast flavour, alvrl_set_math_mode(0)) against the oracle at north_star's
+tolerance -- per-entry reduced-matrix contributions within 1e-4 relative in fp32, excluding documented grazing-hit ties --
+on the BASELINE configuration itself (C2: 1024x1024, 100k VRLs, 4 + 4 samples) and on the other config shapes.
+
+Grazing ties: the oracle flags an R entry when one of its shadow rays has an occlusion decision within 1e-5 (barycentric
+units; 1e-5 x segment length along the ray) of flipping (oracle_core.hpp: Scene::shadowDecisionFragile, test
+instrumentation).  Flagged entries are excluded from the 1e-4 assertion and their fraction is stated."""
+import numpy as np
+import pytest
+
+from conftest import small_case, setup
+
+pytestmark = pytest.mark.gpu
+
+GRAZE_TOL = 1e-5
+
+
+def _gpu(pkg, strict, **params):
+    g = pkg.integrator(0, **params)
+    g._call("set_math_mode", pkg.binding.C.c_int(1 if strict else 0))
+    return g
+
+
+def r_entry_errors(Rg, Ro):
+    """relative error of the mean (floor 1e-12 x max) and of the variance on the scale of the second moment the clustering
+    consumes (Preprocessor.cpp:996), exactly as tests/test_parity_gpu.py::_check_R"""
+    mg, mo, vg, vo = Rg[..., 0], Ro[..., 0], Rg[..., 1], Ro[..., 1]
+    floor = 1e-12 * np.abs(mo).max()
+    em = np.abs(mg - mo) / (np.abs(mo) + floor)
+    ev = np.abs(vg - vo) / (vo + mo * mo + floor * floor)
+    return em, ev
+
+
+def parity_report(Rg, Ro, graze, tol=1e-4):
+    em, ev = r_entry_errors(Rg, Ro)
+    bad = (em > tol) | (ev > tol)
+    clean = ~graze.astype(bool)
+    return dict(entries=int(bad.size), max_rel=float(em.max()), p9999=float(np.quantile(em, 0.9999)), median=float(np.median(em)),
+                frac_gt_tol=float(bad.mean()), frac_graze=float(graze.mean()), bad_clean=int((bad & clean).sum()),
+                frac_gt_tol_clean=float((bad & clean).sum() / max(1, clean.sum())),
+                max_rel_clean=float(em[clean].max()) if clean.any() else 0.0)
+
+
+def _first_slices_R(pkg, orc, name, strict, n_slices, **kw):
+    scene, vrls, params = pkg.scenes.make_config(name, **kw)
+    g = setup(_gpu(pkg, strict, **params), scene, vrls)
+    o = setup(orc.Oracle(**params), scene, vrls)
+    o.set_graze_tolerance(GRAZE_TOL)
+    for it in (g, o):
+        it.build_slices(); it.set_slice_range(0, n_slices); it.sample_slice_mapping()
+    off, px = g.rep_pixels()
+    assert np.array_equal(px, o.rep_pixels()[1])
+    rows = int(off[n_slices])
+    g.build_R(); o.build_R()
+    return g.get_R(0, rows), o.get_R(0, rows), o.R_graze(0, rows)
+
+
+@pytest.mark.parametrize("strict", [False, True], ids=["fast", "strict"])
+def test_c2_first_slice_R_vs_oracle_1e4(pkg, orc, strict):
+    """C2 itself: the R rows of slice 0 (157 rows x 100 000 VRLs = 15.7 M integrateVRL calls, 8 shadow rays each) on the same
+    counter stream; every entry whose visibility decisions are not oracle-flagged grazing ties is within 1e-4."""
+    Rg, Ro, graze = _first_slices_R(pkg, orc, "C2", strict, 1)
+    rep = parity_report(Rg, Ro, graze)
+    print(("strict" if strict else "fast"), "C2 slice 0:", rep)
+    assert Rg.shape[1] == 100_000 and Rg.shape[0] >= 100
+    assert rep["frac_graze"] < 2e-3
+    # entries outside 1e-4 that the oracle did not flag: none expected; bound = 2 per million
+    assert rep["frac_gt_tol_clean"] <= 2e-6, rep
+    assert rep["median"] < 1e-5
+
+
+@pytest.mark.parametrize("strict", [False, True], ids=["fast", "strict"])
+@pytest.mark.parametrize("name,kw", [("C5", dict(width=96, height=54, n_vrls=600)), ("C3", dict(width=48, height=48, n_vrls=96, grid=32)),
+                                     ("C4", dict(width=64, height=36, n_vrls=128, occluders=12))])
+def test_other_config_shapes_R_vs_oracle_1e4(pkg, orc, name, kw, strict):
+    """HG phase with 16 + 4 samples (C5), grid medium with the Simpson march (C3), the BVH traversal path with icosphere
+    occluders (C4): both flavours against the oracle at 1e-4."""
+    scene, vrls, params = small_case(pkg, name, kw["width"], kw["height"], kw["n_vrls"], grid=kw.get("grid"), occluders=kw.get("occluders"))
+    params.update(targetNumSlices=8)
+    g = setup(_gpu(pkg, strict, **params), scene, vrls)
+    o = setup(orc.Oracle(**params), scene, vrls)
+    o.set_graze_tolerance(GRAZE_TOL)
+    for it in (g, o):
+        it.build_slices(); it.sample_slice_mapping(); it.build_R()
+    rep = parity_report(g.get_R(), o.get_R(), o.R_graze())
+    print(name, ("strict" if strict else "fast"), rep)
+    assert rep["frac_gt_tol_clean"] <= 1e-5, rep
+    assert rep["frac_graze"] < 1e-2
+
+
+def _rel_rmse(a, b):
+    """mtsutil rms, relative variant (src/utils/rms.cpp:88-110): gamma 1, pixels whose reference is zero are masked"""
+    m = b > 0
+    return float(np.sqrt(np.mean(((a[m] - b[m]) / b[m]) ** 2)))
+
+
+def test_c1_full_frame_clustered_image_rel_rmse_fast(pkg, orc):
+    """G6 on the full pipeline of the benchmarked flavour: C1 (256 x 256, 1 000 VRLs), slices -> R -> clusters -> clustered
+    render, free running.  The GPU image (seed 3) against an oracle image (seed 2) may not be further away, in the
+    rms-style relative RMSE, than 1.5 x the distance between two oracle images (seeds 1 and 2) -- the Monte-Carlo noise floor
+    of the estimator + clustering itself."""
+    scene, vrls, params = pkg.scenes.make_config("C1")
+    imgs = []
+    for seed in (1, 2):
+        o = setup(orc.Oracle(seed=seed, **params), scene, vrls)
+        o.build_slices(); o.prepass()
+        imgs.append(o.render())
+    g = setup(_gpu(pkg, False, seed=3, **params), scene, vrls)
+    g.build_slices(); g.prepass()
+    ig = g.render()
+    floor = _rel_rmse(imgs[0], imgs[1])
+    mine = _rel_rmse(ig, imgs[1])
+    print(f"C1 clustered frame: relRMSE(gpu fast, oracle) = {mine:.4f}, oracle-vs-oracle noise floor = {floor:.4f}")
+    assert np.array_equal(ig.sum(-1) == 0, imgs[1].sum(-1) == 0)           # the same pixels are black (misses)
+    assert mine <= 1.5 * floor + 1e-6, (mine, floor)
+
+
+def test_c2_crop_clustered_image_vs_oracle_clusters_fast(pkg, orc):
+    """C2 itself, render side: the fast render kernel with the GPU's own clusters (built from its own fast R for the first
+    two slices), compared per pixel on 1 500 pixels of those slices with the oracle evaluating the SAME representative
+    lists on the same counter stream: 1e-3 relative per pixel (a pixel sums ~1 000 terms; 1e-4 per term)."""
+    scene, vrls, params = pkg.scenes.make_config("C2")
+    g = setup(_gpu(pkg, False, **params), scene, vrls)
+    o = setup(orc.Oracle(**params), scene, vrls)
+    for it in (g, o):
+        it.build_slices(); it.set_slice_range(0, 2); it.sample_slice_mapping()
+    g.build_R(); g.build_clusters()
+    cl = g.clusters()
+    o.set_clusters(cl)
+    p2s = g.pixel_to_slice()
+    assert np.array_equal(p2s, o.pixel_to_slice())
+    rng = np.random.default_rng(5)
+    px = rng.choice(np.flatnonzero(p2s < 2), 1500, replace=False).astype(np.uint32)
+    io = o.render_pixels(px)
+    ig = g.render()                                                        # [H, W, 3]; pixel index = y + H * x
+    H = g.H
+    igp = ig[px % H, px // H]
+    floor = 1e-6 * io.max()
+    err = np.abs(igp - io) / (io + floor)
+    print(f"C2 crop: {len(px)} pixels, K per slice {np.diff(cl['offset'])[:2]}, max rel err {err.max():.2e}, frac > 1e-3: {(err > 1e-3).mean():.2e}")
+    assert (err > 1e-3).mean() < 2e-3
+    assert np.median(err) < 1e-5

@@ -322,19 +322,31 @@ def test_clusters_with_zero_columns_and_fallback(pkg, orc):
 
 
 def test_end_to_end_strict_image_and_clusters(pkg, orc):
+    """free-running strict flavour, whole prepass on both sides.  R differs by ulps only, so every split decision agrees
+    unless the oracle itself flags a split as a near-tie (best vs second-best split variance within 1e-6 relative, G5): then
+    -- and only then -- the clusters may differ, and the images are compared as two draws of the same estimator against the
+    oracle-vs-oracle noise floor (G6) instead of per pixel."""
     g, o = _pair(pkg, orc, "C1", 64, 64, 150, strict=True, seed=12)
     for it in (g, o):
         it.build_slices(); it.prepass()
     cg, co = g.clusters(), o.clusters()
     same = np.array_equal(cg["offset"], co["offset"]) and np.array_equal(cg["vrls"], co["vrls"])
     ig, io = g.render(), o.render()
-    if same:                         # R differs by ulps only, so normally every split decision agrees
+    near_ties = o.cluster_diag()["near_tie_splits"]
+    print("clusters identical:", same, "oracle near-tie splits:", near_ties, "per-slice K:", np.diff(cg["offset"])[:8])
+    if same:
         floor = 1e-6 * io.max()
         err = np.abs(ig - io) / (io + floor)
         assert (err > 1e-3).mean() < 1e-3
-    else:                            # a near-tie flipped: the images are two draws of the same estimator
-        assert abs(ig.mean() - io.mean()) / io.mean() < 0.2
-    print("clusters identical:", same, "per-slice K:", np.diff(cg["offset"])[:8])
+    else:
+        assert near_ties > 0, "clusters differ from the oracle's although the oracle flagged no near-tie split"
+        def rel_rmse(a, b):
+            m = b > 0
+            return float(np.sqrt(np.mean(((a[m] - b[m]) / b[m]) ** 2)))
+        scene, vrls, params = small_case(pkg, "C1", 64, 64, 150, seed=13)
+        o2 = setup(orc.Oracle(**params), scene, vrls)
+        o2.build_slices(); o2.prepass()
+        assert rel_rmse(ig, io) <= 1.5 * rel_rmse(o2.render(), io) + 1e-6
 
 
 def test_multi_handle_slice_ranges_compose(pkg, orc):

@@ -1,0 +1,123 @@
+"""GPU suite, part 3: the drop-in boundary end to end.  vrl.so -- the `integrator type="vrl"` plugin shim -- is driven the
+way Mitsuba drives the reference plugin: CreateInstance(props with vrlFile) -> preprocess(scene) -> prepass -> render
+(src/integrators/vrl/vrlIntegrator.cpp:237-356, src/librender/scene.cpp:416-449, integrator.cpp:380-440), and its image
+must equal the image of the same calls made directly on the C ABI.  The VRL set arrives through the reference's ASCII
+file format (VRL.h:43-54, 120-128), which is the plugin's only ingestion path (alvrl_load_vrl_file)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _plugin():
+    lib = C.CDLL(os.path.join(ROOT, "mitsuba-alvrl_b200", "vrl.so"))
+    lib.alvrl_plugin_props_new.restype = C.c_void_p
+    lib.alvrl_plugin_scene_new.restype = C.c_void_p
+    return lib
+
+
+def _by_material(scene):
+    """one TriMesh per material, as Mitsuba shapes carry one BSDF each; returns the regrouped flat scene too"""
+    meshes, verts, tris, mats = [], scene["verts"], scene["tris"], scene["tri_material"]
+    for m in range(len(scene["albedo"])):
+        t = np.ascontiguousarray(tris[mats == m], dtype=np.uint32)
+        if len(t):
+            meshes.append((np.ascontiguousarray(verts, dtype=np.float32), t, np.ascontiguousarray(scene["albedo"][m], dtype=np.float32), m))
+    flat = dict(scene)
+    nv = len(verts)
+    flat["verts"] = np.concatenate([mv for mv, _, _, _ in meshes])
+    flat["tris"] = np.concatenate([t + i * nv for i, (_, t, _, _) in enumerate(meshes)])
+    flat["tri_material"] = np.concatenate([np.full(len(t), i, np.uint32) for i, (_, t, _, _) in enumerate(meshes)])
+    flat["albedo"] = np.stack([a for _, _, a, _ in meshes])
+    flat["mat_bits"] = np.ones(len(meshes), np.uint32)
+    return meshes, flat
+
+
+@pytest.mark.parametrize("clustered", [True, False], ids=["clustered", "unclustered"])
+def test_plugin_frame_equals_direct_abi(pkg, tmp_path, clustered):
+    lib = _plugin()
+    scene, vrls, params = pkg.scenes.make_config("C1", width=64, height=48, n_vrls=180)
+    start, end, power, pc = vrls
+    # a few lines the reader must filter (VRL.h:148-158): zero power, zero length
+    start = np.concatenate([start, [[0.5, 0.5, 0.5], [0.2, 0.2, 0.2]]]).astype(np.float32)
+    end = np.concatenate([end, [[0.6, 0.5, 0.5], [0.2, 0.2, 0.2]]]).astype(np.float32)
+    power = np.concatenate([power, [[0, 0, 0], [1, 1, 1]]]).astype(np.float32)
+    path = str(tmp_path / "cornell.vrl")
+    pkg.scenes.write_vrl_file(path, start, end, power)
+    meshes, flat = _by_material(scene)
+    xml = dict(params, targetNumSlices=12, seed=5, vrlFile=path)
+    if not clustered:
+        xml.update(globalCluster=False, localRefinement=False)
+
+    # --- through the plugin ---
+    p = C.c_void_p(lib.alvrl_plugin_props_new())
+    for k, v in xml.items():
+        if isinstance(v, bool):
+            lib.alvrl_plugin_props_set_bool(p, k.encode(), int(v))
+        elif isinstance(v, int):
+            lib.alvrl_plugin_props_set_int(p, k.encode(), v)
+        elif isinstance(v, float):
+            lib.alvrl_plugin_props_set_float(p, k.encode(), C.c_float(v))
+        else:
+            lib.alvrl_plugin_props_set_string(p, k.encode(), str(v).encode())
+    inst = C.c_void_p()
+    err = C.create_string_buffer(1024)
+    assert lib.alvrl_plugin_create(p, C.byref(inst), err, 1024) == 0, err.value
+    assert lib.alvrl_plugin_unqueried(p) == 0
+    sc = C.c_void_p(lib.alvrl_plugin_scene_new())
+    fp, up = C.POINTER(C.c_float), C.POINTER(C.c_uint32)
+    for v, t, a, _ in meshes:
+        lib.alvrl_plugin_scene_add_mesh(sc, v.ctypes.data_as(fp), C.c_uint32(len(v)), t.ctypes.data_as(up), C.c_uint32(len(t)), a.ctypes.data_as(fp), 1)
+    med = scene["medium"]
+    sa, ss = np.ascontiguousarray(med["sigmaA"], np.float32), np.ascontiguousarray(med["sigmaS"], np.float32)
+    lib.alvrl_plugin_scene_add_medium_homogeneous(sc, sa.ctypes.data_as(fp), ss.ctypes.data_as(fp), C.c_float(-1.0), 0, C.c_float(0.0))
+    cam = scene["camera"]
+    s2c = np.ascontiguousarray(cam["sampleToCamera"], np.float32).reshape(16)
+    c2w = np.ascontiguousarray(cam["cameraToWorld"], np.float32).reshape(16)
+    pos = np.ascontiguousarray(cam["origin"], np.float32)
+    W, H = cam["width"], cam["height"]
+    lib.alvrl_plugin_scene_set_sensor(sc, s2c.ctypes.data_as(fp), c2w.ctypes.data_as(fp), C.c_uint32(W), C.c_uint32(H),
+                                      C.c_float(cam["near"]), C.c_float(cam["far"]), pos.ctypes.data_as(fp))
+    img_plugin = np.zeros((H, W, 3), np.float32)
+    rc = lib.alvrl_plugin_render_frame(inst, sc, img_plugin.ctypes.data_as(fp), err, 1024)
+    assert rc == 0, err.value
+    lib.alvrl_plugin_destroy(inst); lib.alvrl_plugin_scene_free(sc); lib.alvrl_plugin_props_free(p)
+
+    # --- the same calls on the C ABI ---
+    direct = {k: v for k, v in xml.items() if k != "vrlFile"}
+    g = pkg.integrator(0, **direct)
+    g.set_scene(flat)
+    g.load_vrl_file(path)
+    assert g.N == 180                                   # the two bad lines were dropped by the put() filter
+    if clustered:
+        g.build_slices(); g.prepass()
+    img_direct = g.render(clustered)
+    assert img_plugin.max() > 0
+    assert np.array_equal(img_plugin, img_direct)
+
+    # and the file path gives the VRL set that the array path gives
+    g2 = pkg.integrator(0, **direct)
+    g2.set_scene(flat)
+    g2.set_vrls(start, end, power, 0)
+    if clustered:
+        g2.build_slices(); g2.prepass()
+    np.testing.assert_allclose(g2.render(clustered), img_direct, rtol=1e-5, atol=1e-9)
+
+
+def test_plugin_reports_missing_vrl_file(pkg, tmp_path):
+    lib = _plugin()
+    p = C.c_void_p(lib.alvrl_plugin_props_new())
+    lib.alvrl_plugin_props_set_string(p, b"vrlFile", str(tmp_path / "nope.vrl").encode())
+    inst = C.c_void_p()
+    err = C.create_string_buffer(1024)
+    assert lib.alvrl_plugin_create(p, C.byref(inst), err, 1024) == 0
+    sc = C.c_void_p(lib.alvrl_plugin_scene_new())
+    img = np.zeros(3, np.float32)
+    rc = lib.alvrl_plugin_render_frame(inst, sc, img.ctypes.data_as(C.POINTER(C.c_float)), err, 1024)
+    assert rc != 0 and b"medium" in err.value           # vrlIntegrator.cpp:244-248: exactly one medium
+    lib.alvrl_plugin_destroy(inst); lib.alvrl_plugin_scene_free(sc); lib.alvrl_plugin_props_free(p)
