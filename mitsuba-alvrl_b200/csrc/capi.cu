@@ -20,6 +20,27 @@ using namespace alvrl;
 
 namespace {
 
+/* pair-level culling (occ_query.h): the side of every slab face / plane that a whole VRL lies on, stored in the two spare
+ * words of its record (dir.w: plane bits, power.w: slab-side bits) */
+__global__ void k_vrl_occ_sides(VrlRec *__restrict__ vrls, uint32_t n, OccDev oc) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 s = vrls[i].s, e = vrls[i].e;
+    const uint32_t slabs = occ_slab_sides(oc, s.x, s.y, s.z, e.x, e.y, e.z, oc.cullMargin);
+    const uint32_t planes = occ_plane_sides(oc, s.x, s.y, s.z, e.x, e.y, e.z, oc.cullMargin, false);
+    vrls[i].dir.w = __uint_as_float(planes);
+    vrls[i].power.w = __uint_as_float(slabs);
+}
+/* representative records of the render lists: rec[k] = vrls[idx[k]] with the cluster weight in e.w */
+__global__ void k_gather_reps(const VrlRec *__restrict__ vrls, const uint32_t *__restrict__ idx, const float *__restrict__ w, uint32_t n,
+                              VrlRec *__restrict__ out) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    VrlRec r = vrls[idx[k]];
+    r.e.w = w[k];
+    out[k] = r;
+}
+
 thread_local std::string g_err;
 
 int fail(int code, const std::string &m) { g_err = m; return code; }
@@ -92,8 +113,25 @@ void ensure_scene(alvrl_ctx *c) {
         }
     }
     if (visEnv && !strcmp(visEnv, "tree")) s.visMode = 0;
+    c->occHost.cullMargin = 1e-5f * std::max(mx[0] - mn[0], std::max(mx[1] - mn[1], mx[2] - mn[2]));
+    if (getenv("ALVRL_NO_PAIR_CULL")) c->occHost.cullMargin = INFINITY;      /* experiments: nothing is ever "strictly beyond" */
+    c->vrlSidesValid = false;
     c->stats.bvhNodes = s.numNodes; c->stats.visMode = (uint32_t) s.visMode;
     c->sceneDirty = false; c->segsDirty = true;
+}
+
+/* per-VRL side bits of the compiled occluder set (needs scene + VRLs; redone when either changes) */
+void ensure_vrl_sides(alvrl_ctx *c) {
+    ensure_scene(c);
+    if (c->vrlSidesValid || !c->haveVrls) return;
+    if (c->sceneDev.visMode == 2) {
+        const uint32_t n = (uint32_t) c->vrlHost.size();
+        k_vrl_occ_sides<<<(n + 255) / 256, 256, 0, c->stream>>>(c->dVrls.p, n, c->occHost);
+        c->stats.kernelLaunches++;
+        ALVRL_CUDA(cudaGetLastError());
+    }
+    c->vrlSidesValid = true;
+    c->renderListsDirty = true;
 }
 
 void ensure_primary(alvrl_ctx *c) {
@@ -166,11 +204,12 @@ void make_sfmt_tape(alvrl_ctx *c, std::vector<float> &tape) {
 }
 
 void build_render_lists(alvrl_ctx *c) {
+    ensure_vrl_sides(c);
     if (!c->renderListsDirty) return;
     const uint32_t S = (uint32_t) c->slices.size();
-    std::vector<uint32_t> slicePixels, repOffset(S + 1, 0);
+    std::vector<uint32_t> slicePixels, repOffset(S + 1, 0), repIdx;
+    std::vector<float> repW;
     std::vector<uint4> work;
-    std::vector<VrlRec> recs;
     for (uint32_t s = 0; s < S; s++) {
         std::vector<uint32_t> px = c->slices[s].pixels;
         std::sort(px.begin(), px.end());                 /* pixel order inside a slice is free: sort for ray coherence */
@@ -182,17 +221,24 @@ void build_render_lists(alvrl_ctx *c) {
         const std::vector<float> &wt = c->clusterWeight[s];
         for (size_t i = 0; i < vr.size(); i++) {
             if (vr[i] >= c->vrlHost.size()) throw Error(ALVRL_ERR_ARG, "cluster representative out of range");
-            VrlRec r = c->vrlHost[vr[i]];
-            r.e.w = wt[i];
-            recs.push_back(r);
+            repIdx.push_back(vr[i]); repW.push_back(wt[i]);
         }
-        repOffset[s + 1] = (uint32_t) recs.size();
+        repOffset[s + 1] = (uint32_t) repIdx.size();
     }
     c->dSlicePixels.upload(slicePixels, c->stream);
     c->dWork.upload(work, c->stream);
     c->dRepOffset.upload(repOffset, c->stream);
-    if (recs.empty()) recs.push_back(VrlRec());
-    c->dRepRecs.upload(recs, c->stream);
+    /* the representatives' records are gathered on the device (they carry the per-VRL side bits of ensure_vrl_sides) */
+    const uint32_t nRep = (uint32_t) repIdx.size();
+    c->dRepRecs.alloc(std::max<uint32_t>(1, nRep));
+    if (nRep) {
+        DevBuf<uint32_t> dIdx; DevBuf<float> dW;
+        dIdx.upload(repIdx, c->stream); dW.upload(repW, c->stream);
+        k_gather_reps<<<(nRep + 255) / 256, 256, 0, c->stream>>>(c->dVrls.p, dIdx.p, dW.p, nRep, c->dRepRecs.p);
+        c->stats.kernelLaunches++;
+        ALVRL_CUDA(cudaGetLastError());
+        ALVRL_CUDA(cudaStreamSynchronize(c->stream));
+    }
     c->numWork = (uint32_t) work.size();
     c->renderListsDirty = false;
 }
@@ -402,6 +448,7 @@ int alvrl_set_vrls(alvrl_handle c, const float *s, const float *e, const float *
     c->particleCount = particleCount ? particleCount : c->vrlHost.size();
     if (c->vrlHost.empty()) throw Error(ALVRL_ERR_ARG, "no usable VRLs");
     c->dVrls.upload(c->vrlHost, c->stream);
+    c->vrlSidesValid = false;
     c->haveVrls = true; c->haveR = false; c->haveClusters = false; c->haveFallback = false; c->renderListsDirty = true;
     c->stats.numVrls = (uint32_t) c->vrlHost.size();
     API_END
@@ -492,6 +539,7 @@ int alvrl_build_R(alvrl_handle c) {
     if (!c->haveRows || !c->haveVrls || !c->haveMedium) throw Error(ALVRL_ERR_STATE, "sample_slice_mapping / set_vrls / set_medium first");
     double t0 = now_ms();
     ensure_primary(c);
+    ensure_vrl_sides(c);
     const uint32_t N = (uint32_t) c->vrlHost.size(), G = (uint32_t) c->rowPixel.size(), S = (uint32_t) c->slices.size();
     c->dRowPixel.upload(c->rowPixel, c->stream);
     c->dRowSegs.alloc(G);
@@ -590,6 +638,7 @@ int alvrl_render_unclustered(alvrl_handle c, float *rgb) {
     if (!c->haveVrls || !c->haveMedium) throw Error(ALVRL_ERR_STATE, "set_vrls / set_medium first");
     double t0 = now_ms();
     ensure_primary(c);
+    ensure_vrl_sides(c);
     const uint32_t P = c->numPixels(), N = (uint32_t) c->vrlHost.size();
     std::vector<uint32_t> px(P), off = {0, N};
     std::vector<uint4> work;

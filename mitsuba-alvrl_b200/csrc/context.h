@@ -139,6 +139,7 @@ struct alvrl_ctx {
     /* VRLs */
     std::vector<VrlRec> vrlHost; uint64_t particleCount = 0;
     alvrl::DevBuf<VrlRec> dVrls;
+    bool vrlSidesValid = false;       /* per-VRL side bits of the compiled occluder set are in dVrls (occ_query.h) */
 
     /* per pixel (index y + H*x) */
     alvrl::DevBuf<SegRec> dPixSegs; alvrl::DevBuf<uint32_t> dHitPrim; alvrl::DevBuf<float> dHitT;

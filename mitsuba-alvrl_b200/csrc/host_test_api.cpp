@@ -101,4 +101,48 @@ int alvrl_host_occ_query(const void *dev, const float *triRecs, const float *o, 
     return 0;
 }
 
+
+/* pair-level culling of occ_query.h: for every pair (camera segment [E, Usurf], VRL [S, End]) the side bits of the two ends
+ * are ANDed like the transport kernels do (per lane, without the warp vote), `samples` random shadow segments of the pair
+ * are queried with and without the resulting active masks, and every disagreement is counted.
+ * stats = {mismatches, box tests culled, box tests, plane tests culled, plane tests, occluded segments} */
+int alvrl_host_pair_cull_check(const void *dev, const float *triRecs, const float *E, const float *Usurf, const float *S, const float *End,
+                               uint32_t nPairs, uint32_t samples, uint64_t seed, float margin, uint64_t *stats) {
+    OccDev oc; memcpy(&oc, dev, sizeof(oc));
+    oc.cullMargin = margin;
+    const float4 *tr = reinterpret_cast<const float4 *>(triRecs);
+    uint64_t x = seed * 0x9e3779b97f4a7c15ull + 1;
+    auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return (float) ((x >> 40) * (1.0 / 16777216.0)); };
+    for (int k = 0; k < 6; k++) stats[k] = 0;
+    const uint32_t nb = oc.numBoxes;
+    const uint32_t boxAll = (1u << nb) - 1u, planeAll = (1u << oc.numPlanes) - 1u;
+    for (uint32_t i = 0; i < nPairs; i++) {
+        const float *e = E + 3 * i, *u = Usurf + 3 * i, *s = S + 3 * i, *t = End + 3 * i;
+        const uint32_t segHull = occ_slab_sides(oc, e[0], e[1], e[2], u[0], u[1], u[2], margin);
+        const uint32_t segSurf = occ_slab_sides(oc, u[0], u[1], u[2], u[0], u[1], u[2], margin);
+        const uint32_t segPl = occ_plane_sides(oc, e[0], e[1], e[2], u[0], u[1], u[2], margin, true);
+        const uint32_t vSl = occ_slab_sides(oc, s[0], s[1], s[2], t[0], t[1], t[2], margin);
+        const uint32_t vPl = occ_plane_sides(oc, s[0], s[1], s[2], t[0], t[1], t[2], margin, false);
+        uint32_t pc = segPl & vPl; pc = (pc | (pc >> 16)) & 0xffffu;
+        const uint32_t planeAct = planeAll & ~pc;
+        const uint32_t boxVV = boxAll & ~occ_boxes_culled(segHull & vSl, nb), boxVS = boxAll & ~occ_boxes_culled(segSurf & vSl, nb);
+        for (uint32_t q = 0; q < samples; q++) {
+            const bool surf = q & 1;
+            const float a = surf ? 1.0f : rnd(), b = rnd();
+            float o[3], d[3], len2 = 0;
+            for (int k = 0; k < 3; k++) { o[k] = surf ? u[k] : e[k] + a * (u[k] - e[k]); d[k] = (s[k] + b * (t[k] - s[k])) - o[k]; len2 += d[k] * d[k]; }
+            const float len = std::sqrt(len2);
+            if (!(len > 0)) continue;
+            for (int k = 0; k < 3; k++) d[k] /= len;
+            const float tmin = surf ? 1e-4f * std::max(std::fabs(o[0]), std::max(std::fabs(o[1]), std::fabs(o[2]))) : 0.0f;
+            const bool full = occ_query(oc, tr, o[0], o[1], o[2], d[0], d[1], d[2], tmin, len, true);
+            const bool culled = occ_query(oc, tr, o[0], o[1], o[2], d[0], d[1], d[2], tmin, len, true, surf ? boxVS : boxVV, planeAct);
+            stats[0] += full != culled; stats[5] += full;
+            stats[1] += __builtin_popcount(boxAll & ~(surf ? boxVS : boxVV)); stats[2] += nb;
+            stats[3] += __builtin_popcount(planeAll & ~planeAct); stats[4] += oc.numPlanes;
+        }
+    }
+    return 0;
+}
+
 }

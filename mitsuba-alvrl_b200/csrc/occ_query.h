@@ -24,6 +24,7 @@ struct OccDev {
     float4 planes[ALVRL_OCC_MAX_PLANES];     /* n.xyz, c */
     uint32_t planeInfo[ALVRL_OCC_MAX_PLANES];/* first << 8 | count into the triangle records */
     uint32_t numBoxes, numSlabs, numPlanes, numTris;   /* slabs [0, 3 numBoxes) are the boxes */
+    float cullMargin;                                  /* 1e-5 x scene extent: strictness of the pair-level side tests */
 };
 
 #ifdef __CUDACC__
@@ -55,12 +56,60 @@ static inline uint32_t alvrl_occ_bits(float f) { uint32_t u; __builtin_memcpy(&u
 /* the segment touches the solid's boundary iff the clipped line is non-empty and enters or leaves it inside [tmin, tmax] */
 #define ALVRL_OCC_TOUCH() (tn <= tf && ((tn >= tmin && tn <= tmax) || (tf >= tmin && tf <= tmax)))
 
+/*
+ * Pair-level conservative culling.  Every shadow segment of one (camera segment, VRL) pair joins a point of the camera
+ * segment [E, Usurf] (vol->vol) or Usurf itself (vol->surf) to a point of the VRL [S, End]: it stays inside the convex hull
+ * of those points.  If all of them lie strictly beyond one face of a slab, no segment of the pair can touch that solid; if
+ * all of them lie strictly on one side of a plane, none can cross it.  "Beyond" is recorded once per camera segment and once
+ * per VRL as bit masks (margin = 1e-5 x scene extent, >> the fp32 error of the per-ray tests, so a culled test could not
+ * have reported a hit), and a pair's culled set is the AND of the two.  A camera segment ENDS on a surface: Usurf only has
+ * to be on the plane's side up to the margin (the ray towards a point strictly on that side leaves the surface).
+ *   slab side bits : slab k < 16 -> bit 2k "below c_lo", bit 2k+1 "above c_hi"
+ *   plane bits     : plane i < 16 -> bit i "positive side", bit 16+i "negative side"
+ * Solids / planes beyond those indices are never culled.  boxActive / planeActive of occ_query are warp-uniform masks of
+ * what still has to be tested (bit b: box b; bit i: plane i).
+ */
+#define ALVRL_OCC_MASK_SLABS 16
+#define ALVRL_OCC_MASK_PLANES 16
+/* side bits of one point set {p0, p1}; loose1: p1 may sit on a plane (within the margin) */
+ALVRL_OCC_HD uint32_t occ_slab_sides(const OccDev &oc, float ax, float ay, float az, float bx, float by, float bz, float m) {
+    uint32_t bits = 0;
+    const uint32_t ns = oc.numSlabs < ALVRL_OCC_MASK_SLABS ? oc.numSlabs : ALVRL_OCC_MASK_SLABS;
+    for (uint32_t k = 0; k < ns; k++) {
+        const float4 a = oc.slabA[k];
+        const float chi = oc.slabB[k].x;
+        const float da = fmaf(a.x, ax, fmaf(a.y, ay, a.z * az)), db = fmaf(a.x, bx, fmaf(a.y, by, a.z * bz));
+        bits |= ((da < a.w - m && db < a.w - m) ? 1u : 0u) << (2 * k);
+        bits |= ((da > chi + m && db > chi + m) ? 1u : 0u) << (2 * k + 1);
+    }
+    return bits;
+}
+ALVRL_OCC_HD uint32_t occ_plane_sides(const OccDev &oc, float ax, float ay, float az, float bx, float by, float bz, float m, bool looseB) {
+    uint32_t bits = 0;
+    const uint32_t np = oc.numPlanes < ALVRL_OCC_MASK_PLANES ? oc.numPlanes : ALVRL_OCC_MASK_PLANES;
+    const float mb = looseB ? -m : m;
+    for (uint32_t i = 0; i < np; i++) {
+        const float4 p = oc.planes[i];
+        const float da = fmaf(p.x, ax, fmaf(p.y, ay, p.z * az)) - p.w, db = fmaf(p.x, bx, fmaf(p.y, by, p.z * bz)) - p.w;
+        bits |= ((da > m && db > mb) ? 1u : 0u) << i;
+        bits |= ((da < -m && db < -mb) ? 1u : 0u) << (16 + i);
+    }
+    return bits;
+}
+/* boxes of a lane that the AND of a segment's and a VRL's slab-side bits culls: bit b = some face separates box b */
+ALVRL_OCC_HD uint32_t occ_boxes_culled(uint32_t sideBits, uint32_t numBoxes) {
+    uint32_t c = 0;
+    for (uint32_t b = 0; b < numBoxes && 6 * b < 32; b++) c |= (((sideBits >> (6 * b)) & 63u) ? 1u : 0u) << b;
+    return c;
+}
+
 ALVRL_OCC_HD bool occ_query(const OccDev &oc, const float4 *tris, float ox, float oy, float oz, float dx, float dy, float dz, float tmin,
-                            float tmax, bool need) {
+                            float tmax, bool need, uint32_t boxActive = 0xffffffffu, uint32_t planeActive = 0xffffffffu) {
     const float INF = INFINITY;
     bool hit = false;
     const uint32_t nb = oc.numBoxes;
     for (uint32_t b = 0; b < nb; b++) {
+        if (!((boxActive >> b) & 1u)) continue;
         float tn = -INF, tf = INF;
         ALVRL_OCC_CLIP(oc.slabA[3 * b], oc.slabB[3 * b].x);
         ALVRL_OCC_CLIP(oc.slabA[3 * b + 1], oc.slabB[3 * b + 1].x);
@@ -79,6 +128,7 @@ ALVRL_OCC_HD bool occ_query(const OccDev &oc, const float4 *tris, float ox, floa
     }
     uint32_t mask = 0;
     for (uint32_t i = 0; i < oc.numPlanes; i++) {
+        if (!((planeActive >> i) & 1u)) continue;
         const float4 p = oc.planes[i];
         const float den = fmaf(p.x, dx, fmaf(p.y, dy, p.z * dz));
         const float no = fmaf(p.x, ox, fmaf(p.y, oy, p.z * oz));

@@ -149,18 +149,21 @@ __device__ __forceinline__ bool spec_valid(const float c[3]) {            /* spe
     return isfinite(c[0]) && isfinite(c[1]) && isfinite(c[2]) && c[0] >= 0.0f && c[1] >= 0.0f && c[2] >= 0.0f;
 }
 
-/* vrlIntegrator::getClosestPoints (962-1032): closest distance h and the closest point on the VRL */
+/* vrlIntegrator::getClosestPoints (962-1032): closest distance h and the closest point on the VRL.
+ * D, sN, tN are differences of nearly equal products when the two segments are close to parallel (relative error
+ * eps / sin^2): they are evaluated with explicitly rounded operations in the reference's order in BOTH flavours, so that
+ * FMA contraction in the fast flavour cannot move h and Vh of such pairs away from the oracle's. */
 __device__ __forceinline__ float closest_points(const F3 &S1P0, const F3 &S1P1, const F3 &S2P0, const F3 &S2P1, F3 &S2h) {
     const F3 u = S1P1 - S1P0, v = S2P1 - S2P0, w = S1P0 - S2P0;
-    const float a = dot(u, u), b = dot(u, v), c = dot(v, v), d = dot(u, w), e = dot(v, w);
-    const float D = a * c - b * b;
+    const float a = xdot(u, u), b = xdot(u, v), c = xdot(v, v), d = xdot(u, w), e = xdot(v, w);
+    const float D = xsub(xmul(a, c), xmul(b, b));
     float sN, sD = D, tN, tD = D;
-    if (D < ALVRL_EPSILON * len2(u) * len2(v)) { sN = 0.0f; sD = 1.0f; tN = e; tD = c; }
+    if (D < xmul(xmul(ALVRL_EPSILON, a), c)) { sN = 0.0f; sD = 1.0f; tN = e; tD = c; }
     else {
-        sN = (b * e - c * d);
-        tN = (a * e - b * d);
+        sN = xsub(xmul(b, e), xmul(c, d));
+        tN = xsub(xmul(a, e), xmul(b, d));
         if (sN < 0.0f) { sN = 0.0f; tN = e; tD = c; }
-        else if (sN > sD) { sN = sD; tN = e + b; tD = c; }
+        else if (sN > sD) { sN = sD; tN = xadd(e, b); tD = c; }
     }
     if (tN < 0.0f) {
         tN = 0.0f;
@@ -169,14 +172,21 @@ __device__ __forceinline__ float closest_points(const F3 &S1P0, const F3 &S1P1, 
         else { sN = -d; sD = a; }
     } else if (tN > tD) {
         tN = tD;
-        if ((-d + b) < 0.0f) sN = 0;
-        else if ((-d + b) > a) sN = sD;
-        else { sN = (-d + b); sD = a; }
+        const float db = xadd(-d, b);
+        if (db < 0.0f) sN = 0;
+        else if (db > a) sN = sD;
+        else { sN = db; sD = a; }
     }
     const float sc = m_div(sN, sD), tc = m_div(tN, tD);
-    const F3 dP = w + (sc * u) - (tc * v);
-    S2h = S2P0 + tc * (S2P1 - S2P0);
-    return m_len(dP);
+    const F3 dP = xsub3(xadd3(w, xscale(u, sc)), xscale(v, tc));       /* the distance of two nearly touching segments cancels too */
+    S2h = xadd3(S2P0, xscale(v, tc));
+    return m_sqrt(xdot(dP, dP));
+}
+/* cos / sin of the angle between the camera ray and the VRL (sampleVtoDistance, 925-927): 1 - cos^2 cancels for nearly
+ * parallel pairs, so both flavours round it exactly like the reference does */
+__device__ __forceinline__ void cos_sin_theta(const F3 &dn, const F3 &SV, float &cosTheta, float &sinTheta) {
+    cosTheta = xdot(dn, SV);
+    sinTheta = m_sqrt(fmaxf(0.0f, xsub(1.0f, xmul(cosTheta, cosTheta))));
 }
 
 /*
@@ -198,8 +208,8 @@ __device__ __forceinline__ void integrate_pair(const TransportParams &P, const S
     /* ---- volume to volume, L (V|D|S)* V V S* E (646-703) ---- */
     if (Nvv > 0) {
         /* per-pair part of sampleVtoDistance (916-953) */
-        const float cosTheta = dot(f3(seg.dn), SV);
-        const float sinTheta = m_sqrt(fmaxf(0.0f, 1 - cosTheta * cosTheta));
+        float cosTheta, sinTheta;
+        cos_sin_theta(f3(seg.dn), SV, cosTheta, sinTheta);
         const bool parallel = sinTheta < ALVRL_EPSILON;
         float h = 0, A0 = 0, A1 = 0, dVhS = 0;
         if (!parallel) {
@@ -446,6 +456,10 @@ __global__ void __launch_bounds__(ALVRL_CTA_SEGS, ALVRL_MIN_CTAS) ALVRL_NAME(k_b
         active = (__float_as_uint(seg.dn.w) & SEG_VALID) != 0;
     }
     const bool scattering = !(P.medium.sigmaS[0] == 0 && P.medium.sigmaS[1] == 0 && P.medium.sigmaS[2] == 0);
+#ifdef ALVRL_FAST
+    SegSides sides; sides.slabHull = sides.slabSurf = sides.planes = 0;
+    if (SMALL == 2) sides = seg_sides(P.occ, seg, active && scattering);
+#endif
 
     for (uint32_t t = 0; t < numTiles; t++) {
         if (tid == 0 && t + 1 < numTiles) issue(t + 1);
@@ -466,7 +480,9 @@ __global__ void __launch_bounds__(ALVRL_CTA_SEGS, ALVRL_MIN_CTAS) ALVRL_NAME(k_b
                     rng.key = alvrl_rng_key(P.seed, P.rngDomain, P.rowBase + row, v);
                     rng.k = 0;
                     float rgb[3], m, s2;
-                    integrate_pair_fast<MED, false, true, SMALL>(P, &sbvh, seg, vr.s, vr.e, vr.dir, vr.power, rng, rgb, m, s2, active && scattering);
+                    PairCull cull; cull.boxVV = cull.boxVS = cull.planes = 0xffffffffu;
+                    if (SMALL == 2) cull = pair_cull(P.occ, sides, vr.dir, vr.power);
+                    integrate_pair_fast<MED, false, true, SMALL>(P, &sbvh, seg, vr.s, vr.e, vr.dir, vr.power, rng, rgb, m, s2, active && scattering, cull);
                     mean = m * P.normalization;
                     var = s2 * P.normalization * P.normalization;
                 } else
@@ -537,6 +553,10 @@ __global__ void __launch_bounds__(ALVRL_CTA_SEGS, ALVRL_MIN_CTAS) ALVRL_NAME(k_r
     }
     const bool scattering = !(P.medium.sigmaS[0] == 0 && P.medium.sigmaS[1] == 0 && P.medium.sigmaS[2] == 0);
     float Li[3] = {0, 0, 0};
+#ifdef ALVRL_FAST
+    SegSides sides; sides.slabHull = sides.slabSurf = sides.planes = 0;
+    if (SMALL == 2) sides = seg_sides(P.occ, seg, active && scattering);
+#endif
     for (uint32_t t = 0; t < numTiles; t++) {
         if (tid == 0 && t + 1 < numTiles) issue(t + 1);
         mbar_wait(&sm.full[t & 1], (t >> 1) & 1);
@@ -552,8 +572,11 @@ __global__ void __launch_bounds__(ALVRL_CTA_SEGS, ALVRL_MIN_CTAS) ALVRL_NAME(k_r
                 rng.k = 0;
                 float rgb[3] = {0, 0, 0}, m, s2;
 #ifdef ALVRL_FAST
-                if constexpr (MED != 1) integrate_pair_fast<MED, true, false, SMALL>(P, &sbvh, seg, vr.s, vr.e, vr.dir, vr.power, rng, rgb, m, s2, active && scattering);
-                else
+                if constexpr (MED != 1) {
+                    PairCull cull; cull.boxVV = cull.boxVS = cull.planes = 0xffffffffu;
+                    if (SMALL == 2) cull = pair_cull(P.occ, sides, vr.dir, vr.power);
+                    integrate_pair_fast<MED, true, false, SMALL>(P, &sbvh, seg, vr.s, vr.e, vr.dir, vr.power, rng, rgb, m, s2, active && scattering, cull);
+                } else
 #endif
                 if (active && scattering) integrate_pair<(MED == 2 ? 0 : MED), true, false>(P, seg, vr.s, vr.e, vr.dir, vr.power, rng, rgb, m, s2);
                 if (CLUSTERED) {                                             /* 587-589: Li += weight_k * integrateVRL */

@@ -86,11 +86,41 @@ __device__ __forceinline__ bool occluded_flat(const BvhSmem &sb, uint32_t numLea
     return false;
 }
 
+/* what a pair still has to test of the compiled occluder set (warp-uniform; occ_query.h "pair-level culling") */
+struct PairCull { uint32_t boxVV, boxVS, planes; };
+
+/* the camera segment's side of every slab face / plane: hull = {E, Usurf} (vol->vol), surf = {Usurf} (vol->surf).  A lane
+ * without a segment culls everything, so that it never keeps a test alive for its warp */
+struct SegSides { uint32_t slabHull, slabSurf, planes; };
+__device__ __forceinline__ SegSides seg_sides(const OccDev &oc, const SegRec &seg, bool active) {
+    SegSides s;
+    if (!active) { s.slabHull = s.slabSurf = s.planes = 0xffffffffu; return s; }
+    const float m = oc.cullMargin;
+    s.slabHull = occ_slab_sides(oc, seg.o.x, seg.o.y, seg.o.z, seg.p.x, seg.p.y, seg.p.z, m);
+    s.slabSurf = occ_slab_sides(oc, seg.p.x, seg.p.y, seg.p.z, seg.p.x, seg.p.y, seg.p.z, m);
+    s.planes = occ_plane_sides(oc, seg.o.x, seg.o.y, seg.o.z, seg.p.x, seg.p.y, seg.p.z, m, true);
+    return s;
+}
+/* called by all lanes of the warp together */
+__device__ __forceinline__ PairCull pair_cull(const OccDev &oc, const SegSides &sg, const float4 vDir, const float4 vPow) {
+    const uint32_t vPl = __float_as_uint(vDir.w), vSl = __float_as_uint(vPow.w);
+    const uint32_t nb = oc.numBoxes;
+    const uint32_t boxAll = nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u), planeAll = oc.numPlanes >= 32 ? 0xffffffffu : ((1u << oc.numPlanes) - 1u);
+    uint32_t pc = sg.planes & vPl;
+    pc = (pc | (pc >> 16)) & 0xffffu;
+    PairCull c;
+    c.planes = planeAll & ~__reduce_and_sync(0xffffffffu, pc);
+    c.boxVV = boxAll & ~__reduce_and_sync(0xffffffffu, occ_boxes_culled(sg.slabHull & vSl, nb));
+    c.boxVS = boxAll & ~__reduce_and_sync(0xffffffffu, occ_boxes_culled(sg.slabSurf & vSl, nb));
+    return c;
+}
+
 template <int SMALL>
-__device__ __forceinline__ bool occluded_fast(const TransportParams &P, const BvhSmem *sb, const F3 &p1, bool onSurf, const F3 &dir, float remaining, bool need) {
+__device__ __forceinline__ bool occluded_fast(const TransportParams &P, const BvhSmem *sb, const F3 &p1, bool onSurf, const F3 &dir, float remaining, bool need,
+                                              uint32_t boxActive = 0xffffffffu, uint32_t planeActive = 0xffffffffu) {
     /* adaptive epsilon of the shadow-ray overload, skdtree.cpp:154-157 */
     const float mint = onSurf ? ALVRL_EPSILON * fmaxf(fmaxf(fabsf(p1.x), fabsf(p1.y)), fabsf(p1.z)) : 0.0f;
-    if (SMALL == 2) return occ_query(P.occ, sb->tris, p1.x, p1.y, p1.z, dir.x, dir.y, dir.z, mint, remaining, need);
+    if (SMALL == 2) return occ_query(P.occ, sb->tris, p1.x, p1.y, p1.z, dir.x, dir.y, dir.z, mint, remaining, need, boxActive, planeActive);
     if (SMALL == 1) return occluded_flat(*sb, P.scene.numLeaves, p1, dir, mint, remaining, need);
     if (!need || !(remaining > mint)) return false;
     return bvh_occluded_fast(P.scene, p1, dir, mint, remaining);
@@ -105,7 +135,7 @@ __device__ __forceinline__ float f_len(const F3 &a, float &l2) { l2 = len2(a); r
 template <int MED, bool WANT_RGB, bool WANT_STAT, int SMALL>
 __device__ __forceinline__ void integrate_pair_fast(const TransportParams &P, const BvhSmem *sb, const SegRec &seg,
                                                     const float4 vS, const float4 vE, const float4 vDir, const float4 vPow, Rng &rng,
-                                                    float rgb[3], float &outMean, float &outVar, const bool laneOn) {
+                                                    float rgb[3], float &outMean, float &outVar, const bool laneOn, const PairCull cull) {
     const F3 S = f3(vS), End = f3(vE), SV = f3(vDir);
     const float vlen = vS.w;
     const F3 E = f3(seg.o), EU = f3(seg.d), Usurf = f3(seg.p);
@@ -124,8 +154,8 @@ __device__ __forceinline__ void integrate_pair_fast(const TransportParams &P, co
     if (Nvv > 0) {
         /* power * sigma_s(V) * sigma_s(U): constant per pair in a homogeneous medium */
         const float k0 = vPow.x * M.sigmaS[0] * M.sigmaS[0], k1 = vPow.y * M.sigmaS[1] * M.sigmaS[1], k2 = vPow.z * M.sigmaS[2] * M.sigmaS[2];
-        const float cosTheta = dot(f3(seg.dn), SV);
-        const float sinTheta = sqrtf(fmaxf(0.0f, 1 - cosTheta * cosTheta));
+        float cosTheta, sinTheta;
+        cos_sin_theta(f3(seg.dn), SV, cosTheta, sinTheta);
         const bool parallel = sinTheta < ALVRL_EPSILON;
         float h = 0, A0 = 0, dA = 0, dVhS = 0, rSin = 0, pdfVc = 0;
         if (!parallel) {
@@ -172,7 +202,7 @@ __device__ __forceinline__ void integrate_pair_fast(const TransportParams &P, co
             float tmp;
             const float dSV = f_len(V - S, tmp);
             const bool ok = laneOn && d2 > 0.0f && dEU * sTmin <= cutoff && dSV * sTmin <= cutoff;
-            const bool occ = occluded_fast<SMALL>(P, sb, U, false, -VU, dUV, ok);
+            const bool occ = occluded_fast<SMALL>(P, sb, U, false, -VU, dUV, ok, cull.boxVV, cull.planes);
             float lum = 0;
             if (ok && !occ) {
                 const float path = dSV + dUV + dEU;
@@ -237,7 +267,7 @@ __device__ __forceinline__ void integrate_pair_fast(const TransportParams &P, co
                 const float dSV = fabsf(sv);
                 const float cosWo = -dot(VU, nrm);                           /* diffuse.cpp:110-118 */
                 const bool ok = surf && d2 > 0.0f && dSV * sTmin <= cutoff && frontI && cosWo > 0;
-                const bool occ = occluded_fast<SMALL>(P, sb, Usurf, true, -VU, dUV, ok);
+                const bool occ = occluded_fast<SMALL>(P, sb, Usurf, true, -VU, dUV, ok, cull.boxVS, cull.planes);
                 float lum = 0;
                 if (ok && !occ) {
                     const float path = dSV + dUV;

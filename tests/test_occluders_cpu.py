@@ -15,7 +15,8 @@ MAX_SLABS, MAX_PLANES = 24, 24        # csrc/occ_query.h
 class OccDev(C.Structure):            # mirrors struct OccDev (csrc/occ_query.h)
     _fields_ = [("slabA", C.c_float * (4 * MAX_SLABS)), ("slabB", C.c_float * (2 * MAX_SLABS)),
                 ("planes", C.c_float * (4 * MAX_PLANES)), ("planeInfo", C.c_uint32 * MAX_PLANES),
-                ("numBoxes", C.c_uint32), ("numSlabs", C.c_uint32), ("numPlanes", C.c_uint32), ("numTris", C.c_uint32)]
+                ("numBoxes", C.c_uint32), ("numSlabs", C.c_uint32), ("numPlanes", C.c_uint32), ("numTris", C.c_uint32),
+                ("cullMargin", C.c_float), ("pad", C.c_float * 3)]     # float4 members: the C++ struct is 16-byte aligned
 
 
 def compile_occ(host_lib, verts, tris, num_leaves=18):
@@ -220,3 +221,40 @@ def test_mixed_solids_boxes_first_and_axis_parallel_segments(pkg, host_lib):
     want, graze = brute(verts, tris, o, d, np.zeros_like(L), L, margin=1e-4)
     bad = (got != want) & ~graze
     assert not bad.any(), int(bad.sum())
+
+
+def test_pair_level_culling_never_changes_a_decision(host_lib, pkg, orc):
+    """occ_query.h, pair-level culling: the side bits of a camera segment [E, Usurf] and of a VRL [S, End] decide which boxes
+    and planes the pair's shadow segments still have to test.  On real camera segments of the Cornell scene (hit points from
+    the oracle's primary rays) x synthetic VRLs, 1.5 M random shadow segments (vol->vol from a point of the camera segment,
+    vol->surf from the hit point with the adaptive epsilon) give the same answer with and without the culled tests, and the
+    culling removes most of the plane tests and a good part of the box tests."""
+    from conftest import small_case, setup
+    scene, vrls, params = small_case(pkg, "C1", 48, 48, 400)
+    counts, occ = compile_occ(host_lib, scene["verts"], scene["tris"])
+    assert counts[0] == 1
+    o = setup(orc.Oracle(**params), scene, vrls)
+    prim, t, pos, nrm = o.primary_hits()
+    hit = prim != 0xFFFFFFFF
+    rng = np.random.default_rng(11)
+    n = 150_000
+    pix = rng.choice(np.flatnonzero(hit), n)
+    vi = rng.integers(0, len(vrls[0]), n)
+    E = np.broadcast_to(scene["camera"]["origin"], (n, 3)).astype(np.float32).copy()
+    U = np.ascontiguousarray(pos[pix], dtype=np.float32)
+    S = np.ascontiguousarray(vrls[0][vi], dtype=np.float32)
+    En = np.ascontiguousarray(vrls[1][vi], dtype=np.float32)
+    # VRLs that start or end exactly on a wall (what a tracer produces), and VRLs inside a box
+    S[: n // 20, 1] = 0.0
+    En[n // 20: n // 10, 0] = 1.0
+    stats = np.zeros(6, np.uint64)
+    dev, recs = occ
+    ext = float(np.ptp(scene["verts"], axis=0).max())
+    host_lib.alvrl_host_pair_cull_check(C.byref(dev), recs.ctypes.data_as(C.c_void_p), E.ctypes.data_as(C.c_void_p), U.ctypes.data_as(C.c_void_p),
+                                        S.ctypes.data_as(C.c_void_p), En.ctypes.data_as(C.c_void_p), C.c_uint32(n), C.c_uint32(10),
+                                        C.c_uint64(3), C.c_float(1e-5 * ext), stats.ctypes.data_as(C.c_void_p))
+    mism, boxC, boxT, plC, plT, occl = (int(x) for x in stats)
+    print(f"pair culling: {mism} mismatches in {n * 10} segments ({occl} occluded); boxes culled {boxC / boxT:.2%}, planes culled {plC / plT:.2%}")
+    assert mism == 0
+    assert occl > 0.05 * n * 10
+    assert plC / plT > 0.7 and boxC / boxT > 0.2
