@@ -1060,12 +1060,29 @@ struct Workspace {
         RfScratch scr;
         scr.keys = dKeysG.p; scr.w = dWG.p; scr.Wf = dWG.p + (size_t) grid * N; scr.Wr = dWG.p + (size_t) grid * 2 * N; scr.pairs = dPairsG.p;
         scr.keyStride = keyStride; scr.stepStride = N; scr.unfoldRows = getenv("ALVRL_RF_UNFOLD") ? 1u : 0u;
+        /* gangs: clusters of >= gangMin columns are split by several CTAs together (refine_split.inl); ALVRL_GANG_MIN=0 turns them off */
+        scr.gangMin = 8192u; scr.gangMax = RF_GANG_MAX;
+        if (const char *e = getenv("ALVRL_GANG_MIN")) scr.gangMin = (uint32_t) std::max(0, atoi(e));
+        if (const char *e = getenv("ALVRL_GANG_MAX")) scr.gangMax = (uint32_t) std::min(RF_GANG_MAX, std::max(1, atoi(e)));
+        /* a gang trades CTA time (members wait for each other) for latency: worth it while there are fewer large clusters than
+         * CTAs, i.e. when a GPU holds few objects (one rank of a multi-GPU job).  With `load` objects per CTA a root cluster of N
+         * columns gets about 1 / load CTAs: gangMin = load x N (ALVRL_GANG_LOAD scales it) */
+        if (scr.gangMin && !getenv("ALVRL_GANG_MIN")) {
+            double scale = 1.0;
+            if (const char *e = getenv("ALVRL_GANG_LOAD")) scale = atof(e);
+            const double perCta = (double) dev.size() / (double) std::max(1, sms);
+            scr.gangMin = std::max<uint32_t>(scr.gangMin, (uint32_t) std::min(4e9, scale * perCta * (double) N));
+        }
+        if (scr.gangMin && scr.gangMin < 2u * RF_SMALL) scr.gangMin = 2u * RF_SMALL;          /* gangs use the large-cluster code path */
+        DevBuf<double> dCarry; dCarry.alloc((size_t) grid * 2 * RF_GANG_MAX * RF_MAXROWS);
+        scr.carry = dCarry.p;
         scr.snapHeap = dSnap.p; scr.nodes = dNodes.p; scr.singles = dSingles.p; scr.heapOv = dHeapOv.p; scr.heapCap = heapCap; scr.nodeCap = nodeCap;
         scr.srcPos = dSrcPos.p; scr.posTmp = dSrcPos.p + (size_t) grid * N;
         scr.initNodes = dInitNodes.p; scr.initSingles = dInitSingles.p; scr.outNodes = dOutNodes.p; scr.outSingles = dOutSingles.p; scr.cursors = dCursors.p;
         if (mt) {
             /* the ticket ring: at most MT_K split tasks or one control task per object are in flight */
-            uint32_t qcap = 65536; while (qcap < 4 * (MT_K + 1) * dev.size()) qcap <<= 1;
+            const size_t gangTickets = scr.gangMin ? (size_t) (N / scr.gangMin + 1) * RF_GANG_MAX : 0;   /* per object, on top of MT_K */
+            uint32_t qcap = 65536; while (qcap < 4 * (MT_K + 1 + gangTickets) * dev.size()) qcap <<= 1;
             dSlots.alloc(qcap); dMtClk.alloc((size_t) grid * 32);
             ALVRL_CUDA(cudaMemsetAsync(dSlots.p, 0, qcap * sizeof(unsigned long long), st));
             ALVRL_CUDA(cudaMemsetAsync(dOutstanding.p, 0, pool * sizeof(uint32_t), st));
@@ -1091,6 +1108,7 @@ struct Workspace {
                 for (size_t i = 0; i < ck.size(); i++) t[i % 32] += ck[i];
                 fprintf(stderr, "[alvrl clustering]   k_refine_mt on %u CTAs: control passes %llu (%.1f Mcycles), split tasks %llu, waiting for tickets %.1f Mcycles\n",
                         grid, t[26], t[24] * 1e-6, t[27], t[25] * 1e-6);
+                fprintf(stderr, "[alvrl clustering]   gangs (>= %u columns, up to %u CTAs): %llu syncs, %.1f Mcycles waiting in them; sweeps: carries %.1f, main pass %.1f Mcycles\n", scr.gangMin, scr.gangMax, t[29], t[28] * 1e-6, t[30] * 1e-6, t[31] * 1e-6);
                 for (int k = 0; k < 2; k++)
                     fprintf(stderr, "[alvrl clustering]   %s split tasks %llu, Mcycles summed over CTAs: pick %.1f direction %.1f stage %.1f project %.1f sort %.1f weights %.1f sweep %.1f pairs %.1f result %.1f\n",
                             k ? "large" : "small", t[12 * k + 9], t[12 * k + 0] * 1e-6, t[12 * k + 1] * 1e-6, t[12 * k + 2] * 1e-6, t[12 * k + 3] * 1e-6, t[12 * k + 4] * 1e-6,

@@ -107,7 +107,7 @@ ALVRL_OCC_HD bool occ_query(const OccDev &oc, const float4 *tris, float ox, floa
                             float tmax, bool need, uint32_t boxActive = 0xffffffffu, uint32_t planeActive = 0xffffffffu) {
     const float INF = INFINITY;
     bool hit = false;
-    const uint32_t nb = oc.numBoxes;
+    const uint32_t nb = boxActive ? oc.numBoxes : 0u;                 /* nothing left to test: skip the loop, not only its bodies */
     for (uint32_t b = 0; b < nb; b++) {
         if (!((boxActive >> b) & 1u)) continue;
         float tn = -INF, tf = INF;
@@ -118,7 +118,7 @@ ALVRL_OCC_HD bool occ_query(const OccDev &oc, const float4 *tris, float ox, floa
     }
     {
         float tn = -INF, tf = INF;
-        for (uint32_t i = 3 * nb; i < oc.numSlabs; i++) {
+        for (uint32_t i = 3 * oc.numBoxes; i < oc.numSlabs; i++) {
             ALVRL_OCC_CLIP(oc.slabA[i], oc.slabB[i].x);
             if (ALVRL_OCC_BITS(oc.slabB[i].y)) {
                 hit |= ALVRL_OCC_TOUCH();
@@ -127,7 +127,8 @@ ALVRL_OCC_HD bool occ_query(const OccDev &oc, const float4 *tris, float ox, floa
         }
     }
     uint32_t mask = 0;
-    for (uint32_t i = 0; i < oc.numPlanes; i++) {
+    const uint32_t np = planeActive ? oc.numPlanes : 0u;
+    for (uint32_t i = 0; i < np; i++) {
         if (!((planeActive >> i) & 1u)) continue;
         const float4 p = oc.planes[i];
         const float den = fmaf(p.x, dx, fmaf(p.y, dy, p.z * dz));

@@ -73,7 +73,19 @@ struct RfScratch {                      /* per CTA */
     const ClusterNode *initNodes; const uint32_t *initSingles; ClusterNode *outNodes; uint32_t *outSingles;
     uint32_t *cursors;                  /* [0] next object, [1] output node cursor, [2] output singleton cursor */
     uint32_t unfoldRows;                /* experiment (ALVRL_RF_UNFOLD): one row per thread in the variance sweeps when nr <= 256 */
+    /* gangs (k_refine_mt): clusters of >= gangMin columns are split by 2 CTAs, >= 2 gangMin by 4, ... up to gangMax (0: off) */
+    uint32_t gangMin, gangMax;
+    double *carry;                      /* [grid][2][RF_GANG_MAX][RF_MAXROWS] row sums of the members' step ranges */
 };
+#define RF_GANG_MAX 16
+/* CTAs that split a cluster of n columns together: a pure function of n (and of the launch), so that every member and the
+ * control pass that hands the cluster out agree */
+__host__ __device__ __forceinline__ uint32_t rf_gang_size(uint32_t n, uint32_t gangMin, uint32_t gangMax) {
+    if (!gangMin || n < gangMin) return 1u;
+    uint32_t g = 2u;
+    while (g < gangMax && (uint64_t) n >= (uint64_t) gangMin * g) g <<= 1;
+    return g;
+}
 
 struct RfShared {
     float tile[RF_TILE_FLOATS];                         /* staged columns of the local matrix (swizzled granules, see k_refine) */
@@ -91,7 +103,8 @@ struct RfShared {
     /* control block (written by thread 0 between barriers) */
     uint32_t inst, begin, end, srcBuf, found, pick[2], flags, done, snap, err, nodeKey, nodePos;
     uint32_t task[2], stop, selCount, sel[32];             /* k_refine_mt: the task in hand, the control pass */
-    unsigned long long mtClk[4];
+    uint32_t gang[3];                                      /* k_refine_mt: gang size, this CTA's member index, the leader's block */
+    unsigned long long mtClk[8];                          /* control cycles, ticket wait, control passes, split tasks, gang sync wait, gang syncs */
     float u1, u2, norm[3];
     /* refinement state (thread 0) */
     uint32_t rngPos, heapCount, nodeCount, singleCount, sHeapCount, sSingleCount, nearTies, splits, degenerate;
@@ -318,6 +331,8 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_refine(float *XA, float *XB, 
             if (tid == 0) { tPhase = clock64(); sm.clk[small ? 0 : 1][9]++; sm.clk[small ? 0 : 1][10] += n; sm.clk[small ? 0 : 1][11] += (n <= TV) ? 0u : n; }
 
             uint32_t *listDst = list;                                  /* this kernel sorts the list in place */
+            const uint32_t gG = 1u, gMi = 0u; uint32_t gPhase = 0u; uint32_t *const gCnt = nullptr, *const gCursor = nullptr; double *const gCarry = nullptr;   /* no gangs here */
+            (void) gPhase; (void) gCnt; (void) gCarry; (void) gCursor;
 #include "refine_split.inl"
             if (tid == 0) {
                 best = sm.rb[0]; second = sm.rs[0]; bi = sm.ri[0];
@@ -468,20 +483,16 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_refine_mt(float *XA, float *X
     extern __shared__ __align__(16) unsigned char rfRaw[];
     RfShared &sm = *reinterpret_cast<RfShared *>(rfRaw);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    unsigned long long *keysG = scr.keys + (uint64_t) blockIdx.x * scr.keyStride;
-    double *wG = scr.w + (uint64_t) blockIdx.x * scr.stepStride, *WfG = scr.Wf + (uint64_t) blockIdx.x * scr.stepStride,
-           *WrG = scr.Wr + (uint64_t) blockIdx.x * scr.stepStride;
-    float2 *pairsG = scr.pairs + (uint64_t) blockIdx.x * 2 * scr.stepStride;
-    uint32_t *srcG = scr.srcPos + (uint64_t) blockIdx.x * scr.stepStride, *posTmp = scr.posTmp + (uint64_t) blockIdx.x * scr.stepStride;
     uint32_t scanIt = 0;
     uint32_t ringPhase = 0;
     if (tid == 0) {
         for (int a = 0; a < 4; a++) rf_mbar_init(&sm.mbar[a >> 1][a & 1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         for (int a = 0; a < 24; a++) sm.clk[a / 12][a % 12] = 0;
-        for (int a = 0; a < 4; a++) sm.mtClk[a] = 0;
+        for (int a = 0; a < 8; a++) sm.mtClk[a] = 0;
     }
     long long tPhase = 0;
+    uint32_t gangCap = 1u; while (gangCap * 2u <= gridDim.x && gangCap * 2u <= min(scr.gangMax, (uint32_t) RF_GANG_MAX)) gangCap <<= 1;   /* a gang never exceeds the grid */
 
     for (;;) {
         /* ---- draw a ticket and wait for its task ---- */
@@ -526,8 +537,26 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_refine_mt(float *XA, float *X
                 sm.u1 = alvrl_rng_uniform(sm.nodeKey, 0); sm.u2 = alvrl_rng_uniform(sm.nodeKey, 1); sm.nodePos = 2;   /* 597-602 */
                 sm.flags = 0; sm.found = 0xffffffffu; sm.err = RF_DONE; sm.degenerate = 0;
                 sm.mtClk[3]++;
+                /* a large cluster arrives as G identical, consecutive tickets: the CTAs that draw them form a gang.  Members are
+                 * numbered in the order they arrive (node.pad[2]); the first one leads: its scratch arrays are the gang's */
+                const uint32_t G = rf_gang_size(sm.end - sm.begin, scr.gangMin, gangCap);
+                uint32_t mi = 0, leader = blockIdx.x;
+                if (G > 1u) {
+                    mi = atomicAdd(&nd->pad[2], 1u);
+                    if (mi == 0u) { atomicExch(&nd->pad[0], blockIdx.x + 1u); }
+                    else { uint32_t l; while ((l = *(volatile uint32_t *) &nd->pad[0]) == 0u) __nanosleep(64); leader = l - 1u; }
+                }
+                sm.gang[0] = G; sm.gang[1] = mi; sm.gang[2] = leader;
             }
             __syncthreads();
+            const uint32_t gG = sm.gang[0], gMi = sm.gang[1], gLead = sm.gang[2];
+            uint32_t gPhase = 0u; uint32_t *const gCnt = &nd->pad[1], *const gCursor = &nd->bi;   /* bi is free until the leader reports */
+            double *const gCarry = scr.carry + (uint64_t) gLead * 2u * RF_GANG_MAX * RF_MAXROWS;
+            unsigned long long *keysG = scr.keys + (uint64_t) gLead * scr.keyStride;
+            double *wG = scr.w + (uint64_t) gLead * scr.stepStride, *WfG = scr.Wf + (uint64_t) gLead * scr.stepStride,
+                   *WrG = scr.Wr + (uint64_t) gLead * scr.stepStride;
+            float2 *pairsG = scr.pairs + (uint64_t) gLead * 2 * scr.stepStride;
+            uint32_t *srcG = scr.srcPos + (uint64_t) gLead * scr.stepStride, *posTmp = scr.posTmp + (uint64_t) gLead * scr.stepStride;
             const uint32_t begin = sm.begin, n = sm.end - sm.begin;
             const uint32_t srcBuf = sm.srcBuf;
             const uint32_t *list = (srcBuf ? L1 : L0) + I->listOff + begin;
@@ -545,6 +574,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_refine_mt(float *XA, float *X
                 } while (0);
             } else if (tid == 0) sm.err = RF_ERR_SPLIT;
             __syncthreads();
+            if (gMi != 0u) continue;                     /* gang members are done; the leader reports (an error is the same on every member) */
             if (tid == 0) {
                 uint32_t flags = 0;
                 if (sm.err != RF_DONE) flags = sm.err << 28;
@@ -785,7 +815,16 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_refine_mt(float *XA, float *X
                 if (sm.selCount) {
                     __threadfence();
                     atomicAdd(mp.outstanding + o, sm.selCount);                 /* before the tasks can complete */
-                    mt_push(mp, 0u, o, sm.sel, sm.selCount);
+                    /* clusters for one CTA go out together; a cluster for a gang goes out as G consecutive tickets of its own
+                     * (consecutive: the CTAs draw tickets in order, so no later task can be waited for before a gang is complete) */
+                    uint32_t plain[32], np = 0;
+                    for (uint32_t q = 0; q < sm.selCount; q++) {
+                        const MtNode &sn = nodes[sm.sel[q]];
+                        const uint32_t G = rf_gang_size(sn.end - (sn.begin & 0x7fffffffu), scr.gangMin, gangCap);
+                        if (G > 1u) { uint32_t ids[RF_GANG_MAX]; for (uint32_t a = 0; a < G; a++) ids[a] = sm.sel[q]; mt_push(mp, 0u, o, ids, G); }
+                        else plain[np++] = sm.sel[q];
+                    }
+                    if (np) mt_push(mp, 0u, o, plain, np);
                 }
                 __threadfence();
                 if (atomicCAS(mp.ctl + o, 1u, 0u) != 1u) {                      /* a result the object waits for arrived meanwhile: run again */
@@ -800,7 +839,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_refine_mt(float *XA, float *X
     if (tid == 0 && mp.clk) {
         unsigned long long *out = mp.clk + (uint64_t) blockIdx.x * 32;
         for (int a = 0; a < 24; a++) out[a] = sm.clk[a / 12][a % 12];
-        for (int a = 0; a < 4; a++) out[24 + a] = sm.mtClk[a];
+        for (int a = 0; a < 8; a++) out[24 + a] = sm.mtClk[a];
     }
 }
 

@@ -7,9 +7,34 @@
  *   begin, n, small, list (the cluster's VRLs, read) and listDst (where the sorted order goes; may alias list),
  *   Xs / Xd (the cluster's columns in list order, read / in sorted order, written), keys, wA / WfA / WrA, pairsF / pairsR,
  *   srcG / posTmp, scanIt, ringPhase, tPhase, and sm.u1 / sm.u2 / sm.nodeKey / sm.nodePos (the cluster's sample sub-stream).
+ * Gangs (k_refine_mt only): a large cluster is split by gG CTAs together (gMi = this CTA's index in the gang, 0 = leader;
+ * gG == 1: no gang).  Every member runs the cheap sequential parts redundantly (the two draws, the direction: pure functions
+ * of the cluster), the column loops of the projections, the sort passes, the sorted copy and the step ranges of the variance
+ * sweeps are dealt to the members, the scratch arrays are the leader's, and RF_GANG_SYNC() -- a counter in the node record --
+ * separates the phases.  The sweeps of a member start from carries S_r(k0 - 1) that a cheap first pass sums per step range
+ * (the same re-association of the double sums as the segment carries of the batched pipeline, clustering.cu).
  * A `break` leaves the enclosing loop with sm.err set.  On exit, warp w's candidate is in sm.rb / sm.rs / sm.ri [w], the
  * sorted (projection, vrl) keys are in keys[], and pairsF / pairsR hold the head / tail variance pairs.
  */
+#ifndef RF_GANG_SYNC
+/* all members of the gang have finished the phase, and what they wrote is visible (the fence invalidates this SM's L1) */
+#define RF_GANG_SYNC()                                                                              \
+    do {                                                                                            \
+        __syncthreads();                                                                            \
+        if (gG > 1u) {                                                                              \
+            gPhase += gG;                                                                           \
+            if (tid == 0) {                                                                         \
+                const long long gw0_ = clock64();                                                   \
+                __threadfence();                                                                    \
+                atomicAdd(gCnt, 1u);                                                                \
+                while (*(volatile uint32_t *) gCnt < gPhase) __nanosleep(64);                       \
+                __threadfence();                                                                    \
+                sm.mtClk[4] += (unsigned long long) (clock64() - gw0_); sm.mtClk[5]++;              \
+            }                                                                                       \
+            __syncthreads();                                                                        \
+        }                                                                                           \
+    } while (0)
+#endif
             /* ---- weightedSample x 2 (597-602, 1534-1580) ---- */
             const uint32_t numChunks = (n + RF_CHUNK - 1) / RF_CHUNK;
             uint32_t idx[2] = {0, 0};
@@ -173,7 +198,7 @@
                  * at slot g ^ ((c >> 1) & 3) of the column's 64 bytes: the LDS.128 of 8 consecutive threads cover 8 distinct slots. */
                 float *const pbuf0 = sm.tile, *const pbuf1 = sm.tile + RF_THREADS * 16;
                 const uint32_t nrb = (nq + 3u) >> 2;
-                for (uint32_t c0 = 0; c0 < n; c0 += RF_THREADS) {
+                for (uint32_t c0 = gMi * RF_THREADS; c0 < n; c0 += gG * RF_THREADS) {
                     const uint32_t cc = min((uint32_t) RF_THREADS, n - c0);
                     auto stageRows = [&](uint32_t rb) {
                         float *dst = (rb & 1u) ? pbuf1 : pbuf0;
@@ -225,42 +250,47 @@
              *      up to RF_SORT_BLOCK keys in one piece (the tile is free when the keys live in global memory), more as
              *      block-local passes plus global steps for the strides that span blocks ---- */
             uint32_t m = 2; while (m < n) m <<= 1;
-            for (uint32_t i = n + tid; i < m; i += RF_THREADS) { keys[i] = ~0ull; if (small) sm.pos[i] = 0; }
-            __syncthreads();
+            for (uint32_t i = n + gMi * RF_THREADS + tid; i < m; i += gG * RF_THREADS) { keys[i] = ~0ull; if (small) sm.pos[i] = 0; }
+            RF_GANG_SYNC();
             RF_TICK(3);
             if (small) {
                 for (uint32_t k = 2; k <= m; k <<= 1) rf_sort_steps(sm.keys, m, 0, k, k >> 1, sm.pos);
             } else {
                 unsigned long long *sk = reinterpret_cast<unsigned long long *>(sm.tile);
-                const uint32_t blkLen = min(m, (uint32_t) RF_SORT_BLOCK);
-                for (uint32_t blk = 0; blk < m; blk += blkLen) {                /* every block sorted (direction by global index) */
+                const uint32_t blkLen = min(m, (uint32_t) RF_SORT_BLOCK), nblk = m / blkLen;
+                for (uint32_t bq = gMi; bq < nblk; bq += gG) {                  /* every block sorted (direction by global index) */
+                    const uint32_t blk = bq * blkLen;
                     for (uint32_t i = tid; i < blkLen; i += RF_THREADS) sk[i] = keys[blk + i];
                     __syncthreads();
                     for (uint32_t k = 2; k <= blkLen; k <<= 1) rf_sort_steps(sk, blkLen, blk, k, k >> 1, nullptr);
                     for (uint32_t i = tid; i < blkLen; i += RF_THREADS) keys[blk + i] = sk[i];
                     __syncthreads();
                 }
+                RF_GANG_SYNC();
+                const uint32_t tPer = (m >> 1) / gG;                            /* compare-exchange pairs per member (powers of two) */
                 for (uint32_t k = 2 * blkLen; k <= m; k <<= 1) {                /* merges across blocks */
                     for (uint32_t j = k >> 1; j >= blkLen; j >>= 1) {
-                        for (uint32_t t = tid; t < (m >> 1); t += RF_THREADS) {
+                        for (uint32_t t = gMi * tPer + tid; t < (gMi + 1u) * tPer; t += RF_THREADS) {
                             const uint32_t lo = ((t & ~(j - 1)) << 1) | (t & (j - 1)), hi = lo | j;
                             const unsigned long long a = keys[lo], b = keys[hi];
                             if ((a > b) == ((lo & k) == 0)) { keys[lo] = b; keys[hi] = a; }
                         }
-                        __syncthreads();
+                        RF_GANG_SYNC();
                     }
-                    for (uint32_t blk = 0; blk < m; blk += blkLen) {
+                    for (uint32_t bq = gMi; bq < nblk; bq += gG) {
+                        const uint32_t blk = bq * blkLen;
                         for (uint32_t i = tid; i < blkLen; i += RF_THREADS) sk[i] = keys[blk + i];
                         __syncthreads();
                         rf_sort_steps(sk, blkLen, blk, k, blkLen >> 1, nullptr);
                         for (uint32_t i = tid; i < blkLen; i += RF_THREADS) keys[blk + i] = sk[i];
                         __syncthreads();
                     }
+                    RF_GANG_SYNC();
                 }
             }
             RF_TICK(4);
-            /* ---- sorted list, weights and prefix weights (forward and reverse order) ---- */
-            {
+            /* ---- sorted list, weights and prefix weights (forward and reverse order); the gang leader alone ---- */
+            if (gMi == 0u) {
                 double cW[2] = {0, 0};
                 for (uint32_t k0 = 0; k0 < n; k0 += RF_THREADS) {
                     const uint32_t k = k0 + tid, cnt = min((uint32_t) RF_THREADS, n - k0);
@@ -278,29 +308,47 @@
                 }
             }
             /* the sorted copy: from the tile when the local matrix is resident, else gathered column by column (the variance
-             * sweeps then stream it with bulk copies) */
+             * sweeps then stream it with bulk copies).  In a gang the members start on it at once -- they look the source column
+             * up themselves (posTmp[vrl]) -- and claim chunks of 256 columns from a cursor, so that the leader, busy with the
+             * prefix weights above, only takes what is left when it gets here. */
             if (fits) {
                 for (uint32_t i = tid; i < n * nq; i += RF_THREADS) {
                     const uint32_t k = i / nq, q = i - k * nq, pc = sm.pos[k];
                     *reinterpret_cast<float4 *>(Xd + (size_t) k * nrP + 4 * q) = *reinterpret_cast<const float4 *>(sm.tile + pc * tS + 4 * (q ^ (pc & 7u)));
                 }
             } else {
-                for (uint32_t k4 = warp * 4; k4 < n; k4 += RF_WARPS * 4) {     /* warp = column, four columns in flight */
-                    const float4 *src[4];
+                auto copyColumns = [&](uint32_t kFrom, uint32_t kTo, uint32_t stride) {
+                    for (uint32_t k4 = kFrom + warp * 4; k4 < kTo; k4 += stride) {     /* warp = column, four columns in flight */
+                        const float4 *src[4];
 #pragma unroll
-                    for (int u = 0; u < 4; u++) { const uint32_t k = min(k4 + u, n - 1); src[u] = reinterpret_cast<const float4 *>(Xs + (size_t) (small ? (uint32_t) sm.pos[k] : srcG[k]) * nrP); }
-                    for (uint32_t q = lane; q < nq; q += 32) {
-                        float4 e[4];
+                        for (int u = 0; u < 4; u++) {
+                            const uint32_t k = min(k4 + u, kTo - 1);
+                            const uint32_t sp = small ? (uint32_t) sm.pos[k] : (gG > 1u ? posTmp[(uint32_t) (keys[k] & 0xffffffffull)] : srcG[k]);
+                            src[u] = reinterpret_cast<const float4 *>(Xs + (size_t) sp * nrP);
+                        }
+                        for (uint32_t q = lane; q < nq; q += 32) {
+                            float4 e[4];
 #pragma unroll
-                        for (int u = 0; u < 4; u++) e[u] = src[u][q];
+                            for (int u = 0; u < 4; u++) e[u] = src[u][q];
 #pragma unroll
-                        for (int u = 0; u < 4; u++) if (k4 + u < n) reinterpret_cast<float4 *>(Xd + (size_t) (k4 + u) * nrP)[q] = e[u];
+                            for (int u = 0; u < 4; u++) if (k4 + u < kTo) reinterpret_cast<float4 *>(Xd + (size_t) (k4 + u) * nrP)[q] = e[u];
+                        }
                     }
-                }
+                };
+                if (gG > 1u) {
+                    for (;;) {
+                        __syncthreads();
+                        if (tid == 0) sm.found = atomicAdd(gCursor, 1u);
+                        __syncthreads();
+                        const uint32_t kFrom = sm.found * 256u;
+                        if (kFrom >= n) break;
+                        copyColumns(kFrom, min(n, kFrom + 256u), RF_WARPS * 4);
+                    }
+                } else copyColumns(0, n, RF_WARPS * 4);
                 __threadfence_block();
                 asm volatile("fence.proxy.async;" ::: "memory");
             }
-            __syncthreads();
+            RF_GANG_SYNC();
             RF_TICK(5);
             /* ---- calculateClusterVariance (1058-1120): the forward sweep on threads 0..255 and the reverse sweep on threads
              *      256..511, thread = row, sequential over the sorted steps (S_r is a running sum, accesses are contiguous across
@@ -318,9 +366,15 @@
                 uint32_t KC = min(32u, (uint32_t) (RF_TILE_FLOATS / 4) / nrP);
                 if (KC > 16u && KC < 32u) KC = 16u;
                 float *ring = sm.tile + half * (RF_TILE_FLOATS / 2);
-                const uint32_t nch = (n + KC - 1) / KC;
+                /* the steps of this gang member: [kBeg, kEnd) of the forward order and of the reverse order; the boundaries are
+                 * symmetric (b_g + b_{G-g} = n) */
+                auto gBound = [&](uint32_t g) -> uint32_t {
+                    return 2u * g <= gG ? (uint32_t) (((uint64_t) g * n) / gG) : n - (uint32_t) (((uint64_t) (gG - g) * n) / gG);
+                };
+                const uint32_t kBeg = gG > 1u ? gBound(gMi) : 0u, kEnd = gG > 1u ? gBound(gMi + 1u) : n;
+                const uint32_t nch = (kEnd - kBeg + KC - 1) / KC;
                 auto issue = [&](uint32_t c) {                                          /* the columns of chunk c -> ring stage c & 1 */
-                    const uint32_t k0 = c * KC, cnt = min(KC, n - k0);
+                    const uint32_t k0 = kBeg + c * KC, cnt = min(KC, kEnd - k0);
                     if (hr == 0) {
                         asm volatile("fence.proxy.async;" ::: "memory");
                         const uint32_t bytes = cnt * nrP * (uint32_t) sizeof(float);
@@ -342,10 +396,56 @@
                 const bool actA = hr < RS && rA < nr, actB = hr < RS && rB < nr;
                 const uint32_t nw = RS >> 5;
                 double SA = 0, SB = 0;
+                const long long gs0_ = clock64();
+                if (gG > 1u) {
+                    /* carries: the row sums of every member's step range (one streaming pass over its columns, rows in step
+                     * order), then S_r(kBeg - 1) = the sums of the ranges before this one */
+                    /* all threads stream the range: thread = (granule of 4 rows, column slot), 8 columns in flight each, the slots'
+                     * partial sums meet in shared memory (the tile is free until the main pass stages into it) */
+                    {
+                        const uint32_t slots = RF_THREADS / nq, q = tid % nq, slot = tid / nq;
+                        double *part4 = reinterpret_cast<double *>(sm.tile);                /* [slots][nrP] */
+                        for (uint32_t dirc = 0; dirc < 2; dirc++) {
+                            double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+                            if (slot < slots) {
+                                for (uint32_t k = kBeg + slot; k < kEnd; k += 8u * slots) {
+                                    float4 e[8];
+#pragma unroll
+                                    for (int u = 0; u < 8; u++) {
+                                        const uint32_t kk = k + (uint32_t) u * slots;
+                                        e[u] = make_float4(0, 0, 0, 0);
+                                        if (kk < kEnd) e[u] = __ldcg(reinterpret_cast<const float4 *>(Xd + (size_t) (dirc ? n - 1 - kk : kk) * nrP) + q);
+                                    }
+#pragma unroll
+                                    for (int u = 0; u < 8; u++) { a0 += (double) e[u].x; a1 += (double) e[u].y; a2 += (double) e[u].z; a3 += (double) e[u].w; }
+                                }
+                                double *o4 = part4 + (size_t) slot * nrP + 4u * q;
+                                o4[0] = a0; o4[1] = a1; o4[2] = a2; o4[3] = a3;
+                            }
+                            __syncthreads();
+                            for (uint32_t r = tid; r < nrP; r += RF_THREADS) {
+                                double t = 0;
+                                for (uint32_t sl = 0; sl < slots; sl++) t += part4[(size_t) sl * nrP + r];
+                                gCarry[(size_t) (dirc * gG + gMi) * RF_MAXROWS + r] = t;
+                            }
+                            __syncthreads();
+                        }
+                    }
+                    if (tid == 0) sm.mtClk[6] += (unsigned long long) (clock64() - gs0_);
+                    RF_GANG_SYNC();
+                    if (hw < nw) {
+                        for (uint32_t g = 0; g + 1u <= gMi; g++) {
+                            const double *theirs = gCarry + (size_t) (half * gG + g) * RF_MAXROWS;
+                            if (actA) SA += __ldcg(theirs + rA);
+                            if (actB) SB += __ldcg(theirs + rB);
+                        }
+                    }
+                }
                 uint32_t buf = 0;
-                if (!fits) issue(0);
+                const long long gs1_ = clock64();
+                if (!fits && nch) issue(0);
                 for (uint32_t c = 0; c < nch; c++) {
-                    const uint32_t k0 = c * KC, cnt = min(KC, n - k0);
+                    const uint32_t k0 = kBeg + c * KC, cnt = min(KC, kEnd - k0);
                     if (!fits) {
                         if (c + 1 < nch) { issue(c + 1); rf_cp_wait<1>(); } else rf_cp_wait<0>();
                         rf_mbar_wait(&sm.mbar[half][c & 1u], (ringPhase >> (c & 1u)) & 1u);
@@ -409,9 +509,11 @@
                     }
                     buf ^= 1;
                 }
+                if (tid == 0 && gG > 1u) sm.mtClk[7] += (unsigned long long) (clock64() - gs1_);
             }
-            __syncthreads();
+            RF_GANG_SYNC();
             RF_TICK(6);
+            if (gMi != 0u) break;                       /* the leader alone turns the B_k into variance pairs and finds the split */
             /* prefix pairs (1098-1106), thread = step: first = lw W_k Q_k, second = lw W_k SV_k */
             for (uint32_t dir = 0; dir < 2; dir++) {
                 const double *WA = dir ? WrA : WfA;

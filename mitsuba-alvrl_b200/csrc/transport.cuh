@@ -46,7 +46,7 @@
 #define ALVRL_CTA_SEGS 128
 
 /* ---- flavoured math ---------------------------------------------------------------------------- */
-#ifdef ALVRL_FAST
+#if defined(ALVRL_FAST) && !defined(ALVRL_DIAG_EXACT_M)
 __device__ __forceinline__ float m_exp(float x) { return __expf(x); }
 __device__ __forceinline__ float m_rcp(float x) { return __frcp_rn(x); }
 __device__ __forceinline__ float m_div(float a, float b) { return __fdividef(a, b); }
@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(ALVRL_CTA_SEGS, ALVRL_MIN_CTAS) ALVRL_NAME(k_b
             for (uint32_t j = 0; j < cnt; j++) {
                 float mean = 0, var = 0;
                 const uint32_t v = v0 + j;
-#ifdef ALVRL_FAST
+#if defined(ALVRL_FAST) && !defined(ALVRL_DIAG_GENERIC)
                 if constexpr (MED != 1) {
                     /* every lane of the warp takes part (the shadow rays of a warp are traced from a shared pool) */
                     const VrlRec &vr = sm.tile[t & 1][j];

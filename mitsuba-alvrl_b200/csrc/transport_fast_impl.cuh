@@ -126,9 +126,52 @@ __device__ __forceinline__ bool occluded_fast(const TransportParams &P, const Bv
     return bvh_occluded_fast(P.scene, p1, dir, mint, remaining);
 }
 
+/* diagnostic variants (tools/build_variant.sh -DALVRL_DIAG_*): accurate library functions in place of the MUFU forms, to
+ * attribute the deviation from the oracle to its sources */
+#ifdef ALVRL_DIAG_EXP
+__device__ __forceinline__ float f_exp(float x) { return expf(x); }
+#else
+__device__ __forceinline__ float f_exp(float x) { return __expf(x); }
+#endif
+#ifdef ALVRL_DIAG_SINH
+__device__ __forceinline__ float f_sinh(float a) { return sinhf(a); }
+__device__ __forceinline__ float f_asinh(float x) { return asinhf(x); }
+#elif defined(ALVRL_SINH_MUFU_ONLY)
 __device__ __forceinline__ float f_sinh(float a) { const float e = __expf(a); return 0.5f * (e - f_rcp(e)); }
 __device__ __forceinline__ float f_asinh(float x) { const float a = fabsf(x); return copysignf(__logf(a + sqrtf(fmaf(a, a, 1.0f))), x); }
+#else
+/* sinh / asinh through MUFU (ex2, lg2) away from zero, odd polynomials near zero: (e^a - e^-a) / 2 and log(a + sqrt(a^2 + 1))
+ * lose their leading digits there (relative error eps / |a|), and V is sampled AROUND the closest point of the VRL, i.e.
+ * around a = 0; measured on C2 (tools/probe_parity.py) the MUFU-only forms put 2.6e-4 of the R entries beyond 1e-4 */
+__device__ __forceinline__ float f_sinh(float a) {
+    const float e = __expf(a);
+    const float big = 0.5f * (e - f_rcp(e));
+    const float a2 = a * a;
+    const float small = a * fmaf(a2, fmaf(a2, fmaf(a2, 1.0f / 5040.0f, 1.0f / 120.0f), 1.0f / 6.0f), 1.0f);   /* |a| < 0.5: 3e-9 relative */
+    return fabsf(a) < 0.5f ? small : big;
+}
+__device__ __forceinline__ float f_asinh(float x) {
+    const float a = fabsf(x), a2 = a * a;
+    const float big = __logf(a + sqrtf(fmaf(a, a, 1.0f)));
+    const float small = a * fmaf(a2, fmaf(a2, fmaf(a2, -15.0f / 336.0f, 3.0f / 40.0f), -1.0f / 6.0f), 1.0f);   /* a < 0.125: 4e-9 relative */
+    return copysignf(a < 0.125f ? small : big, x);
+}
+#endif
+#ifdef ALVRL_DIAG_TAN
+__device__ __forceinline__ float f_tan(float x) { return tanf(x); }
+#else
 __device__ __forceinline__ float f_tan(float x) { return __tanf(x); }
+#endif
+#ifdef ALVRL_DIAG_ATAN
+__device__ __forceinline__ float f_atan(float x) { return (float) atan((double) x); }
+#else
+__device__ __forceinline__ float f_atan(float x) { return atanf(x); }
+#endif
+#ifdef ALVRL_DIAG_DIV
+#define f_div(a, b) ((a) / (b))
+#else
+#define f_div(a, b) __fdividef(a, b)
+#endif
 __device__ __forceinline__ float f_len(const F3 &a, float &l2) { l2 = len2(a); return l2 * rsqrtf(fmaxf(l2, 1e-38f)); }
 
 /* homogeneous media only (MED 0: RGB sigma_t, MED 2: grey sigma_t) */
@@ -165,10 +208,10 @@ __device__ __forceinline__ void integrate_pair_fast(const TransportParams &P, co
             dVhS = f_len(Vh - S, l2);
             const float V1c = f_len(Vh - End, l2);
             rSin = f_rcp(sinTheta);
-            const float sh = __fdividef(sinTheta, h);
+            const float sh = f_div(sinTheta, h);
             A0 = f_asinh(-dVhS * sh);
             dA = f_asinh(V1c * sh) - A0;
-            pdfVc = __fdividef(sinTheta, dA);                              /* 1 / denom, denom = (A1 - A0) / sinTheta */
+            pdfVc = f_div(sinTheta, dA);                              /* 1 / denom, denom = (A1 - A0) / sinTheta */
         }
         const float invNvv = f_rcp((float) Nvv);
         float mean = 0, M2 = 0;
@@ -190,9 +233,9 @@ __device__ __forceinline__ void integrate_pair_fast(const TransportParams &P, co
             float l2;
             const float Dis = f_len(V - I, l2);
             const float rDis = f_rcp(Dis);
-            const float th_a = atanf(-dotPr * rDis), th_b = atanf((edist - dotPr) * rDis);
+            const float th_a = f_atan(-dotPr * rDis), th_b = f_atan((edist - dotPr) * rDis);
             const float t = Dis * f_tan(fmaf(u2, th_b - th_a, th_a));
-            pdf *= __fdividef(Dis, (th_b - th_a) * fmaf(t, t, l2));
+            pdf *= f_div(Dis, (th_b - th_a) * fmaf(t, t, l2));
             const F3 U = I + t * EU;
             const F3 UV = U - V;
             float d2;
@@ -208,14 +251,14 @@ __device__ __forceinline__ void integrate_pair_fast(const TransportParams &P, co
                 const float path = dSV + dUV + dEU;
                 float T0, T1, T2, pf;
                 if (MED == 2) {
-                    T0 = T1 = T2 = __expf(-sT0 * path);
-                    pf = fmaf(__expf(-sT0 * dSV), wS, wF);
+                    T0 = T1 = T2 = f_exp(-sT0 * path);
+                    pf = fmaf(f_exp(-sT0 * dSV), wS, wF);
                 } else {
-                    T0 = __expf(-sT0 * path); T1 = __expf(-sT1 * path); T2 = __expf(-sT2 * path);
-                    pf = fmaf((__expf(-sT0 * dSV) + __expf(-sT1 * dSV) + __expf(-sT2 * dSV)) * (1.0f / 3.0f), wS, wF);
+                    T0 = f_exp(-sT0 * path); T1 = f_exp(-sT1 * path); T2 = f_exp(-sT2 * path);
+                    pf = fmaf((f_exp(-sT0 * dSV) + f_exp(-sT1 * dSV) + f_exp(-sT2 * dSV)) * (1.0f / 3.0f), wS, wF);
                 }
-                float common = __fdividef(1.0f, pdf * d2);
-                if (P.shortVrls) common = __fdividef(common, pf);
+                float common = f_div(1.0f, pdf * d2);
+                if (P.shortVrls) common = f_div(common, pf);
                 common *= phase_eval(M, dot(VU, EU)) * phase_eval(M, -dot(SV, VU));
                 const float c0 = k0 * T0 * common, c1 = k1 * T1 * common, c2 = k2 * T2 * common;
                 if (isfinite(c0) && isfinite(c1) && isfinite(c2) && c0 >= 0.0f && c1 >= 0.0f && c2 >= 0.0f) {   /* isValid(), 686 */
@@ -225,11 +268,11 @@ __device__ __forceinline__ void integrate_pair_fast(const TransportParams &P, co
             }
             if (WANT_STAT) {                                                 /* 693-699 */
                 const float delta = lum - mean;
-                mean += __fdividef(delta, (float) (k + 1));
+                mean += f_div(delta, (float) (k + 1));
                 M2 = fmaf(delta, lum - mean, M2);
             }
         }
-        if (WANT_STAT) { outMean += mean; outVar += __fdividef(M2, (float) ((Nvv - 1) * Nvv)); }
+        if (WANT_STAT) { outMean += mean; outVar += f_div(M2, (float) ((Nvv - 1) * Nvv)); }
     }
 
     /* ---- volume to surface (706-782) ---- */
@@ -247,8 +290,8 @@ __device__ __forceinline__ void integrate_pair_fast(const TransportParams &P, co
             float l2;
             const float Dis = f_len(Usurf - I, l2);
             const float rDis = f_rcp(Dis);
-            const float th_a = atanf(-dotPr * rDis), th_b = atanf((vlen - dotPr) * rDis);
-            const float pdfC = __fdividef(Dis, th_b - th_a);
+            const float th_a = f_atan(-dotPr * rDis), th_b = f_atan((vlen - dotPr) * rDis);
+            const float pdfC = f_div(Dis, th_b - th_a);
             const float invNvs = f_rcp((float) Nvs);
             const F3 nrm = f3(seg.n);
             const bool frontI = seg.d.w > 0;
@@ -257,7 +300,7 @@ __device__ __forceinline__ void integrate_pair_fast(const TransportParams &P, co
             for (int k = 0; k < Nvs; k++) {
                 const float u = surf ? rng.next() : 0.5f;
                 const float t = Dis * f_tan(fmaf(u, th_b - th_a, th_a));
-                const float pdf = __fdividef(pdfC, fmaf(t, t, l2));
+                const float pdf = f_div(pdfC, fmaf(t, t, l2));
                 const float sv = dotPr + t;                                  /* V = S + sv * SV */
                 const F3 V = S + sv * SV;
                 const F3 UV = Usurf - V;
@@ -273,14 +316,14 @@ __device__ __forceinline__ void integrate_pair_fast(const TransportParams &P, co
                     const float path = dSV + dUV;
                     float T0, T1, T2, pf;
                     if (MED == 2) {
-                        T0 = T1 = T2 = __expf(-sT0 * path);
-                        pf = fmaf(__expf(-sT0 * dSV), wS, wF);
+                        T0 = T1 = T2 = f_exp(-sT0 * path);
+                        pf = fmaf(f_exp(-sT0 * dSV), wS, wF);
                     } else {
-                        T0 = __expf(-sT0 * path); T1 = __expf(-sT1 * path); T2 = __expf(-sT2 * path);
-                        pf = fmaf((__expf(-sT0 * dSV) + __expf(-sT1 * dSV) + __expf(-sT2 * dSV)) * (1.0f / 3.0f), wS, wF);
+                        T0 = f_exp(-sT0 * path); T1 = f_exp(-sT1 * path); T2 = f_exp(-sT2 * path);
+                        pf = fmaf((f_exp(-sT0 * dSV) + f_exp(-sT1 * dSV) + f_exp(-sT2 * dSV)) * (1.0f / 3.0f), wS, wF);
                     }
-                    float common = __fdividef(ALVRL_INV_PI * cosWo, pdf * d2);
-                    if (P.shortVrls) common = __fdividef(common, pf);
+                    float common = f_div(ALVRL_INV_PI * cosWo, pdf * d2);
+                    if (P.shortVrls) common = f_div(common, pf);
                     common *= phase_eval(M, -dot(SV, VU));
                     const float c0 = k0 * T0 * common, c1 = k1 * T1 * common, c2 = k2 * T2 * common;
                     if (isfinite(c0) && isfinite(c1) && isfinite(c2) && c0 >= 0.0f && c1 >= 0.0f && c2 >= 0.0f) {
@@ -290,11 +333,11 @@ __device__ __forceinline__ void integrate_pair_fast(const TransportParams &P, co
                 }
                 if (WANT_STAT) {
                     const float delta = lum - mean;
-                    mean += __fdividef(delta, (float) (k + 1));
+                    mean += f_div(delta, (float) (k + 1));
                     M2 = fmaf(delta, lum - mean, M2);
                 }
             }
         }
-        if (WANT_STAT) { outMean += mean; outVar += __fdividef(M2, (float) ((Nvs - 1) * Nvs)); }
+        if (WANT_STAT) { outMean += mean; outVar += f_div(M2, (float) ((Nvs - 1) * Nvs)); }
     }
 }

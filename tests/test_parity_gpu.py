@@ -134,8 +134,8 @@ def test_R_strict_flavour_within_1e4_c1_shape(pkg, orc):
 
 def test_R_fast_flavour_tolerance(pkg, orc):
     g, o, Rg, Ro = _R_pair(pkg, orc, False, name="C1", w=128, h=128, n=400)
-    em, ev, frac = _check_R(Rg, Ro, 1e-3, 1e-3, 1e-4)      # fast-math flavour: 1e-3 per entry, stated here
-    assert np.median(em) < 1e-5
+    em, ev, frac = _check_R(Rg, Ro, 1e-4, 1e-4, 1e-3)      # fast-math flavour: 1e-4 per entry, <= 1e-3 of the entries outside
+    assert np.median(em) < 1e-6                            # (grazing ties included here; tests/test_c2_parity_gpu.py separates them)
     print(f"fast: median rel err {np.median(em):.2e}, p99.99 {np.quantile(em, 0.9999):.2e}, outliers {frac:.2e}")
 
 
@@ -269,13 +269,17 @@ def test_clusters_identical_given_oracle_R(pkg, orc, kw):
 _LARGE = {}
 
 
-@pytest.mark.parametrize("path", ["many_ctas_per_object", "one_cta_per_object", "host_rounds"])
+@pytest.mark.parametrize("path", ["many_ctas_per_object", "gangs_of_ctas_per_cluster", "no_gangs", "one_cta_per_object", "host_rounds"])
 def test_clusters_large_splits_all_device_paths(pkg, orc, monkeypatch, path):
     """9 000 VRLs: the top of every split tree has clusters beyond the shared-memory limits of the refinement kernels (1 024
     columns, 8 192 sort keys), and a slice is refined through hundreds of splits.  The three ways the product can drive the
     refinement in the counter stream -- CTAs pulling clusters of any object from a queue (default), one CTA per object, and
     host-driven rounds of batched kernels -- must all reproduce the oracle's clusters."""
-    if path == "one_cta_per_object":
+    if path == "gangs_of_ctas_per_cluster":            # clusters of >= 2 048 columns are split by 2 / 4 / 8 CTAs together
+        monkeypatch.setenv("ALVRL_GANG_MIN", "2048")
+    elif path == "no_gangs":
+        monkeypatch.setenv("ALVRL_GANG_MIN", "0")
+    elif path == "one_cta_per_object":
         monkeypatch.setenv("ALVRL_REFINE_ST", "1")
     elif path == "host_rounds":
         monkeypatch.setenv("ALVRL_HOST_ROUNDS", "1")
