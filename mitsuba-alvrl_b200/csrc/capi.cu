@@ -149,14 +149,25 @@ void ensure_primary(alvrl_ctx *c) {
     c->havePrimary = true; c->segsDirty = false;
 }
 
-void invalidate_from_slices(alvrl_ctx *c) { c->haveRows = false; c->haveR = false; c->haveClusters = false; c->haveFallback = false; c->renderListsDirty = true; }
+void invalidate_from_slices(alvrl_ctx *c) { c->pixelListsDirty = true; c->haveRows = false; c->haveR = false; c->haveClusters = false; c->haveFallback = false; c->renderListsDirty = true; }
 
+/* host loop of slices.h (reference order, sequential), then the same device-resident representation the device builder leaves */
 void finish_slices(alvrl_ctx *c, const std::vector<P3> &pos, const std::vector<P3> &dir) {
     SliceTree tree(pos, dir);
-    c->pixelToSlice = tree.build((uint32_t) c->P.targetNumSlices, c->slices);
+    std::vector<SliceInfo> slices;
+    const std::vector<uint32_t> toSlice = tree.build((uint32_t) c->P.targetNumSlices, slices);
+    const uint32_t P = (uint32_t) toSlice.size();
+    std::vector<uint32_t> recIdx; recIdx.reserve(P);
+    c->sliceLo.clear(); c->sliceSize.clear();
+    for (const SliceInfo &si : slices) {
+        c->sliceLo.push_back((uint32_t) recIdx.size()); c->sliceSize.push_back((uint32_t) si.pixels.size());
+        recIdx.insert(recIdx.end(), si.pixels.begin(), si.pixels.end());
+    }
+    recIdx.resize(P, 0u);
+    c->dRecIdx.upload(recIdx, c->stream); c->dPixelToSlice.upload(toSlice, c->stream);
     c->haveSlices = true;
     invalidate_from_slices(c);
-    c->stats.numSlices = (uint32_t) c->slices.size();
+    c->stats.numSlices = c->numSlices();
 }
 
 TransportParams make_transport_params(alvrl_ctx *c, uint32_t domain) {
@@ -176,7 +187,7 @@ TransportParams make_transport_params(alvrl_ctx *c, uint32_t domain) {
 /* reference-stream tape for build_R: the prepass loops draw 2*Nvv (+ Nvs when the vol->surf loop runs) uniforms per
  * (row, vrl), rows in slice order, VRLs in index order (vrlIntegrator.cpp:322-333,804-816) */
 void make_sfmt_tape(alvrl_ctx *c, std::vector<float> &tape) {
-    const uint32_t N = (uint32_t) c->vrlHost.size(), G = (uint32_t) c->rowPixel.size(), K = c->K(), S = (uint32_t) c->slices.size();
+    const uint32_t N = (uint32_t) c->vrlHost.size(), G = (uint32_t) c->rowPixel.size(), K = c->K(), S = c->numSlices();
     const uint64_t need = (uint64_t) G * N * K;
     if (need > (1ull << 31)) throw Error(ALVRL_ERR_UNSUPPORTED, "rngMode=SFMT needs a G*N*(2*Nvv+Nvs) float tape; too large for this configuration");
     tape.assign(need, 0.5f);
@@ -206,17 +217,16 @@ void make_sfmt_tape(alvrl_ctx *c, std::vector<float> &tape) {
 void build_render_lists(alvrl_ctx *c) {
     ensure_vrl_sides(c);
     if (!c->renderListsDirty) return;
-    const uint32_t S = (uint32_t) c->slices.size();
-    std::vector<uint32_t> slicePixels, repOffset(S + 1, 0), repIdx;
+    const uint32_t S = c->numSlices();
+    std::vector<uint32_t> sliceStart(S, 0), repOffset(S + 1, 0), repIdx;
     std::vector<float> repW;
     std::vector<uint4> work;
+    uint32_t total = 0;
     for (uint32_t s = 0; s < S; s++) {
-        std::vector<uint32_t> px = c->slices[s].pixels;
-        std::sort(px.begin(), px.end());                 /* pixel order inside a slice is free: sort for ray coherence */
-        const uint32_t base = (uint32_t) slicePixels.size();
-        slicePixels.insert(slicePixels.end(), px.begin(), px.end());
-        for (uint32_t o = 0; o < px.size(); o += ALVRL_CTA_SEGS_HOST)
-            work.push_back(make_uint4(s, base + o, std::min<uint32_t>(ALVRL_CTA_SEGS_HOST, (uint32_t) px.size() - o), 0));
+        const uint32_t base = total, cnt = c->sliceSize[s];
+        sliceStart[s] = base; total += cnt;
+        for (uint32_t o = 0; o < cnt; o += ALVRL_CTA_SEGS_HOST)
+            work.push_back(make_uint4(s, base + o, std::min<uint32_t>(ALVRL_CTA_SEGS_HOST, cnt - o), 0));
         const std::vector<uint32_t> &vr = c->selectedVrls[s];
         const std::vector<float> &wt = c->clusterWeight[s];
         for (size_t i = 0; i < vr.size(); i++) {
@@ -225,7 +235,8 @@ void build_render_lists(alvrl_ctx *c) {
         }
         repOffset[s + 1] = (uint32_t) repIdx.size();
     }
-    c->dSlicePixels.upload(slicePixels, c->stream);
+    /* the pixel lists are bucketed on the device from pixelToSlice (nearly sorted inside a slice: ray coherence) */
+    if (c->pixelListsDirty) { slice_bucket_pixels_device(c, sliceStart, total); c->pixelListsDirty = false; }
     c->dWork.upload(work, c->stream);
     c->dRepOffset.upload(repOffset, c->stream);
     /* the representatives' records are gathered on the device (they carry the per-VRL side bits of ensure_vrl_sides) */
@@ -245,7 +256,7 @@ void build_render_lists(alvrl_ctx *c) {
 
 /* work items restricted to the slice range of this handle (multi-GPU sharding by slice) */
 void select_work(alvrl_ctx *c, const uint4 *&work, uint32_t &numWork, std::vector<uint4> &tmp, DevBuf<uint4> &dTmp) {
-    const uint32_t S = (uint32_t) c->slices.size();
+    const uint32_t S = c->numSlices();
     const uint32_t sb = std::min(c->sliceBegin, S), se = std::min(c->sliceEnd, S);
     if (sb == 0 && se == S) { work = c->dWork.p; numWork = c->numWork; return; }
     std::vector<uint4> all(c->numWork);
@@ -274,8 +285,8 @@ void render_clustered_into(alvrl_ctx *c, float4 *fb, cudaStream_t st) {
     c->stats.msTransportKernelRender = ms;
     c->stats.kernelLaunches++;
     uint64_t pairs = 0;
-    const uint32_t S = (uint32_t) c->slices.size(), sb = std::min(c->sliceBegin, S), se = std::min(c->sliceEnd, S);
-    for (uint32_t s = sb; s < se; s++) pairs += (uint64_t) c->slices[s].pixels.size() * c->selectedVrls[s].size();
+    const uint32_t S = c->numSlices(), sb = std::min(c->sliceBegin, S), se = std::min(c->sliceEnd, S);
+    for (uint32_t s = sb; s < se; s++) pairs += (uint64_t) c->sliceSize[s] * c->selectedVrls[s].size();
     c->stats.pairsRender += pairs;
     c->stats.shadowRays += pairs * (uint64_t) (c->P.volVolSamples + c->P.volSurfSamples);
 }
@@ -492,17 +503,27 @@ int alvrl_build_slices(alvrl_handle c) {
     launch_gather_points(c->dPixSegs.p, P, directionScale, dPos.p, dDir.p, c->stream);
     c->stats.kernelLaunches++;
     ALVRL_CUDA(cudaGetLastError());
-    std::vector<P3> pos(P), dir(P);
-    static_assert(sizeof(P3) == 12, "P3 is three packed floats");
-    dPos.download(reinterpret_cast<float *>(pos.data()), 3 * (size_t) P, c->stream);
-    dDir.download(reinterpret_cast<float *>(dir.data()), 3 * (size_t) P, c->stream);
-    finish_slices(c, pos, dir);
+    /* the partitions and extrema of getSlicesPQ run on the device (slices_dev.cu); ALVRL_SLICES_HOST=1, or a degenerate node,
+     * takes the sequential host loop over the downloaded gather points instead -- same slices either way */
+    bool onDevice = false;
+    if (!getenv("ALVRL_SLICES_HOST")) {
+        onDevice = build_slices_device(c, dPos.p, dDir.p, P, (uint32_t) c->P.targetNumSlices);
+        if (onDevice) { c->haveSlices = true; invalidate_from_slices(c); c->stats.numSlices = c->numSlices(); }
+    }
+    if (!onDevice) {
+        std::vector<P3> pos(P), dir(P);
+        static_assert(sizeof(P3) == 12, "P3 is three packed floats");
+        dPos.download(reinterpret_cast<float *>(pos.data()), 3 * (size_t) P, c->stream);
+        dDir.download(reinterpret_cast<float *>(dir.data()), 3 * (size_t) P, c->stream);
+        finish_slices(c, pos, dir);
+    }
     c->stats.msSlices = (float) (now_ms() - t0);
     API_END
 }
 
 int alvrl_build_slices_from_gather(alvrl_handle c, const float *pos_, const float *dir_) {
     API_BEGIN
+    use_device(c);
     if (!c->haveCam) throw Error(ALVRL_ERR_STATE, "set_camera first");
     const uint32_t P = c->numPixels();
     std::vector<P3> pos(P), dir(P);
@@ -515,17 +536,20 @@ int alvrl_sample_slice_mapping(alvrl_handle c) {
     API_BEGIN
     if (!c->haveSlices) throw Error(ALVRL_ERR_STATE, "build_slices first");
     double t0 = now_ms();
-    const size_t S = c->slices.size();
-    c->rowOffset.assign(S + 1, 0); c->rowPixel.clear(); c->sliceUndersampling.resize(S);
+    use_device(c);
+    const size_t S = c->numSlices();
+    c->rowOffset.assign(S + 1, 0); c->sliceUndersampling.resize(S);
     size_t totalPix = 0, totalRep = 0;
+    std::vector<uint32_t> positions;                       /* of the chosen pixels in the partition-ordered pixel array */
     for (size_t i = 0; i < S; i++) {
         c->mainSampler->setContext(ALVRL_RNG_SLICEMAP, (uint32_t) i, 0);
-        std::vector<uint32_t> px = sampleRepresentativePixels(c->slices[i], c->P.targetPixelUndersampling, c->mainSampler.get());
-        c->rowPixel.insert(c->rowPixel.end(), px.begin(), px.end());
-        c->rowOffset[i + 1] = (uint32_t) c->rowPixel.size();
-        c->sliceUndersampling[i] = ((float) px.size()) / c->slices[i].pixels.size();      /* Preprocessor.cpp:1513 */
-        totalRep += px.size(); totalPix += c->slices[i].pixels.size();
+        const std::vector<uint32_t> idx = sampleRepresentativeIndices(c->sliceSize[i], c->P.targetPixelUndersampling, c->mainSampler.get());
+        for (uint32_t k : idx) positions.push_back(c->sliceLo[i] + k);
+        c->rowOffset[i + 1] = (uint32_t) positions.size();
+        c->sliceUndersampling[i] = ((float) idx.size()) / c->sliceSize[i];      /* Preprocessor.cpp:1513 */
+        totalRep += idx.size(); totalPix += c->sliceSize[i];
     }
+    slice_gather_rows_device(c, positions, c->rowPixel);                          /* rowPixel = pixel ids of the positions */
     c->globalPixelUndersampling = ((float) totalRep) / totalPix;                          /* 1519 */
     c->haveRows = true; c->haveR = false; c->haveClusters = false; c->haveFallback = false;
     c->stats.msSliceMapping = (float) (now_ms() - t0);
@@ -540,8 +564,8 @@ int alvrl_build_R(alvrl_handle c) {
     double t0 = now_ms();
     ensure_primary(c);
     ensure_vrl_sides(c);
-    const uint32_t N = (uint32_t) c->vrlHost.size(), G = (uint32_t) c->rowPixel.size(), S = (uint32_t) c->slices.size();
-    c->dRowPixel.upload(c->rowPixel, c->stream);
+    const uint32_t N = (uint32_t) c->vrlHost.size(), G = (uint32_t) c->rowPixel.size(), S = c->numSlices();
+    c->dRowPixel.upload(c->rowPixel, c->stream);                              /* (set_rep_pixels may have replaced the mirror) */
     c->dRowSegs.alloc(G);
     launch_gather_rows(c->dPixSegs.p, c->dRowPixel.p, G, c->dRowSegs.p, c->stream);
     c->stats.kernelLaunches++;
@@ -702,11 +726,13 @@ int alvrl_get_primary_hits(alvrl_handle c, uint32_t *prim, float *t, float *p, f
 
 int alvrl_get_pixel_to_slice(alvrl_handle c, uint32_t *out) {
     if (!c->haveSlices) return fail(ALVRL_ERR_STATE, "build_slices first");
-    memcpy(out, c->pixelToSlice.data(), c->pixelToSlice.size() * 4);
-    return ALVRL_OK;
+    API_BEGIN
+    use_device(c);
+    c->dPixelToSlice.download(out, c->numPixels(), c->stream);
+    API_END
 }
 int alvrl_get_num_slices(alvrl_handle c, uint32_t *ns, uint32_t *nr) {
-    *ns = (uint32_t) c->slices.size(); *nr = c->haveRows ? (uint32_t) c->rowPixel.size() : 0;
+    *ns = c->numSlices(); *nr = c->haveRows ? (uint32_t) c->rowPixel.size() : 0;
     return ALVRL_OK;
 }
 int alvrl_get_rep_pixels(alvrl_handle c, uint32_t *off, uint32_t *px) {
@@ -715,7 +741,7 @@ int alvrl_get_rep_pixels(alvrl_handle c, uint32_t *off, uint32_t *px) {
     return ALVRL_OK;
 }
 int alvrl_set_rep_pixels(alvrl_handle c, const uint32_t *off, const uint32_t *px, uint32_t ns) {
-    if (!c->haveSlices || ns != c->slices.size()) return fail(ALVRL_ERR_STATE, "slice count mismatch");
+    if (!c->haveSlices || ns != c->numSlices()) return fail(ALVRL_ERR_STATE, "slice count mismatch");
     if (off[0] != 0) return fail(ALVRL_ERR_ARG, "set_rep_pixels: sliceRowOffset[0] must be 0");
     for (uint32_t i = 0; i < ns; i++) if (off[i + 1] < off[i]) return fail(ALVRL_ERR_ARG, "set_rep_pixels: sliceRowOffset must be non-decreasing");
     for (uint32_t i = 0; i < off[ns]; i++) if (px[i] >= c->numPixels()) return fail(ALVRL_ERR_ARG, "set_rep_pixels: pixel index out of range");
@@ -723,8 +749,8 @@ int alvrl_set_rep_pixels(alvrl_handle c, const uint32_t *off, const uint32_t *px
     c->sliceUndersampling.resize(ns);
     size_t totalPix = 0;
     for (uint32_t i = 0; i < ns; i++) {
-        c->sliceUndersampling[i] = ((float) (off[i + 1] - off[i])) / c->slices[i].pixels.size();
-        totalPix += c->slices[i].pixels.size();
+        c->sliceUndersampling[i] = ((float) (off[i + 1] - off[i])) / c->sliceSize[i];
+        totalPix += c->sliceSize[i];
     }
     c->globalPixelUndersampling = ((float) off[ns]) / totalPix;
     c->haveRows = true; c->haveR = false; c->haveClusters = false; c->haveFallback = false;
@@ -761,7 +787,7 @@ int alvrl_get_cluster_counts(alvrl_handle c, uint32_t *off, uint32_t *ng, uint32
     API_BEGIN
     use_device(c);
     if (!c->haveClusters) throw Error(ALVRL_ERR_STATE, "build_clusters first");
-    const uint32_t S_ = (uint32_t) c->slices.size();
+    const uint32_t S_ = c->numSlices();
     const bool ranged = !(std::min(c->sliceBegin, S_) == 0 && std::min(c->sliceEnd, S_) == S_);
     /* lazily: global + fallback lists (they span all rows of R: a handle that owns a slice range reports them empty) */
     if (!c->haveFallback && c->haveR && !ranged) build_clusters_device(c, true);
@@ -781,7 +807,7 @@ int alvrl_get_clusters(alvrl_handle c, uint32_t *vrls, float *weights, uint32_t 
 }
 int alvrl_set_clusters(alvrl_handle c, const uint32_t *off, uint32_t ns, const uint32_t *vrls, const float *weights,
                        const uint32_t *fv, const float *fw, uint32_t nf) {
-    if (!c->haveSlices || ns != c->slices.size()) return fail(ALVRL_ERR_STATE, "slice count mismatch");
+    if (!c->haveSlices || ns != c->numSlices()) return fail(ALVRL_ERR_STATE, "slice count mismatch");
     if (off[0] != 0) return fail(ALVRL_ERR_ARG, "set_clusters: sliceOffset[0] must be 0");
     for (uint32_t i = 0; i < ns; i++) if (off[i + 1] < off[i]) return fail(ALVRL_ERR_ARG, "set_clusters: sliceOffset must be non-decreasing");
     for (uint32_t i = 0; i < off[ns]; i++) if (vrls[i] >= c->vrlHost.size()) return fail(ALVRL_ERR_ARG, "set_clusters: representative out of range");

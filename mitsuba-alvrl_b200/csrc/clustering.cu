@@ -1072,6 +1072,7 @@ struct Workspace {
             if (const char *e = getenv("ALVRL_GANG_LOAD")) scale = atof(e);
             const double perCta = (double) dev.size() / (double) std::max(1, sms);
             scr.gangMin = std::max<uint32_t>(scr.gangMin, (uint32_t) std::min(4e9, scale * perCta * (double) N));
+            if (perCta * scale >= 0.5) scr.gangMin = 0;        /* the GPU is full of objects: throughput, not latency, bounds the kernel */
         }
         if (scr.gangMin && scr.gangMin < 2u * RF_SMALL) scr.gangMin = 2u * RF_SMALL;          /* gangs use the large-cluster code path */
         DevBuf<double> dCarry; dCarry.alloc((size_t) grid * 2 * RF_GANG_MAX * RF_MAXROWS);
@@ -1453,7 +1454,7 @@ float measure_fp32_peak_tflops() {
 }
 
 void build_clusters_device(alvrl_ctx *c, bool needFallback) {
-    const uint32_t N = (uint32_t) c->vrlHost.size(), G = (uint32_t) c->rowPixel.size(), S = (uint32_t) c->slices.size();
+    const uint32_t N = (uint32_t) c->vrlHost.size(), G = (uint32_t) c->rowPixel.size(), S = c->numSlices();
     if (c->globalPixelUndersampling < 0) throw Error(ALVRL_ERR_STATE, "Invalid pixel undersampling. Did you forget to call buildSlices first?");
     cudaStream_t st = c->stream;
     const bool sfmt = c->P.rngMode == ALVRL_RNG_MODE_SFMT;

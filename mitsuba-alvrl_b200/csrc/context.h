@@ -146,7 +146,11 @@ struct alvrl_ctx {
     bool havePrimary = false;
 
     /* slices / rows */
-    std::vector<uint32_t> pixelToSlice; std::vector<alvrl::SliceInfo> slices; bool haveSlices = false;
+    /* slices live on the device: dRecIdx = the pixel ids in partition order (slice s = positions [sliceLo[s], sliceLo[s] +
+     * sliceSize[s])), dPixelToSlice = m_slices; the host keeps the ranges only */
+    std::vector<uint32_t> sliceLo, sliceSize; bool haveSlices = false;
+    alvrl::DevBuf<uint32_t> dRecIdx, dPixelToSlice;
+    uint32_t numSlices() const { return (uint32_t) sliceSize.size(); }
     std::vector<uint32_t> rowOffset, rowPixel; bool haveRows = false;
     std::vector<float> sliceUndersampling; float globalPixelUndersampling = -1;
     alvrl::DevBuf<uint32_t> dRowPixel; alvrl::DevBuf<SegRec> dRowSegs;
@@ -167,7 +171,7 @@ struct alvrl_ctx {
     /* render lists */
     alvrl::DevBuf<uint32_t> dSlicePixels, dRepOffset; alvrl::DevBuf<uint4> dWork; alvrl::DevBuf<VrlRec> dRepRecs;
     alvrl::DevBuf<float4> dFb; alvrl::DevBuf<float> dRgb;
-    uint32_t numWork = 0; bool renderListsDirty = true;
+    uint32_t numWork = 0; bool renderListsDirty = true, pixelListsDirty = true;
 
     /* sample streams */
     std::unique_ptr<alvrl::HostSampler> mainSampler;
@@ -182,4 +186,8 @@ namespace alvrl {
 void build_clusters_device(alvrl_ctx *c, bool needFallback);
 void column_nonzero_device(alvrl_ctx *c, std::vector<uint8_t> &flags);
 float measure_fp32_peak_tflops();
+/* slices_dev.cu: Preprocessor::getSlices on the device (Preprocessor.cpp:1200-1227,1349-1418) and its consumers */
+bool build_slices_device(alvrl_ctx *c, const float *dPos, const float *dDir, uint32_t P, uint32_t targetNumSlices);
+void slice_gather_rows_device(alvrl_ctx *c, const std::vector<uint32_t> &positions, std::vector<uint32_t> &rowPixel);
+void slice_bucket_pixels_device(alvrl_ctx *c, const std::vector<uint32_t> &sliceStart, uint32_t total);
 }

@@ -87,9 +87,9 @@ void member_frame(alvrl_group *g, Member *m, float *rgbHost) {
     alvrl_ctx *c = m->c;
     ALVRL_CUDA(cudaSetDevice(c->device));
     G_API(alvrl_build_slices(c));                                            /* Preprocessor::buildSlices: replicated, identical on every rank */
-    const uint32_t S = (uint32_t) c->slices.size();
+    const uint32_t S = c->numSlices();
     std::vector<uint32_t> sizes(S);
-    for (uint32_t i = 0; i < S; i++) sizes[i] = (uint32_t) c->slices[i].pixels.size();
+    for (uint32_t i = 0; i < S; i++) sizes[i] = c->sliceSize[i];
     balanced_slice_range(sizes.data(), S, g->world, m->rank, m->sliceBegin, m->sliceEnd);
     G_API(alvrl_set_slice_range(c, m->sliceBegin, m->sliceEnd));
     G_API(alvrl_sample_slice_mapping(c));

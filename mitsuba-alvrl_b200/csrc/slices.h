@@ -128,17 +128,22 @@ public:
     }
 };
 
-/* Slice::sampleRepresentativePixels, Preprocessor.cpp:66-121 */
-inline std::vector<uint32_t> sampleRepresentativePixels(const SliceInfo &s, float targetUndersampling, HostSampler *smp) {
-    const size_t numPixels = s.pixels.size();
+/* Slice::sampleRepresentativePixels, Preprocessor.cpp:66-121, in terms of positions inside the slice's pixel list (the device
+ * path gathers the pixel ids itself): all of them, a shuffled prefix, or rejection-sampled distinct positions */
+inline std::vector<uint32_t> sampleRepresentativeIndices(size_t numPixels, float targetUndersampling, HostSampler *smp) {
     size_t targetNum = (size_t) (0.5 + numPixels / targetUndersampling);
     if (targetNum < 2) targetNum = std::min((size_t) 2, numPixels);
-    if (numPixels <= targetNum) return s.pixels;
     std::vector<uint32_t> idx;
+    if (numPixels <= targetNum) {
+        idx.resize(numPixels);
+        for (size_t i = 0; i < numPixels; i++) idx[i] = (uint32_t) i;
+        return idx;
+    }
     if (numPixels <= 2 * targetNum) {
         idx.resize(numPixels);
         for (size_t i = 0; i < numPixels; i++) idx[i] = (uint32_t) i;
         for (size_t i = numPixels - 1; i > 0; i--) std::swap(idx[i], idx[(size_t) ((i + 1) * smp->next1D())]);   /* quirk B8 */
+        idx.resize(targetNum);
     } else {
         idx.resize(targetNum);
         for (size_t n = 0; n < targetNum; n++) {
@@ -150,8 +155,12 @@ inline std::vector<uint32_t> sampleRepresentativePixels(const SliceInfo &s, floa
             } while (!unique);
         }
     }
-    std::vector<uint32_t> out(targetNum);
-    for (size_t i = 0; i < targetNum; i++) out[i] = s.pixels[idx[i]];
+    return idx;
+}
+inline std::vector<uint32_t> sampleRepresentativePixels(const SliceInfo &s, float targetUndersampling, HostSampler *smp) {
+    const std::vector<uint32_t> idx = sampleRepresentativeIndices(s.pixels.size(), targetUndersampling, smp);
+    std::vector<uint32_t> out(idx.size());
+    for (size_t i = 0; i < idx.size(); i++) out[i] = s.pixels[idx[i]];
     return out;
 }
 
