@@ -315,7 +315,9 @@ int alvrl_create(int device, const alvrl_params *p, alvrl_handle *out) {
     if (p->targetNumSlices < 1) return fail(ALVRL_ERR_ARG, "Invalid target number of slices!");
     if (p->neighbourWeight > 0) return fail(ALVRL_ERR_UNSUPPORTED, "neighbourWeight > 0 (neighbour slices in L_i) is outside the device path");
     if (p->Rsamples != 1) return fail(ALVRL_ERR_UNSUPPORTED, "Rsamples != 1 is outside the device path");
-    if (p->depthCorrection != 1) return fail(ALVRL_ERR_UNSUPPORTED, "depthCorrection != 1 (ReplayableSampler pass) is outside the device path");
+    if (p->depthCorrection != 1 && p->rngMode != ALVRL_RNG_MODE_COUNTER)
+        return fail(ALVRL_ERR_UNSUPPORTED, "depthCorrection != 1 replays the split decisions: it needs the counter sample stream (rngMode = COUNTER)");
+    if (!(p->depthCorrection > 0)) return fail(ALVRL_ERR_ARG, "depthCorrection must be positive");
     if (p->numVrlFalseColor || p->slicesFalseColor || p->convergenceFalseColor)
         return fail(ALVRL_ERR_UNSUPPORTED, "false-colour debug outputs (vrlIntegrator.cpp:199-201) are not implemented on the device path");
     if (p->maxPasses > 1) return fail(ALVRL_ERR_UNSUPPORTED, "maxPasses > 1: the device path renders one pass per VRL set (the caller accumulates passes)");

@@ -661,6 +661,8 @@ struct Inst {                                                                  /
     uint32_t nearTies = 0;
     bool listsStale = false;      /* the device holds a newer permutation than `vrls` */
     bool currentIsBest = true;    /* adaptive refinement: the current state is the best-so-far snapshot */
+    /* depthCorrection != 1 (403-408, 455-470): splits so far, splits at the best convergence constant, split count of pass 2 */
+    uint32_t splitsDone = 0, bestSplits = 0, fixedSplits = 0;
 
     uint32_t numMulti() const { return (uint32_t) pq.size(); }
     uint32_t numClusters() const { return (uint32_t) (pq.size() + singletons.size()); }
@@ -898,6 +900,7 @@ struct Workspace {
         }
     }
     /* Clustering::refine for the given instances, all advancing one split per round (380-489, 590-684) */
+    float depthCorrection = 1.0f;     /* of the objects of this workspace (the per-slice ones: Preprocessor.cpp:268-269) */
     void refine(const std::vector<Inst *> &which, float undersampling) {
         for (Inst *in : which) {
             in->failed = false; in->done = false; in->refining = true;
@@ -913,44 +916,51 @@ struct Workspace {
             }
         }
         auto afterSplit = [](Inst *in) {
+            in->splitsDone++;
             if (in->adaptive) {
                 const float curr = in->convergenceConstant();                   /* 436-452 */
                 in->currentIsBest = curr < in->bestConstant;
-                if (in->currentIsBest) { in->snapshot(); in->bestConstant = curr; }
+                if (in->currentIsBest) { in->snapshot(); in->bestConstant = curr; in->bestSplits = in->splitsDone; }
                 if (in->lowerBound() >= in->bestConstant || in->numMulti() == 0) { in->restore(); in->done = true; }
-            } else if (!(in->numClusters() < in->targetClusters && in->numMulti() > 0)) in->done = true;
+            } else if (in->fixedSplits) { if (in->splitsDone >= in->fixedSplits || in->numMulti() == 0) in->done = true; }   /* 455-470 */
+            else if (!(in->numClusters() < in->targetClusters && in->numMulti() > 0)) in->done = true;
         };
-        if (deviceRounds && !getenv("ALVRL_HOST_ROUNDS")) {
-            /* EXPERIMENT, off unless ALVRL_HYBRID_ROUNDS=<columns> is set (not yet measured on the GPU): while the cluster at the
-             * top of an object's queue is larger than that, it is split by the batched grid-wide kernels of the rounds -- every
-             * SM works on it -- instead of by one CTA of k_refine_mt, whose chain of large splits bounds the kernel when a GPU
-             * holds few objects.  Both paths compute the same split, so the result does not depend on it. */
-            const char *hy = getenv("ALVRL_HYBRID_ROUNDS");
-            const uint32_t hybrid = hy ? (uint32_t) std::max(0, atoi(hy)) : 0u;
-            for (; hybrid;) {
-                std::vector<Inst *> round;
-                for (Inst *in : which)
-                    if (!in->done && !in->pq.empty() &&
-                        (in->pq.front().end - in->pq.front().begin > hybrid || (in->adaptive && !in->currentIsBest)))
-                        round.push_back(in);                /* the device kernel starts from a state that is its own best-so-far snapshot */
+        /* depthCorrection != 1 (per-slice objects only, 268-269): the queue before the first split is what the second pass starts from */
+        const bool secondPass = depthCorrection != 1.0f && undersampling <= 0;
+        struct Initial { std::vector<ClusterNode> pq; std::list<uint32_t> singletons; float underVar, intVar; };
+        std::vector<Initial> initial;
+        if (secondPass) for (Inst *in : which) { initial.push_back(Initial{in->pq, in->singletons, in->underVar, in->intVar}); in->splitsDone = in->bestSplits = in->fixedSplits = 0; }
+        auto drive = [&]() {
+            if (deviceRounds && !getenv("ALVRL_HOST_ROUNDS")) {
+                refineDevice(which);
+            }
+            for (;;) {
+                /* one runnable instance per sampler group: a shared sequential stream (SFMT) serialises its instances */
+                std::vector<Inst *> round; std::vector<int> groupsBusy;
+                for (Inst *in : which) {
+                    if (in->done) continue;
+                    if (std::find(groupsBusy.begin(), groupsBusy.end(), in->group) != groupsBusy.end()) continue;
+                    groupsBusy.push_back(in->group);
+                    round.push_back(in);
+                }
                 if (round.empty()) break;
-                splitRoundDevice(round);
+                if (deviceRounds) splitRoundDevice(round); else splitRound(round);
                 for (Inst *in : round) afterSplit(in);
             }
-            refineDevice(which);
-        }
-        for (;;) {
-            /* one runnable instance per sampler group: a shared sequential stream (SFMT) serialises its instances */
-            std::vector<Inst *> round; std::vector<int> groupsBusy;
-            for (Inst *in : which) {
-                if (in->done) continue;
-                if (std::find(groupsBusy.begin(), groupsBusy.end(), in->group) != groupsBusy.end()) continue;
-                groupsBusy.push_back(in->group);
-                round.push_back(in);
+        };
+        drive();
+        if (secondPass) {
+            /* the VRL lists stay as the first pass left them (makeRefinementSnapshot does not cover m_vrls, 686-699) */
+            for (size_t i = 0; i < which.size(); i++) {
+                Inst *in = which[i];
+                if (in->failed || initial[i].pq.empty()) continue;
+                const int corrected = (int) (0.5 + depthCorrection * (float) in->bestSplits);        /* 460 */
+                in->pq = initial[i].pq; in->singletons = initial[i].singletons; in->underVar = initial[i].underVar; in->intVar = initial[i].intVar;
+                in->adaptive = false; in->fixedSplits = (uint32_t) std::max(0, corrected); in->splitsDone = 0;
+                in->done = corrected <= 0 || in->numMulti() == 0;
             }
-            if (round.empty()) break;
-            if (deviceRounds) splitRoundDevice(round); else splitRound(round);
-            for (Inst *in : round) afterSplit(in);
+            drive();
+            for (Inst *in : which) in->fixedSplits = 0;
         }
         if (!lazyMirrors) syncLists(which);
         for (Inst *in : which) in->refining = false;
@@ -1017,6 +1027,7 @@ struct Workspace {
             xFloats += (uint64_t) N * r.nrP;
             r.numVrlsTotal = in->numVrlsTotal; r.pixelUndersampling = in->pixelUndersampling; r.tracingVar = in->tracingVar; r.unclIntVar = in->unclIntVar;
             r.adaptive = in->adaptive ? 1u : 0u; r.targetClusters = in->targetClusters; r.rngKey = key; r.rngPos = pos;
+            r.splitsBase = in->splitsDone; r.bestSplits = in->bestSplits; r.fixedSplits = in->fixedSplits;
             r.underVar = in->underVar; r.intVar = in->intVar; r.bestConstant = in->bestConstant;
             r.heapCount = r.nodeCount = (uint32_t) in->pq.size(); r.singleCount = (uint32_t) in->singletons.size();
             r.initNodeOff = (uint32_t) initNodes.size(); r.initSingleOff = (uint32_t) initSingles.size();
@@ -1152,6 +1163,7 @@ struct Workspace {
             in.underVar = r.underVar; in.intVar = r.intVar; in.s_under = r.sUnder; in.s_int = r.sInt; in.bestConstant = r.bestConstant;
             in.smp->setCounterPos(r.rngPos);
             in.nearTies += r.nearTies; in.listsStale = true;
+            in.splitsDone += r.splits; in.bestSplits = r.bestSplits;
             splits += r.splits; degenerate += r.degenerate;
             { unsigned long long tot = 0; for (int a = 0; a < 24; a++) { clk[a / 12][a % 12] += r.clk[a / 12][a % 12]; if (a % 12 != 9) tot += r.clk[a / 12][a % 12]; } perObj.push_back(std::make_pair(tot, i)); }
             if (r.status == RF_DONE) { if (in.adaptive) in.restore(); in.done = true; }
@@ -1586,6 +1598,7 @@ void build_clusters_device(alvrl_ctx *c, bool needFallback) {
                     w2.lazyMirrors = true;
                     w2.columnWeights(); lap("columnWeights");
                     w2.construct(c->globalVrlsPerCluster); lap("construct");
+                    w2.depthCorrection = c->P.depthCorrection;
                     if (c->P.localRefinement) w2.refine(w2.insts, c->P.localUndersampling);
                     lap("refine");
                     w2.sampleRepresentativesDevice(c->selectedVrls, c->clusterWeight);

@@ -107,15 +107,25 @@ ALVRL_OCC_HD bool occ_query(const OccDev &oc, const float4 *tris, float ox, floa
                             float tmax, bool need, uint32_t boxActive = 0xffffffffu, uint32_t planeActive = 0xffffffffu) {
     const float INF = INFINITY;
     bool hit = false;
-    const uint32_t nb = boxActive ? oc.numBoxes : 0u;                 /* nothing left to test: skip the loop, not only its bodies */
-    for (uint32_t b = 0; b < nb; b++) {
-        if (!((boxActive >> b) & 1u)) continue;
-        float tn = -INF, tf = INF;
-        ALVRL_OCC_CLIP(oc.slabA[3 * b], oc.slabB[3 * b].x);
-        ALVRL_OCC_CLIP(oc.slabA[3 * b + 1], oc.slabB[3 * b + 1].x);
-        ALVRL_OCC_CLIP(oc.slabA[3 * b + 2], oc.slabB[3 * b + 2].x);
-        hit |= ALVRL_OCC_TOUCH();
-    }
+    /* the first two boxes (the Cornell class has exactly two) are tested by straight-line code at fixed parameter offsets; a
+     * loop takes the rest.  Nothing left to test: neither runs */
+    const uint32_t nbAll = oc.numBoxes;
+#define ALVRL_OCC_BOX(B)                                                          \
+    do {                                                                          \
+        float tn = -INF, tf = INF;                                                \
+        ALVRL_OCC_CLIP(oc.slabA[3 * (B)], oc.slabB[3 * (B)].x);                   \
+        ALVRL_OCC_CLIP(oc.slabA[3 * (B) + 1], oc.slabB[3 * (B) + 1].x);           \
+        ALVRL_OCC_CLIP(oc.slabA[3 * (B) + 2], oc.slabB[3 * (B) + 2].x);           \
+        hit |= ALVRL_OCC_TOUCH();                                                 \
+    } while (0)
+    if ((boxActive & 1u) && nbAll > 0u) ALVRL_OCC_BOX(0);
+    if ((boxActive & 2u) && nbAll > 1u) ALVRL_OCC_BOX(1);
+    if (boxActive >> 2)
+        for (uint32_t b = 2; b < nbAll; b++) {
+            if (!((boxActive >> b) & 1u)) continue;
+            ALVRL_OCC_BOX(b);
+        }
+#undef ALVRL_OCC_BOX
     {
         float tn = -INF, tf = INF;
         for (uint32_t i = 3 * oc.numBoxes; i < oc.numSlabs; i++) {

@@ -50,6 +50,9 @@ struct RfInst {
     uint32_t nrP; uint64_t xOff, vOff;  /* the compacted local matrix: X[xOff + vrl * nrP + row], nrP = roundup(nr, 4); Vcol[vOff + vrl] */
     uint32_t numVrlsTotal; float pixelUndersampling, tracingVar, unclIntVar;
     uint32_t adaptive, targetClusters, rngKey;
+    /* depthCorrection != 1 (Preprocessor.cpp:403-408, 455-470): pass 1 records the split count of the best convergence constant
+     * (bestSplits, counted from splitsBase), pass 2 -- not adaptive -- runs exactly fixedSplits splits from the initial queue */
+    uint32_t splitsBase, bestSplits, fixedSplits;
     /* state, in and out */
     uint32_t rngPos; float underVar, intVar, bestConstant;
     uint32_t heapCount, nodeCount, singleCount;
@@ -107,7 +110,7 @@ struct RfShared {
     unsigned long long mtClk[8];                          /* control cycles, ticket wait, control passes, split tasks, gang sync wait, gang syncs */
     float u1, u2, norm[3];
     /* refinement state (thread 0) */
-    uint32_t rngPos, heapCount, nodeCount, singleCount, sHeapCount, sSingleCount, nearTies, splits, degenerate;
+    uint32_t rngPos, heapCount, nodeCount, singleCount, sHeapCount, sSingleCount, nearTies, splits, degenerate, bestSplits;
     float underVar, intVar, bestConstant, sUnder, sInt;
     unsigned long long clk[2][12];
 };
@@ -295,7 +298,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_refine(float *XA, float *XB, 
             sm.rngPos = I->rngPos; sm.heapCount = I->heapCount; sm.nodeCount = I->nodeCount; sm.singleCount = I->singleCount;
             sm.underVar = I->underVar; sm.intVar = I->intVar; sm.bestConstant = I->bestConstant;
             sm.sHeapCount = I->heapCount; sm.sSingleCount = I->singleCount; sm.sUnder = I->underVar; sm.sInt = I->intVar;
-            sm.nearTies = 0; sm.splits = 0; sm.degenerate = 0; sm.err = RF_DONE;
+            sm.nearTies = 0; sm.splits = 0; sm.degenerate = 0; sm.err = RF_DONE; sm.bestSplits = I->bestSplits;
             for (int a = 0; a < 24; a++) sm.clk[a / 12][a % 12] = 0;
         }
         __syncthreads();
@@ -370,10 +373,11 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_refine(float *XA, float *XB, 
                         if (!isfinite(curr) || curr <= 0) { sm.err = RF_ERR_CONSTANT; sm.done = 1; }
                         else if (!isfinite(lower) || lower <= 0) { sm.err = RF_ERR_LOWER; sm.done = 1; }
                         else {
-                            if (curr < sm.bestConstant) { sm.snap = 1; sm.bestConstant = curr; }
+                            if (curr < sm.bestConstant) { sm.snap = 1; sm.bestConstant = curr; sm.bestSplits = I->splitsBase + sm.splits; }
                             if (lower >= sm.bestConstant || sm.heapCount == 0) sm.done = 1;
                         }
-                    } else if (!(numClusters < I->targetClusters && sm.heapCount > 0)) sm.done = 1;     /* refineFixedDepth, 387-399 */
+                    } else if (I->fixedSplits) { if (I->splitsBase + sm.splits >= I->fixedSplits || sm.heapCount == 0) sm.done = 1; }   /* second pass, 455-470 */
+                    else if (!(numClusters < I->targetClusters && sm.heapCount > 0)) sm.done = 1;     /* refineFixedDepth, 387-399 */
                 }
             }
             __syncthreads();
@@ -401,7 +405,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_refine(float *XA, float *XB, 
             I->rngPos = sm.rngPos; I->underVar = sm.underVar; I->intVar = sm.intVar; I->bestConstant = sm.bestConstant;
             I->heapCount = sm.heapCount; I->nodeCount = sm.nodeCount; I->singleCount = sm.singleCount;
             I->sHeapCount = sm.sHeapCount; I->sSingleCount = sm.sSingleCount; I->sUnder = sm.sUnder; I->sInt = sm.sInt;
-            I->nearTies = sm.nearTies; I->status = sm.err; I->splits = sm.splits; I->degenerate = sm.degenerate;
+            I->nearTies = sm.nearTies; I->status = sm.err; I->splits = sm.splits; I->degenerate = sm.degenerate; I->bestSplits = sm.bestSplits;
         }
     }
 }
@@ -632,7 +636,9 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_refine_mt(float *XA, float *X
             if (!I->mtInit) {
                 sm.sHeapCount = I->heapCount; sm.sSingleCount = I->singleCount; sm.sUnder = I->underVar; sm.sInt = I->intVar;
                 sm.nearTies = 0; sm.splits = 0; sm.degenerate = 0;
+                sm.bestSplits = I->bestSplits;
             } else {
+                sm.bestSplits = I->bestSplits;
                 sm.sHeapCount = I->sHeapCount; sm.sSingleCount = I->sSingleCount; sm.sUnder = I->sUnder; sm.sInt = I->sInt;
                 sm.nearTies = I->nearTies; sm.splits = I->splits; sm.degenerate = I->degenerate;
             }
@@ -701,10 +707,11 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_refine_mt(float *XA, float *X
                                 if (!isfinite(curr) || curr <= 0) { sm.err = RF_ERR_CONSTANT; sm.done = 1; }
                                 else if (!isfinite(lower) || lower <= 0) { sm.err = RF_ERR_LOWER; sm.done = 1; }
                                 else {
-                                    if (curr < sm.bestConstant) { sm.snap = 1; sm.bestConstant = curr; }
+                                    if (curr < sm.bestConstant) { sm.snap = 1; sm.bestConstant = curr; sm.bestSplits = I->splitsBase + sm.splits; }
                                     if (lower >= sm.bestConstant || sm.heapCount == 0) sm.done = 1;
                                 }
-                            } else if (!(numClusters < I->targetClusters && sm.heapCount > 0)) sm.done = 1;     /* refineFixedDepth, 387-399 */
+                            } else if (I->fixedSplits) { if (I->splitsBase + sm.splits >= I->fixedSplits || sm.heapCount == 0) sm.done = 1; }   /* second pass, 455-470 */
+                            else if (!(numClusters < I->targetClusters && sm.heapCount > 0)) sm.done = 1;     /* refineFixedDepth, 387-399 */
                         }
                     }
                 }
@@ -805,7 +812,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_refine_mt(float *XA, float *X
             I->underVar = sm.underVar; I->intVar = sm.intVar; I->bestConstant = sm.bestConstant;
             I->heapCount = sm.heapCount; I->nodeCount = sm.nodeCount; I->singleCount = sm.singleCount;
             I->sHeapCount = sm.sHeapCount; I->sSingleCount = sm.sSingleCount; I->sUnder = sm.sUnder; I->sInt = sm.sInt;
-            I->nearTies = sm.nearTies; I->splits = sm.splits; I->degenerate = sm.degenerate;
+            I->nearTies = sm.nearTies; I->splits = sm.splits; I->degenerate = sm.degenerate; I->bestSplits = sm.bestSplits;
             I->mtInit = 1; I->mtWaves++;
         }
         __syncthreads();

@@ -164,8 +164,22 @@ __device__ __forceinline__ float f_tan(float x) { return __tanf(x); }
 #endif
 #ifdef ALVRL_DIAG_ATAN
 __device__ __forceinline__ float f_atan(float x) { return (float) atan((double) x); }
-#else
+#elif defined(ALVRL_ATAN_LIB)
 __device__ __forceinline__ float f_atan(float x) { return atanf(x); }
+#else
+/* atan by one MUFU reciprocal (|x| > 1: pi/2 - atan(1/|x|)) and an 8-term odd minimax polynomial on [0, 1]: absolute error
+ * 1.1e-7 (the library atanf: ~28 instructions for the same error class) */
+__device__ __forceinline__ float f_atan(float x) {
+    const float a = fabsf(x);
+    const bool big = a > 1.0f;
+    const float r = big ? f_rcp(a) : a, q = r * r;
+    float p = -0.004105130676180124f;
+    p = fmaf(p, q, 0.022052252665162086f); p = fmaf(p, q, -0.05619571730494499f); p = fmaf(p, q, 0.09663795679807663f);
+    p = fmaf(p, q, -0.1391744166612625f); p = fmaf(p, q, 0.19948409497737885f); p = fmaf(p, q, -0.33330032229423523f);
+    p = fmaf(p, q, 0.9999994039535522f);
+    p *= r;
+    return copysignf(big ? 1.57079632679489662f - p : p, x);
+}
 #endif
 #ifdef ALVRL_DIAG_DIV
 #define f_div(a, b) ((a) / (b))
@@ -217,14 +231,16 @@ __device__ __forceinline__ void integrate_pair_fast(const TransportParams &P, co
         float mean = 0, M2 = 0;
         for (int k = 0; k < Nvv; k++) {
             const float u1 = rng.next();
-            F3 V; float pdf;
+            F3 V; float pdf, dSV;                                           /* dSV = |V - S|: V = S + s SV with a unit SV */
             if (parallel) {
                 V = S + u1 * (End - S);
                 pdf = f_rcp(vlen);
+                dSV = u1 * vlen;
             } else {
                 const float nv = h * f_sinh(fmaf(u1, dA, A0)) * rSin;
                 pdf = rsqrtf(fmaf(nv * nv, sinTheta * sinTheta, h * h)) * pdfVc;
                 V = S + (nv + dVhS) * SV;
+                dSV = fabsf(nv + dVhS);
             }
             const float u2 = rng.next();
             /* KullaSampling along the eye segment w.r.t. V (889-914), signed-angle form; dir = EU, A = E, |AB| = edist */
@@ -242,8 +258,6 @@ __device__ __forceinline__ void integrate_pair_fast(const TransportParams &P, co
             const float dUV = f_len(UV, d2);
             const F3 VU = UV * f_rcp(dUV);
             const float dEU = fabsf(dotPr + t);                             /* |U - E|, U = E + (dotPr + t) EU */
-            float tmp;
-            const float dSV = f_len(V - S, tmp);
             const bool ok = laneOn && d2 > 0.0f && dEU * sTmin <= cutoff && dSV * sTmin <= cutoff;
             const bool occ = occluded_fast<SMALL>(P, sb, U, false, -VU, dUV, ok, cull.boxVV, cull.planes);
             float lum = 0;
@@ -261,7 +275,9 @@ __device__ __forceinline__ void integrate_pair_fast(const TransportParams &P, co
                 if (P.shortVrls) common = f_div(common, pf);
                 common *= phase_eval(M, dot(VU, EU)) * phase_eval(M, -dot(SV, VU));
                 const float c0 = k0 * T0 * common, c1 = k1 * T1 * common, c2 = k2 * T2 * common;
-                if (isfinite(c0) && isfinite(c1) && isfinite(c2) && c0 >= 0.0f && c1 >= 0.0f && c2 >= 0.0f) {   /* isValid(), 686 */
+                /* isValid(), 686: every channel finite and >= 0.  k and T are finite and >= 0, so that is: common is a finite
+                 * non-negative number and the largest channel did not overflow */
+                if (common >= 0.0f && fmaxf(common, fmaxf(c0, fmaxf(c1, c2))) < INFINITY) {
                     if (WANT_RGB) { rgb[0] = fmaf(c0, invNvv, rgb[0]); rgb[1] = fmaf(c1, invNvv, rgb[1]); rgb[2] = fmaf(c2, invNvv, rgb[2]); }
                     lum = c0 * lw0 + c1 * lw1 + c2 * lw2;
                 }
@@ -326,7 +342,7 @@ __device__ __forceinline__ void integrate_pair_fast(const TransportParams &P, co
                     if (P.shortVrls) common = f_div(common, pf);
                     common *= phase_eval(M, -dot(SV, VU));
                     const float c0 = k0 * T0 * common, c1 = k1 * T1 * common, c2 = k2 * T2 * common;
-                    if (isfinite(c0) && isfinite(c1) && isfinite(c2) && c0 >= 0.0f && c1 >= 0.0f && c2 >= 0.0f) {
+                    if (common >= 0.0f && fmaxf(common, fmaxf(c0, fmaxf(c1, c2))) < INFINITY) {
                         if (WANT_RGB) { rgb[0] = fmaf(c0, invNvs, rgb[0]); rgb[1] = fmaf(c1, invNvs, rgb[1]); rgb[2] = fmaf(c2, invNvs, rgb[2]); }
                         lum = c0 * lw0 + c1 * lw1 + c2 * lw2;
                     }

@@ -220,6 +220,8 @@ struct Sampler {
      * a sequential stream (SFMT, tapes) just keeps drawing */
     virtual void enterNode(uint32_t, uint32_t) {}
     virtual void leaveNode() {}
+    /* the draws of a cluster's split do not depend on what was drawn before (counter stream) */
+    virtual bool replayable() const { return false; }
     uint64_t draws = 0;
 };
 struct SfmtSampler : Sampler {
@@ -236,6 +238,7 @@ struct CounterSampler : Sampler {
     void enterNode(uint32_t begin, uint32_t end) override { if (inNode) fail("CounterSampler::enterNode nested"); outerKey = key; outerK = k; key = alvrl_rng_node_key(key, begin, end); k = 0; inNode = true; }
     void leaveNode() override { if (inNode) { key = outerKey; k = outerK; inNode = false; } }
     Float next1D() override { draws++; return alvrl_rng_uniform(key, k++); }
+    bool replayable() const override { return true; }
     Sampler *clone() override { return new CounterSampler(seed); }
 };
 /* Replays a tape laid out like alvrl_set_sample_tape: K slots per (row, vrl) */

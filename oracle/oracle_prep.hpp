@@ -210,19 +210,41 @@ public:
         return true;
     }
     bool refineAdaptively(Sampler *sampler, Float depthCorrection) {       // 402-489
-        if (depthCorrection != 1) fail("depthCorrection != 1 (ReplayableSampler path) is not restated");
+        /* depthCorrection != 1 (403-408, 455-470): the reference draws the split decisions from a fresh ReplayableSampler
+         * (src/libbidir/rsampler.cpp:23-80; seeded by Random() = /dev/urandom, so not reproducible run to run), keeps only the
+         * INITIAL snapshot, and afterwards replays the uniforms for 0.5 + depthCorrection * bestNumberOfSplits splits from the
+         * restored queue.  The VRL list is NOT part of the snapshot (686-699): the second pass partitions the ranges as the
+         * first pass left them, so -- the centres being picked by running sums in list order -- it does not retrace the first
+         * pass's splits even though it sees the same uniforms.  That quirk is kept.  Restated for the counter stream, where a
+         * split draws from the sub-stream of the cluster [begin, end) it splits (Sampler::enterNode): "the same uniforms
+         * again" then holds by construction.  A sequential SFMT stream has no defined second pass and refuses. */
+        if (depthCorrection != 1 && !sampler->replayable()) fail("depthCorrection != 1 needs the counter sample stream (rngMode = COUNTER)");
         if (numMultiClusters() <= 0) return true;
         if (unclusteredVariance() == 0) return false;
         Float bestConstant = convergenceConstant();
+        int numberOfSplits = 0, bestNumberOfSplits = 0;
         makeRefinementSnapshot();
         while (numMultiClusters() > 0) {
             ClusterNode cn = popMultiCluster();
             if (!split(cn.begin, cn.end, sampler)) fail("couldn't split cluster!");
+            numberOfSplits++;
             Float currConstant = convergenceConstant();
-            if (currConstant < bestConstant) { makeRefinementSnapshot(); bestConstant = currConstant; }
+            if (currConstant < bestConstant) {
+                if (depthCorrection == 1) makeRefinementSnapshot();
+                bestConstant = currConstant;
+                bestNumberOfSplits = numberOfSplits;
+            }
             if (lowerBoundOfFutureConvergenceConstants() >= bestConstant) break;
         }
         restoreSnapshot();
+        if (depthCorrection != 1) {                                        // 455-470
+            int correctedNumberOfSplits = 0.5 + depthCorrection * bestNumberOfSplits;
+            for (int i = 0; i < correctedNumberOfSplits; i++) {
+                if (numMultiClusters() == 0) break;                        // EWarn in the reference
+                ClusterNode cn = popMultiCluster();
+                if (!split(cn.begin, cn.end, sampler)) fail("couldn't split cluster in second pass!");
+            }
+        }
         return true;
     }
     Float unclusteredVariance() const { return m_vrlTracingVariance + m_unclusteredVrlIntegrationVariance; }

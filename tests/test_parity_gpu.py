@@ -253,7 +253,8 @@ def _clusters_equal(cg, co, what=""):
     assert np.array_equal(cg["global_vrls"], co["global_vrls"])
 
 
-@pytest.mark.parametrize("kw", [dict(), dict(localUndersampling=4.0), dict(localRefinement=0), dict(globalCluster=1, globalUndersampling=20.0)])
+@pytest.mark.parametrize("kw", [dict(), dict(localUndersampling=4.0), dict(localRefinement=0), dict(globalCluster=1, globalUndersampling=20.0),
+                                dict(depthCorrection=0.5), dict(depthCorrection=1.7)])
 def test_clusters_identical_given_oracle_R(pkg, orc, kw):
     g, o = _pair(pkg, orc, "C1", 64, 64, 200, seed=4, **kw)
     for it in (g, o):
