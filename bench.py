@@ -228,10 +228,14 @@ def run_ours(a):
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    saved_stdout = None
     if multi:
-        # the caller's NCCL_DEBUG stays as it is (the driver reads the rank count from NCCL's INFO lines); NCCL's own output
-        # goes to stderr so that stdout carries the one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # the caller's NCCL_DEBUG stays as it is (the driver reads the rank count from NCCL's INFO lines).  NCCL logs to
+        # stdout: while the job runs, file descriptor 1 points at stderr, and it is put back for the one JSON line
+        # (NCCL_DEBUG_FILE=/dev/stderr would truncate a redirected log file)
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
 
     scene, vrls, params, desc, hg = workload(pkg, a)
@@ -357,7 +361,12 @@ def run_ours(a):
                 line["parity"] = {"error": repr(e)}
         if not a.no_cpu_baseline and world == 1:
             line["cpu_baseline"], _ = cpu_baseline(pkg, scene, vrls, params, hg, a.cpu_seconds, desc["workload"])
-        print(json.dumps(line))
+        sys.stdout.flush()
+        if saved_stdout is not None:
+            os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        if saved_stdout is not None:
+            os.dup2(2, 1)
     group.close()
     if multi:
         dist.barrier()

@@ -164,6 +164,7 @@ void finish_slices(alvrl_ctx *c, const std::vector<P3> &pos, const std::vector<P
         recIdx.insert(recIdx.end(), si.pixels.begin(), si.pixels.end());
     }
     recIdx.resize(P, 0u);
+    c->sliceCentroid = tree.centroids;
     c->dRecIdx.upload(recIdx, c->stream); c->dPixelToSlice.upload(toSlice, c->stream);
     c->haveSlices = true;
     invalidate_from_slices(c);
@@ -238,6 +239,7 @@ void build_render_lists(alvrl_ctx *c) {
     /* the pixel lists are bucketed on the device from pixelToSlice (nearly sorted inside a slice: ray coherence) */
     if (c->pixelListsDirty) { slice_bucket_pixels_device(c, sliceStart, total); c->pixelListsDirty = false; }
     c->dWork.upload(work, c->stream);
+    c->workHost = work;
     c->dRepOffset.upload(repOffset, c->stream);
     /* the representatives' records are gathered on the device (they carry the per-VRL side bits of ensure_vrl_sides) */
     const uint32_t nRep = (uint32_t) repIdx.size();
@@ -259,10 +261,8 @@ void select_work(alvrl_ctx *c, const uint4 *&work, uint32_t &numWork, std::vecto
     const uint32_t S = c->numSlices();
     const uint32_t sb = std::min(c->sliceBegin, S), se = std::min(c->sliceEnd, S);
     if (sb == 0 && se == S) { work = c->dWork.p; numWork = c->numWork; return; }
-    std::vector<uint4> all(c->numWork);
-    c->dWork.download(all.data(), c->numWork, c->stream);
     tmp.clear();
-    for (const uint4 &w : all) if (w.x >= sb && w.x < se) tmp.push_back(w);
+    for (const uint4 &w : c->workHost) if (w.x >= sb && w.x < se) tmp.push_back(w);
     dTmp.upload(tmp, c->stream);
     work = dTmp.p; numWork = (uint32_t) tmp.size();
 }
@@ -313,7 +313,9 @@ int alvrl_create(int device, const alvrl_params *p, alvrl_handle *out) {
     if (p->volVolSamples != 0 && p->volVolSamples < 2) return fail(ALVRL_ERR_ARG, "Need at least 2 volVolSamples for variance estimate");
     if (p->volSurfSamples != 0 && p->volSurfSamples < 2) return fail(ALVRL_ERR_ARG, "Need at least 2 volSurfSamples for variance estimate");
     if (p->targetNumSlices < 1) return fail(ALVRL_ERR_ARG, "Invalid target number of slices!");
-    if (p->neighbourWeight > 0) return fail(ALVRL_ERR_UNSUPPORTED, "neighbourWeight > 0 (neighbour slices in L_i) is outside the device path");
+    if (p->neighbourWeight > 0 && p->rngMode != ALVRL_RNG_MODE_COUNTER)
+        return fail(ALVRL_ERR_UNSUPPORTED, "neighbourWeight > 0 (neighbour slices in L_i) needs the counter sample stream on the device path");
+    if (p->neighbourWeight >= 1) return fail(ALVRL_ERR_ARG, "neighbourWeight must be below 1");
     if (p->Rsamples != 1) return fail(ALVRL_ERR_UNSUPPORTED, "Rsamples != 1 is outside the device path");
     if (p->depthCorrection != 1 && p->rngMode != ALVRL_RNG_MODE_COUNTER)
         return fail(ALVRL_ERR_UNSUPPORTED, "depthCorrection != 1 replays the split decisions: it needs the counter sample stream (rngMode = COUNTER)");
@@ -572,8 +574,9 @@ int alvrl_build_R(alvrl_handle c) {
     launch_gather_rows(c->dPixSegs.p, c->dRowPixel.p, G, c->dRowSegs.p, c->stream);
     c->stats.kernelLaunches++;
     c->ldR = (G + 31u) & ~31u;
+    /* every entry of the rows this handle owns is written by the kernel (inactive rows store zeros), and nothing reads the
+     * others (alvrl_get_R answers zeros for them): no 13 GB memset per frame */
     c->dR.alloc((size_t) N * c->ldR);
-    ALVRL_CUDA(cudaMemsetAsync(c->dR.p, 0, (size_t) N * c->ldR * sizeof(float2), c->stream));
     TransportParams T = make_transport_params(c, ALVRL_RNG_R);
     if (!c->userTape.empty()) {
         if (c->userTape.size() < (uint64_t) G * N * c->K()) throw Error(ALVRL_ERR_ARG, "sample tape too short: need G*N*(2*Nvv+Nvs) floats");
@@ -597,6 +600,7 @@ int alvrl_build_R(alvrl_handle c) {
     ALVRL_CUDA(cudaGetLastError());
     ALVRL_CUDA(cudaStreamSynchronize(c->stream));
     c->haveR = true; c->haveClusters = false; c->haveFallback = false;
+    c->builtRow0 = r0; c->builtRow1 = r1;
     c->stats.pairsPreprocess += (uint64_t) (r1 - r0) * N;
     c->stats.shadowRays += (uint64_t) (r1 - r0) * N * (uint64_t) (c->P.volVolSamples + c->P.volSurfSamples);
     c->stats.msBuildR = (float) (now_ms() - t0);
@@ -766,8 +770,11 @@ int alvrl_get_R(alvrl_handle c, uint32_t r0, uint32_t r1, float *mv) {
     if (r0 > r1 || r1 > c->rowPixel.size()) throw Error(ALVRL_ERR_ARG, "get_R: row range out of bounds");
     const uint32_t N = (uint32_t) c->vrlHost.size();
     std::vector<float2> col(c->ldR);
+    /* rows outside the range this handle built (slice sharding) were never written: they read as zeros */
+    const uint32_t b0 = std::max(r0, c->builtRow0), b1 = std::min(r1, c->builtRow1);
     for (uint32_t v = 0; v < N; v++) {
-        c->dR.download(col.data() + r0, r1 - r0, c->stream, (size_t) v * c->ldR + r0);
+        std::fill(col.begin() + r0, col.begin() + r1, make_float2(0, 0));
+        if (b0 < b1) c->dR.download(col.data() + b0, b1 - b0, c->stream, (size_t) v * c->ldR + b0);
         for (uint32_t r = r0; r < r1; r++) { mv[((size_t) (r - r0) * N + v) * 2] = col[r].x; mv[((size_t) (r - r0) * N + v) * 2 + 1] = col[r].y; }
     }
     API_END
@@ -782,6 +789,7 @@ int alvrl_set_R(alvrl_handle c, const float *mv) {
     for (uint32_t r = 0; r < G; r++)
         for (uint32_t v = 0; v < N; v++) t[(size_t) v * c->ldR + r] = make_float2(mv[((size_t) r * N + v) * 2], mv[((size_t) r * N + v) * 2 + 1]);
     c->dR.upload(t, c->stream);
+    c->builtRow0 = 0; c->builtRow1 = G;
     c->haveR = true; c->haveClusters = false; c->haveFallback = false;
     API_END
 }

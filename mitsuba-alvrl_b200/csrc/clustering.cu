@@ -22,6 +22,7 @@
  * rounding to float with probability ~1e-9 per value (documented near-tie flips, gate G5).
  */
 #include <list>
+#include <set>
 #include <thread>
 #include <atomic>
 #include <algorithm>
@@ -56,16 +57,21 @@ struct ClTask {                 /* one Clustering object's piece of work in a ba
     double lw;                  /* uniform locality weight 1 / nr */
 };
 
-__global__ void k_total_contribution(const float2 *__restrict__ R, uint32_t ldR, uint32_t G, uint32_t N, uint8_t *__restrict__ nonZero) {
-    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+/* totalVrlContribution != 0 (Preprocessor.cpp:846-855, 936-945).  The means are sums of valid -- finite, non-negative --
+ * contributions, so the row sum of a column is non-zero iff some entry is: an OR over the rows this handle owns (the other
+ * rows of a sharded R are zero), one warp per column, rows coalesced. */
+__global__ void k_total_contribution(const float2 *__restrict__ R, uint32_t ldR, uint32_t r0, uint32_t r1, uint32_t N, uint8_t *__restrict__ nonZero) {
+    const uint32_t v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (v >= N) return;
-    float sum = 0;
     const float2 *col = R + (size_t) v * ldR;
-    for (uint32_t r = 0; r < G; r++) sum += col[r].x;
-    nonZero[v] = sum != 0;
+    bool any = false;
+    for (uint32_t r = r0 + lane; r < r1; r += 32) any |= col[r].x != 0.0f;
+    const uint32_t b = __ballot_sync(0xffffffffu, any);
+    if (lane == 0) nonZero[v] = b != 0u;
 }
 
-__global__ void k_column_weights(const float2 *__restrict__ R, uint32_t ldR, uint32_t N, const ClTask *__restrict__ tasks, float *__restrict__ cw) {
+__global__ void k_column_weights(const float2 *__restrict__ R, uint32_t ldR, uint32_t N, const ClTask *__restrict__ tasks, float *__restrict__ cw,
+                                 const double *__restrict__ rowW) {
     const ClTask t = tasks[blockIdx.y];
     const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= N) return;
@@ -73,7 +79,7 @@ __global__ void k_column_weights(const float2 *__restrict__ R, uint32_t ldR, uin
     double acc = 0;
     for (uint32_t r = 0; r < t.nr; r++) {
         const double mean = col[r].x, var = col[r].y;
-        acc += t.lw * (mean * mean + var);
+        acc += (rowW ? rowW[t.r0 + r] : t.lw) * (mean * mean + var);
     }
     cw[t.cwOff + v] = (float) sqrt(fmax(0.0, acc));
 }
@@ -171,7 +177,8 @@ __device__ __forceinline__ void block_reduce2(double &a, double &b, double *sh) 
 }
 
 __global__ void __launch_bounds__(CL_THREADS) k_unclustered(const float2 *__restrict__ R, uint32_t ldR, const ClTask *__restrict__ tasks,
-                                                            const uint32_t *__restrict__ lists, double2 *__restrict__ out, uint32_t maxRowBlocks) {
+                                                            const uint32_t *__restrict__ lists, double2 *__restrict__ out, uint32_t maxRowBlocks,
+                                                            const double *__restrict__ rowW) {
     __shared__ double sh[2 * CL_THREADS / 32];
     const ClTask t = tasks[blockIdx.y];
     if (blockIdx.x >= t.rowBlocks) return;
@@ -209,7 +216,79 @@ __global__ void __launch_bounds__(CL_THREADS) k_unclustered(const float2 *__rest
             }
         }
     }
-    double a = active ? summedVars : 0.0, b = active ? M2 : 0.0;
+    const double rw = rowW ? rowW[row] : 1.0;              /* inner_prod(localityWeights, .), 1044-1046 (uniform: the host applies lw) */
+    double a = active ? rw * summedVars : 0.0, b = active ? rw * M2 : 0.0;
+    block_reduce2(a, b, sh);
+    if (threadIdx.x == 0) out[(size_t) blockIdx.y * maxRowBlocks + blockIdx.x] = make_double2(a, b);
+}
+
+/* The same Welford statistics with the VRL list cut into `segs` segments (grid.z) that run concurrently and are merged in list
+ * order afterwards (Chan et al.'s pairwise update: n = na + nb, d = mean_b - mean_a, M2 = M2a + M2b + d^2 na nb / n): a rank of
+ * a multi-GPU job holds a few hundred rows, and one thread per row walking 10^5 VRLs leaves the GPU empty for ~18 ms whatever
+ * the number of rows.  The double sums are associated differently from the sequential chain (last bits of a double that is
+ * rounded to float afterwards: the same class as the segment carries of the variance sweeps). */
+__global__ void __launch_bounds__(CL_THREADS) k_unclustered_seg(const float2 *__restrict__ R, uint32_t ldR, const ClTask *__restrict__ tasks,
+                                                                const uint32_t *__restrict__ lists, uint32_t segs, double *__restrict__ part,
+                                                                uint32_t maxRowBlocks) {
+    const ClTask t = tasks[blockIdx.y];
+    if (blockIdx.x >= t.rowBlocks) return;
+    const uint32_t lr = blockIdx.x * CL_THREADS + threadIdx.x;
+    const bool active = lr < t.nr;
+    const uint32_t row = t.r0 + (active ? lr : 0);
+    const uint32_t *list = lists + t.listOff;
+    const uint32_t total = t.end - t.begin, seg = blockIdx.z;
+    const uint32_t sb = t.begin + (uint32_t) (((uint64_t) total * seg) / segs), se = t.begin + (uint32_t) (((uint64_t) total * (seg + 1)) / segs);
+    double mean = 0, M2 = 0, summedVars = 0;
+    __shared__ double rcpN[CL_THREADS];
+    for (uint32_t c0 = sb; c0 < se; c0 += CL_THREADS) {
+        __syncthreads();
+        rcpN[threadIdx.x] = 1.0 / (double) (c0 - sb + threadIdx.x + 1u);
+        __syncthreads();
+        const uint32_t cEnd = min(se, c0 + CL_THREADS);
+        for (uint32_t k0 = c0; k0 < cEnd; k0 += 8) {
+            float2 e[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) e[u] = (k0 + u < cEnd) ? R[(size_t) list[k0 + u] * ldR + row] : make_float2(0.0f, 0.0f);
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                if (k0 + u < cEnd) {
+                    const double nD = (double) (k0 + u - sb + 1u), y = rcpN[k0 + u - c0];
+                    summedVars += (double) e[u].y;
+                    const double x = e[u].x, delta = x - mean;
+                    const double q0 = delta * y;
+                    mean += fma(fma(-q0, nD, delta), y, q0);          /* == delta / n */
+                    M2 += delta * (x - mean);
+                }
+            }
+        }
+    }
+    /* part[((task * segs + seg) * maxRowBlocks + rowBlock) * CL_THREADS + thread] x 3 */
+    double *o = part + (((size_t) blockIdx.y * segs + seg) * maxRowBlocks + blockIdx.x) * CL_THREADS * 3 + threadIdx.x;
+    o[0] = mean; o[CL_THREADS] = M2; o[2 * CL_THREADS] = summedVars;
+}
+__global__ void __launch_bounds__(CL_THREADS) k_unclustered_merge(const ClTask *__restrict__ tasks, uint32_t segs, const double *__restrict__ part,
+                                                                  double2 *__restrict__ out, uint32_t maxRowBlocks, const double *__restrict__ rowW) {
+    __shared__ double sh[2 * CL_THREADS / 32];
+    const ClTask t = tasks[blockIdx.y];
+    if (blockIdx.x >= t.rowBlocks) return;
+    const uint32_t lr = blockIdx.x * CL_THREADS + threadIdx.x;
+    const bool active = lr < t.nr;
+    const uint32_t total = t.end - t.begin;
+    double mean = 0, M2 = 0, sv = 0, n = 0;
+    for (uint32_t seg = 0; seg < segs; seg++) {
+        const uint32_t sb = (uint32_t) (((uint64_t) total * seg) / segs), se = (uint32_t) (((uint64_t) total * (seg + 1)) / segs);
+        const double nb = (double) (se - sb);
+        if (nb == 0) continue;
+        const double *o = part + (((size_t) blockIdx.y * segs + seg) * maxRowBlocks + blockIdx.x) * CL_THREADS * 3 + threadIdx.x;
+        const double mb = o[0], Mb = o[CL_THREADS];
+        sv += o[2 * CL_THREADS];
+        const double nn = n + nb, d = mb - mean;
+        M2 = M2 + Mb + d * d * (n * nb / nn);
+        mean = mean + d * (nb / nn);
+        n = nn;
+    }
+    const double rw = rowW ? rowW[t.r0 + (active ? lr : 0)] : 1.0;
+    double a = active ? rw * sv : 0.0, b = active ? rw * M2 : 0.0;
     block_reduce2(a, b, sh);
     if (threadIdx.x == 0) out[(size_t) blockIdx.y * maxRowBlocks + blockIdx.x] = make_double2(a, b);
 }
@@ -391,7 +470,7 @@ __global__ void __launch_bounds__(CL_THREADS) k_carry(const ClTask *__restrict__
 __global__ void __launch_bounds__(CL_THREADS) k_seg_main(const float2 *__restrict__ R, uint32_t ldR, const ClTask *__restrict__ tasks,
                                                          const SegDesc *__restrict__ segs, const uint32_t *__restrict__ lists,
                                                          const double *__restrict__ wArr, const double *__restrict__ WArr,
-                                                         const double *__restrict__ carry, double2 *__restrict__ partial) {
+                                                         const double *__restrict__ carry, double2 *__restrict__ partial, const double *__restrict__ rowW) {
     __shared__ double sB[CL_CHUNK][CL_THREADS];
     __shared__ double sV[CL_CHUNK][CL_THREADS];
     const SegDesc sd = segs[blockIdx.x];
@@ -405,6 +484,7 @@ __global__ void __launch_bounds__(CL_THREADS) k_seg_main(const float2 *__restric
     const uint32_t *list = lists + t.listOff;
     const double *w = wArr + t.stepOff, *W = WArr + t.stepOff;
     double S = (t.nseg > 1) ? carry[t.carryOff + (uint64_t) sd.seg * (t.rowBlocks * CL_THREADS) + lr] : 0.0;
+    const double rw = rowW ? rowW[row] : 1.0;              /* inner_prod(localityWeights, .), 1103-1104 (uniform: k_final applies lw) */
     for (uint32_t k0 = kBeg; k0 < kEnd; k0 += CL_CHUNK) {
         const uint32_t cnt = min((uint32_t) CL_CHUNK, kEnd - k0);
         float2 x[CL_CHUNK];
@@ -424,8 +504,8 @@ __global__ void __launch_bounds__(CL_THREADS) k_seg_main(const float2 *__restric
                 const double xm = x[j].x;
                 const double tmp = wk * S - Wprev * xm;
                 S += xm;
-                sB[j][tid] = active ? tmp * tmp : 0.0;
-                sV[j][tid] = active ? (double) x[j].y / wk : 0.0;
+                sB[j][tid] = active ? rw * (tmp * tmp) : 0.0;
+                sV[j][tid] = active ? rw * ((double) x[j].y / wk) : 0.0;
             }
         }
         __syncthreads();
@@ -441,7 +521,7 @@ __global__ void __launch_bounds__(CL_THREADS) k_seg_main(const float2 *__restric
 }
 
 __global__ void __launch_bounds__(CL_THREADS) k_final(const ClTask *__restrict__ tasks, const double *__restrict__ wArr, const double *__restrict__ WArr,
-                                                      const double2 *__restrict__ partial, float2 *__restrict__ out) {
+                                                      const double2 *__restrict__ partial, float2 *__restrict__ out, int weightedRows) {
     __shared__ double sh[CL_THREADS / 32];
     const ClTask t = tasks[blockIdx.x];
     const uint32_t n = t.end - t.begin;
@@ -461,8 +541,9 @@ __global__ void __launch_bounds__(CL_THREADS) k_final(const ClTask *__restrict__
         const double SV = block_scan_incl(tv, carryV, sh);
         if (k < n) {
             float2 r;
-            r.x = (k == 0) ? 0.0f : (float) (t.lw * (Wk * Q));
-            r.y = (float) (t.lw * (SV * Wk));
+            const double lwF = weightedRows ? 1.0 : t.lw;
+            r.x = (k == 0) ? 0.0f : (float) (lwF * (Wk * Q));
+            r.y = (float) (lwF * (SV * Wk));
             if (!t.finalOnly) out[t.outOff + k] = r;
             else if (k == n - 1) out[t.outOff] = r;
         }
@@ -718,9 +799,11 @@ struct Inst {                                                                  /
 /* device-side workspace shared by all Clustering objects of one buildClusters call */
 struct Workspace {
     alvrl_ctx *c = nullptr; cudaStream_t st = nullptr; uint32_t N = 0, ldR = 0; const float2 *R = nullptr;
+    /* per-row locality weights (neighbourWeight > 0: getLocalMatrix 796-820), indexed like the rows of R; nullptr: uniform lw */
+    const double *rowW = nullptr;
     DevBuf<uint32_t> dLists; DevBuf<float> dCw;
     DevBuf<ClTask> dTasks; DevBuf<float> dDir, dProj; DevBuf<uint32_t> dFlags, dStaged;
-    DevBuf<double2> dPartial, dUncl; DevBuf<double> dW1, dW2, dCarry; DevBuf<float2> dPairs; DevBuf<SegDesc> dSegs;
+    DevBuf<double2> dPartial, dUncl; DevBuf<double> dUnclPart; DevBuf<double> dW1, dW2, dCarry; DevBuf<float2> dPairs; DevBuf<SegDesc> dSegs;
     std::vector<Inst *> insts;
     Prof prof;
 
@@ -744,7 +827,7 @@ struct Workspace {
         std::vector<ClTask> tasks;
         for (Inst *in : insts) tasks.push_back(baseTask(*in));
         dTasks.upload(tasks, st);
-        k_column_weights<<<dim3((N + 127) / 128, (uint32_t) tasks.size()), 128, 0, st>>>(R, ldR, N, dTasks.p, dCw.p);
+        k_column_weights<<<dim3((N + 127) / 128, (uint32_t) tasks.size()), 128, 0, st>>>(R, ldR, N, dTasks.p, dCw.p, rowW);
         launches(1);
         ALVRL_CUDA(cudaGetLastError());
         ensure(dFlags, tasks.size());
@@ -819,8 +902,8 @@ struct Workspace {
             k_carry<<<dim3(pl.T, pl.maxRb), CL_THREADS, 0, st>>>(dT.p, dCarry.p);
             launches(2);
         }
-        k_seg_main<<<dim3(pl.segTotal, pl.maxRb), CL_THREADS, 0, st>>>(R, ldR, dT.p, dSegs.p, dLists.p, dW1.p, dW2.p, dCarry.p, dPartial.p);
-        k_final<<<pl.T, CL_THREADS, 0, st>>>(dT.p, dW1.p, dW2.p, dPartial.p, dPairs.p);
+        k_seg_main<<<dim3(pl.segTotal, pl.maxRb), CL_THREADS, 0, st>>>(R, ldR, dT.p, dSegs.p, dLists.p, dW1.p, dW2.p, dCarry.p, dPartial.p, rowW);
+        k_final<<<pl.T, CL_THREADS, 0, st>>>(dT.p, dW1.p, dW2.p, dPartial.p, dPairs.p, rowW ? 1 : 0);
         launches(3);
         ALVRL_CUDA(cudaGetLastError());
     }
@@ -856,7 +939,7 @@ struct Workspace {
         }
         for (Inst *in : insts) {
             in->numVrlsTotal = N; in->underVar = 0; in->intVar = 0; in->pq.clear(); in->singletons.clear();
-            if (std::fabs((float) (in->lw * in->nr) - 1) > 1e-3) throw Error(ALVRL_ERR_ARG, "Incorrect normalization in localityWeights");
+            if (!rowW && std::fabs((float) (in->lw * in->nr) - 1) > 1e-3) throw Error(ALVRL_ERR_ARG, "Incorrect normalization in localityWeights");
             if (in->pixelUndersampling <= 0 || in->pixelUndersampling > 1) throw Error(ALVRL_ERR_ARG, "Invalid pixel undersampling");
         }
         clap("host lists");
@@ -886,8 +969,19 @@ struct Workspace {
         for (Inst *in : insts) { ClTask t = baseTask(*in); t.begin = 0; t.end = total; ut.push_back(t); maxRb = std::max(maxRb, t.rowBlocks); }
         ensure(dUncl, ut.size() * (size_t) maxRb);
         dTasks.upload(ut, st);
-        k_unclustered<<<dim3(maxRb, (uint32_t) ut.size()), CL_THREADS, 0, st>>>(R, ldR, dTasks.p, dLists.p, dUncl.p, maxRb);
-        launches(1);
+        /* few row blocks (a rank of a multi-GPU job): the VRL list is cut into segments that run concurrently */
+        uint32_t totalRb = 0; for (const ClTask &t : ut) totalRb += t.rowBlocks;
+        uint32_t segs = 1;
+        if (!getenv("ALVRL_UNCL_SEQ")) { while (segs < 64u && totalRb * segs < 592u && (total / (2u * segs)) >= 512u) segs <<= 1; }
+        if (segs > 1) {
+            ensure(dUnclPart, ut.size() * (size_t) segs * maxRb * CL_THREADS * 3);
+            k_unclustered_seg<<<dim3(maxRb, (uint32_t) ut.size(), segs), CL_THREADS, 0, st>>>(R, ldR, dTasks.p, dLists.p, segs, dUnclPart.p, maxRb);
+            k_unclustered_merge<<<dim3(maxRb, (uint32_t) ut.size()), CL_THREADS, 0, st>>>(dTasks.p, segs, dUnclPart.p, dUncl.p, maxRb, rowW);
+            launches(2);
+        } else {
+            k_unclustered<<<dim3(maxRb, (uint32_t) ut.size()), CL_THREADS, 0, st>>>(R, ldR, dTasks.p, dLists.p, dUncl.p, maxRb, rowW);
+            launches(1);
+        }
         ALVRL_CUDA(cudaGetLastError());
         std::vector<double2> u(ut.size() * (size_t) maxRb);
         dUncl.download(u.data(), u.size(), st);
@@ -895,8 +989,9 @@ struct Workspace {
         for (size_t i = 0; i < insts.size(); i++) {
             double a = 0, b = 0;
             for (uint32_t rb = 0; rb < insts[i]->rowBlocks; rb++) { a += u[i * maxRb + rb].x; b += u[i * maxRb + rb].y; }
-            insts[i]->unclIntVar = (float) (insts[i]->lw * a);
-            insts[i]->tracingVar = (float) (insts[i]->lw * b - (double) insts[i]->unclIntVar);
+            const double lwU = rowW ? 1.0 : insts[i]->lw;                     /* per-row weights are applied by the kernel */
+            insts[i]->unclIntVar = (float) (lwU * a);
+            insts[i]->tracingVar = (float) (lwU * b - (double) insts[i]->unclIntVar);
         }
     }
     /* Clustering::refine for the given instances, all advancing one split per round (380-489, 590-684) */
@@ -1065,7 +1160,7 @@ struct Workspace {
         dCursors.alloc(4);
         dX.alloc(xFloats); dX2.alloc(xFloats); dVcol.alloc(dev.size() * (size_t) N); dSrcPos.alloc((size_t) grid * 2 * N);
         rlap("alloc+upload");
-        k_rf_compact<<<dim3((N + 7) / 8, (uint32_t) dev.size()), 256, 0, st>>>(R, ldR, N, dInst.p, dLists.p, dCw.p, dX.p, dVcol.p);
+        k_rf_compact<<<dim3((N + 7) / 8, (uint32_t) dev.size()), 256, 0, st>>>(R, ldR, N, dInst.p, dLists.p, dCw.p, dX.p, dVcol.p, rowW);
         rlap("compact");
         ALVRL_CUDA(cudaMemsetAsync(dCursors.p, 0, 4 * sizeof(uint32_t), st));
         RfScratch scr;
@@ -1088,6 +1183,7 @@ struct Workspace {
         if (scr.gangMin && scr.gangMin < 2u * RF_SMALL) scr.gangMin = 2u * RF_SMALL;          /* gangs use the large-cluster code path */
         DevBuf<double> dCarry; dCarry.alloc((size_t) grid * 2 * RF_GANG_MAX * RF_MAXROWS);
         scr.carry = dCarry.p;
+        scr.rowW = rowW;
         scr.snapHeap = dSnap.p; scr.nodes = dNodes.p; scr.singles = dSingles.p; scr.heapOv = dHeapOv.p; scr.heapCap = heapCap; scr.nodeCap = nodeCap;
         scr.srcPos = dSrcPos.p; scr.posTmp = dSrcPos.p + (size_t) grid * N;
         scr.initNodes = dInitNodes.p; scr.initSingles = dInitSingles.p; scr.outNodes = dOutNodes.p; scr.outSingles = dOutSingles.p; scr.cursors = dCursors.p;
@@ -1415,15 +1511,17 @@ struct Workspace {
 
 /* the same flags left in a caller-owned device buffer (N bytes), for the all-reduce of the multi-GPU path */
 void column_nonzero_into(alvrl_ctx *c, uint8_t *dFlags) {
-    const uint32_t N = (uint32_t) c->vrlHost.size(), G = (uint32_t) c->rowPixel.size();
-    k_total_contribution<<<(N + 127) / 128, 128, 0, c->stream>>>(c->dR.p, c->ldR, G, N, dFlags);
+    const uint32_t N = (uint32_t) c->vrlHost.size(), S = c->numSlices();
+    const uint32_t r0 = c->rowOffset[std::min(c->sliceBegin, S)], r1 = c->rowOffset[std::min(c->sliceEnd, S)];
+    k_total_contribution<<<(N + 7) / 8, 256, 0, c->stream>>>(c->dR.p, c->ldR, r0, r1, N, dFlags);
     c->stats.kernelLaunches++;
     ALVRL_CUDA(cudaGetLastError());
 }
 void column_nonzero_device(alvrl_ctx *c, std::vector<uint8_t> &flags) {
-    const uint32_t N = (uint32_t) c->vrlHost.size(), G = (uint32_t) c->rowPixel.size();
+    const uint32_t N = (uint32_t) c->vrlHost.size(), S = c->numSlices();
+    const uint32_t r0 = c->rowOffset[std::min(c->sliceBegin, S)], r1 = c->rowOffset[std::min(c->sliceEnd, S)];
     DevBuf<uint8_t> dNz; dNz.alloc(N);
-    k_total_contribution<<<(N + 127) / 128, 128, 0, c->stream>>>(c->dR.p, c->ldR, G, N, dNz.p);
+    k_total_contribution<<<(N + 7) / 8, 256, 0, c->stream>>>(c->dR.p, c->ldR, r0, r1, N, dNz.p);
     c->stats.kernelLaunches++;
     ALVRL_CUDA(cudaGetLastError());
     flags.resize(N);
@@ -1463,6 +1561,52 @@ float measure_fp32_peak_tflops() {
     }
     cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d);
     return best;
+}
+
+/* getLocalMatrix with neighbourWeight > 0 (779-827): the rows of slice i followed by the rows of its neighbour slices are
+ * gathered into one contiguous block of a second matrix (the reference copies them too), so that every clustering kernel
+ * keeps addressing "rows [r0, r0 + nr) of every column"; warp = column, lanes = rows */
+__global__ void k_gather_local_rows(const float2 *__restrict__ R, uint32_t ldR, const uint32_t *__restrict__ rowMap, uint32_t rows, uint32_t N,
+                                    float2 *__restrict__ out, uint32_t ldOut) {
+    const uint32_t v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (v >= N) return;
+    const float2 *col = R + (size_t) v * ldR;
+    float2 *dst = out + (size_t) v * ldOut;
+    for (uint32_t j = lane; j < rows; j += 32) dst[j] = col[rowMap[j]];
+}
+
+/* Preprocessor::buildLocalities (1241-1293): the neighbourCount slices closest in the 6-D (position centroid, direction
+ * centroid) distance; quirk B7 kept (maxInd is not reset per slice; entries never filled keep index 0).  std::set order:
+ * by slice index, then distance. */
+static void build_localities(const alvrl_ctx *c, std::vector<std::set<std::pair<uint32_t, float>>> &loc) {
+    const uint32_t S = c->numSlices(), nc = (uint32_t) std::max(0, c->P.neighbourCount);
+    loc.assign(S, {});
+    auto dist = [&](uint32_t i, uint32_t j) {                                   /* sliceDistance, 1230-1239 */
+        const float *a = &c->sliceCentroid[6 * (size_t) i], *b = &c->sliceCentroid[6 * (size_t) j];
+        float dp, dd;
+        { const float x = a[0] - b[0], y = a[1] - b[1], z = a[2] - b[2]; dp = x * x + y * y + z * z; }
+        { const float x = a[3] - b[3], y = a[4] - b[4], z = a[5] - b[5]; dd = x * x + y * y + z * z; }
+        return std::sqrt(dp + dd);
+    };
+    if (S <= nc) {
+        for (uint32_t i = 0; i < S; i++) for (uint32_t j = 0; j < S; j++) if (i != j) loc[i].insert(std::make_pair(j, dist(i, j)));
+        return;
+    }
+    if (nc == 0) return;
+    std::vector<float> distances(nc, std::numeric_limits<float>::infinity()); std::vector<uint32_t> indices(nc, 0);
+    uint32_t maxInd = 0;
+    for (uint32_t i = 0; i < S; i++) {
+        for (uint32_t j = 0; j < nc; j++) distances[j] = std::numeric_limits<float>::infinity();
+        for (uint32_t j = 0; j < S; j++) {
+            if (i == j) continue;
+            const float d = dist(i, j);
+            if (d < distances[maxInd]) {
+                distances[maxInd] = d; indices[maxInd] = j;
+                for (uint32_t k = 0; k < nc; k++) if (distances[k] > distances[maxInd]) maxInd = k;
+            }
+        }
+        for (uint32_t x = 0; x < nc; x++) loc[i].insert(std::make_pair(indices[x], distances[x]));
+    }
 }
 
 void build_clusters_device(alvrl_ctx *c, bool needFallback) {
@@ -1539,9 +1683,54 @@ void build_clusters_device(alvrl_ctx *c, bool needFallback) {
     std::vector<std::unique_ptr<HostSampler>> clones;
     const int w = std::max(1, c->P.workerCount);
     if (sfmt && w > 1) for (int i = 0; i < w; i++) clones.emplace_back(c->mainSampler->clone());   /* ClusterRefiner ctor, 738 */
+    /* neighbour slices in the local matrices (neighbourWeight > 0; getLocalMatrix 796-820, buildLocalities 1241-1293) */
+    const bool neighbours = c->P.neighbourWeight > 0;
+    DevBuf<float2> dRnb; DevBuf<double> dRowW; DevBuf<uint32_t> dRowMap;
+    std::vector<uint32_t> nbR0(S + 1, 0);                     /* first row of slice i's block in the gathered matrix */
+    uint32_t ldNb = 0;
+    if (neighbours) {
+        if (sfmt) throw Error(ALVRL_ERR_UNSUPPORTED, "neighbourWeight > 0 needs the counter sample stream on the device path");
+        if (ranged) throw Error(ALVRL_ERR_UNSUPPORTED, "neighbourWeight > 0: the neighbour slices' rows of R live on other ranks (no halo exchange); use one handle");
+        std::vector<std::set<std::pair<uint32_t, float>>> loc;
+        build_localities(c, loc);
+        std::vector<uint32_t> rowMap; std::vector<double> rowW;
+        for (uint32_t i = 0; i < S; i++) {
+            nbR0[i] = (uint32_t) rowMap.size();
+            const uint32_t nr = c->rowOffset[i + 1] - c->rowOffset[i];
+            for (uint32_t r = c->rowOffset[i]; r < c->rowOffset[i + 1]; r++) rowMap.push_back(r);
+            /* Float arithmetic as written (796-820): 1.0 / dist is a double quotient stored to Float, the rest is Float, the
+             * final weights are widened to double */
+            std::vector<float> neighbourWeights(loc[i].size());
+            float summedNeighbourWeight = 0;
+            size_t j = 0;
+            for (auto it = loc[i].begin(); it != loc[i].end(); ++it, ++j) {
+                for (uint32_t r = c->rowOffset[it->first]; r < c->rowOffset[it->first + 1]; r++) rowMap.push_back(r);
+                neighbourWeights[j] = (float) (1.0 / it->second);
+                summedNeighbourWeight += neighbourWeights[j];
+            }
+            const float sliceWeight = summedNeighbourWeight * (1 - c->P.neighbourWeight) / c->P.neighbourWeight;
+            const float normalization = 1 / (sliceWeight + summedNeighbourWeight);
+            for (uint32_t k = 0; k < nr; k++) rowW.push_back(sliceWeight * normalization / nr);
+            j = 0;
+            for (auto it = loc[i].begin(); it != loc[i].end(); ++it, ++j) {
+                const uint32_t nrj = c->rowOffset[it->first + 1] - c->rowOffset[it->first];
+                for (uint32_t k = 0; k < nrj; k++) rowW.push_back(neighbourWeights[j] * normalization / nrj);
+            }
+        }
+        nbR0[S] = (uint32_t) rowMap.size();
+        const uint32_t rows = (uint32_t) rowMap.size();
+        ldNb = (rows + 31u) & ~31u;
+        dRowMap.upload(rowMap, st); dRowW.upload(rowW, st);
+        dRnb.alloc((size_t) N * ldNb);
+        k_gather_local_rows<<<(N + 7) / 8, 256, 0, st>>>(c->dR.p, c->ldR, dRowMap.p, rows, N, dRnb.p, ldNb);
+        c->stats.kernelLaunches++;
+        ALVRL_CUDA(cudaGetLastError());
+        ALVRL_CUDA(cudaStreamSynchronize(st));
+    }
     for (uint32_t i = sb; i < se; i++) {
         std::unique_ptr<Inst> in(new Inst());
         in->id = i; in->r0 = c->rowOffset[i]; in->nr = c->rowOffset[i + 1] - c->rowOffset[i];
+        if (neighbours) { in->r0 = nbR0[i]; in->nr = nbR0[i + 1] - nbR0[i]; }
         in->rowBlocks = std::max(1u, (in->nr + CL_THREADS - 1) / CL_THREADS);
         in->lw = 1.0 / in->nr; in->pixelUndersampling = c->sliceUndersampling[i];
         if (sfmt) {
@@ -1585,6 +1774,7 @@ void build_clusters_device(alvrl_ctx *c, bool needFallback) {
                 groups[gI].reset(new Workspace());
                 Workspace &w2 = *groups[gI];
                 w2.c = c; w2.N = N; w2.ldR = c->ldR; w2.R = c->dR.p; w2.serialSort = nGroups > 1; w2.deviceRounds = true;
+                if (neighbours) { w2.R = dRnb.p; w2.ldR = ldNb; w2.rowW = dRowW.p; }
                 for (size_t i = gI; i < ws.insts.size(); i += nGroups) w2.insts.push_back(ws.insts[i]);
             }
             for (size_t gI = 0; gI < nGroups; gI++) threads.emplace_back([&, gI]() {

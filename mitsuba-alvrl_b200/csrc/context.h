@@ -149,6 +149,7 @@ struct alvrl_ctx {
     /* slices live on the device: dRecIdx = the pixel ids in partition order (slice s = positions [sliceLo[s], sliceLo[s] +
      * sliceSize[s])), dPixelToSlice = m_slices; the host keeps the ranges only */
     std::vector<uint32_t> sliceLo, sliceSize; bool haveSlices = false;
+    std::vector<float> sliceCentroid;              /* 6 per slice: position / direction box midpoints (Preprocessor.cpp:1337-1338) */
     alvrl::DevBuf<uint32_t> dRecIdx, dPixelToSlice;
     uint32_t numSlices() const { return (uint32_t) sliceSize.size(); }
     std::vector<uint32_t> rowOffset, rowPixel; bool haveRows = false;
@@ -158,6 +159,7 @@ struct alvrl_ctx {
 
     /* R (column-major, see types.h) */
     alvrl::DevBuf<float2> dR; uint32_t ldR = 0; bool haveR = false;
+    uint32_t builtRow0 = 0, builtRow1 = 0;          /* rows of R the last build_R / set_R wrote */
     alvrl::DevBuf<float> dTape; uint32_t tapeK = 0; std::vector<float> userTape;
 
     /* clusters (vrlClusterInfo, vrlIntegrator.cpp:106-112) */
@@ -172,6 +174,7 @@ struct alvrl_ctx {
     alvrl::DevBuf<uint32_t> dSlicePixels, dRepOffset; alvrl::DevBuf<uint4> dWork; alvrl::DevBuf<VrlRec> dRepRecs;
     alvrl::DevBuf<float4> dFb; alvrl::DevBuf<float> dRgb;
     uint32_t numWork = 0; bool renderListsDirty = true, pixelListsDirty = true;
+    std::vector<uint4> workHost;      /* host mirror of dWork (slice-range selection) */
 
     /* sample streams */
     std::unique_ptr<alvrl::HostSampler> mainSampler;

@@ -79,6 +79,7 @@ struct RfScratch {                      /* per CTA */
     /* gangs (k_refine_mt): clusters of >= gangMin columns are split by 2 CTAs, >= 2 gangMin by 4, ... up to gangMax (0: off) */
     uint32_t gangMin, gangMax;
     double *carry;                      /* [grid][2][RF_GANG_MAX][RF_MAXROWS] row sums of the members' step ranges */
+    const double *rowW;                 /* per-row locality weights indexed like the rows of R (neighbour slices in L_i), or nullptr: uniform lw */
 };
 #define RF_GANG_MAX 16
 /* CTAs that split a cluster of n columns together: a pure function of n (and of the launch), so that every member and the
@@ -231,7 +232,7 @@ __device__ __forceinline__ void rf_sort_steps(unsigned long long *sk, uint32_t l
  * copy), so that a split streams n * nrP * 4 contiguous bytes instead of gathering columns from all over R.  Warp = column. */
 __global__ void __launch_bounds__(256) k_rf_compact(const float2 *__restrict__ R, uint32_t ldR, uint32_t N, const RfInst *__restrict__ insts,
                                                     const uint32_t *__restrict__ lists, const float *__restrict__ cw, float *__restrict__ X,
-                                                    double *__restrict__ Vcol) {
+                                                    double *__restrict__ Vcol, const double *__restrict__ rowW) {
     const RfInst &I = insts[blockIdx.y];
     const uint32_t lane = threadIdx.x & 31, i = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (i >= N) return;
@@ -242,7 +243,7 @@ __global__ void __launch_bounds__(256) k_rf_compact(const float2 *__restrict__ R
     double vy = 0;
     for (uint32_t r = lane; r < I.nrP; r += 32) {
         float2 e = make_float2(0, 0);
-        if (r < I.nr) { e = col[r]; vy += (double) e.y / wc; }
+        if (r < I.nr) { e = col[r]; vy += (rowW ? rowW[I.r0 + r] : 1.0) * ((double) e.y / wc); }
         out[r] = e.x;
     }
     for (int o = 16; o > 0; o >>= 1) vy += __shfl_down_sync(0xffffffffu, vy, o);
@@ -279,7 +280,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_refine(float *XA, float *XB, 
         if (sm.inst >= numInst) break;
         RfInst *I = insts + sm.inst;
         const uint32_t nr = I->nr, key = I->rngKey;
-        const double lw = I->lw;
+        const double lw = scr.rowW ? 1.0 : I->lw;                     /* per-row weights enter B_k and Vcol instead */
         uint32_t *ilist = lists + I->listOff;
         const float *icw = cw + I->cwOff;
         /* padded column length, 16-byte granules per column, tile column stride (a multiple of 8 granules: element r of tile
@@ -525,7 +526,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_refine_mt(float *XA, float *X
         RfInst *I = insts + o;
         MtNode *nodes = mp.nodes + (uint64_t) o * mp.nodeCap;
         const uint32_t nr = I->nr;
-        const double lw = I->lw;
+        const double lw = scr.rowW ? 1.0 : I->lw;                     /* per-row weights enter B_k and Vcol instead */
         const float *icw = cw + I->cwOff;
         const uint32_t nrP = I->nrP, nq = nrP >> 2, tS = (nrP + 31u) & ~31u;
         const double *Vi = Vcol + I->vOff;

@@ -395,6 +395,9 @@
                 const uint32_t rA = hr, rB = hr + RS;
                 const bool actA = hr < RS && rA < nr, actB = hr < RS && rB < nr;
                 const uint32_t nw = RS >> 5;
+                /* per-row locality weights (neighbour slices in L_i): B_k = sum_r w_r (..)^2 */
+                const bool rowWeighted = scr.rowW != nullptr;
+                const double wRowA = (rowWeighted && actA) ? scr.rowW[I->r0 + rA] : 1.0, wRowB = (rowWeighted && actB) ? scr.rowW[I->r0 + rB] : 1.0;
                 double SA = 0, SB = 0;
                 const long long gs0_ = clock64();
                 if (gG > 1u) {
@@ -487,7 +490,7 @@
                                     const double xad = (double) xa[u], xbd = (double) xb[u];
                                     const double ta = wk * SA - Wp * xad, tb = wk * SB - Wp * xbd;
                                     SA += xad; SB += xbd;
-                                    b[u] = ta * ta + tb * tb;
+                                    b[u] = rowWeighted ? wRowA * (ta * ta) + wRowB * (tb * tb) : ta * ta + tb * tb;
                                 }
                             }
                             rf_reduce16(b, lane);

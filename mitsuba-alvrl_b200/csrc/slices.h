@@ -29,6 +29,7 @@ struct SliceInfo {
 class SliceTree {
     struct Node {
         uint32_t lo, hi; float diag; unsigned char dim; float split;
+        float centroid[6];                                         /* positionCentroid, directionCentroid: box midpoints, 1337-1338 */
         bool operator<(const Node &o) const { return diag < o.diag; }
     };
     /* a gather point travels with its pixel index: the partition permutes these records themselves (the reference permutes
@@ -51,6 +52,7 @@ class SliceTree {
     }
     Node makeNode(uint32_t lo, uint32_t hi) const {                /* SliceNode ctor, 1301-1339 */
         Node n; n.lo = lo; n.hi = hi;
+        for (int c = 0; c < 6; c++) n.centroid[c] = std::numeric_limits<float>::quiet_NaN();
         if (lo + 1 == hi) { n.diag = 0; n.dim = 0; n.split = std::numeric_limits<float>::quiet_NaN(); return n; }
         const float inf = std::numeric_limits<float>::infinity();
         float mn[6] = {inf, inf, inf, inf, inf, inf}, mx[6] = {-inf, -inf, -inf, -inf, -inf, -inf};
@@ -71,9 +73,11 @@ class SliceTree {
         splitPoint(pmin, pmax, dimP, splitP, extP);
         splitPoint(dmin, dmax, dimD, splitD, extD);
         if (extP > extD) { n.dim = dimP; n.split = splitP; } else { n.dim = 3 + dimD; n.split = splitD; }   /* 1442-1448 */
+        for (int c = 0; c < 6; c++) n.centroid[c] = mn[c] + 0.5f * (mx[c] - mn[c]);
         return n;
     }
 public:
+    std::vector<float> centroids;                                  /* 6 per slice, filled by build() */
     SliceTree(const std::vector<P3> &p, const std::vector<P3> &d) : pos(p), dir(d) {}
 
     /* returns pixel -> slice; fills `slices` in slice-id order */
@@ -117,7 +121,9 @@ public:
                 heap.push_back(makeNode(mid, top.hi)); std::push_heap(heap.begin(), heap.end());
             }
         }
+        centroids.clear();
         for (const Node &nd : heap) {                                         /* slice id = heap array position, 1400-1417 */
+            centroids.insert(centroids.end(), nd.centroid, nd.centroid + 6);
             SliceInfo si;
             si.pixels.resize(nd.hi - nd.lo);
             for (uint32_t k = nd.lo; k < nd.hi; k++) { const uint32_t g = rec[k].idx; si.pixels[k - nd.lo] = g; toSlice[g] = (uint32_t) slices.size(); }

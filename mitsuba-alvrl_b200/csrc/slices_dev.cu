@@ -221,7 +221,7 @@ __global__ void k_slice_finish(const SRec *__restrict__ rec, uint32_t first, uin
     pixelToSlice[px] = ids[a];
 }
 
-struct HNode { uint32_t lo, hi; float diag; unsigned char dim; float split; bool operator<(const HNode &o) const { return diag < o.diag; } };
+struct HNode { uint32_t lo, hi; float diag; unsigned char dim; float split; float centroid[6]; bool operator<(const HNode &o) const { return diag < o.diag; } };
 
 /* findSplitPoint, 1451-1487 (same code as slices.h) */
 void splitPoint(const float mn[3], const float mx[3], unsigned char &dim, float &split, float &extent) {
@@ -237,6 +237,7 @@ void splitPoint(const float mn[3], const float mx[3], unsigned char &dim, float 
 /* SliceNode ctor from the extrema, 1301-1339 */
 HNode makeNode(uint32_t lo, uint32_t hi, const float mn[6], const float mx[6]) {
     HNode n; n.lo = lo; n.hi = hi;
+    for (int c = 0; c < 6; c++) n.centroid[c] = std::numeric_limits<float>::quiet_NaN();
     if (lo + 1 == hi) { n.diag = 0; n.dim = 0; n.split = std::numeric_limits<float>::quiet_NaN(); return n; }
     float dp, dd;
     { const float a = mn[0] - mx[0], b = mn[1] - mx[1], c = mn[2] - mx[2]; dp = a * a + b * b + c * c; }
@@ -246,6 +247,7 @@ HNode makeNode(uint32_t lo, uint32_t hi, const float mn[6], const float mx[6]) {
     splitPoint(mn, mx, dimP, splitP, extP);
     splitPoint(mn + 3, mx + 3, dimD, splitD, extD);
     if (extP > extD) { n.dim = dimP; n.split = splitP; } else { n.dim = 3 + dimD; n.split = splitD; }
+    for (int c = 0; c < 6; c++) n.centroid[c] = mn[c] + 0.5f * (mx[c] - mn[c]);       /* box midpoints, 1337-1338 */
     return n;
 }
 
@@ -290,7 +292,7 @@ bool build_slices_device(alvrl_ctx *c, const float *dPos, const float *dDir, uin
             }
         }
     }
-    c->sliceLo.clear(); c->sliceSize.clear();
+    c->sliceLo.clear(); c->sliceSize.clear(); c->sliceCentroid.clear();
     c->dRecIdx.alloc(P); c->dPixelToSlice.alloc(P);
     std::vector<HNode> heap;
     NodeRes res;
@@ -321,7 +323,7 @@ bool build_slices_device(alvrl_ctx *c, const float *dPos, const float *dDir, uin
     /* slice id = heap array position, 1400-1417 */
     const uint32_t S = (uint32_t) heap.size();
     std::vector<std::pair<uint32_t, uint32_t>> byStart(S);
-    for (uint32_t s = 0; s < S; s++) { c->sliceLo.push_back(heap[s].lo); c->sliceSize.push_back(heap[s].hi - heap[s].lo); byStart[s] = std::make_pair(heap[s].lo, s); }
+    for (uint32_t s = 0; s < S; s++) { c->sliceLo.push_back(heap[s].lo); c->sliceSize.push_back(heap[s].hi - heap[s].lo); c->sliceCentroid.insert(c->sliceCentroid.end(), heap[s].centroid, heap[s].centroid + 6); byStart[s] = std::make_pair(heap[s].lo, s); }
     std::sort(byStart.begin(), byStart.end());
     std::vector<uint32_t> starts(std::max(1u, S)), ids(std::max(1u, S));
     for (uint32_t s = 0; s < S; s++) { starts[s] = byStart[s].first; ids[s] = byStart[s].second; }

@@ -254,7 +254,10 @@ def _clusters_equal(cg, co, what=""):
 
 
 @pytest.mark.parametrize("kw", [dict(), dict(localUndersampling=4.0), dict(localRefinement=0), dict(globalCluster=1, globalUndersampling=20.0),
-                                dict(depthCorrection=0.5), dict(depthCorrection=1.7)])
+                                dict(depthCorrection=0.5), dict(depthCorrection=1.7),
+                                dict(neighbourCount=3, neighbourWeight=0.4, targetNumSlices=12),      # neighbour slices' rows in L_i, 796-820
+                                dict(neighbourCount=20, neighbourWeight=0.25, targetNumSlices=8),     # every slice is every slice's neighbour, 1245-1258
+                                dict(neighbourCount=2, neighbourWeight=0.6, targetNumSlices=10, localUndersampling=5.0)])
 def test_clusters_identical_given_oracle_R(pkg, orc, kw):
     g, o = _pair(pkg, orc, "C1", 64, 64, 200, seed=4, **kw)
     for it in (g, o):

@@ -9,6 +9,7 @@ import argparse
 ap = argparse.ArgumentParser()
 ap.add_argument("--config", default="C2"); ap.add_argument("--width", type=int, default=None); ap.add_argument("--height", type=int, default=None)
 ap.add_argument("--vrls", type=int, default=None); ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--slice-range", type=int, nargs=2, default=None, help="what one rank of a multi-GPU job owns")
 a = ap.parse_args()
 scene, vrls, params = pkg.scenes.make_config(a.config, width=a.width, height=a.height, n_vrls=a.vrls)
 g = pkg.integrator(0, **params)
@@ -20,6 +21,7 @@ for r in range(a.reps):
         global t0
         now = time.time(); t[name] = (now - t0) * 1e3; t0 = now
     g.build_slices(); lap("build_slices")
+    if a.slice_range: g.set_slice_range(*a.slice_range)
     g.sample_slice_mapping(); lap("slice_mapping")
     g.build_R(); lap("build_R")
     g.build_clusters(); lap("build_clusters")
