@@ -1190,7 +1190,12 @@ struct Workspace {
         if (mt) {
             /* the ticket ring: at most MT_K split tasks or one control task per object are in flight */
             const size_t gangTickets = scr.gangMin ? (size_t) (N / scr.gangMin + 1) * RF_GANG_MAX : 0;   /* per object, on top of MT_K */
-            uint32_t qcap = 65536; while (qcap < 4 * (MT_K + 1 + gangTickets) * dev.size()) qcap <<= 1;
+            /* splits of one object kept in flight: 32 when the GPU is full of objects; a rank of a multi-GPU job holds few, and
+             * more speculation keeps its CTAs busy (the clusters with the largest keys are the ones the queue pops next) */
+            uint32_t inflight = 32;
+            { const double load = (double) dev.size() / std::max(1, sms); if (load < 0.25) inflight = 128; else if (load < 0.5) inflight = 64; }
+            if (const char *e = getenv("ALVRL_MT_K")) inflight = (uint32_t) std::min(MT_K_MAX, std::max(1, atoi(e)));
+            uint32_t qcap = 65536; while (qcap < 4 * (inflight + 1 + gangTickets) * dev.size()) qcap <<= 1;
             dSlots.alloc(qcap); dMtClk.alloc((size_t) grid * 32);
             ALVRL_CUDA(cudaMemsetAsync(dSlots.p, 0, qcap * sizeof(unsigned long long), st));
             ALVRL_CUDA(cudaMemsetAsync(dOutstanding.p, 0, pool * sizeof(uint32_t), st));
@@ -1205,6 +1210,7 @@ struct Workspace {
             MtPools mp;
             mp.nodes = dMtNodes.p; mp.heap = dMtHeap.p; mp.snap = dSnap.p; mp.singles = dSingles.p; mp.outstanding = dOutstanding.p;
             mp.ctl = dCtl.p; mp.waitNode = dWaitNode.p;
+            mp.inflight = inflight;
             mp.slots = dSlots.p; mp.qmask = qcap - 1; mp.ctr = dCtr.p; mp.nodeCap = nodeCap; mp.heapCap = heapCap; mp.clk = dMtClk.p;
             ALVRL_CUDA(cudaFuncSetAttribute(k_refine_mt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(RfShared)));
             k_refine_mt<<<grid, RF_THREADS, sizeof(RfShared), st>>>(dX.p, dX2.p, dVcol.p, dInst.p, (uint32_t) dev.size(), dLists.p, dLists1.p, dCw.p, scr, mp);

@@ -17,6 +17,8 @@
  */
 #include <dlfcn.h>
 #include <nccl.h>
+#include <chrono>
+#include <cstdio>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -83,17 +85,30 @@ struct alvrl_group {
 namespace {
 
 /* one frame on one member: every rank builds the (deterministic) slices, takes its range, and renders its pixels */
+double gnow_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 void member_frame(alvrl_group *g, Member *m, float *rgbHost) {
     alvrl_ctx *c = m->c;
     ALVRL_CUDA(cudaSetDevice(c->device));
+    const bool prof = getenv("ALVRL_PROFILE") != nullptr;
+    double t0 = gnow_ms(), tPrev = t0;
+    std::string log;
+    auto lap = [&](const char *what) { if (prof) { cudaStreamSynchronize(c->stream); const double n = gnow_ms(); char b[64]; snprintf(b, sizeof(b), " %s %.1f", what, n - tPrev); log += b; tPrev = n; } };
     G_API(alvrl_build_slices(c));                                            /* Preprocessor::buildSlices: replicated, identical on every rank */
     const uint32_t S = c->numSlices();
+    /* cost of a slice on a rank: its pixels (rows of R, refinement sweeps and render work grow with them) plus a constant per
+     * Clustering object (picks, sorts and queue work do not depend on the rows): measured on C2, one object weighs about
+     * 1/500 of all pixels */
     std::vector<uint32_t> sizes(S);
-    for (uint32_t i = 0; i < S; i++) sizes[i] = c->sliceSize[i];
+    uint64_t totalPix = 0;
+    for (uint32_t i = 0; i < S; i++) totalPix += c->sliceSize[i];
+    for (uint32_t i = 0; i < S; i++) sizes[i] = c->sliceSize[i] + (uint32_t) (totalPix / 500u);
     balanced_slice_range(sizes.data(), S, g->world, m->rank, m->sliceBegin, m->sliceEnd);
     G_API(alvrl_set_slice_range(c, m->sliceBegin, m->sliceEnd));
+    lap("slices");
     G_API(alvrl_sample_slice_mapping(c));
     G_API(alvrl_build_R(c));
+    lap("mapping+R");
     const uint32_t N = (uint32_t) c->vrlHost.size(), P = c->numPixels();
     if (g->world > 1) {                                                      /* zero / non-zero columns over ALL rows: OR across ranks, on the device */
         m->flags.alloc(N);
@@ -103,10 +118,13 @@ void member_frame(alvrl_group *g, Member *m, float *rgbHost) {
         m->flags.download(f.data(), N, c->stream);
         G_API(alvrl_set_column_nonzero(c, f.data()));
     } else G_API(alvrl_set_column_nonzero(c, nullptr));
+    lap("flags");
     G_API(alvrl_build_clusters(c));
+    lap("clusters");
     m->fb.alloc(P);
     ALVRL_CUDA(cudaMemsetAsync(m->fb.p, 0, (size_t) P * sizeof(float4), c->stream));
     G_API(alvrl_render_device(c, m->fb.p, c->stream));
+    lap("render");
     if (g->world > 1) G_NCCL(nccl().Reduce(m->fb.p, m->fb.p, (size_t) P * 4, ncclFloat, ncclSum, 0, m->comm, c->stream));
     if (m->rank == 0 && rgbHost) {
         m->rgb.alloc(3 * (size_t) P);
@@ -115,6 +133,8 @@ void member_frame(alvrl_group *g, Member *m, float *rgbHost) {
         m->rgb.download(rgbHost, 3 * (size_t) P, c->stream);
     }
     ALVRL_CUDA(cudaStreamSynchronize(c->stream));
+    lap("reduce+image");
+    if (prof) fprintf(stderr, "[alvrl group] rank %d slices [%u, %u):%s | total %.1f ms\n", m->rank, m->sliceBegin, m->sliceEnd, log.c_str(), gnow_ms() - t0);
 }
 
 } // namespace

@@ -106,7 +106,7 @@ struct RfShared {
     float rb[RF_WARPS], rs[RF_WARPS]; uint32_t ri[RF_WARPS];
     /* control block (written by thread 0 between barriers) */
     uint32_t inst, begin, end, srcBuf, found, pick[2], flags, done, snap, err, nodeKey, nodePos;
-    uint32_t task[2], stop, selCount, sel[32];             /* k_refine_mt: the task in hand, the control pass */
+    uint32_t task[2], stop, selCount, sel[128];             /* k_refine_mt: the task in hand, the control pass */
     uint32_t gang[3];                                      /* k_refine_mt: gang size, this CTA's member index, the leader's block */
     unsigned long long mtClk[8];                          /* control cycles, ticket wait, control passes, split tasks, gang sync wait, gang syncs */
     float u1, u2, norm[3];
@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_refine(float *XA, float *XB, 
  * cluster is what the consumed splits left, 641-642).
  * No co-residency is assumed: a CTA only waits for a ticket it has drawn, and tickets are filled by running CTAs.
  * ------------------------------------------------------------------------------------------------------------------- */
-#define MT_K 32
+#define MT_K_MAX 128                /* most splits of one object in flight (sm.sel) */
 
 struct MtNode {                         /* 64 bytes */
     float under, integ; uint32_t begin, end;            /* ClusterNode; bit 31 of begin: which copy holds list range and columns */
@@ -456,6 +456,7 @@ struct MtPools {
     unsigned long long *slots; uint32_t qmask;                  /* ticket ring: (generation << 40) | (type << 39) | (object << 24) | node */
     uint32_t *ctr;                                              /* [0] next ticket to draw, [1] next ticket to fill, [2] objects not done */
     uint32_t nodeCap, heapCap;
+    uint32_t inflight;                                          /* splits of one object kept in flight (<= MT_K_MAX) */
     unsigned long long *clk;                                    /* [grid][32] profile counters */
 };
 
@@ -738,7 +739,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_refine_mt(float *XA, float *X
                 /* keep MT_K splits in flight; the top of the queue is handed out in any case (it is what the object waits for) */
                 const uint32_t inflight = *(volatile uint32_t *) (mp.outstanding + o);
                 sm.selCount = 0;
-                sm.pick[0] = inflight < MT_K ? MT_K - inflight : 0u;
+                sm.pick[0] = inflight < mp.inflight ? mp.inflight - inflight : 0u;
                 if (sm.pick[0] == 0u && *(volatile uint32_t *) &nodes[heap[0].id].state == 0u) sm.pick[0] = 1u;
             }
             __syncthreads();
@@ -825,7 +826,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_refine_mt(float *XA, float *X
                     atomicAdd(mp.outstanding + o, sm.selCount);                 /* before the tasks can complete */
                     /* clusters for one CTA go out together; a cluster for a gang goes out as G consecutive tickets of its own
                      * (consecutive: the CTAs draw tickets in order, so no later task can be waited for before a gang is complete) */
-                    uint32_t plain[32], np = 0;
+                    uint32_t *plain = reinterpret_cast<uint32_t *>(sm.chunkEnd), np = 0;   /* (scratch: the pick buffers are free in a control pass) */
                     for (uint32_t q = 0; q < sm.selCount; q++) {
                         const MtNode &sn = nodes[sm.sel[q]];
                         const uint32_t G = rf_gang_size(sn.end - (sn.begin & 0x7fffffffu), scr.gangMin, gangCap);

@@ -356,9 +356,15 @@ void slice_gather_rows_device(alvrl_ctx *c, const std::vector<uint32_t> &positio
 /* the pixel lists of the render pass, slice by slice: pixels are visited in index order and appended to their slice's list
  * (warp-aggregated cursor bumps: the lists come out nearly sorted, which is all the render kernel wants -- ray coherence;
  * the image does not depend on the order) */
-__global__ void k_slice_bucket_pixels(const uint32_t *__restrict__ pixelToSlice, uint32_t P, const uint32_t *__restrict__ sliceStart,
+__global__ void k_slice_bucket_pixels(const uint32_t *__restrict__ pixelToSlice, uint32_t P, uint32_t W, uint32_t H, const uint32_t *__restrict__ sliceStart,
                                       uint32_t *__restrict__ cursor, uint32_t *__restrict__ slicePixels) {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    /* a block visits a 16 x 16 tile of the image and a warp an 8 x 4 patch of it, so that 32 consecutive entries of a slice's
+     * list are neighbours in both directions (pixel index = y + H x) */
+    const uint32_t tilesY = (H + 15u) / 16u;
+    const uint32_t tx = blockIdx.x / tilesY, ty = blockIdx.x % tilesY;
+    const uint32_t warp = threadIdx.x >> 5, l = threadIdx.x & 31;
+    const uint32_t x = tx * 16u + (warp & 1u) * 8u + (l & 7u), y = ty * 16u + (warp >> 1) * 4u + (l >> 3);
+    const uint32_t p = (x < W && y < H) ? y + H * x : P;
     const uint32_t s = p < P ? pixelToSlice[p] : ALVRL_NO_SLICE;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t peers = __match_any_sync(0xffffffffu, s);
@@ -375,7 +381,7 @@ void slice_bucket_pixels_device(alvrl_ctx *c, const std::vector<uint32_t> &slice
     if (!S || !total) return;
     DevBuf<uint32_t> dStart, dCursor; dStart.upload(sliceStart, c->stream); dCursor.alloc(S);
     ALVRL_CUDA(cudaMemsetAsync(dCursor.p, 0, S * sizeof(uint32_t), c->stream));
-    k_slice_bucket_pixels<<<(P + 255) / 256, 256, 0, c->stream>>>(c->dPixelToSlice.p, P, dStart.p, dCursor.p, c->dSlicePixels.p);
+    k_slice_bucket_pixels<<<((c->cam.W + 15u) / 16u) * ((c->cam.H + 15u) / 16u), 256, 0, c->stream>>>(c->dPixelToSlice.p, P, c->cam.W, c->cam.H, dStart.p, dCursor.p, c->dSlicePixels.p);
     c->stats.kernelLaunches++;
     ALVRL_CUDA(cudaGetLastError());
     ALVRL_CUDA(cudaStreamSynchronize(c->stream));
