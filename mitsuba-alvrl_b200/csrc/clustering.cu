@@ -1114,7 +1114,7 @@ struct Workspace {
         ALVRL_CUDA(cudaMemGetInfo(&freeB, &totalB));
         for (Inst *in : which) {
             uint32_t key = 0, pos = 0;
-            if (in->done || in->nr > RF_MAXROWS || in->nr == 0 || !in->smp->counterState(key, pos)) continue;
+            if (in->done || in->nr > RF_MAXROWS_BIG || in->nr == 0 || !in->smp->counterState(key, pos)) continue;
             if (2 * (xFloats + (uint64_t) N * (in->nr + 4)) * sizeof(float) + (dev.size() + 1) * (uint64_t) N * 160 > freeB / 2) continue;   /* the two compacted copies would not fit */
             RfInst r; memset(&r, 0, sizeof(r));
             r.r0 = in->r0; r.nr = in->nr; r.lw = in->lw; r.listOff = in->listOff; r.cwOff = in->cwOff;
@@ -1277,8 +1277,8 @@ struct Workspace {
                              dev.size(), grid, (unsigned long long) splits, (unsigned long long) degenerate, (unsigned long long) resumed, Prof::now() - p0);
         if (prof.on) {
             uint32_t nrMax = 0; size_t skippedRows = 0;
-            for (Inst *in : which) { nrMax = std::max(nrMax, in->nr); if (in->nr > RF_MAXROWS) skippedRows++; }
-            fprintf(stderr, "[alvrl clustering]   objects %zu, %zu with more than %d rows (max %u)\n", which.size(), skippedRows, RF_MAXROWS, nrMax);
+            for (Inst *in : which) { nrMax = std::max(nrMax, in->nr); if (in->nr > RF_MAXROWS_BIG) skippedRows++; }
+            fprintf(stderr, "[alvrl clustering]   objects %zu, %zu with more than %d rows (max %u)\n", which.size(), skippedRows, RF_MAXROWS_BIG, nrMax);
             for (int k = 0; k < 2; k++)
                 fprintf(stderr, "[alvrl clustering]   %s splits %llu, Mcycles summed over CTAs: pick %.1f direction %.1f stage %.1f project %.1f sort %.1f weights %.1f sweep %.1f pairs %.1f argmin+queue %.1f\n",
                         k ? "large" : "small", clk[k][9], clk[k][0] * 1e-6, clk[k][1] * 1e-6, clk[k][2] * 1e-6, clk[k][3] * 1e-6, clk[k][4] * 1e-6, clk[k][5] * 1e-6, clk[k][6] * 1e-6,

@@ -32,7 +32,8 @@ namespace alvrl {
 
 #define RF_THREADS 512
 #define RF_WARPS (RF_THREADS / 32)
-#define RF_MAXROWS 512
+#define RF_MAXROWS 512              /* rows whose sweeps fit one pass (thread = 2 rows); gangs and resident tiles need this */
+#define RF_MAXROWS_BIG 4096         /* more rows than RF_MAXROWS: row-block passes in the sweeps, direction in the tile */
 #define RF_TILE_FLOATS 24576
 #define RF_HEAP_CAP 4096           /* queue entries kept in shared memory; deeper levels spill to global memory (SplitHeap) */
 #define RF_SMALL 1024
@@ -545,7 +546,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_refine_mt(float *XA, float *X
                 sm.mtClk[3]++;
                 /* a large cluster arrives as G identical, consecutive tickets: the CTAs that draw them form a gang.  Members are
                  * numbered in the order they arrive (node.pad[2]); the first one leads: its scratch arrays are the gang's */
-                const uint32_t G = rf_gang_size(sm.end - sm.begin, scr.gangMin, gangCap);
+                const uint32_t G = I->nr <= RF_MAXROWS ? rf_gang_size(sm.end - sm.begin, scr.gangMin, gangCap) : 1u;
                 uint32_t mi = 0, leader = blockIdx.x;
                 if (G > 1u) {
                     mi = atomicAdd(&nd->pad[2], 1u);
@@ -829,7 +830,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) k_refine_mt(float *XA, float *X
                     uint32_t *plain = reinterpret_cast<uint32_t *>(sm.chunkEnd), np = 0;   /* (scratch: the pick buffers are free in a control pass) */
                     for (uint32_t q = 0; q < sm.selCount; q++) {
                         const MtNode &sn = nodes[sm.sel[q]];
-                        const uint32_t G = rf_gang_size(sn.end - (sn.begin & 0x7fffffffu), scr.gangMin, gangCap);
+                        const uint32_t G = I->nr <= RF_MAXROWS ? rf_gang_size(sn.end - (sn.begin & 0x7fffffffu), scr.gangMin, gangCap) : 1u;
                         if (G > 1u) { uint32_t ids[RF_GANG_MAX]; for (uint32_t a = 0; a < G; a++) ids[a] = sm.sel[q]; mt_push(mp, 0u, o, ids, G); }
                         else plain[np++] = sm.sel[q];
                     }

@@ -109,16 +109,20 @@
             if (sm.flags & 2u) { if (tid == 0) sm.err = RF_ERR_WEIGHTS; break; }
             RF_TICK(0);
 
-            /* ---- direction (604-623) ---- */
-            for (uint32_t r = tid; r < nr; r += RF_THREADS) { sm.c1[r] = Xs[(size_t) idx[0] * nrP + r]; sm.c2[r] = Xs[(size_t) idx[1] * nrP + r]; }
+            /* ---- direction (604-623) ----  Objects of more than RF_MAXROWS rows keep the two centre columns and the direction in
+             * the tile (free until the projections stage columns into its first 64 KB; the direction sits behind that) */
+            const bool bigRows = nr > (uint32_t) RF_MAXROWS;
+            float *const c1p = bigRows ? sm.tile : sm.c1, *const c2p = bigRows ? sm.tile + RF_MAXROWS_BIG : sm.c2;
+            float *const sdirp = bigRows ? sm.tile + 2 * RF_THREADS * 16 : sm.sdir;
+            for (uint32_t r = tid; r < nr; r += RF_THREADS) { c1p[r] = Xs[(size_t) idx[0] * nrP + r]; c2p[r] = Xs[(size_t) idx[1] * nrP + r]; }
             __syncthreads();
-            if (tid == 0) { float a = 0; for (uint32_t r = 0; r < nr; r++) a += fabsf(sm.c1[r]) * fabsf(sm.c1[r]); sm.norm[0] = sqrtf(a); }
-            else if (tid == 32) { float a = 0; for (uint32_t r = 0; r < nr; r++) a += fabsf(sm.c2[r]) * fabsf(sm.c2[r]); sm.norm[1] = sqrtf(a); }
-            else if (tid == 64) { float a = 0; for (uint32_t r = 0; r < nr; r++) { const float d = sm.c2[r] - sm.c1[r]; a += fabsf(d) * fabsf(d); } sm.norm[2] = sqrtf(a); }
+            if (tid == 0) { float a = 0; for (uint32_t r = 0; r < nr; r++) a += fabsf(c1p[r]) * fabsf(c1p[r]); sm.norm[0] = sqrtf(a); }
+            else if (tid == 32) { float a = 0; for (uint32_t r = 0; r < nr; r++) a += fabsf(c2p[r]) * fabsf(c2p[r]); sm.norm[1] = sqrtf(a); }
+            else if (tid == 64) { float a = 0; for (uint32_t r = 0; r < nr; r++) { const float d = c2p[r] - c1p[r]; a += fabsf(d) * fabsf(d); } sm.norm[2] = sqrtf(a); }
             __syncthreads();
             if (sm.norm[0] != 0 && sm.norm[1] != 0 && sm.norm[2] != 0) {
                 const float dl = sm.norm[2];
-                for (uint32_t r = tid; r < nrP; r += RF_THREADS) sm.sdir[r] = r < nr ? (sm.c2[r] - sm.c1[r]) / dl : 0.0f;
+                for (uint32_t r = tid; r < nrP; r += RF_THREADS) sdirp[r] = r < nr ? (c2p[r] - c1p[r]) / dl : 0.0f;
             } else {
                 /* degenerate centres: direction uniform on the n-sphere, warp::squareToStdNormal(next2D()).x per row (616-622);
                  * log and cos evaluated in double and rounded (pinned transcendental, same on the host path and in the oracle) */
@@ -127,19 +131,19 @@
                     for (uint32_t r = tid; r < nr; r += RF_THREADS) {
                         const float s1 = alvrl_rng_uniform(nkey, base + 2 * r), s2 = alvrl_rng_uniform(nkey, base + 2 * r + 1);
                         const float rr = sqrtf(-2 * (float) log((double) (1 - s1))), phi = (float) (2 * M_PI * s2);
-                        sm.c1[r] = (float) cos((double) phi) * rr;
+                        c1p[r] = (float) cos((double) phi) * rr;
                     }
                     __syncthreads();
                     if (tid == 0) {
                         sm.nodePos = base + 2 * nr; sm.degenerate++;
-                        float a = 0; for (uint32_t r = 0; r < nr; r++) a += fabsf(sm.c1[r]) * fabsf(sm.c1[r]);
+                        float a = 0; for (uint32_t r = 0; r < nr; r++) a += fabsf(c1p[r]) * fabsf(c1p[r]);
                         sm.norm[2] = sqrtf(a);
                     }
                     __syncthreads();
                     if (sm.norm[2] != 0) break;
                 }
                 const float dl = sm.norm[2];
-                for (uint32_t r = tid; r < nrP; r += RF_THREADS) sm.sdir[r] = r < nr ? sm.c1[r] / dl : 0.0f;
+                for (uint32_t r = tid; r < nrP; r += RF_THREADS) sdirp[r] = r < nr ? c1p[r] / dl : 0.0f;
             }
             __syncthreads();
 
@@ -148,7 +152,7 @@
              *      whole chunk is in flight at once), then thread = column sums sequentially in fp32 in row order out of shared
              *      memory (the zero padding of columns and direction adds exact zeros).  A local matrix that fits the tile in one
              *      chunk stays there for the variance sweep. ---- */
-            const bool fits = n <= TV;
+            const bool fits = n <= TV && !bigRows;
             if (fits) {
                 for (uint32_t i = tid; i < n * nq; i += RF_THREADS) {
                     const uint32_t c = i / nq, q = i - c * nq;
@@ -184,7 +188,7 @@
 #pragma unroll 2
                         for (uint32_t q = 0; q < nq; q++) {
                             const float4 e = rf_div4(*reinterpret_cast<const float4 *>(x + 4 * (q ^ sw)), len, y, lenOk);   /* e / len */
-                            const float4 d = *reinterpret_cast<const float4 *>(sm.sdir + 4 * q);
+                            const float4 d = *reinterpret_cast<const float4 *>(sdirp + 4 * q);
                             pj += d.x * e.x; pj += d.y * e.y; pj += d.z * e.z; pj += d.w * e.w;
                         }
                     }
@@ -237,7 +241,7 @@
                             const uint32_t g0 = rb << 2, gcnt = min(4u, nq - g0);
                             for (uint32_t g = 0; g < gcnt; g++) {
                                 const float4 e = rf_div4(*reinterpret_cast<const float4 *>(x + 4u * (g ^ swz)), len, y, lenOk);   /* e / len */
-                                const float4 d = *reinterpret_cast<const float4 *>(sm.sdir + 4u * (g0 + g));
+                                const float4 d = *reinterpret_cast<const float4 *>(sdirp + 4u * (g0 + g));
                                 pj += d.x * e.x; pj += d.y * e.y; pj += d.z * e.z; pj += d.w * e.w;
                             }
                         }
@@ -363,7 +367,10 @@
                 double (*part)[32][8] = reinterpret_cast<double (*)[32][8]>(&sm.sw[0][0]) + half * 2;   /* [buffer][step][warp] */
                 /* steps per stage (>= 12 for nr <= 512); the step loop runs in groups of 16, so 17..31 steps would pay a
                  * second, mostly empty group per stage */
-                uint32_t KC = min(32u, (uint32_t) (RF_TILE_FLOATS / 4) / nrP);
+                /* more than RF_MAXROWS rows: the sweeps run once per block of 512 rows (B_k accumulates over the passes); a stage
+                 * then holds the row block's slice of each of its columns, one bulk copy per column */
+                const uint32_t colStride = bigRows ? 512u : nrP;
+                uint32_t KC = min(32u, (uint32_t) (RF_TILE_FLOATS / 4) / colStride);
                 if (KC > 16u && KC < 32u) KC = 16u;
                 float *ring = sm.tile + half * (RF_TILE_FLOATS / 2);
                 /* the steps of this gang member: [kBeg, kEnd) of the forward order and of the reverse order; the boundaries are
@@ -373,13 +380,17 @@
                 };
                 const uint32_t kBeg = gG > 1u ? gBound(gMi) : 0u, kEnd = gG > 1u ? gBound(gMi + 1u) : n;
                 const uint32_t nch = (kEnd - kBeg + KC - 1) / KC;
+                uint32_t rb0 = 0, rbFloats = nrP;                                       /* first row and padded row count of the current row block */
                 auto issue = [&](uint32_t c) {                                          /* the columns of chunk c -> ring stage c & 1 */
                     const uint32_t k0 = kBeg + c * KC, cnt = min(KC, kEnd - k0);
                     if (hr == 0) {
                         asm volatile("fence.proxy.async;" ::: "memory");
-                        const uint32_t bytes = cnt * nrP * (uint32_t) sizeof(float);
+                        const uint32_t bytes = cnt * rbFloats * (uint32_t) sizeof(float);
                         rf_mbar_expect_tx(&sm.mbar[half][c & 1u], bytes);
-                        rf_bulk_load(ring + (c & 1u) * KC * nrP, Xd + (size_t) (half ? n - k0 - cnt : k0) * nrP, bytes, &sm.mbar[half][c & 1u]);
+                        const float *src = Xd + (size_t) (half ? n - k0 - cnt : k0) * nrP + rb0;
+                        float *dst = ring + (c & 1u) * KC * colStride;
+                        if (!bigRows) rf_bulk_load(dst, src, bytes, &sm.mbar[half][c & 1u]);
+                        else for (uint32_t j = 0; j < cnt; j++) rf_bulk_load(dst + j * colStride, src + (size_t) j * nrP, rbFloats * (uint32_t) sizeof(float), &sm.mbar[half][c & 1u]);
                     }
                     if (!small && hr < cnt) {                                           /* w_k, W_{k-1} live in global memory */
                         const uint32_t k = k0 + hr, sp = half ? n - 1 - k : k;
@@ -391,13 +402,16 @@
                 /* thread = rows hr and hr + RS (nr <= 512): the rows are folded onto the fewest warps, RS = roundup(nr / 2, 32),
                  * so that both row slots of a thread carry a row -- the sweep is issue-bound, and a warp whose second slot is
                  * empty costs as many issue slots as a full one */
-                const uint32_t RS = (scr.unfoldRows && nr <= 256u) ? ((nr + 31u) & ~31u) : min(256u, (((nr + 1u) >> 1) + 31u) & ~31u);
+                for (rb0 = 0; rb0 < (bigRows ? nr : 1u); rb0 += 512u) {
+                const uint32_t nrB = bigRows ? min(512u, nr - rb0) : nr;                /* rows of this pass (block-local indices below) */
+                rbFloats = bigRows ? ((nrB + 3u) & ~3u) : nrP;
+                const uint32_t RS = (scr.unfoldRows && nrB <= 256u) ? ((nrB + 31u) & ~31u) : min(256u, (((nrB + 1u) >> 1) + 31u) & ~31u);
                 const uint32_t rA = hr, rB = hr + RS;
-                const bool actA = hr < RS && rA < nr, actB = hr < RS && rB < nr;
+                const bool actA = hr < RS && rA < nrB, actB = hr < RS && rB < nrB;
                 const uint32_t nw = RS >> 5;
                 /* per-row locality weights (neighbour slices in L_i): B_k = sum_r w_r (..)^2 */
                 const bool rowWeighted = scr.rowW != nullptr;
-                const double wRowA = (rowWeighted && actA) ? scr.rowW[I->r0 + rA] : 1.0, wRowB = (rowWeighted && actB) ? scr.rowW[I->r0 + rB] : 1.0;
+                const double wRowA = (rowWeighted && actA) ? scr.rowW[I->r0 + rb0 + rA] : 1.0, wRowB = (rowWeighted && actB) ? scr.rowW[I->r0 + rb0 + rB] : 1.0;
                 double SA = 0, SB = 0;
                 const long long gs0_ = clock64();
                 if (gG > 1u) {
@@ -456,7 +470,7 @@
                         if (!small) asm volatile("bar.sync %0, 256;" ::"r"(1 + half) : "memory");
                     }
                     if (hw < nw) {
-                        const float *stage = ring + (c & 1u) * KC * nrP;
+                        const float *stage = ring + (c & 1u) * KC * colStride;
                         /* one group of 16 steps; the variants are compile-time so that the common case -- a full group -- carries no
                          * per-step predicates and each residency mode only its own addressing.  A resident column pc keeps element r
                          * at colp[r ^ ((pc & 7) << 2)]: the granule swizzle (r / 4) ^ (pc & 7) touches bits 2..4 of r only. */
@@ -474,7 +488,7 @@
                                         if (actA) xa[u] = colp[rA ^ swz];
                                         if (actB) xb[u] = colp[rB ^ swz];
                                     } else {
-                                        const float *colp = stage + (half ? cnt - 1 - (g + u) : g + u) * nrP;
+                                        const float *colp = stage + (half ? cnt - 1 - (g + u) : g + u) * colStride;
                                         if (actA) xa[u] = colp[rA];
                                         if (actB) xb[u] = colp[rB];
                                     }
@@ -508,11 +522,13 @@
                     if (hr < cnt) {
                         double sum = 0;
                         for (uint32_t w8 = 0; w8 < nw; w8++) sum += part[buf][hr][w8];
-                        Bh[k0 + hr] = sum;
+                        Bh[k0 + hr] = rb0 ? Bh[k0 + hr] + sum : sum;
                     }
                     buf ^= 1;
                 }
                 if (tid == 0 && gG > 1u) sm.mtClk[7] += (unsigned long long) (clock64() - gs1_);
+                asm volatile("bar.sync %0, 256;" ::"r"(1 + half) : "memory");       /* the ring is free for the next row block */
+                }                                                                       /* row blocks */
             }
             RF_GANG_SYNC();
             RF_TICK(6);

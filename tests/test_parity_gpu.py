@@ -298,6 +298,23 @@ def test_clusters_large_splits_all_device_paths(pkg, orc, monkeypatch, path):
     _clusters_equal(g.clusters(), _LARGE["clusters"], path)
 
 
+def test_clusters_objects_of_more_than_512_rows(pkg, orc):
+    """local matrices of ~1 400 and ~2 000 rows (every pixel a representative, few slices): the device-resident refinement
+    runs its variance sweeps in passes over blocks of 512 rows and keeps the split direction in the tile; clusters identical to
+    the oracle's, with and without neighbour rows"""
+    for kw in (dict(targetNumSlices=3), dict(targetNumSlices=2, neighbourCount=1, neighbourWeight=0.3)):
+        g, o = _pair(pkg, orc, "C1", 64, 64, 600, seed=17, targetPixelUndersampling=1.0, **kw)
+        for it in (g, o):
+            it.build_slices(); it.sample_slice_mapping()
+        off, _ = o.rep_pixels()
+        assert np.diff(off).max() > 1024
+        o.build_R()
+        g.set_R(o.get_R())
+        o.build_clusters(); g.build_clusters()
+        print("rows per slice", np.diff(off), "oracle splits", o.cluster_diag())
+        _clusters_equal(g.clusters(), o.clusters(), str(kw))
+
+
 def test_clusters_identical_sfmt_stream(pkg, orc):
     for w in (1, 3):
         g, o = _pair(pkg, orc, "C1", 48, 48, 120, seed=6, rngMode=1, workerCount=w, targetNumSlices=24)
