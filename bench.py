@@ -85,6 +85,9 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the bounded cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=1, help="steps of the end-to-end leg for the configs other than C2")
+    ap.add_argument("--slice-range", type=int, nargs=2, default=None, metavar=("BEGIN", "END"),
+                    help="1 GPU, configs other than C2: a frame covers only these slice ids (R rows, clusters and pixels of those "
+                         "slices, full-size scene / grid / BVH / VRL set) -- the bounded form of a config whose whole frame takes minutes")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity sample (rank 0, N=1 only)")
     ap.add_argument("--no-strict", action="store_true", help="skip the extra frame in the strict math flavour")
     ap.add_argument("--parity-seconds", type=float, default=8.0, help="target CPU time of the parity sample")
@@ -107,6 +110,9 @@ def workload(pkg, a):
                         f"volVolSamples={params['volVolSamples']}, volSurfSamples={params['volSurfSamples']}",
             "slices": params.get("targetNumSlices", 100), "pixel_undersampling": 64,
             "l2_note": f"inputs larger than L2: R alone is rows x VRLs x 8 B ({W * H / 64 * len(vrls[0]) * 8 / 1e9:.1f} GB) and is rewritten every step"}
+    if a.slice_range:
+        desc["slice_range"] = list(a.slice_range)
+        desc["workload"] += f", slices [{a.slice_range[0]}, {a.slice_range[1]}) of {desc['slices']} only"
     return scene, vrls, params, desc, hg
 
 
@@ -266,7 +272,14 @@ def run_ours(a):
         s0 = g.stats()
         if e2e:
             g.set_vrls(*vrls)                                    # host -> device: the step's input (VRL set)
-        img = group.frame(want_image=e2e and rank == 0)          # e2e: device -> host read of the step's result on rank 0
+        if a.slice_range:                                        # bounded form: the same calls alvrl_group_frame makes, on a sub-range
+            g.build_slices(); g.set_slice_range(*a.slice_range); g.sample_slice_mapping(); g.build_R(); g.set_column_nonzero(None)
+            g.build_clusters()
+            img = g.render()                                     # the image comes back to the host in both legs (W x H x 3 floats)
+            if not e2e:
+                img = None
+        else:
+            img = group.frame(want_image=e2e and rank == 0)      # e2e: device -> host read of the step's result on rank 0
         if img is not None:
             host_img = img
         s1 = g.stats()

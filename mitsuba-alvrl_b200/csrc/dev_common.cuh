@@ -215,6 +215,57 @@ __device__ __forceinline__ bool bvh_occluded_fast(const SceneDev &sc, const F3 &
     }
 }
 
+/*
+ * The same query, called by ALL 32 lanes of a warp together (need = false: this lane has no ray).  The per-lane loop above
+ * leaves the reconvergence of lanes that left the node search for a leaf to the hardware scheduler, and on a large tree
+ * (C4: 1.2 M nodes, ~80 node visits per ray) the warp falls apart into single lanes: ncu counted 1.8 active lanes per
+ * instruction in that loop (profiles/r2_c4_bvh_v0.txt).  Here both loops are controlled by warp votes, so every branch
+ * that depends on a lane is a short forward `if`: lanes search for their next leaf together (a lane that found one, or
+ * finished, idles until the vote ends the search), then test the triangles of their leaves together.
+ */
+__device__ __forceinline__ bool bvh_occluded_fast_warp(const SceneDev &sc, const F3 &o, const F3 &d, float mint, float maxt, bool need) {
+    const F3 inv = f3(__frcp_rn(d.x), __frcp_rn(d.y), __frcp_rn(d.z));
+    const F3 oi = f3(-o.x * inv.x, -o.y * inv.y, -o.z * inv.z);
+    const float lo_t = mint, hi_t = maxt * 1.00001f;
+    const uint32_t numNodes = sc.numNodes;
+    uint32_t node = (need && maxt > mint) ? 0u : numNodes;
+    bool hit = false;
+    __syncwarp();
+    while (__any_sync(0xffffffffu, node < numNodes)) {
+        uint32_t leaf = 0;
+        while (__any_sync(0xffffffffu, node < numNodes && !leaf)) {
+            if (node < numNodes && !leaf) {
+                const float4 lo = __ldg(&sc.nodes[node].lo), hi = __ldg(&sc.nodes[node].hi);
+                const float tx1 = fmaf(lo.x, inv.x, oi.x), tx2 = fmaf(hi.x, inv.x, oi.x);
+                const float ty1 = fmaf(lo.y, inv.y, oi.y), ty2 = fmaf(hi.y, inv.y, oi.y);
+                const float tz1 = fmaf(lo.z, inv.z, oi.z), tz2 = fmaf(hi.z, inv.z, oi.z);
+                const float tn = fmaxf(fmaxf(fminf(tx1, tx2), fminf(ty1, ty2)), fmaxf(fminf(tz1, tz2), lo_t));
+                const float tf = fminf(fminf(fmaxf(tx1, tx2), fmaxf(ty1, ty2)), fminf(fmaxf(tz1, tz2), hi_t));
+                const uint32_t esc = __float_as_uint(lo.w), lf = __float_as_uint(hi.w);
+                const bool in = tn <= tf;
+                leaf = in ? lf : 0u;
+                node = (in && !lf) ? node + 1u : esc;
+            }
+        }
+        if (leaf) {
+            const uint32_t first = leaf >> 4, cnt = leaf & 15u;
+            for (uint32_t i = 0; i < cnt; i++) {
+                const float4 p = __ldg(&sc.trisFast[first + i].p);
+                const float den = p.x * d.x + p.y * d.y + p.z * d.z;
+                const float num = p.w - (p.x * o.x + p.y * o.y + p.z * o.z);
+                const float t = __fdividef(num, den);
+                if (!(t >= mint && t <= maxt)) continue;
+                const float4 q = __ldg(&sc.trisFast[first + i].q), r = __ldg(&sc.trisFast[first + i].r);
+                const F3 P = f3(fmaf(t, d.x, o.x), fmaf(t, d.y, o.y), fmaf(t, d.z, o.z));
+                const float u = q.x * P.x + q.y * P.y + q.z * P.z + q.w;
+                const float v = r.x * P.x + r.y * P.y + r.z * P.z + r.w;
+                if (u >= 0.0f && v >= 0.0f && u + v <= 1.0f) { hit = true; node = numNodes; break; }
+            }
+        }
+    }
+    return hit;
+}
+
 /* ---- media (exact flavour: used by the primary kernel and the strict transport flavour) ---------- */
 __device__ __forceinline__ float exp_ref(float x) { return (float) exp((double) x); }   /* math::fastexp, math.h:185-187 */
 
@@ -256,11 +307,15 @@ __device__ __forceinline__ float grid_optical_depth(const MediumDev &m, const F3
     const float stepSz = xdiv(length, (float) nSteps);
     const F3 inc = xscale(d, stepSz);
     float integrated = xadd(grid_lookup(m, p), grid_lookup(m, pLast));
+    /* HETVOL_EARLY_EXIT (heterogeneous.cpp:31, 336-340, 353-360): past -log(Epsilon) of optical depth the march stops with an
+     * infinite optical depth (transmittance exactly 0); -(float) log((double) 1e-4f) = 9.21034f */
+    const float stopValue = xdiv(xmul(9.21034049987793f, 3.0f), xmul(stepSz, m.scale));
     p = xadd3(p, inc);
     float mm = 4;
     for (uint32_t i = 1; i < nSteps; ++i) {
         integrated = xadd(integrated, xmul(mm, grid_lookup(m, p)));
         mm = 6 - mm;
+        if (integrated > stopValue) return INFINITY;
         F3 next = xadd3(p, inc);
         if (p.x == next.x && p.y == next.y && p.z == next.z) break;
         p = next;

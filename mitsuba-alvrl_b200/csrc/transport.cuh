@@ -472,8 +472,8 @@ __global__ void __launch_bounds__(ALVRL_CTA_SEGS, ALVRL_MIN_CTAS) ALVRL_NAME(k_b
                 float mean = 0, var = 0;
                 const uint32_t v = v0 + j;
 #if defined(ALVRL_FAST) && !defined(ALVRL_DIAG_GENERIC)
-                if constexpr (MED != 1) {
-                    /* every lane of the warp takes part (the shadow rays of a warp are traced from a shared pool) */
+                {
+                    /* every lane of the warp takes part: the visibility queries and the grid marches are warp-collective */
                     const VrlRec &vr = sm.tile[t & 1][j];
                     Rng rng;
                     rng.tape = P.tape ? P.tape + ((size_t) (P.rowBase + row) * N + v) * P.tapeK : nullptr;
@@ -482,11 +482,12 @@ __global__ void __launch_bounds__(ALVRL_CTA_SEGS, ALVRL_MIN_CTAS) ALVRL_NAME(k_b
                     float rgb[3], m, s2;
                     PairCull cull; cull.boxVV = cull.boxVS = cull.planes = 0xffffffffu;
                     if (SMALL == 2) cull = pair_cull(P.occ, sides, vr.dir, vr.power);
-                    integrate_pair_fast<MED, false, true, SMALL>(P, &sbvh, seg, vr.s, vr.e, vr.dir, vr.power, rng, rgb, m, s2, active && scattering, cull);
+                    if constexpr (MED == 1) integrate_pair_grid_fast<false, true, SMALL>(P, &sbvh, seg, vr.s, vr.e, vr.dir, vr.power, rng, rgb, m, s2, active && scattering, cull);
+                    else integrate_pair_fast<MED, false, true, SMALL>(P, &sbvh, seg, vr.s, vr.e, vr.dir, vr.power, rng, rgb, m, s2, active && scattering, cull);
                     mean = m * P.normalization;
                     var = s2 * P.normalization * P.normalization;
-                } else
-#endif
+                }
+#else
                 if (active && scattering) {
                     const VrlRec &vr = sm.tile[t & 1][j];
                     Rng rng;
@@ -498,6 +499,7 @@ __global__ void __launch_bounds__(ALVRL_CTA_SEGS, ALVRL_MIN_CTAS) ALVRL_NAME(k_b
                     mean = m * P.normalization;                              /* vrlIntegrator.cpp:812-813 */
                     var = s2 * P.normalization * P.normalization;
                 }
+#endif
                 if (row < numRows) R[(size_t) v * ldR + row] = make_float2(mean, var);   /* lanes = consecutive rows: coalesced */
             }
         }
@@ -571,14 +573,16 @@ __global__ void __launch_bounds__(ALVRL_CTA_SEGS, ALVRL_MIN_CTAS) ALVRL_NAME(k_r
                 rng.key = alvrl_rng_key(P.seed, ALVRL_RNG_RENDER, pixel, v0 + j - vBegin);
                 rng.k = 0;
                 float rgb[3] = {0, 0, 0}, m, s2;
-#ifdef ALVRL_FAST
-                if constexpr (MED != 1) {
+#if defined(ALVRL_FAST) && !defined(ALVRL_DIAG_GENERIC)
+                {
                     PairCull cull; cull.boxVV = cull.boxVS = cull.planes = 0xffffffffu;
                     if (SMALL == 2) cull = pair_cull(P.occ, sides, vr.dir, vr.power);
-                    integrate_pair_fast<MED, true, false, SMALL>(P, &sbvh, seg, vr.s, vr.e, vr.dir, vr.power, rng, rgb, m, s2, active && scattering, cull);
-                } else
-#endif
+                    if constexpr (MED == 1) integrate_pair_grid_fast<true, false, SMALL>(P, &sbvh, seg, vr.s, vr.e, vr.dir, vr.power, rng, rgb, m, s2, active && scattering, cull);
+                    else integrate_pair_fast<MED, true, false, SMALL>(P, &sbvh, seg, vr.s, vr.e, vr.dir, vr.power, rng, rgb, m, s2, active && scattering, cull);
+                }
+#else
                 if (active && scattering) integrate_pair<(MED == 2 ? 0 : MED), true, false>(P, seg, vr.s, vr.e, vr.dir, vr.power, rng, rgb, m, s2);
+#endif
                 if (CLUSTERED) {                                             /* 587-589: Li += weight_k * integrateVRL */
                     const float w = vr.e.w;
                     Li[0] += w * rgb[0]; Li[1] += w * rgb[1]; Li[2] += w * rgb[2];

@@ -122,8 +122,7 @@ __device__ __forceinline__ bool occluded_fast(const TransportParams &P, const Bv
     const float mint = onSurf ? ALVRL_EPSILON * fmaxf(fmaxf(fabsf(p1.x), fabsf(p1.y)), fabsf(p1.z)) : 0.0f;
     if (SMALL == 2) return occ_query(P.occ, sb->tris, p1.x, p1.y, p1.z, dir.x, dir.y, dir.z, mint, remaining, need, boxActive, planeActive);
     if (SMALL == 1) return occluded_flat(*sb, P.scene.numLeaves, p1, dir, mint, remaining, need);
-    if (!need || !(remaining > mint)) return false;
-    return bvh_occluded_fast(P.scene, p1, dir, mint, remaining);
+    return bvh_occluded_fast_warp(P.scene, p1, dir, mint, remaining, need);      /* all lanes of the warp call this together */
 }
 
 /* diagnostic variants (tools/build_variant.sh -DALVRL_DIAG_*): accurate library functions in place of the MUFU forms, to
@@ -298,8 +297,8 @@ __device__ __forceinline__ void integrate_pair_fast(const TransportParams &P, co
         const bool surf = laneOn && !(tE0 == 0 && tE1 == 0 && tE2 == 0) && (flags & SEG_SMOOTH);
         float mean = 0, M2 = 0;
         /* lanes without a vol->surf term (727) still walk the loop -- drawing nothing, contributing nothing -- so that the
-         * warp stays converged through the flat visibility sweep */
-        if (SMALL ? __any_sync(0xffffffffu, surf) : surf) {
+         * warp stays converged through the visibility queries (every strategy is called by the 32 lanes together) */
+        if (__any_sync(0xffffffffu, surf)) {
             /* per-pair part of KullaSampling(A = S, B = End, D = Usurf) */
             const float dotPr = dot(SV, Usurf - S);
             const F3 I = S + dotPr * SV;
@@ -357,3 +356,5 @@ __device__ __forceinline__ void integrate_pair_fast(const TransportParams &P, co
         if (WANT_STAT) { outMean += mean; outVar += f_div(M2, (float) ((Nvs - 1) * Nvs)); }
     }
 }
+
+#include "transport_grid_fast.cuh"

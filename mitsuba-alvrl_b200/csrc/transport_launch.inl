@@ -33,7 +33,7 @@ void ALVRL_NAME(launch_build_R)(const TransportParams &P, const SegRec *rowSegs,
     dim3 grid(rowBlocks, chunks);
 #ifdef ALVRL_FAST
     const int vis = P.scene.visMode;
-    if (P.medium.type == 1) ALVRL_GO_R(1, 0);
+    if (P.medium.type == 1) { if (vis == 2) ALVRL_GO_R(1, 2); else if (vis == 1) ALVRL_GO_R(1, 1); else ALVRL_GO_R(1, 0); }
     else if (P.medium.grey) { if (vis == 2) ALVRL_GO_R(2, 2); else if (vis == 1) ALVRL_GO_R(2, 1); else ALVRL_GO_R(2, 0); }
     else { if (vis == 2) ALVRL_GO_R(0, 2); else if (vis == 1) ALVRL_GO_R(0, 1); else ALVRL_GO_R(0, 0); }
 #else
@@ -62,7 +62,7 @@ void ALVRL_NAME(launch_render)(const TransportParams &P, bool clustered, const S
     } while (0)
 #ifdef ALVRL_FAST
     const int vis = P.scene.visMode;
-    if (P.medium.type == 1) ALVRL_LAUNCH_RENDER(1, 0);
+    if (P.medium.type == 1) { if (vis == 2) ALVRL_LAUNCH_RENDER(1, 2); else if (vis == 1) ALVRL_LAUNCH_RENDER(1, 1); else ALVRL_LAUNCH_RENDER(1, 0); }
     else if (P.medium.grey) { if (vis == 2) ALVRL_LAUNCH_RENDER(2, 2); else if (vis == 1) ALVRL_LAUNCH_RENDER(2, 1); else ALVRL_LAUNCH_RENDER(2, 0); }
     else { if (vis == 2) ALVRL_LAUNCH_RENDER(0, 2); else if (vis == 1) ALVRL_LAUNCH_RENDER(0, 1); else ALVRL_LAUNCH_RENDER(0, 0); }
 #else

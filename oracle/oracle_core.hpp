@@ -551,11 +551,16 @@ struct Medium {
         const Float stepSz = length / nSteps;
         const V3 increment = ray.d * stepSz;
         Float integratedDensity = lookupDensity(p) + lookupDensity(pLast);
+        /* HETVOL_EARLY_EXIT is defined (heterogeneous.cpp:31, 336-340, 353-360): once the running Simpson sum passes
+         * -log(Epsilon) of optical depth the march stops and the optical depth is +infinity (transmittance exactly 0) */
+        const Float stopAfterDensity = -(Float) ::log((double) Epsilon);      // math::fastlog, math.h:193-195
+        const Float stopValue = stopAfterDensity * 3.0f / (stepSz * scale);
         p = p + increment;
         Float m = 4;
         for (uint32_t i = 1; i < nSteps; ++i) {
             integratedDensity += m * lookupDensity(p);
             m = 6 - m;
+            if (integratedDensity > stopValue) return std::numeric_limits<Float>::infinity();
             V3 next = p + increment;
             if (p.x == next.x && p.y == next.y && p.z == next.z) break;
             p = next;
