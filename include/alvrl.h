@@ -33,6 +33,13 @@ extern "C" {
 
 /* BSDF type bits the path needs (include/mitsuba/render/bsdf.h:230-284) */
 #define ALVRL_BSDF_SMOOTH 1u            /* diffuse reflectance: ESmooth */
+/* delta BSDFs of the specular chains (vrlIntegrator.cpp:445-511) and the media on the two sides of a surface */
+#define ALVRL_BSDF_DIELECTRIC 2u        /* smooth dielectric: EDeltaReflection | EDeltaTransmission (src/bsdfs/dielectric.cpp) */
+#define ALVRL_BSDF_CONDUCTOR  4u        /* smooth conductor: EDeltaReflection (src/bsdfs/conductor.cpp) */
+#define ALVRL_BSDF_DELTA (ALVRL_BSDF_DIELECTRIC | ALVRL_BSDF_CONDUCTOR)
+#define ALVRL_MAT_TRANSITION      8u    /* the shape has an interior or exterior medium (Shape::isMediumTransition) */
+#define ALVRL_MAT_INTERIOR_MEDIUM 16u   /* ... its interior medium is the scene's medium (else vacuum) */
+#define ALVRL_MAT_EXTERIOR_MEDIUM 32u   /* ... its exterior medium is the scene's medium (else vacuum) */
 
 #define ALVRL_PHASE_ISOTROPIC 0         /* src/phase/isotropic.cpp:76-78 */
 #define ALVRL_PHASE_HG        1         /* src/phase/hg.cpp:107-110      */
@@ -110,6 +117,18 @@ int alvrl_set_mesh(alvrl_handle h, const float *verts_xyz, uint32_t nverts,
                    const uint32_t *tris, uint32_t ntris, const uint32_t *tri_material);
 /* Diffuse reflectance + type bits per material (src/bsdfs/diffuse.cpp:110-118). */
 int alvrl_set_materials(alvrl_handle h, const float *albedo_rgb, const uint32_t *type_bits, uint32_t nmat);
+/* Optics of the delta BSDFs (ALVRL_BSDF_DIELECTRIC / ALVRL_BSDF_CONDUCTOR), 12 floats per material: dielectric eta =
+ * intIOR / extIOR in [0] (dielectric.cpp:172-189); conductor eta rgb in [0..2] and k rgb in [3..5] (conductor.cpp:199-215);
+ * specularReflectance rgb in [6..8], specularTransmittance rgb in [9..11].  With such materials in the scene every camera
+ * segment grows the specular chain of LiInternal (vrlIntegrator.cpp:445-511): one segment per delta component that survives
+ * the Russian roulette, recursively, each with its weight, all looked up in the slice of the ORIGINAL camera ray.  The rows
+ * of R (getLiLuminanceVrlContributions, 514-526) and the render pass sum over a pixel's chain.  Call after
+ * alvrl_set_materials.  Chains are cut after 30 bounces (the reference only forces roulette from specularForcedRRdepth on). */
+int alvrl_set_material_optics(alvrl_handle h, const float *optics12, uint32_t nmat);
+/* Introspection (tests): the chain segments beyond the camera segment, grouped by pixel.  offset: P + 1 entries; segs: 16
+ * floats per segment {o.xyz, d.xyz, p.xyz, dist, weight.rgb, in-medium flag, path code, material}.  Pass segs = NULL to
+ * get the offsets (and through offset[P] the total) first. */
+int alvrl_get_chain_segments(alvrl_handle h, uint32_t *offset, float *segs);
 /* Extra points to union into Scene::getAABB() (sensor/emitter boxes, scene.cpp:387-413). */
 int alvrl_set_extra_bounds(alvrl_handle h, const float *points_xyz, uint32_t npoints);
 /* HomogeneousMedium (src/medium/homogeneous.cpp:156-184,354-396); samplingWeight < 0 => reference default. */
@@ -159,6 +178,24 @@ int alvrl_prepass(alvrl_handle h);
 int alvrl_render(alvrl_handle h, float *rgb_host);
 /* Unclustered render (globalCluster = localRefinement = false): getVRLContributions over all VRLs. */
 int alvrl_render_unclustered(alvrl_handle h, float *rgb_host);
+/* ---- film: the step after the path -------------------------------------------------------------------
+ * Reconstruction-filter splat and pass accumulation: ImageBlock::put (include/mitsuba/render/imageblock.h:124-202) with
+ * the pre-rasterised filter of ReconstructionFilter::configure / evalDiscretized (src/libcore/rfilter.cpp:37-55,
+ * include/mitsuba/core/rfilter.h:76-77), channels {rgb, alpha, weight}, and the division by the weight channel when the
+ * film is developed (src/libcore/bitmap.cpp:1617-1624).  One sample per pixel centre and pass.
+ *   filter: ALVRL_FILTER_BOX (param = radius, default 0.5; src/rfilters/box.cpp:38,46-48), ALVRL_FILTER_TENT (radius 1,
+ *   src/rfilters/tent.cpp:34,42-44), ALVRL_FILTER_GAUSSIAN (param = stddev, default 0.5, radius 4 stddev; the scene
+ *   default, src/rfilters/gaussian.cpp:30-58).  param <= 0 selects the default.
+ * alvrl_film_configure clears the film; alvrl_film_put adds one pass -- rgb_host (W*H*3, [y][x][c]) or, with NULL, the frame
+ * the last alvrl_render left on the device; alvrl_film_develop returns the normalised image. */
+#define ALVRL_FILTER_BOX 0
+#define ALVRL_FILTER_TENT 1
+#define ALVRL_FILTER_GAUSSIAN 2
+int alvrl_film_configure(alvrl_handle h, int filter, float param);
+int alvrl_film_clear(alvrl_handle h);
+int alvrl_film_put(alvrl_handle h, const float *rgb_host);
+int alvrl_film_develop(alvrl_handle h, float *rgb_host);
+
 /* Device variants for multi-GPU: only slices [sliceBegin, sliceEnd) are processed; the
  * framebuffer (W*H*4 floats, zero-initialised by the caller) lives in caller-owned device memory. */
 int alvrl_set_slice_range(alvrl_handle h, uint32_t sliceBegin, uint32_t sliceEnd);

@@ -130,6 +130,8 @@ class Integrator:
         """scene: dict from scenes.py (mesh, materials, medium, camera)."""
         self.set_mesh(scene["verts"], scene["tris"], scene["tri_material"])
         self.set_materials(scene["albedo"], scene["mat_bits"])
+        if scene.get("optics") is not None:
+            self.set_material_optics(scene["optics"])
         if scene.get("extra_bounds") is not None:
             eb = _f32(scene["extra_bounds"])
             self._call("set_extra_bounds", _p(eb), C.c_uint32(len(eb)))
@@ -151,6 +153,19 @@ class Integrator:
     def set_materials(self, albedo, bits):
         a, b = _f32(albedo), _u32(bits)
         self._call("set_materials", _p(a), _p(b), C.c_uint32(len(b)))
+
+    def set_material_optics(self, optics):
+        o = _f32(optics).reshape(-1, 12)
+        self._call("set_material_optics", _p(o), C.c_uint32(len(o)))
+
+    def chain_segments(self):
+        """(offset[P + 1], segs[total, 16]): the specular-chain segments below the camera segments, grouped by pixel"""
+        off = np.zeros(self.W * self.H + 1, np.uint32)
+        self._call("get_chain_segments", _p(off), None)
+        segs = np.zeros((int(off[-1]), 16), np.float32)
+        if len(segs):
+            self._call("get_chain_segments", _p(off), _p(segs))
+        return off, segs
 
     def set_medium_homogeneous(self, sigmaA, sigmaS, weight=-1.0, phase=PHASE_ISOTROPIC, g=0.0):
         a, s = _f32(sigmaA), _f32(sigmaS)
@@ -228,6 +243,26 @@ class Integrator:
     def render(self, clustered=True):
         out = np.zeros((self.H, self.W, 3), dtype=np.float32)
         self._call("render" if clustered else "render_unclustered", _p(out))
+        return out
+
+    # -- film (reconstruction-filter splat + pass accumulation, include/alvrl.h) -----------------------
+    def film_configure(self, filter, param=0.0):
+        self._call("film_configure", C.c_int(filter), C.c_float(param))
+
+    def film_clear(self):
+        self._call("film_clear")
+
+    def film_put(self, rgb=None):
+        if rgb is None:
+            self._call("film_put", None)
+        else:
+            a = np.ascontiguousarray(rgb, dtype=np.float32)
+            assert a.shape == (self.H, self.W, 3)
+            self._call("film_put", _p(a))
+
+    def film_develop(self):
+        out = np.zeros((self.H, self.W, 3), dtype=np.float32)
+        self._call("film_develop", _p(out))
         return out
 
     def set_slice_range(self, b, e):

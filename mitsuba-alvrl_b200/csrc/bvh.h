@@ -128,6 +128,58 @@ private:
     }
 };
 
+/*
+ * 4-wide tree for the fast flavour's any-hit query (types.h::Bvh4Node), collapsed from the binary tree: the two children of
+ * a node, then repeatedly the inner child with the largest surface area replaced by its own two children until four slots
+ * are taken.  Same leaves, same (padded) boxes, so the set of triangles a ray gets to test can only shrink to those whose
+ * leaf box it enters -- as in the binary tree.  Measured on C4 (998 k triangles, tools/micro/bvh_visits.cpp): 20.8 node visits
+ * per shadow ray instead of 81, 44 instead of 173 for the slowest ray of a warp.
+ */
+inline uint32_t collapse4(const HostBvh &b, std::vector<Bvh4Node> &out) {        /* returns the depth of the 4-wide tree */
+    out.clear();
+    if (b.nodes.empty()) return 0;
+    auto asU = [](float f) { uint32_t u; memcpy(&u, &f, 4); return u; };
+    auto area = [&](uint32_t k) { const BvhNode &n = b.nodes[k]; const float dx = n.hi.x - n.lo.x, dy = n.hi.y - n.lo.y, dz = n.hi.z - n.lo.z; return dx * dy + dy * dz + dz * dx; };
+    struct Item { uint32_t bin; uint32_t me; uint32_t depth; };
+    uint32_t maxDepth = 1, curDepth = 1;
+    std::vector<Item> todo;
+    auto emit = [&](const uint32_t *kids, int n, uint32_t me) {
+        Bvh4Node nd;
+        float lo[3][4], hi[3][4]; int ch[4];
+        for (int k = 0; k < 4; k++) { for (int c = 0; c < 3; c++) { lo[c][k] = INFINITY; hi[c][k] = -INFINITY; } ch[k] = (int) 0x80000000u; }
+        for (int k = 0; k < n; k++) {
+            const BvhNode &x = b.nodes[kids[k]];
+            lo[0][k] = x.lo.x; lo[1][k] = x.lo.y; lo[2][k] = x.lo.z; hi[0][k] = x.hi.x; hi[1][k] = x.hi.y; hi[2][k] = x.hi.z;
+            const uint32_t lf = asU(x.hi.w);
+            if (lf) ch[k] = ~(int) lf;
+            else { ch[k] = (int) out.size(); out.push_back(Bvh4Node()); todo.push_back({kids[k], (uint32_t) ch[k], curDepth + 1}); }
+        }
+        nd.lox = make_float4(lo[0][0], lo[0][1], lo[0][2], lo[0][3]); nd.loy = make_float4(lo[1][0], lo[1][1], lo[1][2], lo[1][3]);
+        nd.loz = make_float4(lo[2][0], lo[2][1], lo[2][2], lo[2][3]); nd.hix = make_float4(hi[0][0], hi[0][1], hi[0][2], hi[0][3]);
+        nd.hiy = make_float4(hi[1][0], hi[1][1], hi[1][2], hi[1][3]); nd.hiz = make_float4(hi[2][0], hi[2][1], hi[2][2], hi[2][3]);
+        nd.child = make_int4(ch[0], ch[1], ch[2], ch[3]); nd.pad = make_int4(0, 0, 0, 0);
+        out[me] = nd;
+    };
+    out.push_back(Bvh4Node());
+    if (asU(b.nodes[0].hi.w)) { const uint32_t k = 0; emit(&k, 1, 0); return 1; }   /* the root is a leaf */
+    todo.push_back({0, 0, 1});
+    while (!todo.empty()) {                                  /* breadth-first-ish: children of a node sit close together */
+        const Item it = todo.back(); todo.pop_back();
+        curDepth = it.depth; maxDepth = std::max(maxDepth, curDepth);
+        uint32_t kids[4]; int n = 2;
+        kids[0] = it.bin + 1; kids[1] = asU(b.nodes[it.bin + 1].lo.w);           /* second child = the first one's escape index */
+        while (n < 4) {
+            int best = -1; float ba = -1;
+            for (int k = 0; k < n; k++) if (!asU(b.nodes[kids[k]].hi.w) && area(kids[k]) > ba) { ba = area(kids[k]); best = k; }
+            if (best < 0) break;
+            const uint32_t x = kids[best];
+            kids[best] = x + 1; kids[n++] = asU(b.nodes[x + 1].lo.w);
+        }
+        emit(kids, n, it.me);
+    }
+    return maxDepth;
+}
+
 /* Wald TriAccel precomputation, include/mitsuba/render/triaccel.h:61-95 (IEEE fp32, same operation order) */
 inline TriRec makeTriRec(const float *A, const float *B, const float *C, uint32_t origIndex) {
     static const int waldModulo[4] = {1, 2, 0, 1};

@@ -113,6 +113,17 @@ void ensure_scene(alvrl_ctx *c) {
         }
     }
     if (visEnv && !strcmp(visEnv, "tree")) s.visMode = 0;
+    s.nodes4 = nullptr; s.numNodes4 = 0;
+    if (s.visMode == 0) {                                    /* large scenes: 4-wide tree for the fast flavour's any-hit query */
+        std::vector<Bvh4Node> n4;
+        const uint32_t depth = collapse4(bvh, n4);
+        /* a lane's stack holds at most three pending siblings per level (dev_common.cuh::ALVRL_BVH4_STACK = 64); a deeper tree
+         * keeps the binary skip-pointer query, which needs no stack */
+        if (3 * depth + 4 <= 64 && !getenv("ALVRL_NO_BVH4")) {
+            c->dNodes4.upload(n4, c->stream);
+            s.nodes4 = c->dNodes4.p; s.numNodes4 = (uint32_t) n4.size();
+        }
+    }
     c->occHost.cullMargin = 1e-5f * std::max(mx[0] - mn[0], std::max(mx[1] - mn[1], mx[2] - mn[2]));
     if (getenv("ALVRL_NO_PAIR_CULL")) c->occHost.cullMargin = INFINITY;      /* experiments: nothing is ever "strictly beyond" */
     c->vrlSidesValid = false;
@@ -146,7 +157,48 @@ void ensure_primary(alvrl_ctx *c) {
     c->stats.kernelLaunches++;
     ALVRL_CUDA(cudaGetLastError());
     ALVRL_CUDA(cudaStreamSynchronize(c->stream));
-    c->havePrimary = true; c->segsDirty = false;
+    c->havePrimary = true; c->segsDirty = false; c->chainsValid = false;
+}
+
+/* the specular chains below the camera segments (chain.cu): count, scan, write; host mirrors of the grouping */
+void ensure_chains(alvrl_ctx *c) {
+    ensure_primary(c);
+    if (c->chainsValid) return;
+    const uint32_t P = c->numPixels();
+    c->anyDelta = false;
+    for (uint32_t b : c->matBits) if (b & ALVRL_BSDF_DELTA) c->anyDelta = true;
+    c->chainOffset.assign(P + 1, 0u); c->chainMeta.clear();
+    if (c->anyDelta) {
+        if (c->optics.size() != 12 * c->matBits.size()) throw Error(ALVRL_ERR_STATE, "materials with delta components need alvrl_set_material_optics");
+        DevBuf<uint32_t> dCount; dCount.alloc(P);
+        launch_chain_count(c->sceneDev, c->medium, c->haveMedium, c->dTriVerts.p, c->dTriMat.p, c->dMatAlbedo.p, c->dMatBits.p, c->dMatOptics.p, c->P.seed,
+                           c->P.specularForcedRRdepth, c->P.initialSpecularThroughput, c->dPixSegs.p, c->dHitPrim.p, c->dHitT.p, P, dCount.p, c->stream);
+        c->stats.kernelLaunches++;
+        ALVRL_CUDA(cudaGetLastError());
+        std::vector<uint32_t> cnt(P);
+        dCount.download(cnt.data(), P, c->stream);
+        for (uint32_t i = 0; i < P; i++) c->chainOffset[i + 1] = c->chainOffset[i] + cnt[i];
+        const uint32_t total = c->chainOffset[P];
+        if (total) {
+            DevBuf<uint32_t> dOff; dOff.upload(c->chainOffset, c->stream);
+            c->dChainSegs.alloc(total); c->dChainMeta.alloc(total);
+            launch_chain_write(c->sceneDev, c->medium, c->haveMedium, c->dTriVerts.p, c->dTriMat.p, c->dMatAlbedo.p, c->dMatBits.p, c->dMatOptics.p, c->P.seed,
+                               c->P.specularForcedRRdepth, c->P.initialSpecularThroughput, c->dPixSegs.p, c->dHitPrim.p, c->dHitT.p, P, dOff.p,
+                               c->dChainSegs.p, c->dChainMeta.p, c->stream);
+            c->stats.kernelLaunches++;
+            ALVRL_CUDA(cudaGetLastError());
+            c->chainMeta.resize(total);
+            c->dChainMeta.download(c->chainMeta.data(), total, c->stream);
+            std::vector<uint32_t> key(total);
+            for (uint32_t e = 0; e < total; e++) {
+                if (c->chainMeta[e].x >= (1u << 24) || c->chainMeta[e].y >= 255u) throw Error(ALVRL_ERR_UNSUPPORTED, "specular chains: more than 2^24 pixels or 254 segments below one pixel");
+                key[e] = c->chainMeta[e].x + ((c->chainMeta[e].y + 1u) << 24);
+            }
+            c->dChainKey.upload(key, c->stream);
+            ALVRL_CUDA(cudaStreamSynchronize(c->stream));
+        }
+    }
+    c->chainsValid = true;
 }
 
 void invalidate_from_slices(alvrl_ctx *c) { c->pixelListsDirty = true; c->haveRows = false; c->haveR = false; c->haveClusters = false; c->haveFallback = false; c->renderListsDirty = true; }
@@ -287,6 +339,45 @@ void render_clustered_into(alvrl_ctx *c, float4 *fb, cudaStream_t st) {
     uint64_t pairs = 0;
     const uint32_t S = c->numSlices(), sb = std::min(c->sliceBegin, S), se = std::min(c->sliceEnd, S);
     for (uint32_t s = sb; s < se; s++) pairs += (uint64_t) c->sliceSize[s] * c->selectedVrls[s].size();
+    /* LiSpec (462-505): the in-medium segments of the pixels' specular chains, rendered from their own list with the
+     * representatives of the slice of the ORIGINAL camera ray (552-566), then added to their pixel, weighted, in chain order */
+    ensure_chains(c);
+    if (c->anyDelta && c->chainOffset.back()) {
+        std::vector<uint32_t> pts(c->numPixels());
+        c->dPixelToSlice.download(pts.data(), pts.size(), st);
+        std::vector<std::vector<uint32_t>> bySlice(S);
+        std::vector<uint32_t> xPix;
+        const uint32_t total = c->chainOffset.back();
+        for (uint32_t pix = 0; pix < c->numPixels(); pix++) {
+            const uint32_t a = c->chainOffset[pix], b = c->chainOffset[pix + 1], sl = pts[pix];
+            if (a == b || sl == ALVRL_NO_SLICE || sl < sb || sl >= se) continue;
+            bool any = false;
+            for (uint32_t e = a; e < b; e++) if (c->chainMeta[e].w & 1u) { bySlice[sl].push_back(e); any = true; }
+            if (any) xPix.push_back(pix);
+        }
+        std::vector<uint32_t> list; std::vector<uint4> xwork;
+        for (uint32_t s = sb; s < se; s++) {
+            const uint32_t base = (uint32_t) list.size(), cnt = (uint32_t) bySlice[s].size();
+            list.insert(list.end(), bySlice[s].begin(), bySlice[s].end());
+            for (uint32_t o = 0; o < cnt; o += ALVRL_CTA_SEGS_HOST) xwork.push_back(make_uint4(s, base + o, std::min<uint32_t>(ALVRL_CTA_SEGS_HOST, cnt - o), 0));
+            pairs += (uint64_t) cnt * c->selectedVrls[s].size();
+        }
+        if (!list.empty()) {
+            c->dXList.upload(list, st); c->dXWork.upload(xwork, st); c->dXPix.upload(xPix, st);
+            c->dSubLi.alloc(total);
+            ALVRL_CUDA(cudaMemsetAsync(c->dSubLi.p, 0, (size_t) total * sizeof(float4), st));
+            if (c->mathMode == 1) launch_render_strict(T, true, c->dChainSegs.p, c->dXList.p, c->dXWork.p, (uint32_t) xwork.size(), c->dRepRecs.p, c->dRepOffset.p, c->dSubLi.p, c->cam.W, c->cam.H, st, c->dChainKey.p);
+            else launch_render_fast(T, true, c->dChainSegs.p, c->dXList.p, c->dXWork.p, (uint32_t) xwork.size(), c->dRepRecs.p, c->dRepOffset.p, c->dSubLi.p, c->cam.W, c->cam.H, st, c->dChainKey.p);
+            /* per pixel: first = chainOffset[pix], end = chainOffset[pix + 1] */
+            std::vector<uint32_t> firstEnd(2 * xPix.size());
+            for (size_t i = 0; i < xPix.size(); i++) { firstEnd[2 * i] = c->chainOffset[xPix[i]]; firstEnd[2 * i + 1] = c->chainOffset[xPix[i] + 1]; }
+            c->dXPixFirst.upload(firstEnd, st);
+            launch_chain_accumulate(fb, c->cam.W, c->cam.H, c->dSubLi.p, c->dChainSegs.p, c->dXPix.p, c->dXPixFirst.p, (uint32_t) xPix.size(), st);
+            c->stats.kernelLaunches += 2;
+            ALVRL_CUDA(cudaGetLastError());
+            ALVRL_CUDA(cudaStreamSynchronize(st));
+        }
+    }
     c->stats.pairsRender += pairs;
     c->stats.shadowRays += pairs * (uint64_t) (c->P.volVolSamples + c->P.volSurfSamples);
 }
@@ -377,6 +468,42 @@ int alvrl_set_materials(alvrl_handle c, const float *albedo, const uint32_t *bit
     for (uint32_t i = 0; i < nm; i++) a[i] = make_float4(albedo[3 * i], albedo[3 * i + 1], albedo[3 * i + 2], 0);
     c->dMatAlbedo.upload(a, c->stream); c->dMatBits.upload(c->matBits, c->stream);
     c->haveMat = true; c->segsDirty = true;
+    API_END
+}
+
+int alvrl_set_material_optics(alvrl_handle c, const float *optics, uint32_t nm) {
+    API_BEGIN
+    use_device(c);
+    if (!c->haveMat || nm != c->matBits.size()) throw Error(ALVRL_ERR_ARG, "alvrl_set_material_optics: call alvrl_set_materials first, with the same material count");
+    if (!optics) throw Error(ALVRL_ERR_ARG, "alvrl_set_material_optics: null optics");
+    for (uint32_t i = 0; i < nm; i++)
+        if ((c->matBits[i] & ALVRL_BSDF_DIELECTRIC) && !(optics[12 * (size_t) i] > 0)) throw Error(ALVRL_ERR_ARG, "alvrl_set_material_optics: dielectric eta must be positive");
+    c->optics.assign(optics, optics + 12 * (size_t) nm);
+    std::vector<float4> o(3 * (size_t) nm);
+    for (uint32_t i = 0; i < nm; i++) for (int k = 0; k < 3; k++) o[3 * (size_t) i + k] = make_float4(optics[12 * (size_t) i + 4 * k], optics[12 * (size_t) i + 4 * k + 1], optics[12 * (size_t) i + 4 * k + 2], optics[12 * (size_t) i + 4 * k + 3]);
+    c->dMatOptics.upload(o, c->stream);
+    c->chainsValid = false; c->haveR = false; c->haveClusters = false;
+    API_END
+}
+
+int alvrl_get_chain_segments(alvrl_handle c, uint32_t *offset, float *segs) {
+    API_BEGIN
+    use_device(c);
+    if (!offset) throw Error(ALVRL_ERR_ARG, "alvrl_get_chain_segments: null offset");
+    ensure_chains(c);
+    const uint32_t P = c->numPixels(), total = c->chainOffset[P];
+    memcpy(offset, c->chainOffset.data(), (size_t) (P + 1) * sizeof(uint32_t));
+    if (segs && total) {
+        std::vector<SegRec> s(total);
+        c->dChainSegs.download(s.data(), total, c->stream);
+        for (uint32_t e = 0; e < total; e++) {
+            float *o = segs + 16 * (size_t) e;
+            o[0] = s[e].o.x; o[1] = s[e].o.y; o[2] = s[e].o.z; o[3] = s[e].d.x; o[4] = s[e].d.y; o[5] = s[e].d.z;
+            o[6] = s[e].p.x; o[7] = s[e].p.y; o[8] = s[e].p.z; o[9] = s[e].o.w;
+            o[10] = s[e].p.w; o[11] = s[e].n.w; o[12] = s[e].albedo.w; o[13] = (c->chainMeta[e].w & 1u) ? 1.0f : 0.0f;
+            o[14] = (float) c->chainMeta[e].z; o[15] = (float) (c->chainMeta[e].w >> 1);
+        }
+    }
     API_END
 }
 
@@ -599,6 +726,41 @@ int alvrl_build_R(alvrl_handle c) {
     c->stats.kernelLaunches++;
     ALVRL_CUDA(cudaGetLastError());
     ALVRL_CUDA(cudaStreamSynchronize(c->stream));
+    /* rows whose pixel continues as a specular chain: the chain's in-medium segments are rows of a second matrix (their own
+     * streams, their weights inside the estimate), added to the row of their pixel in chain order (getVRLContributions 812-813) */
+    ensure_chains(c);
+    uint64_t chainRows = 0;
+    if (c->anyDelta && c->chainOffset.back()) {
+        std::vector<uint32_t> xIdx, xKey, xFirst(r1 - r0 + 1, 0u);
+        for (uint32_t r = r0; r < r1; r++) {
+            const uint32_t pix = c->rowPixel[r];
+            for (uint32_t e = c->chainOffset[pix]; e < c->chainOffset[pix + 1]; e++)
+                if (c->chainMeta[e].w & 1u) {
+                    if (r >= (1u << 24)) throw Error(ALVRL_ERR_UNSUPPORTED, "specular chains: more than 2^24 rows");
+                    xIdx.push_back(e); xKey.push_back(r + ((c->chainMeta[e].y + 1u) << 24));
+                }
+            xFirst[r - r0 + 1] = (uint32_t) xIdx.size();
+        }
+        const uint32_t nX = (uint32_t) xIdx.size();
+        if (nX) {
+            if (T.tape) throw Error(ALVRL_ERR_UNSUPPORTED, "specular chains draw from the counter stream (no sample tape / rngMode=SFMT)");
+            c->dXIdx.upload(xIdx, c->stream); c->dXKey.upload(xKey, c->stream); c->dXFirst.upload(xFirst, c->stream);
+            c->dXSegs.alloc(nX);
+            launch_gather_rows(c->dChainSegs.p, c->dXIdx.p, nX, c->dXSegs.p, c->stream);
+            const uint32_t ldX = (nX + 31u) & ~31u;
+            c->dX.alloc((size_t) N * ldX);
+            TransportParams TX = T; TX.rowBase = 0;
+            if (c->mathMode == 1) launch_build_R_strict(TX, c->dXSegs.p, nX, c->dVrls.p, c->dX.p, ldX, c->stream, c->dXKey.p, true);
+            else launch_build_R_fast(TX, c->dXSegs.p, nX, c->dVrls.p, c->dX.p, ldX, c->stream, c->dXKey.p, true);
+            launch_add_chain_rows(c->dR.p, c->ldR, r0, r1 - r0, c->dX.p, ldX, c->dXFirst.p, N, c->stream);
+            c->stats.kernelLaunches += 3;
+            ALVRL_CUDA(cudaGetLastError());
+            ALVRL_CUDA(cudaStreamSynchronize(c->stream));
+            chainRows = nX;
+        }
+    }
+    c->stats.pairsPreprocess += chainRows * N;
+    c->stats.shadowRays += chainRows * N * (uint64_t) (c->P.volVolSamples + c->P.volSurfSamples);
     c->haveR = true; c->haveClusters = false; c->haveFallback = false;
     c->builtRow0 = r0; c->builtRow1 = r1;
     c->stats.pairsPreprocess += (uint64_t) (r1 - r0) * N;
@@ -669,6 +831,8 @@ int alvrl_render_unclustered(alvrl_handle c, float *rgb) {
     double t0 = now_ms();
     ensure_primary(c);
     ensure_vrl_sides(c);
+    ensure_chains(c);
+    if (c->anyDelta && c->chainOffset.back()) throw Error(ALVRL_ERR_UNSUPPORTED, "alvrl_render_unclustered does not follow specular chains (use the clustered render)");
     const uint32_t P = c->numPixels(), N = (uint32_t) c->vrlHost.size();
     std::vector<uint32_t> px(P), off = {0, N};
     std::vector<uint4> work;
@@ -699,6 +863,81 @@ int alvrl_set_slice_range(alvrl_handle c, uint32_t b, uint32_t e) {
     }
     c->sliceBegin = b; c->sliceEnd = e;
     return ALVRL_OK;
+}
+
+/* ---- film (film.cu) ------------------------------------------------------------------------------- */
+int alvrl_film_configure(alvrl_handle c, int filter, float param) {
+    API_BEGIN
+    if (!c->haveCam) throw Error(ALVRL_ERR_STATE, "set_camera first");
+    use_device(c);
+    /* filter radius and profile: box.cpp:38,46-48, tent.cpp:34,42-44, gaussian.cpp:30-35,52-58 */
+    float radius, stddev = 0.5f;
+    if (filter == ALVRL_FILTER_BOX) radius = (param > 0 ? param : 0.5f) + 1e-5f;
+    else if (filter == ALVRL_FILTER_TENT) radius = 1.0f;
+    else if (filter == ALVRL_FILTER_GAUSSIAN) { stddev = param > 0 ? param : 0.5f; radius = 4 * stddev; }
+    else throw Error(ALVRL_ERR_ARG, "alvrl_film_configure: unknown filter");
+    auto eval = [&](float x) -> float {
+        if (filter == ALVRL_FILTER_BOX) return std::fabs(x) <= radius ? 1.0f : 0.0f;
+        if (filter == ALVRL_FILTER_TENT) return std::max(0.0f, 1.0f - std::fabs(x / radius));
+        const float alpha = -1.0f / (2.0f * stddev * stddev);
+        return std::max(0.0f, (float) std::exp((double) (alpha * x * x)) - (float) std::exp((double) (alpha * radius * radius)));
+    };
+    /* ReconstructionFilter::configure, rfilter.cpp:37-55 */
+    FilmFilterDev &f = c->film;
+    float sum = 0.0f;
+    for (int i = 0; i < ALVRL_FILTER_RESOLUTION; i++) { const float v = eval((radius * i) / ALVRL_FILTER_RESOLUTION); f.table[i] = v; sum += v; }
+    f.table[ALVRL_FILTER_RESOLUTION] = 0.0f;
+    f.scaleFactor = ALVRL_FILTER_RESOLUTION / radius;
+    sum *= 2 * radius / ALVRL_FILTER_RESOLUTION;
+    const float normalization = 1.0f / sum;
+    for (int i = 0; i < ALVRL_FILTER_RESOLUTION; i++) f.table[i] *= normalization;
+    f.radius = radius; f.taps = (int) std::floor(radius);
+    c->haveFilm = true;
+    c->dFilm.alloc(5 * (size_t) c->numPixels());
+    ALVRL_CUDA(cudaMemsetAsync(c->dFilm.p, 0, 5 * (size_t) c->numPixels() * sizeof(float), c->stream));
+    c->filmPasses = 0;
+    API_END
+}
+
+int alvrl_film_clear(alvrl_handle c) {
+    API_BEGIN
+    if (!c->haveFilm) throw Error(ALVRL_ERR_STATE, "alvrl_film_configure first");
+    use_device(c);
+    ALVRL_CUDA(cudaMemsetAsync(c->dFilm.p, 0, 5 * (size_t) c->numPixels() * sizeof(float), c->stream));
+    c->filmPasses = 0;
+    API_END
+}
+
+int alvrl_film_put(alvrl_handle c, const float *rgb) {
+    API_BEGIN
+    if (!c->haveFilm) throw Error(ALVRL_ERR_STATE, "alvrl_film_configure first");
+    use_device(c);
+    const uint32_t P = c->numPixels(), W = c->cam.W, H = c->cam.H;
+    if (rgb) {                                           /* a frame from the host: [y][x][c] -> the framebuffer layout */
+        std::vector<float4> fb(P);
+        for (uint32_t i = 0; i < P; i++) fb[i] = make_float4(rgb[3 * (size_t) i], rgb[3 * (size_t) i + 1], rgb[3 * (size_t) i + 2], 1.0f);
+        c->dFb.alloc(P);
+        c->dFb.upload(fb, c->stream);
+    } else if (c->dFb.n < P) throw Error(ALVRL_ERR_STATE, "alvrl_film_put(NULL): no rendered frame on the device (alvrl_render first)");
+    launch_film_splat(c->dFb.p, W, H, c->film, c->dFilm.p, c->stream);
+    c->stats.kernelLaunches++;
+    ALVRL_CUDA(cudaGetLastError());
+    ALVRL_CUDA(cudaStreamSynchronize(c->stream));
+    c->filmPasses++;
+    API_END
+}
+
+int alvrl_film_develop(alvrl_handle c, float *rgb) {
+    API_BEGIN
+    if (!c->haveFilm) throw Error(ALVRL_ERR_STATE, "alvrl_film_configure first");
+    if (!rgb) throw Error(ALVRL_ERR_ARG, "alvrl_film_develop: null output");
+    use_device(c);
+    const uint32_t P = c->numPixels();
+    c->dRgb.alloc(3 * (size_t) P);
+    launch_film_develop(c->dFilm.p, P, c->dRgb.p, c->stream);
+    c->stats.kernelLaunches++;
+    c->dRgb.download(rgb, 3 * (size_t) P, c->stream);
+    API_END
 }
 
 int alvrl_render_device(alvrl_handle c, void *rgba, void *stream) {

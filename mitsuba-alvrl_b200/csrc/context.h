@@ -132,7 +132,8 @@ struct alvrl_ctx {
     std::vector<float> gridHost;
 
     /* scene (device) */
-    alvrl::DevBuf<BvhNode> dNodes, dLeafNodes; alvrl::DevBuf<TriRec> dTris; alvrl::DevBuf<TriFast> dTrisFast; alvrl::DevBuf<float4> dTriVerts, dOcc;
+    FilmFilterDev film; bool haveFilm = false; uint32_t filmPasses = 0; alvrl::DevBuf<float> dFilm;
+    alvrl::DevBuf<BvhNode> dNodes, dLeafNodes; alvrl::DevBuf<Bvh4Node> dNodes4; alvrl::DevBuf<TriRec> dTris; alvrl::DevBuf<TriFast> dTrisFast; alvrl::DevBuf<float4> dTriVerts, dOcc;
     alvrl::DevBuf<uint32_t> dTriMat, dMatBits; alvrl::DevBuf<float4> dMatAlbedo; alvrl::DevBuf<float> dGrid;
     SceneDev sceneDev; OccDev occHost;
 
@@ -143,6 +144,13 @@ struct alvrl_ctx {
 
     /* per pixel (index y + H*x) */
     alvrl::DevBuf<SegRec> dPixSegs; alvrl::DevBuf<uint32_t> dHitPrim; alvrl::DevBuf<float> dHitT;
+    /* specular chains (chain.cu): the segments below the camera segments, grouped by pixel */
+    std::vector<float> optics; alvrl::DevBuf<float4> dMatOptics; bool anyDelta = false, chainsValid = false;
+    std::vector<uint32_t> chainOffset;                 /* P + 1 */
+    std::vector<uint4> chainMeta;                      /* {pixel, ordinal, path code, (material << 1) | in-medium} */
+    alvrl::DevBuf<SegRec> dChainSegs; alvrl::DevBuf<uint4> dChainMeta; alvrl::DevBuf<uint32_t> dChainKey;
+    alvrl::DevBuf<SegRec> dXSegs; alvrl::DevBuf<uint32_t> dXIdx, dXKey, dXFirst; alvrl::DevBuf<float2> dX;     /* chain rows of R */
+    alvrl::DevBuf<float4> dSubLi; alvrl::DevBuf<uint32_t> dXList, dXPix, dXPixFirst; alvrl::DevBuf<uint4> dXWork;   /* chain render pass */
     bool havePrimary = false;
 
     /* slices / rows */

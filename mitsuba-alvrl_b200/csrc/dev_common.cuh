@@ -266,6 +266,66 @@ __device__ __forceinline__ bool bvh_occluded_fast_warp(const SceneDev &sc, const
     return hit;
 }
 
+/*
+ * Any-hit query on the 4-wide tree (types.h::Bvh4Node, bvh.h::collapse4), called by ALL 32 lanes of a warp together.  A
+ * lane keeps its pending subtrees and leaves on a small stack in local memory; one round of the loop expands the inner
+ * node a lane holds (four slab tests on one 128-byte line, hits pushed) or tests the triangles of the leaf it holds, then
+ * pops.  The loop and both phases are controlled by warp votes.  A quarter of the dependent node fetches of the binary
+ * tree (C4: 21 instead of 81 per ray), which is what bounds a traversal that waits for L2 on every step.
+ */
+#define ALVRL_BVH4_STACK 64
+__device__ __forceinline__ bool bvh4_occluded_warp(const SceneDev &sc, const F3 &o, const F3 &d, float mint, float maxt, bool need) {
+    const F3 inv = f3(__frcp_rn(d.x), __frcp_rn(d.y), __frcp_rn(d.z));
+    const F3 oi = f3(-o.x * inv.x, -o.y * inv.y, -o.z * inv.z);
+    const float lo_t = mint, hi_t = maxt * 1.00001f;
+    const int DONE = (int) 0x80000000u;
+    int stack[ALVRL_BVH4_STACK];
+    int sp = 0;
+    int cur = (need && maxt > mint) ? 0 : DONE;
+    bool hit = false;
+    __syncwarp();
+    while (__any_sync(0xffffffffu, cur != DONE)) {
+        if (cur >= 0) {                                                    /* inner node: test the four children */
+            const Bvh4Node *nd = sc.nodes4 + cur;
+            const float4 lox = __ldg(&nd->lox), hix = __ldg(&nd->hix), loy = __ldg(&nd->loy), hiy = __ldg(&nd->hiy),
+                         loz = __ldg(&nd->loz), hiz = __ldg(&nd->hiz);
+            const int4 ch = __ldg(&nd->child);
+#define ALVRL_B4_CHILD(C, K)                                                                                              \
+            {                                                                                                             \
+                const float tx1 = fmaf(lox.C, inv.x, oi.x), tx2 = fmaf(hix.C, inv.x, oi.x);                              \
+                const float ty1 = fmaf(loy.C, inv.y, oi.y), ty2 = fmaf(hiy.C, inv.y, oi.y);                              \
+                const float tz1 = fmaf(loz.C, inv.z, oi.z), tz2 = fmaf(hiz.C, inv.z, oi.z);                              \
+                const float tn = fmaxf(fmaxf(fminf(tx1, tx2), fminf(ty1, ty2)), fmaxf(fminf(tz1, tz2), lo_t));            \
+                const float tf = fminf(fminf(fmaxf(tx1, tx2), fmaxf(ty1, ty2)), fminf(fmaxf(tz1, tz2), hi_t));            \
+                if (tn <= tf && K != DONE && sp < ALVRL_BVH4_STACK) stack[sp++] = K;                                      \
+            }
+            ALVRL_B4_CHILD(x, ch.x) ALVRL_B4_CHILD(y, ch.y) ALVRL_B4_CHILD(z, ch.z) ALVRL_B4_CHILD(w, ch.w)
+#undef ALVRL_B4_CHILD
+            cur = sp ? stack[--sp] : DONE;
+        }
+        if (__any_sync(0xffffffffu, cur < 0 && cur != DONE)) {
+            if (cur < 0 && cur != DONE) {                                  /* leaf: ~((first << 4) | count) */
+                const uint32_t lf = (uint32_t) ~cur;
+                const uint32_t first = lf >> 4, cnt = lf & 15u;
+                for (uint32_t i = 0; i < cnt; i++) {
+                    const float4 p = __ldg(&sc.trisFast[first + i].p);
+                    const float den = p.x * d.x + p.y * d.y + p.z * d.z;
+                    const float num = p.w - (p.x * o.x + p.y * o.y + p.z * o.z);
+                    const float t = __fdividef(num, den);
+                    if (!(t >= mint && t <= maxt)) continue;
+                    const float4 q = __ldg(&sc.trisFast[first + i].q), r = __ldg(&sc.trisFast[first + i].r);
+                    const F3 P = f3(fmaf(t, d.x, o.x), fmaf(t, d.y, o.y), fmaf(t, d.z, o.z));
+                    const float u = q.x * P.x + q.y * P.y + q.z * P.z + q.w;
+                    const float v = r.x * P.x + r.y * P.y + r.z * P.z + r.w;
+                    if (u >= 0.0f && v >= 0.0f && u + v <= 1.0f) { hit = true; break; }
+                }
+                cur = (hit || !sp) ? DONE : stack[--sp];
+            }
+        }
+    }
+    return hit;
+}
+
 /* ---- media (exact flavour: used by the primary kernel and the strict transport flavour) ---------- */
 __device__ __forceinline__ float exp_ref(float x) { return (float) exp((double) x); }   /* math::fastexp, math.h:185-187 */
 

@@ -16,16 +16,31 @@ void launch_eval_transmittance(const SceneDev &sc, const MediumDev &med, const f
                                uint32_t n, float *T, cudaStream_t st);
 void launch_fb_to_rgb(const float4 *fb, float *rgb, uint32_t n, cudaStream_t st);
 
+/* chain.cu (exact arithmetic): specular chains */
+void launch_chain_count(const SceneDev &sc, const MediumDev &med, bool haveMedium, const float4 *triVerts, const uint32_t *triMat, const float4 *matAlbedo,
+                        const uint32_t *matBits, const float4 *matOptics, uint64_t seed, int specRRdepth, float initialThroughput, const SegRec *pixSegs,
+                        const uint32_t *hitPrim, const float *hitT, uint32_t P, uint32_t *counts, cudaStream_t st);
+void launch_chain_write(const SceneDev &sc, const MediumDev &med, bool haveMedium, const float4 *triVerts, const uint32_t *triMat, const float4 *matAlbedo,
+                        const uint32_t *matBits, const float4 *matOptics, uint64_t seed, int specRRdepth, float initialThroughput, const SegRec *pixSegs,
+                        const uint32_t *hitPrim, const float *hitT, uint32_t P, const uint32_t *offset, SegRec *out, uint4 *meta, cudaStream_t st);
+void launch_add_chain_rows(float2 *R, uint32_t ldR, uint32_t rowBegin, uint32_t numRows, const float2 *X, uint32_t ldX, const uint32_t *xFirst, uint32_t N, cudaStream_t st);
+void launch_chain_accumulate(float4 *fb, uint32_t W, uint32_t H, const float4 *subLi, const SegRec *segs, const uint32_t *pixList, const uint32_t *first, uint32_t nPix, cudaStream_t st);
+
+/* film.cu (exact arithmetic) */
+void launch_film_splat(const float4 *fb, uint32_t W, uint32_t H, const FilmFilterDev &f, float *acc, cudaStream_t st);
+void launch_film_develop(const float *acc, uint32_t n, float *rgb, cudaStream_t st);
+
 /* transport_strict.cu / transport_fast.cu */
+/* rowKey (optional): the stream key of every row (default: P.rowBase + row); weighted: the segments carry LiInternal's weight */
 void launch_build_R_strict(const TransportParams &P, const SegRec *rowSegs, uint32_t numRows, const VrlRec *vrls, float2 *R,
-                           uint32_t ldR, cudaStream_t st);
+                           uint32_t ldR, cudaStream_t st, const uint32_t *rowKey = nullptr, bool weighted = false);
 void launch_build_R_fast(const TransportParams &P, const SegRec *rowSegs, uint32_t numRows, const VrlRec *vrls, float2 *R,
-                         uint32_t ldR, cudaStream_t st);
+                         uint32_t ldR, cudaStream_t st, const uint32_t *rowKey = nullptr, bool weighted = false);
 void launch_render_strict(const TransportParams &P, bool clustered, const SegRec *pixSegs, const uint32_t *slicePixels,
                           const uint4 *work, uint32_t numWork, const VrlRec *repRecs, const uint32_t *repOffset, float4 *fb,
-                          uint32_t W, uint32_t H, cudaStream_t st);
+                          uint32_t W, uint32_t H, cudaStream_t st, const uint32_t *segKey = nullptr);
 void launch_render_fast(const TransportParams &P, bool clustered, const SegRec *pixSegs, const uint32_t *slicePixels,
                         const uint4 *work, uint32_t numWork, const VrlRec *repRecs, const uint32_t *repOffset, float4 *fb,
-                        uint32_t W, uint32_t H, cudaStream_t st);
+                        uint32_t W, uint32_t H, cudaStream_t st, const uint32_t *segKey = nullptr);
 
 } // namespace alvrl

@@ -55,9 +55,9 @@ __global__ void __launch_bounds__(128) k_primary(SceneDev sc, MediumDev med, Cam
     s.o = make_float4(o.x, o.y, o.z, 0.0f);
     s.d = make_float4(d.x, d.y, d.z, 0.0f);
     s.dn = make_float4(dn.x, dn.y, dn.z, __uint_as_float(0u));
-    s.p = make_float4(NAN, NAN, NAN, 0.0f);
-    s.n = make_float4(NAN, NAN, NAN, 0.0f);
-    s.albedo = make_float4(0, 0, 0, 0);
+    s.p = make_float4(NAN, NAN, NAN, 1.0f);
+    s.n = make_float4(NAN, NAN, NAN, 1.0f);
+    s.albedo = make_float4(0, 0, 0, 1.0f);
     s.tE = make_float4(0, 0, 0, 0);
     if (hit) {
         const F3 p0 = f3(__ldg(&triVerts[3 * (size_t) prim])), p1 = f3(__ldg(&triVerts[3 * (size_t) prim + 1])),
@@ -70,12 +70,12 @@ __global__ void __launch_bounds__(128) k_primary(SceneDev sc, MediumDev med, Cam
         const float wiz = xdot(f3(-d.x, -d.y, -d.z), fn);
         const float dist = xlen(xsub3(p, o));
         const uint32_t mat = triMat[prim];
-        uint32_t flags = SEG_VALID | ((matBits[mat] & ALVRL_BSDF_SMOOTH) ? SEG_SMOOTH : 0u);
+        uint32_t flags = SEG_VALID | ((matBits[mat] & ALVRL_BSDF_SMOOTH) ? SEG_SMOOTH : 0u) | ((matBits[mat] & ALVRL_BSDF_DELTA) ? SEG_DELTA : 0u);
         s.o.w = dist; s.d.w = wiz;
         s.dn.w = __uint_as_float(flags);
-        s.p = make_float4(p.x, p.y, p.z, 0.0f);
-        s.n = make_float4(fn.x, fn.y, fn.z, 0.0f);
-        s.albedo = matAlbedo[mat];
+        s.p = make_float4(p.x, p.y, p.z, 1.0f);
+        s.n = make_float4(fn.x, fn.y, fn.z, 1.0f);
+        s.albedo = matAlbedo[mat]; s.albedo.w = 1.0f;
         if (haveMedium && dist != 0) {                                              /* vrlIntegrator.cpp:711-719 */
             float T[3];
             medium_transmittance_exact(med, o, d, dist, T);

@@ -202,6 +202,10 @@ __device__ __forceinline__ void integrate_pair(const TransportParams &P, const S
     const F3 E = f3(seg.o), EU = f3(seg.d), Usurf = f3(seg.p);
     const float edist = seg.o.w;
     const int Nvv = P.Nvv, Nvs = P.Nvs;
+    /* LiInternal's `weight` of the segment (1 for a camera segment; specular chains, 500): inside the estimate for the rows of R
+     * (getVRLContributions passes it on, 811); the render pass multiplies the pixel's sum afterwards (598) */
+    const float wgt[3] = {seg.p.w, seg.n.w, seg.albedo.w};
+    (void) wgt;
     if (WANT_RGB) rgb[0] = rgb[1] = rgb[2] = 0;
     outMean = 0; outVar = 0;
 
@@ -280,7 +284,7 @@ __device__ __forceinline__ void integrate_pair(const TransportParams &P, const S
                     float c[3];
 #pragma unroll
                     for (int i = 0; i < 3; i++) {
-                        float x = pw[i];
+                        float x = WANT_STAT ? wgt[i] * pw[i] : pw[i];           /* 668-669: contribution = weight; *= power */
                         x *= (sSv[i] * sSe[i]) * rpdf;
                         x *= rd2;
                         x *= Tv[i];
@@ -349,7 +353,7 @@ __device__ __forceinline__ void integrate_pair(const TransportParams &P, const S
                     float c[3];
 #pragma unroll
                     for (int i = 0; i < 3; i++) {
-                        float x = pw[i];
+                        float x = WANT_STAT ? wgt[i] * pw[i] : pw[i];           /* 745-746 */
                         x *= P.medium.sigmaS[i] * rpdf;                      /* base-class getSigmaS(), quirk B2 */
                         x *= rd2;
                         x *= Tv[i];
@@ -414,10 +418,10 @@ struct TileSmem {
  * "Building R" (vrlIntegrator.cpp:302-337,792-825): rows = representative-pixel segments, columns = VRLs.
  * grid.x = row blocks of 128, grid.y = VRL chunks of vrlsPerCta (multiple of the tile size).
  */
-template <int MED, int SMALL>
+template <int MED, int SMALL, bool WEIGHTED>
 __global__ void __launch_bounds__(ALVRL_CTA_SEGS, ALVRL_MIN_CTAS) ALVRL_NAME(k_build_R)(TransportParams P, const SegRec *__restrict__ rowSegs, uint32_t numRows,
                                                                        const VrlRec *__restrict__ vrls, float2 *__restrict__ R, uint32_t ldR,
-                                                                       uint32_t vrlsPerCta) {
+                                                                       uint32_t vrlsPerCta, const uint32_t *__restrict__ rowKey) {
 #ifdef ALVRL_FAST
     extern __shared__ __align__(128) unsigned char dynSmem[];
     TileSmem &sm = *reinterpret_cast<TileSmem *>(dynSmem);
@@ -427,9 +431,12 @@ __global__ void __launch_bounds__(ALVRL_CTA_SEGS, ALVRL_MIN_CTAS) ALVRL_NAME(k_b
     __shared__ __align__(128) TileSmem sm;
 #endif
     const uint32_t tid = threadIdx.x;
-    const uint32_t row = blockIdx.x * ALVRL_CTA_SEGS + tid;
+    /* grid medium: the VRL chunk is the fast grid index, so that the CTAs in flight share a few row blocks -- their camera-
+     * segment marches (E -> U) then hit in L2 instead of streaming the 512 MB grid from DRAM once per VRL chunk */
+    const uint32_t rowBlock = MED == 1 ? blockIdx.y : blockIdx.x, chunk = MED == 1 ? blockIdx.x : blockIdx.y;
+    const uint32_t row = rowBlock * ALVRL_CTA_SEGS + tid;
     const uint32_t N = P.numVrls;
-    const uint32_t vBegin = blockIdx.y * vrlsPerCta;
+    const uint32_t vBegin = chunk * vrlsPerCta;
     const uint32_t vEnd = min(N, vBegin + vrlsPerCta);
     if (vBegin >= vEnd) return;
     const uint32_t numTiles = (vEnd - vBegin + ALVRL_TILE_VRLS - 1) / ALVRL_TILE_VRLS;
@@ -456,6 +463,9 @@ __global__ void __launch_bounds__(ALVRL_CTA_SEGS, ALVRL_MIN_CTAS) ALVRL_NAME(k_b
         active = (__float_as_uint(seg.dn.w) & SEG_VALID) != 0;
     }
     const bool scattering = !(P.medium.sigmaS[0] == 0 && P.medium.sigmaS[1] == 0 && P.medium.sigmaS[2] == 0);
+    /* stream of the row: (row, vrl); the segments of a specular chain are rows of their own matrix and carry the key
+     * (row of their pixel) + (ordinal in the chain << 24) */
+    const uint32_t keyRow = rowKey ? (row < numRows ? rowKey[row] : 0u) : P.rowBase + row;
 #ifdef ALVRL_FAST
     SegSides sides; sides.slabHull = sides.slabSurf = sides.planes = 0;
     if (SMALL == 2) sides = seg_sides(P.occ, seg, active && scattering);
@@ -477,13 +487,13 @@ __global__ void __launch_bounds__(ALVRL_CTA_SEGS, ALVRL_MIN_CTAS) ALVRL_NAME(k_b
                     const VrlRec &vr = sm.tile[t & 1][j];
                     Rng rng;
                     rng.tape = P.tape ? P.tape + ((size_t) (P.rowBase + row) * N + v) * P.tapeK : nullptr;
-                    rng.key = alvrl_rng_key(P.seed, P.rngDomain, P.rowBase + row, v);
+                    rng.key = alvrl_rng_key(P.seed, P.rngDomain, keyRow, v);
                     rng.k = 0;
                     float rgb[3], m, s2;
                     PairCull cull; cull.boxVV = cull.boxVS = cull.planes = 0xffffffffu;
                     if (SMALL == 2) cull = pair_cull(P.occ, sides, vr.dir, vr.power);
                     if constexpr (MED == 1) integrate_pair_grid_fast<false, true, SMALL>(P, &sbvh, seg, vr.s, vr.e, vr.dir, vr.power, rng, rgb, m, s2, active && scattering, cull);
-                    else integrate_pair_fast<MED, false, true, SMALL>(P, &sbvh, seg, vr.s, vr.e, vr.dir, vr.power, rng, rgb, m, s2, active && scattering, cull);
+                    else integrate_pair_fast<MED, false, true, SMALL, WEIGHTED>(P, &sbvh, seg, vr.s, vr.e, vr.dir, vr.power, rng, rgb, m, s2, active && scattering, cull);
                     mean = m * P.normalization;
                     var = s2 * P.normalization * P.normalization;
                 }
@@ -492,7 +502,7 @@ __global__ void __launch_bounds__(ALVRL_CTA_SEGS, ALVRL_MIN_CTAS) ALVRL_NAME(k_b
                     const VrlRec &vr = sm.tile[t & 1][j];
                     Rng rng;
                     rng.tape = P.tape ? P.tape + ((size_t) (P.rowBase + row) * N + v) * P.tapeK : nullptr;
-                    rng.key = alvrl_rng_key(P.seed, P.rngDomain, P.rowBase + row, v);
+                    rng.key = alvrl_rng_key(P.seed, P.rngDomain, keyRow, v);
                     rng.k = 0;
                     float rgb[3], m, s2;
                     integrate_pair<(MED == 2 ? 0 : MED), false, true>(P, seg, vr.s, vr.e, vr.dir, vr.power, rng, rgb, m, s2);
@@ -516,7 +526,7 @@ template <int MED, bool CLUSTERED, int SMALL>
 __global__ void __launch_bounds__(ALVRL_CTA_SEGS, ALVRL_MIN_CTAS) ALVRL_NAME(k_render)(TransportParams P, const SegRec *__restrict__ pixSegs,
                                                                       const uint32_t *__restrict__ slicePixels, const uint4 *__restrict__ work,
                                                                       const VrlRec *__restrict__ repRecs, const uint32_t *__restrict__ repOffset,
-                                                                      float4 *__restrict__ fb, uint32_t W, uint32_t H) {
+                                                                      float4 *__restrict__ fb, uint32_t W, uint32_t H, const uint32_t *__restrict__ segKey) {
 #ifdef ALVRL_FAST
     extern __shared__ __align__(128) unsigned char dynSmem[];
     TileSmem &sm = *reinterpret_cast<TileSmem *>(dynSmem);
@@ -555,6 +565,9 @@ __global__ void __launch_bounds__(ALVRL_CTA_SEGS, ALVRL_MIN_CTAS) ALVRL_NAME(k_r
     }
     const bool scattering = !(P.medium.sigmaS[0] == 0 && P.medium.sigmaS[1] == 0 && P.medium.sigmaS[2] == 0);
     float Li[3] = {0, 0, 0};
+    /* segments of specular chains are rendered from their own list: slicePixels indexes that list, segKey gives the stream key
+     * (pixel + (ordinal << 24)) and the result goes to fb[list index] (k_chain_accumulate adds it to the pixel, weighted) */
+    const uint32_t keyPix = segKey ? (inRange ? segKey[pixel] : 0u) : pixel;
 #ifdef ALVRL_FAST
     SegSides sides; sides.slabHull = sides.slabSurf = sides.planes = 0;
     if (SMALL == 2) sides = seg_sides(P.occ, seg, active && scattering);
@@ -570,7 +583,7 @@ __global__ void __launch_bounds__(ALVRL_CTA_SEGS, ALVRL_MIN_CTAS) ALVRL_NAME(k_r
                 const VrlRec &vr = sm.tile[t & 1][j];
                 Rng rng;
                 rng.tape = nullptr;
-                rng.key = alvrl_rng_key(P.seed, ALVRL_RNG_RENDER, pixel, v0 + j - vBegin);
+                rng.key = alvrl_rng_key(P.seed, ALVRL_RNG_RENDER, keyPix, v0 + j - vBegin);
                 rng.k = 0;
                 float rgb[3] = {0, 0, 0}, m, s2;
 #if defined(ALVRL_FAST) && !defined(ALVRL_DIAG_GENERIC)
@@ -578,7 +591,7 @@ __global__ void __launch_bounds__(ALVRL_CTA_SEGS, ALVRL_MIN_CTAS) ALVRL_NAME(k_r
                     PairCull cull; cull.boxVV = cull.boxVS = cull.planes = 0xffffffffu;
                     if (SMALL == 2) cull = pair_cull(P.occ, sides, vr.dir, vr.power);
                     if constexpr (MED == 1) integrate_pair_grid_fast<true, false, SMALL>(P, &sbvh, seg, vr.s, vr.e, vr.dir, vr.power, rng, rgb, m, s2, active && scattering, cull);
-                    else integrate_pair_fast<MED, true, false, SMALL>(P, &sbvh, seg, vr.s, vr.e, vr.dir, vr.power, rng, rgb, m, s2, active && scattering, cull);
+                    else integrate_pair_fast<MED, true, false, SMALL, false>(P, &sbvh, seg, vr.s, vr.e, vr.dir, vr.power, rng, rgb, m, s2, active && scattering, cull);
                 }
 #else
                 if (active && scattering) integrate_pair<(MED == 2 ? 0 : MED), true, false>(P, seg, vr.s, vr.e, vr.dir, vr.power, rng, rgb, m, s2);
@@ -599,6 +612,7 @@ __global__ void __launch_bounds__(ALVRL_CTA_SEGS, ALVRL_MIN_CTAS) ALVRL_NAME(k_r
             Li[0] *= r; Li[1] *= r; Li[2] *= r;
         }
         const uint32_t x = pixel / H, y = pixel % H;
-        fb[(size_t) y * W + x] = make_float4(Li[0], Li[1], Li[2], 1.0f);
+        if (segKey) fb[pixel] = make_float4(Li[0], Li[1], Li[2], 1.0f);
+        else fb[(size_t) y * W + x] = make_float4(Li[0], Li[1], Li[2], 1.0f);
     }
 }

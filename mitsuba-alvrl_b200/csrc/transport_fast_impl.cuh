@@ -122,7 +122,9 @@ __device__ __forceinline__ bool occluded_fast(const TransportParams &P, const Bv
     const float mint = onSurf ? ALVRL_EPSILON * fmaxf(fmaxf(fabsf(p1.x), fabsf(p1.y)), fabsf(p1.z)) : 0.0f;
     if (SMALL == 2) return occ_query(P.occ, sb->tris, p1.x, p1.y, p1.z, dir.x, dir.y, dir.z, mint, remaining, need, boxActive, planeActive);
     if (SMALL == 1) return occluded_flat(*sb, P.scene.numLeaves, p1, dir, mint, remaining, need);
-    return bvh_occluded_fast_warp(P.scene, p1, dir, mint, remaining, need);      /* all lanes of the warp call this together */
+    /* all lanes of the warp call these together */
+    if (P.scene.nodes4) return bvh4_occluded_warp(P.scene, p1, dir, mint, remaining, need);
+    return bvh_occluded_fast_warp(P.scene, p1, dir, mint, remaining, need);
 }
 
 /* diagnostic variants (tools/build_variant.sh -DALVRL_DIAG_*): accurate library functions in place of the MUFU forms, to
@@ -188,7 +190,7 @@ __device__ __forceinline__ float f_atan(float x) {
 __device__ __forceinline__ float f_len(const F3 &a, float &l2) { l2 = len2(a); return l2 * rsqrtf(fmaxf(l2, 1e-38f)); }
 
 /* homogeneous media only (MED 0: RGB sigma_t, MED 2: grey sigma_t) */
-template <int MED, bool WANT_RGB, bool WANT_STAT, int SMALL>
+template <int MED, bool WANT_RGB, bool WANT_STAT, int SMALL, bool WEIGHTED>
 __device__ __forceinline__ void integrate_pair_fast(const TransportParams &P, const BvhSmem *sb, const SegRec &seg,
                                                     const float4 vS, const float4 vE, const float4 vDir, const float4 vPow, Rng &rng,
                                                     float rgb[3], float &outMean, float &outVar, const bool laneOn, const PairCull cull) {
@@ -209,7 +211,10 @@ __device__ __forceinline__ void integrate_pair_fast(const TransportParams &P, co
     /* ---- volume to volume (646-703) ---- */
     if (Nvv > 0) {
         /* power * sigma_s(V) * sigma_s(U): constant per pair in a homogeneous medium */
-        const float k0 = vPow.x * M.sigmaS[0] * M.sigmaS[0], k1 = vPow.y * M.sigmaS[1] * M.sigmaS[1], k2 = vPow.z * M.sigmaS[2] * M.sigmaS[2];
+        /* WEIGHTED: the segment of a specular chain carries LiInternal's weight (p.w, n.w, albedo.w); camera segments weigh 1 and
+         * their kernels do not spend the registers */
+        float k0 = vPow.x * M.sigmaS[0] * M.sigmaS[0], k1 = vPow.y * M.sigmaS[1] * M.sigmaS[1], k2 = vPow.z * M.sigmaS[2] * M.sigmaS[2];
+        if (WEIGHTED) { k0 *= seg.p.w; k1 *= seg.n.w; k2 *= seg.albedo.w; }
         float cosTheta, sinTheta;
         cos_sin_theta(f3(seg.dn), SV, cosTheta, sinTheta);
         const bool parallel = sinTheta < ALVRL_EPSILON;
@@ -310,8 +315,9 @@ __device__ __forceinline__ void integrate_pair_fast(const TransportParams &P, co
             const float invNvs = f_rcp((float) Nvs);
             const F3 nrm = f3(seg.n);
             const bool frontI = seg.d.w > 0;
-            const float k0 = vPow.x * M.sigmaS[0] * seg.albedo.x * tE0, k1 = vPow.y * M.sigmaS[1] * seg.albedo.y * tE1,
-                        k2 = vPow.z * M.sigmaS[2] * seg.albedo.z * tE2;
+            float k0 = vPow.x * M.sigmaS[0] * seg.albedo.x * tE0, k1 = vPow.y * M.sigmaS[1] * seg.albedo.y * tE1,
+                  k2 = vPow.z * M.sigmaS[2] * seg.albedo.z * tE2;
+            if (WEIGHTED) { k0 *= seg.p.w; k1 *= seg.n.w; k2 *= seg.albedo.w; }
             for (int k = 0; k < Nvs; k++) {
                 const float u = surf ? rng.next() : 0.5f;
                 const float t = Dis * f_tan(fmaf(u, th_b - th_a, th_a));

@@ -102,6 +102,9 @@ __device__ __forceinline__ void integrate_pair_grid_fast(const TransportParams &
     if (WANT_RGB) rgb[0] = rgb[1] = rgb[2] = 0;
     outMean = 0; outVar = 0;
     const float lw0 = 0.212671f, lw1 = 0.715160f, lw2 = 0.072169f;
+    /* LiInternal's weight of a specular-chain segment: inside the estimate for the rows of R only (the render pass multiplies the
+     * pixel's sum afterwards) */
+    const float wg0 = WANT_STAT ? seg.p.w : 1.0f, wg1 = WANT_STAT ? seg.n.w : 1.0f, wg2 = WANT_STAT ? seg.albedo.w : 1.0f;
 
     /* ---- volume to volume (646-703) ---- */
     if (Nvv > 0) {
@@ -166,8 +169,8 @@ __device__ __forceinline__ void integrate_pair_grid_fast(const TransportParams &
                 float common = f_div(densU * densV, pdf * d2) * T;
                 if (P.shortVrls) common = f_div(common, pf);                     /* 0 / 0 = NaN past the early exit: invalid, dropped */
                 common *= phase_eval(M, dot(VU, EU)) * phase_eval(M, -dot(SV, VU));
-                const float c0 = vPow.x * M.albedo[0] * M.albedo[0] * common, c1 = vPow.y * M.albedo[1] * M.albedo[1] * common,
-                            c2 = vPow.z * M.albedo[2] * M.albedo[2] * common;
+                const float c0 = vPow.x * M.albedo[0] * M.albedo[0] * common * wg0, c1 = vPow.y * M.albedo[1] * M.albedo[1] * common * wg1,
+                            c2 = vPow.z * M.albedo[2] * M.albedo[2] * common * wg2;
                 if (common >= 0.0f && fmaxf(common, fmaxf(c0, fmaxf(c1, c2))) < INFINITY) {
                     if (WANT_RGB) { rgb[0] = fmaf(c0, invNvv, rgb[0]); rgb[1] = fmaf(c1, invNvv, rgb[1]); rgb[2] = fmaf(c2, invNvv, rgb[2]); }
                     lum = c0 * lw0 + c1 * lw1 + c2 * lw2;
@@ -200,8 +203,8 @@ __device__ __forceinline__ void integrate_pair_grid_fast(const TransportParams &
             const F3 nrm = f3(seg.n);
             const bool frontI = seg.d.w > 0;
             /* vrlMedium->getSigmaS() is the base sigma_s of the grid medium (quirk B2), 748 */
-            const float k0 = vPow.x * M.sigmaS[0] * seg.albedo.x * tE0, k1 = vPow.y * M.sigmaS[1] * seg.albedo.y * tE1,
-                        k2 = vPow.z * M.sigmaS[2] * seg.albedo.z * tE2;
+            const float k0 = vPow.x * M.sigmaS[0] * seg.albedo.x * tE0 * wg0, k1 = vPow.y * M.sigmaS[1] * seg.albedo.y * tE1 * wg1,
+                        k2 = vPow.z * M.sigmaS[2] * seg.albedo.z * tE2 * wg2;
             for (int k = 0; k < Nvs; k++) {
                 const float u = surf ? rng.next() : 0.5f;
                 const float t = Dis * f_tan(fmaf(u, th_b - th_a, th_a));

@@ -36,14 +36,15 @@ struct VrlRec {
 
 #define SEG_VALID  1u   /* primary ray hit geometry (vrlIntegrator.cpp:418-423) */
 #define SEG_SMOOTH 2u   /* BSDF has an ESmooth component (vrlIntegrator.cpp:726-727) */
+#define SEG_DELTA  4u   /* BSDF has delta components: the segment continues as a specular chain (445-448) */
 
 struct SegRec {
     float4 o;      /* ray.o.xyz, distance(its.p, ray.o) */
     float4 d;      /* ray.d.xyz, cosTheta(its.wi) */
     float4 dn;     /* normalize(ray.d).xyz (sampleVtoDistance re-normalises, 925), flags as int bits */
-    float4 p;      /* its.p.xyz (barycentric), 0 */
-    float4 n;      /* shading normal.xyz, 0 */
-    float4 albedo; /* diffuse reflectance rgb, 0 */
+    float4 p;      /* its.p.xyz (barycentric), weight.r of the segment (LiInternal's `weight`: 1 for a camera segment) */
+    float4 n;      /* shading normal.xyz, weight.g */
+    float4 albedo; /* diffuse reflectance rgb, weight.b */
     float4 tE;     /* transmittance eye -> surface rgb (vrlIntegrator.cpp:711-719), 0 */
 };
 
@@ -52,6 +53,16 @@ struct BvhNode {
     float4 hi;     /* bmax.xyz, __int_as_float(leaf: (first << 4) | count, inner: 0) */
 };
 #define BVH_END 0x7fffffff
+
+/* 4-wide node of the fast flavour's any-hit query on large scenes (bvh.h::collapse4): the boxes of up to four children in
+ * SoA form -- one 128-byte line per node, seven 16-byte loads -- and what each child is: >= 0 an inner node (index into the
+ * Bvh4Node array), < 0 a leaf, ~((first << 4) | count) into the triangle arrays; an unused slot has an empty box
+ * (lo = +inf, hi = -inf) that no ray enters */
+struct __align__(128) Bvh4Node {
+    float4 lox, loy, loz, hix, hiy, hiz;
+    int4 child;
+    int4 pad;
+};
 
 struct TriRec {
     float4 a;      /* __int_as_float(k), n_u, n_v, n_d */
@@ -74,6 +85,15 @@ struct MediumDev {
     float gsc[3], gtr[3];   /* worldToGrid: g = gsc * p + gtr (gridvolume.cpp:188-196) */
 };
 
+/* pre-rasterised reconstruction filter (include/mitsuba/core/rfilter.h:28,76-77,96-98) */
+#define ALVRL_FILTER_RESOLUTION 31
+struct FilmFilterDev {
+    float table[ALVRL_FILTER_RESOLUTION + 1];
+    float scaleFactor;      /* MTS_FILTER_RESOLUTION / radius */
+    float radius;
+    int taps;               /* floor(radius): the integer offsets a sample at a pixel centre reaches */
+};
+
 struct CameraDev {
     float s2c[16], c2w[16];
     uint32_t W, H; float nearClip, farClip; float invResX, invResY;
@@ -85,6 +105,7 @@ struct SceneDev {
     int anyHit;
     /* small scenes, fast flavour (occluders.h): visMode 0 = tree traversal, 1 = flat leaf sweep, 2 = compiled occluder set */
     const float4 *occTris; uint32_t numOccTris; int visMode;
+    const Bvh4Node *nodes4; uint32_t numNodes4;   /* visMode 0 */
 };
 
 struct TransportParams {

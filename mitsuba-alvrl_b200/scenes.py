@@ -13,6 +13,8 @@ import math
 import numpy as np
 
 BSDF_SMOOTH = 1
+BSDF_DIELECTRIC, BSDF_CONDUCTOR = 2, 4          # delta BSDFs of the specular chains (include/alvrl.h)
+MAT_TRANSITION, MAT_INTERIOR_MEDIUM, MAT_EXTERIOR_MEDIUM = 8, 16, 32
 
 
 # ---- camera ------------------------------------------------------------------------------------
@@ -229,6 +231,37 @@ def cornell_scene(width, height, medium=None, closed=False, mesh=None):
         cam = perspective_camera(width, height, origin=(0.5, 0.5, -1.4), target=(0.5, 0.5, 0.0), fov=40.0)
     return dict(verts=v, tris=t, tri_material=m, albedo=_ALBEDO.copy(),
                 mat_bits=np.full(len(_ALBEDO), BSDF_SMOOTH, np.uint32),
+                medium=medium or homogeneous_medium(), camera=cam, extra_bounds=cam["origin"].reshape(1, 3))
+
+
+def chain_scene(width, height, medium=None, glass_eta=1.5):
+    """Cornell box with a glass sphere (smooth dielectric, the fog outside, vacuum inside) in front of the boxes and the tall
+    box turned into a copper-like mirror (smooth conductor): camera segments that end on them continue as specular chains
+    (vrlIntegrator.cpp:445-511)."""
+    m = _Mesh()
+    m.quad((0, 0, 0), (0, 0, 1), (1, 0, 1), (1, 0, 0), WHITE)
+    m.quad((0, 1, 0), (1, 1, 0), (1, 1, 1), (0, 1, 1), WHITE)
+    m.quad((0, 0, 1), (0, 1, 1), (1, 1, 1), (1, 0, 1), WHITE)
+    m.quad((0, 0, 0), (0, 1, 0), (0, 1, 1), (0, 0, 1), RED)
+    m.quad((1, 0, 0), (1, 0, 1), (1, 1, 1), (1, 1, 0), GREEN)
+    GLASS, MIRROR = 3, 4
+    m.box((0.33, 0.15, 0.33), (0.15, 0.15, 0.15), 17.0, WHITE)
+    m.box((0.67, 0.30, 0.64), (0.15, 0.30, 0.15), -18.0, MIRROR)
+    v0, t0, m0 = m.arrays()
+    sv, sf = _icosphere(2)
+    verts = (np.array([0.36, 0.52, 0.30]) + 0.17 * sv).astype(np.float32)
+    faces = (sf + len(v0)).astype(np.uint32)
+    v = np.concatenate([v0, verts]); t = np.concatenate([t0, faces]); mm = np.concatenate([m0, np.full(len(faces), GLASS, np.uint32)])
+    albedo = np.concatenate([_ALBEDO, np.zeros((2, 3), np.float32)])
+    bits = np.array([BSDF_SMOOTH, BSDF_SMOOTH, BSDF_SMOOTH,
+                     BSDF_DIELECTRIC | MAT_TRANSITION | MAT_EXTERIOR_MEDIUM, BSDF_CONDUCTOR], np.uint32)
+    optics = np.zeros((5, 12), np.float32)
+    optics[:, 6:12] = 1.0
+    optics[GLASS, 0] = glass_eta
+    optics[MIRROR, 0:3] = (0.27, 0.68, 1.22)          # eta, k of a copper-like conductor (rgb)
+    optics[MIRROR, 3:6] = (3.61, 2.63, 2.29)
+    cam = perspective_camera(width, height, origin=(0.5, 0.5, -1.4), target=(0.5, 0.5, 0.0), fov=40.0)
+    return dict(verts=v, tris=t, tri_material=mm, albedo=albedo, mat_bits=bits, optics=optics,
                 medium=medium or homogeneous_medium(), camera=cam, extra_bounds=cam["origin"].reshape(1, 3))
 
 

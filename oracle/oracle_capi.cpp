@@ -27,6 +27,8 @@ struct Ctx {
     std::vector<VRL> vrls; uint64_t particleCount = 0;
     std::vector<Ray> rays; std::vector<Intersection> hits;       // per pixel index y + H*x
     bool havePrimary = false;
+    struct ChainSeg { Ray ray; Intersection its; Spec weight; bool inMedium; uint32_t code; };
+    std::vector<std::vector<ChainSeg>> chains; bool haveChains = false; bool anyDelta = false;   // vrlIntegrator.cpp:445-511
     std::vector<uint32_t> pixelToSlice; std::vector<SliceData> slices; bool haveSlices = false;
     std::vector<uint32_t> rowOffset, rowPixel; bool haveRows = false;
     std::vector<Float> sliceUndersampling; Float globalPixelUndersampling = -1;
@@ -85,6 +87,62 @@ void tracePrimary(Ctx *c) {
     c->havePrimary = true;
 }
 
+/* The specular chains of LiInternal (vrlIntegrator.cpp:445-511) below every camera segment whose surface has delta components:
+ * the segments LiInternal recurses into, in its own order (component 0 and everything below it before component 1), each with
+ * the `weight` its VRL contributions are multiplied by.  The roulette draw of a branch (485: rRec.nextSample1D()) comes from the
+ * counter stream of (pixel, path code), path code = 2 * parent's + component, the camera segment being 1. */
+static const int kChainMaxDepth = 30;
+static void chainBelow(Ctx *c, uint32_t pixel, const Ray &ray, const Intersection &its, bool inMedium, Spec throughputWithEtaSq,
+                       Spec weight, int depth, uint32_t code, std::vector<Ctx::ChainSeg> &out) {
+    const uint32_t bits = c->scene.matBits[its.material];
+    if (!(bits & ALVRL_BSDF_DELTA)) return;                                  // 447-448: no specular chains
+    if (c->scene.optics.size() != c->scene.matBits.size()) throw std::runtime_error("delta material without alvrl_set_material_optics");
+    Spec transmittance(1.0f);                                                // 450-459
+    if (inMedium) { MediumSamplingRecord mRec; c->medium.eval(Ray(ray.o, ray.d, 0, its.t), mRec); transmittance = mRec.transmittance; }
+    if (transmittance.isZero()) return;
+    if (depth > kChainMaxDepth) return;
+    const HitFrame fr = c->scene.hitFrame(its);
+    const V3 wi = fr.toLocal(-ray.d);                                        // skdtree.h:427
+    const int compCount = (bits & ALVRL_BSDF_DIELECTRIC) ? 2 : 1;
+    for (int i = 0; i < compCount; i++) {                                    // 467-504
+        V3 wo; Float eta = 1;
+        Spec bsdfWeight = sampleDelta(bits, c->scene.optics[its.material], wi, i, wo, eta);
+        if (bsdfWeight.isZero()) continue;
+        Spec throughputWithEtaSq2 = throughputWithEtaSq * transmittance * bsdfWeight * (eta * eta);
+        Float maxRRprob = depth >= c->P.specularForcedRRdepth ? (Float) 0.98 : (Float) 1;
+        Float rrProb = std::min(maxRRprob, throughputWithEtaSq2.max());
+        const uint32_t childCode = code * 2u + (uint32_t) i;
+        if (rrProb <= 0) continue;
+        if (rrProb < 1) {
+            const Float u = alvrl_rng_uniform(alvrl_rng_key(c->P.seed, ALVRL_RNG_CHAIN, pixel, childCode), 0);
+            if (u > rrProb) continue;
+        }
+        throughputWithEtaSq2 /= rrProb;
+        Ray ray2(its.p, fr.toWorld(wo), Epsilon, std::numeric_limits<Float>::infinity());   // 490: RayDifferential(p, d, time)
+        bool inMedium2 = inMedium;
+        if (bits & ALVRL_MAT_TRANSITION)                                                      // 491-493, records.inl:81-86
+            inMedium2 = dot(ray2.d, its.n) > 0 ? (bits & ALVRL_MAT_EXTERIOR_MEDIUM) != 0 : (bits & ALVRL_MAT_INTERIOR_MEDIUM) != 0;
+        Spec weightSpec = weight * transmittance * bsdfWeight / rrProb;                        // 500
+        Intersection its2;
+        if (!c->scene.rayIntersect(ray2, its2)) continue;                                      // 416-423: an infinite segment adds nothing
+        out.push_back(Ctx::ChainSeg{ray2, its2, weightSpec, inMedium2, childCode});
+        chainBelow(c, pixel, ray2, its2, inMedium2, throughputWithEtaSq2, weightSpec, depth + 1, childCode, out);
+    }
+}
+void traceChains(Ctx *c) {
+    tracePrimary(c);
+    if (c->haveChains) return;
+    const uint32_t P = c->P_();
+    c->chains.assign(P, {});
+    c->anyDelta = false;
+    for (uint32_t b : c->scene.matBits) if (b & ALVRL_BSDF_DELTA) c->anyDelta = true;
+    if (c->anyDelta)
+        for (uint32_t pix = 0; pix < P; pix++)
+            if (c->hits[pix].isValid())       // Li: rRec.newQuery(ESensorRay, sensor medium): depth 1, the camera sits in the medium
+                chainBelow(c, pix, c->rays[pix], c->hits[pix], true, Spec(c->P.initialSpecularThroughput), Spec(1.0f), 1, 1u, c->chains[pix]);
+    c->haveChains = true;
+}
+
 /* getVRLContributions for one row, vrlIntegrator.cpp:792-825 with vrlContributions != NULL */
 void buildRow(Ctx *c, IntegratorCore &core, Sampler *sampler, uint32_t row, VrlContribution *out) {
     uint32_t N = c->vrls.size();
@@ -104,6 +162,22 @@ void buildRow(Ctx *c, IntegratorCore &core, Sampler *sampler, uint32_t row, VrlC
             if (core.grazed && !c->Rgraze.empty()) c->Rgraze[(size_t) row * N + v] = 1;
             out[v].mean += contribution * normalization;
             out[v].var += variance * normalization * normalization;
+        }
+    }
+    /* the chain below the camera segment (LiInternal 462-505 with vrlContributions != NULL): every segment inside the medium
+     * adds its weighted contributions; its draws come from the stream of (row + (ordinal << 24), vrl) */
+    if (c->anyDelta) {
+        const std::vector<Ctx::ChainSeg> &ch = c->chains[pixel];
+        for (size_t e = 0; e < ch.size(); e++) {
+            if (!ch[e].inMedium) continue;
+            for (uint32_t v = 0; v < N; v++) {
+                Float normalization = 1.0 / c->particleCount;
+                Float contribution, variance;
+                sampler->setContext(ALVRL_RNG_R, row + ((uint32_t) (e + 1) << 24), v);
+                core.integrateVRL(ch[e].ray, ch[e].its, c->vrls[v], sampler, &contribution, &variance, ch[e].weight);
+                out[v].mean += contribution * normalization;
+                out[v].var += variance * normalization * normalization;
+            }
         }
     }
 }
@@ -164,6 +238,14 @@ int orc_set_materials(void *h, const float *albedo, const uint32_t *bits, uint32
     c->scene.albedo.resize(nm); c->scene.matBits.assign(bits, bits + nm);
     for (uint32_t i = 0; i < nm; i++) c->scene.albedo[i] = Spec(albedo[3 * i], albedo[3 * i + 1], albedo[3 * i + 2]);
     c->haveMat = true;
+    return ALVRL_OK;
+}
+int orc_set_material_optics(void *h, const float *optics, uint32_t nm) {
+    Ctx *c = (Ctx *) h;
+    if (!c->haveMat || nm != c->scene.matBits.size()) return seterr(ALVRL_ERR_ARG, "set_material_optics: set_materials first, same count");
+    c->scene.optics.resize(nm);
+    for (uint32_t i = 0; i < nm; i++) memcpy(c->scene.optics[i].v, optics + 12 * (size_t) i, 12 * sizeof(float));
+    c->havePrimary = false; c->haveChains = false;
     return ALVRL_OK;
 }
 int orc_set_extra_bounds(void *h, const float *p, uint32_t n) {
@@ -327,7 +409,7 @@ static int buildR_impl(Ctx *c, std::vector<float> *recordTape) {
     if (!c->haveRows || !c->haveVrls || !c->haveMedium) return seterr(ALVRL_ERR_STATE, "sample_slice_mapping / set_vrls / set_medium first");
     ORC_TRY
     double t0 = now_ms();
-    tracePrimary(c);
+    traceChains(c);
     uint32_t N = c->vrls.size(), G = c->rowPixel.size(), S = c->slices.size();
     c->R.assign((size_t) G * N, VrlContribution{0, 0});
     if (c->grazeTol > 0) c->Rgraze.assign((size_t) G * N, 0); else c->Rgraze.clear();
@@ -531,7 +613,7 @@ int orc_prepass(void *h) {
 static int render_impl(Ctx *c, float *rgb, bool clustered, const uint32_t *pixelSubset, uint32_t nSubset) {
     ORC_TRY
     double t0 = now_ms();
-    tracePrimary(c);
+    traceChains(c);
     uint32_t W = c->cam.W, H = c->cam.H, P = W * H, N = c->vrls.size();
     uint32_t count = pixelSubset ? nSubset : P;
     if (!pixelSubset) for (size_t i = 0; i < (size_t) P * 3; i++) rgb[i] = 0;
@@ -559,6 +641,19 @@ static int render_impl(Ctx *c, float *rgb, bool clustered, const uint32_t *pixel
                     }
                     Li /= (Float) c->particleCount;
                     pairs[t] += vr.size();
+                    /* LiSpec (462-505): the chain's segments use the slice of the original camera ray (552-566) and carry their weight */
+                    if (c->anyDelta) for (size_t e = 0; e < c->chains[pix].size(); e++) {
+                        const Ctx::ChainSeg &cs = c->chains[pix][e];
+                        if (!cs.inMedium) continue;
+                        Spec LiS(0.0f);
+                        for (size_t i = 0; i < vr.size(); i++) {
+                            smp.setContext(ALVRL_RNG_RENDER, pix + ((uint32_t) (e + 1) << 24), (uint32_t) i);
+                            LiS += wt.at(i) * core.integrateVRL(cs.ray, cs.its, c->vrls[vr.at(i)], &smp, nullptr, nullptr);
+                        }
+                        LiS /= (Float) c->particleCount;
+                        Li += LiS * cs.weight;                                // 598: return Li * weight
+                        pairs[t] += vr.size();
+                    }
                 } else {
                     for (uint32_t v = 0; v < N; v++) {                       // getVRLContributions, 803-816
                         Float normalization = 1.0 / c->particleCount;
@@ -568,6 +663,18 @@ static int render_impl(Ctx *c, float *rgb, bool clustered, const uint32_t *pixel
                         Li += vc;
                     }
                     pairs[t] += N;
+                    if (c->anyDelta) for (size_t e = 0; e < c->chains[pix].size(); e++) {      // 462-505 around getVRLContributions
+                        const Ctx::ChainSeg &cs = c->chains[pix][e];
+                        if (!cs.inMedium) continue;
+                        for (uint32_t v = 0; v < N; v++) {
+                            Float normalization = 1.0 / c->particleCount;
+                            smp.setContext(ALVRL_RNG_RENDER, pix + ((uint32_t) (e + 1) << 24), v);
+                            Spec vc = core.integrateVRL(cs.ray, cs.its, c->vrls[v], &smp, nullptr, nullptr, cs.weight);
+                            vc *= normalization;
+                            Li += vc;
+                        }
+                        pairs[t] += N;
+                    }
                 }
             }
             float *o = pixelSubset ? rgb + 3 * (size_t) q : rgb + 3 * ((size_t) y * W + x);
@@ -736,6 +843,89 @@ int orc_integrate_pair(void *h, uint32_t pixel, uint32_t vrl, const float *unifo
     if (c->hits[pixel].isValid()) s = core.integrateVRL(c->rays[pixel], c->hits[pixel], c->vrls[vrl], &smp, &m, &v);
     out[0] = m; out[1] = v; out[2] = s[0]; out[3] = s[1]; out[4] = s[2];
     ORC_CATCH
+}
+
+/* the chain segments below the camera segments, grouped by pixel (layout: include/alvrl.h::alvrl_get_chain_segments) */
+int orc_get_chain_segments(void *h, uint32_t *offset, float *segs) {
+    Ctx *c = (Ctx *) h;
+    ORC_TRY
+    traceChains(c);
+    const uint32_t P = c->P_();
+    uint32_t total = 0;
+    for (uint32_t pix = 0; pix < P; pix++) {
+        offset[pix] = total;
+        for (const Ctx::ChainSeg &cs : c->chains[pix]) {
+            if (segs) {
+                float *o = segs + 16 * (size_t) total;
+                o[0] = cs.ray.o.x; o[1] = cs.ray.o.y; o[2] = cs.ray.o.z; o[3] = cs.ray.d.x; o[4] = cs.ray.d.y; o[5] = cs.ray.d.z;
+                o[6] = cs.its.p.x; o[7] = cs.its.p.y; o[8] = cs.its.p.z; o[9] = distance(cs.its.p, cs.ray.o);
+                o[10] = cs.weight[0]; o[11] = cs.weight[1]; o[12] = cs.weight[2]; o[13] = cs.inMedium ? 1.0f : 0.0f;
+                o[14] = (float) cs.code; o[15] = (float) cs.its.material;
+            }
+            total++;
+        }
+    }
+    offset[P] = total;
+    ORC_CATCH
+}
+
+/* Film: ReconstructionFilter::configure / evalDiscretized (src/libcore/rfilter.cpp:37-55, include/mitsuba/core/rfilter.h:76-77),
+ * ImageBlock::put for one sample per pixel centre (include/mitsuba/render/imageblock.h:144-185; the film is one block, samples
+ * put in raster order), the division by the weight channel of Bitmap::convertMultiSpectrumAlphaWeight (bitmap.cpp:1617-1624).
+ * frames: nPasses images [y][x][c]; out: the developed film. */
+int orc_film(uint32_t W, uint32_t H, int filter, float param, const float *frames, uint32_t nPasses, float *out) {
+    const int RES = 31;                                                    // MTS_FILTER_RESOLUTION
+    Float radius, stddev = 0.5f;
+    if (filter == ALVRL_FILTER_BOX) radius = (param > 0 ? param : 0.5f) + 1e-5f;        // box.cpp:38
+    else if (filter == ALVRL_FILTER_TENT) radius = 1.0f;                               // tent.cpp:34
+    else if (filter == ALVRL_FILTER_GAUSSIAN) { stddev = param > 0 ? param : 0.5f; radius = 4 * stddev; }   // gaussian.cpp:30-35
+    else return seterr(ALVRL_ERR_ARG, "unknown filter");
+    auto eval = [&](Float x) -> Float {
+        if (filter == ALVRL_FILTER_BOX) return std::abs(x) <= radius ? 1.0f : 0.0f;    // box.cpp:46-48
+        if (filter == ALVRL_FILTER_TENT) return std::max((Float) 0.0f, 1.0f - std::abs(x / radius));   // tent.cpp:42-44
+        Float alpha = -1.0f / (2.0f * stddev * stddev);                                // gaussian.cpp:52-58
+        return std::max((Float) 0.0f, fastexp(alpha * x * x) - fastexp(alpha * radius * radius));
+    };
+    Float values[RES + 1], sum = 0.0f;
+    for (int i = 0; i < RES; ++i) { Float value = eval((radius * i) / RES); values[i] = value; sum += value; }
+    values[RES] = 0.0f;
+    const Float scaleFactor = RES / radius;
+    sum *= 2 * radius / RES;
+    const Float normalization = 1.0f / sum;
+    for (int i = 0; i < RES; ++i) values[i] *= normalization;
+    auto evalDiscretized = [&](Float x) { return values[std::min((int) std::abs(x * scaleFactor), RES)]; };
+
+    const int channels = 5;
+    std::vector<Float> bitmap((size_t) W * H * channels, 0.0f);
+    std::vector<Float> weightsX(2 * (size_t) std::ceil(radius) + 2), weightsY(weightsX.size());
+    for (uint32_t pass = 0; pass < nPasses; pass++) {
+        const float *img = frames + (size_t) pass * W * H * 3;
+        for (uint32_t sy = 0; sy < H; sy++) for (uint32_t sx = 0; sx < W; sx++) {
+            const float *v = img + ((size_t) sy * W + sx) * 3;
+            const Float value[5] = {v[0], v[1], v[2], 1.0f, 1.0f};
+            bool bad = false;
+            for (int i = 0; i < channels; ++i) if (!std::isfinite(value[i]) || value[i] < 0) bad = true;     // 147-151
+            if (bad) continue;
+            const Float posx = (sx + 0.5f) - 0.5f, posy = (sy + 0.5f) - 0.5f;         // offset 0, border cropped by the film
+            const int minx = std::max((int) std::ceil(posx - radius), 0), miny = std::max((int) std::ceil(posy - radius), 0),
+                      maxx = std::min((int) std::floor(posx + radius), (int) W - 1), maxy = std::min((int) std::floor(posy + radius), (int) H - 1);
+            for (int x = minx, idx = 0; x <= maxx; ++x) weightsX[idx++] = evalDiscretized(x - posx);
+            for (int y = miny, idx = 0; y <= maxy; ++y) weightsY[idx++] = evalDiscretized(y - posy);
+            for (int y = miny, yr = 0; y <= maxy; ++y, ++yr) {
+                const Float weightY = weightsY[yr];
+                Float *dest = bitmap.data() + ((size_t) y * W + minx) * channels;
+                for (int x = minx, xr = 0; x <= maxx; ++x, ++xr) {
+                    const Float weight = weightsX[xr] * weightY;
+                    for (int k = 0; k < channels; ++k) *dest++ += weight * value[k];
+                }
+            }
+        }
+    }
+    for (size_t k = 0; k < (size_t) W * H; k++) {
+        const Float weight = bitmap[k * channels + 4], invWeight = weight == 0 ? 0 : (Float) 1 / weight;
+        for (int i = 0; i < 3; i++) out[3 * k + i] = bitmap[k * channels + i] * invWeight;
+    }
+    return ALVRL_OK;
 }
 
 } // extern "C"

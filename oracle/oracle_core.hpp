@@ -356,11 +356,16 @@ struct Intersection {
     bool isValid() const { return t != std::numeric_limits<Float>::infinity(); }
 };
 
+/* per-material optics (include/alvrl.h::alvrl_set_material_optics): dielectric eta = intIOR / extIOR in [0]; conductor
+ * eta rgb in [0..2], k rgb in [3..5]; specularReflectance [6..8], specularTransmittance [9..11] */
+struct Optics { Float v[12]; };
+
 struct Scene {
     std::vector<V3> verts;
     std::vector<uint32_t> tris, triMat;
     std::vector<Spec> albedo;
     std::vector<uint32_t> matBits;
+    std::vector<Optics> optics;
     std::vector<TriAccel> accel;
     std::vector<V3> extraBounds;
     AABB kdAABB, sceneAABB;
@@ -429,6 +434,9 @@ struct Scene {
         return loose && !robust;
     }
     /* ShapeKDTree::rayIntersect(ray, its) + fillIntersectionRecord<true> (skdtree.cpp:112-142, skdtree.h:343-428) */
+    /* shading frame of a triangle hit: n = face normal, s = normalize(dpdu - n dot(n, dpdu)) with dpdu = p1 - p0, t = cross(n, s)
+     * (skdtree.h:367-378,395-396,426; util.cpp:603-608) */
+    struct HitFrame hitFrame(const Intersection &its) const;
     bool rayIntersect(const Ray &ray, Intersection &its) {
         Float u = 0, v = 0;
         its = Intersection();
@@ -446,6 +454,65 @@ struct Scene {
         return true;
     }
 };
+
+/* ---- delta BSDFs of the specular chains (vrlIntegrator.cpp:445-511) --------------------------- */
+/* fresnelDielectricExt, src/libcore/util.cpp:651-681 */
+inline Float fresnelDielectricExt(Float cosThetaI_, Float &cosThetaT_, Float eta) {
+    if (eta == 1) { cosThetaT_ = -cosThetaI_; return 0.0f; }
+    Float scale = (cosThetaI_ > 0) ? 1 / eta : eta, cosThetaTSqr = 1 - (1 - cosThetaI_ * cosThetaI_) * (scale * scale);
+    if (cosThetaTSqr <= 0.0f) { cosThetaT_ = 0.0f; return 1.0f; }
+    Float cosThetaI = std::abs(cosThetaI_);
+    Float cosThetaT = std::sqrt(cosThetaTSqr);
+    Float Rs = (cosThetaI - eta * cosThetaT) / (cosThetaI + eta * cosThetaT);
+    Float Rp = (eta * cosThetaI - cosThetaT) / (eta * cosThetaI + cosThetaT);
+    cosThetaT_ = (cosThetaI_ > 0) ? -cosThetaT : cosThetaT;
+    return 0.5f * (Rs * Rs + Rp * Rp);
+}
+/* fresnelConductorExact, util.cpp:739-761, one channel */
+inline Float fresnelConductorExact(Float cosThetaI, Float eta, Float k) {
+    Float cosThetaI2 = cosThetaI * cosThetaI, sinThetaI2 = 1 - cosThetaI2, sinThetaI4 = sinThetaI2 * sinThetaI2;
+    Float temp1 = eta * eta - k * k - sinThetaI2, a2pb2 = safe_sqrt(temp1 * temp1 + k * k * eta * eta * 4), a = safe_sqrt((a2pb2 + temp1) * 0.5f);
+    Float term1 = a2pb2 + cosThetaI2, term2 = a * (2 * cosThetaI);
+    Float Rs2 = (term1 - term2) / (term1 + term2);
+    Float term3 = a2pb2 * cosThetaI2 + sinThetaI4, term4 = term2 * sinThetaI2;
+    Float Rp2 = Rs2 * (term3 - term4) / (term3 + term4);
+    return 0.5f * (Rp2 + Rs2);
+}
+/* Frame of a triangle hit: shFrame.n = face normal, s and t from computeShadingFrame(n, dpdu = p1 - p0) (skdtree.h:367-426,
+ * util.cpp:603-608) */
+struct HitFrame {
+    V3 s, t, n;
+    V3 toLocal(const V3 &v) const { return V3(dot(v, s), dot(v, t), dot(v, n)); }
+    V3 toWorld(const V3 &v) const { return s * v.x + t * v.y + n * v.z; }
+};
+inline HitFrame Scene::hitFrame(const Intersection &its) const {
+    const V3 &p0 = verts[tris[3 * its.prim]], &p1 = verts[tris[3 * its.prim + 1]];
+    HitFrame f; f.n = its.n;
+    const V3 dpdu = p1 - p0;
+    f.s = normalize(dpdu - f.n * dot(f.n, dpdu));
+    f.t = cross(f.n, f.s);
+    return f;
+}
+/* BSDF::sample(bRec, Point2(0.5)) with bRec.component = comp, mode = ERadiance, of the smooth dielectric (dielectric.cpp:335-387,
+ * 218-226) and the smooth conductor (conductor.cpp:254-268).  Returns the weight, fills wo (local) and eta. */
+inline Spec sampleDelta(uint32_t bits, const Optics &o, const V3 &wi, int comp, V3 &wo, Float &etaOut) {
+    const Spec specR(o.v[6], o.v[7], o.v[8]), specT(o.v[9], o.v[10], o.v[11]);
+    if (bits & ALVRL_BSDF_DIELECTRIC) {
+        const Float eta = o.v[0], invEta = 1 / eta;
+        Float cosThetaT;
+        Float F = fresnelDielectricExt(wi.z, cosThetaT, eta);
+        if (comp == 0) { wo = V3(-wi.x, -wi.y, wi.z); etaOut = 1.0f; return specR * F; }
+        Float scale = -(cosThetaT < 0 ? invEta : eta);
+        wo = V3(scale * wi.x, scale * wi.y, cosThetaT);
+        etaOut = cosThetaT < 0 ? eta : invEta;
+        Float factor = cosThetaT < 0 ? invEta : eta;                        // ERadiance
+        return specT * (factor * factor * (1 - F));
+    }
+    /* conductor: one component */
+    if (comp != 0 || wi.z <= 0) return Spec(0.0f);
+    wo = V3(-wi.x, -wi.y, wi.z); etaOut = 1.0f;
+    return specR * Spec(fresnelConductorExact(wi.z, o.v[0], o.v[3]), fresnelConductorExact(wi.z, o.v[1], o.v[4]), fresnelConductorExact(wi.z, o.v[2], o.v[5]));
+}
 
 /* ---- sensor: src/sensors/perspective.cpp:247-269 ---------------------------------------- */
 struct Camera {

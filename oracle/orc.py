@@ -37,6 +37,20 @@ def api(fast=False):
     return _api[fast]
 
 
+def film(frames, filter, param=0.0):
+    """frames: [passes, H, W, 3] (or one [H, W, 3] frame) -> developed film [H, W, 3] (orc_film: rfilter table, ImageBlock::put
+    in raster order, weight division)"""
+    fr = np.ascontiguousarray(frames, dtype=np.float32)
+    if fr.ndim == 3:
+        fr = fr[None]
+    n, H, W, _ = fr.shape
+    out = np.zeros((H, W, 3), np.float32)
+    rc = api().lib.orc_film(C.c_uint32(W), C.c_uint32(H), C.c_int(filter), C.c_float(param), binding._p(fr), C.c_uint32(n), binding._p(out))
+    if rc != 0:
+        raise RuntimeError("orc_film failed")
+    return out
+
+
 class Oracle(binding.Integrator):
     def __init__(self, fast=False, threads=None, **params):
         super().__init__(api(fast), 0, **params)
