@@ -700,10 +700,16 @@ int alvrl_build_R(alvrl_handle c) {
     c->dRowSegs.alloc(G);
     launch_gather_rows(c->dPixSegs.p, c->dRowPixel.p, G, c->dRowSegs.p, c->stream);
     c->stats.kernelLaunches++;
-    c->ldR = (G + 31u) & ~31u;
     /* every entry of the rows this handle owns is written by the kernel (inactive rows store zeros), and nothing reads the
-     * others (alvrl_get_R answers zeros for them): no 13 GB memset per frame */
-    c->dR.alloc((size_t) N * c->ldR);
+     * others (alvrl_get_R answers zeros for them): no 13 GB memset per frame, and no storage for rows of other ranks */
+    {
+        const uint32_t sb_ = std::min(c->sliceBegin, S), se_ = std::min(c->sliceEnd, S);
+        const uint32_t a = c->rowOffset[sb_] & ~31u, b = c->rowOffset[se_];
+        c->rShift = a;
+        c->ldR = std::max(32u, (b - a + 31u) & ~31u);
+        c->dRstore.alloc((size_t) N * c->ldR);
+        c->dR.p = c->dRstore.p - a;
+    }
     TransportParams T = make_transport_params(c, ALVRL_RNG_R);
     if (!c->userTape.empty()) {
         if (c->userTape.size() < (uint64_t) G * N * c->K()) throw Error(ALVRL_ERR_ARG, "sample tape too short: need G*N*(2*Nvv+Nvs) floats");
@@ -1008,12 +1014,12 @@ int alvrl_get_R(alvrl_handle c, uint32_t r0, uint32_t r1, float *mv) {
     if (!c->haveR) throw Error(ALVRL_ERR_STATE, "build_R first");
     if (r0 > r1 || r1 > c->rowPixel.size()) throw Error(ALVRL_ERR_ARG, "get_R: row range out of bounds");
     const uint32_t N = (uint32_t) c->vrlHost.size();
-    std::vector<float2> col(c->ldR);
+    std::vector<float2> col(c->rowPixel.size() + 32);
     /* rows outside the range this handle built (slice sharding) were never written: they read as zeros */
     const uint32_t b0 = std::max(r0, c->builtRow0), b1 = std::min(r1, c->builtRow1);
     for (uint32_t v = 0; v < N; v++) {
         std::fill(col.begin() + r0, col.begin() + r1, make_float2(0, 0));
-        if (b0 < b1) c->dR.download(col.data() + b0, b1 - b0, c->stream, (size_t) v * c->ldR + b0);
+        if (b0 < b1) c->dRstore.download(col.data() + b0, b1 - b0, c->stream, (size_t) v * c->ldR + b0 - c->rShift);
         for (uint32_t r = r0; r < r1; r++) { mv[((size_t) (r - r0) * N + v) * 2] = col[r].x; mv[((size_t) (r - r0) * N + v) * 2 + 1] = col[r].y; }
     }
     API_END
@@ -1027,7 +1033,7 @@ int alvrl_set_R(alvrl_handle c, const float *mv) {
     std::vector<float2> t((size_t) N * c->ldR, make_float2(0, 0));
     for (uint32_t r = 0; r < G; r++)
         for (uint32_t v = 0; v < N; v++) t[(size_t) v * c->ldR + r] = make_float2(mv[((size_t) r * N + v) * 2], mv[((size_t) r * N + v) * 2 + 1]);
-    c->dR.upload(t, c->stream);
+    c->dRstore.upload(t, c->stream); c->dR.p = c->dRstore.p; c->rShift = 0;
     c->builtRow0 = 0; c->builtRow1 = G;
     c->haveR = true; c->haveClusters = false; c->haveFallback = false;
     API_END

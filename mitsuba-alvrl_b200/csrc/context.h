@@ -166,7 +166,10 @@ struct alvrl_ctx {
     uint32_t sliceBegin = 0, sliceEnd = 0xffffffffu;
 
     /* R (column-major, see types.h) */
-    alvrl::DevBuf<float2> dR; uint32_t ldR = 0; bool haveR = false;
+    /* R: only the rows of the handle's slice range are stored (C5: 1 TB over all rows).  dR.p is the address row 0 WOULD have,
+     * so that every consumer keeps indexing dR.p[vrl * ldR + global row]; rows outside [builtRow0, builtRow1) do not exist */
+    alvrl::DevBuf<float2> dRstore; struct { float2 *p = nullptr; } dR; uint32_t rShift = 0;
+    uint32_t ldR = 0; bool haveR = false;
     uint32_t builtRow0 = 0, builtRow1 = 0;          /* rows of R the last build_R / set_R wrote */
     alvrl::DevBuf<float> dTape; uint32_t tapeK = 0; std::vector<float> userTape;
 

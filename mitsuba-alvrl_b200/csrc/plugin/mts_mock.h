@@ -51,7 +51,13 @@ private:
 };
 
 /* what preprocess() reads from `const Scene *` (triangle meshes with diffuse BSDFs, one medium, a perspective sensor) */
-struct TriMeshView { const float *positions; uint32_t vertexCount; const uint32_t *indices; uint32_t triangleCount; float reflectance[3]; bool smooth; };
+/* bsdf: 0 diffuse (reflectance), 1 smooth dielectric (eta = intIOR / extIOR), 2 smooth conductor (eta, k rgb); the shape's
+ * interior / exterior medium is the scene's medium or none (Shape::getInteriorMedium / getExteriorMedium) */
+struct TriMeshView {
+    const float *positions; uint32_t vertexCount; const uint32_t *indices; uint32_t triangleCount; float reflectance[3]; bool smooth;
+    int bsdf = 0; float eta[3] = {1, 1, 1}, k[3] = {0, 0, 0}, specularReflectance[3] = {1, 1, 1}, specularTransmittance[3] = {1, 1, 1};
+    bool mediumTransition = false, interiorMedium = false, exteriorMedium = false;
+};
 struct MediumView {
     bool homogeneous; float sigmaA[3], sigmaS[3]; float mediumSamplingWeight; int phaseType; float g;
     const float *grid; int res[3]; float bboxMin[3], bboxMax[3]; float scale; float albedo[3];

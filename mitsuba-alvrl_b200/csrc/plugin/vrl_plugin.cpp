@@ -74,7 +74,8 @@ public:
                           "medium where all VRLs will 'live'");
         chk(alvrl_create(m_device, &m_p, &m_h));
         /* triangle soup + one diffuse material per mesh */
-        std::vector<float> verts, albedo; std::vector<uint32_t> tris, mat, bits;
+        std::vector<float> verts, albedo, optics; std::vector<uint32_t> tris, mat, bits;
+        bool anyDelta = false;
         for (size_t m = 0; m < scene->meshes.size(); m++) {
             const mts::TriMeshView &tm = scene->meshes[m];
             const uint32_t base = (uint32_t) (verts.size() / 3);
@@ -82,10 +83,20 @@ public:
             for (uint32_t i = 0; i < 3 * tm.triangleCount; i++) tris.push_back(base + tm.indices[i]);
             mat.insert(mat.end(), tm.triangleCount, (uint32_t) m);
             albedo.insert(albedo.end(), tm.reflectance, tm.reflectance + 3);
-            bits.push_back(tm.smooth ? ALVRL_BSDF_SMOOTH : 0u);
+            /* BSDF type bits (bsdf.h:230-284) and the media on the two sides of the shape (shape.h:427-433): what the specular
+             * chains of LiInternal read (vrlIntegrator.cpp:445-511) */
+            uint32_t b = tm.smooth ? ALVRL_BSDF_SMOOTH : 0u;
+            if (tm.bsdf == 1) b = ALVRL_BSDF_DIELECTRIC; else if (tm.bsdf == 2) b = ALVRL_BSDF_CONDUCTOR;
+            if (tm.mediumTransition) b |= ALVRL_MAT_TRANSITION | (tm.interiorMedium ? ALVRL_MAT_INTERIOR_MEDIUM : 0u) | (tm.exteriorMedium ? ALVRL_MAT_EXTERIOR_MEDIUM : 0u);
+            anyDelta = anyDelta || (b & ALVRL_BSDF_DELTA);
+            bits.push_back(b);
+            const float o[12] = {tm.eta[0], tm.eta[1], tm.eta[2], tm.k[0], tm.k[1], tm.k[2], tm.specularReflectance[0], tm.specularReflectance[1],
+                                 tm.specularReflectance[2], tm.specularTransmittance[0], tm.specularTransmittance[1], tm.specularTransmittance[2]};
+            optics.insert(optics.end(), o, o + 12);
         }
         chk(alvrl_set_mesh(m_h, verts.data(), (uint32_t) (verts.size() / 3), tris.data(), (uint32_t) (tris.size() / 3), mat.data()));
         chk(alvrl_set_materials(m_h, albedo.data(), bits.data(), (uint32_t) bits.size()));
+        if (anyDelta) chk(alvrl_set_material_optics(m_h, optics.data(), (uint32_t) bits.size()));
         chk(alvrl_set_extra_bounds(m_h, scene->sensor.position, 1));                                    /* scene.cpp:387-413 */
         const mts::MediumView &md = scene->media[0];
         if (md.homogeneous) chk(alvrl_set_medium_homogeneous(m_h, md.sigmaA, md.sigmaS, md.mediumSamplingWeight, md.phaseType, md.g));
@@ -141,6 +152,13 @@ int alvrl_plugin_create(void *props, void **inst, char *err, int errLen) {
  * integrator.cpp:380-440) -- with a Film that hands the image back */
 void *alvrl_plugin_scene_new() { return new mts::Scene(); }
 void alvrl_plugin_scene_free(void *s) { delete static_cast<mts::Scene *>(s); }
+/* the BSDF and media of the mesh added last: bsdf 1 = dielectric (eta[0] = intIOR / extIOR), 2 = conductor (eta, k rgb) */
+void alvrl_plugin_scene_set_mesh_bsdf(void *s, int bsdf, const float *eta, const float *k, int mediumTransition, int interiorMedium, int exteriorMedium) {
+    mts::TriMeshView &m = static_cast<mts::Scene *>(s)->meshes.back();
+    m.bsdf = bsdf; m.smooth = bsdf == 0;
+    for (int i = 0; i < 3; i++) { m.eta[i] = eta ? eta[i] : 1.0f; m.k[i] = k ? k[i] : 0.0f; }
+    m.mediumTransition = mediumTransition != 0; m.interiorMedium = interiorMedium != 0; m.exteriorMedium = exteriorMedium != 0;
+}
 void alvrl_plugin_scene_add_mesh(void *s, const float *positions, uint32_t nv, const uint32_t *indices, uint32_t nt, const float *reflectance, int smooth) {
     mts::TriMeshView m; m.positions = positions; m.vertexCount = nv; m.indices = indices; m.triangleCount = nt;
     m.reflectance[0] = reflectance[0]; m.reflectance[1] = reflectance[1]; m.reflectance[2] = reflectance[2]; m.smooth = smooth != 0;

@@ -121,3 +121,59 @@ def test_plugin_reports_missing_vrl_file(pkg, tmp_path):
     rc = lib.alvrl_plugin_render_frame(inst, sc, img.ctypes.data_as(C.POINTER(C.c_float)), err, 1024)
     assert rc != 0 and b"medium" in err.value           # vrlIntegrator.cpp:244-248: exactly one medium
     lib.alvrl_plugin_destroy(inst); lib.alvrl_plugin_scene_free(sc); lib.alvrl_plugin_props_free(p)
+
+
+def test_plugin_frame_with_specular_chains(pkg, tmp_path):
+    """a glass sphere and a conductor in the scene: the shim marshals BSDF types, optics and the shapes' interior / exterior media
+    (bsdf.h:230-284, shape.h:427-433), and the frame with the specular chains of LiInternal (vrlIntegrator.cpp:445-511) equals
+    the frame of the same calls on the C ABI"""
+    lib = _plugin()
+    scene = pkg.scenes.chain_scene(48, 40)
+    start, end, power, pc = pkg.scenes.synthetic_vrls(96, sigma_t=1.05, seed=3)
+    path = str(tmp_path / "chain.vrl")
+    pkg.scenes.write_vrl_file(path, start, end, power)
+    meshes, flat = _by_material(scene)
+    keep = [m for _, _, _, m in meshes]
+    flat["mat_bits"] = scene["mat_bits"][keep]
+    flat["optics"] = scene["optics"][keep]
+    xml = dict(volVolSamples=2, volSurfSamples=2, targetNumSlices=8, seed=9, vrlFile=path)
+    p = C.c_void_p(lib.alvrl_plugin_props_new())
+    for k, v in xml.items():
+        if isinstance(v, int):
+            lib.alvrl_plugin_props_set_int(p, k.encode(), v)
+        else:
+            lib.alvrl_plugin_props_set_string(p, k.encode(), str(v).encode())
+    inst = C.c_void_p()
+    err = C.create_string_buffer(1024)
+    assert lib.alvrl_plugin_create(p, C.byref(inst), err, 1024) == 0, err.value
+    sc = C.c_void_p(lib.alvrl_plugin_scene_new())
+    fp, up = C.POINTER(C.c_float), C.POINTER(C.c_uint32)
+    S = pkg.scenes
+    for v, t, a, m in meshes:
+        bits = int(scene["mat_bits"][m])
+        lib.alvrl_plugin_scene_add_mesh(sc, v.ctypes.data_as(fp), C.c_uint32(len(v)), t.ctypes.data_as(up), C.c_uint32(len(t)), a.ctypes.data_as(fp), int(bits & 1))
+        if bits & (S.BSDF_DIELECTRIC | S.BSDF_CONDUCTOR):
+            eta = np.ascontiguousarray(scene["optics"][m, 0:3], np.float32); kk = np.ascontiguousarray(scene["optics"][m, 3:6], np.float32)
+            lib.alvrl_plugin_scene_set_mesh_bsdf(sc, 1 if bits & S.BSDF_DIELECTRIC else 2, eta.ctypes.data_as(fp), kk.ctypes.data_as(fp),
+                                                 int(bool(bits & S.MAT_TRANSITION)), int(bool(bits & S.MAT_INTERIOR_MEDIUM)), int(bool(bits & S.MAT_EXTERIOR_MEDIUM)))
+    med = scene["medium"]
+    sa, ss = np.ascontiguousarray(med["sigmaA"], np.float32), np.ascontiguousarray(med["sigmaS"], np.float32)
+    lib.alvrl_plugin_scene_add_medium_homogeneous(sc, sa.ctypes.data_as(fp), ss.ctypes.data_as(fp), C.c_float(-1.0), 0, C.c_float(0.0))
+    cam = scene["camera"]
+    s2c = np.ascontiguousarray(cam["sampleToCamera"], np.float32).reshape(16)
+    c2w = np.ascontiguousarray(cam["cameraToWorld"], np.float32).reshape(16)
+    pos = np.ascontiguousarray(cam["origin"], np.float32)
+    W, H = cam["width"], cam["height"]
+    lib.alvrl_plugin_scene_set_sensor(sc, s2c.ctypes.data_as(fp), c2w.ctypes.data_as(fp), C.c_uint32(W), C.c_uint32(H),
+                                      C.c_float(cam["near"]), C.c_float(cam["far"]), pos.ctypes.data_as(fp))
+    img_plugin = np.zeros((H, W, 3), np.float32)
+    assert lib.alvrl_plugin_render_frame(inst, sc, img_plugin.ctypes.data_as(fp), err, 1024) == 0, err.value
+    lib.alvrl_plugin_destroy(inst); lib.alvrl_plugin_scene_free(sc); lib.alvrl_plugin_props_free(p)
+
+    g = pkg.integrator(0, **{k: v for k, v in xml.items() if k != "vrlFile"})
+    g.set_scene(flat)
+    g.load_vrl_file(path)
+    off, _ = g.chain_segments()
+    assert off[-1] > 100                                  # the chains exist
+    g.build_slices(); g.prepass()
+    assert np.array_equal(img_plugin, g.render())
