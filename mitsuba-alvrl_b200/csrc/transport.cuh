@@ -418,8 +418,11 @@ struct TileSmem {
  * "Building R" (vrlIntegrator.cpp:302-337,792-825): rows = representative-pixel segments, columns = VRLs.
  * grid.x = row blocks of 128, grid.y = VRL chunks of vrlsPerCta (multiple of the tile size).
  */
+/* (the grid-medium kernels wait for memory: measured with 5 CTAs per SM and 96 registers they lose 60 % against 8 CTAs with
+ * spills -- the march needs warps in flight more than registers) */
+#define ALVRL_MIN_CTAS_MED(MED) ALVRL_MIN_CTAS
 template <int MED, int SMALL, bool WEIGHTED>
-__global__ void __launch_bounds__(ALVRL_CTA_SEGS, ALVRL_MIN_CTAS) ALVRL_NAME(k_build_R)(TransportParams P, const SegRec *__restrict__ rowSegs, uint32_t numRows,
+__global__ void __launch_bounds__(ALVRL_CTA_SEGS, ALVRL_MIN_CTAS_MED(MED)) ALVRL_NAME(k_build_R)(TransportParams P, const SegRec *__restrict__ rowSegs, uint32_t numRows,
                                                                        const VrlRec *__restrict__ vrls, float2 *__restrict__ R, uint32_t ldR,
                                                                        uint32_t vrlsPerCta, const uint32_t *__restrict__ rowKey) {
 #ifdef ALVRL_FAST
@@ -523,7 +526,7 @@ __global__ void __launch_bounds__(ALVRL_CTA_SEGS, ALVRL_MIN_CTAS) ALVRL_NAME(k_b
  * weight in e.w) stream through the same TMA tile pipeline.  work[cta] = {slice, firstPixel, pixelCount, 0}.
  */
 template <int MED, bool CLUSTERED, int SMALL>
-__global__ void __launch_bounds__(ALVRL_CTA_SEGS, ALVRL_MIN_CTAS) ALVRL_NAME(k_render)(TransportParams P, const SegRec *__restrict__ pixSegs,
+__global__ void __launch_bounds__(ALVRL_CTA_SEGS, ALVRL_MIN_CTAS_MED(MED)) ALVRL_NAME(k_render)(TransportParams P, const SegRec *__restrict__ pixSegs,
                                                                       const uint32_t *__restrict__ slicePixels, const uint4 *__restrict__ work,
                                                                       const VrlRec *__restrict__ repRecs, const uint32_t *__restrict__ repOffset,
                                                                       float4 *__restrict__ fb, uint32_t W, uint32_t H, const uint32_t *__restrict__ segKey) {

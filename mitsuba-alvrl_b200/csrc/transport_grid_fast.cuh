@@ -9,13 +9,17 @@
  * the warp waiting for its longest ray.  Here the 32 lanes of a warp march ONE ray together: lane l evaluates the Simpson nodes
  * l, l + 32, ... and a shuffle reduction adds the weighted densities.  Consecutive nodes are half a voxel apart, so one load
  * instruction of the warp touches a few neighbouring sectors instead of 32 unrelated ones, and the lanes stay busy whatever
- * the lengths of the 32 rays.  The quadrature is the reference's -- the same nodes (up to the rounding of o + i * inc against
- * the reference's running p += inc), the same weights, the same early exit: the running sum of non-negative densities is
+ * the lengths of the 32 rays.  The quadrature is the reference's -- the same nodes (the reference's running fp32 positions, reproduced in
+ * closed form for the long rays: CoordRun below), the same weights, the same early exit: the running sum of non-negative densities is
  * monotone, so "passed the threshold at some node" == "the complete sum passes it" -- summed in a different order (relative
  * 1e-6 on the optical depth); tests/test_c2_parity_gpu.py::test_other_config_shapes_R_vs_oracle_1e4[C3-fast] holds it to the
  * oracle at 1e-4 per R entry.
  */
 #pragma once
+
+#ifndef ALVRL_DRIFT_MIN_STEPS
+#define ALVRL_DRIFT_MIN_STEPS 320u      /* rays with fewer Simpson nodes use o + i * inc: their drift is below 10^-5 */
+#endif
 
 /* GridDataSource::lookupFloat in grid coordinates (g = gsc * p + gtr already applied), FMA lerps, one 64-bit base address */
 __device__ __forceinline__ float grid_lookup_g(const MediumDev &m, float gx, float gy, float gz) {
@@ -36,6 +40,51 @@ __device__ __forceinline__ float grid_lookup_g(const MediumDev &m, float gx, flo
 __device__ __forceinline__ float grid_lookup_fast(const MediumDev &m, const F3 &p) {
     return grid_lookup_g(m, fmaf(m.gsc[0], p.x, m.gtr[0]), fmaf(m.gsc[1], p.y, m.gtr[1]), fmaf(m.gsc[2], p.z, m.gtr[2]));
 }
+
+/*
+ * The reference marches with a RUNNING position, p += increment in fp32 (heterogeneous.cpp:343-369).  With ~10^3 steps of
+ * ~10^-3 added to coordinates of ~0.5, each add drops the bits of the increment below ulp(p): the positions drift from
+ * o + i * inc by up to n * ulp / 2 (1.5 % of a voxel at 512^3), systematically, and the optical depth moves by a relative
+ * 10^-5 .. 6 * 10^-4 -- more than the tolerance of an R entry on fine grids (measured with exact positions o + i * inc: 4.7 % of
+ * the entries beyond 1e-4 at 384^3, 2.5 % in the 512^3 bench sample; with the running positions below: 0.36 %, the same
+ * near-singular pairs at every resolution).  A lane that evaluates node i directly therefore has to know the reference's
+ * p_i.  It can: while a coordinate stays in one binade, p is a multiple of u = ulp(p) and fl(p + inc) = p + k u with
+ * k = round(inc / u) the same at every step (a tie rounds to even: after one step the mantissa is even and k is the even
+ * neighbour), so p_j = p_s + (j - s) k u exactly; the add that leaves the binade is done as a true fp32 add.  CoordRun holds
+ * the current run of one coordinate; tools/micro/running_sum.py checks the construction against sequential float32
+ * accumulation (12 007 random rays, none differ).
+ */
+struct CoordRun {
+    float pS, u, inc; int iS, iE, k;          /* positions p_j = pS + ((j - iS) * k) * u for j in [iS, iE] */
+    __device__ __forceinline__ void start(float p, int i, int n) {
+        pS = p; iS = i;
+        const uint32_t bits = __float_as_uint(p), eb = (bits >> 23) & 255u;
+        if (eb < 67u) { k = 0; u = 0.0f; iE = i; return; }                    /* |p| < 2^-60: the next add gives the increment itself */
+        u = __uint_as_float((eb - 23u) << 23);                                 /* ulp of the binade of |p| */
+        const float q = inc * __uint_as_float((277u - eb) << 23);              /* inc / u, exact */
+        if (!(fabsf(q) < 8388608.0f)) { k = 0; iE = i; return; }               /* the step leaves the binade at once */
+        const float fl = floorf(q), frac = q - fl;
+        int kk;
+        if (frac == 0.5f) {
+            if (bits & 1u) { k = 0; iE = i; return; }                           /* odd mantissa: one true add first */
+            kk = (int) fl; kk += kk & 1;                                         /* the even one of {fl, fl + 1} */
+        } else kk = (int) fl + (frac > 0.5f ? 1 : 0);
+        k = kk;
+        const int M = (int) ((bits & 0x7fffffu) | 0x800000u);                   /* |p| / u */
+        const int along = (bits >> 31) ? -kk : kk;                               /* the step along |p| */
+        int m;
+        if (along > 0) m = (0xffffff - M) / along; else if (along < 0) m = (M - 0x800000) / (-along); else m = n;
+        iE = i + min(m, n - i);
+    }
+    __device__ __forceinline__ float at(int j) {                                 /* j >= iS, called with non-decreasing j */
+        while (j > iE) {
+            const float pe = pS + (float) ((iE - iS) * k) * u;                   /* exact */
+            const int ni = iE + 1;
+            start(__fadd_rn(pe, inc), ni, 0x3fffffff);
+        }
+        return pS + (float) ((j - iS) * k) * u;
+    }
+};
 
 /*
  * Optical depth of the segment o + t d, t in [0, dist], for every lane's ray; called by the 32 lanes of a warp together
@@ -65,15 +114,27 @@ __device__ __forceinline__ float warp_grid_optical_depth(const MediumDev &m, con
                 uint32_t nSteps = (uint32_t) ceilf(xdiv(length, m.stepSize));
                 nSteps += nSteps & 1u;
                 const float stepSz = xdiv(length, (float) nSteps);
-                /* node i in grid coordinates: g0 + i * ginc; node nSteps is ray(maxt) itself (319, 332-333) */
-                const float g0x = fmaf(m.gsc[0], p0.x, m.gtr[0]), g0y = fmaf(m.gsc[1], p0.y, m.gtr[1]), g0z = fmaf(m.gsc[2], p0.z, m.gtr[2]);
-                const float gix = m.gsc[0] * d.x * stepSz, giy = m.gsc[1] * d.y * stepSz, giz = m.gsc[2] * d.z * stepSz;
                 float sum = 0.0f;
+                if (nSteps >= ALVRL_DRIFT_MIN_STEPS) {
+                    /* node i sits at the reference's running position p_i (CoordRun); node nSteps is ray(maxt) itself (319, 332-333) */
+                    CoordRun rx, ry, rz;
+                    rx.inc = xmul(d.x, stepSz); ry.inc = xmul(d.y, stepSz); rz.inc = xmul(d.z, stepSz);
+                    rx.start(p0.x, 0, (int) nSteps); ry.start(p0.y, 0, (int) nSteps); rz.start(p0.z, 0, (int) nSteps);
+                    for (uint32_t i = lane; i < nSteps; i += 32u) {
+                        const float w = i == 0u ? 1.0f : ((i & 1u) ? 4.0f : 2.0f);
+                        const float px = rx.at((int) i), py = ry.at((int) i), pz = rz.at((int) i);
+                        sum = fmaf(w, grid_lookup_g(m, xadd(xmul(m.gsc[0], px), m.gtr[0]), xadd(xmul(m.gsc[1], py), m.gtr[1]), xadd(xmul(m.gsc[2], pz), m.gtr[2])), sum);
+                    }
+                } else {
+                    /* a short ray: its running positions stay within n * ulp / 2 < 10^-5 of o + i * inc (a 200th of a voxel at 512^3) */
+                    const float g0x = fmaf(m.gsc[0], p0.x, m.gtr[0]), g0y = fmaf(m.gsc[1], p0.y, m.gtr[1]), g0z = fmaf(m.gsc[2], p0.z, m.gtr[2]);
+                    const float gix = m.gsc[0] * d.x * stepSz, giy = m.gsc[1] * d.y * stepSz, giz = m.gsc[2] * d.z * stepSz;
 #pragma unroll 2
-                for (uint32_t i = lane; i < nSteps; i += 32u) {
-                    const float fi = (float) i;
-                    const float w = i == 0u ? 1.0f : ((i & 1u) ? 4.0f : 2.0f);
-                    sum = fmaf(w, grid_lookup_g(m, fmaf(fi, gix, g0x), fmaf(fi, giy, g0y), fmaf(fi, giz, g0z)), sum);
+                    for (uint32_t i = lane; i < nSteps; i += 32u) {
+                        const float fi = (float) i;
+                        const float w = i == 0u ? 1.0f : ((i & 1u) ? 4.0f : 2.0f);
+                        sum = fmaf(w, grid_lookup_g(m, fmaf(fi, gix, g0x), fmaf(fi, giy, g0y), fmaf(fi, giz, g0z)), sum);
+                    }
                 }
                 if (lane == (nSteps & 31u)) sum += grid_lookup_fast(m, pLast);
 #pragma unroll
