@@ -83,7 +83,8 @@ typedef struct alvrl_params {
     int32_t workerCount;                /* 1: emulated Scheduler::getWorkerCount() -- decides how the SFMT
                                            sampler is cloned over contiguous slice ranges
                                            (vrlIntegrator.cpp:305-321,1048-1051; Preprocessor.cpp:738-741) */
-    int32_t reserved[6];
+    int32_t rrDepth;                    /* 5 (tracer only; src/librender/integrator.cpp:272-298) */
+    int32_t reserved[5];
 } alvrl_params;
 
 typedef struct alvrl_ctx *alvrl_handle;
@@ -178,6 +179,22 @@ int alvrl_prepass(alvrl_handle h);
 int alvrl_render(alvrl_handle h, float *rgb_host);
 /* Unclustered render (globalCluster = localRefinement = false): getVRLContributions over all VRLs. */
 int alvrl_render_unclustered(alvrl_handle h, float *rgb_host);
+/* ---- VRL tracer: the step before the path ----------------------------------------------------------------
+ * vrlTracer::randomWalk (src/integrators/vrl/vrlTracer.h:14-58): light particles are traced from an area emitter
+ * (Scene::sampleEmitterPosition, scene.cpp:958-974; AreaLight::samplePosition / sampleDirection, src/emitters/area.cpp:94-123;
+ * TriMesh::samplePosition, trimesh.cpp:412-423) through the medium (HomogeneousMedium::sampleDistance, homogeneous.cpp:275-352;
+ * phase function sampling, isotropic.cpp:62-67, hg.cpp:74-98) and off the surfaces (diffuse.cpp:129-138, dielectric.cpp:335-364,
+ * conductor.cpp:254-268, medium transitions) with Russian roulette from rrDepth on (traceOneParticle, vrlTracer.h:91-230);
+ * every path segment inside the scattering medium becomes a VRL (vrlVector::put, VRL.h:148-158) until vrlTargetNum VRLs
+ * exist.  Particle i draws from the counter stream of (ALVRL_RNG_TRACER, i); the particles are independent, so the device
+ * traces them in parallel and keeps the particles 0 .. n-1, n the first count that reaches the target -- what the
+ * reference's sequential loop stops at.  Homogeneous media only.
+ *   emitter_tris: indices (into the mesh of alvrl_set_mesh) of the triangles of the emitter's shape, in the shape's order.
+ * alvrl_trace_vrls replaces the handle's VRL set (as alvrl_set_vrls would) and its particle count. */
+int alvrl_set_area_emitter(alvrl_handle h, const uint32_t *emitter_tris, uint32_t ntris, const float radiance_rgb[3]);
+int alvrl_trace_vrls(alvrl_handle h, uint32_t target_num /* 0: params.vrlTargetNum */);
+int alvrl_get_vrls(alvrl_handle h, float *start_xyz, float *end_xyz, float *power_rgb, uint64_t *particle_count);
+
 /* ---- film: the step after the path -------------------------------------------------------------------
  * Reconstruction-filter splat and pass accumulation: ImageBlock::put (include/mitsuba/render/imageblock.h:124-202) with
  * the pre-rasterised filter of ReconstructionFilter::configure / evalDiscretized (src/libcore/rfilter.cpp:37-55,

@@ -45,7 +45,8 @@ enum {
     ALVRL_RNG_RENDER   = 2,
     ALVRL_RNG_SLICEMAP = 3,
     ALVRL_RNG_CLUSTER  = 4,
-    ALVRL_RNG_CHAIN    = 5     /* a = pixel index, b = path code of the branch: the roulette draw of LiInternal (485) */
+    ALVRL_RNG_CHAIN    = 5,    /* a = pixel index, b = path code of the branch: the roulette draw of LiInternal (485) */
+    ALVRL_RNG_TRACER   = 6     /* a = particle index, b = 0: the draws of vrlTracer::traceOneParticle in their order */
 };
 #define ALVRL_RNG_GLOBAL_ID 0xfffffffeu
 

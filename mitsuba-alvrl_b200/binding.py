@@ -29,7 +29,7 @@ class Params(C.Structure):
         ("depthCorrection", C.c_float), ("numVrlFalseColor", C.c_int32), ("slicesFalseColor", C.c_int32),
         ("convergenceFalseColor", C.c_int32), ("maxPasses", C.c_int32),
         ("rngMode", C.c_int32), ("seed", C.c_uint64), ("anyHitShadowRays", C.c_int32),
-        ("workerCount", C.c_int32), ("reserved", C.c_int32 * 6),
+        ("workerCount", C.c_int32), ("rrDepth", C.c_int32), ("reserved", C.c_int32 * 5),
     ]
 
 
@@ -153,6 +153,25 @@ class Integrator:
     def set_materials(self, albedo, bits):
         a, b = _f32(albedo), _u32(bits)
         self._call("set_materials", _p(a), _p(b), C.c_uint32(len(b)))
+
+    # -- VRL tracer (include/alvrl.h) ---------------------------------------------------------------
+    def set_area_emitter(self, tris, radiance):
+        t, r = _u32(tris), _f32(radiance)
+        self._call("set_area_emitter", _p(t), C.c_uint32(len(t)), _p(r))
+
+    def trace_vrls(self, target=0):
+        self._call("trace_vrls", C.c_uint32(target))
+        n = C.c_uint32()
+        self._call("get_num_vrls", C.byref(n))
+        self.N = n.value
+
+    def get_vrls(self):
+        n = C.c_uint32()
+        self._call("get_num_vrls", C.byref(n))
+        s, e, p = (np.zeros((n.value, 3), np.float32) for _ in range(3))
+        pc = C.c_uint64()
+        self._call("get_vrls", _p(s), _p(e), _p(p), C.byref(pc))
+        return s, e, p, pc.value
 
     def set_material_optics(self, optics):
         o = _f32(optics).reshape(-1, 12)

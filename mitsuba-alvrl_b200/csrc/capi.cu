@@ -395,7 +395,7 @@ void alvrl_params_default(alvrl_params *p) {
     p->globalUndersampling = -1; p->localRefinement = 1; p->localUndersampling = -1; p->fallBackUndersampling = 5;
     p->targetNumSlices = 100; p->targetPixelUndersampling = 64; p->sliceCurvatureFactor = 0.5f;
     p->neighbourCount = 0; p->neighbourWeight = 0; p->Rsamples = 1; p->depthCorrection = 1; p->maxPasses = 1;
-    p->rngMode = ALVRL_RNG_MODE_COUNTER; p->seed = 0; p->anyHitShadowRays = 1; p->workerCount = 1;
+    p->rngMode = ALVRL_RNG_MODE_COUNTER; p->seed = 0; p->anyHitShadowRays = 1; p->workerCount = 1; p->rrDepth = 5;
 }
 
 int alvrl_create(int device, const alvrl_params *p, alvrl_handle *out) {
@@ -869,6 +869,96 @@ int alvrl_set_slice_range(alvrl_handle c, uint32_t b, uint32_t e) {
     }
     c->sliceBegin = b; c->sliceEnd = e;
     return ALVRL_OK;
+}
+
+/* ---- VRL tracer (tracer.cu) ------------------------------------------------------------------------ */
+int alvrl_set_area_emitter(alvrl_handle c, const uint32_t *tris, uint32_t n, const float radiance[3]) {
+    API_BEGIN
+    use_device(c);
+    if (!c->haveMesh || !tris || !n || !radiance) throw Error(ALVRL_ERR_ARG, "alvrl_set_area_emitter: set_mesh first; at least one triangle");
+    const uint32_t nt = (uint32_t) c->triMat.size();
+    /* TriMesh::prepareSamplingTable (trimesh.cpp:388-403): DiscreteDistribution::append / normalize (pmf.h:48-52, 101-114) over
+     * Triangle::surfaceArea (triangle.cpp:61-67), in float */
+    c->emTris.assign(tris, tris + n);
+    c->emCdf.assign(1, 0.0f);
+    for (uint32_t i = 0; i < n; i++) {
+        if (tris[i] >= nt) throw Error(ALVRL_ERR_ARG, "alvrl_set_area_emitter: triangle index out of range");
+        const float *p0 = &c->verts[3 * (size_t) c->tris[3 * (size_t) tris[i]]], *p1 = &c->verts[3 * (size_t) c->tris[3 * (size_t) tris[i] + 1]],
+                    *p2 = &c->verts[3 * (size_t) c->tris[3 * (size_t) tris[i] + 2]];
+        const float a[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]}, b[3] = {p2[0] - p0[0], p2[1] - p0[1], p2[2] - p0[2]};
+        const float cx = a[1] * b[2] - a[2] * b[1], cy = a[2] * b[0] - a[0] * b[2], cz = a[0] * b[1] - a[1] * b[0];
+        c->emCdf.push_back(c->emCdf.back() + 0.5f * std::sqrt(cx * cx + cy * cy + cz * cz));
+    }
+    const float sum = c->emCdf.back(), normalization = 1.0f / sum;
+    if (!(sum > 0)) throw Error(ALVRL_ERR_ARG, "alvrl_set_area_emitter: the emitter has no area");
+    for (size_t i = 1; i < c->emCdf.size(); ++i) c->emCdf[i] *= normalization;
+    c->emCdf.back() = 1.0f;
+    for (int k = 0; k < 3; k++) c->emPower[k] = radiance[k] * (float) M_PI * sum;          /* area.cpp:198 */
+    c->dEmTris.upload(c->emTris, c->stream); c->dEmCdf.upload(c->emCdf, c->stream);
+    c->haveEmitter = true;
+    API_END
+}
+
+int alvrl_trace_vrls(alvrl_handle c, uint32_t target) {
+    API_BEGIN
+    use_device(c);
+    if (!c->haveEmitter || !c->haveMedium || !c->haveMat) throw Error(ALVRL_ERR_STATE, "alvrl_trace_vrls: set_area_emitter / set_medium / set_materials first");
+    if (c->medium.type != 0) throw Error(ALVRL_ERR_UNSUPPORTED, "alvrl_trace_vrls: homogeneous media only");
+    ensure_scene(c);
+    bool anyDelta = false;
+    for (uint32_t b : c->matBits) if (b & ALVRL_BSDF_DELTA) anyDelta = true;
+    if (anyDelta && c->optics.size() != 12 * c->matBits.size()) throw Error(ALVRL_ERR_STATE, "materials with delta components need alvrl_set_material_optics");
+    if (!anyDelta && c->dMatOptics.n == 0) { std::vector<float4> z(3 * std::max<size_t>(1, c->matBits.size()), make_float4(0, 0, 0, 0)); c->dMatOptics.upload(z, c->stream); }
+    if (!target) target = (uint32_t) c->P.vrlTargetNum;
+    /* randomWalk (vrlTracer.h:29-40) stops after the particle that brings the count to the target: trace batches of independent
+     * particles, find that particle on the host */
+    std::vector<uint32_t> counts;
+    uint64_t have = 0; uint32_t traced = 0, cut = 0;
+    uint32_t batch = std::max<uint32_t>(1024u, target / 16u);
+    DevBuf<uint32_t> dCnt;
+    while (!cut) {
+        dCnt.alloc(batch);
+        launch_trace_count(c->sceneDev, c->medium, c->dEmTris.p, c->dEmCdf.p, (uint32_t) c->emTris.size(), c->emPower, c->P.seed, c->P.shortVrls,
+                           c->P.maxParticleDepth, c->P.rrDepth, c->dTriVerts.p, c->dTriMat.p, c->dMatAlbedo.p, c->dMatBits.p, c->dMatOptics.p, traced, batch, dCnt.p, c->stream);
+        c->stats.kernelLaunches++;
+        ALVRL_CUDA(cudaGetLastError());
+        counts.resize((size_t) traced + batch);
+        dCnt.download(counts.data() + traced, batch, c->stream);
+        for (uint32_t i = traced; i < traced + batch && !cut; i++) { have += counts[i]; if (have >= target) cut = i + 1; }
+        traced += batch;
+        if (!cut && traced > (1u << 30)) throw Error(ALVRL_ERR_ARG, "alvrl_trace_vrls: no VRLs are being generated (is the emitter inside the medium?)");
+        batch = std::min<uint32_t>(batch * 2u, 1u << 22);
+    }
+    std::vector<uint32_t> offset((size_t) cut + 1, 0u);
+    for (uint32_t i = 0; i < cut; i++) offset[i + 1] = offset[i] + counts[i];
+    const uint32_t n = offset[cut];
+    DevBuf<uint32_t> dOff; dOff.upload(offset, c->stream);
+    DevBuf<float> dOut; dOut.alloc(9 * (size_t) n);
+    launch_trace_write(c->sceneDev, c->medium, c->dEmTris.p, c->dEmCdf.p, (uint32_t) c->emTris.size(), c->emPower, c->P.seed, c->P.shortVrls,
+                       c->P.maxParticleDepth, c->P.rrDepth, c->dTriVerts.p, c->dTriMat.p, c->dMatAlbedo.p, c->dMatBits.p, c->dMatOptics.p, cut, dOff.p, dOut.p, c->stream);
+    c->stats.kernelLaunches++;
+    ALVRL_CUDA(cudaGetLastError());
+    std::vector<float> rec(9 * (size_t) n);
+    dOut.download(rec.data(), rec.size(), c->stream);
+    std::vector<float> s(3 * (size_t) n), e(3 * (size_t) n), p(3 * (size_t) n);
+    for (uint32_t i = 0; i < n; i++) for (int k = 0; k < 3; k++) { s[3 * (size_t) i + k] = rec[9 * (size_t) i + k]; e[3 * (size_t) i + k] = rec[9 * (size_t) i + 3 + k]; p[3 * (size_t) i + k] = rec[9 * (size_t) i + 6 + k]; }
+    const int rc = alvrl_set_vrls(c, s.data(), e.data(), p.data(), n, cut);               /* the put() filter already ran on the device: nothing is dropped */
+    if (rc != ALVRL_OK) return rc;
+    API_END
+}
+
+int alvrl_get_vrls(alvrl_handle c, float *s, float *e, float *p, uint64_t *pc) {
+    API_BEGIN
+    if (!c->haveVrls) throw Error(ALVRL_ERR_STATE, "no VRLs");
+    const size_t n = c->vrlHost.size();
+    for (size_t i = 0; i < n; i++) {
+        const VrlRec &v = c->vrlHost[i];
+        if (s) { s[3 * i] = v.s.x; s[3 * i + 1] = v.s.y; s[3 * i + 2] = v.s.z; }
+        if (e) { e[3 * i] = v.e.x; e[3 * i + 1] = v.e.y; e[3 * i + 2] = v.e.z; }
+        if (p) { p[3 * i] = v.power.x; p[3 * i + 1] = v.power.y; p[3 * i + 2] = v.power.z; }
+    }
+    if (pc) *pc = c->particleCount;
+    API_END
 }
 
 /* ---- film (film.cu) ------------------------------------------------------------------------------- */

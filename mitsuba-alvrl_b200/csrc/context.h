@@ -144,6 +144,9 @@ struct alvrl_ctx {
 
     /* per pixel (index y + H*x) */
     alvrl::DevBuf<SegRec> dPixSegs; alvrl::DevBuf<uint32_t> dHitPrim; alvrl::DevBuf<float> dHitT;
+    /* VRL tracer (tracer.cu): the area emitter */
+    std::vector<uint32_t> emTris; std::vector<float> emCdf; float emPower[3] = {0, 0, 0}; bool haveEmitter = false;
+    alvrl::DevBuf<uint32_t> dEmTris; alvrl::DevBuf<float> dEmCdf;
     /* specular chains (chain.cu): the segments below the camera segments, grouped by pixel */
     std::vector<float> optics; alvrl::DevBuf<float4> dMatOptics; bool anyDelta = false, chainsValid = false;
     std::vector<uint32_t> chainOffset;                 /* P + 1 */

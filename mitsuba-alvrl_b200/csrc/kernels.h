@@ -26,6 +26,14 @@ void launch_chain_write(const SceneDev &sc, const MediumDev &med, bool haveMediu
 void launch_add_chain_rows(float2 *R, uint32_t ldR, uint32_t rowBegin, uint32_t numRows, const float2 *X, uint32_t ldX, const uint32_t *xFirst, uint32_t N, cudaStream_t st);
 void launch_chain_accumulate(float4 *fb, uint32_t W, uint32_t H, const float4 *subLi, const SegRec *segs, const uint32_t *pixList, const uint32_t *first, uint32_t nPix, cudaStream_t st);
 
+/* tracer.cu (exact arithmetic): the VRL tracer */
+void launch_trace_count(const SceneDev &sc, const MediumDev &med, const uint32_t *emTris, const float *emCdf, uint32_t emN, const float emPower[3],
+                        uint64_t seed, int shortVrls, int maxDepth, int rrDepth, const float4 *triVerts, const uint32_t *triMat, const float4 *matAlbedo,
+                        const uint32_t *matBits, const float4 *matOptics, uint32_t first, uint32_t n, uint32_t *counts, cudaStream_t st);
+void launch_trace_write(const SceneDev &sc, const MediumDev &med, const uint32_t *emTris, const float *emCdf, uint32_t emN, const float emPower[3],
+                        uint64_t seed, int shortVrls, int maxDepth, int rrDepth, const float4 *triVerts, const uint32_t *triMat, const float4 *matAlbedo,
+                        const uint32_t *matBits, const float4 *matOptics, uint32_t n, const uint32_t *offset, float *out, cudaStream_t st);
+
 /* film.cu (exact arithmetic) */
 void launch_film_splat(const float4 *fb, uint32_t W, uint32_t H, const FilmFilterDev &f, float *acc, cudaStream_t st);
 void launch_film_develop(const float *acc, uint32_t n, float *rgb, cudaStream_t st);

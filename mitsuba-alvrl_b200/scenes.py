@@ -234,6 +234,24 @@ def cornell_scene(width, height, medium=None, closed=False, mesh=None):
                 medium=medium or homogeneous_medium(), camera=cam, extra_bounds=cam["origin"].reshape(1, 3))
 
 
+def tracer_scene(width, height, medium=None, glass=True):
+    """Closed Cornell box (front wall added, camera inside) with a ceiling area light -- a quad just below the ceiling, facing
+    down -- and, optionally, the glass sphere and the conductor box of chain_scene: what the VRL tracer (vrlTracer.h) walks.
+    Returns (scene, emitter triangle indices, radiance)."""
+    scene = dict(chain_scene(width, height, medium) if glass else cornell_scene(width, height, medium))
+    v, t, m = scene["verts"], scene["tris"], scene["tri_material"]
+    q = np.array([(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0),                                      # front wall (+z)
+                  (0.35, 0.998, 0.35), (0.65, 0.998, 0.35), (0.65, 0.998, 0.65), (0.35, 0.998, 0.65)], np.float32)   # light (-y)
+    i = len(v)
+    scene["verts"] = np.concatenate([v, q])
+    scene["tris"] = np.concatenate([t, np.array([(i, i + 1, i + 2), (i, i + 2, i + 3), (i + 4, i + 5, i + 6), (i + 4, i + 6, i + 7)], np.uint32)])
+    scene["tri_material"] = np.concatenate([m, np.full(4, WHITE, np.uint32)])
+    cam = perspective_camera(width, height, origin=(0.5, 0.5, 0.02), target=(0.5, 0.5, 1.0), fov=80.0)
+    scene["camera"] = cam
+    scene["extra_bounds"] = cam["origin"].reshape(1, 3)
+    return scene, np.array([len(t) + 2, len(t) + 3], np.uint32), np.array([18.0, 15.0, 12.0], np.float32)
+
+
 def chain_scene(width, height, medium=None, glass_eta=1.5):
     """Cornell box with a glass sphere (smooth dielectric, the fog outside, vacuum inside) in front of the boxes and the tall
     box turned into a copper-like mirror (smooth conductor): camera segments that end on them continue as specular chains

@@ -26,6 +26,8 @@ struct Ctx {
     bool haveMesh = false, haveMat = false, haveMedium = false, haveCam = false, haveVrls = false;
     std::vector<VRL> vrls; uint64_t particleCount = 0;
     std::vector<Ray> rays; std::vector<Intersection> hits;       // per pixel index y + H*x
+    /* area emitter of the VRL tracer: the triangles of its shape, TriMesh::prepareSamplingTable (trimesh.cpp:388-403) */
+    std::vector<uint32_t> emTris; std::vector<Float> emCdf; Float emInvArea = 0; Spec emPower; bool haveEmitter = false;
     bool havePrimary = false;
     struct ChainSeg { Ray ray; Intersection its; Spec weight; bool inMedium; uint32_t code; };
     std::vector<std::vector<ChainSeg>> chains; bool haveChains = false; bool anyDelta = false;   // vrlIntegrator.cpp:445-511
@@ -195,7 +197,7 @@ void orc_params_default(alvrl_params *p) {
     p->globalUndersampling = -1; p->localRefinement = 1; p->localUndersampling = -1; p->fallBackUndersampling = 5;
     p->targetNumSlices = 100; p->targetPixelUndersampling = 64; p->sliceCurvatureFactor = 0.5f;
     p->neighbourCount = 0; p->neighbourWeight = 0; p->Rsamples = 1; p->depthCorrection = 1; p->maxPasses = 1;
-    p->rngMode = ALVRL_RNG_MODE_COUNTER; p->seed = 0; p->anyHitShadowRays = 1; p->workerCount = 1;
+    p->rngMode = ALVRL_RNG_MODE_COUNTER; p->seed = 0; p->anyHitShadowRays = 1; p->workerCount = 1; p->rrDepth = 5;
 }
 
 int orc_create(int, const alvrl_params *p, void **out) {
@@ -867,6 +869,233 @@ int orc_get_chain_segments(void *h, uint32_t *offset, float *segs) {
     }
     offset[P] = total;
     ORC_CATCH
+}
+
+/* ---- VRL tracer: vrlTracer.h:14-58, 91-230 --------------------------------------------------------------------------- */
+int orc_set_area_emitter(void *h, const uint32_t *tris, uint32_t n, const float radiance[3]) {
+    Ctx *c = (Ctx *) h;
+    if (!c->haveMesh || !n) return seterr(ALVRL_ERR_ARG, "set_area_emitter: set_mesh first, at least one triangle");
+    c->emTris.assign(tris, tris + n);
+    /* DiscreteDistribution::append / normalize (pmf.h:48-52,101-114) over Triangle::surfaceArea (triangle.cpp:61-67) */
+    c->emCdf.assign(1, 0.0f);
+    for (uint32_t i = 0; i < n; i++) {
+        if (tris[i] >= c->scene.numTris()) return seterr(ALVRL_ERR_ARG, "set_area_emitter: triangle index out of range");
+        const V3 &p0 = c->scene.verts[c->scene.tris[3 * tris[i]]], &p1 = c->scene.verts[c->scene.tris[3 * tris[i] + 1]], &p2 = c->scene.verts[c->scene.tris[3 * tris[i] + 2]];
+        V3 sideA = p1 - p0, sideB = p2 - p0;
+        c->emCdf.push_back(c->emCdf.back() + 0.5f * cross(sideA, sideB).length());
+    }
+    const Float sum = c->emCdf.back(), normalization = 1.0f / sum;
+    for (size_t i = 1; i < c->emCdf.size(); ++i) c->emCdf[i] *= normalization;
+    c->emCdf.back() = 1.0f;
+    c->emInvArea = 1.0f / sum;
+    c->emPower = Spec(radiance[0], radiance[1], radiance[2]) * (Float) M_PI * sum;       // area.cpp:198
+    c->haveEmitter = true;
+    return ALVRL_OK;
+}
+namespace {
+inline void sincosF(Float theta, Float *s, Float *cs) { *s = (Float) ::sin((double) theta); *cs = (Float) ::cos((double) theta); }   // math::sincos, pinned through double
+inline V3 squareToUniformSphere(Float sx, Float sy) {                       // warp.cpp:25-31
+    Float z = 1.0f - 2.0f * sy;
+    Float r = safe_sqrt(1.0f - z * z);
+    Float sinPhi, cosPhi;
+    sincosF((Float) (2.0f * M_PI * sx), &sinPhi, &cosPhi);
+    return V3(r * cosPhi, r * sinPhi, z);
+}
+inline V3 squareToCosineHemisphere(Float sx, Float sy) {                    // warp.cpp:43-52, 81-102
+    Float r1 = 2.0f * sx - 1.0f, r2 = 2.0f * sy - 1.0f;
+    Float phi, r;
+    if (r1 == 0 && r2 == 0) { r = phi = 0; }
+    else if (r1 * r1 > r2 * r2) { r = r1; phi = (Float) ((M_PI / 4.0f) * (r2 / r1)); }
+    else { r = r2; phi = (Float) ((M_PI / 2.0f) - (r1 / r2) * (M_PI / 4.0f)); }
+    Float cosPhi, sinPhi;
+    sincosF(phi, &sinPhi, &cosPhi);
+    Float px = r * cosPhi, py = r * sinPhi;
+    Float z = safe_sqrt(1.0f - px * px - py * py);
+    if (z == 0) z = 1e-10f;
+    return V3(px, py, z);
+}
+inline void coordinateSystem(const V3 &a, V3 &b, V3 &c) {                    // util.cpp:592-601
+    if (std::abs(a.x) > std::abs(a.y)) { Float invLen = 1.0f / std::sqrt(a.x * a.x + a.z * a.z); c = V3(a.z * invLen, 0.0f, -a.x * invLen); }
+    else { Float invLen = 1.0f / std::sqrt(a.y * a.y + a.z * a.z); c = V3(0.0f, a.z * invLen, -a.y * invLen); }
+    b = cross(c, a);
+}
+inline V3 frameToWorld(const V3 &n, const V3 &v) { V3 s, t; coordinateSystem(n, s, t); return s * v.x + t * v.y + n * v.z; }   // Frame(n).toWorld
+struct TracedVrl { Spec power; V3 start, end; };
+
+/* vrlTracer::traceOneParticle, vrlTracer.h:91-230; the VRLs it stores (vrlVector::put filter applied) are appended to out */
+void traceOneParticle(Ctx *c, Sampler *smp, std::vector<TracedVrl> &out) {
+    const bool shortVrls = c->P.shortVrls != 0;
+    const int maxDepth = c->P.maxParticleDepth, rrDepth = c->P.rrDepth;
+    Medium &med = c->medium;
+    /* scene->sampleEmitterPosition(pRec, next2D()): one emitter, m_emitterPDF = {0, 1}: the sample and the value pass unchanged
+     * (scene.cpp:958-974); TriMesh::samplePosition (trimesh.cpp:412-423), Triangle::sample (triangle.cpp:24-45) */
+    Float sx = smp->next1D(), sy = smp->next1D();
+    {
+        std::vector<Float>::const_iterator entry = std::lower_bound(c->emCdf.begin(), c->emCdf.end(), sy);        // pmf.h:123-135
+        size_t index = std::min(c->emCdf.size() - 2, (size_t) std::max((ptrdiff_t) 0, entry - c->emCdf.begin() - 1));
+        while ((c->emCdf[index + 1] - c->emCdf[index]) == 0 && index < c->emCdf.size() - 1) ++index;
+        sy = (sy - c->emCdf[index]) / (c->emCdf[index + 1] - c->emCdf[index]);                                      // sampleReuse, 164-169
+        const uint32_t tri = c->emTris[index];
+        const V3 &p0 = c->scene.verts[c->scene.tris[3 * tri]], &p1 = c->scene.verts[c->scene.tris[3 * tri + 1]], &p2 = c->scene.verts[c->scene.tris[3 * tri + 2]];
+        Float a = safe_sqrt(1.0f - sx);                                                                             // squareToUniformTriangle, warp.cpp:76-79
+        Float bx = 1 - a, by = a * sy;
+        V3 sideA = p1 - p0, sideB = p2 - p0;
+        V3 p = p0 + (sideA * bx) + (sideB * by);
+        V3 n = normalize(cross(sideA, sideB));
+        Spec power = c->emPower;                                                                                    // area.cpp:94-98; / emPdf = 1
+        /* emitter->sampleDirection(dRec, pRec, next2D()), area.cpp:115-123 */
+        Float dx = smp->next1D(), dy = smp->next1D();
+        V3 local = squareToCosineHemisphere(dx, dy);
+        V3 d = frameToWorld(n, local);
+        power *= Spec(1.0f);
+        if (power.isZero()) return;
+        bool inMedium = true;                                           // emitter->getMedium(): the emitter sits in the scene's medium
+        TracedVrl cur; cur.power = power; cur.start = p;                // handleEmission (nextParticle is counted by the caller)
+        bool curMedium = inMedium;
+        auto endCurrent = [&](const V3 &q) {                            // endCurrentVrl + vrlVector::put, VRL.h:148-158
+            if (distance(cur.start, q) == 0) return;
+            cur.end = q;
+            if (!curMedium || med.sigmaS.isZero()) return;
+            if (cur.power.isZero()) return;
+            if (distance(cur.start, cur.end) == 0) return;
+            out.push_back(cur);
+        };
+        Ray ray(p, d, Epsilon, std::numeric_limits<Float>::infinity());
+        int depth = 1;
+        Spec throughput(1.0f);
+        Float eta = 1.0f;
+        while (!throughput.isZero() && (depth <= maxDepth || maxDepth < 0)) {
+            Intersection its;
+            c->scene.rayIntersect(ray, its);                            // rayIntersectAll: no special shapes here
+            /* medium->sampleDistance(Ray(ray, 0, its.t), mRec, sampler), homogeneous.cpp:275-352 (EBalance) */
+            bool scattered = false;
+            Spec mTrans(1.0f), mSigmaS; Float pdfFailure = 1, pdfSuccess = 1; V3 mP;
+            if (inMedium) {
+                Float rnd = smp->next1D(), sampledDistance;
+                Float samplingDensity = 0;
+                if (rnd < med.samplingWeight) {
+                    rnd /= med.samplingWeight;
+                    int channel = std::min((int) (smp->next1D() * 3), 2);
+                    samplingDensity = med.sigmaT[channel];
+                    sampledDistance = -((Float) ::log((double) (1 - rnd))) / samplingDensity;
+                } else sampledDistance = std::numeric_limits<Float>::infinity();
+                Float distSurf = its.t - 0;
+                bool success = true;
+                if (sampledDistance < distSurf) {
+                    Float t = sampledDistance + 0;
+                    mP = ray.o + t * ray.d;
+                    mSigmaS = med.sigmaS;
+                    if (mP.x == ray.o.x && mP.y == ray.o.y && mP.z == ray.o.z) success = false;
+                } else { sampledDistance = distSurf; success = false; }
+                pdfFailure = 0; pdfSuccess = 0;
+                for (int i = 0; i < 3; ++i) { Float tmp = fastexp(-med.sigmaT[i] * sampledDistance); pdfFailure += tmp; pdfSuccess += med.sigmaT[i] * tmp; }
+                pdfFailure /= 3; pdfSuccess /= 3;
+                for (int i = 0; i < 3; ++i) mTrans[i] = fastexp(med.sigmaT[i] * (-sampledDistance));
+                pdfSuccess = pdfSuccess * med.samplingWeight;
+                pdfFailure = med.samplingWeight * pdfFailure + (1 - med.samplingWeight);
+                if (mTrans.max() < 1e-20) mTrans = Spec(0.0f);
+                scattered = success;
+            }
+            if (inMedium && scattered) {
+                throughput *= mTrans * mSigmaS / pdfSuccess;
+                /* medium->getPhaseFunction()->sample(pRec, sampler): returns 1 (isotropic.cpp:62-67, hg.cpp:74-98) */
+                Float px = smp->next1D(), py = smp->next1D();
+                V3 wo;
+                if (med.phaseType == ALVRL_PHASE_ISOTROPIC) wo = squareToUniformSphere(px, py);
+                else {
+                    Float cosTheta;
+                    if (std::abs(med.g) < Epsilon) cosTheta = 1 - 2 * px;
+                    else { Float sqrTerm = (1 - med.g * med.g) / (1 - med.g + 2 * med.g * px); cosTheta = (1 + med.g * med.g - sqrTerm * sqrTerm) / (2 * med.g); }
+                    Float sinTheta = safe_sqrt(1.0f - cosTheta * cosTheta), sinPhi, cosPhi;
+                    sincosF((Float) (2 * M_PI * py), &sinPhi, &cosPhi);
+                    wo = frameToWorld(ray.d, V3(sinTheta * cosPhi, sinTheta * sinPhi, cosTheta));      // Frame(-pRec.wi), wi = -ray.d
+                }
+                V3 endPoint;
+                if (shortVrls) endPoint = mP;
+                else { if (its.isValid()) endPoint = its.p; else break; }
+                endCurrent(endPoint);                                                                   // handleMediumScattering
+                cur.power = throughput * power; cur.start = mP; curMedium = inMedium;
+                ray = Ray(mP, wo, 0, std::numeric_limits<Float>::infinity());
+            } else if (its.isValid()) {
+                if (inMedium) throughput *= mTrans / pdfFailure;
+                const uint32_t bits = c->scene.matBits[its.material];
+                const HitFrame fr = c->scene.hitFrame(its);
+                const V3 wi = fr.toLocal(-ray.d);
+                Float bsx = smp->next1D(), bsy = smp->next1D();
+                V3 woL; Float bEta = 1.0f; Spec bsdfWeight(0.0f);
+                if (bits & ALVRL_BSDF_DIELECTRIC) {                                                     // dielectric.cpp:335-364, EImportance
+                    const Optics &o = c->scene.optics[its.material];
+                    const Float e = o.v[0], invE = 1 / e;
+                    Float cosThetaT;
+                    Float F = fresnelDielectricExt(wi.z, cosThetaT, e);
+                    if (bsx <= F) { woL = V3(-wi.x, -wi.y, wi.z); bEta = 1.0f; bsdfWeight = Spec(o.v[6], o.v[7], o.v[8]); }
+                    else {
+                        Float scale = -(cosThetaT < 0 ? invE : e);
+                        woL = V3(scale * wi.x, scale * wi.y, cosThetaT);
+                        bEta = cosThetaT < 0 ? e : invE;
+                        Float factor = 1.0f;
+                        bsdfWeight = Spec(o.v[9], o.v[10], o.v[11]) * (factor * factor);
+                    }
+                } else if (bits & ALVRL_BSDF_CONDUCTOR) {                                               // conductor.cpp:254-268
+                    const Optics &o = c->scene.optics[its.material];
+                    if (wi.z > 0) {
+                        woL = V3(-wi.x, -wi.y, wi.z);
+                        bsdfWeight = Spec(o.v[6], o.v[7], o.v[8]) * Spec(fresnelConductorExact(wi.z, o.v[0], o.v[3]), fresnelConductorExact(wi.z, o.v[1], o.v[4]), fresnelConductorExact(wi.z, o.v[2], o.v[5]));
+                    }
+                } else if ((bits & ALVRL_BSDF_SMOOTH) && wi.z > 0) {                                    // diffuse.cpp:129-138
+                    woL = squareToCosineHemisphere(bsx, bsy);
+                    bsdfWeight = c->scene.albedo[its.material];
+                }
+                if (bsdfWeight.isZero()) { endCurrent(its.p); break; }
+                V3 wiW = -ray.d, woW = fr.toWorld(woL);
+                Float wiDotGeoN = dot(its.n, wiW), woDotGeoN = dot(its.n, woW);
+                if (wiDotGeoN * wi.z <= 0 || woDotGeoN * woL.z <= 0) { endCurrent(its.p); break; }     // [Veach, p. 158]
+                throughput *= bsdfWeight;
+                eta *= bEta;
+                if (bits & ALVRL_MAT_TRANSITION) inMedium = woDotGeoN > 0 ? (bits & ALVRL_MAT_EXTERIOR_MEDIUM) != 0 : (bits & ALVRL_MAT_INTERIOR_MEDIUM) != 0;
+                endCurrent(its.p);                                                                      // handleSurfaceScattering
+                cur.power = throughput * power; cur.start = its.p; curMedium = inMedium;
+                ray = Ray(its.p, woW, Epsilon, std::numeric_limits<Float>::infinity());
+            } else break;
+            if (depth++ >= rrDepth) {
+                Float q = std::min(throughput.max() * eta * eta, (Float) 0.95f);
+                if (smp->next1D() >= q) break;
+                throughput /= q;
+            }
+        }
+    }
+}
+} // namespace
+int orc_trace_vrls(void *h, uint32_t target) {
+    Ctx *c = (Ctx *) h;
+    if (!c->haveEmitter || !c->haveMedium || !c->haveMat) return seterr(ALVRL_ERR_STATE, "trace_vrls: set_area_emitter / set_medium / set_materials first");
+    if (c->medium.type != 0) return seterr(ALVRL_ERR_UNSUPPORTED, "trace_vrls: homogeneous media only");
+    ORC_TRY
+    if (!target) target = (uint32_t) c->P.vrlTargetNum;
+    CounterSampler smp(c->P.seed);
+    std::vector<TracedVrl> all;
+    uint64_t particles = 0;
+    while (all.size() < target) {                                          // randomWalk, vrlTracer.h:29-40
+        smp.setContext(ALVRL_RNG_TRACER, (uint32_t) particles, 0);
+        particles++;                                                       // m_vrls->nextParticle()
+        traceOneParticle(c, &smp, all);
+        if (particles > (1ull << 31)) throw std::runtime_error("trace_vrls: no VRLs are being generated");
+    }
+    c->vrls.clear();
+    for (const TracedVrl &t : all) { VRL v; v.power = t.power; v.start = t.start; v.end = t.end; c->vrls.push_back(v); }
+    c->particleCount = particles;
+    c->haveVrls = true; c->haveR = false; c->haveClusters = false;
+    ORC_CATCH
+}
+int orc_get_vrls(void *h, float *s, float *e, float *p, uint64_t *pc) {
+    Ctx *c = (Ctx *) h;
+    for (size_t i = 0; i < c->vrls.size(); i++) {
+        const VRL &v = c->vrls[i];
+        s[3 * i] = v.start.x; s[3 * i + 1] = v.start.y; s[3 * i + 2] = v.start.z; e[3 * i] = v.end.x; e[3 * i + 1] = v.end.y; e[3 * i + 2] = v.end.z;
+        p[3 * i] = v.power[0]; p[3 * i + 1] = v.power[1]; p[3 * i + 2] = v.power[2];
+    }
+    if (pc) *pc = c->particleCount;
+    return ALVRL_OK;
 }
 
 /* Film: ReconstructionFilter::configure / evalDiscretized (src/libcore/rfilter.cpp:37-55, include/mitsuba/core/rfilter.h:76-77),
