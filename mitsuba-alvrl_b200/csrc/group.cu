@@ -67,6 +67,8 @@ struct Member {
     alvrl_ctx *c = nullptr; int rank = 0; ncclComm_t comm = nullptr; bool owned = false;
     DevBuf<float4> fb; DevBuf<uint8_t> flags; DevBuf<float> rgb;
     uint32_t sliceBegin = 0, sliceEnd = 0;
+    /* load balance: cost estimate per slice, corrected after every frame by the ranks' measured times (identical on every rank) */
+    std::vector<double> sliceCost; DevBuf<float> times; cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::string err;
 };
 
@@ -99,16 +101,31 @@ void member_frame(alvrl_group *g, Member *m, float *rgbHost) {
     /* cost of a slice on a rank: its pixels (rows of R, refinement sweeps and render work grow with them) plus a constant per
      * Clustering object (picks, sorts and queue work do not depend on the rows): measured on C2, one object weighs about
      * 1/500 of all pixels */
-    std::vector<uint32_t> sizes(S);
     uint64_t totalPix = 0;
     for (uint32_t i = 0; i < S; i++) totalPix += c->sliceSize[i];
-    for (uint32_t i = 0; i < S; i++) sizes[i] = c->sliceSize[i] + (uint32_t) (totalPix / 500u);
+    const bool adaptive = g->world > 1 && !getenv("ALVRL_GROUP_STATIC");
+    if (m->sliceCost.size() != S) {
+        m->sliceCost.resize(S);
+        for (uint32_t i = 0; i < S; i++) m->sliceCost[i] = (double) c->sliceSize[i] + (double) (totalPix / 500u);
+    }
+    /* the ranges are cut on integer weights (sharding.h, shared with the CPU helpers): the cost estimates scaled to 2^20 */
+    std::vector<uint32_t> sizes(S);
+    {
+        double mx = 0;
+        for (uint32_t i = 0; i < S; i++) mx = std::max(mx, m->sliceCost[i]);
+        const bool first = !adaptive || m->ev[0] == nullptr;                    /* first frame: the pixel counts themselves */
+        for (uint32_t i = 0; i < S; i++)
+            sizes[i] = first ? c->sliceSize[i] + (uint32_t) (totalPix / 500u) : std::max<uint32_t>(1u, (uint32_t) (m->sliceCost[i] / mx * 1048576.0));
+    }
     balanced_slice_range(sizes.data(), S, g->world, m->rank, m->sliceBegin, m->sliceEnd);
+    if (adaptive && m->ev[0] == nullptr) for (int k = 0; k < 4; k++) ALVRL_CUDA(cudaEventCreate(&m->ev[k]));
+    if (adaptive) ALVRL_CUDA(cudaEventRecord(m->ev[0], c->stream));
     G_API(alvrl_set_slice_range(c, m->sliceBegin, m->sliceEnd));
     lap("slices");
     G_API(alvrl_sample_slice_mapping(c));
     G_API(alvrl_build_R(c));
     lap("mapping+R");
+    if (adaptive) ALVRL_CUDA(cudaEventRecord(m->ev[1], c->stream));
     const uint32_t N = (uint32_t) c->vrlHost.size(), P = c->numPixels();
     if (g->world > 1) {                                                      /* zero / non-zero columns over ALL rows: OR across ranks, on the device */
         m->flags.alloc(N);
@@ -119,12 +136,14 @@ void member_frame(alvrl_group *g, Member *m, float *rgbHost) {
         G_API(alvrl_set_column_nonzero(c, f.data()));
     } else G_API(alvrl_set_column_nonzero(c, nullptr));
     lap("flags");
+    if (adaptive) ALVRL_CUDA(cudaEventRecord(m->ev[2], c->stream));
     G_API(alvrl_build_clusters(c));
     lap("clusters");
     m->fb.alloc(P);
     ALVRL_CUDA(cudaMemsetAsync(m->fb.p, 0, (size_t) P * sizeof(float4), c->stream));
     G_API(alvrl_render_device(c, m->fb.p, c->stream));
     lap("render");
+    if (adaptive) ALVRL_CUDA(cudaEventRecord(m->ev[3], c->stream));
     if (g->world > 1) G_NCCL(nccl().Reduce(m->fb.p, m->fb.p, (size_t) P * 4, ncclFloat, ncclSum, 0, m->comm, c->stream));
     if (m->rank == 0 && rgbHost) {
         m->rgb.alloc(3 * (size_t) P);
@@ -134,6 +153,31 @@ void member_frame(alvrl_group *g, Member *m, float *rgbHost) {
     }
     ALVRL_CUDA(cudaStreamSynchronize(c->stream));
     lap("reduce+image");
+    if (adaptive) {
+        /* what this rank's range cost (R + clusters + render; the waits in the two exchanges excluded), known to every rank
+         * after an all-reduce of world floats; the estimates of a rank's slices are scaled by measured / predicted, damped */
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, m->ev[0], m->ev[1]); cudaEventElapsedTime(&b, m->ev[2], m->ev[3]);
+        std::vector<float> t((size_t) g->world, 0.0f);
+        t[m->rank] = a + b;
+        m->times.upload(t, c->stream);
+        G_NCCL(nccl().AllReduce(m->times.p, m->times.p, (size_t) g->world, ncclFloat, ncclSum, m->comm, c->stream));
+        m->times.download(t.data(), (size_t) g->world, c->stream);
+        double tot = 0, totCost = 0;
+        for (int r = 0; r < g->world; r++) tot += t[r];
+        for (uint32_t i = 0; i < S; i++) totCost += m->sliceCost[i];
+        if (tot > 0 && totCost > 0) {
+            for (int r = 0; r < g->world; r++) {
+                uint32_t b0, e0;
+                balanced_slice_range(sizes.data(), S, g->world, r, b0, e0);
+                double sum = 0;
+                for (uint32_t i = b0; i < e0; i++) sum += m->sliceCost[i];
+                if (!(sum > 0) || !(t[r] > 0)) continue;
+                const double scale = (t[r] / tot) / (sum / totCost);              /* measured share / predicted share */
+                for (uint32_t i = b0; i < e0; i++) m->sliceCost[i] *= 0.5 + 0.5 * scale;
+            }
+        }
+    }
     if (prof) fprintf(stderr, "[alvrl group] rank %d slices [%u, %u):%s | total %.1f ms\n", m->rank, m->sliceBegin, m->sliceEnd, log.c_str(), gnow_ms() - t0);
 }
 
@@ -251,7 +295,8 @@ void alvrl_group_destroy(alvrl_group_handle g) {
     if (!g) return;
     for (Member *m : g->members) {
         if (m->c) cudaSetDevice(m->c->device);
-        m->fb.release(); m->flags.release(); m->rgb.release();
+        m->fb.release(); m->flags.release(); m->rgb.release(); m->times.release();
+        for (int k = 0; k < 4; k++) if (m->ev[k]) cudaEventDestroy(m->ev[k]);
         if (m->comm) nccl().CommDestroy(m->comm);
         if (m->owned && m->c) alvrl_destroy(m->c);
     }
