@@ -68,7 +68,7 @@ struct Member {
     DevBuf<float4> fb; DevBuf<uint8_t> flags; DevBuf<float> rgb;
     uint32_t sliceBegin = 0, sliceEnd = 0;
     /* load balance: cost estimate per slice, corrected after every frame by the ranks' measured times (identical on every rank) */
-    std::vector<double> sliceCost; DevBuf<float> times; cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<double> sliceCost; uint32_t corrections = 0; DevBuf<float> times; cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::string err;
 };
 
@@ -174,8 +174,10 @@ void member_frame(alvrl_group *g, Member *m, float *rgbHost) {
                 for (uint32_t i = b0; i < e0; i++) sum += m->sliceCost[i];
                 if (!(sum > 0) || !(t[r] > 0)) continue;
                 const double scale = (t[r] / tot) / (sum / totCost);              /* measured share / predicted share */
-                for (uint32_t i = b0; i < e0; i++) m->sliceCost[i] *= 0.5 + 0.5 * scale;
+                const double alpha = m->corrections < 2u ? 1.0 : 0.5;                /* the first corrections in full, then damped */
+                for (uint32_t i = b0; i < e0; i++) m->sliceCost[i] *= (1.0 - alpha) + alpha * scale;
             }
+            m->corrections++;
         }
     }
     if (prof) fprintf(stderr, "[alvrl group] rank %d slices [%u, %u):%s | total %.1f ms\n", m->rank, m->sliceBegin, m->sliceEnd, log.c_str(), gnow_ms() - t0);
