@@ -174,7 +174,10 @@ void member_frame(alvrl_group *g, Member *m, float *rgbHost) {
                 for (uint32_t i = b0; i < e0; i++) sum += m->sliceCost[i];
                 if (!(sum > 0) || !(t[r] > 0)) continue;
                 const double scale = (t[r] / tot) / (sum / totCost);              /* measured share / predicted share */
-                const double alpha = m->corrections < 2u ? 1.0 : 0.5;                /* the first corrections in full, then damped */
+                /* a rank's time varies by +-15 % from frame to frame (the order in which k_refine_mt's tickets are drawn), so the
+                 * model error is taken out in the first two corrections and later ones only follow slowly; small deviations are left alone */
+                const double alpha = m->corrections < 2u ? 0.5 : 0.2;
+                if (std::fabs(scale - 1.0) < 0.05) continue;
                 for (uint32_t i = b0; i < e0; i++) m->sliceCost[i] *= (1.0 - alpha) + alpha * scale;
             }
             m->corrections++;
