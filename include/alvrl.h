@@ -195,6 +195,28 @@ int alvrl_set_area_emitter(alvrl_handle h, const uint32_t *emitter_tris, uint32_
 int alvrl_trace_vrls(alvrl_handle h, uint32_t target_num /* 0: params.vrlTargetNum */);
 int alvrl_get_vrls(alvrl_handle h, float *start_xyz, float *end_xyz, float *power_rgb, uint64_t *particle_count);
 
+/* ---- ground truth: volpath restricted to VRL paths ------------------------------------------------------
+ * VolumetricPathTracer::Li / Li_original with `onlyVRLpaths` (src/integrators/path/volpath.cpp:76-460: the unbiased estimate of
+ * exactly the light paths the VRL integrator renders -- first vertex in the volume or on a diffuse surface inside the medium,
+ * second vertex in the volume, initial specular vertices ignored) and rayIntersectAndLookForEmitter (484-535), driven like
+ * SamplingIntegrator::renderBlock (src/librender/integrator.cpp:210-268): `spp` samples per pixel (pixel centre when spp == 1,
+ * jittered otherwise), each the mean of `internalSamples` walks (volpath.cpp:111-120); box reconstruction filter, invalid
+ * samples rejected (imageblock.h:147-151).  Emitter sampling + phase / BSDF sampling combined by the power heuristic, Russian
+ * roulette from params.rrDepth on.  Needs alvrl_set_area_emitter; one homogeneous medium (the sensor sits in it), diffuse /
+ * smooth dielectric / smooth conductor surfaces, no index-matched (ENull) boundaries, no environment emitter.
+ * Outer sample j of pixel p draws from the counter stream of (ALVRL_RNG_VOLPATH, p, j); thread = pixel, one launch per outer
+ * sample, so the device image equals the oracle's bit for bit.  max_depth: -1 = unlimited (the `maxDepth` property).
+ * rgb_host: W*H*3 floats [y][x][c].  The image metric that goes with it (src/utils/rms.cpp) is mitsuba-alvrl_b200/rms.py. */
+#define ALVRL_VOLPATH_ONLY_VRL_PATHS  1u    /* onlyVRLpaths   (default true)  */
+#define ALVRL_VOLPATH_VOL_TO_VOL      2u    /* vrlVolToVol    (default true)  */
+#define ALVRL_VOLPATH_VOL_TO_SURF     4u    /* vrlVolToSurf   (default true)  */
+#define ALVRL_VOLPATH_SINGLE_SCATTER  8u    /* onlySingleScatter (default false) */
+#define ALVRL_VOLPATH_STRICT_NORMALS 16u    /* strictNormals  (default false) */
+#define ALVRL_VOLPATH_HIDE_EMITTERS  32u    /* hideEmitters   (default false) */
+#define ALVRL_VOLPATH_CENTRE_SAMPLES 64u    /* every sample through the pixel centre, as the VRL render pass does */
+#define ALVRL_VOLPATH_DEFAULT (ALVRL_VOLPATH_ONLY_VRL_PATHS | ALVRL_VOLPATH_VOL_TO_VOL | ALVRL_VOLPATH_VOL_TO_SURF)
+int alvrl_volpath_render(alvrl_handle h, uint32_t spp, uint32_t internalSamples, uint32_t flags, int32_t max_depth, float *rgb_host);
+
 /* ---- film: the step after the path -------------------------------------------------------------------
  * Reconstruction-filter splat and pass accumulation: ImageBlock::put (include/mitsuba/render/imageblock.h:124-202) with
  * the pre-rasterised filter of ReconstructionFilter::configure / evalDiscretized (src/libcore/rfilter.cpp:37-55,

@@ -46,7 +46,8 @@ enum {
     ALVRL_RNG_SLICEMAP = 3,
     ALVRL_RNG_CLUSTER  = 4,
     ALVRL_RNG_CHAIN    = 5,    /* a = pixel index, b = path code of the branch: the roulette draw of LiInternal (485) */
-    ALVRL_RNG_TRACER   = 6     /* a = particle index, b = 0: the draws of vrlTracer::traceOneParticle in their order */
+    ALVRL_RNG_TRACER   = 6,    /* a = particle index, b = 0: the draws of vrlTracer::traceOneParticle in their order */
+    ALVRL_RNG_VOLPATH  = 7     /* a = pixel index, b = outer sample index: the draws of renderBlock + VolumetricPathTracer::Li */
 };
 #define ALVRL_RNG_GLOBAL_ID 0xfffffffeu
 

@@ -173,6 +173,16 @@ class Integrator:
         self._call("get_vrls", _p(s), _p(e), _p(p), C.byref(pc))
         return s, e, p, pc.value
 
+    # -- ground truth: volpath restricted to VRL paths (include/alvrl.h) -------------------------------
+    VOLPATH_ONLY_VRL_PATHS, VOLPATH_VOL_TO_VOL, VOLPATH_VOL_TO_SURF, VOLPATH_SINGLE_SCATTER = 1, 2, 4, 8
+    VOLPATH_STRICT_NORMALS, VOLPATH_HIDE_EMITTERS, VOLPATH_CENTRE_SAMPLES, VOLPATH_DEFAULT = 16, 32, 64, 7
+
+    def volpath_render(self, spp=1, internal_samples=1, flags=7, max_depth=-1):
+        """VolumetricPathTracer with onlyVRLpaths (volpath.cpp:76-460): image [H, W, 3]"""
+        out = np.zeros((self.H, self.W, 3), dtype=np.float32)
+        self._call("volpath_render", C.c_uint32(spp), C.c_uint32(internal_samples), C.c_uint32(flags), C.c_int32(max_depth), _p(out))
+        return out
+
     def set_material_optics(self, optics):
         o = _f32(optics).reshape(-1, 12)
         self._call("set_material_optics", _p(o), C.c_uint32(len(o)))

@@ -27,8 +27,9 @@ build_one slices_dev.cu -fmad=false
 build_one film.cu -fmad=false
 build_one chain.cu -fmad=false
 build_one tracer.cu -fmad=false
+build_one volpath.cu -fmad=false
 fail=0
 for p in "${pids[@]}"; do wait "$p" || fail=1; done
 if [ $fail -ne 0 ]; then echo "build.sh: compilation failed" >&2; exit 1; fi
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $OUT obj/primary.o obj/transport_strict.o obj/transport_fast.o obj/clustering.o obj/capi.o obj/group.o obj/slices_dev.o obj/film.o obj/chain.o obj/tracer.o -ldl
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $OUT obj/primary.o obj/transport_strict.o obj/transport_fast.o obj/clustering.o obj/capi.o obj/group.o obj/slices_dev.o obj/film.o obj/chain.o obj/tracer.o obj/volpath.o -ldl
 echo "built $OUT"

@@ -895,6 +895,11 @@ int alvrl_set_area_emitter(alvrl_handle c, const uint32_t *tris, uint32_t n, con
     c->emCdf.back() = 1.0f;
     for (int k = 0; k < 3; k++) c->emPower[k] = radiance[k] * (float) M_PI * sum;          /* area.cpp:198 */
     c->dEmTris.upload(c->emTris, c->stream); c->dEmCdf.upload(c->emCdf, c->stream);
+    for (int k = 0; k < 3; k++) c->emRadiance[k] = radiance[k];
+    c->emInvArea = normalization;                                                           /* TriMesh::m_invSurfaceArea, trimesh.cpp:401 */
+    std::vector<uint8_t> isEm(nt, 0);                                                       /* Shape::isEmitter of the triangle's shape */
+    for (uint32_t i = 0; i < n; i++) isEm[tris[i]] = 1;
+    c->dTriEmitter.upload(isEm, c->stream);
     c->haveEmitter = true;
     API_END
 }
@@ -944,6 +949,37 @@ int alvrl_trace_vrls(alvrl_handle c, uint32_t target) {
     for (uint32_t i = 0; i < n; i++) for (int k = 0; k < 3; k++) { s[3 * (size_t) i + k] = rec[9 * (size_t) i + k]; e[3 * (size_t) i + k] = rec[9 * (size_t) i + 3 + k]; p[3 * (size_t) i + k] = rec[9 * (size_t) i + 6 + k]; }
     const int rc = alvrl_set_vrls(c, s.data(), e.data(), p.data(), n, cut);               /* the put() filter already ran on the device: nothing is dropped */
     if (rc != ALVRL_OK) return rc;
+    API_END
+}
+
+int alvrl_volpath_render(alvrl_handle c, uint32_t spp, uint32_t internalSamples, uint32_t flags, int32_t maxDepth, float *rgb) {
+    API_BEGIN
+    use_device(c);
+    if (!c->haveEmitter || !c->haveMedium || !c->haveMat || !c->haveCam) throw Error(ALVRL_ERR_STATE, "alvrl_volpath_render: set_area_emitter / set_medium / set_materials / set_camera first");
+    if (c->medium.type != 0) throw Error(ALVRL_ERR_UNSUPPORTED, "alvrl_volpath_render: homogeneous media only");
+    if (!spp || !internalSamples || !rgb) throw Error(ALVRL_ERR_ARG, "alvrl_volpath_render: spp and internalSamples must be positive");
+    if (flags & ~127u) throw Error(ALVRL_ERR_ARG, "alvrl_volpath_render: unknown flag bits");
+    ensure_scene(c);
+    bool anyDelta = false;
+    for (uint32_t b : c->matBits) if (b & ALVRL_BSDF_DELTA) anyDelta = true;
+    if (anyDelta && c->optics.size() != 12 * c->matBits.size()) throw Error(ALVRL_ERR_STATE, "materials with delta components need alvrl_set_material_optics");
+    if (!anyDelta && c->dMatOptics.n == 0) { std::vector<float4> z(3 * std::max<size_t>(1, c->matBits.size()), make_float4(0, 0, 0, 0)); c->dMatOptics.upload(z, c->stream); }
+    const uint32_t P = c->numPixels();
+    c->dVolpathAcc.alloc(P);
+    ALVRL_CUDA(cudaMemsetAsync(c->dVolpathAcc.p, 0, (size_t) P * sizeof(float4), c->stream));
+    const bool centre = spp == 1 || (flags & ALVRL_VOLPATH_CENTRE_SAMPLES);                /* integrator.cpp:240-246 */
+    for (uint32_t j = 0; j < spp; j++) {                                                    /* one outer sample of every pixel per launch: the film's order */
+        launch_volpath_sample(c->sceneDev, c->medium, c->cam, c->dEmTris.p, c->dEmCdf.p, (uint32_t) c->emTris.size(), c->emRadiance, c->emInvArea, c->dTriEmitter.p,
+                              c->dTriVerts.p, c->dTriMat.p, c->dMatAlbedo.p, c->dMatBits.p, c->dMatOptics.p, c->P.seed, j, (int) internalSamples, flags, centre,
+                              maxDepth, c->P.rrDepth, c->dVolpathAcc.p, c->stream);
+        c->stats.kernelLaunches++;
+    }
+    ALVRL_CUDA(cudaGetLastError());
+    c->dVolpathRgb.alloc(3 * (size_t) P);
+    launch_volpath_develop(c->dVolpathAcc.p, c->cam.W, c->cam.H, c->dVolpathRgb.p, c->stream);
+    c->stats.kernelLaunches++;
+    ALVRL_CUDA(cudaGetLastError());
+    c->dVolpathRgb.download(rgb, 3 * (size_t) P, c->stream);
     API_END
 }
 

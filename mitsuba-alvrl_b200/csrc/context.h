@@ -147,6 +147,8 @@ struct alvrl_ctx {
     /* VRL tracer (tracer.cu): the area emitter */
     std::vector<uint32_t> emTris; std::vector<float> emCdf; float emPower[3] = {0, 0, 0}; bool haveEmitter = false;
     alvrl::DevBuf<uint32_t> dEmTris; alvrl::DevBuf<float> dEmCdf;
+    /* ground truth (volpath.cu): the emitter's radiance, 1 / area, Shape::isEmitter per triangle; {rgb, weight} accumulator */
+    float emRadiance[3] = {0, 0, 0}, emInvArea = 0; alvrl::DevBuf<uint8_t> dTriEmitter; alvrl::DevBuf<float4> dVolpathAcc; alvrl::DevBuf<float> dVolpathRgb;
     /* specular chains (chain.cu): the segments below the camera segments, grouped by pixel */
     std::vector<float> optics; alvrl::DevBuf<float4> dMatOptics; bool anyDelta = false, chainsValid = false;
     std::vector<uint32_t> chainOffset;                 /* P + 1 */

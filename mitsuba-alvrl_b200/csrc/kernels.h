@@ -34,6 +34,13 @@ void launch_trace_write(const SceneDev &sc, const MediumDev &med, const uint32_t
                         uint64_t seed, int shortVrls, int maxDepth, int rrDepth, const float4 *triVerts, const uint32_t *triMat, const float4 *matAlbedo,
                         const uint32_t *matBits, const float4 *matOptics, uint32_t n, const uint32_t *offset, float *out, cudaStream_t st);
 
+/* volpath.cu (exact arithmetic): VolumetricPathTracer with onlyVRLpaths, one outer sample of every pixel per launch */
+void launch_volpath_sample(const SceneDev &sc, const MediumDev &med, const CameraDev &cam, const uint32_t *emTris, const float *emCdf, uint32_t emN,
+                           const float emRadiance[3], float emInvArea, const uint8_t *triEmitter, const float4 *triVerts, const uint32_t *triMat,
+                           const float4 *matAlbedo, const uint32_t *matBits, const float4 *matOptics, uint64_t seed, uint32_t sample, int internalSamples,
+                           uint32_t flags, bool centre, int maxDepth, int rrDepth, float4 *acc, cudaStream_t st);
+void launch_volpath_develop(const float4 *acc, uint32_t W, uint32_t H, float *rgb, cudaStream_t st);
+
 /* film.cu (exact arithmetic) */
 void launch_film_splat(const float4 *fb, uint32_t W, uint32_t H, const FilmFilterDev &f, float *acc, cudaStream_t st);
 void launch_film_develop(const float *acc, uint32_t n, float *rgb, cudaStream_t st);

@@ -27,7 +27,8 @@ struct Ctx {
     std::vector<VRL> vrls; uint64_t particleCount = 0;
     std::vector<Ray> rays; std::vector<Intersection> hits;       // per pixel index y + H*x
     /* area emitter of the VRL tracer: the triangles of its shape, TriMesh::prepareSamplingTable (trimesh.cpp:388-403) */
-    std::vector<uint32_t> emTris; std::vector<Float> emCdf; Float emInvArea = 0; Spec emPower; bool haveEmitter = false;
+    std::vector<uint32_t> emTris; std::vector<Float> emCdf; Float emInvArea = 0; Spec emPower, emRadiance; bool haveEmitter = false;
+    std::vector<uint8_t> triIsEmitter;                            // Shape::isEmitter of the triangle's shape
     bool havePrimary = false;
     struct ChainSeg { Ray ray; Intersection its; Spec weight; bool inMedium; uint32_t code; };
     std::vector<std::vector<ChainSeg>> chains; bool haveChains = false; bool anyDelta = false;   // vrlIntegrator.cpp:445-511
@@ -889,6 +890,9 @@ int orc_set_area_emitter(void *h, const uint32_t *tris, uint32_t n, const float 
     c->emCdf.back() = 1.0f;
     c->emInvArea = 1.0f / sum;
     c->emPower = Spec(radiance[0], radiance[1], radiance[2]) * (Float) M_PI * sum;       // area.cpp:198
+    c->emRadiance = Spec(radiance[0], radiance[1], radiance[2]);
+    c->triIsEmitter.assign(c->scene.numTris(), 0);
+    for (uint32_t i = 0; i < n; i++) c->triIsEmitter[tris[i]] = 1;
     c->haveEmitter = true;
     return ALVRL_OK;
 }
@@ -1096,6 +1100,303 @@ int orc_get_vrls(void *h, float *s, float *e, float *p, uint64_t *pc) {
     }
     if (pc) *pc = c->particleCount;
     return ALVRL_OK;
+}
+
+/* ---- ground truth: the volumetric path tracer restricted to the paths VRLs represent --------------------------------
+ * VolumetricPathTracer::Li / Li_original with onlyVRLpaths (src/integrators/path/volpath.cpp:76-460) and
+ * rayIntersectAndLookForEmitter (484-535), driven like SamplingIntegrator::renderBlock (src/librender/integrator.cpp:210-268:
+ * one sample at the pixel centre when the sample count is 1, jittered otherwise; this fork's rule, 240-246), for the scenes of
+ * this path: one homogeneous medium, one area emitter (Scene::sampleAttenuatedEmitterDirect, scene.cpp:854-899;
+ * AreaLight::sampleDirect / pdfDirect / eval, src/emitters/area.cpp:103-108,158-183; Shape::sampleDirect / pdfDirect,
+ * shape.cpp:102-126; TriMesh::samplePosition, trimesh.cpp:412-423), diffuse / smooth dielectric / smooth conductor surfaces
+ * (diffuse.cpp:110-148, dielectric.cpp:281-332, conductor.cpp:268-283), no ENull surfaces (so the emitter search is one
+ * intersection), no environment emitter, no subsurface integrator.  The film is the box filter: every sample lands in its
+ * own pixel and the developed value is the sum times 1 / (sum of weights) (bitmap.cpp:1617-1624); invalid samples are
+ * rejected like ImageBlock::put (imageblock.h:147-151).  Outer sample j of pixel p draws from the counter stream of
+ * (ALVRL_RNG_VOLPATH, p, j) in the reference's order; its internalSamples walks continue that stream (volpath.cpp:111-120). */
+namespace {
+struct VolpathCfg { bool only, volToVol, volToSurf, singleScatter, strictNormals, hideEmitters; int internalSamples, maxDepth, rrDepth; };
+struct DirectRec { V3 ref, refN, p, n, d; Float dist = 0, pdf = 0; };
+
+inline Float miWeight(Float pdfA, Float pdfB) { pdfA *= pdfA; pdfB *= pdfB; return pdfA / (pdfA + pdfB); }             // volpath.cpp:537-540
+
+/* HomogeneousMedium::sampleDistance(Ray(ray, 0, itsT), mRec, sampler), homogeneous.cpp:275-352 (strategy = balance) */
+struct MRec { Spec transmittance, sigmaS; Float pdfFailure = 1, pdfSuccess = 1; V3 p; };
+inline bool sampleDistanceH(const Medium &med, const Ray &ray, Float itsT, Sampler *smp, MRec &m) {
+    Float rnd = smp->next1D(), sampledDistance;
+    Float samplingDensity = 0;
+    if (rnd < med.samplingWeight) {
+        rnd /= med.samplingWeight;
+        int channel = std::min((int) (smp->next1D() * 3), 2);
+        samplingDensity = med.sigmaT[channel];
+        sampledDistance = -((Float) ::log((double) (1 - rnd))) / samplingDensity;
+    } else sampledDistance = std::numeric_limits<Float>::infinity();
+    Float distSurf = itsT - 0;
+    bool success = true;
+    if (sampledDistance < distSurf) {
+        Float t = sampledDistance + 0;
+        m.p = ray.o + t * ray.d;
+        m.sigmaS = med.sigmaS;
+        if (m.p.x == ray.o.x && m.p.y == ray.o.y && m.p.z == ray.o.z) success = false;
+    } else { sampledDistance = distSurf; success = false; }
+    m.pdfFailure = 0; m.pdfSuccess = 0;
+    for (int i = 0; i < 3; ++i) { Float tmp = fastexp(-med.sigmaT[i] * sampledDistance); m.pdfFailure += tmp; m.pdfSuccess += med.sigmaT[i] * tmp; }
+    m.pdfFailure /= 3; m.pdfSuccess /= 3;
+    for (int i = 0; i < 3; ++i) m.transmittance[i] = fastexp(med.sigmaT[i] * (-sampledDistance));
+    m.pdfSuccess = m.pdfSuccess * med.samplingWeight;
+    m.pdfFailure = med.samplingWeight * m.pdfFailure + (1 - med.samplingWeight);
+    if (m.transmittance.max() < 1e-20) m.transmittance = Spec(0.0f);
+    return success;
+}
+
+/* emitter->sampleDirect(dRec, sample): AreaLight::sampleDirect over Shape::sampleDirect over TriMesh::samplePosition
+ * (area.cpp:158-174, shape.cpp:102-115, trimesh.cpp:412-423, triangle.cpp:24-45); returns radiance / pdf, fills dRec */
+inline Spec emitterSampleDirect(Ctx *c, DirectRec &dRec, Float sx, Float sy) {
+    /* one emitter: m_emitterPDF.sampleReuse(sample.x) leaves the sample unchanged, emPdf = 1 (scene.cpp:860-862) */
+    std::vector<Float>::const_iterator entry = std::lower_bound(c->emCdf.begin(), c->emCdf.end(), sy);                  // pmf.h:123-135
+    size_t index = std::min(c->emCdf.size() - 2, (size_t) std::max((ptrdiff_t) 0, entry - c->emCdf.begin() - 1));
+    while ((c->emCdf[index + 1] - c->emCdf[index]) == 0 && index < c->emCdf.size() - 1) ++index;
+    sy = (sy - c->emCdf[index]) / (c->emCdf[index + 1] - c->emCdf[index]);
+    const uint32_t tri = c->emTris[index];
+    const V3 &p0 = c->scene.verts[c->scene.tris[3 * tri]], &p1 = c->scene.verts[c->scene.tris[3 * tri + 1]], &p2 = c->scene.verts[c->scene.tris[3 * tri + 2]];
+    Float a = safe_sqrt(1.0f - sx);
+    Float bx = 1 - a, by = a * sy;
+    V3 sideA = p1 - p0, sideB = p2 - p0;
+    dRec.p = p0 + (sideA * bx) + (sideB * by);
+    dRec.n = normalize(cross(sideA, sideB));
+    dRec.pdf = c->emInvArea;
+    dRec.d = dRec.p - dRec.ref;
+    Float distSquared = dRec.d.lengthSquared();
+    dRec.dist = std::sqrt(distSquared);
+    dRec.d = dRec.d / dRec.dist;
+    Float dp = std::abs(dot(dRec.d, dRec.n));
+    dRec.pdf *= dp != 0 ? (distSquared / dp) : 0.0f;
+    if (dot(dRec.d, dRec.refN) >= 0 && dot(dRec.d, dRec.n) < 0 && dRec.pdf != 0) return c->emRadiance / dRec.pdf;
+    dRec.pdf = 0.0f;
+    return Spec(0.0f);
+}
+/* Scene::evalTransmittance(ref, refOnSurface, p, true, ...) in the medium or in vacuum, scene.cpp:619-679 without ENull surfaces */
+inline Spec shadowTransmittance(Ctx *c, const V3 &ref, bool refOnSurface, const V3 &p, bool inMedium) {
+    V3 d = p - ref;
+    Float remaining = d.length();
+    d = d / remaining;
+    Ray ray(ref, d, refOnSurface ? Epsilon : 0, remaining * (1 - ShadowEpsilon));
+    if (!(remaining > 0)) return Spec(1.0f);
+    Float t, u, v; uint32_t prim;
+    if (c->scene.closestHit(ray, true, t, prim, u, v, nullptr)) return Spec(0.0f);
+    if (!inMedium) return Spec(1.0f);
+    return c->medium.evalTransmittance(Ray(ray.o, ray.d, 0, std::min(t, remaining)));
+}
+inline Float pdfEmitterDirect(Ctx *c, const DirectRec &dRec) {                                                           // scene.cpp:949-952, area.cpp:176-183, shape.cpp:117-121
+    if (dot(dRec.d, dRec.refN) >= 0 && dot(dRec.d, dRec.n) < 0) return c->emInvArea * (dRec.dist * dRec.dist) / std::abs(dot(dRec.d, dRec.n));
+    return 0.0f;
+}
+
+Spec volpathLiOriginal(Ctx *c, const VolpathCfg &cfg, Sampler *smp, const Ray &r, bool sensorInMedium) {
+    Medium &med = c->medium;
+    Ray ray(r);
+    Spec Li(0.0f);
+    Float eta = 1.0f;
+    bool vrlFirstVertexOK = false, vrlSecondVertexOK = false, prevWasDiffuseSurface = false, prevWasVolume = false;
+    bool inMedium = sensorInMedium;
+    int depth = 1;
+    bool emitted = true, indirectMedium = true;                          // rRec.type: ERadiance, later ERadianceNoEmission
+    Intersection its;
+    c->scene.rayIntersect(ray, its);
+    Spec throughput(1.0f);
+    bool scattered = false;
+    auto vrlDirectOK = [&]() {
+        /* (!rRec.depth == 2 || ...) of the reference is ((!depth) == 2 || ...): the first operand is never true */
+        return !cfg.only || (depth != 1 && ((prevWasVolume || prevWasDiffuseSurface) && (!prevWasDiffuseSurface || cfg.volToSurf) && (!prevWasVolume || cfg.volToVol)));
+    };
+    /* rayIntersectAndLookForEmitter without ENull surfaces: one intersection; an emitter that is hit gives its unattenuated radiance */
+    auto lookForEmitter = [&](const Ray &q, DirectRec &dRec, Spec &value) {
+        bool surface = c->scene.rayIntersect(q, its);
+        if (surface && c->triIsEmitter[its.prim]) {
+            dRec.p = its.p; dRec.n = its.n; dRec.d = q.d; dRec.dist = its.t;                                            // setQuery, records.inl:170-178
+            value = dot(its.n, -q.d) <= 0 ? Spec(0.0f) : c->emRadiance;                                                 // area.cpp:103-108
+        }
+    };
+    while (depth <= cfg.maxDepth || cfg.maxDepth < 0) {
+        if (cfg.only && depth > 2 && !(vrlFirstVertexOK && vrlSecondVertexOK)) break;
+        MRec mRec;
+        if (inMedium && sampleDistanceH(med, ray, its.t, smp, mRec)) {
+            if (cfg.singleScatter) indirectMedium = false;
+            if (depth == 1) { if (cfg.volToVol) vrlFirstVertexOK = true; }
+            if (depth == 2) vrlSecondVertexOK = true;
+            if (depth >= cfg.maxDepth && cfg.maxDepth != -1) break;
+            throughput *= mRec.sigmaS * mRec.transmittance / mRec.pdfSuccess;
+            DirectRec dRec; dRec.ref = mRec.p; dRec.refN = V3(0.0f);
+            if (vrlDirectOK()) {
+                Float sx = smp->next1D(), sy = smp->next1D();
+                Spec value = emitterSampleDirect(c, dRec, sx, sy);                                                      // sampleAttenuatedEmitterDirect, scene.cpp:854-874
+                if (dRec.pdf != 0) value *= shadowTransmittance(c, dRec.ref, false, dRec.p, inMedium);
+                if (!value.isZero()) {
+                    Float phaseVal = med.phaseEval(-ray.d, dRec.d);
+                    if (phaseVal != 0) {
+                        Float phasePdf = phaseVal;                                                                      // PhaseFunction::pdf = eval
+                        const Float weight = miWeight(dRec.pdf, phasePdf);
+                        Li += throughput * value * phaseVal * weight;
+                    }
+                }
+            }
+            /* phase function sampling: sample(pRec, pdf, sampler) returns 1 (isotropic.cpp:69-74, hg.cpp:99-104) */
+            Float phasePdf;
+            Float px = smp->next1D(), py = smp->next1D();
+            V3 wo;
+            if (med.phaseType == ALVRL_PHASE_ISOTROPIC) { wo = squareToUniformSphere(px, py); phasePdf = INV_FOURPI; }
+            else {
+                Float cosTheta;
+                if (std::abs(med.g) < Epsilon) cosTheta = 1 - 2 * px;
+                else { Float sqrTerm = (1 - med.g * med.g) / (1 - med.g + 2 * med.g * px); cosTheta = (1 + med.g * med.g - sqrTerm * sqrTerm) / (2 * med.g); }
+                Float sinTheta = safe_sqrt(1.0f - cosTheta * cosTheta), sinPhi, cosPhi;
+                sincosF((Float) (2 * M_PI * py), &sinPhi, &cosPhi);
+                wo = frameToWorld(ray.d, V3(sinTheta * cosPhi, sinTheta * sinPhi, cosTheta));                           // Frame(-pRec.wi), wi = -ray.d
+                phasePdf = med.phaseEval(-ray.d, wo);
+            }
+            ray = Ray(mRec.p, wo, 0, std::numeric_limits<Float>::infinity());
+            Spec value(0.0f);
+            lookForEmitter(ray, dRec, value);
+            if (!value.isZero() && vrlDirectOK()) {
+                const Float emitterPdf = pdfEmitterDirect(c, dRec);
+                Li += throughput * value * miWeight(phasePdf, emitterPdf);
+            }
+            if (!indirectMedium) break;
+            emitted = false;
+            prevWasVolume = true; prevWasDiffuseSurface = false;
+        } else {
+            if (inMedium) throughput *= mRec.transmittance / mRec.pdfFailure;
+            if (!its.isValid()) break;                                   // no environment emitter
+            if (c->triIsEmitter[its.prim] && emitted && (!cfg.hideEmitters || scattered) && (!cfg.only || (vrlFirstVertexOK && vrlSecondVertexOK)))
+                Li += throughput * (dot(its.n, -ray.d) <= 0 ? Spec(0.0f) : c->emRadiance);
+            if (depth >= cfg.maxDepth && cfg.maxDepth != -1) break;
+            const uint32_t bits = c->scene.matBits[its.material];
+            const HitFrame fr = c->scene.hitFrame(its);
+            const V3 wi = fr.toLocal(-ray.d);
+            Float wiDotGeoN = -dot(its.n, ray.d), wiDotShN = wi.z;
+            if (wiDotGeoN * wiDotShN < 0 && cfg.strictNormals) break;
+            const bool smooth = !(bits & ALVRL_BSDF_DELTA) && (bits & ALVRL_BSDF_SMOOTH);
+            DirectRec dRec; dRec.ref = its.p; dRec.refN = (bits & ALVRL_BSDF_DIELECTRIC) ? V3(0.0f) : its.n;            // records.inl:160-164
+            const Intersection here = its;
+            if (smooth && (!cfg.only || (vrlFirstVertexOK && vrlSecondVertexOK))) {
+                Float sx = smp->next1D(), sy = smp->next1D();
+                Spec value = emitterSampleDirect(c, dRec, sx, sy);                                                      // scene.cpp:876-899
+                if (dRec.pdf != 0) {
+                    bool shadowMedium = inMedium;                                                                       // its.getTargetMedium(dRec.d)
+                    if (bits & ALVRL_MAT_TRANSITION) shadowMedium = dot(dRec.d, here.n) > 0 ? (bits & ALVRL_MAT_EXTERIOR_MEDIUM) != 0 : (bits & ALVRL_MAT_INTERIOR_MEDIUM) != 0;
+                    value *= shadowTransmittance(c, here.p, true, dRec.p, shadowMedium);
+                }
+                if (!value.isZero()) {
+                    const V3 woL = fr.toLocal(dRec.d);
+                    Spec bsdfVal(0.0f);                                                                                 // diffuse.cpp:110-118
+                    if (!(wi.z <= 0 || woL.z <= 0)) bsdfVal = c->scene.albedo[here.material] * (INV_PI * woL.z);
+                    Float woDotGeoN = dot(here.n, dRec.d);
+                    if (!bsdfVal.isZero() && (!cfg.strictNormals || woDotGeoN * woL.z > 0)) {
+                        Float bsdfPdf = (wi.z <= 0 || woL.z <= 0) ? 0.0f : INV_PI * woL.z;                              // diffuse.cpp:120-127, warp.h
+                        const Float weight = miWeight(dRec.pdf, bsdfPdf);
+                        Li += throughput * value * bsdfVal * weight;
+                    }
+                }
+            }
+            /* BSDF sampling: sample(bRec, pdf, nextSample2D()), mode = ERadiance */
+            Float bsx = smp->next1D(), bsy = smp->next1D();
+            V3 woL; Float bEta = 1.0f, bsdfPdf = 0; Spec bsdfWeight(0.0f); bool delta = false;
+            if (bits & ALVRL_BSDF_DIELECTRIC) {                                                                         // dielectric.cpp:281-332
+                const Optics &o = c->scene.optics[here.material];
+                const Float e = o.v[0], invE = 1 / e;
+                Float cosThetaT;
+                Float F = fresnelDielectricExt(wi.z, cosThetaT, e);
+                delta = true;
+                if (bsx <= F) { woL = V3(-wi.x, -wi.y, wi.z); bEta = 1.0f; bsdfPdf = F; bsdfWeight = Spec(o.v[6], o.v[7], o.v[8]); }
+                else {
+                    Float scale = -(cosThetaT < 0 ? invE : e);
+                    woL = V3(scale * wi.x, scale * wi.y, cosThetaT);
+                    bEta = cosThetaT < 0 ? e : invE;
+                    bsdfPdf = 1 - F;
+                    Float factor = cosThetaT < 0 ? invE : e;
+                    bsdfWeight = Spec(o.v[9], o.v[10], o.v[11]) * (factor * factor);
+                }
+            } else if (bits & ALVRL_BSDF_CONDUCTOR) {                                                                   // conductor.cpp:268-283
+                const Optics &o = c->scene.optics[here.material];
+                if (wi.z > 0) {
+                    delta = true;
+                    woL = V3(-wi.x, -wi.y, wi.z); bsdfPdf = 1;
+                    bsdfWeight = Spec(o.v[6], o.v[7], o.v[8]) * Spec(fresnelConductorExact(wi.z, o.v[0], o.v[3]), fresnelConductorExact(wi.z, o.v[1], o.v[4]), fresnelConductorExact(wi.z, o.v[2], o.v[5]));
+                }
+            } else if ((bits & ALVRL_BSDF_SMOOTH) && wi.z > 0) {                                                        // diffuse.cpp:139-148
+                woL = squareToCosineHemisphere(bsx, bsy);
+                bsdfPdf = INV_PI * woL.z;
+                bsdfWeight = c->scene.albedo[here.material];
+            }
+            if (bsdfWeight.isZero()) break;
+            const V3 wo = fr.toWorld(woL);
+            Float woDotGeoN = dot(here.n, wo);
+            if (woDotGeoN * woL.z <= 0 && cfg.strictNormals) break;
+            if (depth == 1 && delta) depth--;                            // 'undo' initial specular vertices
+            if (cfg.volToSurf) { if (depth == 1 && inMedium && !delta) vrlFirstVertexOK = true; }
+            prevWasVolume = false;
+            prevWasDiffuseSurface = !delta;
+            ray = Ray(here.p, wo, Epsilon, std::numeric_limits<Float>::infinity());
+            throughput *= bsdfWeight;
+            eta *= bEta;
+            if (bits & ALVRL_MAT_TRANSITION) inMedium = dot(here.n, ray.d) > 0 ? (bits & ALVRL_MAT_EXTERIOR_MEDIUM) != 0 : (bits & ALVRL_MAT_INTERIOR_MEDIUM) != 0;
+            Spec value(0.0f);
+            lookForEmitter(ray, dRec, value);
+            if (!value.isZero() && (!cfg.only || (vrlFirstVertexOK && vrlSecondVertexOK))) {
+                const Float emitterPdf = !delta ? pdfEmitterDirect(c, dRec) : 0;
+                Li += throughput * value * miWeight(bsdfPdf, emitterPdf);
+            }
+            emitted = false;
+        }
+        if (depth++ >= cfg.rrDepth) {
+            Float q = std::min(throughput.max() * eta * eta, (Float) 0.95f);
+            if (smp->next1D() >= q) break;
+            throughput /= q;
+        }
+        scattered = true;
+    }
+    if (cfg.only && !(vrlFirstVertexOK && vrlSecondVertexOK)) Li *= 0;
+    return Li;
+}
+} // namespace
+int orc_volpath_render(void *h, uint32_t spp, uint32_t internalSamples, uint32_t flags, int32_t maxDepth, float *rgb) {
+    Ctx *c = (Ctx *) h;
+    if (!c->haveEmitter || !c->haveMedium || !c->haveMat || !c->haveCam) return seterr(ALVRL_ERR_STATE, "volpath_render: set_area_emitter / set_medium / set_materials / set_camera first");
+    if (c->medium.type != 0) return seterr(ALVRL_ERR_UNSUPPORTED, "volpath_render: homogeneous media only");
+    if (!spp || !internalSamples) return seterr(ALVRL_ERR_ARG, "volpath_render: spp and internalSamples must be positive");
+    ORC_TRY
+    VolpathCfg cfg;
+    cfg.only = flags & ALVRL_VOLPATH_ONLY_VRL_PATHS; cfg.volToVol = flags & ALVRL_VOLPATH_VOL_TO_VOL; cfg.volToSurf = flags & ALVRL_VOLPATH_VOL_TO_SURF;
+    cfg.singleScatter = flags & ALVRL_VOLPATH_SINGLE_SCATTER; cfg.strictNormals = flags & ALVRL_VOLPATH_STRICT_NORMALS; cfg.hideEmitters = flags & ALVRL_VOLPATH_HIDE_EMITTERS;
+    cfg.internalSamples = (int) internalSamples; cfg.maxDepth = maxDepth; cfg.rrDepth = c->P.rrDepth;
+    const bool centre = spp == 1 || (flags & ALVRL_VOLPATH_CENTRE_SAMPLES);
+    const uint32_t W = c->cam.W, H = c->cam.H;
+    auto work = [&](uint32_t x0, uint32_t x1) {
+        CounterSampler smp(c->P.seed);
+        for (uint32_t x = x0; x < x1; x++) for (uint32_t y = 0; y < H; y++) {
+            const uint32_t pix = x * H + y;
+            Spec sum(0.0f); Float weight = 0;
+            for (uint32_t j = 0; j < spp; j++) {
+                smp.setContext(ALVRL_RNG_VOLPATH, pix, j);
+                Float ox = 0.5f, oy = 0.5f;
+                if (!centre) { ox = smp.next1D(); oy = smp.next1D(); }                                                   // integrator.cpp:240-246
+                const Ray ray = c->cam.sampleRay((Float) x + ox, (Float) y + oy);
+                Spec Li(0.0f);                                                                                          // volpath.cpp:111-120
+                for (int i = 0; i < cfg.internalSamples; i++) Li += volpathLiOriginal(c, cfg, &smp, ray, true);
+                Li = Li / (Float) cfg.internalSamples;
+                if (!Li.isValid()) continue;                                                                            // imageblock.h:147-151
+                sum += Li; weight += 1.0f;
+            }
+            const Float invWeight = weight == 0 ? 0 : (Float) 1 / weight;
+            float *o = rgb + 3 * ((size_t) y * W + x);
+            for (int k = 0; k < 3; k++) o[k] = sum[k] * invWeight;
+        }
+    };
+    int T = std::max(1, c->threads);
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; t++) th.emplace_back(work, (uint32_t) ((uint64_t) W * t / T), (uint32_t) ((uint64_t) W * (t + 1) / T));
+    for (auto &t : th) t.join();
+    ORC_CATCH
 }
 
 /* Film: ReconstructionFilter::configure / evalDiscretized (src/libcore/rfilter.cpp:37-55, include/mitsuba/core/rfilter.h:76-77),
