@@ -179,6 +179,13 @@ int alvrl_prepass(alvrl_handle h);
 int alvrl_render(alvrl_handle h, float *rgb_host);
 /* Unclustered render (globalCluster = localRefinement = false): getVRLContributions over all VRLs. */
 int alvrl_render_unclustered(alvrl_handle h, float *rgb_host);
+/* A new sample stream for the next progressive pass.  ProgressiveMonteCarloIntegrator::render (src/librender/integrator.cpp:
+ * 398-434) runs prepass + render once per pass on a sampler that keeps advancing, so every pass traces a fresh VRL set and
+ * draws fresh samples; in the counter stream a pass is addressed by its seed.  Everything drawn from the stream (traced VRLs
+ * stay until alvrl_trace_vrls is called again; slice mapping, R, clusters, specular chains) is invalidated; the slices are
+ * not (Preprocessor::buildSlices draws nothing).  Counter stream only. */
+int alvrl_set_seed(alvrl_handle h, uint64_t seed);
+
 /* ---- VRL tracer: the step before the path ----------------------------------------------------------------
  * vrlTracer::randomWalk (src/integrators/vrl/vrlTracer.h:14-58): light particles are traced from an area emitter
  * (Scene::sampleEmitterPosition, scene.cpp:958-974; AreaLight::samplePosition / sampleDirection, src/emitters/area.cpp:94-123;

@@ -154,6 +154,10 @@ class Integrator:
         a, b = _f32(albedo), _u32(bits)
         self._call("set_materials", _p(a), _p(b), C.c_uint32(len(b)))
 
+    def set_seed(self, seed):
+        """the sample stream of the next progressive pass (integrator.cpp:398-434)"""
+        self._call("set_seed", C.c_uint64(seed))
+
     # -- VRL tracer (include/alvrl.h) ---------------------------------------------------------------
     def set_area_emitter(self, tris, radiance):
         t, r = _u32(tris), _f32(radiance)

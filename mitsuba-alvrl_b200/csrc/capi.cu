@@ -871,6 +871,17 @@ int alvrl_set_slice_range(alvrl_handle c, uint32_t b, uint32_t e) {
     return ALVRL_OK;
 }
 
+int alvrl_set_seed(alvrl_handle c, uint64_t seed) {
+    if (c->P.rngMode == ALVRL_RNG_MODE_SFMT) return fail(ALVRL_ERR_UNSUPPORTED, "alvrl_set_seed: the sequential SFMT stream continues from pass to pass by itself");
+    if (seed != c->P.seed) {
+        c->P.seed = seed;
+        c->mainSampler.reset(new_stream(c->P));
+        c->globalStream.reset();
+        c->chainsValid = false; c->haveRows = false; c->haveR = false; c->haveClusters = false; c->haveFallback = false; c->renderListsDirty = true;
+    }
+    return ALVRL_OK;
+}
+
 /* ---- VRL tracer (tracer.cu) ------------------------------------------------------------------------ */
 int alvrl_set_area_emitter(alvrl_handle c, const uint32_t *tris, uint32_t n, const float radiance[3]) {
     API_BEGIN

@@ -63,10 +63,14 @@ struct MediumView {
     const float *grid; int res[3]; float bboxMin[3], bboxMax[3]; float scale; float albedo[3];
 };
 struct SensorView { float sampleToCamera[16], cameraToWorld[16]; uint32_t width, height; float nearClip, farClip; float position[3]; };
-class Film { public: virtual ~Film() {} virtual void setImage(const float *rgb, uint32_t width, uint32_t height) = 0; };
+/* Film: its reconstruction filter (Film::getReconstructionFilter: 0 box, 1 tent, 2 gaussian = ALVRL_FILTER_*; param <= 0 = the
+ * filter's default radius / stddev) and where the developed image goes */
+class Film { public: virtual ~Film() {} int rfilter = 0; float rfilterParam = 0.0f; virtual void setImage(const float *rgb, uint32_t width, uint32_t height) = 0; };
+/* an area emitter attached to a triangle mesh (Scene::getEmitters, src/emitters/area.cpp): mesh index + radiance */
+struct EmitterView { uint32_t meshIndex; float radiance[3]; };
 class Scene {
 public:
-    std::vector<TriMeshView> meshes; std::vector<MediumView> media; SensorView sensor; Film *film = nullptr;
+    std::vector<TriMeshView> meshes; std::vector<MediumView> media; std::vector<EmitterView> emitters; SensorView sensor; Film *film = nullptr;
 };
 
 class Integrator {

@@ -54,7 +54,7 @@ public:
         m_p.convergenceFalseColor = props.getBoolean("convergenceFalseColor", false);
         m_vrlFile = props.getString("vrlFile", "");
         /* inherited (src/librender/integrator.cpp:53,272-298,348-349): queried so that the loader does not warn */
-        m_p.maxPasses = props.getInteger("maxPasses", 1);
+        m_p.maxPasses = m_maxPasses = props.getInteger("maxPasses", 1);
         props.getBoolean("dumpPasses", false); props.getInteger("rrDepth", 5); props.getInteger("maxDepth", -1);
         props.getBoolean("strictNormals", false); props.getBoolean("hideEmitters", false); props.getInteger("numPasses", 1);
         /* device selection has no XML equivalent in the reference */
@@ -67,18 +67,27 @@ public:
 
     /* vrlIntegrator::preprocess, 237-267 */
     bool preprocess(const mts::Scene *scene) override {
-        if (m_vrlFile.empty())
-            mts::LogError("the B200 path integrates preloaded VRLs: set 'vrlFile' (the VRL tracer, vrlTracer.h, is upstream of it)");
-        if (scene->media.size() != 1)                                                                    /* 244-248 */
-            mts::LogError("When loading VRLs from a file, the scene should (currently) contain exactly one medium, which will be the "
-                          "medium where all VRLs will 'live'");
-        chk(alvrl_create(m_device, &m_p, &m_h));
+        if (!m_vrlFile.empty()) {
+            if (scene->media.size() != 1)                                                                /* 244-248 */
+                mts::LogError("When loading VRLs from a file, the scene should (currently) contain exactly one medium, which will be the "
+                              "medium where all VRLs will 'live'");
+        } else {
+            /* the VRLs are traced in every prepass (279-280): the device tracer walks one medium and starts on one area emitter */
+            if (scene->media.size() != 1) mts::LogError("the device VRL tracer needs exactly one medium in the scene");
+            if (scene->emitters.size() != 1) mts::LogError("the device VRL tracer needs exactly one area emitter (attached to a triangle mesh) in the scene");
+            if (scene->emitters[0].meshIndex >= scene->meshes.size()) mts::LogError("the emitter's shape is not a mesh of the scene");
+        }
+        if (m_maxPasses < 0) mts::LogError("maxPasses < 0 (render until cancelled) is not supported by the device path: give a pass count");
+        alvrl_params hp = m_p; hp.maxPasses = 1;                              /* the passes are driven from render() below */
+        chk(alvrl_create(m_device, &hp, &m_h));
         /* triangle soup + one diffuse material per mesh */
         std::vector<float> verts, albedo, optics; std::vector<uint32_t> tris, mat, bits;
         bool anyDelta = false;
+        std::vector<uint32_t> firstTri;
         for (size_t m = 0; m < scene->meshes.size(); m++) {
             const mts::TriMeshView &tm = scene->meshes[m];
             const uint32_t base = (uint32_t) (verts.size() / 3);
+            firstTri.push_back((uint32_t) (tris.size() / 3));
             verts.insert(verts.end(), tm.positions, tm.positions + 3 * (size_t) tm.vertexCount);
             for (uint32_t i = 0; i < 3 * tm.triangleCount; i++) tris.push_back(base + tm.indices[i]);
             mat.insert(mat.end(), tm.triangleCount, (uint32_t) m);
@@ -103,28 +112,56 @@ public:
         else chk(alvrl_set_medium_grid(m_h, md.grid, md.res, md.bboxMin, md.bboxMax, md.scale, md.albedo, md.sigmaS, md.phaseType, md.g));
         const mts::SensorView &s = scene->sensor;
         chk(alvrl_set_camera(m_h, s.sampleToCamera, s.cameraToWorld, s.width, s.height, s.nearClip, s.farClip));
-        chk(alvrl_load_vrl_file(m_h, m_vrlFile.c_str()));                                               /* 249-251 */
+        if (!m_vrlFile.empty()) chk(alvrl_load_vrl_file(m_h, m_vrlFile.c_str()));                       /* 249-251 */
+        else {                                                                                          /* the emitter's shape: Scene::getEmitters */
+            const mts::EmitterView &em = scene->emitters[0];
+            std::vector<uint32_t> emTris(scene->meshes[em.meshIndex].triangleCount);
+            for (uint32_t i = 0; i < (uint32_t) emTris.size(); i++) emTris[i] = firstTri[em.meshIndex] + i;
+            chk(alvrl_set_area_emitter(m_h, emTris.data(), (uint32_t) emTris.size(), em.radiance));
+        }
         if (m_p.globalCluster || m_p.localRefinement) chk(alvrl_build_slices(m_h));                     /* 254-265 */
+        m_pass = 0;
         return true;
     }
-    /* vrlIntegrator::prepass, 270-356 */
+    /* vrlIntegrator::prepass, 270-356: one call per progressive pass */
     bool prepass(const mts::Scene *) override {
         if (!m_h) mts::LogError("VRL filename given, but vrls were not loaded!");                       /* 285-286 */
+        /* the reference's sampler keeps advancing from pass to pass (integrator.cpp:432-433); a pass of the counter stream is
+         * addressed by its seed */
+        if (m_pass > 0) chk(alvrl_set_seed(m_h, m_p.seed + (uint64_t) m_pass));
+        m_pass++;
+        if (m_vrlFile.empty()) chk(alvrl_trace_vrls(m_h, 0));                                           /* 276-280: vrlTracer::randomWalk */
         if (m_p.globalCluster || m_p.localRefinement) chk(alvrl_prepass(m_h));
         return true;
     }
-    /* the render pass: every pixel centre through Li (386-393) */
-    bool render(mts::Scene *scene) override {
-        std::vector<float> rgb((size_t) scene->sensor.width * scene->sensor.height * 3);
+    /* one render pass: every pixel centre through Li (386-393; MonteCarloIntegrator::render) */
+    bool renderPass(mts::Scene *scene, std::vector<float> &rgb) {
+        rgb.resize((size_t) scene->sensor.width * scene->sensor.height * 3);
         if (m_p.globalCluster || m_p.localRefinement) chk(alvrl_render(m_h, rgb.data()));
         else chk(alvrl_render_unclustered(m_h, rgb.data()));
+        return true;
+    }
+    /* ProgressiveMonteCarloIntegrator::render (src/librender/integrator.cpp:380-440): prepass + render pass, maxPasses times,
+     * into a film that is not cleared in between; the film's reconstruction filter and the division by the accumulated weights
+     * run on the device (alvrl_film_*).  One pass through a box filter is the render pass's image itself. */
+    bool render(mts::Scene *scene) override {
+        std::vector<float> rgb;
+        const int filter = scene->film ? scene->film->rfilter : ALVRL_FILTER_BOX;
+        const bool useFilm = m_maxPasses > 1 || filter != ALVRL_FILTER_BOX;
+        if (useFilm) chk(alvrl_film_configure(m_h, filter, scene->film ? scene->film->rfilterParam : 0.0f));
+        for (int pass = 1; pass <= m_maxPasses; pass++) {
+            if (!prepass(scene)) return false;
+            if (!renderPass(scene, rgb)) return false;
+            if (useFilm) chk(alvrl_film_put(m_h, nullptr));                   /* the frame alvrl_render left on the device */
+        }
+        if (useFilm) chk(alvrl_film_develop(m_h, rgb.data()));
         if (scene->film) scene->film->setImage(rgb.data(), scene->sensor.width, scene->sensor.height);
         return true;
     }
     alvrl_handle handle() const { return m_h; }
 private:
     static void chk(int rc) { if (rc != ALVRL_OK) mts::LogError(alvrl_last_error()); }
-    alvrl_params m_p; std::string m_vrlFile; int m_device = 0; alvrl_handle m_h = nullptr;
+    alvrl_params m_p; std::string m_vrlFile; int m_device = 0, m_maxPasses = 1, m_pass = 0; alvrl_handle m_h = nullptr;
 };
 
 } // namespace
@@ -177,16 +214,26 @@ void alvrl_plugin_scene_set_sensor(void *s, const float *sampleToCamera, const f
     v.width = w; v.height = h; v.nearClip = nearClip; v.farClip = farClip;
     memcpy(v.position, position, 3 * sizeof(float));
 }
+/* an area emitter on the mesh with this index (in the order of alvrl_plugin_scene_add_mesh) */
+void alvrl_plugin_scene_add_area_emitter(void *s, uint32_t meshIndex, const float *radiance) {
+    mts::EmitterView e; e.meshIndex = meshIndex; e.radiance[0] = radiance[0]; e.radiance[1] = radiance[1]; e.radiance[2] = radiance[2];
+    static_cast<mts::Scene *>(s)->emitters.push_back(e);
+}
+int alvrl_plugin_render_frame_filtered(void *inst, void *scene, int rfilter, float rfilterParam, float *rgbOut, char *err, int errLen);
 int alvrl_plugin_render_frame(void *inst, void *scene, float *rgbOut, char *err, int errLen) {
+    return alvrl_plugin_render_frame_filtered(inst, scene, ALVRL_FILTER_BOX, 0.0f, rgbOut, err, errLen);
+}
+int alvrl_plugin_render_frame_filtered(void *inst, void *scene, int rfilter, float rfilterParam, float *rgbOut, char *err, int errLen) {
     struct CopyFilm : mts::Film {
         float *dst; explicit CopyFilm(float *d) : dst(d) {}
         void setImage(const float *rgb, uint32_t w, uint32_t h) override { memcpy(dst, rgb, (size_t) w * h * 3 * sizeof(float)); }
     } film(rgbOut);
+    film.rfilter = rfilter; film.rfilterParam = rfilterParam;
     mts::Scene *sc = static_cast<mts::Scene *>(scene);
     mts::Integrator *it = static_cast<vrlIntegrator *>(inst);
     try {
         sc->film = &film;
-        it->preprocess(sc); it->prepass(sc); it->render(sc);
+        it->preprocess(sc); it->render(sc);           /* render() = ProgressiveMonteCarloIntegrator::render: prepass + render pass per pass */
         sc->film = nullptr;
         return 0;
     } catch (const std::exception &e) { sc->film = nullptr; strncpy(err, e.what(), errLen - 1); err[errLen - 1] = 0; return -1; }

@@ -872,6 +872,17 @@ int orc_get_chain_segments(void *h, uint32_t *offset, float *segs) {
     ORC_CATCH
 }
 
+int orc_set_seed(void *h, uint64_t seed) {                                 // the next progressive pass (integrator.cpp:398-434)
+    Ctx *c = (Ctx *) h;
+    if (c->P.rngMode == ALVRL_RNG_MODE_SFMT) return seterr(ALVRL_ERR_UNSUPPORTED, "set_seed: counter stream only");
+    if (seed != c->P.seed) {
+        c->P.seed = seed;
+        c->mainSampler.reset(c->newStream());
+        c->haveChains = false; c->haveRows = false; c->haveR = false; c->haveClusters = false;
+    }
+    return ALVRL_OK;
+}
+
 /* ---- VRL tracer: vrlTracer.h:14-58, 91-230 --------------------------------------------------------------------------- */
 int orc_set_area_emitter(void *h, const uint32_t *tris, uint32_t n, const float radiance[3]) {
     Ctx *c = (Ctx *) h;

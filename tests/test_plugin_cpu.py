@@ -76,3 +76,48 @@ def test_reference_constructor_errors(plugin, pkg):
 def test_unknown_attribute_is_left_unqueried(plugin, pkg):
     rc, err, p, unq = _create(plugin, pkg, notAParameter=1)
     assert rc == 0 and unq == 1                      # scenehandler.cpp:792-795 would warn about it
+
+
+def test_preprocess_checks_the_scene_before_it_touches_the_device(plugin):
+    """what preprocess() refuses is decided on the host (no CUDA device needed): a VRL file wants exactly one medium
+    (vrlIntegrator.cpp:244-248); without a file the VRLs are traced in every prepass (276-280), which on the device needs one
+    medium and one area emitter on a mesh; maxPasses < 0 ("until cancelled", integrator.cpp:398) is refused"""
+    import numpy as np
+    plugin.alvrl_plugin_scene_new.restype = C.c_void_p
+    fp = C.POINTER(C.c_float)
+    img = np.zeros(3, np.float32)
+    one = np.ones(3, np.float32)
+
+    def frame(scene_setup, **props):
+        p = C.c_void_p(plugin.alvrl_plugin_props_new())
+        for k, v in props.items():
+            if isinstance(v, int):
+                plugin.alvrl_plugin_props_set_int(p, k.encode(), v)
+            else:
+                plugin.alvrl_plugin_props_set_string(p, k.encode(), str(v).encode())
+        inst = C.c_void_p()
+        err = C.create_string_buffer(512)
+        assert plugin.alvrl_plugin_create(p, C.byref(inst), err, 512) == 0, err.value
+        sc = C.c_void_p(plugin.alvrl_plugin_scene_new())
+        scene_setup(sc)
+        rc = plugin.alvrl_plugin_render_frame(inst, sc, img.ctypes.data_as(fp), err, 512)
+        plugin.alvrl_plugin_destroy(inst); plugin.alvrl_plugin_scene_free(sc); plugin.alvrl_plugin_props_free(p)
+        return rc, err.value.decode()
+
+    def medium(sc):
+        plugin.alvrl_plugin_scene_add_medium_homogeneous(sc, one.ctypes.data_as(fp), one.ctypes.data_as(fp), C.c_float(-1.0), 0, C.c_float(0.0))
+
+    rc, err = frame(lambda sc: None, vrlFile="/tmp/some.vrl")
+    assert rc != 0 and "exactly one medium" in err
+    rc, err = frame(lambda sc: None)
+    assert rc != 0 and "one medium" in err
+    rc, err = frame(medium)
+    assert rc != 0 and "area emitter" in err
+
+    def medium_and_dangling_emitter(sc):
+        medium(sc)
+        plugin.alvrl_plugin_scene_add_area_emitter(sc, C.c_uint32(4), one.ctypes.data_as(fp))
+    rc, err = frame(medium_and_dangling_emitter)
+    assert rc != 0 and "not a mesh" in err
+    rc, err = frame(medium, vrlFile="/tmp/some.vrl", maxPasses=-1)
+    assert rc != 0 and "maxPasses" in err

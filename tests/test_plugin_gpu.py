@@ -177,3 +177,101 @@ def test_plugin_frame_with_specular_chains(pkg, tmp_path):
     assert off[-1] > 100                                  # the chains exist
     g.build_slices(); g.prepass()
     assert np.array_equal(img_plugin, g.render())
+
+
+def _scene_to_plugin(lib, sc, scene, meshes):
+    """the mock Scene from a flat scene dict: meshes, the one medium, the sensor; returns the arrays that must stay alive"""
+    fp, up = C.POINTER(C.c_float), C.POINTER(C.c_uint32)
+    for v, t, a, _ in meshes:
+        lib.alvrl_plugin_scene_add_mesh(sc, v.ctypes.data_as(fp), C.c_uint32(len(v)), t.ctypes.data_as(up), C.c_uint32(len(t)), a.ctypes.data_as(fp), 1)
+    med = scene["medium"]
+    sa, ss = np.ascontiguousarray(med["sigmaA"], np.float32), np.ascontiguousarray(med["sigmaS"], np.float32)
+    lib.alvrl_plugin_scene_add_medium_homogeneous(sc, sa.ctypes.data_as(fp), ss.ctypes.data_as(fp), C.c_float(-1.0), 0, C.c_float(0.0))
+    cam = scene["camera"]
+    s2c = np.ascontiguousarray(cam["sampleToCamera"], np.float32).reshape(16)
+    c2w = np.ascontiguousarray(cam["cameraToWorld"], np.float32).reshape(16)
+    pos = np.ascontiguousarray(cam["origin"], np.float32)
+    lib.alvrl_plugin_scene_set_sensor(sc, s2c.ctypes.data_as(fp), c2w.ctypes.data_as(fp), C.c_uint32(cam["width"]), C.c_uint32(cam["height"]),
+                                      C.c_float(cam["near"]), C.c_float(cam["far"]), pos.ctypes.data_as(fp))
+    return sa, ss, s2c, c2w, pos
+
+
+@pytest.mark.parametrize("passes,rfilter", [(1, 0), (3, 0), (2, 2)], ids=["one-pass", "three-passes-box", "two-passes-gaussian"])
+def test_plugin_traces_its_vrls_and_renders_progressive_passes(pkg, passes, rfilter):
+    """vrlFile == "": every prepass traces a fresh VRL set (vrlIntegrator.cpp:276-280) and ProgressiveMonteCarloIntegrator::render
+    runs prepass + render pass maxPasses times into one film (integrator.cpp:380-440).  Through vrl.so == the same calls on the ABI."""
+    lib = _plugin()
+    scene, em, rad = pkg.scenes.tracer_scene(40, 32, glass=False)
+    scene = dict(scene)
+    # the emitter's quad as a shape of its own (an area emitter is attached to one shape): a material id of its own
+    scene["albedo"] = np.concatenate([scene["albedo"], scene["albedo"][scene["tri_material"][em[0]]][None]]).astype(np.float32)
+    tm = scene["tri_material"].copy(); tm[em] = len(scene["albedo"]) - 1
+    scene["tri_material"] = tm
+    scene["mat_bits"] = np.ones(len(scene["albedo"]), np.uint32)
+    meshes, flat = _by_material(scene)
+    em_mesh = [i for i, (_, _, _, m) in enumerate(meshes) if m == len(scene["albedo"]) - 1][0]
+    em_flat = np.nonzero(flat["tri_material"] == em_mesh)[0].astype(np.uint32)
+    assert len(em_flat) == len(em)
+    xml = dict(volVolSamples=2, volSurfSamples=2, targetNumSlices=8, seed=5, vrlTargetNum=300, maxPasses=passes)
+
+    p = C.c_void_p(lib.alvrl_plugin_props_new())
+    for k, v in xml.items():
+        lib.alvrl_plugin_props_set_int(p, k.encode(), v)
+    inst = C.c_void_p()
+    err = C.create_string_buffer(1024)
+    assert lib.alvrl_plugin_create(p, C.byref(inst), err, 1024) == 0, err.value
+    sc = C.c_void_p(lib.alvrl_plugin_scene_new())
+    keep = _scene_to_plugin(lib, sc, scene, meshes)
+    fp = C.POINTER(C.c_float)
+    H, W = scene["camera"]["height"], scene["camera"]["width"]
+    img_plugin = np.zeros((H, W, 3), np.float32)
+    # no emitter in the scene: the tracer has nothing to start from
+    assert lib.alvrl_plugin_render_frame(inst, sc, img_plugin.ctypes.data_as(fp), err, 1024) != 0 and b"emitter" in err.value
+    lib.alvrl_plugin_destroy(inst)
+    assert lib.alvrl_plugin_create(p, C.byref(inst), err, 1024) == 0, err.value
+    r = np.ascontiguousarray(rad, np.float32)
+    lib.alvrl_plugin_scene_add_area_emitter(sc, C.c_uint32(em_mesh), r.ctypes.data_as(fp))
+    rc = lib.alvrl_plugin_render_frame_filtered(inst, sc, rfilter, C.c_float(0.0), img_plugin.ctypes.data_as(fp), err, 1024)
+    assert rc == 0, err.value
+    lib.alvrl_plugin_destroy(inst); lib.alvrl_plugin_scene_free(sc); lib.alvrl_plugin_props_free(p)
+    del keep
+
+    g = pkg.integrator(0, **{k: v for k, v in xml.items() if k != "maxPasses"})
+    g.set_scene(flat)
+    g.set_area_emitter(em_flat, rad)
+    g.build_slices()
+    use_film = passes > 1 or rfilter != 0
+    if use_film:
+        g.film_configure(rfilter, 0.0)
+    sets = []
+    for k in range(passes):
+        if k:
+            g.set_seed(5 + k)
+        g.trace_vrls()
+        sets.append(g.get_vrls()[0])
+        g.prepass()
+        img_direct = g.render()
+        if use_film:
+            g.film_put(None)
+    if use_film:
+        img_direct = g.film_develop()
+    assert img_plugin.max() > 0 and np.array_equal(img_plugin, img_direct)
+    if passes > 1:                                       # every pass has its own VRL set
+        assert not np.array_equal(sets[0][:50], sets[1][:50])
+
+
+def test_set_seed_equals_a_fresh_handle(pkg):
+    """alvrl_set_seed(s) on a used handle == a handle created with seed s: slice mapping, R, clusters and the image"""
+    scene, vrls, params = pkg.scenes.make_config("C1", width=48, height=40, n_vrls=150)
+    params.update(targetNumSlices=8)
+    a = pkg.integrator(0, **dict(params, seed=3))
+    a.set_scene(scene); a.set_vrls(*vrls); a.build_slices(); a.prepass()
+    img3 = a.render()
+    a.set_seed(11)
+    a.prepass()
+    img11 = a.render()
+    b = pkg.integrator(0, **dict(params, seed=11))
+    b.set_scene(scene); b.set_vrls(*vrls); b.build_slices(); b.prepass()
+    assert np.array_equal(img11, b.render()) and not np.array_equal(img3, img11)
+    ca, cb = a.clusters(), b.clusters()
+    assert np.array_equal(ca["offset"], cb["offset"]) and np.array_equal(ca["vrls"], cb["vrls"])
