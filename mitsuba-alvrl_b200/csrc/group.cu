@@ -98,25 +98,15 @@ void member_frame(alvrl_group *g, Member *m, float *rgbHost) {
     auto lap = [&](const char *what) { if (prof) { cudaStreamSynchronize(c->stream); const double n = gnow_ms(); char b[64]; snprintf(b, sizeof(b), " %s %.1f", what, n - tPrev); log += b; tPrev = n; } };
     G_API(alvrl_build_slices(c));                                            /* Preprocessor::buildSlices: replicated, identical on every rank */
     const uint32_t S = c->numSlices();
-    /* cost of a slice on a rank: its pixels (rows of R, refinement sweeps and render work grow with them) plus a constant per
-     * Clustering object (picks, sorts and queue work do not depend on the rows): measured on C2, one object weighs about
-     * 1/500 of all pixels */
+    /* cost estimate per slice and the weights the ranges are cut on (sharding.h, shared with the CPU tests) */
     uint64_t totalPix = 0;
     for (uint32_t i = 0; i < S; i++) totalPix += c->sliceSize[i];
     const bool adaptive = g->world > 1 && !getenv("ALVRL_GROUP_STATIC");
-    if (m->sliceCost.size() != S) {
-        m->sliceCost.resize(S);
-        for (uint32_t i = 0; i < S; i++) m->sliceCost[i] = (double) c->sliceSize[i] + (double) (totalPix / 500u);
-    }
-    /* the ranges are cut on integer weights (sharding.h, shared with the CPU helpers): the cost estimates scaled to 2^20 */
+    if (m->sliceCost.size() != S) initial_slice_costs(c->sliceSize.data(), S, m->sliceCost);
     std::vector<uint32_t> sizes(S);
-    {
-        double mx = 0;
-        for (uint32_t i = 0; i < S; i++) mx = std::max(mx, m->sliceCost[i]);
-        const bool first = !adaptive || m->ev[0] == nullptr;                    /* first frame: the pixel counts themselves */
-        for (uint32_t i = 0; i < S; i++)
-            sizes[i] = first ? c->sliceSize[i] + (uint32_t) (totalPix / 500u) : std::max<uint32_t>(1u, (uint32_t) (m->sliceCost[i] / mx * 1048576.0));
-    }
+    if (!adaptive || m->ev[0] == nullptr) {                                      /* first frame: the pixel counts themselves */
+        for (uint32_t i = 0; i < S; i++) sizes[i] = c->sliceSize[i] + (uint32_t) (totalPix / 500u);
+    } else cut_weights(m->sliceCost, sizes);
     balanced_slice_range(sizes.data(), S, g->world, m->rank, m->sliceBegin, m->sliceEnd);
     if (adaptive && m->ev[0] == nullptr) for (int k = 0; k < 4; k++) ALVRL_CUDA(cudaEventCreate(&m->ev[k]));
     if (adaptive) ALVRL_CUDA(cudaEventRecord(m->ev[0], c->stream));
@@ -163,25 +153,7 @@ void member_frame(alvrl_group *g, Member *m, float *rgbHost) {
         m->times.upload(t, c->stream);
         G_NCCL(nccl().AllReduce(m->times.p, m->times.p, (size_t) g->world, ncclFloat, ncclSum, m->comm, c->stream));
         m->times.download(t.data(), (size_t) g->world, c->stream);
-        double tot = 0, totCost = 0;
-        for (int r = 0; r < g->world; r++) tot += t[r];
-        for (uint32_t i = 0; i < S; i++) totCost += m->sliceCost[i];
-        if (tot > 0 && totCost > 0) {
-            for (int r = 0; r < g->world; r++) {
-                uint32_t b0, e0;
-                balanced_slice_range(sizes.data(), S, g->world, r, b0, e0);
-                double sum = 0;
-                for (uint32_t i = b0; i < e0; i++) sum += m->sliceCost[i];
-                if (!(sum > 0) || !(t[r] > 0)) continue;
-                const double scale = (t[r] / tot) / (sum / totCost);              /* measured share / predicted share */
-                /* a rank's time varies by +-15 % from frame to frame (the order in which k_refine_mt's tickets are drawn), so the
-                 * model error is taken out in the first two corrections and later ones only follow slowly; small deviations are left alone */
-                const double alpha = m->corrections < 2u ? 0.5 : 0.2;
-                if (std::fabs(scale - 1.0) < 0.05) continue;
-                for (uint32_t i = b0; i < e0; i++) m->sliceCost[i] *= (1.0 - alpha) + alpha * scale;
-            }
-            m->corrections++;
-        }
+        if (correct_slice_costs(m->sliceCost, sizes.data(), g->world, t.data(), m->corrections)) m->corrections++;
     }
     if (prof) fprintf(stderr, "[alvrl group] rank %d slices [%u, %u):%s | total %.1f ms\n", m->rank, m->sliceBegin, m->sliceEnd, log.c_str(), gnow_ms() - t0);
 }

@@ -22,6 +22,24 @@ int alvrl_host_balanced_range(const uint32_t *sizes, uint32_t S, int world, int 
     return 0;
 }
 
+/* measured-time balancing of the slice ranges (sharding.h; group.cu runs the same functions after every frame):
+ * cost[S] in/out (corrections == 0 and cost[0] < 0: initialised from the pixel counts), weights[S] out = what the NEXT frame
+ * is cut on, t[world] = what each rank's range took in the frame cut on weightsIn (NULL: pixel counts + constant, the first
+ * frame's cut) */
+int alvrl_host_balance_step(const uint32_t *sliceSize, uint32_t S, int world, double *cost, const uint32_t *weightsIn, const float *t,
+                            uint32_t corrections, uint32_t *weightsOut) {
+    std::vector<double> c(cost, cost + S);
+    if (corrections == 0 && S && cost[0] < 0) initial_slice_costs(sliceSize, S, c);
+    std::vector<uint32_t> w(S);
+    if (weightsIn) w.assign(weightsIn, weightsIn + S);
+    else { uint64_t tot = 0; for (uint32_t i = 0; i < S; i++) tot += sliceSize[i]; for (uint32_t i = 0; i < S; i++) w[i] = sliceSize[i] + (uint32_t) (tot / 500u); }
+    const bool counted = correct_slice_costs(c, w.data(), world, t, corrections);
+    std::vector<uint32_t> next;
+    cut_weights(c, next);
+    for (uint32_t i = 0; i < S; i++) { cost[i] = c[i]; weightsOut[i] = next[i]; }
+    return counted ? 1 : 0;
+}
+
 int alvrl_host_sfmt_ulongs(uint64_t seed, uint32_t cloneDepth, uint32_t skip, uint64_t *out, uint32_t n) {
     Sfmt19937 g(seed);
     if (cloneDepth == 0) { for (uint32_t i = 0; i < skip; i++) g.next64(); for (uint32_t i = 0; i < n; i++) out[i] = g.next64(); return 0; }

@@ -135,3 +135,73 @@ def test_balanced_slice_ranges_match_the_python_sharding_helper(host_lib, pkg):
             got.append((b.value, e.value))
         assert got == want, (S, world)
         assert got[0][0] == 0 and got[-1][1] == S and all(got[i][1] == got[i + 1][0] for i in range(world - 1))
+
+
+def test_measured_time_balancing_converges_and_is_rank_independent(host_lib):
+    """The group frame (csrc/group.cu) recuts the slice ranges after every frame from the ranks' measured times (sharding.h).
+    Simulated here with cost models the first cut (pixels + a small constant) does not predict.  Smooth models -- a large
+    constant per slice, a super-linear cost -- are balanced within two frames to (nearly) the best contiguous cut; every rank
+    computes the same estimates and cuts from the same numbers; ranges stay contiguous and covering.  Known limit, stated: a
+    rank's time cannot tell WHICH of its slices was expensive, so a few outlier slices (4 x their neighbours) are chased from
+    rank to rank instead of being isolated -- the imbalance then stays near the static cut's instead of the optimum."""
+    rng = np.random.default_rng(3)
+    S, world = 100, 8
+    pixels = rng.integers(2000, 30000, S).astype(np.uint32)
+    vp = C.c_void_p
+
+    def ranges(weights):
+        out = []
+        for r in range(world):
+            b, e = C.c_uint32(), C.c_uint32()
+            host_lib.alvrl_host_balanced_range(weights.ctypes.data_as(vp), C.c_uint32(S), C.c_int(world), C.c_int(r), C.byref(b), C.byref(e))
+            out.append((b.value, e.value))
+        assert out[0][0] == 0 and out[-1][1] == S and all(out[i][1] == out[i + 1][0] for i in range(world - 1))
+        return out
+
+    def best_contiguous_cut(cost):                     # min over contiguous partitions of max / mean, by bisection
+        lo, hi = float(cost.max()), float(cost.sum())
+        for _ in range(60):
+            mid, k, acc = (lo + hi) / 2, 1, 0.0
+            for c in cost:
+                if acc + c > mid:
+                    k, acc = k + 1, c
+                else:
+                    acc += c
+            lo, hi = (lo, mid) if k <= world else (mid, hi)
+        return hi / (cost.sum() / world)
+
+    def run(true_cost, noise, frames=10):
+        first = (pixels + np.uint32(int(pixels.sum()) // 500)).astype(np.uint32)
+        cost = np.full(S, -1.0)
+        weights, w_in, hist = first.copy(), None, []
+        for it in range(frames):
+            rg = ranges(weights)
+            t = np.array([true_cost[b:e].sum() for b, e in rg], np.float64)
+            hist.append(float(t.max() / t.mean()))
+            t = (t * (1 + noise * rng.standard_normal(world))).astype(np.float32)
+            nxt, cost_b, nxt_b = np.zeros(S, np.uint32), cost.copy(), np.zeros(S, np.uint32)
+            args = lambda c, n: (pixels.ctypes.data_as(vp), C.c_uint32(S), C.c_int(world), c.ctypes.data_as(vp),
+                                 None if w_in is None else w_in.ctypes.data_as(vp), t.ctypes.data_as(vp), C.c_uint32(it), n.ctypes.data_as(vp))
+            assert host_lib.alvrl_host_balance_step(*args(cost, nxt)) == 1
+            assert host_lib.alvrl_host_balance_step(*args(cost_b, nxt_b)) == 1          # a second "rank": same inputs, same outputs
+            assert np.array_equal(cost, cost_b) and np.array_equal(nxt, nxt_b)
+            assert (nxt >= 1).all() and nxt.max() == 1048576
+            w_in, weights = nxt.copy(), nxt
+        return hist
+
+    for true_cost in (pixels + 30000.0, pixels.astype(np.float64) ** 1.3):
+        opt = best_contiguous_cut(true_cost)
+        hist = run(true_cost, 0.0)
+        assert hist[0] > opt + 0.05                    # the first cut is off ...
+        assert max(hist[2:]) < opt + 0.03, (hist, opt)  # ... two corrections later the cut is (nearly) the best contiguous one
+        noisy = run(true_cost, 0.05)                   # 5 % timing noise: stays close, does not run away
+        assert np.mean(noisy[3:]) < hist[0] and max(noisy[3:]) < opt + 0.12, (noisy, opt)
+    outliers = pixels.astype(np.float64) ** 1.5
+    outliers[rng.integers(0, S, 5)] *= 4.0
+    hist = run(outliers, 0.0, frames=15)
+    assert max(hist) < 1.15 * hist[0]                  # the stated limit: no improvement guaranteed, but bounded
+    # a frame in which no time was measured changes nothing
+    cost = np.full(S, -1.0); nxt = np.zeros(S, np.uint32); zero = np.zeros(world, np.float32)
+    assert host_lib.alvrl_host_balance_step(pixels.ctypes.data_as(vp), C.c_uint32(S), C.c_int(world), cost.ctypes.data_as(vp), None,
+                                            zero.ctypes.data_as(vp), C.c_uint32(0), nxt.ctypes.data_as(vp)) == 0
+    assert np.allclose(cost, pixels + int(pixels.sum()) // 500)
