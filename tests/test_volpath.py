@@ -152,6 +152,59 @@ def test_vrl_render_against_ground_truth(pkg, orc):
     assert abs(gt1.mean() / gt_inf.mean() - 1) < 0.05, (gt1.mean(), gt_inf.mean())
 
 
+def test_walks_match_the_golden_fixture(pkg, orc):
+    """tests/golden/walks_tiny.npz (made by tests/golden/make_walk_goldens.py): the traced VRL set and two ground-truth images of
+    the glass + conductor scene, strict oracle build"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "walks_tiny.npz"))
+    scene, em, rad = pkg.scenes.tracer_scene(int(g["width"]), int(g["height"]), glass=True)
+    o = _make(pkg, lambda **kw: orc.Oracle(**kw), scene, em, rad, seed=int(g["seed"]), targetNumSlices=4, vrlTargetNum=int(g["target"]))
+    o.trace_vrls()
+    s, e, p, pc = o.get_vrls()
+    assert pc == int(g["particles"]) and np.array_equal(s, g["vrl_start"]) and np.array_equal(e, g["vrl_end"]) and np.array_equal(p, g["vrl_power"])
+    assert np.array_equal(o.volpath_render(spp=3, internal_samples=2), g["volpath"])
+    assert np.array_equal(o.volpath_render(spp=2, internal_samples=1, flags=0, max_depth=5), g["volpath_all_depth5"])
+
+
+def _validation_loop(pkg, make, seed):
+    """the reference authors' loop: trace VRLs, render them (clustered and not), compare with the ground truth by `rms`"""
+    scene, em, rad = pkg.scenes.tracer_scene(24, 24, glass=False)
+    kw = dict(vrlTargetNum=6000, rrDepth=1000, maxParticleDepth=6)          # no roulette: see test_vrl_render_against_ground_truth
+    flags = pkg.binding.Integrator.VOLPATH_DEFAULT | pkg.binding.Integrator.VOLPATH_CENTRE_SAMPLES
+    it = _make(pkg, make, scene, em, rad, seed=seed, **kw)
+    gt = it.volpath_render(spp=128, internal_samples=16, flags=flags, max_depth=8)
+    it.trace_vrls()
+    it.build_slices()
+    it.prepass()
+    return gt, it.render(), it.render(clustered=False)
+
+
+def _check_validation_loop(pkg, gt, clustered, unclustered):
+    rms = pkg.rms.rms
+    # measured with the oracle (seeds 1-3): means 1.00 / 1.00 / 1.11 clustered, 0.97 / 1.01 / 1.05 unclustered; relative RMSE 0.24-0.25
+    # clustered, 0.10-0.12 unclustered, against 0.116 between two ground-truth images of different seeds
+    assert 0.85 < clustered.mean() / gt.mean() < 1.2 and 0.9 < unclustered.mean() / gt.mean() < 1.12
+    assert rms(unclustered, gt, relative=True) < 0.17
+    assert rms(clustered, gt, relative=True) < 0.36
+    assert rms(clustered, unclustered, relative=True) < 0.34          # what the clustering itself costs at ~45 representatives per slice
+
+
+def test_validation_loop_on_the_oracle(pkg, orc):
+    _check_validation_loop(pkg, *_validation_loop(pkg, _oracle(orc), 2))
+
+
+@pytest.mark.gpu
+def test_validation_loop_on_the_device(pkg, orc):
+    """the same loop with every step on the device (tracer, slices, R, clusters, render, ground truth): within the oracle's bounds,
+    ground truth identical to the oracle's"""
+    gt, cl, un = _validation_loop(pkg, lambda **k: pkg.integrator(0, **k), 2)
+    _check_validation_loop(pkg, gt, cl, un)
+    scene, em, rad = pkg.scenes.tracer_scene(24, 24, glass=False)
+    o = _make(pkg, lambda **k: orc.Oracle(threads=8, **k), scene, em, rad, seed=2, vrlTargetNum=6000, rrDepth=1000, maxParticleDepth=6)
+    flags = pkg.binding.Integrator.VOLPATH_DEFAULT | pkg.binding.Integrator.VOLPATH_CENTRE_SAMPLES
+    assert np.array_equal(gt, o.volpath_render(spp=128, internal_samples=16, flags=flags, max_depth=8))
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("glass,kw", [(False, dict(spp=3, internal_samples=2)), (True, dict(spp=3, internal_samples=2)),
                                       (True, dict(spp=1, internal_samples=3)), (False, dict(spp=2, internal_samples=1, flags=0)),
