@@ -336,17 +336,27 @@ def run_ours(a):
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    roof = {"bound": "fp32", "kernel": "k_build_R_fast<homogeneous>", "achieved": achieved, "peak": float(peak.value), "unit": "TFLOP/s",
+    vis_mode = {0: "BVH traversal", 1: "flat leaf sweep", 2: "occluder set"}.get(int(st.visMode), "?")
+    # what SURVEY 8(d) names as the bound of the transport kernel per config; the FP32 fraction is reported for every config so
+    # that the lines are comparable, with the note saying what actually limits the kernel there
+    bound_note = {"C3": "memory system (SURVEY 8d): the Simpson marches stream ~172 KB of the 512 MiB grid per contribution, 3.0 TB/s of DRAM at "
+                        "16 % L2 hit rate (ncu, profiles/r2_c3_c4_transport.txt); the FP32 fraction is not the limiter here",
+                  "C4": "BVH traversal (SURVEY 8d): latency of dependent node fetches, 20.8 node visits per shadow ray in the 4-wide tree, L2 hit "
+                        "rate 87 % (ncu, profiles/r2_c3_c4_transport.txt); see shadow_rays_per_s_R_kernel; the FP32 fraction is not the limiter here"}.get(a.config)
+    roof = {"bound": "fp32", "kernel": f"k_build_R_fast<{'grid' if a.config == 'C3' else 'homogeneous'} medium, {vis_mode}>", "achieved": achieved,
+            "peak": float(peak.value), "unit": "TFLOP/s",
             "frac": achieved / float(peak.value) if peak.value else None,
             # dram__bytes_read.sum + dram__bytes_write.sum of this very launch (C2: 15 759 rows x 100 000 VRLs) from one
-            # `ncu --set full` capture, profiles/r1_buildR_c2_v9.ncu-rep: 0.254 GB read + 12.614 GB written
-            "traffic": 12867996160 if (N == 100000 and W == 1024 and H == 1024 and world == 1) else None,
+            # `ncu --set full` capture of the round-2 kernel, profiles/r2_transport_v11.txt: 0.2349 GB read + 12.6687 GB written
+            "traffic": 12903596944 if (N == 100000 and W == 1024 and H == 1024 and world == 1 and a.config == "C2" and not a.slice_range) else None,
             "peak_source": "FP32 FFMA microbenchmark measured live on this device (alvrl_measure_fp32_peak); north_star names the "
                            "non-tensor FP32 roofline for this kernel (no dense contraction, tensor cores unused); nominal 148 SM x 128 x 2 x 1.965 GHz = 74.5",
             "flops_per_contribution": F, "contributions_per_launch": k_pairs, "launch_ms": k_ms,
             "contributions_per_s_kernel": k_pairs / (k_ms * 1e-3),
             "hbm": {"algorithmic_bytes_per_launch": k_pairs * 8, "achieved_gbs": k_pairs * 8 / (k_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
+    if bound_note:
+        roof["bound_note"] = bound_note
 
     if rank == 0:
         line = {"metric": "vrl_segment_contributions_per_s", "value": pairs / (ms * 1e-3), "unit": "VRL-segment contributions/s",
