@@ -195,7 +195,8 @@ int alvrl_set_seed(alvrl_handle h, uint64_t seed);
  * every path segment inside the scattering medium becomes a VRL (vrlVector::put, VRL.h:148-158) until vrlTargetNum VRLs
  * exist.  Particle i draws from the counter stream of (ALVRL_RNG_TRACER, i); the particles are independent, so the device
  * traces them in parallel and keeps the particles 0 .. n-1, n the first count that reaches the target -- what the
- * reference's sequential loop stops at.  Homogeneous media only.
+ * reference's sequential loop stops at.  Homogeneous media and grid media (HeterogeneousMedium::sampleDistance, method = simpson,
+ * heterogeneous.cpp:422-545, 589-616: the Simpson march inverted by Newton-bisection).
  *   emitter_tris: indices (into the mesh of alvrl_set_mesh) of the triangles of the emitter's shape, in the shape's order.
  * alvrl_trace_vrls replaces the handle's VRL set (as alvrl_set_vrls would) and its particle count. */
 int alvrl_set_area_emitter(alvrl_handle h, const uint32_t *emitter_tris, uint32_t ntris, const float radiance_rgb[3]);
@@ -209,7 +210,7 @@ int alvrl_get_vrls(alvrl_handle h, float *start_xyz, float *end_xyz, float *powe
  * SamplingIntegrator::renderBlock (src/librender/integrator.cpp:210-268): `spp` samples per pixel (pixel centre when spp == 1,
  * jittered otherwise), each the mean of `internalSamples` walks (volpath.cpp:111-120); box reconstruction filter, invalid
  * samples rejected (imageblock.h:147-151).  Emitter sampling + phase / BSDF sampling combined by the power heuristic, Russian
- * roulette from params.rrDepth on.  Needs alvrl_set_area_emitter; one homogeneous medium (the sensor sits in it), diffuse /
+ * roulette from params.rrDepth on.  Needs alvrl_set_area_emitter; one homogeneous or grid medium (the sensor sits in it), diffuse /
  * smooth dielectric / smooth conductor surfaces, no index-matched (ENull) boundaries, no environment emitter.
  * Outer sample j of pixel p draws from the counter stream of (ALVRL_RNG_VOLPATH, p, j); thread = pixel, one launch per outer
  * sample, so the device image equals the oracle's bit for bit.  max_depth: -1 = unlimited (the `maxDepth` property).

@@ -919,7 +919,6 @@ int alvrl_trace_vrls(alvrl_handle c, uint32_t target) {
     API_BEGIN
     use_device(c);
     if (!c->haveEmitter || !c->haveMedium || !c->haveMat) throw Error(ALVRL_ERR_STATE, "alvrl_trace_vrls: set_area_emitter / set_medium / set_materials first");
-    if (c->medium.type != 0) throw Error(ALVRL_ERR_UNSUPPORTED, "alvrl_trace_vrls: homogeneous media only");
     ensure_scene(c);
     bool anyDelta = false;
     for (uint32_t b : c->matBits) if (b & ALVRL_BSDF_DELTA) anyDelta = true;
@@ -967,7 +966,6 @@ int alvrl_volpath_render(alvrl_handle c, uint32_t spp, uint32_t internalSamples,
     API_BEGIN
     use_device(c);
     if (!c->haveEmitter || !c->haveMedium || !c->haveMat || !c->haveCam) throw Error(ALVRL_ERR_STATE, "alvrl_volpath_render: set_area_emitter / set_medium / set_materials / set_camera first");
-    if (c->medium.type != 0) throw Error(ALVRL_ERR_UNSUPPORTED, "alvrl_volpath_render: homogeneous media only");
     if (!spp || !internalSamples || !rgb) throw Error(ALVRL_ERR_ARG, "alvrl_volpath_render: spp and internalSamples must be positive");
     if (flags & ~127u) throw Error(ALVRL_ERR_ARG, "alvrl_volpath_render: unknown flag bits");
     ensure_scene(c);

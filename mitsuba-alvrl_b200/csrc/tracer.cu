@@ -73,7 +73,20 @@ __device__ __forceinline__ uint32_t trace_particle(const SceneDev &sc, const Med
         const float itsT = hit ? t : INFINITY;
         bool scattered = false;
         float mT[3] = {1.0f, 1.0f, 1.0f}, pdfFailure = 1.0f, pdfSuccess = 1.0f; F3 mP = ro;
-        if (inMedium) {                                                       /* sampleDistance, homogeneous.cpp:275-352 */
+        float mSigmaS[3] = {med.sigmaS[0], med.sigmaS[1], med.sigmaS[2]};
+        if (inMedium && med.type == 1) {                                      /* sampleDistance, heterogeneous.cpp:589-616 (simpson) */
+            const float desiredDensity = -((float) log((double) xsub(1.0f, smp.next())));
+            float integratedDensity, tt, densityAtT;
+            bool success = false;
+            if (grid_invert_density_integral(med, ro, rd, 0.0f, itsT, desiredDensity, integratedDensity, tt, densityAtT)) {
+                mP = xadd3(ro, xscale(rd, tt));
+                success = true;
+                for (int i = 0; i < 3; ++i) mSigmaS[i] = xmul(med.albedo[i], densityAtT);
+            }
+            const float expVal = exp_ref(-integratedDensity);
+            pdfFailure = expVal; pdfSuccess = xmul(expVal, densityAtT); mT[0] = mT[1] = mT[2] = expVal;
+            scattered = success && pdfSuccess > 0;
+        } else if (inMedium) {                                                /* sampleDistance, homogeneous.cpp:275-352 */
             float rnd = smp.next(), sampledDistance;
             if (rnd < med.samplingWeight) {
                 rnd = xdiv(rnd, med.samplingWeight);
@@ -100,7 +113,7 @@ __device__ __forceinline__ uint32_t trace_particle(const SceneDev &sc, const Med
         }
         if (inMedium && scattered) {
             const float rps = xdiv(1.0f, pdfSuccess);
-            for (int i = 0; i < 3; ++i) thr[i] = xmul(thr[i], xmul(xmul(mT[i], med.sigmaS[i]), rps));
+            for (int i = 0; i < 3; ++i) thr[i] = xmul(thr[i], xmul(xmul(mT[i], mSigmaS[i]), rps));
             const float px = smp.next(), py = smp.next();
             F3 wo;
             if (med.phaseType == ALVRL_PHASE_ISOTROPIC) wo = square_to_uniform_sphere(px, py);

@@ -103,6 +103,7 @@ __device__ __forceinline__ void vp_shadow_transmittance(const VpScene &S, const 
     float t, u, v; uint32_t prim;
     if (scene_intersect<false>(S.sc, ref, dir, refOnSurface ? ALVRL_EPSILON : 0.0f, xmul(remaining, xsub(1.0f, ALVRL_SHADOW_EPSILON)), false, t, prim, u, v)) { T[0] = T[1] = T[2] = 0.0f; return; }
     if (!inMedium) return;
+    if (S.med.type == 1) { T[0] = T[1] = T[2] = exp_ref(-grid_optical_depth(S.med, ref, dir, 0.0f, remaining)); return; }                          /* heterogeneous.cpp:546-548 */
     for (int c = 0; c < 3; c++) T[c] = S.med.sigmaT[c] != 0 ? exp_ref(xmul(S.med.sigmaT[c], xsub(0.0f, remaining))) : 1.0f;      /* homogeneous.cpp:266-273 */
 }
 /* Scene::pdfEmitterDirect, scene.cpp:949-952; AreaLight::pdfDirect, area.cpp:176-183; Shape::pdfDirect, shape.cpp:117-121 */
@@ -131,7 +132,19 @@ __device__ void volpath_li_original(const VpScene &S, const VolpathParams &vp, T
 #define VP_DIRECT_OK() (!vp.only || (depth != 1 && ((prevWasVolume || prevWasDiffuseSurface) && (!prevWasDiffuseSurface || vp.volToSurf) && (!prevWasVolume || vp.volToVol))))
         bool success = false;
         float mT[3] = {1.0f, 1.0f, 1.0f}, pdfFailure = 1.0f, pdfSuccess = 1.0f; F3 mP = ro;
-        if (inMedium) {                                                      /* sampleDistance(Ray(ray, 0, its.t)), homogeneous.cpp:275-352 */
+        float mSigmaS[3] = {med.sigmaS[0], med.sigmaS[1], med.sigmaS[2]};
+        if (inMedium && med.type == 1) {                                     /* sampleDistance(Ray(ray, 0, its.t)), heterogeneous.cpp:589-616 (simpson) */
+            const float desiredDensity = -((float) log((double) xsub(1.0f, smp.next())));
+            float integratedDensity, tt, densityAtT;
+            if (grid_invert_density_integral(med, ro, rd, 0.0f, its.t, desiredDensity, integratedDensity, tt, densityAtT)) {
+                mP = xadd3(ro, xscale(rd, tt));
+                success = true;
+                for (int i = 0; i < 3; ++i) mSigmaS[i] = xmul(med.albedo[i], densityAtT);
+            }
+            const float expVal = exp_ref(-integratedDensity);
+            pdfFailure = expVal; pdfSuccess = xmul(expVal, densityAtT); mT[0] = mT[1] = mT[2] = expVal;
+            success = success && pdfSuccess > 0;
+        } else if (inMedium) {                                               /* sampleDistance(Ray(ray, 0, its.t)), homogeneous.cpp:275-352 */
             float rnd = smp.next(), sampledDistance;
             if (rnd < med.samplingWeight) {
                 rnd = xdiv(rnd, med.samplingWeight);
@@ -162,7 +175,7 @@ __device__ void volpath_li_original(const VpScene &S, const VolpathParams &vp, T
             if (depth >= vp.maxDepth && vp.maxDepth != -1) break;
             {
                 const float rps = xdiv(1.0f, pdfSuccess);
-                for (int i = 0; i < 3; ++i) thr[i] = xmul(thr[i], xmul(xmul(med.sigmaS[i], mT[i]), rps));
+                for (int i = 0; i < 3; ++i) thr[i] = xmul(thr[i], xmul(xmul(mSigmaS[i], mT[i]), rps));
             }
             DirectRec dRec; dRec.ref = mP; dRec.refN = f3(0.0f, 0.0f, 0.0f); dRec.dist = 0; dRec.pdf = 0;
             const F3 wi = f3(-rd.x, -rd.y, -rd.z);

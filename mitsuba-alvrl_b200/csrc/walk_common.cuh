@@ -75,6 +75,65 @@ __device__ __forceinline__ float fresnel_conductor_exact_t(float cosThetaI, floa
 
 struct EmitterDev { const uint32_t *tris; const float *cdf; uint32_t n; float power[3]; };
 
+/* HeterogeneousMedium::invertDensityIntegral, heterogeneous.cpp:422-545 (the oracle's Medium::invertDensityIntegral operation for
+ * operation): composite Simpson march from ray.mint until the optical depth reaches desiredDensity, then Newton-bisection on the
+ * quadratic through the last three lookups.  Returns false when [rmint, rmaxt] holds less than desiredDensity; integratedDensity
+ * then is what the segment holds. */
+__device__ __forceinline__ bool grid_invert_density_integral(const MediumDev &m, const F3 &o, const F3 &d, float rmint, float rmaxt, float desiredDensity,
+                                                             float &integratedDensity, float &t, float &densityAtT) {
+    integratedDensity = 0.0f; densityAtT = 0.0f; t = 0.0f;
+    const F3 dRcp = f3(xdiv(1.0f, d.x), xdiv(1.0f, d.y), xdiv(1.0f, d.z));
+    float mint, maxt;
+    if (!aabb_clip(m.bmin, m.bmax, o, d, dRcp, mint, maxt)) return false;
+    mint = fmaxf(mint, rmint);
+    maxt = fminf(maxt, rmaxt);
+    const float length = xsub(maxt, mint);
+    F3 p = xadd3(o, xscale(d, mint));
+    const F3 pLast = xadd3(o, xscale(d, maxt));
+    float maxComp = 0;
+    maxComp = fmaxf(fmaxf(maxComp, fabsf(p.x)), fabsf(pLast.x));
+    maxComp = fmaxf(fmaxf(maxComp, fabsf(p.y)), fabsf(pLast.y));
+    maxComp = fmaxf(fmaxf(maxComp, fabsf(p.z)), fabsf(pLast.z));
+    if (length < xmul(1e-6f, maxComp)) return false;
+    const uint32_t nSteps = (uint32_t) ceilf(xdiv(length, xmul(2.0f, m.stepSize)));
+    const float stepSz = xdiv(length, (float) nSteps), multiplier = xmul(xmul(1.0f / 6.0f, stepSz), m.scale);
+    const F3 fullStep = xscale(d, stepSz), halfStep = xscale(fullStep, 0.5f);
+    float node1 = grid_lookup(m, p);
+    for (uint32_t i = 0; i < nSteps; ++i) {
+        const float node2 = grid_lookup(m, xadd3(p, halfStep)), node3 = grid_lookup(m, xadd3(p, fullStep));
+        const float newDensity = xadd(integratedDensity, xmul(multiplier, xadd(xadd(node1, xmul(node2, 4.0f)), node3)));
+        if (newDensity >= desiredDensity) {
+            float a = 0, b = stepSz, x = a, fx = xsub(integratedDensity, desiredDensity);
+            const float stepSizeSqr = xmul(stepSz, stepSz), temp = xdiv(m.scale, stepSizeSqr);
+            /* the coefficients of the Lagrange polynomial: (3 node1 - 4 node2 + node3), (node1 - 2 node2 + node3) */
+            const float c1 = xadd(xsub(xmul(3.0f, node1), xmul(4.0f, node2)), node3), c2 = xadd(xsub(node1, xmul(2.0f, node2)), node3);
+            int it = 1;
+            while (true) {
+                const float dfx = xmul(temp, xadd(xsub(xmul(node1, stepSizeSqr), xmul(xmul(c1, stepSz), x)), xmul(xmul(xmul(2.0f, c2), x), x)));
+                x = xsub(x, xdiv(fx, dfx));
+                if (x <= a || x >= b || dfx == 0) x = xmul(0.5f, xadd(b, a));
+                const float poly = xadd(xsub(xmul(xmul(6.0f, node1), stepSizeSqr), xmul(xmul(xmul(3.0f, c1), stepSz), x)), xmul(xmul(xmul(4.0f, c2), x), x));
+                const float intval = xadd(integratedDensity, xmul(xmul(temp, 1.0f / 6.0f), xmul(x, poly)));
+                fx = xsub(intval, desiredDensity);
+                if (fabsf(fx) < 1e-6f) {
+                    t = xadd(xadd(mint, xmul(stepSz, (float) i)), x);
+                    integratedDensity = intval;
+                    densityAtT = xmul(temp, xadd(xsub(xmul(node1, stepSizeSqr), xmul(xmul(c1, stepSz), x)), xmul(xmul(xmul(2.0f, c2), x), x)));
+                    return true;
+                } else if (++it > 30) return false;
+                if (fx > 0) b = x;
+                else a = x;
+            }
+        }
+        const F3 next = xadd3(p, fullStep);
+        if (p.x == next.x && p.y == next.y && p.z == next.z) break;
+        integratedDensity = newDensity;
+        node1 = node3;
+        p = next;
+    }
+    return false;
+}
+
 /* its.p (barycentric) and the face normal of a triangle hit, ShapeKDTree::rayIntersect + fillIntersectionRecord<true>
  * (skdtree.h:343-428): what Scene::rayIntersect(ray, its) leaves in its.p / its.geoFrame.n = its.shFrame.n (no vertex normals) */
 __device__ __forceinline__ void hit_point_normal(const float4 *__restrict__ triVerts, uint32_t prim, float u, float v, F3 &hp, F3 &fn, F3 &dpdu) {

@@ -985,7 +985,22 @@ void traceOneParticle(Ctx *c, Sampler *smp, std::vector<TracedVrl> &out) {
             /* medium->sampleDistance(Ray(ray, 0, its.t), mRec, sampler), homogeneous.cpp:275-352 (EBalance) */
             bool scattered = false;
             Spec mTrans(1.0f), mSigmaS; Float pdfFailure = 1, pdfSuccess = 1; V3 mP;
-            if (inMedium) {
+            if (inMedium && med.type == 1) {
+                /* HeterogeneousMedium::sampleDistance, heterogeneous.cpp:589-616 (simpson): one uniform, the optical depth it asks
+                 * for, the march that finds where the ray reaches it */
+                Float desiredDensity = -((Float) ::log((double) (1 - smp->next1D())));
+                Float integratedDensity, tt, densityAtMinT, densityAtT;
+                Ray seg(ray.o, ray.d, 0, its.t);
+                bool success = false;
+                if (med.invertDensityIntegral(seg, desiredDensity, integratedDensity, tt, densityAtMinT, densityAtT)) {
+                    mP = seg(tt);
+                    success = true;
+                    mSigmaS = med.hetAlbedo * densityAtT;
+                }
+                Float expVal = fastexp(-integratedDensity);
+                pdfFailure = expVal; pdfSuccess = expVal * densityAtT; mTrans = Spec(expVal);
+                scattered = success && pdfSuccess > 0;
+            } else if (inMedium) {
                 Float rnd = smp->next1D(), sampledDistance;
                 Float samplingDensity = 0;
                 if (rnd < med.samplingWeight) {
@@ -1084,7 +1099,6 @@ void traceOneParticle(Ctx *c, Sampler *smp, std::vector<TracedVrl> &out) {
 int orc_trace_vrls(void *h, uint32_t target) {
     Ctx *c = (Ctx *) h;
     if (!c->haveEmitter || !c->haveMedium || !c->haveMat) return seterr(ALVRL_ERR_STATE, "trace_vrls: set_area_emitter / set_medium / set_materials first");
-    if (c->medium.type != 0) return seterr(ALVRL_ERR_UNSUPPORTED, "trace_vrls: homogeneous media only");
     ORC_TRY
     if (!target) target = (uint32_t) c->P.vrlTargetNum;
     CounterSampler smp(c->P.seed);
@@ -1133,7 +1147,21 @@ inline Float miWeight(Float pdfA, Float pdfB) { pdfA *= pdfA; pdfB *= pdfB; retu
 
 /* HomogeneousMedium::sampleDistance(Ray(ray, 0, itsT), mRec, sampler), homogeneous.cpp:275-352 (strategy = balance) */
 struct MRec { Spec transmittance, sigmaS; Float pdfFailure = 1, pdfSuccess = 1; V3 p; };
-inline bool sampleDistanceH(const Medium &med, const Ray &ray, Float itsT, Sampler *smp, MRec &m) {
+inline bool sampleDistanceH(Medium &med, const Ray &ray, Float itsT, Sampler *smp, MRec &m) {
+    if (med.type == 1) {                                                    // heterogeneous.cpp:589-616 (simpson)
+        Float desiredDensity = -((Float) ::log((double) (1 - smp->next1D())));
+        Float integratedDensity, tt, densityAtMinT, densityAtT;
+        Ray seg(ray.o, ray.d, 0, itsT);
+        bool success = false;
+        if (med.invertDensityIntegral(seg, desiredDensity, integratedDensity, tt, densityAtMinT, densityAtT)) {
+            m.p = seg(tt);
+            success = true;
+            m.sigmaS = med.hetAlbedo * densityAtT;
+        }
+        Float expVal = fastexp(-integratedDensity);
+        m.pdfFailure = expVal; m.pdfSuccess = expVal * densityAtT; m.transmittance = Spec(expVal);
+        return success && m.pdfSuccess > 0;
+    }
     Float rnd = smp->next1D(), sampledDistance;
     Float samplingDensity = 0;
     if (rnd < med.samplingWeight) {
@@ -1373,7 +1401,6 @@ Spec volpathLiOriginal(Ctx *c, const VolpathCfg &cfg, Sampler *smp, const Ray &r
 int orc_volpath_render(void *h, uint32_t spp, uint32_t internalSamples, uint32_t flags, int32_t maxDepth, float *rgb) {
     Ctx *c = (Ctx *) h;
     if (!c->haveEmitter || !c->haveMedium || !c->haveMat || !c->haveCam) return seterr(ALVRL_ERR_STATE, "volpath_render: set_area_emitter / set_medium / set_materials / set_camera first");
-    if (c->medium.type != 0) return seterr(ALVRL_ERR_UNSUPPORTED, "volpath_render: homogeneous media only");
     if (!spp || !internalSamples) return seterr(ALVRL_ERR_ARG, "volpath_render: spp and internalSamples must be positive");
     ORC_TRY
     VolpathCfg cfg;

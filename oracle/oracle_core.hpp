@@ -634,6 +634,56 @@ struct Medium {
         }
         return integratedDensity * scale * stepSz * (1.0f / 3.0f);
     }
+    /* HeterogeneousMedium::invertDensityIntegral, heterogeneous.cpp:422-545: composite Simpson march until the optical depth
+     * reaches desiredDensity, then Newton-bisection on the quadratic through the last three lookups */
+    bool invertDensityIntegral(const Ray &ray, Float desiredDensity, Float &integratedDensity, Float &t, Float &densityAtMinT, Float &densityAtT) {
+        integratedDensity = densityAtMinT = densityAtT = 0.0f;
+        AABB box; box.min = bmin; box.max = bmax;
+        Float mint, maxt;
+        if (!box.rayIntersect(ray, mint, maxt)) return false;
+        mint = std::max(mint, ray.mint);
+        maxt = std::min(maxt, ray.maxt);
+        Float length = maxt - mint, maxComp = 0;
+        V3 p = ray(mint), pLast = ray(maxt);
+        for (int i = 0; i < 3; ++i) maxComp = std::max(std::max(maxComp, std::abs(p[i])), std::abs(pLast[i]));
+        if (length < 1e-6f * maxComp) return false;
+        uint32_t nSteps = (uint32_t) std::ceil(length / (2 * stepSize));
+        Float stepSz = length / nSteps, multiplier = (1.0f / 6.0f) * stepSz * scale;
+        V3 fullStep = ray.d * stepSz, halfStep = fullStep * .5f;
+        Float node1 = lookupDensity(p);
+        if (ray.mint == mint) densityAtMinT = node1 * scale;
+        else densityAtMinT = 0.0f;
+        for (uint32_t i = 0; i < nSteps; ++i) {
+            Float node2 = lookupDensity(p + halfStep), node3 = lookupDensity(p + fullStep),
+                  newDensity = integratedDensity + multiplier * (node1 + node2 * 4 + node3);
+            if (newDensity >= desiredDensity) {
+                Float a = 0, b = stepSz, x = a, fx = integratedDensity - desiredDensity, stepSizeSqr = stepSz * stepSz, temp = scale / stepSizeSqr;
+                int it = 1;
+                while (true) {
+                    Float dfx = temp * (node1 * stepSizeSqr - (3 * node1 - 4 * node2 + node3) * stepSz * x + 2 * (node1 - 2 * node2 + node3) * x * x);
+                    x -= fx / dfx;
+                    if (x <= a || x >= b || dfx == 0) x = 0.5f * (b + a);
+                    Float intval = integratedDensity + temp * (1.0f / 6.0f) * (x * (6 * node1 * stepSizeSqr - 3 * (3 * node1 - 4 * node2 + node3) * stepSz * x
+                                                                                  + 4 * (node1 - 2 * node2 + node3) * x * x));
+                    fx = intval - desiredDensity;
+                    if (std::abs(fx) < 1e-6f) {
+                        t = mint + stepSz * i + x;
+                        integratedDensity = intval;
+                        densityAtT = temp * (node1 * stepSizeSqr - (3 * node1 - 4 * node2 + node3) * stepSz * x + 2 * (node1 - 2 * node2 + node3) * x * x);
+                        return true;
+                    } else if (++it > 30) return false;
+                    if (fx > 0) b = x;
+                    else a = x;
+                }
+            }
+            V3 next = p + fullStep;
+            if (p.x == next.x && p.y == next.y && p.z == next.z) break;
+            integratedDensity = newDensity;
+            node1 = node3;
+            p = next;
+        }
+        return false;
+    }
     /* Medium::evalTransmittance */
     Spec evalTransmittance(const Ray &ray) {
         if (type == 0) {                                                   // homogeneous.cpp:266-273
