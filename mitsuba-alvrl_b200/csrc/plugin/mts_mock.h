@@ -9,6 +9,7 @@
  * 483-511) and the few Scene/Sensor/Film/Medium/TriMesh accessors preprocess() marshals from.
  */
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <map>
 #include <set>
@@ -50,6 +51,27 @@ private:
     mutable std::set<std::string> m_q;
 };
 
+/* Stream (include/mitsuba/core/stream.h): what serialize() / the unserializing constructor use -- typed values in sequence */
+class Stream {
+public:
+    void write(const void *p, size_t n) { put(p, n); }                       /* Stream::write, stream.h */
+    void writeInt(int v) { put(&v, sizeof(v)); }
+    void writeFloat(float v) { put(&v, sizeof(v)); }
+    void writeBool(bool v) { uint8_t b = v ? 1 : 0; put(&b, 1); }           /* stream.h: writeBool = writeUChar */
+    int readInt() { int v; get(&v, sizeof(v)); return v; }
+    float readFloat() { float v; get(&v, sizeof(v)); return v; }
+    bool readBool() { uint8_t b; get(&b, 1); return b != 0; }
+    const std::vector<uint8_t> &bytes() const { return m_data; }
+    void seek(size_t pos) { m_pos = pos; }
+private:
+    void put(const void *p, size_t n) { const uint8_t *b = static_cast<const uint8_t *>(p); m_data.insert(m_data.end(), b, b + n); }
+    void get(void *p, size_t n) {
+        if (m_pos + n > m_data.size()) LogError("Stream: read beyond the end of the stream");
+        std::copy(m_data.begin() + m_pos, m_data.begin() + m_pos + n, static_cast<uint8_t *>(p)); m_pos += n;
+    }
+    std::vector<uint8_t> m_data; size_t m_pos = 0;
+};
+
 /* what preprocess() reads from `const Scene *` (triangle meshes with diffuse BSDFs, one medium, a perspective sensor) */
 /* bsdf: 0 diffuse (reflectance), 1 smooth dielectric (eta = intIOR / extIOR), 2 smooth conductor (eta, k rgb); the shape's
  * interior / exterior medium is the scene's medium or none (Shape::getInteriorMedium / getExteriorMedium) */
@@ -79,6 +101,7 @@ public:
     virtual bool preprocess(const Scene *scene) = 0;
     virtual bool prepass(const Scene *scene) = 0;
     virtual bool render(Scene *scene) = 0;
+    virtual void serialize(Stream *stream) const = 0;      /* network rendering: the object travels to the nodes */
     virtual void cancel() {}
 };
 

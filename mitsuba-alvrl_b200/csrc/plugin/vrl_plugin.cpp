@@ -54,12 +54,39 @@ public:
         m_p.convergenceFalseColor = props.getBoolean("convergenceFalseColor", false);
         m_vrlFile = props.getString("vrlFile", "");
         /* inherited (src/librender/integrator.cpp:53,272-298,348-349): queried so that the loader does not warn */
-        m_p.maxPasses = m_maxPasses = props.getInteger("maxPasses", 1);
-        props.getBoolean("dumpPasses", false); props.getInteger("rrDepth", 5); props.getInteger("maxDepth", -1);
-        props.getBoolean("strictNormals", false); props.getBoolean("hideEmitters", false); props.getInteger("numPasses", 1);
+        m_numPasses = props.getInteger("numPasses", 1);                                                  /* SamplingIntegrator, 53 */
+        m_p.rrDepth = props.getInteger("rrDepth", 5);                     /* MonteCarloIntegrator, 270-306; the VRL tracer's roulette (279) */
+        m_maxDepth = props.getInteger("maxDepth", -1);
+        m_strictNormals = props.getBoolean("strictNormals", false); m_hideEmitters = props.getBoolean("hideEmitters", false);
+        if (m_p.rrDepth <= 0) mts::LogError("'rrDepth' must be set to a value greater than zero!");
+        if (m_maxDepth <= 0 && m_maxDepth != -1) mts::LogError("'maxDepth' must be set to -1 (infinite) or a value greater than zero!");
+        m_p.maxPasses = m_maxPasses = props.getInteger("maxPasses", 1);                                  /* ProgressiveMonteCarloIntegrator, 348-349 */
+        m_dumpPasses = props.getBoolean("dumpPasses", false);
         /* device selection has no XML equivalent in the reference */
         m_device = props.getInteger("cudaDevice", 0);
         m_p.seed = (uint64_t) props.getInteger("seed", 0);
+    }
+    /* the unserializing constructor and serialize(): what travels to a network node (vrlIntegrator.cpp:210-235 after the base
+     * classes, src/librender/integrator.cpp:56-63, 307-321, 351-360) -- the reference's own field order; like the reference, the
+     * clustering parameters do not travel */
+    explicit vrlIntegrator(mts::Stream *stream) {
+        alvrl_params_default(&m_p);
+        m_numPasses = stream->readInt();
+        m_p.rrDepth = stream->readInt(); m_maxDepth = stream->readInt(); m_strictNormals = stream->readBool(); m_hideEmitters = stream->readBool();
+        m_p.maxPasses = m_maxPasses = stream->readInt(); m_dumpPasses = stream->readBool();
+        m_p.volVolSamples = stream->readInt(); m_p.volSurfSamples = stream->readInt();
+        m_p.globalCluster = stream->readBool(); m_p.localRefinement = stream->readBool();
+        m_p.specularForcedRRdepth = stream->readInt(); m_p.initialSpecularThroughput = stream->readFloat();
+        m_p.shortVrls = stream->readBool();
+    }
+    void serialize(mts::Stream *stream) const override {
+        stream->writeInt(m_numPasses);
+        stream->writeInt(m_p.rrDepth); stream->writeInt(m_maxDepth); stream->writeBool(m_strictNormals); stream->writeBool(m_hideEmitters);
+        stream->writeInt(m_maxPasses); stream->writeBool(m_dumpPasses);
+        stream->writeInt(m_p.volVolSamples); stream->writeInt(m_p.volSurfSamples);
+        stream->writeBool(m_p.globalCluster != 0); stream->writeBool(m_p.localRefinement != 0);
+        stream->writeInt(m_p.specularForcedRRdepth); stream->writeFloat(m_p.initialSpecularThroughput);
+        stream->writeBool(m_p.shortVrls != 0);
     }
     ~vrlIntegrator() override { if (m_h) alvrl_destroy(m_h); }
 
@@ -149,7 +176,8 @@ public:
         const int filter = scene->film ? scene->film->rfilter : ALVRL_FILTER_BOX;
         const bool useFilm = m_maxPasses > 1 || filter != ALVRL_FILTER_BOX;
         if (useFilm) chk(alvrl_film_configure(m_h, filter, scene->film ? scene->film->rfilterParam : 0.0f));
-        for (int pass = 1; pass <= m_maxPasses; pass++) {
+        m_cancelled = false;
+        for (int pass = 1; pass <= m_maxPasses && !m_cancelled; pass++) {   /* cancel() takes effect between passes */
             if (!prepass(scene)) return false;
             if (!renderPass(scene, rgb)) return false;
             if (useFilm) chk(alvrl_film_put(m_h, nullptr));                   /* the frame alvrl_render left on the device */
@@ -158,10 +186,14 @@ public:
         if (scene->film) scene->film->setImage(rgb.data(), scene->sensor.width, scene->sensor.height);
         return true;
     }
+    /* SamplingIntegrator::cancel (integrator.cpp:68-71) stops the block scheduler; here: no further pass is started */
+    void cancel() override { m_cancelled = true; }
     alvrl_handle handle() const { return m_h; }
 private:
     static void chk(int rc) { if (rc != ALVRL_OK) mts::LogError(alvrl_last_error()); }
     alvrl_params m_p; std::string m_vrlFile; int m_device = 0, m_maxPasses = 1, m_pass = 0; alvrl_handle m_h = nullptr;
+    int m_numPasses = 1, m_maxDepth = -1; bool m_strictNormals = false, m_hideEmitters = false, m_dumpPasses = false;
+    volatile bool m_cancelled = false;
 };
 
 } // namespace
@@ -172,6 +204,22 @@ const char *GetDescription() { return "An implementation of Adaptive Lightslice 
 /* test hook: the parsed parameter block of an instance */
 void alvrl_plugin_get_params(void *inst, alvrl_params *out) { *out = static_cast<vrlIntegrator *>(inst)->params(); }
 void alvrl_plugin_destroy(void *inst) { delete static_cast<vrlIntegrator *>(inst); }
+/* test hooks: serialize an instance into a byte buffer (returns the size; buf may be NULL) and build one from such a buffer */
+int alvrl_plugin_serialize(void *inst, uint8_t *buf, int cap) {
+    mts::Stream st; static_cast<vrlIntegrator *>(inst)->serialize(&st);
+    const int n = (int) st.bytes().size();
+    if (buf && cap >= n) memcpy(buf, st.bytes().data(), (size_t) n);
+    return n;
+}
+int alvrl_plugin_unserialize(const uint8_t *buf, int n, void **inst, char *err, int errLen) {
+    try {
+        mts::Stream st;
+        st.write(buf, (size_t) n);
+        st.seek(0);
+        *inst = new vrlIntegrator(&st);
+        return 0;
+    } catch (const std::exception &e) { strncpy(err, e.what(), errLen - 1); err[errLen - 1] = 0; return -1; }
+}
 /* test hooks for building a Properties object from C */
 void *alvrl_plugin_props_new() { return new mts::Properties(); }
 void alvrl_plugin_props_free(void *p) { delete static_cast<mts::Properties *>(p); }

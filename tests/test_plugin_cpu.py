@@ -121,3 +121,50 @@ def test_preprocess_checks_the_scene_before_it_touches_the_device(plugin):
     assert rc != 0 and "not a mesh" in err
     rc, err = frame(medium, vrlFile="/tmp/some.vrl", maxPasses=-1)
     assert rc != 0 and "maxPasses" in err
+
+
+def test_inherited_parameters_and_their_errors(plugin, pkg):
+    """MonteCarloIntegrator's constructor checks (src/librender/integrator.cpp:300-305); rrDepth reaches the parameter block
+    (it is the roulette depth of the VRL tracer, vrlIntegrator.cpp:279)"""
+    rc, err, params, _ = _create(plugin, pkg, rrDepth=9)
+    assert rc == 0 and params.rrDepth == 9
+    rc, err, _, _ = _create(plugin, pkg, rrDepth=0)
+    assert rc != 0 and "rrDepth" in err
+    rc, err, _, _ = _create(plugin, pkg, maxDepth=0)
+    assert rc != 0 and "maxDepth" in err
+    rc, err, _, _ = _create(plugin, pkg, maxDepth=-1)
+    assert rc == 0
+
+
+def test_serialize_round_trip_in_the_reference_field_order(plugin, pkg):
+    """what travels to a network node: numPasses | rrDepth maxDepth strictNormals hideEmitters | maxPasses dumpPasses |
+    volVolSamples volSurfSamples globalCluster localRefinement specRRdepth initialSpecularThroughput shortVrls
+    (integrator.cpp:61-63, 315-320, 356-359; vrlIntegrator.cpp:226-235) -- ints and floats 4 bytes, bools 1 byte"""
+    import struct
+    p = C.c_void_p(plugin.alvrl_plugin_props_new())
+    for k, v in dict(numPasses=2, rrDepth=7, maxDepth=12, maxPasses=3, volVolSamples=4, volSurfSamples=6, specularForcedRRdepth=50).items():
+        plugin.alvrl_plugin_props_set_int(p, k.encode(), v)
+    for k, v in dict(strictNormals=True, hideEmitters=False, dumpPasses=True, globalCluster=True, localRefinement=False, shortVrls=False).items():
+        plugin.alvrl_plugin_props_set_bool(p, k.encode(), int(v))
+    plugin.alvrl_plugin_props_set_float(p, b"initialSpecularThroughput", C.c_float(12.5))
+    inst = C.c_void_p()
+    err = C.create_string_buffer(512)
+    assert plugin.alvrl_plugin_create(p, C.byref(inst), err, 512) == 0, err.value
+    n = plugin.alvrl_plugin_serialize(inst, None, 0)
+    buf = (C.c_uint8 * n)()
+    assert plugin.alvrl_plugin_serialize(inst, buf, n) == n
+    want = struct.pack("=iii??i?ii??if?", 2, 7, 12, True, False, 3, True, 4, 6, True, False, 50, 12.5, False)
+    assert bytes(buf) == want
+    inst2 = C.c_void_p()
+    assert plugin.alvrl_plugin_unserialize(buf, n, C.byref(inst2), err, 512) == 0, err.value
+    a, b = pkg.binding.Params(), pkg.binding.Params()
+    plugin.alvrl_plugin_get_params(inst, C.byref(a)); plugin.alvrl_plugin_get_params(inst2, C.byref(b))
+    for f in ("rrDepth", "maxPasses", "volVolSamples", "volSurfSamples", "globalCluster", "localRefinement", "specularForcedRRdepth",
+              "initialSpecularThroughput", "shortVrls"):
+        assert getattr(a, f) == getattr(b, f), f
+    n2 = plugin.alvrl_plugin_serialize(inst2, None, 0)
+    buf2 = (C.c_uint8 * n2)()
+    plugin.alvrl_plugin_serialize(inst2, buf2, n2)
+    assert bytes(buf2) == want                           # what was not transmitted (the clustering parameters) is at its default
+    assert plugin.alvrl_plugin_unserialize(buf, n - 3, C.byref(inst2), err, 512) != 0 and b"beyond the end" in err.value
+    plugin.alvrl_plugin_destroy(inst); plugin.alvrl_plugin_props_free(p)
