@@ -1231,6 +1231,19 @@ inline Float pdfEmitterDirect(Ctx *c, const DirectRec &dRec) {                  
     return 0.0f;
 }
 
+/* PhaseFunction::sample(pRec, pdf, sampler) with pRec.wi = wi: isotropic.cpp:69-74, hg.cpp:74-104; returns wo, the value is 1 */
+inline V3 samplePhase(const Medium &med, const V3 &wi, Float px, Float py, Float &pdf) {
+    if (med.phaseType == ALVRL_PHASE_ISOTROPIC) { pdf = INV_FOURPI; return squareToUniformSphere(px, py); }
+    Float cosTheta;
+    if (std::abs(med.g) < Epsilon) cosTheta = 1 - 2 * px;
+    else { Float sqrTerm = (1 - med.g * med.g) / (1 - med.g + 2 * med.g * px); cosTheta = (1 + med.g * med.g - sqrTerm * sqrTerm) / (2 * med.g); }
+    Float sinTheta = safe_sqrt(1.0f - cosTheta * cosTheta), sinPhi, cosPhi;
+    sincosF((Float) (2 * M_PI * py), &sinPhi, &cosPhi);
+    V3 wo = frameToWorld(-wi, V3(sinTheta * cosPhi, sinTheta * sinPhi, cosTheta));                                       // Frame(-pRec.wi)
+    pdf = med.phaseEval(wi, wo);
+    return wo;
+}
+
 Spec volpathLiOriginal(Ctx *c, const VolpathCfg &cfg, Sampler *smp, const Ray &r, bool sensorInMedium) {
     Medium &med = c->medium;
     Ray ray(r);
@@ -1282,17 +1295,7 @@ Spec volpathLiOriginal(Ctx *c, const VolpathCfg &cfg, Sampler *smp, const Ray &r
             /* phase function sampling: sample(pRec, pdf, sampler) returns 1 (isotropic.cpp:69-74, hg.cpp:99-104) */
             Float phasePdf;
             Float px = smp->next1D(), py = smp->next1D();
-            V3 wo;
-            if (med.phaseType == ALVRL_PHASE_ISOTROPIC) { wo = squareToUniformSphere(px, py); phasePdf = INV_FOURPI; }
-            else {
-                Float cosTheta;
-                if (std::abs(med.g) < Epsilon) cosTheta = 1 - 2 * px;
-                else { Float sqrTerm = (1 - med.g * med.g) / (1 - med.g + 2 * med.g * px); cosTheta = (1 + med.g * med.g - sqrTerm * sqrTerm) / (2 * med.g); }
-                Float sinTheta = safe_sqrt(1.0f - cosTheta * cosTheta), sinPhi, cosPhi;
-                sincosF((Float) (2 * M_PI * py), &sinPhi, &cosPhi);
-                wo = frameToWorld(ray.d, V3(sinTheta * cosPhi, sinTheta * sinPhi, cosTheta));                           // Frame(-pRec.wi), wi = -ray.d
-                phasePdf = med.phaseEval(-ray.d, wo);
-            }
+            V3 wo = samplePhase(med, -ray.d, px, py, phasePdf);
             ray = Ray(mRec.p, wo, 0, std::numeric_limits<Float>::infinity());
             Spec value(0.0f);
             lookForEmitter(ray, dRec, value);
@@ -1435,6 +1438,52 @@ int orc_volpath_render(void *h, uint32_t spp, uint32_t internalSamples, uint32_t
     for (int t = 0; t < T; t++) th.emplace_back(work, (uint32_t) ((uint64_t) W * t / T), (uint32_t) ((uint64_t) W * (t + 1) / T));
     for (auto &t : th) t.join();
     ORC_CATCH
+}
+
+/* ---- test hooks for the chi-square tests of the sampling routines (the reference's own strategy for them:
+ * src/tests/test_chisquare.cpp:508-573 phase functions, 575-623 emitters) ------------------------------------------------- */
+int orc_test_phase_sample(int32_t phaseType, float g, const float wi[3], const float *u, uint32_t n, float *wo, float *pdf) {
+    Medium med; med.phaseType = phaseType; med.g = g;
+    for (uint32_t i = 0; i < n; i++) {
+        Float p; V3 w = samplePhase(med, V3(wi[0], wi[1], wi[2]), u[2 * i], u[2 * i + 1], p);
+        wo[3 * i] = w.x; wo[3 * i + 1] = w.y; wo[3 * i + 2] = w.z; pdf[i] = p;
+    }
+    return ALVRL_OK;
+}
+int orc_test_phase_eval(int32_t phaseType, float g, const float wi[3], const float *wo, uint32_t n, float *val) {
+    Medium med; med.phaseType = phaseType; med.g = g;
+    for (uint32_t i = 0; i < n; i++) val[i] = med.phaseEval(V3(wi[0], wi[1], wi[2]), V3(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]));
+    return ALVRL_OK;
+}
+/* emitter->sampleDirect from a reference point in the volume (refN = 0): direction, solid-angle pdf, radiance / pdf */
+int orc_test_emitter_sample_direct(void *h, const float ref[3], const float *u, uint32_t n, float *d, float *pdf, float *value) {
+    Ctx *c = (Ctx *) h;
+    if (!c->haveEmitter) return seterr(ALVRL_ERR_STATE, "set_area_emitter first");
+    for (uint32_t i = 0; i < n; i++) {
+        DirectRec dRec; dRec.ref = V3(ref[0], ref[1], ref[2]); dRec.refN = V3(0.0f);
+        Spec v = emitterSampleDirect(c, dRec, u[2 * i], u[2 * i + 1]);
+        d[3 * i] = dRec.d.x; d[3 * i + 1] = dRec.d.y; d[3 * i + 2] = dRec.d.z; pdf[i] = dRec.pdf;
+        value[3 * i] = v[0]; value[3 * i + 1] = v[1]; value[3 * i + 2] = v[2];
+    }
+    return ALVRL_OK;
+}
+/* the density of having sampled direction d from ref: intersect, and if the emitter is what the ray meets, emitter->pdfDirect of the
+ * query record (test_chisquare.cpp:364-378; volpath.cpp:521-524 + scene.cpp:949-952) */
+int orc_test_emitter_pdf_direct(void *h, const float ref[3], const float *d, uint32_t n, float *pdf) {
+    Ctx *c = (Ctx *) h;
+    if (!c->haveEmitter) return seterr(ALVRL_ERR_STATE, "set_area_emitter first");
+    for (uint32_t i = 0; i < n; i++) {
+        V3 dir(d[3 * i], d[3 * i + 1], d[3 * i + 2]);
+        Ray q(V3(ref[0], ref[1], ref[2]), dir, 0, std::numeric_limits<Float>::infinity());
+        Intersection its;
+        pdf[i] = 0;
+        if (c->scene.rayIntersect(q, its) && c->triIsEmitter[its.prim]) {
+            DirectRec dRec; dRec.ref = q.o; dRec.refN = V3(0.0f);
+            dRec.p = its.p; dRec.n = its.n; dRec.d = dir; dRec.dist = its.t;
+            pdf[i] = pdfEmitterDirect(c, dRec);
+        }
+    }
+    return ALVRL_OK;
 }
 
 /* Film: ReconstructionFilter::configure / evalDiscretized (src/libcore/rfilter.cpp:37-55, include/mitsuba/core/rfilter.h:76-77),
