@@ -141,6 +141,13 @@ int alvrl_set_medium_grid(alvrl_handle h, const float *density, const int32_t re
                           const float bbox_min[3], const float bbox_max[3], float scale,
                           const float albedo[3], const float sigmaS_base[3],
                           int32_t phaseType, float g);
+/* The same medium with the density read from the grid volume file a `gridvolume` plugin would map
+ * (src/volume/gridvolume.cpp:217-287: "VOL", version 3; one channel, float32 or uint8 -- uint8 through the reference's
+ * density map i / 255.0f, gridvolume.cpp:212-215,374-389).  bbox_min / bbox_max: NULL takes the AABB stored in the file,
+ * non-NULL is the `min` / `max` override of gridvolume.cpp:112-117.  Errors keep the reference's messages (ALVRL_ERR_IO:
+ * unreadable or truncated; ALVRL_ERR_ARG: bad identifier / version / type; ALVRL_ERR_UNSUPPORTED: float16, 3 channels). */
+int alvrl_set_medium_grid_file(alvrl_handle h, const char *path, const float *bbox_min, const float *bbox_max, float scale,
+                               const float albedo[3], const float sigmaS_base[3], int32_t phaseType, float g);
 /* PerspectiveCamera (src/sensors/perspective.cpp:126-175,247-269): row-major 4x4 matrices. */
 int alvrl_set_camera(alvrl_handle h, const float sampleToCamera[16], const float cameraToWorld[16],
                      uint32_t width, uint32_t height, float nearClip, float farClip);
@@ -242,6 +249,9 @@ int alvrl_film_configure(alvrl_handle h, int filter, float param);
 int alvrl_film_clear(alvrl_handle h);
 int alvrl_film_put(alvrl_handle h, const float *rgb_host);
 int alvrl_film_develop(alvrl_handle h, float *rgb_host);
+/* The developed film as the NumPy file the reference's `mfilm` writes with fileFormat = numpy (src/films/mfilm.cpp:337-348
+ * through cnpy::npy_save, src/films/cnpy.h:207-236): format 1.0, '<f4', C order, shape (H, W, 3). */
+int alvrl_film_write_npy(alvrl_handle h, const char *path);
 
 /* Device variants for multi-GPU: only slices [sliceBegin, sliceEnd) are processed; the
  * framebuffer (W*H*4 floats, zero-initialised by the caller) lives in caller-owned device memory. */

@@ -6,7 +6,7 @@ tests, bench.py and torch.distributed plumbing.  There is no CPU fallback: `inte
 library is missing."""
 import os
 
-from . import binding, rms, scenes, sharding  # noqa: F401
+from . import binding, rms, scenes, sharding, volfile  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ALVRL_LIB", os.path.join(_HERE, "libalvrl.so"))   # ALVRL_LIB: kernel-variant experiments (tools/build_variant.sh)

@@ -6,6 +6,8 @@ reference's own vocabulary (build_slices, sample_slice_mapping, build_R, build_c
 src/integrators/vrl/vrlIntegrator.cpp:237-356, Preprocessor.cpp:133,1130,1502).
 """
 import ctypes as C
+import os
+
 import numpy as np
 
 NO_SLICE = 0xFFFFFFFF
@@ -211,6 +213,15 @@ class Integrator:
         self._call("set_medium_grid", _p(d), _p(res), _p(mn), _p(mx), C.c_float(scale), _p(al), _p(sb),
                    C.c_int32(phase), C.c_float(g))
 
+    def set_medium_grid_file(self, path, scale, albedo, sigmaS_base, bmin=None, bmax=None, phase=PHASE_ISOTROPIC, g=0.0):
+        """the density from a grid volume file ("VOL", version 3: src/volume/gridvolume.cpp:217-287); bmin / bmax override the
+        AABB stored in the file"""
+        al, sb = _f32(albedo), _f32(sigmaS_base)
+        mn = _f32(bmin) if bmin is not None else None
+        mx = _f32(bmax) if bmax is not None else None
+        self._call("set_medium_grid_file", C.c_char_p(os.fsencode(path)), _p(mn), _p(mx), C.c_float(scale), _p(al), _p(sb),
+                   C.c_int32(phase), C.c_float(g))
+
     def set_camera(self, s2c, c2w, W, H, near, far):
         a, b = _f32(s2c).reshape(16), _f32(c2w).reshape(16)
         self._call("set_camera", _p(a), _p(b), C.c_uint32(W), C.c_uint32(H), C.c_float(near), C.c_float(far))
@@ -297,6 +308,10 @@ class Integrator:
         out = np.zeros((self.H, self.W, 3), dtype=np.float32)
         self._call("film_develop", _p(out))
         return out
+
+    def film_write_npy(self, path):
+        """the developed film as mfilm's NumPy output (src/films/mfilm.cpp:337-348): '<f4', shape (H, W, 3)"""
+        self._call("film_write_npy", C.c_char_p(os.fsencode(path)))
 
     def set_slice_range(self, b, e):
         self._call("set_slice_range", C.c_uint32(b), C.c_uint32(e))

@@ -15,6 +15,7 @@
 #include "context.h"
 #include "occluders.h"
 #include "kernels.h"
+#include "hostio.h"
 
 using namespace alvrl;
 
@@ -554,6 +555,16 @@ int alvrl_set_medium_grid(alvrl_handle c, const float *density, const int32_t re
     API_END
 }
 
+int alvrl_set_medium_grid_file(alvrl_handle c, const char *path, const float *mn, const float *mx, float scale,
+                               const float albedo[3], const float sBase[3], int32_t phase, float g) {
+    VolFile vf;
+    try { read_vol_file(path, vf); }
+    catch (const HostIoError &e) { return fail(e.code, e.what()); }
+    catch (const std::exception &e) { return fail(ALVRL_ERR_IO, e.what()); }
+    if ((mn == nullptr) != (mx == nullptr)) return fail(ALVRL_ERR_ARG, "alvrl_set_medium_grid_file: give both bbox_min and bbox_max, or neither");
+    return alvrl_set_medium_grid(c, vf.density.data(), vf.res, mn ? mn : vf.bmin, mx ? mx : vf.bmax, scale, albedo, sBase, phase, g);
+}
+
 int alvrl_set_camera(alvrl_handle c, const float s2c[16], const float c2w[16], uint32_t W, uint32_t H, float nearClip, float farClip) {
     API_BEGIN
     if (W == 0 || H == 0) throw Error(ALVRL_ERR_ARG, "empty film");
@@ -1079,6 +1090,16 @@ int alvrl_film_develop(alvrl_handle c, float *rgb) {
     c->stats.kernelLaunches++;
     c->dRgb.download(rgb, 3 * (size_t) P, c->stream);
     API_END
+}
+
+int alvrl_film_write_npy(alvrl_handle c, const char *path) {
+    if (!path) return fail(ALVRL_ERR_ARG, "alvrl_film_write_npy: null file name");
+    std::vector<float> rgb(3 * (size_t) c->numPixels());
+    const int rc = alvrl_film_develop(c, rgb.data());
+    if (rc != ALVRL_OK) return rc;
+    try { write_npy_f32(path, rgb.data(), c->cam.H, c->cam.W, 3); }
+    catch (const HostIoError &e) { return fail(e.code, e.what()); }
+    return ALVRL_OK;
 }
 
 int alvrl_render_device(alvrl_handle c, void *rgba, void *stream) {

@@ -10,6 +10,7 @@
 #include "occluders.h"
 #include "occ_query.h"
 #include "sharding.h"
+#include "hostio.h"
 #include <algorithm>
 #include <cstring>
 using namespace alvrl;
@@ -38,6 +39,30 @@ int alvrl_host_balance_step(const uint32_t *sliceSize, uint32_t S, int world, do
     cut_weights(c, next);
     for (uint32_t i = 0; i < S; i++) { cost[i] = c[i]; weightsOut[i] = next[i]; }
     return counted ? 1 : 0;
+}
+
+/* hostio.h: the grid volume reader behind alvrl_set_medium_grid_file and the NumPy writer behind alvrl_film_write_npy.
+ * header[11] = {type, xres, yres, zres, channels, then the AABB's six floats as bit patterns}; density NULL: header only.
+ * Returns 0 or the ABI's error code, with the message in err. */
+int alvrl_host_read_vol(const char *path, int32_t *header, float *density, char *err, uint32_t errLen) {
+    try {
+        VolFile vf;
+        read_vol_file(path, vf, density == nullptr);
+        header[0] = vf.type; header[1] = vf.res[0]; header[2] = vf.res[1]; header[3] = vf.res[2]; header[4] = vf.channels;
+        memcpy(header + 5, vf.bmin, 12); memcpy(header + 8, vf.bmax, 12);
+        if (density) memcpy(density, vf.density.data(), vf.density.size() * sizeof(float));
+        return 0;
+    } catch (const HostIoError &e) {
+        if (err && errLen) { strncpy(err, e.what(), errLen - 1); err[errLen - 1] = 0; }
+        return e.code;
+    }
+}
+int alvrl_host_write_npy(const char *path, const float *data, uint32_t height, uint32_t width, uint32_t channels, char *err, uint32_t errLen) {
+    try { write_npy_f32(path, data, height, width, channels); return 0; }
+    catch (const HostIoError &e) {
+        if (err && errLen) { strncpy(err, e.what(), errLen - 1); err[errLen - 1] = 0; }
+        return e.code;
+    }
 }
 
 int alvrl_host_sfmt_ulongs(uint64_t seed, uint32_t cloneDepth, uint32_t skip, uint64_t *out, uint32_t n) {
