@@ -116,6 +116,18 @@ int  alvrl_set_math_mode(alvrl_handle h, int strict);
  * (include/mitsuba/render/triaccel.h:61-95, src/librender/skdtree.cpp:60-104) with a device BVH. */
 int alvrl_set_mesh(alvrl_handle h, const float *verts_xyz, uint32_t nverts,
                    const uint32_t *tris, uint32_t ntris, const uint32_t *tri_material);
+/* The reference's analytic shapes, handed over as triangles appended to the mesh (call after alvrl_set_mesh, or instead of
+ * it; alvrl_set_mesh starts over).  firstTriangle / triangleCount (may be NULL) tell where they went, e.g. for
+ * alvrl_set_area_emitter.
+ *   rectangle (src/shapes/rectangle.cpp:76-118,170-196): the square [-1, 1]^2 of the xy plane under toWorld (row-major 4x4,
+ *     affine), flipNormals as there; two triangles cover exactly the same surface, wound so that their geometric normal is
+ *     the shape's normal.
+ *   sphere (src/shapes/sphere.cpp:108-131,245-251): centre, radius, flipNormals (what the constructor folds toWorld into);
+ *     an approximation by 4 T (T - 2) triangles with the vertices on the sphere, T = thetaSteps polar steps (0 selects 64:
+ *     the surface is within 6.5e-4 radius of the sphere). */
+int alvrl_add_rectangle(alvrl_handle h, const float toWorld[16], int flipNormals, uint32_t material, uint32_t *firstTriangle);
+int alvrl_add_sphere(alvrl_handle h, const float center[3], float radius, int flipNormals, uint32_t thetaSteps, uint32_t material,
+                     uint32_t *firstTriangle, uint32_t *triangleCount);
 /* Diffuse reflectance + type bits per material (src/bsdfs/diffuse.cpp:110-118). */
 int alvrl_set_materials(alvrl_handle h, const float *albedo_rgb, const uint32_t *type_bits, uint32_t nmat);
 /* Optics of the delta BSDFs (ALVRL_BSDF_DIELECTRIC / ALVRL_BSDF_CONDUCTOR), 12 floats per material: dielectric eta =

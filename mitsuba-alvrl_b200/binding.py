@@ -152,6 +152,21 @@ class Integrator:
         v, t, m = _f32(verts), _u32(tris), _u32(tri_material)
         self._call("set_mesh", _p(v), C.c_uint32(len(v)), _p(t), C.c_uint32(len(t)), _p(m))
 
+    def add_rectangle(self, to_world, material, flip_normals=False):
+        """a `rectangle` shape (src/shapes/rectangle.cpp) as two triangles appended to the mesh -> index of the first one"""
+        m = _f32(to_world).reshape(16)
+        first = C.c_uint32()
+        self._call("add_rectangle", _p(m), C.c_int(int(flip_normals)), C.c_uint32(material), C.byref(first))
+        return first.value
+
+    def add_sphere(self, center, radius, material, flip_normals=False, theta_steps=0):
+        """a `sphere` shape (src/shapes/sphere.cpp) as triangles appended to the mesh -> (first triangle, count)"""
+        c = _f32(center)
+        first, count = C.c_uint32(), C.c_uint32()
+        self._call("add_sphere", _p(c), C.c_float(radius), C.c_int(int(flip_normals)), C.c_uint32(theta_steps), C.c_uint32(material),
+                   C.byref(first), C.byref(count))
+        return first.value, count.value
+
     def set_materials(self, albedo, bits):
         a, b = _f32(albedo), _u32(bits)
         self._call("set_materials", _p(a), _p(b), C.c_uint32(len(b)))

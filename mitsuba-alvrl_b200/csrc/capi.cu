@@ -16,6 +16,7 @@
 #include "occluders.h"
 #include "kernels.h"
 #include "hostio.h"
+#include "shapes.h"
 
 using namespace alvrl;
 
@@ -458,6 +459,37 @@ int alvrl_set_mesh(alvrl_handle c, const float *v, uint32_t nv, const uint32_t *
     for (size_t i = 0; i < 3 * (size_t) nt; i++) if (tris[i] >= nv) throw Error(ALVRL_ERR_ARG, "triangle index out of range");
     c->verts.assign(v, v + 3 * (size_t) nv); c->tris.assign(tris, tris + 3 * (size_t) nt); c->triMat.assign(mat, mat + nt);
     c->haveMesh = true; c->sceneDirty = true; c->havePrimary = false; c->haveSlices = false; invalidate_from_slices(c);
+    API_END
+}
+
+/* analytic shapes as triangles appended to the host copy of the mesh (shapes.h); the device sees them at the next ensure_scene */
+static void appended_triangles(alvrl_ctx *c, size_t trisBefore, uint32_t material, uint32_t *first, uint32_t *count) {
+    const size_t nt = c->tris.size() / 3;
+    c->triMat.resize(nt, material);
+    if (first) *first = (uint32_t) trisBefore;
+    if (count) *count = (uint32_t) (nt - trisBefore);
+    c->haveMesh = true; c->sceneDirty = true; c->havePrimary = false; c->haveSlices = false; invalidate_from_slices(c);
+}
+
+int alvrl_add_rectangle(alvrl_handle c, const float toWorld[16], int flipNormals, uint32_t material, uint32_t *firstTriangle) {
+    API_BEGIN
+    if (!toWorld) throw Error(ALVRL_ERR_ARG, "alvrl_add_rectangle: null transform");
+    for (int i = 0; i < 12; i++) if (!std::isfinite(toWorld[i])) throw Error(ALVRL_ERR_ARG, "alvrl_add_rectangle: 'toWorld' is not finite");
+    const size_t before = c->tris.size() / 3;
+    tessellate_rectangle(toWorld, flipNormals != 0, c->verts, c->tris);
+    appended_triangles(c, before, material, firstTriangle, nullptr);
+    API_END
+}
+
+int alvrl_add_sphere(alvrl_handle c, const float center[3], float radius, int flipNormals, uint32_t thetaSteps, uint32_t material,
+                     uint32_t *firstTriangle, uint32_t *triangleCount) {
+    API_BEGIN
+    if (!center || !std::isfinite(center[0]) || !std::isfinite(center[1]) || !std::isfinite(center[2]) || !std::isfinite(radius))
+        throw Error(ALVRL_ERR_ARG, "alvrl_add_sphere: centre and radius must be finite");
+    if (thetaSteps > 2048) throw Error(ALVRL_ERR_ARG, "alvrl_add_sphere: at most 2048 polar steps");
+    const size_t before = c->tris.size() / 3;
+    tessellate_sphere(center, radius, flipNormals != 0, thetaSteps ? thetaSteps : 64u, c->verts, c->tris);
+    appended_triangles(c, before, material, firstTriangle, triangleCount);
     API_END
 }
 

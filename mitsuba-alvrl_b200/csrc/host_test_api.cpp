@@ -11,6 +11,7 @@
 #include "occ_query.h"
 #include "sharding.h"
 #include "hostio.h"
+#include "shapes.h"
 #include <algorithm>
 #include <cstring>
 using namespace alvrl;
@@ -63,6 +64,20 @@ int alvrl_host_write_npy(const char *path, const float *data, uint32_t height, u
         if (err && errLen) { strncpy(err, e.what(), errLen - 1); err[errLen - 1] = 0; }
         return e.code;
     }
+}
+
+/* shapes.h: the tessellations behind alvrl_add_rectangle / alvrl_add_sphere.  verts / tris NULL: counts only. */
+int alvrl_host_tessellate(int shape, const float *toWorldOrCenter, float radius, int flipNormals, uint32_t thetaSteps,
+                          float *verts, uint32_t *nverts, uint32_t *tris, uint32_t *ntris) {
+    std::vector<float> v; std::vector<uint32_t> t;
+    try {
+        if (shape == 0) tessellate_rectangle(toWorldOrCenter, flipNormals != 0, v, t);
+        else tessellate_sphere(toWorldOrCenter, radius, flipNormals != 0, thetaSteps, v, t);
+    } catch (const std::exception &) { return -1; }
+    *nverts = (uint32_t) (v.size() / 3); *ntris = (uint32_t) (t.size() / 3);
+    if (verts) memcpy(verts, v.data(), v.size() * sizeof(float));
+    if (tris) memcpy(tris, t.data(), t.size() * sizeof(uint32_t));
+    return 0;
 }
 
 int alvrl_host_sfmt_ulongs(uint64_t seed, uint32_t cloneDepth, uint32_t skip, uint64_t *out, uint32_t n) {

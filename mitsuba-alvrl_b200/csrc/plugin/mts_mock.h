@@ -75,10 +75,17 @@ private:
 /* what preprocess() reads from `const Scene *` (triangle meshes with diffuse BSDFs, one medium, a perspective sensor) */
 /* bsdf: 0 diffuse (reflectance), 1 smooth dielectric (eta = intIOR / extIOR), 2 smooth conductor (eta, k rgb); the shape's
  * interior / exterior medium is the scene's medium or none (Shape::getInteriorMedium / getExteriorMedium) */
-struct TriMeshView {
-    const float *positions; uint32_t vertexCount; const uint32_t *indices; uint32_t triangleCount; float reflectance[3]; bool smooth;
+struct SurfaceView {            /* Shape::getBSDF / getInteriorMedium / getExteriorMedium of any shape */
+    float reflectance[3] = {0.5f, 0.5f, 0.5f}; bool smooth = true;
     int bsdf = 0; float eta[3] = {1, 1, 1}, k[3] = {0, 0, 0}, specularReflectance[3] = {1, 1, 1}, specularTransmittance[3] = {1, 1, 1};
     bool mediumTransition = false, interiorMedium = false, exteriorMedium = false;
+};
+struct TriMeshView : SurfaceView { const float *positions; uint32_t vertexCount; const uint32_t *indices; uint32_t triangleCount; };
+/* the analytic shapes of the reference's scenes: `rectangle` (src/shapes/rectangle.cpp: toWorld, flipNormals) and `sphere`
+ * (src/shapes/sphere.cpp: centre and radius after the constructor folded toWorld into them, flipNormals) */
+struct AnalyticShapeView : SurfaceView {
+    enum Type { ERectangle = 0, ESphere = 1 } type = ERectangle;
+    float toWorld[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}; float center[3] = {0, 0, 0}, radius = 1; bool flipNormals = false;
 };
 struct MediumView {
     bool homogeneous; float sigmaA[3], sigmaS[3]; float mediumSamplingWeight; int phaseType; float g;
@@ -89,10 +96,10 @@ struct SensorView { float sampleToCamera[16], cameraToWorld[16]; uint32_t width,
  * filter's default radius / stddev) and where the developed image goes */
 class Film { public: virtual ~Film() {} int rfilter = 0; float rfilterParam = 0.0f; virtual void setImage(const float *rgb, uint32_t width, uint32_t height) = 0; };
 /* an area emitter attached to a triangle mesh (Scene::getEmitters, src/emitters/area.cpp): mesh index + radiance */
-struct EmitterView { uint32_t meshIndex; float radiance[3]; };
+struct EmitterView { uint32_t meshIndex; float radiance[3]; bool onAnalyticShape = false; /* meshIndex then counts Scene::shapes */ };
 class Scene {
 public:
-    std::vector<TriMeshView> meshes; std::vector<MediumView> media; std::vector<EmitterView> emitters; SensorView sensor; Film *film = nullptr;
+    std::vector<TriMeshView> meshes; std::vector<AnalyticShapeView> shapes; std::vector<MediumView> media; std::vector<EmitterView> emitters; SensorView sensor; Film *film = nullptr;
 };
 
 class Integrator {

@@ -65,6 +65,9 @@ public:
         /* device selection has no XML equivalent in the reference */
         m_device = props.getInteger("cudaDevice", 0);
         m_p.seed = (uint64_t) props.getInteger("seed", 0);
+        /* polar steps of the triangles a `sphere` shape is handed over as (alvrl_add_sphere; 0 = the library's default) */
+        m_sphereTessellation = props.getInteger("sphereTessellation", 0);
+        if (m_sphereTessellation != 0 && m_sphereTessellation < 3) mts::LogError("'sphereTessellation' must be 0 (default) or at least 3");
     }
     /* the unserializing constructor and serialize(): what travels to a network node (vrlIntegrator.cpp:210-235 after the base
      * classes, src/librender/integrator.cpp:56-63, 307-321, 351-360) -- the reference's own field order; like the reference, the
@@ -102,7 +105,8 @@ public:
             /* the VRLs are traced in every prepass (279-280): the device tracer walks one medium and starts on one area emitter */
             if (scene->media.size() != 1) mts::LogError("the device VRL tracer needs exactly one medium in the scene");
             if (scene->emitters.size() != 1) mts::LogError("the device VRL tracer needs exactly one area emitter (attached to a triangle mesh) in the scene");
-            if (scene->emitters[0].meshIndex >= scene->meshes.size()) mts::LogError("the emitter's shape is not a mesh of the scene");
+            if (scene->emitters[0].meshIndex >= (scene->emitters[0].onAnalyticShape ? scene->shapes.size() : scene->meshes.size()))
+                mts::LogError("the emitter's shape is not a mesh of the scene");
         }
         if (m_maxPasses < 0) mts::LogError("maxPasses < 0 (render until cancelled) is not supported by the device path: give a pass count");
         alvrl_params hp = m_p; hp.maxPasses = 1;                              /* the passes are driven from render() below */
@@ -111,26 +115,38 @@ public:
         std::vector<float> verts, albedo, optics; std::vector<uint32_t> tris, mat, bits;
         bool anyDelta = false;
         std::vector<uint32_t> firstTri;
+        /* BSDF type bits (bsdf.h:230-284) and the media on the two sides of the shape (shape.h:427-433): what the specular
+         * chains of LiInternal read (vrlIntegrator.cpp:445-511).  One material per shape. */
+        auto material = [&](const mts::SurfaceView &sv) {
+            albedo.insert(albedo.end(), sv.reflectance, sv.reflectance + 3);
+            uint32_t b = sv.smooth ? ALVRL_BSDF_SMOOTH : 0u;
+            if (sv.bsdf == 1) b = ALVRL_BSDF_DIELECTRIC; else if (sv.bsdf == 2) b = ALVRL_BSDF_CONDUCTOR;
+            if (sv.mediumTransition) b |= ALVRL_MAT_TRANSITION | (sv.interiorMedium ? ALVRL_MAT_INTERIOR_MEDIUM : 0u) | (sv.exteriorMedium ? ALVRL_MAT_EXTERIOR_MEDIUM : 0u);
+            anyDelta = anyDelta || (b & ALVRL_BSDF_DELTA);
+            bits.push_back(b);
+            const float o[12] = {sv.eta[0], sv.eta[1], sv.eta[2], sv.k[0], sv.k[1], sv.k[2], sv.specularReflectance[0], sv.specularReflectance[1],
+                                 sv.specularReflectance[2], sv.specularTransmittance[0], sv.specularTransmittance[1], sv.specularTransmittance[2]};
+            optics.insert(optics.end(), o, o + 12);
+            return (uint32_t) (bits.size() - 1);
+        };
         for (size_t m = 0; m < scene->meshes.size(); m++) {
             const mts::TriMeshView &tm = scene->meshes[m];
             const uint32_t base = (uint32_t) (verts.size() / 3);
             firstTri.push_back((uint32_t) (tris.size() / 3));
             verts.insert(verts.end(), tm.positions, tm.positions + 3 * (size_t) tm.vertexCount);
             for (uint32_t i = 0; i < 3 * tm.triangleCount; i++) tris.push_back(base + tm.indices[i]);
-            mat.insert(mat.end(), tm.triangleCount, (uint32_t) m);
-            albedo.insert(albedo.end(), tm.reflectance, tm.reflectance + 3);
-            /* BSDF type bits (bsdf.h:230-284) and the media on the two sides of the shape (shape.h:427-433): what the specular
-             * chains of LiInternal read (vrlIntegrator.cpp:445-511) */
-            uint32_t b = tm.smooth ? ALVRL_BSDF_SMOOTH : 0u;
-            if (tm.bsdf == 1) b = ALVRL_BSDF_DIELECTRIC; else if (tm.bsdf == 2) b = ALVRL_BSDF_CONDUCTOR;
-            if (tm.mediumTransition) b |= ALVRL_MAT_TRANSITION | (tm.interiorMedium ? ALVRL_MAT_INTERIOR_MEDIUM : 0u) | (tm.exteriorMedium ? ALVRL_MAT_EXTERIOR_MEDIUM : 0u);
-            anyDelta = anyDelta || (b & ALVRL_BSDF_DELTA);
-            bits.push_back(b);
-            const float o[12] = {tm.eta[0], tm.eta[1], tm.eta[2], tm.k[0], tm.k[1], tm.k[2], tm.specularReflectance[0], tm.specularReflectance[1],
-                                 tm.specularReflectance[2], tm.specularTransmittance[0], tm.specularTransmittance[1], tm.specularTransmittance[2]};
-            optics.insert(optics.end(), o, o + 12);
+            mat.insert(mat.end(), tm.triangleCount, material(tm));
         }
-        chk(alvrl_set_mesh(m_h, verts.data(), (uint32_t) (verts.size() / 3), tris.data(), (uint32_t) (tris.size() / 3), mat.data()));
+        if (!tris.empty()) chk(alvrl_set_mesh(m_h, verts.data(), (uint32_t) (verts.size() / 3), tris.data(), (uint32_t) (tris.size() / 3), mat.data()));
+        /* analytic shapes go in as triangles (alvrl_add_rectangle: the same surface; alvrl_add_sphere: vertices on the sphere) */
+        std::vector<uint32_t> shapeFirstTri, shapeTriCount;
+        for (const mts::AnalyticShapeView &sh : scene->shapes) {
+            uint32_t first = 0, count = 2;
+            const uint32_t id = material(sh);
+            if (sh.type == mts::AnalyticShapeView::ERectangle) chk(alvrl_add_rectangle(m_h, sh.toWorld, sh.flipNormals, id, &first));
+            else chk(alvrl_add_sphere(m_h, sh.center, sh.radius, sh.flipNormals, (uint32_t) m_sphereTessellation, id, &first, &count));
+            shapeFirstTri.push_back(first); shapeTriCount.push_back(count);
+        }
         chk(alvrl_set_materials(m_h, albedo.data(), bits.data(), (uint32_t) bits.size()));
         if (anyDelta) chk(alvrl_set_material_optics(m_h, optics.data(), (uint32_t) bits.size()));
         chk(alvrl_set_extra_bounds(m_h, scene->sensor.position, 1));                                    /* scene.cpp:387-413 */
@@ -142,8 +158,9 @@ public:
         if (!m_vrlFile.empty()) chk(alvrl_load_vrl_file(m_h, m_vrlFile.c_str()));                       /* 249-251 */
         else {                                                                                          /* the emitter's shape: Scene::getEmitters */
             const mts::EmitterView &em = scene->emitters[0];
-            std::vector<uint32_t> emTris(scene->meshes[em.meshIndex].triangleCount);
-            for (uint32_t i = 0; i < (uint32_t) emTris.size(); i++) emTris[i] = firstTri[em.meshIndex] + i;
+            const uint32_t emFirst = em.onAnalyticShape ? shapeFirstTri[em.meshIndex] : firstTri[em.meshIndex];
+            std::vector<uint32_t> emTris(em.onAnalyticShape ? shapeTriCount[em.meshIndex] : scene->meshes[em.meshIndex].triangleCount);
+            for (uint32_t i = 0; i < (uint32_t) emTris.size(); i++) emTris[i] = emFirst + i;
             chk(alvrl_set_area_emitter(m_h, emTris.data(), (uint32_t) emTris.size(), em.radiance));
         }
         if (m_p.globalCluster || m_p.localRefinement) chk(alvrl_build_slices(m_h));                     /* 254-265 */
@@ -192,6 +209,7 @@ public:
 private:
     static void chk(int rc) { if (rc != ALVRL_OK) mts::LogError(alvrl_last_error()); }
     alvrl_params m_p; std::string m_vrlFile; int m_device = 0, m_maxPasses = 1, m_pass = 0; alvrl_handle m_h = nullptr;
+    int m_sphereTessellation = 0;
     int m_numPasses = 1, m_maxDepth = -1; bool m_strictNormals = false, m_hideEmitters = false, m_dumpPasses = false;
     volatile bool m_cancelled = false;
 };
@@ -248,6 +266,29 @@ void alvrl_plugin_scene_add_mesh(void *s, const float *positions, uint32_t nv, c
     mts::TriMeshView m; m.positions = positions; m.vertexCount = nv; m.indices = indices; m.triangleCount = nt;
     m.reflectance[0] = reflectance[0]; m.reflectance[1] = reflectance[1]; m.reflectance[2] = reflectance[2]; m.smooth = smooth != 0;
     static_cast<mts::Scene *>(s)->meshes.push_back(m);
+}
+/* analytic shapes (mts::AnalyticShapeView): a `rectangle` under toWorld (row-major 4x4), a `sphere` by centre and radius */
+void alvrl_plugin_scene_add_rectangle(void *s, const float *toWorld, int flipNormals, const float *reflectance) {
+    mts::AnalyticShapeView v; v.type = mts::AnalyticShapeView::ERectangle; memcpy(v.toWorld, toWorld, 16 * sizeof(float)); v.flipNormals = flipNormals != 0;
+    memcpy(v.reflectance, reflectance, 3 * sizeof(float));
+    static_cast<mts::Scene *>(s)->shapes.push_back(v);
+}
+void alvrl_plugin_scene_add_sphere(void *s, const float *center, float radius, int flipNormals, const float *reflectance) {
+    mts::AnalyticShapeView v; v.type = mts::AnalyticShapeView::ESphere; memcpy(v.center, center, 3 * sizeof(float)); v.radius = radius; v.flipNormals = flipNormals != 0;
+    memcpy(v.reflectance, reflectance, 3 * sizeof(float));
+    static_cast<mts::Scene *>(s)->shapes.push_back(v);
+}
+/* the BSDF and media of the analytic shape added last (as alvrl_plugin_scene_set_mesh_bsdf) */
+void alvrl_plugin_scene_set_shape_bsdf(void *s, int bsdf, const float *eta, const float *k, int mediumTransition, int interiorMedium, int exteriorMedium) {
+    mts::AnalyticShapeView &m = static_cast<mts::Scene *>(s)->shapes.back();
+    m.bsdf = bsdf; m.smooth = bsdf == 0;
+    for (int i = 0; i < 3; i++) { m.eta[i] = eta ? eta[i] : 1.0f; m.k[i] = k ? k[i] : 0.0f; }
+    m.mediumTransition = mediumTransition != 0; m.interiorMedium = interiorMedium != 0; m.exteriorMedium = exteriorMedium != 0;
+}
+/* an area emitter on the analytic shape with this index (in the order they were added) */
+void alvrl_plugin_scene_add_area_emitter_on_shape(void *s, uint32_t shapeIndex, const float *radiance) {
+    mts::EmitterView e; e.meshIndex = shapeIndex; e.onAnalyticShape = true; e.radiance[0] = radiance[0]; e.radiance[1] = radiance[1]; e.radiance[2] = radiance[2];
+    static_cast<mts::Scene *>(s)->emitters.push_back(e);
 }
 void alvrl_plugin_scene_add_medium_homogeneous(void *s, const float *sigmaA, const float *sigmaS, float weight, int phaseType, float g) {
     mts::MediumView m; memset(&m, 0, sizeof(m));

@@ -8,6 +8,7 @@
  * sampleSliceMapping / buildClusters (Preprocessor.cpp:133-283,1130-1193,1502-1525).
  */
 #include "oracle_prep.hpp"
+#include "../mitsuba-alvrl_b200/csrc/shapes.h"   /* the hand-over triangles of analytic shapes (see orc_add_rectangle) */
 #include <thread>
 #include <set>
 #include <memory>
@@ -236,6 +237,36 @@ int orc_set_mesh(void *h, const float *v, uint32_t nv, const uint32_t *tris, uin
     c->haveMesh = true; c->havePrimary = false;
     return ALVRL_OK;
 }
+/* alvrl_add_rectangle / alvrl_add_sphere: the triangles an analytic shape is handed over as.  NOT a restatement -- there is
+ * nothing in the reference to restate (it intersects the analytic shapes): both sides append the triangles of csrc/shapes.h,
+ * and tests/test_shapes_cpu.py checks those against the shapes' definitions (src/shapes/rectangle.cpp, src/shapes/sphere.cpp)
+ * and, through this oracle's ray caster, against the analytic intersections. */
+static int appendShape(Ctx *c, const std::vector<float> &v, const std::vector<uint32_t> &t, uint32_t material, uint32_t *first, uint32_t *count) {
+    const uint32_t base = (uint32_t) c->scene.verts.size(), before = (uint32_t) c->scene.triMat.size();
+    for (size_t i = 0; i < v.size(); i += 3) c->scene.verts.push_back(V3(v[i], v[i + 1], v[i + 2]));
+    for (uint32_t i : t) c->scene.tris.push_back(base + i);
+    c->scene.triMat.resize(c->scene.tris.size() / 3, material);
+    if (first) *first = before;
+    if (count) *count = (uint32_t) (t.size() / 3);
+    c->scene.finalize();
+    c->haveMesh = true; c->havePrimary = false;
+    return ALVRL_OK;
+}
+int orc_add_rectangle(void *h, const float toWorld[16], int flipNormals, uint32_t material, uint32_t *firstTriangle) {
+    ORC_TRY
+    std::vector<float> v; std::vector<uint32_t> t;
+    alvrl::tessellate_rectangle(toWorld, flipNormals != 0, v, t);
+    return appendShape((Ctx *) h, v, t, material, firstTriangle, nullptr);
+    ORC_CATCH
+}
+int orc_add_sphere(void *h, const float center[3], float radius, int flipNormals, uint32_t thetaSteps, uint32_t material,
+                   uint32_t *firstTriangle, uint32_t *triangleCount) {
+    ORC_TRY
+    std::vector<float> v; std::vector<uint32_t> t;
+    alvrl::tessellate_sphere(center, radius, flipNormals != 0, thetaSteps ? thetaSteps : 64u, v, t);
+    return appendShape((Ctx *) h, v, t, material, firstTriangle, triangleCount);
+    ORC_CATCH
+}
 int orc_set_materials(void *h, const float *albedo, const uint32_t *bits, uint32_t nm) {
     Ctx *c = (Ctx *) h;
     c->scene.albedo.resize(nm); c->scene.matBits.assign(bits, bits + nm);
@@ -272,6 +303,41 @@ int orc_set_medium_grid(void *h, const float *density, const int32_t res[3], con
     c->medium.phaseType = phase; c->medium.g = g;
     c->haveMedium = true;
     return ALVRL_OK;
+}
+/* GridDataSource::loadFromFile (src/volume/gridvolume.cpp:217-287) in front of orc_set_medium_grid: "VOL", version 3, type,
+ * resolution, channels, the AABB (unless `min` / `max` were given, 112-117, 272-280), the voxels from float 12 on (285).  The
+ * density is looked up with lookupFloat (337-389): EFloat32 voxels as they are, EUInt8 voxels through m_densityMap
+ * (212-215) -- resolved here once per voxel instead of once per lookup, the eight corner values are the same floats. */
+int orc_set_medium_grid_file(void *h, const char *path, const float *mn, const float *mx, float scale,
+                             const float albedo[3], const float sBase[3], int32_t phase, float g) {
+    FILE *f = path ? fopen(path, "rb") : nullptr;
+    if (!f) return seterr(ALVRL_ERR_IO, "cannot open volume data file");
+    std::vector<unsigned char> bytes;
+    unsigned char buf[65536]; size_t got;
+    while ((got = fread(buf, 1, sizeof(buf), f)) > 0) bytes.insert(bytes.end(), buf, buf + got);
+    fclose(f);
+    if (bytes.size() < 48) return seterr(ALVRL_ERR_IO, "Encountered an invalid volume data file (truncated header)");
+    if (bytes[0] != 'V' || bytes[1] != 'O' || bytes[2] != 'L') return seterr(ALVRL_ERR_ARG, "Encountered an invalid volume data file (incorrect header identifier)");
+    if (bytes[3] != 3) return seterr(ALVRL_ERR_ARG, "Encountered an invalid volume data file (incorrect file version)");
+    int32_t head[5]; memcpy(head, &bytes[4], 20);                       /* little-endian host assumed (test infrastructure) */
+    float box[6]; memcpy(box, &bytes[24], 24);
+    const int32_t type = head[0], res[3] = {head[1], head[2], head[3]}, channels = head[4];
+    if (type == 2) return seterr(ALVRL_ERR_UNSUPPORTED, "Error: float16 volumes are not yet supported!");
+    if (type != 1 && type != 3) return seterr(type == 4 ? ALVRL_ERR_UNSUPPORTED : ALVRL_ERR_ARG, "Encountered a volume data file of unknown type");
+    if (channels != 1) return seterr(channels == 3 ? ALVRL_ERR_UNSUPPORTED : ALVRL_ERR_ARG, "only one-channel density volumes");
+    if (res[0] < 1 || res[1] < 1 || res[2] < 1) return seterr(ALVRL_ERR_ARG, "Encountered an invalid volume data file (resolution out of range)");
+    const size_t n = (size_t) res[0] * res[1] * res[2];
+    if (bytes.size() < 48 + n * (type == 1 ? 4 : 1)) return seterr(ALVRL_ERR_IO, "Encountered an invalid volume data file (fewer voxels than the header announces)");
+    std::vector<float> density(n);
+    if (type == 1) memcpy(density.data(), &bytes[48], 4 * n);
+    else {
+        Float densityMap[256];
+        for (int i = 0; i < 255; i++) densityMap[i] = i / 255.0f;
+        densityMap[255] = 1.0f;
+        for (size_t i = 0; i < n; i++) density[i] = densityMap[bytes[48 + i]];
+    }
+    if ((mn == nullptr) != (mx == nullptr)) return seterr(ALVRL_ERR_ARG, "give both bbox_min and bbox_max, or neither");
+    return orc_set_medium_grid(h, density.data(), res, mn ? mn : box, mx ? mx : box + 3, scale, albedo, sBase, phase, g);
 }
 int orc_set_camera(void *h, const float s2c[16], const float c2w[16], uint32_t W, uint32_t H, float nearClip, float farClip) {
     Ctx *c = (Ctx *) h;

@@ -119,3 +119,30 @@ def test_npy_film_output_loads_in_numpy_and_has_the_cnpy_header_layout(host_lib,
     assert raw[10:10 + hlen].decode().rstrip() == "{'descr': '<f4', 'fortran_order': False, 'shape': " + shp + ", }"
     assert len(raw) == 10 + hlen + 4 * H * W * ch
     assert host_lib.alvrl_host_write_npy(str(tmp_path / "no" / "dir.npy").encode(), _p(img), C.c_uint32(H), C.c_uint32(W), C.c_uint32(ch), err, C.c_uint32(256)) == -4
+
+
+@pytest.mark.parametrize("uint8", [False, True], ids=["float32", "uint8"])
+def test_library_reader_agrees_with_the_oracles_restatement_of_loadFromFile(pkg, orc, host_lib, tmp_path, uint8):
+    """two independent readers: the library's (csrc/hostio.h, through libalvrl_host.so) and the oracle's restatement of
+    GridDataSource::loadFromFile + the uint8 density map (oracle_capi.cpp: orc_set_medium_grid_file).  A medium set from the
+    file on the oracle == a medium set from the array the library's reader returns, on 2 000 transmittance queries."""
+    from conftest import small_case
+    scene, vrls, params = small_case(pkg, "C3", 16, 16, 16, grid=20)
+    m = scene["medium"]
+    path = tmp_path / "density.vol"
+    pkg.volfile.write_vol(path, m["density"], (0.05, 0, 0.1), (0.9, 1, 1), pkg.volfile.VOL_UINT8 if uint8 else pkg.volfile.VOL_FLOAT32)
+    rc, hdr, dens = _read(host_lib, path)
+    assert rc == 0
+    a = orc.Oracle(**params); a.set_scene(scene)
+    a.set_medium_grid_file(str(path), m["scale"], m["albedo"], m["sigmaS_base"])
+    b = orc.Oracle(**params); b.set_scene(scene)
+    b.set_medium_grid(dens, hdr["bmin"], hdr["bmax"], m["scale"], m["albedo"], m["sigmaS_base"])
+    rng = np.random.default_rng(8)
+    p1, p2 = rng.uniform(0.02, 0.98, (2000, 3)).astype(np.float32), rng.uniform(0.02, 0.98, (2000, 3)).astype(np.float32)
+    s = np.zeros(2000, np.int32)
+    ta, tb = a.eval_transmittance(p1, s, p2), b.eval_transmittance(p1, s, p2)
+    assert np.array_equal(ta, tb) and 0 < ta[ta > 0].min() < ta.max() <= 1 and (ta > 0).mean() > 0.5      # (zeros: occluded segments)
+    if not uint8:
+        c = orc.Oracle(**params); c.set_scene(scene)
+        c.set_medium_grid(m["density"], (0.05, 0, 0.1), (0.9, 1, 1), m["scale"], m["albedo"], m["sigmaS_base"])
+        assert np.array_equal(ta, c.eval_transmittance(p1, s, p2))

@@ -122,6 +122,21 @@ def test_preprocess_checks_the_scene_before_it_touches_the_device(plugin):
     rc, err = frame(medium, vrlFile="/tmp/some.vrl", maxPasses=-1)
     assert rc != 0 and "maxPasses" in err
 
+    def medium_and_emitter_on_a_missing_shape(sc):       # analytic shapes (mts::AnalyticShapeView) are counted separately
+        medium(sc)
+        plugin.alvrl_plugin_scene_add_area_emitter_on_shape(sc, C.c_uint32(0), one.ctypes.data_as(fp))
+    rc, err = frame(medium_and_emitter_on_a_missing_shape)
+    assert rc != 0 and "not a mesh" in err
+
+
+def test_sphere_tessellation_parameter(plugin, pkg):
+    """`sphereTessellation` (no equivalent in the reference, like cudaDevice): polar steps of the triangles a `sphere` shape is
+    handed to the path as; 0 = the library's default"""
+    rc, err, params, unq = _create(plugin, pkg, sphereTessellation=32)
+    assert rc == 0 and unq == 0
+    rc, err, _, _ = _create(plugin, pkg, sphereTessellation=2)
+    assert rc != 0 and "sphereTessellation" in err
+
 
 def test_inherited_parameters_and_their_errors(plugin, pkg):
     """MonteCarloIntegrator's constructor checks (src/librender/integrator.cpp:300-305); rrDepth reaches the parameter block
