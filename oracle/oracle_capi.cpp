@@ -1000,6 +1000,43 @@ inline void coordinateSystem(const V3 &a, V3 &b, V3 &c) {                    // 
     else { Float invLen = 1.0f / std::sqrt(a.y * a.y + a.z * a.z); c = V3(0.0f, a.z * invLen, -a.y * invLen); }
     b = cross(c, a);
 }
+/* BSDF::sample(bRec, pdf, sample) of the three surface models of the path, in the local frame (wi, wo with z along the shading
+ * normal): smooth dielectric (dielectric.cpp:281-364; mode ERadiance scales transmitted radiance by the squared relative index,
+ * EImportance does not, 322-326), smooth conductor (conductor.cpp:254-283), diffuse (diffuse.cpp:129-148).  Returns the weight
+ * f * cos / pdf (zero: no sample); pdf is the discrete probability for the delta components, the solid-angle density otherwise. */
+inline Spec sampleSurfaceBsdf(uint32_t bits, const Spec &albedo, const Optics *opt, const V3 &wi, Float bsx, Float bsy, bool radianceMode,
+                              V3 &woL, Float &bEta, Float &bsdfPdf, bool &delta) {
+    Spec bsdfWeight(0.0f);
+    bEta = 1.0f; bsdfPdf = 0; delta = false; woL = V3(0.0f);
+    if (bits & ALVRL_BSDF_DIELECTRIC) {
+        const Optics &o = *opt;
+        const Float e = o.v[0], invE = 1 / e;
+        Float cosThetaT;
+        Float F = fresnelDielectricExt(wi.z, cosThetaT, e);
+        delta = true;
+        if (bsx <= F) { woL = V3(-wi.x, -wi.y, wi.z); bEta = 1.0f; bsdfPdf = F; bsdfWeight = Spec(o.v[6], o.v[7], o.v[8]); }
+        else {
+            Float scale = -(cosThetaT < 0 ? invE : e);
+            woL = V3(scale * wi.x, scale * wi.y, cosThetaT);
+            bEta = cosThetaT < 0 ? e : invE;
+            bsdfPdf = 1 - F;
+            Float factor = radianceMode ? (cosThetaT < 0 ? invE : e) : 1.0f;
+            bsdfWeight = Spec(o.v[9], o.v[10], o.v[11]) * (factor * factor);
+        }
+    } else if (bits & ALVRL_BSDF_CONDUCTOR) {
+        const Optics &o = *opt;
+        if (wi.z > 0) {
+            delta = true;
+            woL = V3(-wi.x, -wi.y, wi.z); bsdfPdf = 1;
+            bsdfWeight = Spec(o.v[6], o.v[7], o.v[8]) * Spec(fresnelConductorExact(wi.z, o.v[0], o.v[3]), fresnelConductorExact(wi.z, o.v[1], o.v[4]), fresnelConductorExact(wi.z, o.v[2], o.v[5]));
+        }
+    } else if ((bits & ALVRL_BSDF_SMOOTH) && wi.z > 0) {
+        woL = squareToCosineHemisphere(bsx, bsy);
+        bsdfPdf = INV_PI * woL.z;
+        bsdfWeight = albedo;
+    }
+    return bsdfWeight;
+}
 inline V3 frameToWorld(const V3 &n, const V3 &v) { V3 s, t; coordinateSystem(n, s, t); return s * v.x + t * v.y + n * v.z; }   // Frame(n).toWorld
 struct TracedVrl { Spec power; V3 start, end; };
 
@@ -1118,30 +1155,9 @@ void traceOneParticle(Ctx *c, Sampler *smp, std::vector<TracedVrl> &out) {
                 const HitFrame fr = c->scene.hitFrame(its);
                 const V3 wi = fr.toLocal(-ray.d);
                 Float bsx = smp->next1D(), bsy = smp->next1D();
-                V3 woL; Float bEta = 1.0f; Spec bsdfWeight(0.0f);
-                if (bits & ALVRL_BSDF_DIELECTRIC) {                                                     // dielectric.cpp:335-364, EImportance
-                    const Optics &o = c->scene.optics[its.material];
-                    const Float e = o.v[0], invE = 1 / e;
-                    Float cosThetaT;
-                    Float F = fresnelDielectricExt(wi.z, cosThetaT, e);
-                    if (bsx <= F) { woL = V3(-wi.x, -wi.y, wi.z); bEta = 1.0f; bsdfWeight = Spec(o.v[6], o.v[7], o.v[8]); }
-                    else {
-                        Float scale = -(cosThetaT < 0 ? invE : e);
-                        woL = V3(scale * wi.x, scale * wi.y, cosThetaT);
-                        bEta = cosThetaT < 0 ? e : invE;
-                        Float factor = 1.0f;
-                        bsdfWeight = Spec(o.v[9], o.v[10], o.v[11]) * (factor * factor);
-                    }
-                } else if (bits & ALVRL_BSDF_CONDUCTOR) {                                               // conductor.cpp:254-268
-                    const Optics &o = c->scene.optics[its.material];
-                    if (wi.z > 0) {
-                        woL = V3(-wi.x, -wi.y, wi.z);
-                        bsdfWeight = Spec(o.v[6], o.v[7], o.v[8]) * Spec(fresnelConductorExact(wi.z, o.v[0], o.v[3]), fresnelConductorExact(wi.z, o.v[1], o.v[4]), fresnelConductorExact(wi.z, o.v[2], o.v[5]));
-                    }
-                } else if ((bits & ALVRL_BSDF_SMOOTH) && wi.z > 0) {                                    // diffuse.cpp:129-138
-                    woL = squareToCosineHemisphere(bsx, bsy);
-                    bsdfWeight = c->scene.albedo[its.material];
-                }
+                V3 woL; Float bEta, bPdf; bool bDelta;                                                  // EImportance: particles
+                const Spec bsdfWeight = sampleSurfaceBsdf(bits, c->scene.albedo[its.material], (bits & ALVRL_BSDF_DELTA) ? &c->scene.optics[its.material] : nullptr,
+                                                          wi, bsx, bsy, false, woL, bEta, bPdf, bDelta);
                 if (bsdfWeight.isZero()) { endCurrent(its.p); break; }
                 V3 wiW = -ray.d, woW = fr.toWorld(woL);
                 Float wiDotGeoN = dot(its.n, wiW), woDotGeoN = dot(its.n, woW);
@@ -1408,34 +1424,9 @@ Spec volpathLiOriginal(Ctx *c, const VolpathCfg &cfg, Sampler *smp, const Ray &r
             }
             /* BSDF sampling: sample(bRec, pdf, nextSample2D()), mode = ERadiance */
             Float bsx = smp->next1D(), bsy = smp->next1D();
-            V3 woL; Float bEta = 1.0f, bsdfPdf = 0; Spec bsdfWeight(0.0f); bool delta = false;
-            if (bits & ALVRL_BSDF_DIELECTRIC) {                                                                         // dielectric.cpp:281-332
-                const Optics &o = c->scene.optics[here.material];
-                const Float e = o.v[0], invE = 1 / e;
-                Float cosThetaT;
-                Float F = fresnelDielectricExt(wi.z, cosThetaT, e);
-                delta = true;
-                if (bsx <= F) { woL = V3(-wi.x, -wi.y, wi.z); bEta = 1.0f; bsdfPdf = F; bsdfWeight = Spec(o.v[6], o.v[7], o.v[8]); }
-                else {
-                    Float scale = -(cosThetaT < 0 ? invE : e);
-                    woL = V3(scale * wi.x, scale * wi.y, cosThetaT);
-                    bEta = cosThetaT < 0 ? e : invE;
-                    bsdfPdf = 1 - F;
-                    Float factor = cosThetaT < 0 ? invE : e;
-                    bsdfWeight = Spec(o.v[9], o.v[10], o.v[11]) * (factor * factor);
-                }
-            } else if (bits & ALVRL_BSDF_CONDUCTOR) {                                                                   // conductor.cpp:268-283
-                const Optics &o = c->scene.optics[here.material];
-                if (wi.z > 0) {
-                    delta = true;
-                    woL = V3(-wi.x, -wi.y, wi.z); bsdfPdf = 1;
-                    bsdfWeight = Spec(o.v[6], o.v[7], o.v[8]) * Spec(fresnelConductorExact(wi.z, o.v[0], o.v[3]), fresnelConductorExact(wi.z, o.v[1], o.v[4]), fresnelConductorExact(wi.z, o.v[2], o.v[5]));
-                }
-            } else if ((bits & ALVRL_BSDF_SMOOTH) && wi.z > 0) {                                                        // diffuse.cpp:139-148
-                woL = squareToCosineHemisphere(bsx, bsy);
-                bsdfPdf = INV_PI * woL.z;
-                bsdfWeight = c->scene.albedo[here.material];
-            }
+            V3 woL; Float bEta, bsdfPdf; bool delta;
+            const Spec bsdfWeight = sampleSurfaceBsdf(bits, c->scene.albedo[here.material], (bits & ALVRL_BSDF_DELTA) ? &c->scene.optics[here.material] : nullptr,
+                                                      wi, bsx, bsy, true, woL, bEta, bsdfPdf, delta);
             if (bsdfWeight.isZero()) break;
             const V3 wo = fr.toWorld(woL);
             Float woDotGeoN = dot(here.n, wo);
@@ -1519,6 +1510,20 @@ int orc_test_phase_sample(int32_t phaseType, float g, const float wi[3], const f
 int orc_test_phase_eval(int32_t phaseType, float g, const float wi[3], const float *wo, uint32_t n, float *val) {
     Medium med; med.phaseType = phaseType; med.g = g;
     for (uint32_t i = 0; i < n; i++) val[i] = med.phaseEval(V3(wi[0], wi[1], wi[2]), V3(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]));
+    return ALVRL_OK;
+}
+/* BSDF::sample of one surface model in the local frame (test_chisquare.cpp:398-506): bits = ALVRL_BSDF_* of the material,
+ * optics12 as alvrl_set_material_optics; delta[i] = 1 for a discrete component (pdf = its probability) */
+int orc_test_bsdf_sample(uint32_t bits, const float albedo[3], const float *optics12, const float wi[3], const float *u, uint32_t n,
+                         int radianceMode, float *wo, float *pdf, float *weight, uint8_t *delta) {
+    Optics o; if (optics12) memcpy(o.v, optics12, 12 * sizeof(float));
+    for (uint32_t i = 0; i < n; i++) {
+        V3 w; Float eta, p; bool d;
+        Spec wt = sampleSurfaceBsdf(bits, Spec(albedo[0], albedo[1], albedo[2]), optics12 ? &o : nullptr, V3(wi[0], wi[1], wi[2]), u[2 * i], u[2 * i + 1],
+                                    radianceMode != 0, w, eta, p, d);
+        wo[3 * i] = w.x; wo[3 * i + 1] = w.y; wo[3 * i + 2] = w.z; pdf[i] = p; delta[i] = d ? 1 : 0;
+        weight[3 * i] = wt[0]; weight[3 * i + 1] = wt[1]; weight[3 * i + 2] = wt[2];
+    }
     return ALVRL_OK;
 }
 /* emitter->sampleDirect from a reference point in the volume (refN = 0): direction, solid-angle pdf, radiance / pdf */

@@ -228,3 +228,133 @@ def test_area_emitter_direct_sampling_matches_its_density(pkg, orc, ref):
     assert abs(integral - 1) < 2e-3, integral
     ok, pval, chsq, df = cs.run_test()
     assert ok, f"chi-square rejects: p={pval:.3e} chi2={chsq:.1f} df={df}"
+
+
+# ---- test01_BSDF ---------------------------------------------------------------------------------------------------------
+BSDF_SMOOTH, BSDF_DIELECTRIC, BSDF_CONDUCTOR = 1, 2, 4        # include/alvrl.h: ALVRL_BSDF_*
+
+
+def _bsdf_sample(lib, bits, albedo, optics, wi, u, radiance=False):
+    n = len(u)
+    wo, pdf, wt, delta = np.zeros((n, 3), np.float32), np.zeros(n, np.float32), np.zeros((n, 3), np.float32), np.zeros(n, np.uint8)
+    al, w = np.ascontiguousarray(albedo, np.float32), np.ascontiguousarray(wi, np.float32)
+    op = np.ascontiguousarray(optics, np.float32) if optics is not None else None
+    assert lib.orc_test_bsdf_sample(C.c_uint32(bits), _p(al), _p(op) if op is not None else None, _p(w), _p(u), C.c_uint32(n), int(radiance),
+                                    _p(wo), _p(pdf), _p(wt), _p(delta)) == 0
+    return wo, pdf, wt, delta
+
+
+def test_bsdf_flag_values_match_the_header():
+    import re
+    from conftest import ROOT
+    import os
+    txt = open(os.path.join(ROOT, "include", "alvrl.h")).read()
+    for name, val in (("ALVRL_BSDF_SMOOTH", BSDF_SMOOTH), ("ALVRL_BSDF_DIELECTRIC", BSDF_DIELECTRIC), ("ALVRL_BSDF_CONDUCTOR", BSDF_CONDUCTOR)):
+        m = re.search(r"#define\s+" + name + r"\s+(\w+)", txt)
+        assert m and int(m.group(1).rstrip("u"), 0) == val, name
+
+
+def test_diffuse_bsdf_sampling_matches_its_density(orc):
+    """test_chisquare.cpp:398-506 (test01_BSDF) for the `diffuse` model of test_bsdf.xml: directions of sample() against pdf() =
+    cos(theta) / pi on the upper hemisphere (diffuse.cpp:120-148), for 20 incident directions; the weight is the reflectance"""
+    lib = orc.api().lib
+    rng = np.random.default_rng(21)
+    albedo = np.array([0.2, 0.5, 0.7], np.float32)
+    wi_samples = 20
+    for j in range(wi_samples):
+        a = rng.random(2)
+        z = a[1]                                                                    # the upper hemisphere (BSDFAdapter: wi.z > 0 for one-sided models)
+        r = np.sqrt(max(0.0, 1 - z * z))
+        wi = np.array([r * np.cos(2 * np.pi * a[0]), r * np.sin(2 * np.pi * a[0]), max(z, 1e-3)], np.float32)
+        cs = ChiSquare(10, 20, wi_samples)
+        u = rng.random((cs.sample_count, 2), dtype=np.float32)
+        wo, pdf, wt, delta = _bsdf_sample(lib, BSDF_SMOOTH, albedo, None, wi, u)
+        assert not delta.any() and (wo[:, 2] > 0).all()
+        assert np.allclose(pdf, wo[:, 2] / np.pi, rtol=1e-6) and np.array_equal(wt, np.broadcast_to(albedo, wt.shape))
+        integral = cs.fill(wo.astype(np.float64), np.ones(len(wo)), lambda w: np.where(w[:, 2] > 0, w[:, 2] / np.pi, 0.0), quad=32)
+        assert abs(integral - 1) < 1e-6
+        ok, pval, chsq, df = cs.run_test()
+        assert ok, f"chi-square rejects: p={pval:.3e} chi2={chsq:.1f} df={df}"
+    # from below, a one-sided diffuse surface returns no sample (diffuse.cpp:131-133)
+    wo, pdf, wt, delta = _bsdf_sample(lib, BSDF_SMOOTH, albedo, None, np.array([0.3, 0.1, -0.9], np.float32), rng.random((16, 2), dtype=np.float32))
+    assert not wt.any()
+
+
+def _fresnel_dielectric(cos_i, eta):
+    """unpolarised Fresnel reflectance, the textbook form (independent of fresnelDielectricExt's arrangement, util.cpp:651-681)"""
+    if cos_i < 0:
+        eta, cos_i = 1 / eta, -cos_i
+    sin2_t = (1 - cos_i * cos_i) / (eta * eta)
+    if sin2_t >= 1:
+        return 1.0, 0.0
+    cos_t = np.sqrt(1 - sin2_t)
+    rs = (cos_i - eta * cos_t) / (cos_i + eta * cos_t)
+    rp = (eta * cos_i - cos_t) / (eta * cos_i + cos_t)
+    return 0.5 * (rs * rs + rp * rp), cos_t
+
+
+@pytest.mark.parametrize("eta", [1.5, 1 / 1.5, 1.33])
+def test_dielectric_bsdf_discrete_components(orc, eta):
+    """the smooth `dielectric` of test_bsdf.xml has two discrete components (dielectric.cpp:281-364): the chi-square test
+    compares how often each direction is drawn with the probability pdf() reports (chisquare.cpp:124-141: discrete directions
+    enter the reference table with pdf x sampleCount).  Here additionally: the probabilities are the Fresnel terms of an
+    independent formula, the directions obey reflection and Snell's law, and radiance picks up the squared relative index
+    when it is transmitted while importance does not (322-326)."""
+    lib = orc.api().lib
+    rng = np.random.default_rng(1000 + int(eta * 100))    # (seed 133 draws a 4-sigma sample of the uniforms themselves in one of its 20 runs)
+    optics = np.zeros(12, np.float32); optics[0] = eta; optics[6:12] = 1.0
+    one = np.ones(3, np.float32)
+    for j in range(20):
+        a = rng.random(2)
+        z = 1 - 2 * a[1]
+        if abs(z) < 0.02:
+            z = 0.02
+        r = np.sqrt(max(0.0, 1 - z * z))
+        wi = np.array([r * np.cos(2 * np.pi * a[0]), r * np.sin(2 * np.pi * a[0]), z], np.float32)
+        wi /= np.linalg.norm(wi)
+        n = 200_000
+        u = rng.random((n, 2), dtype=np.float32)
+        wo, pdf, wt, delta = _bsdf_sample(lib, BSDF_DIELECTRIC, one, optics, wi, u, radiance=False)
+        assert delta.all()
+        F, cos_t = _fresnel_dielectric(float(wi[2]), eta)
+        refl = np.all(wo == np.array([-wi[0], -wi[1], wi[2]], np.float32), axis=1)
+        assert np.allclose(pdf[refl], F, atol=2e-6) and np.allclose(pdf[~refl], 1 - F, atol=2e-6)
+        # two cells of a contingency table: reflected / transmitted counts against pdf x sampleCount
+        cs = ChiSquare(1, 2, 20)
+        cs.table = np.array([[refl.sum(), (~refl).sum()]], np.float64)
+        cs.ref = np.array([[F * n, (1 - F) * n]])
+        if min(cs.ref.reshape(-1)) >= CHISQR_MIN_EXP_FREQUENCY:
+            ok, pval, chsq, df = cs.run_test()
+            assert ok, (wi, F, pval)
+        else:
+            assert abs(refl.mean() - F) < 1e-3
+        if (~refl).any():                                                          # Snell: sin_t = sin_i / eta (towards the other side)
+            t = wo[~refl][0].astype(np.float64)
+            assert abs(np.linalg.norm(t) - 1) < 1e-5 and np.sign(t[2]) == -np.sign(wi[2]) and abs(abs(t[2]) - cos_t) < 1e-5
+            rel = eta if wi[2] > 0 else 1 / eta
+            assert np.allclose(t[:2], -wi[:2].astype(np.float64) / rel, atol=1e-5)
+            wo_r, _, wt_r, _ = _bsdf_sample(lib, BSDF_DIELECTRIC, one, optics, wi, u[:64], radiance=True)
+            tr = ~np.all(wo_r == np.array([-wi[0], -wi[1], wi[2]], np.float32), axis=1)
+            assert np.allclose(wt[~refl][0], 1.0) and (not tr.any() or np.allclose(wt_r[tr], 1 / (rel * rel), rtol=1e-5))
+
+
+def test_conductor_bsdf_reflects_with_the_exact_fresnel_term(orc):
+    """the smooth `conductor` (conductor.cpp:254-283): one discrete direction, weight = specularReflectance x fresnelConductorExact
+    per channel (util.cpp:739-761) -- against the closed form written out independently here"""
+    lib = orc.api().lib
+    eta, k = np.array([0.27, 0.68, 1.22]), np.array([3.61, 2.63, 2.29])
+    optics = np.zeros(12, np.float32); optics[0:3] = eta; optics[3:6] = k; optics[6:12] = 1.0
+    u = np.random.default_rng(1).random((8, 2), dtype=np.float32)
+    for cz in (1.0, 0.8, 0.3, 0.05):
+        wi = np.array([np.sqrt(1 - cz * cz), 0.0, cz], np.float32)
+        wo, pdf, wt, delta = _bsdf_sample(lib, BSDF_CONDUCTOR, np.ones(3, np.float32), optics, wi, u)
+        assert delta.all() and (pdf == 1).all() and (wo == np.array([-wi[0], 0.0, wi[2]], np.float32)).all()
+        c2 = float(wi[2]) ** 2; s2 = 1 - c2; s4 = s2 * s2
+        t = eta * eta - k * k - s2
+        a2b2 = np.sqrt(t * t + 4 * eta * eta * k * k)
+        a = np.sqrt(0.5 * (a2b2 + t))
+        rs = (a2b2 + c2 - 2 * a * np.sqrt(c2)) / (a2b2 + c2 + 2 * a * np.sqrt(c2))
+        rp = rs * (c2 * a2b2 + s4 - 2 * a * np.sqrt(c2) * s2) / (c2 * a2b2 + s4 + 2 * a * np.sqrt(c2) * s2)
+        assert np.allclose(wt[0], 0.5 * (rs + rp), rtol=2e-5), (cz, wt[0], 0.5 * (rs + rp))
+    wo, pdf, wt, delta = _bsdf_sample(lib, BSDF_CONDUCTOR, np.ones(3, np.float32), optics, np.array([0.6, 0, -0.8], np.float32), u)
+    assert not wt.any()                                                            # from behind: no sample (conductor.cpp:262-263)
