@@ -8,9 +8,15 @@
  * load this code; the product (libalvrl.so) never does.
  *
  * The reference itself cannot be compiled in this image (no Boost/Xerces/OpenEXR headers, see
- * DESIGN.md), so parity of everything except the SFMT stream is "parity unpinned" by the
+ * DESIGN.md).  What the reference's own test suite pins of this path is reproduced: the SFMT stream
+ * (known-answer vector, src/tests/test_random.cpp) and the chi-square test of the phase-function,
+ * BSDF and emitter sampling routines (src/tests/test_chisquare.cpp; tests/test_chisquare_cpu.py).
+ * Everything else -- integrateVRL, R, slices, clusters, images -- is "parity unpinned" by the
  * reference's own tests: this file *defines* the reference result, line by line from the cited
- * sources (paths relative to the reference tree).
+ * sources (paths relative to the reference tree).  Where no vector exists the restatement is
+ * checked against independent computations instead (quadrature of the estimator's integrand and of
+ * the grid medium's optical depth, tests/test_estimator_quadrature_cpu.py; the ground-truth path
+ * tracer and a brute-force estimator, tests/test_volpath.py).
  */
 #pragma once
 #include <cmath>
