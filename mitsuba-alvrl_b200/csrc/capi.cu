@@ -640,18 +640,9 @@ int alvrl_set_vrls(alvrl_handle c, const float *s, const float *e, const float *
 }
 
 int alvrl_load_vrl_file(alvrl_handle c, const char *path) {
-    std::ifstream f(path);
-    if (!f) return fail(ALVRL_ERR_IO, std::string("cannot open VRL file ") + path);
     std::vector<float> s, e, p;
-    std::string line;
-    while (std::getline(f, line)) {                                         /* VRL.h:43-54: 9 floats per line */
-        std::stringstream ss(line);
-        float v[9];
-        int k = 0;
-        while (k < 9 && (ss >> v[k])) k++;
-        if (k < 9) break;
-        s.insert(s.end(), v, v + 3); e.insert(e.end(), v + 3, v + 6); p.insert(p.end(), v + 6, v + 9);
-    }
+    try { read_vrl_file(path, s, e, p); }                                   /* hostio.h: VRL.h:43-54, 120-128 */
+    catch (const HostIoError &err) { return fail(err.code, err.what()); }
     return alvrl_set_vrls(c, s.data(), e.data(), p.data(), (uint32_t) (s.size() / 3), 0);    /* m_numParticles = size(), VRL.h:128 */
 }
 

@@ -58,6 +58,16 @@ int alvrl_host_read_vol(const char *path, int32_t *header, float *density, char 
         return e.code;
     }
 }
+/* out: 9 floats per VRL read (start, end, power); out NULL: count only */
+int alvrl_host_read_vrl_file(const char *path, float *out, uint32_t *n) {
+    try {
+        std::vector<float> s, e, p;
+        read_vrl_file(path, s, e, p);
+        *n = (uint32_t) (s.size() / 3);
+        if (out) for (uint32_t i = 0; i < *n; i++) { memcpy(out + 9 * i, &s[3 * i], 12); memcpy(out + 9 * i + 3, &e[3 * i], 12); memcpy(out + 9 * i + 6, &p[3 * i], 12); }
+        return 0;
+    } catch (const HostIoError &err) { return err.code; }
+}
 int alvrl_host_write_npy(const char *path, const float *data, uint32_t height, uint32_t width, uint32_t channels, char *err, uint32_t errLen) {
     try { write_npy_f32(path, data, height, width, channels); return 0; }
     catch (const HostIoError &e) {

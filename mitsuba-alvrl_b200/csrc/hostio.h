@@ -1,5 +1,5 @@
 /*
- * hostio.h -- the two binary data formats either side of the path (host only, no CUDA):
+ * hostio.h -- the file formats either side of the path (host only, no CUDA):
  *
  *   read_vol_file   the grid volume file a `gridvolume` plugin maps (src/volume/gridvolume.cpp:217-287: "VOL", version 3,
  *                   little endian, type / xres / yres / zres / channels as int32, the data AABB as six float32, then the
@@ -11,14 +11,20 @@
  *                   format 1.0, '<f4', C order, shape (height, width, channels) -- (height, width) for one channel --, the
  *                   dictionary padded with spaces to a multiple of 16 bytes and closed by a newline.
  *
- * Both throw HostIoError {code, message}; capi.cu maps it to the ABI's status + alvrl_last_error(), host_test_api.cpp
+ *   read_vrl_file   the ASCII VRL file of the `vrlFile` property (see below).
+ *
+ * All throw HostIoError {code, message}; capi.cu maps it to the ABI's status + alvrl_last_error(), host_test_api.cpp
  * exposes them to the CPU tests.
  */
 #pragma once
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
+#include <locale>
+#include <sstream>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -99,6 +105,38 @@ inline void read_vol_file(const char *path, VolFile &out, bool headerOnly = fals
             for (size_t i = 0; i < want; i++) out.density[done + i] = map[buf[i]];
             done += want;
         }
+    }
+}
+
+/* The ASCII VRL file of the `vrlFile` property (src/integrators/vrl/VRL.h:43-54, 120-128): one VRL per line, nine numbers
+ * "sx sy sz ex ey ez r g b".  The reference reads lines until the stream throws at the end of the file; a VRL whose power is
+ * not valid (NaN, infinite or negative) makes its constructor Log(EError), which throws into the same catch block (124-126) --
+ * the reading ends there and the VRLs read so far are kept.  A line that does not hold nine numbers leaves the reference with
+ * uninitialised members (undefined behaviour); here it ends the reading like the end of the file.  The put() filter (zero
+ * power, zero length, 148-158) is applied by the caller (alvrl_set_vrls). */
+inline void read_vrl_file(const char *path, std::vector<float> &start, std::vector<float> &end, std::vector<float> &power) {
+    using namespace hostio_detail;
+    if (!path) throw HostIoError(-1, "null VRL file name");
+    File fh(fopen(path, "rb"));
+    if (!fh.f) throw HostIoError(-4, std::string("cannot open VRL file ") + path);
+    std::string line;
+    bool eof = false;
+    while (!eof) {
+        line.clear();
+        int ch;
+        while ((ch = fgetc(fh.f)) != EOF && ch != 10) if (ch != 13) line.push_back((char) ch);      /* Stream::readLine, stream.cpp:392-414 */
+        eof = ch == EOF;
+        if (eof && line.empty()) break;
+        float v[9];
+        int k = 0;
+        std::istringstream ss(line);                        /* as VRL.h:47-50: operator>> on a stringstream of the line ... */
+        ss.imbue(std::locale::classic());                   /* ... in the "C" locale whatever the host process has set */
+        while (k < 9 && (ss >> v[k])) k++;
+        if (k < 9) break;
+        bool valid = true;
+        for (int i = 6; i < 9; i++) valid = valid && std::isfinite(v[i]) && v[i] >= 0;               /* Spectrum::isValid, VRL.h:51-53 */
+        if (!valid) break;
+        start.insert(start.end(), v, v + 3); end.insert(end.end(), v + 3, v + 6); power.insert(power.end(), v + 6, v + 9);
     }
 }
 

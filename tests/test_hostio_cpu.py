@@ -146,3 +146,37 @@ def test_library_reader_agrees_with_the_oracles_restatement_of_loadFromFile(pkg,
         c = orc.Oracle(**params); c.set_scene(scene)
         c.set_medium_grid(m["density"], (0.05, 0, 0.1), (0.9, 1, 1), m["scale"], m["albedo"], m["sigmaS_base"])
         assert np.array_equal(ta, c.eval_transmittance(p1, s, p2))
+
+
+def _read_vrls(host_lib, path):
+    n = C.c_uint32()
+    rc = host_lib.alvrl_host_read_vrl_file(str(path).encode(), None, C.byref(n))
+    if rc != 0:
+        return rc, None
+    out = np.zeros((n.value, 9), np.float32)
+    assert host_lib.alvrl_host_read_vrl_file(str(path).encode(), _p(out), C.byref(n)) == 0
+    return 0, out
+
+
+def test_vrl_file_reader_follows_the_reference_constructor(pkg, host_lib, tmp_path):
+    """VRL.h:43-54 + 120-128: nine numbers per line; reading ends at the end of the file, at a line without nine numbers, and
+    -- silently, keeping what was read -- at a VRL whose power is not valid (the constructor's Log(EError) lands in the reader's
+    own catch block).  Zero power / zero length lines are read here and dropped later by the put() filter."""
+    s, e, p, _ = pkg.scenes.synthetic_vrls(40, sigma_t=1.05, seed=4)
+    path = tmp_path / "set.vrl"
+    pkg.scenes.write_vrl_file(path, s, e, p)
+    rc, got = _read_vrls(host_lib, path)
+    assert rc == 0 and np.array_equal(got, np.concatenate([s, e, p], 1))              # repr() round-trips every float32
+    # CR LF line ends, extra columns, exponents, a last line without a newline
+    path.write_text("0 0 0 1 0 0 1 1 1\r\n1e-1 2E-1 .3 4 5 6 7 8 9 10 11\r\n-1 -2 -3 0.5 0.5 0.5 0 0 0")
+    rc, got = _read_vrls(host_lib, path)
+    assert rc == 0 and len(got) == 3 and np.array_equal(got[1], np.float32([0.1, 0.2, 0.3, 4, 5, 6, 7, 8, 9])) and not got[2, 6:].any()
+    # the reading ends at: a negative power, a NaN, a short line, an empty line
+    for bad in ("0 0 0 1 1 1 1 -1 1", "0 0 0 1 1 1 nan 1 1", "0 0 0 1 1 1 1 1", "", "x y z"):
+        path.write_text("0 0 0 1 0 0 1 1 1\n0 0 0 2 0 0 1 1 1\n" + bad + "\n0 0 0 3 0 0 1 1 1\n")
+        rc, got = _read_vrls(host_lib, path)
+        assert rc == 0 and len(got) == 2, (bad, got)
+    path.write_text("")
+    rc, got = _read_vrls(host_lib, path)
+    assert rc == 0 and len(got) == 0
+    assert _read_vrls(host_lib, tmp_path / "missing.vrl")[0] == -4
