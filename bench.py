@@ -373,6 +373,7 @@ def run_ours(a):
                 "shadow_rays_per_s_R_kernel": k_pairs * (params["volVolSamples"] + params["volSurfSamples"]) / (k_ms * 1e-3),
                 "visibility_mode": {0: "stackless BVH traversal per lane", 1: "flat leaf sweep", 2: "compiled occluder set + pair-level culling"}.get(int(st.visMode), "?"),
                 "bvh_nodes": int(st.bvhNodes),
+                "scene_build_ms": float(st.msSceneBuild),     # host BVH build + triangle records + upload: outside the frame, reported separately
                 "comm": {"library": "NCCL via alvrl_group_* (csrc/group.cu)" if multi else None, "nranks": comm_ranks},
                 "frame_definition": "buildSlices + sampleSliceMapping + Building R + buildClusters (per-slice refinement; the global/"
                                     "fallback lists are only computed when a slice cannot be refined, as no slice of this workload "

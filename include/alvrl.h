@@ -98,6 +98,8 @@ typedef struct alvrl_stats {
     uint32_t kernelLaunches;    /* kernels launched by this handle since creation */
     uint32_t numSlices, numRows, numVrls, bvhNodes;
     uint32_t visMode;           /* shadow-ray strategy of the fast flavour: 0 BVH traversal, 1 flat leaf sweep, 2 compiled occluder set */
+    float msSceneBuild;         /* host: BVH build + triangle records + occluder set + upload of the last scene change; outside the
+                                   frame time by definition ("excluding scene upload and BVH build (reported separately)") */
 } alvrl_stats;
 
 /* ---- life cycle -------------------------------------------------------------------------- */

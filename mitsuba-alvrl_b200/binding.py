@@ -43,6 +43,7 @@ class Stats(C.Structure):
         ("msTransportKernelR", C.c_float), ("msTransportKernelRender", C.c_float),
         ("kernelLaunches", C.c_uint32), ("numSlices", C.c_uint32), ("numRows", C.c_uint32),
         ("numVrls", C.c_uint32), ("bvhNodes", C.c_uint32), ("visMode", C.c_uint32),
+        ("msSceneBuild", C.c_float),
     ]
 
 

@@ -66,6 +66,7 @@ HostSampler *new_stream(const alvrl_params &P) {
 void ensure_scene(alvrl_ctx *c) {
     if (!c->sceneDirty) return;
     if (!c->haveMesh) throw Error(ALVRL_ERR_STATE, "set_mesh first");
+    const double tScene0 = now_ms();
     const uint32_t nt = (uint32_t) c->triMat.size();
     HostBvh bvh;
     BvhBuilder(c->verts.data(), c->tris.data(), nt).build(bvh);
@@ -130,6 +131,7 @@ void ensure_scene(alvrl_ctx *c) {
     if (getenv("ALVRL_NO_PAIR_CULL")) c->occHost.cullMargin = INFINITY;      /* experiments: nothing is ever "strictly beyond" */
     c->vrlSidesValid = false;
     c->stats.bvhNodes = s.numNodes; c->stats.visMode = (uint32_t) s.visMode;
+    c->stats.msSceneBuild = (float) (now_ms() - tScene0);
     c->sceneDirty = false; c->segsDirty = true;
 }
 
