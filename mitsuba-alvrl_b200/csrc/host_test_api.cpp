@@ -156,7 +156,7 @@ int alvrl_host_compile_occluders(const float *verts, const uint32_t *tris, uint3
     const OccluderSet os = compile_occluders(verts, tris, nt, numLeaves);
     counts[0] = os.use; counts[1] = os.numSlabs; counts[2] = os.numPlanes; counts[3] = os.numTris; counts[4] = os.numPolytopes; counts[5] = os.numBoxes;
     if (os.tris.size() > maxFloat4) return -1;
-    if (os.use) { memcpy(dev, &os.dev, sizeof(OccDev)); memcpy(triRecs, os.tris.data(), os.tris.size() * sizeof(float4)); }
+    if (os.use) { memcpy(dev, &os.dev, sizeof(OccDev)); if (!os.tris.empty()) memcpy(triRecs, os.tris.data(), os.tris.size() * sizeof(float4)); }
     return (int) sizeof(OccDev);
 }
 /* occ_query.h on the host: n segments (origin o, unit direction d, [tmin, tmax]) against a compiled set */
