@@ -215,7 +215,8 @@ def run_reference(a):
     line = {"impl": "reference", "metric": "vrl_segment_contributions_per_s", "value": v, "unit": "VRL-segment contributions/s",
             "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": float(np.mean(times)) * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": desc, "cpu_baseline": base,
+            # the same config object as the product arm's line (the driver compares them key by key)
+            "config": dict(desc, parallelism=f"slice-sharded x{int(os.environ.get('WORLD_SIZE', a.gpus))}"), "cpu_baseline": base,
             "e2e": {"value": v, "unit": "VRL-segment contributions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
