@@ -205,3 +205,20 @@ def test_measured_time_balancing_converges_and_is_rank_independent(host_lib):
     assert host_lib.alvrl_host_balance_step(pixels.ctypes.data_as(vp), C.c_uint32(S), C.c_int(world), cost.ctypes.data_as(vp), None,
                                             zero.ctypes.data_as(vp), C.c_uint32(0), nxt.ctypes.data_as(vp)) == 0
     assert np.allclose(cost, pixels + int(pixels.sum()) // 500)
+
+
+def test_header_is_plain_c99_and_links_from_c(pkg, tmp_path):
+    """the drop-in boundary is a C ABI: include/alvrl.h (and alvrl_rng.h) compile as strict C99 -- no C++ types in any signature --
+    and a C program linked against libalvrl.so reads the reference's defaults through it (no device needed for that call)"""
+    import subprocess
+    src = tmp_path / "c_abi.c"
+    src.write_text('#include "alvrl.h"\n#include "alvrl_rng.h"\n#include <stdio.h>\n'
+                   'int main(void) { alvrl_params p; alvrl_params_default(&p);\n'
+                   '  printf("%d %d %d %g\\n", (int) p.volVolSamples, (int) p.targetNumSlices, (int) p.vrlTargetNum, (double) p.targetPixelUndersampling);\n'
+                   '  return alvrl_last_error() == 0; }\n')
+    lib_dir = os.path.join(ROOT, "mitsuba-alvrl_b200")
+    exe = tmp_path / "c_abi"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src),
+                           "-L" + lib_dir, "-lalvrl", "-Wl,-rpath," + lib_dir, "-o", str(exe)])
+    out = subprocess.check_output([str(exe)]).decode().split()
+    assert out == ["2", "100", "500", "64"]                               # vrlIntegrator.cpp:128-208
