@@ -94,12 +94,21 @@ struct MediumView {
 struct SensorView { float sampleToCamera[16], cameraToWorld[16]; uint32_t width, height; float nearClip, farClip; float position[3]; };
 /* Film: its reconstruction filter (Film::getReconstructionFilter: 0 box, 1 tent, 2 gaussian = ALVRL_FILTER_*; param <= 0 = the
  * filter's default radius / stddev) and where the developed image goes */
-class Film { public: virtual ~Film() {} int rfilter = 0; float rfilterParam = 0.0f; virtual void setImage(const float *rgb, uint32_t width, uint32_t height) = 0; };
+class Film {
+public:
+    virtual ~Film() {}
+    int rfilter = 0; float rfilterParam = 0.0f;
+    virtual void setImage(const float *rgb, uint32_t width, uint32_t height) = 0;
+    /* ProgressiveMonteCarloIntegrator::dumpPass (src/librender/integrator.cpp:361-378): setDestinationFile(passFile), develop(),
+     * setDestinationFile(original) -- here the developed image arrives with the file name */
+    virtual void dumpPass(const std::string &passFile, const float *rgb, uint32_t width, uint32_t height) { (void) passFile; (void) rgb; (void) width; (void) height; }
+};
 /* an area emitter attached to a triangle mesh (Scene::getEmitters, src/emitters/area.cpp): mesh index + radiance */
 struct EmitterView { uint32_t meshIndex; float radiance[3]; bool onAnalyticShape = false; /* meshIndex then counts Scene::shapes */ };
 class Scene {
 public:
     std::vector<TriMeshView> meshes; std::vector<AnalyticShapeView> shapes; std::vector<MediumView> media; std::vector<EmitterView> emitters; SensorView sensor; Film *film = nullptr;
+    std::string destinationFile;                          /* Scene::getDestinationFile */
 };
 
 class Integrator {

@@ -8,7 +8,10 @@
  * replacement renders the whole frame at once: render() hands the framebuffer to the film ("Threading").
  * Exported plugin ABI: CreateInstance / GetDescription (include/mitsuba/core/cobject.h:99-107, vrlIntegrator.cpp:1127).
  */
+#include <chrono>
+#include <cstdio>
 #include <cstring>
+#include <ctime>
 #include <string>
 #include <vector>
 #include "../../../include/alvrl.h"
@@ -194,15 +197,37 @@ public:
         const bool useFilm = m_maxPasses > 1 || filter != ALVRL_FILTER_BOX;
         if (useFilm) chk(alvrl_film_configure(m_h, filter, scene->film ? scene->film->rfilterParam : 0.0f));
         m_cancelled = false;
-        for (int pass = 1; pass <= m_maxPasses && !m_cancelled; pass++) {   /* cancel() takes effect between passes */
+        double prepassCpu = 0, prepassWall = 0, renderCpu = 0, renderWall = 0;     /* cumulative, as integrator.cpp:394-430 */
+        int pass = 1;
+        for (; pass <= m_maxPasses && !m_cancelled; pass++) {               /* cancel() takes effect between passes */
+            const double w0 = wallSeconds(), c0 = cpuSeconds();
             if (!prepass(scene)) return false;
+            const double w1 = wallSeconds(), c1 = cpuSeconds();
             if (!renderPass(scene, rgb)) return false;
             if (useFilm) chk(alvrl_film_put(m_h, nullptr));                   /* the frame alvrl_render left on the device */
+            prepassWall += w1 - w0; prepassCpu += c1 - c0; renderWall += wallSeconds() - w1; renderCpu += cpuSeconds() - c1;
         }
+        pass--;
         if (useFilm) chk(alvrl_film_develop(m_h, rgb.data()));
         if (scene->film) scene->film->setImage(rgb.data(), scene->sensor.width, scene->sensor.height);
+        /* dumpPasses: with a pass count only the last pass is dumped (integrator.cpp:436-438), under a name that carries the
+         * cumulative prepass / render times and, from passFileSuffix (vrlIntegrator.cpp:357-364), the two StatsCounters */
+        if (m_dumpPasses && scene->film && pass >= 1)
+            scene->film->dumpPass(passFileName(scene->destinationFile, pass, prepassCpu, prepassWall, renderCpu, renderWall), rgb.data(),
+                                  scene->sensor.width, scene->sensor.height);
         return true;
     }
+    /* ProgressiveMonteCarloIntegrator::dumpPass's file name (integrator.cpp:365-374) */
+    std::string passFileName(const std::string &origFile, int pass, double prepassCpu, double prepassWall, double renderCpu, double renderWall) const {
+        alvrl_stats st; memset(&st, 0, sizeof(st));
+        chk(alvrl_get_stats(m_h, &st));
+        char buf[512];
+        snprintf(buf, sizeof(buf), "_pass%03d_precpu%.4e_prewall%.4e_rencpu%.4e_renwall%.4e_prevrl%.4e_renvrl%.4e.blahExtensionTODO", pass,
+                 prepassCpu, prepassWall, renderCpu, renderWall, (double) (float) st.pairsPreprocess, (double) (float) st.pairsRender);
+        return origFile + buf;
+    }
+    static double wallSeconds() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+    static double cpuSeconds() { return (double) std::clock() / CLOCKS_PER_SEC; }        /* user + system of the process, as cpu_timer */
     /* SamplingIntegrator::cancel (integrator.cpp:68-71) stops the block scheduler; here: no further pass is started */
     void cancel() override { m_cancelled = true; }
     alvrl_handle handle() const { return m_h; }
@@ -324,6 +349,25 @@ int alvrl_plugin_render_frame_filtered(void *inst, void *scene, int rfilter, flo
         sc->film = &film;
         it->preprocess(sc); it->render(sc);           /* render() = ProgressiveMonteCarloIntegrator::render: prepass + render pass per pass */
         sc->film = nullptr;
+        return 0;
+    } catch (const std::exception &e) { sc->film = nullptr; strncpy(err, e.what(), errLen - 1); err[errLen - 1] = 0; return -1; }
+}
+/* one frame with a destination file: returns the pass file name the film was handed (empty: dumpPasses is off) */
+int alvrl_plugin_render_frame_dump(void *inst, void *scene, const char *destinationFile, float *rgbOut, char *passFile, int passFileLen, char *err, int errLen) {
+    struct DumpFilm : mts::Film {
+        float *dst; std::string name; std::vector<float> dumped;
+        explicit DumpFilm(float *d) : dst(d) {}
+        void setImage(const float *rgb, uint32_t w, uint32_t h) override { memcpy(dst, rgb, (size_t) w * h * 3 * sizeof(float)); }
+        void dumpPass(const std::string &f, const float *rgb, uint32_t w, uint32_t h) override { name = f; dumped.assign(rgb, rgb + (size_t) w * h * 3); }
+    } film(rgbOut);
+    mts::Scene *sc = static_cast<mts::Scene *>(scene);
+    mts::Integrator *it = static_cast<vrlIntegrator *>(inst);
+    try {
+        sc->film = &film; sc->destinationFile = destinationFile;
+        it->preprocess(sc); it->render(sc);
+        sc->film = nullptr;
+        strncpy(passFile, film.name.c_str(), passFileLen - 1); passFile[passFileLen - 1] = 0;
+        if (!film.name.empty() && memcmp(film.dumped.data(), rgbOut, film.dumped.size() * sizeof(float)) != 0) { strncpy(err, "the dumped pass is not the developed film", errLen - 1); return -2; }
         return 0;
     } catch (const std::exception &e) { sc->film = nullptr; strncpy(err, e.what(), errLen - 1); err[errLen - 1] = 0; return -1; }
 }

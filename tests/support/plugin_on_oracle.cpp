@@ -36,6 +36,7 @@
 #define alvrl_build_slices orc_build_slices
 #define alvrl_trace_vrls orc_trace_vrls
 #define alvrl_prepass orc_prepass
+#define alvrl_get_stats orc_get_stats
 #define alvrl_set_camera t_set_camera
 #define alvrl_render t_render
 #define alvrl_render_unclustered t_render_unclustered

@@ -161,3 +161,44 @@ def test_traced_vrls_progressive_passes_and_analytic_shapes(pkg, orc, lib, host_
     assert img_plugin.max() > 0 and np.array_equal(img_plugin, img)
     if passes > 1:
         assert not np.array_equal(frames[0], frames[1])
+
+
+def test_dump_passes_names_the_pass_file_like_the_reference(pkg, orc, lib, tmp_path):
+    """dumpPasses (src/librender/integrator.cpp:361-378, 436-438; passFileSuffix, vrlIntegrator.cpp:357-364): with a pass count the
+    last pass is dumped under <destination>_passNNN_precpu.._prewall.._rencpu.._renwall.._prevrl.._renvrl...blahExtensionTODO --
+    cumulative times in %.4e, the two StatsCounters ("Number of integrated VRLs during preprocessing / rendering") as floats"""
+    import re
+    scene, vrls, params = pkg.scenes.make_config("C1", width=24, height=20, n_vrls=40)
+    start, end, power, pc = vrls
+    path = str(tmp_path / "set.vrl")
+    pkg.scenes.write_vrl_file(path, start, end, power)
+    meshes, flat = _by_material(scene)
+    xml = dict(params, targetNumSlices=5, seed=2, vrlFile=path, maxPasses=2)
+    fp = C.POINTER(C.c_float)
+    names = {}
+    for dump in (True, False):
+        p, inst = _instance(lib, dumpPasses=dump, **xml)
+        sc = C.c_void_p(lib.alvrl_plugin_scene_new())
+        keep = _scene_to_plugin(lib, sc, scene, meshes)
+        img = np.zeros((20, 24, 3), np.float32)
+        name, err = C.create_string_buffer(600), C.create_string_buffer(600)
+        rc = lib.alvrl_plugin_render_frame_dump(inst, sc, b"/renders/cornell", img.ctypes.data_as(fp), name, 600, err, 600)
+        assert rc == 0, err.value
+        names[dump] = name.value.decode()
+        lib.alvrl_plugin_destroy(inst); lib.alvrl_plugin_scene_free(sc); lib.alvrl_plugin_props_free(p)
+        del keep
+    assert names[False] == ""
+    num = r"(\d\.\d{4}e[+-]\d{2})"
+    m = re.fullmatch(r"/renders/cornell_pass(\d{3})_precpu" + num + "_prewall" + num + "_rencpu" + num + "_renwall" + num + "_prevrl" + num +
+                     "_renvrl" + num + r"\.blahExtensionTODO", names[True])
+    assert m, names[True]
+    assert m.group(1) == "002" and float(m.group(3)) > 0 and float(m.group(5)) > 0
+    # the counters: the same two passes on the oracle itself
+    o = orc.Oracle(**{k: v for k, v in xml.items() if k not in ("vrlFile", "maxPasses")})
+    o.set_scene(flat); o.set_vrls(start, end, power, 0); o.build_slices()
+    for k in range(2):
+        if k:
+            o.set_seed(2 + k)
+        o.prepass(); o.render()
+    st = o.stats()
+    assert m.group(6) == "%.4e" % np.float32(st.pairsPreprocess) and m.group(7) == "%.4e" % np.float32(st.pairsRender)
