@@ -56,6 +56,9 @@ int alvrl_host_read_vol(const char *path, int32_t *header, float *density, char 
     } catch (const HostIoError &e) {
         if (err && errLen) { strncpy(err, e.what(), errLen - 1); err[errLen - 1] = 0; }
         return e.code;
+    } catch (const std::exception &e) {                     /* (bad_alloc: alvrl_set_medium_grid_file answers ALVRL_ERR_IO too) */
+        if (err && errLen) { strncpy(err, e.what(), errLen - 1); err[errLen - 1] = 0; }
+        return -4;
     }
 }
 /* out: 9 floats per VRL read (start, end, power); out NULL: count only */

@@ -87,6 +87,13 @@ inline void read_vol_file(const char *path, VolFile &out, bool headerOnly = fals
         if (out.res[i] < 1 || out.res[i] > (1 << 14)) throw HostIoError(-1, "Encountered an invalid volume data file (resolution out of range)");
     if (headerOnly) { out.density.clear(); return; }
     const size_t n = (size_t) out.res[0] * (size_t) out.res[1] * (size_t) out.res[2];
+    /* the voxels the header announces must be in the file: checked against its length before anything is allocated (a corrupt
+     * header can announce terabytes; the reference maps the file and would read past the mapping) */
+    if (fseek(fh.f, 0, SEEK_END) != 0) throw HostIoError(-4, "cannot seek in the volume data file");
+    const long fileSize = ftell(fh.f);
+    if (fileSize < 0 || fseek(fh.f, (long) sizeof(h), SEEK_SET) != 0) throw HostIoError(-4, "cannot seek in the volume data file");
+    if ((size_t) fileSize - sizeof(h) < n * (out.type == VOL_FLOAT32 ? 4u : 1u))
+        throw HostIoError(-4, "Encountered an invalid volume data file (fewer voxels than the header announces)");
     out.density.resize(n);
     if (out.type == VOL_FLOAT32) {
         if (fread(out.density.data(), 4, n, fh.f) != n) throw HostIoError(-4, "Encountered an invalid volume data file (fewer voxels than the header announces)");

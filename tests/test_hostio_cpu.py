@@ -180,3 +180,38 @@ def test_vrl_file_reader_follows_the_reference_constructor(pkg, host_lib, tmp_pa
     rc, got = _read_vrls(host_lib, path)
     assert rc == 0 and len(got) == 0
     assert _read_vrls(host_lib, tmp_path / "missing.vrl")[0] == -4
+
+
+def test_file_readers_survive_corrupt_input(pkg, host_lib, tmp_path):
+    """hypothesis: truncated, bit-flipped and random files never crash the readers and never make them allocate what the file
+    cannot hold -- a header that announces 16384^3 voxels in a 60-byte file is refused from the file's length"""
+    from hypothesis import given, settings, strategies as st
+    good = tmp_path / "good.vol"
+    pkg.volfile.write_vol(good, np.random.default_rng(0).random((3, 4, 5), dtype=np.float32), (0, 0, 0), (1, 1, 1))
+    base = good.read_bytes()
+    huge = tmp_path / "huge.vol"
+    huge.write_bytes(b"VOL\x03" + struct.pack("<iiiii", 1, 16384, 16384, 16384, 1) + struct.pack("<6f", 0, 0, 0, 1, 1, 1) + b"\0" * 12)
+    rc, hdr, _ = _read(host_lib, huge, voxels=False)
+    assert rc == 0 and hdr["res"] == (16384, 16384, 16384)               # the header alone is well formed ...
+    one, err, h11 = np.zeros(1, np.float32), C.create_string_buffer(256), np.zeros(11, np.int32)
+    assert host_lib.alvrl_host_read_vol(str(huge).encode(), _p(h11), _p(one), err, C.c_uint32(256)) == -4 and b"fewer voxels" in err.value
+    path = tmp_path / "fuzz.bin"
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.integers(0, len(base)), st.lists(st.tuples(st.integers(0, len(base) - 1), st.integers(0, 255)), max_size=6), st.binary(max_size=80))
+    def check(cut, flips, tail):
+        b = bytearray(base[:cut])
+        for pos, val in flips:
+            if pos < len(b):
+                b[pos] = val
+        path.write_bytes(bytes(b) + tail)
+        hdr = np.zeros(11, np.int32)
+        err = C.create_string_buffer(256)
+        rc = host_lib.alvrl_host_read_vol(str(path).encode(), _p(hdr), None, err, C.c_uint32(256))
+        assert rc in (0, -1, -4, -5)
+        if rc == 0 and int(hdr[1]) * int(hdr[2]) * int(hdr[3]) <= 1 << 22:
+            d = np.zeros(int(hdr[1]) * int(hdr[2]) * int(hdr[3]), np.float32)
+            assert host_lib.alvrl_host_read_vol(str(path).encode(), _p(hdr), _p(d), err, C.c_uint32(256)) in (0, -4)
+        n = C.c_uint32()
+        assert host_lib.alvrl_host_read_vrl_file(str(path).encode(), None, C.byref(n)) == 0        # a VRL file reader stops at the first bad line
+    check()
