@@ -26,16 +26,16 @@ namespace alvrl {
 /* appends 4 vertices and 2 triangles; toWorld row-major 4x4 (affine) */
 inline void tessellate_rectangle(const float toWorld[16], bool flipNormals, std::vector<float> &verts, std::vector<uint32_t> &tris) {
     const float *m = toWorld;
-    const float corners[4][2] = {{-1, -1}, {1, -1}, {1, 1}, {-1, 1}};                  /* rectangle.cpp:179-182 */
-    const uint32_t base = (uint32_t) (verts.size() / 3);
-    for (int i = 0; i < 4; i++)
-        for (int r = 0; r < 3; r++) verts.push_back(m[4 * r + 0] * corners[i][0] + m[4 * r + 1] * corners[i][1] + m[4 * r + 3]);
     /* determinant of the linear part, with the third column negated by flipNormals (rectangle.cpp:82-83) */
     const double sz = flipNormals ? -1.0 : 1.0;
     const double a = m[0], b = m[1], c = sz * m[2], d = m[4], e = m[5], f = sz * m[6], g = m[8], h = m[9], i = sz * m[10];
     const double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
-    if (!(det != 0)) throw std::runtime_error("rectangle: 'toWorld' is singular");
+    if (!(det != 0)) throw std::runtime_error("rectangle: 'toWorld' is singular");          /* before anything is appended */
     const bool reverse = det < 0;
+    const float corners[4][2] = {{-1, -1}, {1, -1}, {1, 1}, {-1, 1}};                  /* rectangle.cpp:179-182 */
+    const uint32_t base = (uint32_t) (verts.size() / 3);
+    for (int k = 0; k < 4; k++)
+        for (int r = 0; r < 3; r++) verts.push_back(m[4 * r + 0] * corners[k][0] + m[4 * r + 1] * corners[k][1] + m[4 * r + 3]);
     const uint32_t t[2][3] = {{0, 1, 2}, {2, 3, 0}};                                   /* rectangle.cpp:190-196 */
     for (int k = 0; k < 2; k++) {
         tris.push_back(base + t[k][0]);
