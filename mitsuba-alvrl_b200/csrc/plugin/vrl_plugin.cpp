@@ -113,6 +113,15 @@ public:
         }
         if (m_maxPasses < 0) mts::LogError("maxPasses < 0 (render until cancelled) is not supported by the device path: give a pass count");
         alvrl_params hp = m_p; hp.maxPasses = 1;                              /* the passes are driven from render() below */
+        /* the false-colour debug outputs (vrlIntegrator.cpp:199-201) are produced here, from the library's slice map and cluster
+         * counts (falseColorPass below); the library itself only ever renders radiance */
+        hp.numVrlFalseColor = hp.slicesFalseColor = hp.convergenceFalseColor = 0;
+        if (m_p.numVrlFalseColor || m_p.slicesFalseColor || m_p.convergenceFalseColor) {
+            for (const mts::TriMeshView &tm : scene->meshes) if (tm.bsdf != 0) mts::LogError("the false-colour outputs are not supported with specular surfaces (the chain segments' weights stay on the device)");
+            for (const mts::AnalyticShapeView &sh : scene->shapes) if (sh.bsdf != 0) mts::LogError("the false-colour outputs are not supported with specular surfaces (the chain segments' weights stay on the device)");
+            if (m_p.slicesFalseColor && !m_p.numVrlFalseColor && !(m_p.globalCluster || m_p.localRefinement))
+                mts::LogError("requested slices false color image without clustering!");                 /* 438-440 */
+        }
         chk(alvrl_create(m_device, &hp, &m_h));
         /* triangle soup + one diffuse material per mesh */
         std::vector<float> verts, albedo, optics; std::vector<uint32_t> tris, mat, bits;
@@ -182,8 +191,52 @@ public:
         return true;
     }
     /* one render pass: every pixel centre through Li (386-393; MonteCarloIntegrator::render) */
+    /* numVrlFalseColor / slicesFalseColor for scenes without delta surfaces: LiInternal returns LiDirect (447-448), which is the
+     * value getClusteredVrlContributions / getVRLContributions compute instead of radiance (574-584, 806-807) for every camera ray
+     * that hits something, and zero for the rays that leave the scene (418-423).  convergenceFalseColor only takes effect behind
+     * delta surfaces (quirk B4: the early return at 447-448 comes first), so without them it is the radiance image. */
+    void falseColorPass(mts::Scene *scene, std::vector<float> &rgb) {
+        const uint32_t W = scene->sensor.width, H = scene->sensor.height, P = W * H;
+        std::vector<uint32_t> prim(P), toSlice(P, ALVRL_NO_SLICE), offset;
+        chk(alvrl_get_primary_hits(m_h, prim.data(), nullptr, nullptr, nullptr));
+        const bool clustered = m_p.globalCluster || m_p.localRefinement;
+        uint32_t nVrls = 0, nGlobal = 0, nFallback = 0, nSlices = 0, nRows = 0;
+        if (clustered) {
+            chk(alvrl_get_pixel_to_slice(m_h, toSlice.data()));
+            chk(alvrl_get_num_slices(m_h, &nSlices, &nRows));
+            if (m_p.numVrlFalseColor) {
+                offset.resize(nSlices + 1);
+                chk(alvrl_get_cluster_counts(m_h, offset.data(), &nGlobal, &nFallback));
+                chk(alvrl_get_num_vrls(m_h, &nVrls));
+            }
+        }
+        for (uint32_t y = 0; y < H; y++)
+            for (uint32_t x = 0; x < W; x++) {
+                const uint32_t i = y + H * x;                                   /* m_ci->m_slices[y + sizeY * x], 558 */
+                float c[3] = {0, 0, 0};
+                if (prim[i] != ALVRL_NO_HIT) {
+                    const uint32_t sl = toSlice[i];
+                    if (m_p.numVrlFalseColor) {
+                        if (!clustered) c[0] = c[1] = c[2] = 1.0f;              /* Li = weight, 806-807 */
+                        else {
+                            uint32_t count = sl == ALVRL_NO_SLICE ? nFallback : offset[sl + 1] - offset[sl];
+                            if (count == 0) count = nFallback;                  /* a slice without a list of its own renders with the fallback list */
+                            c[0] = c[1] = c[2] = (float) count / (float) nVrls;  /* 574-575 */
+                        }
+                    } else if (sl == ALVRL_NO_SLICE) c[0] = c[1] = c[2] = 0.5f;   /* "fallback clustering in gray", 577-578 */
+                    else {                                                      /* 580-584, in the reference's unsigned arithmetic */
+                        c[0] = (float) (((sl + sl * sl) % 43u) / 43.0);
+                        c[1] = (float) (((7u * sl + 2u * sl * sl + 7u) % 41u) / 41.0);
+                        c[2] = (float) (((23u * sl + 5u * sl * sl + sl * sl * sl + 17u) % 53u) / 53.0);
+                    }
+                }
+                float *o = &rgb[3 * ((size_t) y * W + x)];
+                o[0] = c[0]; o[1] = c[1]; o[2] = c[2];
+            }
+    }
     bool renderPass(mts::Scene *scene, std::vector<float> &rgb) {
         rgb.resize((size_t) scene->sensor.width * scene->sensor.height * 3);
+        if (m_p.numVrlFalseColor || m_p.slicesFalseColor) { falseColorPass(scene, rgb); return true; }
         if (m_p.globalCluster || m_p.localRefinement) chk(alvrl_render(m_h, rgb.data()));
         else chk(alvrl_render_unclustered(m_h, rgb.data()));
         return true;
@@ -204,7 +257,8 @@ public:
             if (!prepass(scene)) return false;
             const double w1 = wallSeconds(), c1 = cpuSeconds();
             if (!renderPass(scene, rgb)) return false;
-            if (useFilm) chk(alvrl_film_put(m_h, nullptr));                   /* the frame alvrl_render left on the device */
+            /* the frame alvrl_render left on the device; a false-colour pass was made here, on the host */
+            if (useFilm) chk(alvrl_film_put(m_h, (m_p.numVrlFalseColor || m_p.slicesFalseColor) ? rgb.data() : nullptr));
             prepassWall += w1 - w0; prepassCpu += c1 - c0; renderWall += wallSeconds() - w1; renderCpu += cpuSeconds() - c1;
         }
         pass--;

@@ -37,6 +37,11 @@
 #define alvrl_trace_vrls orc_trace_vrls
 #define alvrl_prepass orc_prepass
 #define alvrl_get_stats orc_get_stats
+#define alvrl_get_primary_hits orc_get_primary_hits
+#define alvrl_get_pixel_to_slice orc_get_pixel_to_slice
+#define alvrl_get_num_slices orc_get_num_slices
+#define alvrl_get_cluster_counts orc_get_cluster_counts
+#define alvrl_get_num_vrls orc_get_num_vrls
 #define alvrl_set_camera t_set_camera
 #define alvrl_render t_render
 #define alvrl_render_unclustered t_render_unclustered

@@ -202,3 +202,82 @@ def test_dump_passes_names_the_pass_file_like_the_reference(pkg, orc, lib, tmp_p
         o.prepass(); o.render()
     st = o.stats()
     assert m.group(6) == "%.4e" % np.float32(st.pairsPreprocess) and m.group(7) == "%.4e" % np.float32(st.pairsRender)
+
+
+@pytest.mark.parametrize("mode", ["slicesFalseColor", "numVrlFalseColor", "numVrlFalseColor-unclustered", "convergenceFalseColor"])
+def test_false_colour_debug_outputs(pkg, orc, lib, tmp_path, mode):
+    """numVrlFalseColor / slicesFalseColor / convergenceFalseColor (vrlIntegrator.cpp:199-201, 514-520, 574-584, 806-807) for scenes
+    without delta surfaces, made by the shim from the library's hit mask, slice map and cluster counts.  Expected images are
+    written out here from the reference's formulas; the pixel indexing (m_slices[y + sizeY * x]) is cross-checked against the
+    radiance image: the same pixels are black."""
+    scene, vrls, params = pkg.scenes.make_config("C1", width=36, height=28, n_vrls=60)
+    cam = pkg.scenes.perspective_camera(36, 28, origin=(0.45, 0.55, -2.4), target=(0.5, 0.5, 0.0), fov=40.0)     # further back: rays pass the box
+    scene = dict(scene, camera=cam, extra_bounds=cam["origin"].reshape(1, 3))
+    start, end, power, pc = vrls
+    path = str(tmp_path / "set.vrl")
+    pkg.scenes.write_vrl_file(path, start, end, power)
+    meshes, flat = _by_material(scene)
+    xml = dict(params, targetNumSlices=7, seed=4, vrlFile=path)
+    key = mode.split("-")[0]
+    unclustered = mode.endswith("unclustered")
+    if unclustered:
+        xml.update(globalCluster=False, localRefinement=False)
+
+    def frame(**extra):
+        p, inst = _instance(lib, **dict(xml, **extra))
+        sc = C.c_void_p(lib.alvrl_plugin_scene_new())
+        keep = _scene_to_plugin(lib, sc, scene, meshes)
+        img = _frame(lib, inst, sc, scene)
+        lib.alvrl_plugin_destroy(inst); lib.alvrl_plugin_scene_free(sc); lib.alvrl_plugin_props_free(p)
+        del keep
+        return img
+
+    img = frame(**{key: True})
+    radiance = frame()
+    o = orc.Oracle(**{k: v for k, v in xml.items() if k != "vrlFile"})
+    o.set_scene(flat); o.set_vrls(start, end, power, 0)
+    H, W = 28, 36
+    hit = (o.primary_hits()[0] != pkg.binding.NO_HIT).reshape(W, H).T                 # the library's pixel index is y + H * x
+    assert 0 < hit.sum() < hit.size                                                  # some camera rays leave the open box
+    assert np.array_equal(radiance.sum(-1) > 0, hit)                                 # ... and those pixels are black in the radiance image
+    if key == "convergenceFalseColor":                                               # quirk B4: no delta surface, no effect
+        assert np.array_equal(img, radiance)
+        return
+    if unclustered:
+        want = np.where(hit[..., None], np.float32(1.0), np.float32(0.0)) * np.ones(3, np.float32)
+    else:
+        o.build_slices(); o.prepass()
+        sl = o.pixel_to_slice().reshape(W, H).T.astype(np.uint64)
+        if key == "slicesFalseColor":
+            s = sl % (1 << 32)
+            rgbv = np.stack([((s + s * s) % (1 << 32) % 43) / 43.0, ((7 * s + 2 * s * s + 7) % (1 << 32) % 41) / 41.0,
+                             ((23 * s + 5 * s * s + s * s * s + 17) % (1 << 32) % 53) / 53.0], -1).astype(np.float32)
+        else:
+            cl = o.clusters()
+            counts = np.diff(cl["offset"]).astype(np.float32)
+            assert (counts > 0).all()
+            rgbv = (counts[np.minimum(sl, len(counts) - 1).astype(np.int64)] / np.float32(len(start)))[..., None] * np.ones(3, np.float32)
+        want = np.where(hit[..., None], rgbv, np.float32(0.0)).astype(np.float32)
+        assert len(np.unique(sl[hit])) == o.num_slices()[0] > 1
+    assert np.array_equal(img, want)
+
+
+def test_false_colour_refuses_specular_scenes_and_unclustered_slices(pkg, lib, tmp_path):
+    scene = pkg.scenes.chain_scene(16, 16)
+    meshes, flat = _by_material(scene)
+    fp, up = C.POINTER(C.c_float), C.POINTER(C.c_uint32)
+    for xml, needle, specular in ((dict(slicesFalseColor=True, vrlFile="/x.vrl"), "specular surfaces", True),
+                                  (dict(slicesFalseColor=True, localRefinement=False, globalCluster=False, vrlFile="/x.vrl"), "without clustering", False)):
+        p, inst = _instance(lib, **xml)
+        sc = C.c_void_p(lib.alvrl_plugin_scene_new())
+        for v, t, a, m in meshes:
+            lib.alvrl_plugin_scene_add_mesh(sc, v.ctypes.data_as(fp), C.c_uint32(len(v)), t.ctypes.data_as(up), C.c_uint32(len(t)), a.ctypes.data_as(fp), 1)
+            if specular and int(scene["mat_bits"][m]) & pkg.scenes.BSDF_DIELECTRIC:
+                lib.alvrl_plugin_scene_set_mesh_bsdf(sc, 1, None, None, 1, 0, 1)
+        keep = _scene_to_plugin(lib, sc, scene, [])
+        img = np.zeros((16, 16, 3), np.float32)
+        err = C.create_string_buffer(600)
+        rc = lib.alvrl_plugin_render_frame(inst, sc, img.ctypes.data_as(fp), err, 600)
+        assert rc != 0 and needle.encode() in err.value, err.value
+        lib.alvrl_plugin_destroy(inst); lib.alvrl_plugin_scene_free(sc); lib.alvrl_plugin_props_free(p)
+        del keep
