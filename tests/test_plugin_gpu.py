@@ -335,3 +335,11 @@ def test_analytic_shapes_through_the_abi_and_through_the_plugin(pkg, host_lib):
     lib.alvrl_plugin_destroy(inst); lib.alvrl_plugin_scene_free(sc); lib.alvrl_plugin_props_free(p)
     del keep
     assert np.array_equal(img_plugin, img_a)
+
+
+def test_slices_false_colour_through_the_plugin(pkg, orc, tmp_path):
+    """slicesFalseColor through vrl.so on the device: the shim colours every hit pixel by its slice id with the reference's formula
+    (vrlIntegrator.cpp:577-584).  Same body as the CPU test (where the shim runs on the oracle); the slice map is bit-identical
+    between device and oracle, so the expected image is the same."""
+    from test_plugin_oracle_cpu import test_false_colour_debug_outputs as body
+    body(pkg, orc, _plugin(), tmp_path, "slicesFalseColor")
