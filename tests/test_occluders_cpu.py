@@ -258,3 +258,67 @@ def test_pair_level_culling_never_changes_a_decision(host_lib, pkg, orc):
     assert mism == 0
     assert occl > 0.05 * n * 10
     assert plC / plT > 0.7 and boxC / boxT > 0.2
+
+
+def _rotation(rng):
+    q = rng.normal(size=4); q /= np.linalg.norm(q)
+    w, x, y, z = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def _random_box(rng):
+    """an arbitrarily rotated box: 8 corners, 12 outward triangles"""
+    half = rng.uniform(0.04, 0.22, 3)
+    c = rng.uniform(0.2, 0.8, 3)
+    R = _rotation(rng) if rng.random() < 0.7 else np.eye(3)
+    corners = np.array([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)], np.float64) * half
+    v = (corners @ R.T + c).astype(np.float32)
+    # corner index = 4 * (x > 0) + 2 * (y > 0) + (z > 0); faces wound counter-clockwise seen from outside
+    quads = [(0, 1, 3, 2), (4, 6, 7, 5), (0, 4, 5, 1), (2, 3, 7, 6), (0, 2, 6, 4), (1, 5, 7, 3)]
+    t = np.array([f for a, b, cc, d in quads for f in ((a, b, cc), (a, cc, d))], np.uint32)
+    return v, t
+
+
+def _random_quad(rng):
+    o = rng.uniform(0.05, 0.95, 3)
+    R = _rotation(rng)
+    e1, e2 = R[:, 0] * rng.uniform(0.1, 0.5), R[:, 1] * rng.uniform(0.1, 0.5)
+    v = np.array([o, o + e1, o + e1 + e2, o + e2], np.float32)
+    return v, np.array([(0, 1, 2), (0, 2, 3)], np.uint32)
+
+
+def test_random_boxes_and_quads_match_brute_force(host_lib):
+    """hypothesis over scene compositions: up to four arbitrarily rotated boxes (which may overlap each other) and up to four free
+    quads.  Whatever the compiler makes of them -- boxes, general polytopes, planar groups, or nothing (it may decline, then the
+    kernels traverse the tree instead) -- the compiled set answers 6 000 random segments like brute-force triangle tests, outside
+    a 1e-4 grazing margin."""
+    from hypothesis import given, settings, strategies as st
+    stats = {"compiled": 0, "declined": 0}
+
+    @settings(max_examples=120, deadline=None)          # (600 examples: also clean, 32 s)
+    @given(st.integers(0, 2**31 - 1), st.integers(0, 4), st.integers(0, 4))
+    def check(seed, n_boxes, n_quads):
+        if n_boxes + n_quads == 0:
+            return
+        rng = np.random.default_rng(seed)
+        vs, ts, base = [], [], 0
+        for k in range(n_boxes + n_quads):
+            v, t = _random_box(rng) if k < n_boxes else _random_quad(rng)
+            vs.append(v); ts.append(t + base); base += len(v)
+        verts, tris = np.concatenate(vs), np.concatenate(ts).astype(np.uint32)
+        counts, stream = compile_occ(host_lib, verts, tris, num_leaves=max(1, len(tris) // 2))
+        if counts[0] != 1:
+            stats["declined"] += 1
+            return
+        stats["compiled"] += 1
+        o, d, L = random_segments(rng, 6000)
+        tmin = np.zeros_like(L)
+        got = query(host_lib, counts, stream, o, d, tmin, L)
+        want, graze = brute(verts, tris, o, d, tmin, L, margin=1e-4)
+        bad = (got != want) & ~graze
+        assert not bad.any(), (seed, n_boxes, n_quads, int(bad.sum()), o[bad][:2], d[bad][:2], L[bad][:2])
+        assert graze.mean() < 0.02
+    check()
+    assert stats["compiled"] >= 50, stats
