@@ -322,3 +322,48 @@ def test_random_boxes_and_quads_match_brute_force(host_lib):
         assert graze.mean() < 0.02
     check()
     assert stats["compiled"] >= 50, stats
+
+
+def test_pair_level_culling_on_random_scenes(host_lib):
+    """the pair-level culling (side bits of camera segment and VRL decide which boxes and planes a pair's shadow segments still
+    test) on random compositions of rotated boxes and quads: camera segments from random eyes to random points ON the surfaces,
+    random VRLs, some starting on a surface -- culled and unculled queries agree on every shadow segment"""
+    from hypothesis import given, settings, strategies as st
+    tot = {"scenes": 0, "segments": 0, "occluded": 0, "box_culled": 0, "box_tests": 0, "plane_culled": 0, "plane_tests": 0}
+
+    @settings(max_examples=50, deadline=None)
+    @given(st.integers(0, 2**31 - 1), st.integers(0, 4), st.integers(0, 4))
+    def check(seed, n_boxes, n_quads):
+        if n_boxes + n_quads == 0:
+            return
+        rng = np.random.default_rng(seed)
+        vs, ts, base = [], [], 0
+        for k in range(n_boxes + n_quads):
+            v, t = _random_box(rng) if k < n_boxes else _random_quad(rng)
+            vs.append(v); ts.append(t + base); base += len(v)
+        verts, tris = np.concatenate(vs), np.concatenate(ts).astype(np.uint32)
+        counts, (dev, recs) = compile_occ(host_lib, verts, tris, num_leaves=max(1, len(tris) // 2))
+        if counts[0] != 1:
+            return
+        n = 8000
+        v64 = verts.astype(np.float64)
+        t = tris[rng.integers(0, len(tris), n)]
+        bary = rng.dirichlet((1, 1, 1), n)
+        U = (v64[t[:, 0]] * bary[:, :1] + v64[t[:, 1]] * bary[:, 1:2] + v64[t[:, 2]] * bary[:, 2:]).astype(np.float32)
+        E = rng.uniform(-0.3, 1.3, (n, 3)).astype(np.float32)
+        S = rng.uniform(-0.1, 1.1, (n, 3)).astype(np.float32)
+        En = rng.uniform(-0.1, 1.1, (n, 3)).astype(np.float32)
+        S[: n // 10] = U[rng.permutation(n)[: n // 10]]                      # VRLs that start on a surface, as a tracer's do
+        stats = np.zeros(6, np.uint64)
+        ext = float(np.ptp(verts, axis=0).max())
+        host_lib.alvrl_host_pair_cull_check(C.byref(dev), recs.ctypes.data_as(C.c_void_p), E.ctypes.data_as(C.c_void_p), U.ctypes.data_as(C.c_void_p),
+                                            S.ctypes.data_as(C.c_void_p), En.ctypes.data_as(C.c_void_p), C.c_uint32(n), C.c_uint32(6),
+                                            C.c_uint64(seed & 0xFFFF), C.c_float(1e-5 * ext), stats.ctypes.data_as(C.c_void_p))
+        mism, boxC, boxT, plC, plT, occl = (int(x) for x in stats)
+        assert mism == 0, (seed, n_boxes, n_quads, mism)
+        tot["scenes"] += 1; tot["segments"] += 6 * n; tot["occluded"] += occl
+        tot["box_culled"] += boxC; tot["box_tests"] += boxT; tot["plane_culled"] += plC; tot["plane_tests"] += plT
+    check()
+    print(tot)
+    assert tot["scenes"] >= 20 and tot["occluded"] > 0.02 * tot["segments"]
+    assert tot["box_culled"] > 0 and tot["plane_culled"] > 0                 # the culling is exercised, not vacuous
