@@ -12,6 +12,7 @@
 #include "sharding.h"
 #include "hostio.h"
 #include "shapes.h"
+#include "bvh.h"
 #include <algorithm>
 #include <cstring>
 using namespace alvrl;
@@ -90,6 +91,111 @@ int alvrl_host_tessellate(int shape, const float *toWorldOrCenter, float radius,
     *nverts = (uint32_t) (v.size() / 3); *ntris = (uint32_t) (t.size() / 3);
     if (verts) memcpy(verts, v.data(), v.size() * sizeof(float));
     if (tris) memcpy(tris, t.data(), t.size() * sizeof(uint32_t));
+    return 0;
+}
+
+/* bvh.h: the binary threaded BVH and the 4-wide tree collapsed from it.  Structure: preorder, escape indices, leaf ranges that
+ * partition the triangle order, boxes that hold their triangles.  Culling: for every ray segment, each triangle a brute-force
+ * test (Moeller-Trumbore in double) hits must sit in a leaf that a traversal with an exact slab test on the stored (padded)
+ * boxes reaches -- in the stackless binary tree (hit inner -> node + 1, leaf / miss -> escape) and in the 4-wide tree.
+ * stats = {structure error (0 = none), hits, hits missed by the binary tree, hits missed by the 4-wide tree, binary node
+ * visits, 4-wide node visits, binary nodes, 4-wide nodes} */
+int alvrl_host_bvh_check(const float *verts, const uint32_t *tris, uint32_t nt, const float *o, const float *d, const float *tmax,
+                         uint32_t nrays, uint64_t *stats) {
+    for (int i = 0; i < 8; i++) stats[i] = 0;
+    HostBvh bvh;
+    BvhBuilder(verts, tris, nt).build(bvh);
+    std::vector<Bvh4Node> wide;
+    collapse4(bvh, wide);
+    auto asU = [](float f) { uint32_t u; memcpy(&u, &f, 4); return u; };
+    const uint32_t nn = (uint32_t) bvh.nodes.size();
+    stats[6] = nn; stats[7] = wide.size();
+    /* structure */
+    if (bvh.triOrder.size() != nt) { stats[0] = 1; return 0; }
+    { std::vector<uint32_t> seen(nt, 0); for (uint32_t t : bvh.triOrder) { if (t >= nt || seen[t]++) { stats[0] = 2; return 0; } } }
+    std::vector<uint32_t> covered(nt, 0);
+    for (uint32_t k = 0; k < nn; k++) {
+        const BvhNode &n = bvh.nodes[k];
+        const uint32_t esc = asU(n.lo.w), lf = asU(n.hi.w);
+        if (esc <= k || esc > nn) { stats[0] = 3; return 0; }
+        if (lf) {
+            const uint32_t first = lf >> 4, cnt = lf & 15u;
+            if (cnt == 0 || cnt > 4 || first + cnt > nt || esc != k + 1) { stats[0] = 4; return 0; }
+            for (uint32_t i = first; i < first + cnt; i++) {
+                covered[i]++;
+                for (int c = 0; c < 3; c++) {
+                    const float *p = verts + 3 * (size_t) tris[3 * (size_t) bvh.triOrder[i] + c];
+                    if (p[0] < n.lo.x || p[1] < n.lo.y || p[2] < n.lo.z || p[0] > n.hi.x || p[1] > n.hi.y || p[2] > n.hi.z) { stats[0] = 5; return 0; }
+                }
+            }
+        } else {
+            if (k + 1 >= nn) { stats[0] = 6; return 0; }
+            const uint32_t second = asU(bvh.nodes[k + 1].lo.w);            /* the first child's escape = the second child */
+            if (second >= esc) { stats[0] = 7; return 0; }
+            for (uint32_t ch : {k + 1, second}) {                              /* children's boxes inside the parent's */
+                const BvhNode &x = bvh.nodes[ch];
+                if (x.lo.x < n.lo.x || x.lo.y < n.lo.y || x.lo.z < n.lo.z || x.hi.x > n.hi.x || x.hi.y > n.hi.y || x.hi.z > n.hi.z) { stats[0] = 8; return 0; }
+            }
+        }
+    }
+    for (uint32_t i = 0; i < nt; i++) if (covered[i] != 1) { stats[0] = 9; return 0; }
+    /* culling */
+    auto slab = [](const double lo[3], const double hi[3], const double O[3], const double D[3], double tm) {
+        double t0 = 0, t1 = tm;
+        for (int c = 0; c < 3; c++) {
+            if (D[c] == 0) { if (O[c] < lo[c] || O[c] > hi[c]) return false; continue; }
+            double a = (lo[c] - O[c]) / D[c], b = (hi[c] - O[c]) / D[c];
+            if (a > b) std::swap(a, b);
+            t0 = std::max(t0, a); t1 = std::min(t1, b);
+        }
+        return t0 <= t1;
+    };
+    std::vector<uint8_t> vis2(nt), vis4(nt);
+    for (uint32_t r = 0; r < nrays; r++) {
+        const double O[3] = {o[3 * r], o[3 * r + 1], o[3 * r + 2]}, D[3] = {d[3 * r], d[3 * r + 1], d[3 * r + 2]};
+        const double tm = tmax[r];
+        std::fill(vis2.begin(), vis2.end(), 0); std::fill(vis4.begin(), vis4.end(), 0);
+        for (uint32_t k = 0; k < nn;) {                                       /* the stackless walk */
+            const BvhNode &n = bvh.nodes[k];
+            stats[4]++;
+            const double lo[3] = {n.lo.x, n.lo.y, n.lo.z}, hi[3] = {n.hi.x, n.hi.y, n.hi.z};
+            const uint32_t lf = asU(n.hi.w);
+            if (!slab(lo, hi, O, D, tm)) { k = asU(n.lo.w); continue; }
+            if (lf) { for (uint32_t i = lf >> 4; i < (lf >> 4) + (lf & 15u); i++) vis2[i] = 1; k = asU(n.lo.w); }
+            else k++;
+        }
+        std::vector<int> stack;
+        if (!wide.empty()) stack.push_back(0);
+        while (!stack.empty()) {
+            const Bvh4Node &n = wide[stack.back()]; stack.pop_back();
+            stats[5]++;
+            const float *lx = &n.lox.x, *ly = &n.loy.x, *lz = &n.loz.x, *hx = &n.hix.x, *hy = &n.hiy.x, *hz = &n.hiz.x;
+            const int *ch = &n.child.x;
+            for (int k = 0; k < 4; k++) {
+                const double lo[3] = {lx[k], ly[k], lz[k]}, hi[3] = {hx[k], hy[k], hz[k]};
+                if (!(lo[0] <= hi[0])) continue;                               /* unused slot: empty box */
+                if (!slab(lo, hi, O, D, tm)) continue;
+                if (ch[k] >= 0) stack.push_back(ch[k]);
+                else { const uint32_t lf = (uint32_t) ~ch[k]; for (uint32_t i = lf >> 4; i < (lf >> 4) + (lf & 15u); i++) { if (i >= nt) { stats[0] = 10; return 0; } vis4[i] = 1; } }
+            }
+        }
+        for (uint32_t i = 0; i < nt; i++) {                                    /* brute force, in leaf order */
+            const uint32_t t = bvh.triOrder[i];
+            const float *A = verts + 3 * (size_t) tris[3 * (size_t) t], *B = verts + 3 * (size_t) tris[3 * (size_t) t + 1], *Cc = verts + 3 * (size_t) tris[3 * (size_t) t + 2];
+            const double e1[3] = {(double) B[0] - A[0], (double) B[1] - A[1], (double) B[2] - A[2]}, e2[3] = {(double) Cc[0] - A[0], (double) Cc[1] - A[1], (double) Cc[2] - A[2]};
+            const double p[3] = {D[1] * e2[2] - D[2] * e2[1], D[2] * e2[0] - D[0] * e2[2], D[0] * e2[1] - D[1] * e2[0]};
+            const double det = p[0] * e1[0] + p[1] * e1[1] + p[2] * e1[2];
+            if (std::fabs(det) < 1e-14) continue;
+            const double s[3] = {O[0] - A[0], O[1] - A[1], O[2] - A[2]};
+            const double u = (s[0] * p[0] + s[1] * p[1] + s[2] * p[2]) / det;
+            const double q[3] = {s[1] * e1[2] - s[2] * e1[1], s[2] * e1[0] - s[0] * e1[2], s[0] * e1[1] - s[1] * e1[0]};
+            const double v = (D[0] * q[0] + D[1] * q[1] + D[2] * q[2]) / det, tt = (e2[0] * q[0] + e2[1] * q[1] + e2[2] * q[2]) / det;
+            if (u < 0 || v < 0 || u + v > 1 || tt < 0 || tt > tm) continue;
+            stats[1]++;
+            if (!vis2[i]) stats[2]++;
+            if (!vis4[i]) stats[3]++;
+        }
+    }
     return 0;
 }
 
