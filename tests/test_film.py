@@ -49,6 +49,39 @@ def test_oracle_film_gaussian_footprint(orc):
     assert np.allclose(out[7, 8], out[8, 7]) and np.allclose(out[6, 6], out[8, 8])
 
 
+def _numpy_film(frames, radius, eval_fn):
+    """ImageBlock::put for samples at pixel centres + the weight division, written independently: the offsets between a sample and
+    the pixels it reaches are integers, so the pre-rasterised filter (31 entries over the radius, the 32nd zero; rfilter.cpp:37-55,
+    rfilter.h:76-77) is looked up at |k| * 31 / radius only, and the film is a separable correlation of the valid samples with those
+    weights divided by the same correlation of the valid mask (imageblock.h:144-185, bitmap.cpp:1617-1624)"""
+    R = int(np.floor(radius))
+    table = np.array([eval_fn(radius * i / 31.0) for i in range(31)] + [0.0])
+    w = np.array([table[min(int(abs(k) * (31.0 / radius)), 31)] for k in range(-R, R + 1)])
+    n, H, W, _ = frames.shape
+    acc = np.zeros((H + 2 * R, W + 2 * R, 4))
+    for f in frames.astype(np.float64):
+        valid = (np.isfinite(f) & (f >= 0)).all(-1)
+        val = np.where(valid[..., None], np.concatenate([np.nan_to_num(f, nan=0.0, posinf=0.0, neginf=0.0), np.ones((H, W, 1))], -1), 0.0)
+        for dy in range(-R, R + 1):
+            for dx in range(-R, R + 1):
+                acc[R + dy:R + dy + H, R + dx:R + dx + W] += w[dy + R] * w[dx + R] * val
+    inner = acc[R:R + H, R:R + W]
+    return np.where(inner[..., 3:] > 0, inner[..., :3] / np.maximum(inner[..., 3:], 1e-300), 0.0)
+
+
+@pytest.mark.parametrize("filt,param", [(GAUSS, 0.0), (GAUSS, 0.8), (TENT, 0.0)], ids=["gaussian-0.5", "gaussian-0.8", "tent"])
+def test_oracle_film_equals_an_independent_numpy_film(orc, filt, param):
+    fr = _frames(H=23, W=31, n=3, seed=9)
+    if filt == GAUSS:
+        sd = param or 0.5
+        radius, ev = 4 * sd, (lambda x: max(0.0, np.exp(-x * x / (2 * sd * sd)) - np.exp(-(4 * sd) ** 2 / (2 * sd * sd))))   # gaussian.cpp:36-58
+    else:
+        radius, ev = 1.0, (lambda x: max(0.0, 1.0 - abs(x)))                                                                # tent.cpp:34-44
+    want = _numpy_film(fr, radius, ev)
+    got = orc.film(fr, filt, param)
+    assert np.allclose(got, want, rtol=3e-6, atol=1e-7), float(np.abs(got - want).max())
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("filt,param", [(BOX, 0.0), (TENT, 0.0), (GAUSS, 0.0), (GAUSS, 0.8)])
 def test_film_matches_oracle_bit_exact(pkg, orc, filt, param):
