@@ -250,3 +250,50 @@ def test_neighbour_slices_in_local_matrices(pkg, orc):
     assert len(everybody["offset"]) == S + 1 and np.isfinite(everybody["weights"]).all()
     with pytest.raises(Exception):
         run(neighbourCount=0, neighbourWeight=0.5)
+
+
+def test_primary_hits_against_a_textbook_pinhole_and_brute_force(pkg, orc):
+    """camera + closest hit (rows a8 / a10) checked independently of the oracle's code: rays of a textbook pinhole (eye, target,
+    up, horizontal field of view; pixel centres; image y pointing down) instead of the sampleToCamera / cameraToWorld matrices
+    (perspective.cpp:126-175, 367-385), closest hit by Moeller-Trumbore in float64 over all triangles instead of the TriAccel
+    test (triaccel.h:97-145): same triangle, same distance and hit point, for every pixel away from triangle edges"""
+    W, H = 72, 56
+    scene, vrls, params = pkg.scenes.make_config("C1", width=W, height=H, n_vrls=4)
+    eye, target, fov = np.array([0.45, 0.52, -2.2]), np.array([0.5, 0.5, 0.0]), 40.0         # off-centre and further back: some rays miss
+    scene = dict(scene, camera=pkg.scenes.perspective_camera(W, H, origin=eye, target=target, fov=fov))
+    scene["extra_bounds"] = scene["camera"]["origin"].reshape(1, 3)
+    o = orc.Oracle(**params); o.set_scene(scene); o.set_vrls(*vrls)
+    prim, t, p, n = o.primary_hits()
+    prim, t, p = prim.reshape(W, H).T, t.reshape(W, H).T, p.reshape(W, H, 3).transpose(1, 0, 2)      # index y + H * x -> [y][x]
+    fwd = (target - eye) / np.linalg.norm(target - eye)
+    right = np.cross(fwd, np.array([0.0, 1.0, 0.0])); right /= np.linalg.norm(right)          # the viewer's right hand (world -x when looking along +z)
+    upc = np.cross(right, fwd)
+    th = np.tan(np.radians(fov) / 2)
+    xs, ys = (np.arange(W) + 0.5) / W, (np.arange(H) + 0.5) / H
+    d = fwd[None, None, :] + ((2 * xs - 1) * th)[None, :, None] * right[None, None, :] + ((1 - 2 * ys) * th * H / W)[:, None, None] * upc[None, None, :]
+    d /= np.linalg.norm(d, axis=2, keepdims=True)
+    v = scene["verts"].astype(np.float64)
+    best_t = np.full((H, W), np.inf); best = np.full((H, W), -1); edge = np.zeros((H, W), bool)
+    for k, (a, b, c) in enumerate(scene["tris"]):
+        e1, e2 = v[b] - v[a], v[c] - v[a]
+        pv = np.cross(d, e2)
+        det = pv @ e1
+        with np.errstate(divide="ignore", invalid="ignore"):
+            s = eye - v[a]
+            u = (pv @ s) / det
+            q = np.cross(s, e1)
+            w = (d @ q) / det
+            tt = (q @ e2) / det
+        ok = (np.abs(det) > 1e-12) & (u >= 0) & (w >= 0) & (u + w <= 1) & (tt > 0)
+        near_edge = ok & ((u < 1e-4) | (w < 1e-4) | (u + w > 1 - 1e-4))
+        closer = ok & (tt < best_t)
+        edge = np.where(closer, near_edge, edge | (ok & near_edge & (np.abs(tt - best_t) < 1e-6)))
+        best = np.where(closer, k, best); best_t = np.where(closer, tt, best_t)
+    hit = best >= 0
+    assert 0.3 < hit.mean() < 1.0
+    assert np.array_equal(prim != pkg.binding.NO_HIT, hit)
+    clean = hit & ~edge
+    assert clean.sum() > 0.9 * hit.sum()
+    assert np.array_equal(prim[clean], best[clean])
+    assert np.allclose(t[clean], best_t[clean], rtol=2e-5)
+    assert np.allclose(p[clean], (eye + best_t[..., None] * d)[clean], atol=2e-5)
