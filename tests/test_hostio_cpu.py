@@ -197,7 +197,7 @@ def test_file_readers_survive_corrupt_input(pkg, host_lib, tmp_path):
     assert host_lib.alvrl_host_read_vol(str(huge).encode(), _p(h11), _p(one), err, C.c_uint32(256)) == -4 and b"fewer voxels" in err.value
     path = tmp_path / "fuzz.bin"
 
-    @settings(max_examples=300, deadline=None)
+    @settings(max_examples=300, deadline=None, derandomize=True, database=None)
     @given(st.integers(0, len(base)), st.lists(st.tuples(st.integers(0, len(base) - 1), st.integers(0, 255)), max_size=6), st.binary(max_size=80))
     def check(cut, flips, tail):
         b = bytearray(base[:cut])

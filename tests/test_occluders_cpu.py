@@ -297,7 +297,7 @@ def test_random_boxes_and_quads_match_brute_force(host_lib):
     from hypothesis import given, settings, strategies as st
     stats = {"compiled": 0, "declined": 0}
 
-    @settings(max_examples=120, deadline=None)          # (600 examples: also clean, 32 s)
+    @settings(max_examples=120, deadline=None, derandomize=True, database=None)          # (600 examples: also clean, 32 s)
     @given(st.integers(0, 2**31 - 1), st.integers(0, 4), st.integers(0, 4))
     def check(seed, n_boxes, n_quads):
         if n_boxes + n_quads == 0:
@@ -331,7 +331,7 @@ def test_pair_level_culling_on_random_scenes(host_lib):
     from hypothesis import given, settings, strategies as st
     tot = {"scenes": 0, "segments": 0, "occluded": 0, "box_culled": 0, "box_tests": 0, "plane_culled": 0, "plane_tests": 0}
 
-    @settings(max_examples=50, deadline=None)
+    @settings(max_examples=50, deadline=None, derandomize=True, database=None)
     @given(st.integers(0, 2**31 - 1), st.integers(0, 4), st.integers(0, 4))
     def check(seed, n_boxes, n_quads):
         if n_boxes + n_quads == 0:
