@@ -1512,6 +1512,27 @@ int orc_test_phase_eval(int32_t phaseType, float g, const float wi[3], const flo
     for (uint32_t i = 0; i < n; i++) val[i] = med.phaseEval(V3(wi[0], wi[1], wi[2]), V3(wo[3 * i], wo[3 * i + 1], wo[3 * i + 2]));
     return ALVRL_OK;
 }
+/* Medium::sampleDistance(Ray(o, d, 0, itsT), mRec, sampler) of the handle's medium, n times on two uniforms each (the
+ * homogeneous medium draws two, the grid medium one): distance of the sampled point from o (itsT when no interaction was
+ * sampled), success flag, pdfSuccess, pdfFailure, transmittance */
+int orc_test_sample_distance(void *h, const float o[3], const float d[3], float itsT, const float *u, uint32_t n,
+                             float *t, uint8_t *success, float *pdfSuccess, float *pdfFailure, float *transmittance) {
+    Ctx *c = (Ctx *) h;
+    ORC_TRY
+    if (!c->haveMedium) return seterr(ALVRL_ERR_STATE, "set a medium first");
+    const Ray ray(V3(o[0], o[1], o[2]), V3(d[0], d[1], d[2]), 0, itsT);
+    for (uint32_t i = 0; i < n; i++) {
+        TapeSampler smp(u + 2 * (size_t) i, 2, 2, 1);
+        smp.setContext(0, 0, 0);
+        MRec m;
+        const bool ok = sampleDistanceH(c->medium, ray, itsT, &smp, m);
+        success[i] = ok ? 1 : 0;
+        t[i] = ok ? (m.p - ray.o).length() : itsT;
+        pdfSuccess[i] = m.pdfSuccess; pdfFailure[i] = m.pdfFailure;
+        transmittance[3 * i] = m.transmittance[0]; transmittance[3 * i + 1] = m.transmittance[1]; transmittance[3 * i + 2] = m.transmittance[2];
+    }
+    ORC_CATCH
+}
 /* BSDF::sample of one surface model in the local frame (test_chisquare.cpp:398-506): bits = ALVRL_BSDF_* of the material,
  * optics12 as alvrl_set_material_optics; delta[i] = 1 for a discrete component (pdf = its probability) */
 int orc_test_bsdf_sample(uint32_t bits, const float albedo[3], const float *optics12, const float wi[3], const float *u, uint32_t n,
