@@ -799,7 +799,7 @@ int orc_get_primary_ties(void *h, uint8_t *tie) {
 int orc_get_pixel_to_slice(void *h, uint32_t *out) {
     Ctx *c = (Ctx *) h;
     if (!c->haveSlices) return seterr(ALVRL_ERR_STATE, "build_slices first");
-    memcpy(out, c->pixelToSlice.data(), c->pixelToSlice.size() * 4);
+    if (!c->pixelToSlice.empty()) memcpy(out, c->pixelToSlice.data(), c->pixelToSlice.size() * 4);
     return ALVRL_OK;
 }
 int orc_get_num_slices(void *h, uint32_t *ns, uint32_t *nr) {
@@ -808,7 +808,8 @@ int orc_get_num_slices(void *h, uint32_t *ns, uint32_t *nr) {
 int orc_get_rep_pixels(void *h, uint32_t *off, uint32_t *px) {
     Ctx *c = (Ctx *) h;
     if (!c->haveRows) return seterr(ALVRL_ERR_STATE, "sample_slice_mapping first");
-    memcpy(off, c->rowOffset.data(), c->rowOffset.size() * 4); memcpy(px, c->rowPixel.data(), c->rowPixel.size() * 4);
+    if (!c->rowOffset.empty()) memcpy(off, c->rowOffset.data(), c->rowOffset.size() * 4);
+    if (!c->rowPixel.empty()) memcpy(px, c->rowPixel.data(), c->rowPixel.size() * 4);      /* (no rows: every pixel missed) */
     return ALVRL_OK;
 }
 int orc_set_rep_pixels(void *h, const uint32_t *off, const uint32_t *px, uint32_t ns) {
