@@ -297,3 +297,28 @@ def test_host_slices_property_based_vs_oracle(pkg, orc, host_lib):
         compared[0] += 1
     check()
     assert compared[0] >= 150, compared          # most examples are compared in full; the rest hit the reference's error case
+
+
+@pytest.mark.parametrize("rng_mode", [0, 1], ids=["counter", "sfmt"])
+@pytest.mark.parametrize("undersampling", [1.6, 8.0], ids=["shuffled-prefix", "rejection"])
+def test_representative_pixels_are_a_uniform_subset(host_lib, undersampling, rng_mode):
+    """Slice::sampleRepresentativePixels (Preprocessor.cpp:66-121): int(0.5 + n / undersampling) distinct pixels of the slice -- a
+    shuffled prefix when that is at least half of them, rejection sampling otherwise.  Over 3 000 seeds every pixel of a 60-pixel
+    slice is chosen equally often (chi-square), in the counter stream and in the SFMT stream"""
+    from scipy import stats
+    n, seeds = 60, 3000
+    rng = np.random.default_rng(1)
+    pos = rng.random((n, 3), dtype=np.float32); d = (0.1 * rng.random((n, 3))).astype(np.float32)
+    k = int(0.5 + n / undersampling)
+    counts = np.zeros(n)
+    p2s = np.zeros(n, np.uint32); ns = C.c_uint32(); off = np.zeros(2, np.uint32); px = np.zeros(n, np.uint32)
+    for seed in range(seeds):
+        host_lib.alvrl_host_slices(pos.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p), C.c_uint32(n), C.c_uint32(1),
+                                   C.c_float(undersampling), C.c_int(rng_mode), C.c_uint64(seed), p2s.ctypes.data_as(C.c_void_p), C.byref(ns),
+                                   off.ctypes.data_as(C.c_void_p), px.ctypes.data_as(C.c_void_p))
+        assert ns.value == 1 and off[1] == k
+        chosen = px[:k]
+        assert len(np.unique(chosen)) == k and chosen.max() < n
+        counts[chosen] += 1
+    chi2 = ((counts - seeds * k / n) ** 2 / (seeds * k / n * (1 - k / n))).sum()          # hypergeometric marginals: variance p (1 - p)
+    assert stats.chi2.sf(chi2, n - 1) > 1e-3, (chi2, counts.min(), counts.max())
