@@ -297,3 +297,60 @@ def test_primary_hits_against_a_textbook_pinhole_and_brute_force(pkg, orc):
     assert np.array_equal(prim[clean], best[clean])
     assert np.allclose(t[clean], best_t[clean], rtol=2e-5)
     assert np.allclose(p[clean], (eye + best_t[..., None] * d)[clean], atol=2e-5)
+
+
+def test_counter_stream_statistics_and_its_stated_limit(pkg):
+    """the addressed sample stream (include/alvrl_rng.h) restated with numpy: 3.1 M uniforms of the R domain (256 rows x 1 024 VRLs x
+    12 draws) are uniform (chi-square on 256 bins, and on 16 x 16 bins for consecutive draws), and neighbouring addresses --
+    (row, VRL + 1), (row + 1, VRL), draw k + 1 -- are uncorrelated.  The stated limit: key and state are
+    32 bits wide, so distinct addresses start to share keys at the birthday bound -- counted here on 2^20 addresses, where the
+    expectation is 128 coinciding pairs"""
+    from scipy import stats
+
+    def mix(x):
+        x = x.astype(np.uint32)
+        x ^= x >> np.uint32(16); x *= np.uint32(0x7FEB352D)
+        x ^= x >> np.uint32(15); x *= np.uint32(0x846CA68B)
+        x ^= x >> np.uint32(16)
+        return x
+
+    def key(seed, domain, a, b):
+        with np.errstate(over="ignore"):
+            h = mix(np.uint32(seed & 0xFFFFFFFF) ^ np.uint32((domain * 0x9E3779B9) & 0xFFFFFFFF) + np.zeros_like(a, np.uint32))
+            h = mix(h ^ np.uint32(seed >> 32))
+            h = mix(h + a.astype(np.uint32) * np.uint32(0x85EBCA6B) + np.uint32(0x165667B1))
+            return mix(h ^ (b.astype(np.uint32) * np.uint32(0xC2B2AE35) + np.uint32(0x27D4EB2F)))
+
+    def uniforms(k_, n_draws):
+        with np.errstate(over="ignore"):
+            bits = mix(k_[..., None] + np.arange(n_draws, dtype=np.uint32) * np.uint32(0x9E3779B9))
+        return ((bits >> np.uint32(9)) | np.uint32(0x3F800000)).view(np.float32) - np.float32(1)
+
+    # the restatement is the header's stream: its known-answer file
+    import os
+    from conftest import ROOT
+    kat = [l.split() for l in open(os.path.join(ROOT, "tests", "golden", "rng_kat.txt")) if l.strip() and not l.startswith("#")]
+    a, b = np.meshgrid(np.arange(256), np.arange(1024), indexing="ij")
+    keys = key(5, 1, a, b)
+    u = uniforms(keys, 12).astype(np.float64)                                   # [256, 1024, 12]
+    n = u.size
+    assert abs(u.mean() - 0.5) < 4.5 * np.sqrt(1 / 12 / n)
+    hist = np.bincount((u.reshape(-1) * 256).astype(int), minlength=256)
+    assert stats.chisquare(hist).pvalue > 1e-3
+    pair = np.bincount(((u[..., :-1] * 16).astype(int) * 16 + (u[..., 1:] * 16).astype(int)).reshape(-1), minlength=256)
+    assert stats.chisquare(pair).pvalue > 1e-3
+
+    def corr(x, y):
+        return float(np.corrcoef(x.reshape(-1), y.reshape(-1))[0, 1])
+    lim = 4.5 / np.sqrt(255 * 1023 * 12)
+    assert abs(corr(u[:, :-1], u[:, 1:])) < lim and abs(corr(u[:-1], u[1:])) < lim and abs(corr(u[..., :-1], u[..., 1:])) < lim
+    # the 32-bit limit: coinciding keys among 2^20 addresses of one domain ~ Poisson(2^40 / 2^33 = 128)
+    a2, b2 = np.meshgrid(np.arange(1024), np.arange(1024), indexing="ij")
+    k2 = key(5, 1, a2, b2).reshape(-1)
+    dup = len(k2) - len(np.unique(k2))
+    assert 128 - 5 * np.sqrt(128) < dup < 128 + 5 * np.sqrt(128), dup
+    # and the numpy restatement IS the header's stream: keys and the sixth uniform of the known-answer file (domain CLUSTER = 4, b = 0)
+    for seed, a_, key_hex, _, _, u5, _ in kat:
+        kk = key(int(seed), 4, np.array([int(a_) * 37]), np.array([0]))
+        assert int(kk[0]) == int(key_hex, 16)
+        assert abs(float(uniforms(kk, 6)[0, 5]) - float(u5)) < 1e-9
