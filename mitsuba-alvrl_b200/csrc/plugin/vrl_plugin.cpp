@@ -111,7 +111,6 @@ public:
             if (scene->emitters[0].meshIndex >= (scene->emitters[0].onAnalyticShape ? scene->shapes.size() : scene->meshes.size()))
                 mts::LogError("the emitter's shape is not a mesh of the scene");
         }
-        if (m_maxPasses < 0) mts::LogError("maxPasses < 0 (render until cancelled) is not supported by the device path: give a pass count");
         alvrl_params hp = m_p; hp.maxPasses = 1;                              /* the passes are driven from render() below */
         /* the false-colour debug outputs (vrlIntegrator.cpp:199-201) are produced here, from the library's slice map and cluster
          * counts (falseColorPass below); the library itself only ever renders radiance */
@@ -247,12 +246,13 @@ public:
     bool render(mts::Scene *scene) override {
         std::vector<float> rgb;
         const int filter = scene->film ? scene->film->rfilter : ALVRL_FILTER_BOX;
-        const bool useFilm = m_maxPasses > 1 || filter != ALVRL_FILTER_BOX;
+        const bool endless = m_maxPasses < 0;                                /* "while (m_maxPasses < 0 || pass <= m_maxPasses)", 398 */
+        const bool useFilm = endless || m_maxPasses > 1 || filter != ALVRL_FILTER_BOX;
         if (useFilm) chk(alvrl_film_configure(m_h, filter, scene->film ? scene->film->rfilterParam : 0.0f));
         m_cancelled = false;
         double prepassCpu = 0, prepassWall = 0, renderCpu = 0, renderWall = 0;     /* cumulative, as integrator.cpp:394-430 */
         int pass = 1;
-        for (; pass <= m_maxPasses && !m_cancelled; pass++) {               /* cancel() takes effect between passes */
+        for (; (endless || pass <= m_maxPasses) && !m_cancelled; pass++) {  /* cancel() takes effect between passes */
             const double w0 = wallSeconds(), c0 = cpuSeconds();
             if (!prepass(scene)) return false;
             const double w1 = wallSeconds(), c1 = cpuSeconds();
@@ -260,13 +260,19 @@ public:
             /* the frame alvrl_render left on the device; a false-colour pass was made here, on the host */
             if (useFilm) chk(alvrl_film_put(m_h, (m_p.numVrlFalseColor || m_p.slicesFalseColor) ? rgb.data() : nullptr));
             prepassWall += w1 - w0; prepassCpu += c1 - c0; renderWall += wallSeconds() - w1; renderCpu += cpuSeconds() - c1;
+            if (endless && m_dumpPasses && scene->film) {                     /* without a pass count every pass is dumped, 428-430 */
+                std::vector<float> sofar(rgb.size());
+                chk(alvrl_film_develop(m_h, sofar.data()));
+                scene->film->dumpPass(passFileName(scene->destinationFile, pass, prepassCpu, prepassWall, renderCpu, renderWall), sofar.data(),
+                                      scene->sensor.width, scene->sensor.height);
+            }
         }
         pass--;
         if (useFilm) chk(alvrl_film_develop(m_h, rgb.data()));
         if (scene->film) scene->film->setImage(rgb.data(), scene->sensor.width, scene->sensor.height);
         /* dumpPasses: with a pass count only the last pass is dumped (integrator.cpp:436-438), under a name that carries the
          * cumulative prepass / render times and, from passFileSuffix (vrlIntegrator.cpp:357-364), the two StatsCounters */
-        if (m_dumpPasses && scene->film && pass >= 1)
+        if (!endless && m_dumpPasses && scene->film && pass >= 1)
             scene->film->dumpPass(passFileName(scene->destinationFile, pass, prepassCpu, prepassWall, renderCpu, renderWall), rgb.data(),
                                   scene->sensor.width, scene->sensor.height);
         return true;
@@ -423,6 +429,31 @@ int alvrl_plugin_render_frame_dump(void *inst, void *scene, const char *destinat
         strncpy(passFile, film.name.c_str(), passFileLen - 1); passFile[passFileLen - 1] = 0;
         if (!film.name.empty() && memcmp(film.dumped.data(), rgbOut, film.dumped.size() * sizeof(float)) != 0) { strncpy(err, "the dumped pass is not the developed film", errLen - 1); return -2; }
         return 0;
+    } catch (const std::exception &e) { sc->film = nullptr; strncpy(err, e.what(), errLen - 1); err[errLen - 1] = 0; return -1; }
+}
+/* maxPasses < 0: render until cancelled.  The film of this hook cancels the integrator from inside the cancelAfter-th pass dump
+ * (as a GUI thread would between passes); names receives the dumped pass files, one per line */
+int alvrl_plugin_render_until_cancelled(void *inst, void *scene, const char *destinationFile, int cancelAfter, float *rgbOut, char *names, int namesLen,
+                                        char *err, int errLen) {
+    struct CancellingFilm : mts::Film {
+        float *dst; mts::Integrator *it; int after, dumps = 0; std::string names; std::vector<float> last;
+        CancellingFilm(float *d, mts::Integrator *i, int a) : dst(d), it(i), after(a) {}
+        void setImage(const float *rgb, uint32_t w, uint32_t h) override { memcpy(dst, rgb, (size_t) w * h * 3 * sizeof(float)); }
+        void dumpPass(const std::string &f, const float *rgb, uint32_t w, uint32_t h) override {
+            names += f + "\n"; last.assign(rgb, rgb + (size_t) w * h * 3);
+            if (++dumps >= after) it->cancel();
+        }
+    };
+    mts::Scene *sc = static_cast<mts::Scene *>(scene);
+    mts::Integrator *it = static_cast<vrlIntegrator *>(inst);
+    CancellingFilm film(rgbOut, it, cancelAfter);
+    try {
+        sc->film = &film; sc->destinationFile = destinationFile;
+        it->preprocess(sc); it->render(sc);
+        sc->film = nullptr;
+        strncpy(names, film.names.c_str(), namesLen - 1); names[namesLen - 1] = 0;
+        if (film.last.empty() || memcmp(film.last.data(), rgbOut, film.last.size() * sizeof(float)) != 0) { strncpy(err, "the last dumped pass is not the final film", errLen - 1); return -2; }
+        return film.dumps;
     } catch (const std::exception &e) { sc->film = nullptr; strncpy(err, e.what(), errLen - 1); err[errLen - 1] = 0; return -1; }
 }
 int alvrl_plugin_unqueried(void *props) { return (int) static_cast<mts::Properties *>(props)->getUnqueried().size(); }

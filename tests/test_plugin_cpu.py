@@ -81,7 +81,7 @@ def test_unknown_attribute_is_left_unqueried(plugin, pkg):
 def test_preprocess_checks_the_scene_before_it_touches_the_device(plugin):
     """what preprocess() refuses is decided on the host (no CUDA device needed): a VRL file wants exactly one medium
     (vrlIntegrator.cpp:244-248); without a file the VRLs are traced in every prepass (276-280), which on the device needs one
-    medium and one area emitter on a mesh; maxPasses < 0 ("until cancelled", integrator.cpp:398) is refused"""
+    medium and one area emitter on a mesh"""
     import numpy as np
     plugin.alvrl_plugin_scene_new.restype = C.c_void_p
     fp = C.POINTER(C.c_float)
@@ -119,8 +119,6 @@ def test_preprocess_checks_the_scene_before_it_touches_the_device(plugin):
         plugin.alvrl_plugin_scene_add_area_emitter(sc, C.c_uint32(4), one.ctypes.data_as(fp))
     rc, err = frame(medium_and_dangling_emitter)
     assert rc != 0 and "not a mesh" in err
-    rc, err = frame(medium, vrlFile="/tmp/some.vrl", maxPasses=-1)
-    assert rc != 0 and "maxPasses" in err
 
     def medium_and_emitter_on_a_missing_shape(sc):       # analytic shapes (mts::AnalyticShapeView) are counted separately
         medium(sc)

@@ -282,3 +282,35 @@ def test_false_colour_refuses_specular_scenes_and_unclustered_slices(pkg, lib, t
         assert rc != 0 and needle.encode() in err.value, err.value
         lib.alvrl_plugin_destroy(inst); lib.alvrl_plugin_scene_free(sc); lib.alvrl_plugin_props_free(p)
         del keep
+
+
+def test_render_until_cancelled_dumps_every_pass(pkg, orc, lib, tmp_path):
+    """maxPasses < 0 (integrator.cpp:398, 428-430): passes run until cancel(); with dumpPasses every pass is dumped.  The film of the
+    test hook cancels from inside the third dump, as a GUI thread would between passes: three passes, three pass files numbered
+    001..003, and the final film is the film of the third dump = three passes accumulated"""
+    import re
+    scene, vrls, params = pkg.scenes.make_config("C1", width=20, height=16, n_vrls=30)
+    start, end, power, pc = vrls
+    path = str(tmp_path / "set.vrl")
+    pkg.scenes.write_vrl_file(path, start, end, power)
+    meshes, flat = _by_material(scene)
+    xml = dict(params, targetNumSlices=4, seed=7, vrlFile=path, maxPasses=-1, dumpPasses=True)
+    p, inst = _instance(lib, **xml)
+    sc = C.c_void_p(lib.alvrl_plugin_scene_new())
+    keep = _scene_to_plugin(lib, sc, scene, meshes)
+    img = np.zeros((16, 20, 3), np.float32)
+    names, err = C.create_string_buffer(4000), C.create_string_buffer(600)
+    rc = lib.alvrl_plugin_render_until_cancelled(inst, sc, b"/out/img", 3, img.ctypes.data_as(C.POINTER(C.c_float)), names, 4000, err, 600)
+    assert rc == 3, err.value
+    lib.alvrl_plugin_destroy(inst); lib.alvrl_plugin_scene_free(sc); lib.alvrl_plugin_props_free(p)
+    del keep
+    files = names.value.decode().split()
+    assert [re.match(r"/out/img_pass(\d{3})_", f).group(1) for f in files] == ["001", "002", "003"]
+    o = orc.Oracle(**{k: v for k, v in xml.items() if k not in ("vrlFile", "maxPasses", "dumpPasses")})
+    o.set_scene(flat); o.set_vrls(start, end, power, 0); o.build_slices()
+    frames = []
+    for k in range(3):
+        if k:
+            o.set_seed(7 + k)
+        o.prepass(); frames.append(o.render())
+    assert np.array_equal(img, orc.film(np.stack(frames), 0, 0.0))
