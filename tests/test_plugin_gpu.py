@@ -276,70 +276,3 @@ def test_set_seed_equals_a_fresh_handle(pkg):
     ca, cb = a.clusters(), b.clusters()
     assert np.array_equal(ca["offset"], cb["offset"]) and np.array_equal(ca["vrls"], cb["vrls"])
 
-
-def test_analytic_shapes_through_the_abi_and_through_the_plugin(pkg, host_lib):
-    """a `rectangle` (the ceiling light) and a `sphere` handed over as triangles.  alvrl_add_rectangle /
-    alvrl_add_sphere == the same triangles appended by hand (hits, traced VRLs, frame bit-identical), and the frame through
-    vrl.so with mts::AnalyticShapeView shapes and the emitter on the rectangle == the frame of the same calls on the ABI."""
-    from test_shapes_cpu import BALL_CENTER, BALL_RADIUS, BALL_STEPS, LIGHT_TO_WORLD, shapes_scene, with_tessellated_shapes
-    lib = _plugin()
-    scene, light_mat, ball_mat, rad = shapes_scene(pkg)
-    meshes, flat = _by_material(scene)                   # materials without triangles (the two shapes') drop out: renumber
-    n_mesh = len(meshes)
-    flat["albedo"] = np.concatenate([flat["albedo"], scene["albedo"][[light_mat, ball_mat]]]).astype(np.float32)
-    flat["mat_bits"] = np.ones(n_mesh + 2, np.uint32)
-    xml = dict(volVolSamples=2, volSurfSamples=2, targetNumSlices=8, seed=5, vrlTargetNum=300, sphereTessellation=BALL_STEPS)
-    direct = {k: v for k, v in xml.items() if k != "sphereTessellation"}
-
-    def frame(g, em):
-        g.set_area_emitter(em, rad)
-        g.build_slices(); g.trace_vrls(); g.prepass()
-        return g.primary_hits()[0], g.get_vrls()[0], g.render()
-
-    # --- the ABI: shapes added by the library ---
-    a = pkg.integrator(0, **direct)
-    a.set_scene(flat)
-    first = a.add_rectangle(LIGHT_TO_WORLD, n_mesh)
-    sfirst, scount = a.add_sphere(BALL_CENTER, BALL_RADIUS, n_mesh + 1, theta_steps=BALL_STEPS)
-    assert first == len(flat["tris"]) and sfirst == first + 2 and scount == 4 * BALL_STEPS * (BALL_STEPS - 2)
-    prim_a, vrl_a, img_a = frame(a, np.arange(first, first + 2, dtype=np.uint32))
-    # --- the same triangles appended by hand ---
-    full, em = with_tessellated_shapes(host_lib, flat, n_mesh, n_mesh + 1)
-    b = pkg.integrator(0, **direct)
-    b.set_scene(full)
-    prim_b, vrl_b, img_b = frame(b, em)
-    assert np.array_equal(prim_a, prim_b) and np.array_equal(vrl_a, vrl_b) and np.array_equal(img_a, img_b)
-    assert img_a.max() > 0 and (prim_a[prim_a != pkg.binding.NO_HIT] >= sfirst).sum() > 3          # the ball is in the picture
-
-    # --- through vrl.so ---
-    p = C.c_void_p(lib.alvrl_plugin_props_new())
-    for k, v in xml.items():
-        lib.alvrl_plugin_props_set_int(p, k.encode(), v)
-    inst = C.c_void_p()
-    err = C.create_string_buffer(1024)
-    assert lib.alvrl_plugin_create(p, C.byref(inst), err, 1024) == 0, err.value
-    assert lib.alvrl_plugin_unqueried(p) == 0
-    sc = C.c_void_p(lib.alvrl_plugin_scene_new())
-    keep = _scene_to_plugin(lib, sc, scene, meshes)
-    fp = C.POINTER(C.c_float)
-    m16 = np.ascontiguousarray(LIGHT_TO_WORLD, np.float32).reshape(16)
-    la, ba = np.ascontiguousarray(scene["albedo"][light_mat], np.float32), np.ascontiguousarray(scene["albedo"][ball_mat], np.float32)
-    cen, r = np.ascontiguousarray(BALL_CENTER, np.float32), np.ascontiguousarray(rad, np.float32)
-    lib.alvrl_plugin_scene_add_rectangle(sc, m16.ctypes.data_as(fp), 0, la.ctypes.data_as(fp))
-    lib.alvrl_plugin_scene_add_sphere(sc, cen.ctypes.data_as(fp), C.c_float(BALL_RADIUS), 0, ba.ctypes.data_as(fp))
-    lib.alvrl_plugin_scene_add_area_emitter_on_shape(sc, C.c_uint32(0), r.ctypes.data_as(fp))
-    H, W = scene["camera"]["height"], scene["camera"]["width"]
-    img_plugin = np.zeros((H, W, 3), np.float32)
-    rc = lib.alvrl_plugin_render_frame(inst, sc, img_plugin.ctypes.data_as(fp), err, 1024)
-    assert rc == 0, err.value
-    lib.alvrl_plugin_destroy(inst); lib.alvrl_plugin_scene_free(sc); lib.alvrl_plugin_props_free(p)
-    del keep
-    assert np.array_equal(img_plugin, img_a)
-
-
-def test_slices_false_colour_through_the_plugin(pkg, orc, tmp_path):
-    """slicesFalseColor through vrl.so on the device: the shim colours every hit pixel by its slice id with the reference's formula
-    (vrlIntegrator.cpp:577-584).  Same body as the CPU test (where the shim runs on the oracle); the slice map is bit-identical
-    between device and oracle, so the expected image is the same."""
-    from test_plugin_oracle_cpu import test_false_colour_debug_outputs as body
-    body(pkg, orc, _plugin(), tmp_path, "slicesFalseColor")
