@@ -10,7 +10,8 @@
  *   - visibility: scenes with <= 32 BVH leaves keep leaf boxes + triangles in shared memory and answer a shadow ray
  *     with a flat, warp-uniform sweep over the leaf boxes (broadcast LDS, no inner nodes) followed by triangle tests
  *     of the entered leaves only; larger scenes use the per-lane stackless traversal of dev_common.cuh.
- * Agreement with the strict flavour / the oracle: ~1e-6 relative per sample, bounded by the tests at 1e-3 per R entry.
+ * Agreement with the strict flavour / the oracle: median 1.6e-7 relative per R entry; tests/test_c2_parity_gpu.py holds it to 1e-4
+ * per entry on C2 itself, with a stated and asserted fraction of outliers (1.5e-4 of the entries, oracle-flagged grazing ties apart).
  */
 #pragma once
 #include "occ_query.h"
