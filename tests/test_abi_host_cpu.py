@@ -255,28 +255,28 @@ def test_host_slices_property_based_vs_oracle(pkg, orc, host_lib):
     oracles = {}
     compared = [0, 0]
 
-    def oracle(W, H, target):
-        key = (W, H, target)
+    def oracle(W, H, target, undersampling):
+        key = (W, H, target, undersampling)
         if key not in oracles:
-            scene, vrls, params = small_case(pkg, "C1", W, H, 4, targetNumSlices=target, seed=5)
+            scene, vrls, params = small_case(pkg, "C1", W, H, 4, targetNumSlices=target, seed=5, targetPixelUndersampling=undersampling)
             oracles[key] = setup(orc.Oracle(**params), scene, vrls)
         return oracles[key]
 
     @settings(max_examples=400, deadline=None, derandomize=True, database=None)
     @given(st.integers(2, 14), st.integers(1, 9), st.sampled_from([1, 2, 5, 16, 40]), st.integers(0, 2**31 - 1), st.sampled_from([3, 5, 17, 101, 1009]),
-           st.floats(0.0, 0.6))
-    def check(W, H, target, seed, lattice, miss_frac):
+           st.floats(0.0, 0.6), st.sampled_from([0.7, 1.0, 1.6, 3.0, 64.0]))       # all pixels / shuffled prefix / rejection / "at least two"
+    def check(W, H, target, seed, lattice, miss_frac, undersampling):
         n = W * H
         rng = np.random.default_rng(seed)
         pos = (rng.integers(0, lattice, (n, 3)) / np.float32(lattice)).astype(np.float32)
         d = (rng.integers(0, lattice, (n, 3)) / np.float32(lattice) * 0.3).astype(np.float32)
         miss = rng.random(n) < miss_frac
         pos[miss] = np.nan; d[miss] = np.nan
-        o = oracle(W, H, target)
+        o = oracle(W, H, target, undersampling)
         p2s = np.zeros(n, np.uint32); ns = C.c_uint32()
         off = np.zeros(target + 1, np.uint32); px = np.zeros(n, np.uint32)
         host_lib.alvrl_host_slices(pos.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p), C.c_uint32(n), C.c_uint32(target),
-                                   C.c_float(64.0), C.c_int(0), C.c_uint64(5), p2s.ctypes.data_as(C.c_void_p), C.byref(ns),
+                                   C.c_float(undersampling), C.c_int(0), C.c_uint64(5), p2s.ctypes.data_as(C.c_void_p), C.byref(ns),
                                    off.ctypes.data_as(C.c_void_p), px.ctypes.data_as(C.c_void_p))
         assert np.array_equal(p2s == 0xFFFFFFFF, miss) and (p2s[~miss] < ns.value).all()           # every hit pixel has a slice
         try:
