@@ -322,3 +322,55 @@ def test_representative_pixels_are_a_uniform_subset(host_lib, undersampling, rng
         counts[chosen] += 1
     chi2 = ((counts - seeds * k / n) ** 2 / (seeds * k / n * (1 - k / n))).sum()          # hypergeometric marginals: variance p (1 - p)
     assert stats.chi2.sf(chi2, n - 1) > 1e-3, (chi2, counts.min(), counts.max())
+
+
+def test_hoare_partition_is_the_pairing_of_misplaced_records():
+    """The claim the device slice builder rests on (csrc/slices_dev.cu, header): the outcome of the reference's Hoare loop
+    (Preprocessor.cpp:1368-1393, with its `|| i == hi` / `|| j == lo` sentinels) is a pure function of the flags L[p] = isLarger --
+    with nS records not larger the left part becomes [lo, lo + nS), records already on their side stay, and the t-th misplaced
+    larger record from the left swaps with the t-th misplaced not-larger record from the right.  Checked here against the
+    sequential loop on 20 000 random flag vectors (tie-heavy, skewed, tiny); the degenerate vectors -- all records on one side,
+    which the device hands back to the host loop -- are where the two differ, and only there."""
+    rng = np.random.default_rng(17)
+
+    def hoare(flags):
+        idx = list(range(len(flags)))
+        lo, hi = 0, len(flags) - 1
+        i, j = lo - 1, hi + 1
+        while True:
+            while True:
+                i += 1
+                if flags[idx[i]] or i == hi:
+                    break
+            while True:
+                j -= 1
+                if (not flags[idx[j]]) or j == lo:
+                    break
+            if i >= j:
+                break
+            idx[i], idx[j] = idx[j], idx[i]
+        return idx, j + 1
+
+    def pairing(flags):
+        f = np.asarray(flags, bool)
+        n_s = int((~f).sum())
+        idx = np.arange(len(f))
+        left_wrong = np.flatnonzero(f[:n_s])                         # larger records sitting in the left part, from the left
+        right_wrong = n_s + np.flatnonzero(~f[n_s:])                 # not-larger records sitting in the right part ...
+        right_wrong = right_wrong[::-1]                              # ... from the right
+        assert len(left_wrong) == len(right_wrong)
+        idx[left_wrong], idx[right_wrong] = right_wrong.copy(), left_wrong.copy()
+        return list(idx), n_s
+
+    degenerate = agree = 0
+    for _ in range(20000):
+        n = int(rng.integers(2, 40))
+        f = rng.random(n) < rng.choice([0.05, 0.3, 0.5, 0.7, 0.95])
+        a, b = hoare(list(f)), pairing(f)
+        if f.all() or not f.any():
+            degenerate += 1                                          # the sentinels decide: the loop leaves the order alone and cuts after the
+            assert a[0] == list(range(n)) and a[1] == (1 if f.all() else n)      # first record (all larger) or after the last one (none larger:
+            continue                                                 # an empty right child, which the reference's SliceNode refuses, 1306-1308)
+        assert a == b, (f, a, b)
+        agree += 1
+    assert agree > 15000 and degenerate > 100
